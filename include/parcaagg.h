@@ -1,0 +1,198 @@
+/*
+ * parcaagg.h — C ABI of libparcaagg: the B200-native replacement for parca-agent's
+ * per-interval sample → Arrow (v2 schema) aggregation path.
+ *
+ * Drop-in boundary (reference file:line are relative to parca-dev/parca-agent):
+ *   - reporter.Reporter as implemented by ParcaReporter, reporter/parca_reporter.go:56
+ *     (ReportTraceEvent :219, reportTraceEventV2 :332, writeSampleV2 :368, appendLocationV2 :418,
+ *      labelsForTID :568, buildSampleRecordV2 :1742, IPC serialisation :1779-1790 / :1847-1860)
+ *   - the Arrow builders in reporter/arrow_v2.go (SampleWriterV2 :500-682,
+ *     StacktraceDictBuilderV2 :228-497, FunctionDictBuilderV2 :163-218) and the run-end
+ *     wrappers in reporter/arrow.go:14-207.
+ *
+ * A Go (cgo) shim implementing reporter.Reporter binds exactly these entry points; see
+ * INTEGRATION.md. Plain pointers and sizes only; no C++/torch types cross this boundary.
+ * Every function returns 0 on success or a negative PA_E* code; pa_agg_last_error() gives text.
+ * No exception or abort crosses the boundary. All multi-byte fields are little-endian.
+ */
+#ifndef PARCAAGG_H
+#define PARCAAGG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PA_ABI_VERSION 1u
+
+/* ---- error codes -------------------------------------------------------------------------- */
+#define PA_OK 0
+#define PA_EINVAL (-22)   /* bad argument / unknown id */
+#define PA_ENOMEM (-12)   /* host or device allocation failed */
+#define PA_ENOSPC (-28)   /* ring full (submit) — caller must flush */
+#define PA_ENODEV (-19)   /* no usable CUDA device */
+#define PA_EIO (-5)       /* CUDA runtime failure; see pa_agg_last_error */
+#define PA_ERANGE (-34)   /* batch exceeds Arrow int32 limits (reporter/arrow_v2.go:233-234) */
+
+/* ---- sample kinds: one output row each; replaces the Origin switch of
+ *      reportTraceEventV2 (reporter/parca_reporter.go:338-363). The shim expands a
+ *      TraceOriginMemory event into up to four rows (:343-360). ------------------------------ */
+enum {
+  PA_KIND_CPU = 0,          /* TraceOriginSampling :340  value=1      */
+  PA_KIND_OFFCPU = 1,       /* TraceOriginOffCPU   :342  value=OffTime */
+  PA_KIND_CUDA = 2,         /* TraceOriginCuda     :362  value=OffTime */
+  PA_KIND_MEM_INUSE_OBJECTS = 3, /* :351 */
+  PA_KIND_MEM_INUSE_SPACE = 4,   /* :354 */
+  PA_KIND_MEM_ALLOC_OBJECTS = 5, /* :357 */
+  PA_KIND_MEM_ALLOC_SPACE = 6,   /* :358 */
+  PA_KIND_COUNT = 7
+};
+
+/* ---- frame kinds: which branch of appendLocationV2 (reporter/parca_reporter.go:418-555)
+ *      resolves the frame. The frame-type *string* (libpf.FrameType.String(), an un-vendored
+ *      dependency) is supplied by the shim as a string id. ----------------------------------- */
+enum {
+  PA_FRAME_NATIVE = 0,   /* :449-476 */
+  PA_FRAME_KERNEL = 1,   /* :478-514 */
+  PA_FRAME_ABORT = 2,    /* :432-446 */
+  PA_FRAME_OOMPROF = 3,  /* :516-520 */
+  PA_FRAME_INTERP = 4    /* :522-551 (python, ruby, jvm, cuda, ...) */
+};
+#define PA_FRAME_F_MAPPING_FILE 0x1u /* frame.Mapping.Valid() && m.File != {} (:456-462) */
+#define PA_FRAME_F_EXEC_KNOWN 0x2u   /* r.executables.Get(FileID) hit (:460, :490) */
+
+#define PA_HASH_PROVIDED 0u /* trace.Hash arrives in the header — the reference's behaviour (:394-395) */
+#define PA_HASH_XXH64X2 1u  /* hi=XXH64(frame ids LE, seed 0), lo=XXH64(same, seed 0x9E3779B97F4A7C15) on the GPU */
+#define PA_XXH_SEED_LO 0x9E3779B97F4A7C15ull
+
+#define PA_LABEL_DISABLE_CPU 0x1u         /* --metadata-disable-cpu-label (flags/flags.go:317) */
+#define PA_LABEL_DISABLE_THREAD_ID 0x2u   /* --metadata-disable-thread-id-label (:318) */
+#define PA_LABEL_DISABLE_THREAD_COMM 0x4u /* --metadata-disable-thread-comm-label (:319) */
+
+#define PA_NO_STRING 0xFFFFFFFFu /* "no value"; string id 0 is always the empty string "" */
+
+/* One sample = one (trace, meta) pair handed to ReportTraceEvent (:219): 64 bytes. */
+typedef struct pa_sample_hdr {
+  uint64_t hash_hi;      /* trace.Hash (libpf.TraceHash) — ignored in PA_HASH_XXH64X2 mode */
+  uint64_t hash_lo;
+  int64_t timestamp_ns;  /* meta.Timestamp (:397) */
+  int64_t value;         /* meta.OffTime / memory value; ignored for PA_KIND_CPU (value=1) */
+  uint32_t pid;          /* meta.PID — shard key on >1 GPU */
+  uint32_t tid;          /* meta.TID → label thread_id (:621) */
+  uint32_t comm_sid;     /* string id of meta.Comm → label thread_name (:624); 0 (= "") drops it */
+  uint32_t labelset_id;  /* per-PID cached labels (content of the labels LRU, :569) */
+  uint64_t frame_off;    /* index of this sample's first frame id in the batch frame stream;
+                            filled by pa_agg_submit / by the producer after pa_agg_acquire */
+  uint32_t cpu;          /* meta.CPU → label cpu (:618) */
+  uint16_t nframes;      /* len(trace.Frames) */
+  uint8_t kind;          /* PA_KIND_* */
+  uint8_t flags;         /* reserved, 0 */
+} pa_sample_hdr;
+
+/* One distinct libpf.Frame value (the dedup key of appendLocationV2, :421): 56 bytes.
+ * frame ids are dense: the i-th registered frame has id i. The shim guarantees
+ * frame-id equality == libpf.Frame value equality (it interns unique.Handle → id). */
+typedef struct pa_frame_desc {
+  uint8_t kind;                /* PA_FRAME_* */
+  uint8_t flags;               /* PA_FRAME_F_* */
+  uint16_t reserved0;
+  uint32_t type_name_sid;      /* frame.Type.String() */
+  uint64_t address_or_lineno;  /* frame.AddressOrLineno (:429) */
+  uint32_t function_name_sid;  /* frame.FunctionName ("" = 0) */
+  uint32_t source_file_sid;    /* frame.SourceFile */
+  uint32_t source_line;        /* frame.SourceLine */
+  uint32_t exec_file_name_sid; /* execInfo.FileName when PA_FRAME_F_EXEC_KNOWN */
+  uint32_t exec_build_id_sid;  /* execInfo.BuildID ("" → FileID hex, :467-471) */
+  uint32_t reserved1;
+  uint64_t file_id_hi;         /* mf.FileID */
+  uint64_t file_id_lo;
+} pa_frame_desc;
+
+typedef struct pa_label_pair {
+  uint32_t name_sid;
+  uint32_t value_sid;
+} pa_label_pair;
+
+typedef struct pa_agg_config {
+  uint32_t abi_version;        /* PA_ABI_VERSION */
+  int32_t device;              /* CUDA device ordinal */
+  uint32_t hash_mode;          /* PA_HASH_* */
+  uint32_t label_flags;        /* PA_LABEL_DISABLE_* */
+  uint32_t samples_per_second; /* --profiling-cpu-sampling-frequency (period = 1e9/this, :340) */
+  uint32_t n_external_labels;  /* --metadata-external-labels → LabelAll at flush (:1760-1764) */
+  const pa_label_pair* external_labels; /* string ids must be registered before the first flush */
+  uint64_t max_samples;        /* ring capacity in rows (per buffer; two buffers are kept) */
+  uint64_t max_frames;         /* ring capacity in frame ids (per buffer) */
+  uint32_t chunk_samples;      /* H2D/compute overlap granularity; 0 = default */
+  uint32_t reserved;
+} pa_agg_config;
+
+/* Result of one flush; memory is library-owned (pinned host) until pa_agg_release. */
+typedef struct pa_agg_result {
+  const uint8_t* ipc;        /* uncompressed Arrow IPC stream == offline-mode V2 bytes (:1779-1790) */
+  uint64_t ipc_len;
+  uint64_t n_rows;           /* record.NumRows(); 0 ⇒ ipc==NULL (reference skips the send, :1842-1845) */
+  uint64_t n_unique_stacks;  /* StacktraceDictBuilderV2.UniqueStacktraces() (arrow_v2.go:338) */
+  uint64_t n_locations;      /* len(LocationIndex) */
+  uint64_t n_functions;      /* funcDict.Len() */
+  uint64_t n_location_indices;
+  uint32_t gpu_launches;     /* kernels launched for this flush */
+  uint32_t reserved;
+  double h2d_ms, gpu_ms, d2h_ms, host_ms; /* stage timings of this flush */
+} pa_agg_result;
+
+typedef struct pa_agg pa_agg; /* opaque */
+
+/* lifecycle — reporter.New (:836) / Stop (:802) */
+int pa_agg_create(const pa_agg_config* cfg, pa_agg** out);
+void pa_agg_destroy(pa_agg* a);
+const char* pa_agg_last_error(const pa_agg* a);
+uint32_t pa_agg_abi_version(void);
+
+/* dictionaries (host → library, append-only, ids dense in registration order).
+ * strings: n strings as offsets[n+1] into bytes; *first_id receives the id of the first one. */
+int pa_agg_register_strings(pa_agg* a, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, uint32_t* first_id);
+int pa_agg_register_frames(pa_agg* a, const pa_frame_desc* descs, uint32_t n, uint64_t* first_frame_id);
+/* labelsets: n sets, set i = pairs[offsets[i]..offsets[i+1]) sorted by name (labels.Labels order). */
+int pa_agg_register_labelsets(pa_agg* a, const pa_label_pair* pairs, const uint32_t* offsets, uint32_t n, uint32_t* first_id);
+
+/* ingest — ReportTraceEvent (:219). Thread-safe; row order == acquisition order (the mutex at :335).
+ * acquire reserves space for n_rows headers / n_frames frame ids in the pinned ring and returns
+ * where to write them (no Go pointers are retained: the ring is C-owned). *frame_base is the
+ * frame_off of the first reserved frame id. commit publishes the rows. */
+int pa_agg_acquire(pa_agg* a, uint64_t n_rows, uint64_t n_frames, pa_sample_hdr** hdrs, uint64_t** frames, uint64_t* frame_base);
+int pa_agg_commit(pa_agg* a, uint64_t n_rows);
+/* copying convenience: frames of row i are frames[sum(nframes[0..i))..]; frame_off is filled in. */
+int pa_agg_submit(pa_agg* a, const pa_sample_hdr* hdrs, const uint64_t* frames, uint64_t n_rows);
+
+/* flush — buildSampleRecordV2 (:1742) + IPC (:1779-1790): swap the ring buffer under the ingest
+ * lock, run the GPU pipeline on the detached buffer, return the finished IPC stream. */
+int pa_agg_flush(pa_agg* a, pa_agg_result* out);
+void pa_agg_release(pa_agg* a, pa_agg_result* res);
+
+/* bench / profiling hooks: the same pipeline split in its three stages.
+ * stage = swap + H2D only; process = kernels only on the HBM-resident batch (repeatable);
+ * collect = D2H + IPC framing. flush == stage; process; collect. */
+int pa_agg_stage(pa_agg* a);
+int pa_agg_process(pa_agg* a);
+int pa_agg_collect(pa_agg* a, pa_agg_result* out);
+/* device time (ms, CUDA events on the compute stream) of named kernel groups during the last
+ * process(): names are "hash", "header", "rank", "locations", "labels", "columns", "total". */
+int pa_agg_last_kernel_ms(const pa_agg* a, const char* name, double* ms, uint32_t* launches);
+/* copies the per-row 128-bit stack ids (big-endian hi‖lo, 16 B per row) of the staged batch. */
+int pa_agg_debug_stack_ids(pa_agg* a, uint8_t* out, uint64_t n_rows);
+/* per-unique-stack occurrence counts in first-occurrence order (the "count per stack" side table;
+ * not part of the reference's record — see SURVEY §0.2). out has n_unique_stacks entries. */
+int pa_agg_debug_stack_counts(pa_agg* a, uint32_t* out, uint64_t n);
+
+/* host helpers restating reference functions (no GPU involved) */
+/* maybeFixTruncation (reporter/parca_reporter.go:190-216): returns the fixed length, or -1. */
+int64_t pa_fix_truncation(const uint8_t* s, uint64_t len, uint64_t max_len);
+uint64_t pa_xxh64(const void* data, uint64_t len, uint64_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARCAAGG_H */
