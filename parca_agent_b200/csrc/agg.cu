@@ -1,0 +1,1154 @@
+// agg.cu — libparcaagg: host orchestration + C ABI (include/parcaagg.h).
+//
+// One pa_agg = one ParcaReporter's V2 sample writer (reporter/parca_reporter.go). Ingest lands in
+// a C-owned pinned ring (double-buffered: flush swaps buffers under the ingest lock exactly like
+// buildSampleRecordV2 swaps writers, :1743-1748), flush stages the detached buffer to HBM in
+// chunks (copy stream) while the compute stream hashes/dedups the chunks already resident, then
+// ranks/gathers dictionaries, run-end encodes the label and constant columns, and finally copies
+// each finished Arrow buffer device->host straight into its place in the IPC stream.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/parcaagg.h"
+#include "host_tables.hpp"
+#include "ipc_out.hpp"
+#include "kernels.cuh"
+
+namespace pa {
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    size_t want = std::max(n, cap + cap / 2);
+    cudaError_t e = cudaMalloc(&p, want);
+    cap = e == cudaSuccess ? want : 0;
+    return e;
+  }
+  template <class T> T* as() const { return (T*)p; }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// growable device mirror of an append-only host vector
+template <class T>
+struct Mirror {
+  DBuf buf;
+  size_t uploaded = 0;
+  cudaError_t sync(const std::vector<T>& h, cudaStream_t s) {
+    if (!buf.p || h.size() * sizeof(T) > buf.cap) {
+      DBuf nb;
+      cudaError_t e = nb.ensure(std::max<size_t>(h.size() * sizeof(T) * 2, 256));
+      if (e != cudaSuccess) return e;
+      buf.release();
+      buf = nb;
+      uploaded = 0;
+    }
+    if (uploaded < h.size()) {
+      cudaError_t e = cudaMemcpyAsync(buf.as<T>() + uploaded, h.data() + uploaded, (h.size() - uploaded) * sizeof(T), cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) return e;
+      uploaded = h.size();
+    }
+    return cudaSuccess;
+  }
+  const T* ptr() const { return buf.as<T>(); }
+};
+
+struct ColPlan {
+  std::string name;
+  uint32_t type = COL_LS;
+  uint32_t param = 0;              // LS: column index in lsmat; KIND: table row
+  std::vector<uint32_t> vals;      // LS: local value id -> canonical string id
+  std::map<uint32_t, uint32_t> val_index;
+  uint32_t universe = 0;
+  // device pointers for this flush
+  int* run_ends = nullptr;
+  uint32_t* run_keys = nullptr;    // becomes the dictionary indices in place
+  uint32_t* validity = nullptr;
+  uint32_t* order = nullptr;
+};
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  uint32_t launches = 0;
+  double ms = 0;
+};
+static const char* kTimerNames[] = {"header", "hash", "rank", "locations", "labels", "dicts", "total"};
+enum { T_HEADER, T_HASH, T_RANK, T_LOC, T_LABELS, T_DICTS, T_TOTAL, T_COUNT };
+
+}  // namespace pa
+
+using namespace pa;
+
+struct pa_agg {
+  pa_agg_config cfg{};
+  std::string err;
+  int device = 0, sms = 148, G = 592;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+
+  // ---- registration state
+  std::mutex reg_mu;
+  StringPool sp;
+  FrameTableHost ft;
+  LabelSets ls;
+  std::vector<std::pair<uint32_t, uint32_t>> external;  // canonical ids
+  bool cols_dirty = true;
+  std::vector<ColPlan> cols;  // label columns, then the 8 constant-ish columns
+  uint32_t n_label_cols = 0, n_lscols = 0;
+  std::vector<uint32_t> lsmat;
+  std::vector<uint32_t> kindtab;           // [8][8]
+  std::vector<std::vector<std::string>> kind_strings;  // class -> string for the 6 string columns
+  std::vector<int64_t> period_vals;
+  std::vector<uint64_t> duration_vals;
+
+  Mirror<uint64_t> m_addr, m_line;
+  Mirror<uint32_t> m_type, m_map, m_bid, m_func, m_fnfile, m_sid2cid;
+  DBuf d_lsmat, d_kindtab, d_cols, d_jobs;
+
+  // ---- ring (pinned host), double buffered
+  struct Ring { pa_sample_hdr* hdr = nullptr; uint64_t* frames = nullptr; uint64_t rows = 0, nfr = 0; } ring[2];
+  int active = 0, inflight = 0;
+  std::mutex ring_mu;
+  std::condition_variable ring_cv;
+  std::mutex flush_mu;
+
+  // ---- staged batch
+  int staged = -1;
+  uint64_t N = 0, NF = 0;
+  std::vector<cudaEvent_t> chunk_ev;
+  std::vector<std::pair<uint64_t, uint64_t>> chunk_rows;    // [row0,row1)
+  std::vector<uint64_t> chunk_frames_end;
+  cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_d2h0 = nullptr, ev_d2h1 = nullptr;
+  bool processed = false, hash_timed = false;
+
+  // ---- device batch buffers
+  DBuf d_hdr, d_frames, d_ts, d_value, d_uuid, d_stoff, d_stsize, d_slot, d_kind, d_nfr, d_foff, d_ls, d_cpu, d_tid, d_comm;
+  DBuf d_ustream, d_uniq_row, d_uniq_count, d_table, d_ctr, d_arena, d_partial;
+  uint64_t table_cap = 0, retry_cap = 0;
+  uint64_t prev_unique = 0;
+  Counters h_ctr{};
+  Counters* h_ctr_pinned = nullptr;
+  // arena-carved pointers (valid for the current flush)
+  uint32_t *loc_first = nullptr, *loc_rank = nullptr, *loc_order = nullptr;
+  uint32_t *sd_first[4] = {}, *sd_rank[4] = {}, *sd_order[4] = {}, *sd_keys[4] = {}, *sd_valid[4] = {};  // type,map,bid,file
+  uint32_t *fn_first = nullptr, *fn_rank = nullptr, *fn_order = nullptr, *fn_keys = nullptr;
+  LocOut lo{};
+  unsigned long long* tid_slots = nullptr;
+  uint32_t* tid_rank = nullptr;
+  uint32_t tid_mask = 0;
+
+  // ---- output
+  uint8_t* out = nullptr;
+  uint64_t out_cap = 0;
+  std::vector<std::vector<uint8_t>> hostbufs;  // host-built Arrow buffers of the current result
+  Timer tm[T_COUNT];
+  uint32_t launches = 0;
+  double h2d_ms = 0;
+
+  int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    err = what;
+    if (e != cudaSuccess) { err += ": "; err += cudaGetErrorString(e); }
+    return code;
+  }
+};
+
+#define CK(expr)                                                        \
+  do {                                                                  \
+    cudaError_t e_ = (expr);                                            \
+    if (e_ != cudaSuccess) return a->fail(PA_EIO, #expr, e_);           \
+  } while (0)
+
+static uint64_t pow2_at_least(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
+
+// ---------------------------------------------------------------------------------------------
+// column plan: which REE columns exist and how each row's key is derived
+static void build_kind_tables(pa_agg* a) {
+  // reportTraceEventV2's per-origin constants (reporter/parca_reporter.go:338-363)
+  static const char* producer[7] = {"parca_agent", "parca_agent", "parca_agent", "memory", "memory", "memory", "memory"};
+  static const char* stype[7] = {"samples", "wallclock", "cuda", "inuse_objects", "inuse_space", "alloc_objects", "alloc_space"};
+  static const char* sunit[7] = {"count", "nanoseconds", "nanoseconds", "count", "bytes", "count", "bytes"};
+  static const char* ptype[7] = {"cpu", "samples", "cuda", "space", "space", "space", "space"};
+  static const char* punit[7] = {"nanoseconds", "count", "nanoseconds", "bytes", "bytes", "bytes", "bytes"};
+  static const char* tempo[7] = {"delta", "delta", "delta", nullptr, nullptr, nullptr, nullptr};
+  const char* const* tabs[6] = {producer, stype, sunit, ptype, punit, tempo};
+  a->kindtab.assign(8 * 8, kNull);
+  a->kind_strings.assign(6, {});
+  for (int t = 0; t < 6; t++)
+    for (int k = 0; k < 7; k++) {
+      if (!tabs[t][k]) continue;
+      auto& v = a->kind_strings[t];
+      auto it = std::find(v.begin(), v.end(), std::string(tabs[t][k]));
+      if (it == v.end()) { v.push_back(tabs[t][k]); it = v.end() - 1; }
+      a->kindtab[t * 8 + k] = (uint32_t)(it - v.begin());
+    }
+  int64_t per[7] = {1000000000ll / (int64_t)a->cfg.samples_per_second, 0, 1, 524288, 524288, 524288, 524288};
+  uint64_t dur[7] = {1000000000ull, 1000000000ull, 1000000000ull, 0, 0, 0, 0};
+  a->period_vals.clear();
+  a->duration_vals.clear();
+  for (int k = 0; k < 7; k++) {  // equal values share a class: run merging compares values (arrow.go:170-207)
+    auto ip = std::find(a->period_vals.begin(), a->period_vals.end(), per[k]);
+    if (ip == a->period_vals.end()) { a->period_vals.push_back(per[k]); ip = a->period_vals.end() - 1; }
+    a->kindtab[6 * 8 + k] = (uint32_t)(ip - a->period_vals.begin());
+    auto id = std::find(a->duration_vals.begin(), a->duration_vals.end(), dur[k]);
+    if (id == a->duration_vals.end()) { a->duration_vals.push_back(dur[k]); id = a->duration_vals.end() - 1; }
+    a->kindtab[7 * 8 + k] = (uint32_t)(id - a->duration_vals.begin());
+  }
+}
+
+static int build_columns(pa_agg* a) {
+  a->cols.clear();
+  const uint32_t flags = a->cfg.label_flags;
+  const bool on_cpu = !(flags & PA_LABEL_DISABLE_CPU), on_tid = !(flags & PA_LABEL_DISABLE_THREAD_ID), on_comm = !(flags & PA_LABEL_DISABLE_THREAD_COMM);
+  const uint32_t c_cpu = a->sp.intern("cpu"), c_tid = a->sp.intern("thread_id"), c_comm = a->sp.intern("thread_name");
+  std::map<uint32_t, uint32_t> col_of_name;  // name cid -> column
+  a->n_lscols = 0;
+  for (auto& set : a->ls.sets)
+    for (auto& kv : set) {
+      uint32_t name = kv.first;
+      // per-sample labels.Builder.Set overrides the cached value of the same name (:616-625)
+      if ((name == c_cpu && on_cpu) || (name == c_tid && on_tid) || (name == c_comm && on_comm)) continue;
+      auto it = col_of_name.find(name);
+      if (it == col_of_name.end()) {
+        ColPlan c;
+        c.name.assign((const char*)a->sp.ptr(name), a->sp.len(name));
+        c.type = COL_LS;
+        c.param = a->n_lscols++;
+        it = col_of_name.emplace(name, (uint32_t)a->cols.size()).first;
+        a->cols.push_back(std::move(c));
+      }
+      ColPlan& c = a->cols[it->second];
+      if (!c.val_index.count(kv.second)) { c.val_index.emplace(kv.second, (uint32_t)c.vals.size()); c.vals.push_back(kv.second); }
+    }
+  a->lsmat.assign((size_t)std::max<size_t>(1, a->ls.sets.size()) * std::max<uint32_t>(1, a->n_lscols), kNull);
+  for (size_t s = 0; s < a->ls.sets.size(); s++)
+    for (auto& kv : a->ls.sets[s]) {
+      auto it = col_of_name.find(kv.first);
+      if (it == col_of_name.end()) continue;
+      ColPlan& c = a->cols[it->second];
+      a->lsmat[s * std::max<uint32_t>(1, a->n_lscols) + c.param] = c.val_index[kv.second];
+    }
+  for (auto& c : a->cols) c.universe = (uint32_t)c.vals.size();
+  auto add = [a](const char* name, uint32_t type, uint32_t universe) { ColPlan c; c.name = name; c.type = type; c.universe = universe; a->cols.push_back(std::move(c)); };
+  if (on_cpu) add("cpu", COL_CPU, 65536);
+  if (on_tid) add("thread_id", COL_TID, 0);
+  if (on_comm) add("thread_name", COL_COMM, 0 /* = canonical string count, set per flush */);
+  a->n_label_cols = (uint32_t)a->cols.size();
+  if (a->n_label_cols + 8 > (uint32_t)kMaxCols) return a->fail(PA_ERANGE, "too many distinct label names for one batch (limit 40)");
+  static const char* fixed[8] = {"producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality", "period", "duration"};
+  for (uint32_t t = 0; t < 8; t++) { ColPlan c; c.name = fixed[t]; c.type = COL_KIND; c.param = t; a->cols.push_back(std::move(c)); }
+  build_kind_tables(a);
+  a->cols_dirty = false;
+  return PA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+uint32_t pa_agg_abi_version(void) { return PA_ABI_VERSION; }
+const char* pa_agg_last_error(const pa_agg* a) { return a ? a->err.c_str() : "null handle"; }
+
+int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
+  if (!cfg || !out || cfg->abi_version != PA_ABI_VERSION || cfg->samples_per_second == 0 || cfg->max_samples == 0 || cfg->hash_mode > 1) return PA_EINVAL;
+  if (cfg->max_samples > 0x7FFFFFFFull) return PA_ERANGE;  // run ends / ListView offsets are int32
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return PA_ENODEV;
+  pa_agg* a = new pa_agg();
+  a->cfg = *cfg;
+  a->cfg.external_labels = nullptr;
+  a->device = cfg->device;
+  auto bail = [&](int code) { pa_agg_destroy(a); return code; };
+  if (cudaSetDevice(a->device) != cudaSuccess) return bail(PA_ENODEV);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, a->device) != cudaSuccess) return bail(PA_ENODEV);
+  a->sms = prop.multiProcessorCount;
+  a->G = a->sms * 4;
+  if (a->cfg.chunk_samples == 0) a->cfg.chunk_samples = 1u << 20;
+  if (a->cfg.max_frames == 0) a->cfg.max_frames = a->cfg.max_samples * 64;
+  for (uint32_t i = 0; i < cfg->n_external_labels; i++) {  // resolved to canonical ids lazily at flush (strings may come later)
+    a->external.emplace_back(cfg->external_labels[i].name_sid, cfg->external_labels[i].value_sid);
+  }
+  if (cudaStreamCreateWithFlags(&a->s_copy, cudaStreamNonBlocking) != cudaSuccess) return bail(PA_EIO);
+  if (cudaStreamCreateWithFlags(&a->s_comp, cudaStreamNonBlocking) != cudaSuccess) return bail(PA_EIO);
+  cudaEventCreate(&a->ev_h2d0);
+  cudaEventCreate(&a->ev_h2d1);
+  cudaEventCreate(&a->ev_d2h0);
+  cudaEventCreate(&a->ev_d2h1);
+  for (int t = 0; t < T_COUNT; t++) { cudaEventCreate(&a->tm[t].a); cudaEventCreate(&a->tm[t].b); }
+  const uint64_t N = a->cfg.max_samples, NF = a->cfg.max_frames;
+  for (int r = 0; r < 2; r++) {
+    if (cudaHostAlloc((void**)&a->ring[r].hdr, N * sizeof(pa_sample_hdr), cudaHostAllocDefault) != cudaSuccess) return bail(PA_ENOMEM);
+    if (cudaHostAlloc((void**)&a->ring[r].frames, std::max<uint64_t>(NF, 1) * 8, cudaHostAllocDefault) != cudaSuccess) return bail(PA_ENOMEM);
+  }
+  if (cudaHostAlloc((void**)&a->h_ctr_pinned, sizeof(Counters), cudaHostAllocDefault) != cudaSuccess) return bail(PA_ENOMEM);
+  bool ok = true;
+  auto need = [&](DBuf& b, uint64_t bytes) { ok = ok && b.ensure(std::max<uint64_t>(bytes, 256)) == cudaSuccess; };
+  need(a->d_hdr, N * 64); need(a->d_frames, NF * 8);
+  need(a->d_ts, N * 8); need(a->d_value, N * 8); need(a->d_uuid, N * 16); need(a->d_stoff, N * 4); need(a->d_stsize, N * 4);
+  need(a->d_slot, N * 4); need(a->d_kind, N); need(a->d_nfr, N * 2); need(a->d_foff, N * 8);
+  need(a->d_ls, N * 4); need(a->d_cpu, N * 4); need(a->d_tid, N * 4); need(a->d_comm, N * 4);
+  need(a->d_ustream, std::min<uint64_t>(NF, 0x7FFFFFFFull) * 4 + 256);
+  need(a->d_uniq_row, N * 4); need(a->d_uniq_count, N * 4);
+  need(a->d_ctr, sizeof(Counters));
+  need(a->d_partial, (uint64_t)a->G * kMaxCols * sizeof(Pair) + 256);
+  if (!ok) return bail(PA_ENOMEM);
+  *out = a;
+  return PA_OK;
+}
+
+void pa_agg_destroy(pa_agg* a) {
+  if (!a) return;
+  cudaSetDevice(a->device);
+  if (a->s_comp) cudaStreamSynchronize(a->s_comp);
+  if (a->s_copy) cudaStreamSynchronize(a->s_copy);
+  for (int r = 0; r < 2; r++) { if (a->ring[r].hdr) cudaFreeHost(a->ring[r].hdr); if (a->ring[r].frames) cudaFreeHost(a->ring[r].frames); }
+  if (a->h_ctr_pinned) cudaFreeHost(a->h_ctr_pinned);
+  if (a->out) cudaFreeHost(a->out);
+  DBuf* all[] = {&a->d_hdr, &a->d_frames, &a->d_ts, &a->d_value, &a->d_uuid, &a->d_stoff, &a->d_stsize, &a->d_slot, &a->d_kind, &a->d_nfr,
+                 &a->d_foff, &a->d_ls, &a->d_cpu, &a->d_tid, &a->d_comm, &a->d_ustream, &a->d_uniq_row, &a->d_uniq_count, &a->d_table, &a->d_ctr,
+                 &a->d_arena, &a->d_partial, &a->d_lsmat, &a->d_kindtab, &a->d_cols, &a->d_jobs,
+                 &a->m_addr.buf, &a->m_line.buf, &a->m_type.buf, &a->m_map.buf, &a->m_bid.buf, &a->m_func.buf, &a->m_fnfile.buf, &a->m_sid2cid.buf};
+  for (DBuf* b : all) b->release();
+  for (auto e : a->chunk_ev) cudaEventDestroy(e);
+  if (a->ev_h2d0) cudaEventDestroy(a->ev_h2d0);
+  if (a->ev_h2d1) cudaEventDestroy(a->ev_h2d1);
+  if (a->ev_d2h0) cudaEventDestroy(a->ev_d2h0);
+  if (a->ev_d2h1) cudaEventDestroy(a->ev_d2h1);
+  for (int t = 0; t < T_COUNT; t++) { if (a->tm[t].a) cudaEventDestroy(a->tm[t].a); if (a->tm[t].b) cudaEventDestroy(a->tm[t].b); }
+  if (a->s_copy) cudaStreamDestroy(a->s_copy);
+  if (a->s_comp) cudaStreamDestroy(a->s_comp);
+  delete a;
+}
+
+// ---- registration ---------------------------------------------------------------------------
+int pa_agg_register_strings(pa_agg* a, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, uint32_t* first_id) {
+  if (!a || (n && (!bytes && offsets[n] != 0)) || (n && !offsets)) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->reg_mu);
+  if (first_id) *first_id = (uint32_t)a->sp.sid2cid.size();
+  for (uint32_t i = 0; i < n; i++) {
+    if (offsets[i + 1] < offsets[i]) return a->fail(PA_EINVAL, "string offsets must be non-decreasing");
+    a->sp.sid2cid.push_back(a->sp.intern((const char*)bytes + offsets[i], offsets[i + 1] - offsets[i]));
+  }
+  return PA_OK;
+}
+int pa_agg_register_frames(pa_agg* a, const pa_frame_desc* descs, uint32_t n, uint64_t* first_frame_id) {
+  if (!a || (n && !descs)) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->reg_mu);
+  if (first_frame_id) *first_frame_id = a->ft.count();
+  for (uint32_t i = 0; i < n; i++)
+    if (!a->ft.resolve(descs[i], a->sp)) return a->fail(PA_EINVAL, "frame refers to an unregistered string id");
+  return PA_OK;
+}
+int pa_agg_register_labelsets(pa_agg* a, const pa_label_pair* pairs, const uint32_t* offsets, uint32_t n, uint32_t* first_id) {
+  if (!a || (n && !offsets)) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->reg_mu);
+  if (first_id) *first_id = (uint32_t)a->ls.sets.size();
+  for (uint32_t i = 0; i < n; i++) {
+    std::vector<std::pair<uint32_t, uint32_t>> set;
+    for (uint32_t k = offsets[i]; k < offsets[i + 1]; k++) {
+      if (pairs[k].name_sid >= a->sp.sid2cid.size() || pairs[k].value_sid >= a->sp.sid2cid.size()) return a->fail(PA_EINVAL, "labelset refers to an unregistered string id");
+      uint32_t v = a->sp.sid2cid[pairs[k].value_sid];
+      if (v == 0) continue;  // labels.Labels never carries empty values
+      set.emplace_back(a->sp.sid2cid[pairs[k].name_sid], v);
+    }
+    a->ls.sets.push_back(std::move(set));
+  }
+  a->cols_dirty = true;
+  return PA_OK;
+}
+
+// ---- ingest ----------------------------------------------------------------------------------
+int pa_agg_acquire(pa_agg* a, uint64_t n_rows, uint64_t n_frames, pa_sample_hdr** hdrs, uint64_t** frames, uint64_t* frame_base) {
+  if (!a || !hdrs || !frames) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->ring_mu);
+  pa_agg::Ring& r = a->ring[a->active];
+  if (r.rows + n_rows > a->cfg.max_samples || r.nfr + n_frames > a->cfg.max_frames) return PA_ENOSPC;
+  *hdrs = r.hdr + r.rows;
+  *frames = r.frames + r.nfr;
+  if (frame_base) *frame_base = r.nfr;
+  r.rows += n_rows;
+  r.nfr += n_frames;
+  a->inflight++;
+  return PA_OK;
+}
+int pa_agg_commit(pa_agg* a, uint64_t) {
+  if (!a) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->ring_mu);
+  if (a->inflight > 0) a->inflight--;
+  a->ring_cv.notify_all();
+  return PA_OK;
+}
+int pa_agg_submit(pa_agg* a, const pa_sample_hdr* hdrs, const uint64_t* frames, uint64_t n_rows) {
+  if (!a || (n_rows && !hdrs)) return PA_EINVAL;
+  uint64_t nf = 0;
+  for (uint64_t i = 0; i < n_rows; i++) nf += hdrs[i].nframes;
+  pa_sample_hdr* dh; uint64_t* df; uint64_t base;
+  int rc = pa_agg_acquire(a, n_rows, nf, &dh, &df, &base);
+  if (rc) return rc;
+  uint64_t off = 0;
+  for (uint64_t i = 0; i < n_rows; i++) {
+    dh[i] = hdrs[i];
+    dh[i].frame_off = base + off;
+    if (hdrs[i].nframes) memcpy(df + off, frames + off, (size_t)hdrs[i].nframes * 8);
+    off += hdrs[i].nframes;
+  }
+  return pa_agg_commit(a, n_rows);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// stage: swap ring buffers, start the chunked H2D copies
+static int stage_async(pa_agg* a) {
+  CK(cudaSetDevice(a->device));
+  int buf;
+  {
+    std::unique_lock<std::mutex> g(a->ring_mu);
+    a->ring_cv.wait(g, [a] { return a->inflight == 0; });
+    buf = a->active;
+    a->active ^= 1;
+    a->ring[a->active].rows = 0;
+    a->ring[a->active].nfr = 0;
+  }
+  pa_agg::Ring& r = a->ring[buf];
+  a->staged = buf;
+  a->N = r.rows;
+  a->NF = r.nfr;
+  a->processed = false;
+  a->chunk_rows.clear();
+  a->chunk_frames_end.clear();
+  const uint64_t C = a->cfg.chunk_samples;
+  uint64_t nchunks = (a->N + C - 1) / C;
+  while (a->chunk_ev.size() < nchunks) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); a->chunk_ev.push_back(e); }
+  CK(cudaEventRecord(a->ev_h2d0, a->s_copy));
+  uint64_t fdone = 0;
+  for (uint64_t k = 0; k < nchunks; k++) {
+    uint64_t r0 = k * C, r1 = std::min(a->N, r0 + C);
+    // frames are laid out in row order (acquire hands out ascending frame_base): a chunk's frames end where the next chunk's begin
+    uint64_t fend = (r1 < a->N) ? std::min<uint64_t>(r.hdr[r1].frame_off, a->NF) : a->NF;
+    if (fend < fdone) fend = fdone;
+    CK(cudaMemcpyAsync(a->d_hdr.as<uint8_t>() + r0 * 64, r.hdr + r0, (r1 - r0) * 64, cudaMemcpyHostToDevice, a->s_copy));
+    if (fend > fdone) CK(cudaMemcpyAsync(a->d_frames.as<uint64_t>() + fdone, r.frames + fdone, (fend - fdone) * 8, cudaMemcpyHostToDevice, a->s_copy));
+    fdone = fend;
+    CK(cudaEventRecord(a->chunk_ev[k], a->s_copy));
+    a->chunk_rows.emplace_back(r0, r1);
+    a->chunk_frames_end.push_back(fend);
+  }
+  CK(cudaEventRecord(a->ev_h2d1, a->s_copy));
+  return PA_OK;
+}
+
+template <class F>
+static void launch_scan(pa_agg* a, F f, int njobs, Timer& t) {
+  dim3 grid(a->G, njobs);
+  typename F::T* partial = a->d_partial.as<typename F::T>();
+  k_scan_reduce<F><<<grid, kThreads, 0, a->s_comp>>>(f, partial);
+  k_scan_partials<F><<<njobs, 32, 0, a->s_comp>>>(f, partial, a->G);
+  k_scan_emit<F><<<grid, kThreads, 0, a->s_comp>>>(f, partial);
+  t.launches += 3;
+}
+
+static int upload_tables(pa_agg* a) {
+  std::lock_guard<std::mutex> g(a->reg_mu);
+  cudaStream_t s = a->s_comp;
+  CK(a->m_addr.sync(a->ft.addr, s)); CK(a->m_line.sync(a->ft.line, s)); CK(a->m_type.sync(a->ft.type_cid, s));
+  CK(a->m_map.sync(a->ft.map_cid, s)); CK(a->m_bid.sync(a->ft.bid_cid, s)); CK(a->m_func.sync(a->ft.func, s));
+  CK(a->m_fnfile.sync(a->ft.fn_file_cid, s)); CK(a->m_sid2cid.sync(a->sp.sid2cid, s));
+  if (a->cols_dirty) {
+    int rc = build_columns(a);
+    if (rc) return rc;
+    CK(a->d_lsmat.ensure(a->lsmat.size() * 4));
+    CK(cudaMemcpyAsync(a->d_lsmat.p, a->lsmat.data(), a->lsmat.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(a->d_kindtab.ensure(a->kindtab.size() * 4));
+    CK(cudaMemcpyAsync(a->d_kindtab.p, a->kindtab.data(), a->kindtab.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));  // lsmat/kindtab host vectors may be rebuilt later
+  }
+  return PA_OK;
+}
+
+static int process_once(pa_agg* a) {
+  const uint64_t N = a->N;
+  const uint32_t n_cstr = a->sp.count(), n_frames = a->ft.count(), n_funcs = a->ft.n_funcs();
+  const uint32_t ncols = (uint32_t)a->cols.size(), nlab = a->n_label_cols;
+  cudaStream_t s = a->s_comp;
+  for (int t = 0; t < T_COUNT; t++) { a->tm[t].launches = 0; a->tm[t].ms = 0; }
+
+  // ---- stack table capacity: 2x an upper bound on this batch's unique stacks
+  uint64_t bound = N;
+  if (a->prev_unique && N > (1u << 20)) bound = std::min<uint64_t>(N, std::max<uint64_t>(a->prev_unique * 4, 1u << 20));
+  uint64_t cap = std::max<uint64_t>(pow2_at_least(2 * std::max<uint64_t>(bound, 1)), 1024);
+  if (cap < a->retry_cap) cap = a->retry_cap;  // grown by an overflow retry of this batch
+  a->table_cap = cap;
+  CK(a->d_table.ensure((cap + 2) * sizeof(StackSlot)));
+
+  // ---- arena: per-flush scratch and small output buffers
+  struct Req { void** pp; size_t bytes; bool ff; };
+  std::vector<Req> reqs;
+  auto want = [&reqs](auto** pp, size_t bytes, bool ff = false) { reqs.push_back(Req{(void**)pp, (bytes + 255) & ~(size_t)255, ff}); };
+  const size_t P = std::max<uint32_t>(n_frames, 1), S = std::max<uint32_t>(n_cstr, 1), FN = std::max<uint32_t>(n_funcs, 1);
+  want(&a->loc_first, P * 4, true); want(&a->loc_rank, P * 4); want(&a->loc_order, P * 4);
+  for (int d = 0; d < 4; d++) {
+    size_t n = d == 3 ? FN : P;
+    want(&a->sd_first[d], S * 4, true); want(&a->sd_rank[d], S * 4); want(&a->sd_order[d], S * 4);
+    want(&a->sd_keys[d], n * 4); want(&a->sd_valid[d], (n / 32 + 2) * 4);
+  }
+  want(&a->fn_first, FN * 4, true); want(&a->fn_rank, FN * 4); want(&a->fn_order, FN * 4); want(&a->fn_keys, P * 4);
+  want(&a->lo.address, P * 8); want(&a->lo.line_off, P * 4); want(&a->lo.line_size, P * 4); want(&a->lo.line_valid, (P / 32 + 2) * 4);
+  want(&a->lo.line_no, P * 8);
+  a->tid_mask = (uint32_t)pow2_at_least(2 * std::max<uint64_t>(N, 16)) - 1;
+  std::vector<uint32_t*> col_first(ncols, nullptr), col_rank(ncols, nullptr);
+  for (uint32_t c = 0; c < ncols; c++) {
+    ColPlan& cp = a->cols[c];
+    want(&cp.run_ends, std::max<uint64_t>(N, 1) * 4);
+    want(&cp.run_keys, std::max<uint64_t>(N, 1) * 4);
+    if (c >= nlab) continue;
+    want(&cp.validity, (N / 32 + 2) * 4);
+    if (cp.type == COL_COMM) cp.universe = n_cstr;
+    if (cp.type == COL_TID) {
+      want(&a->tid_slots, ((size_t)a->tid_mask + 1) * 8, true);
+      want(&a->tid_rank, ((size_t)a->tid_mask + 1) * 4);
+      want(&cp.order, std::max<uint64_t>(N, 1) * 4);
+    } else {
+      size_t u = std::max<uint32_t>(cp.universe, 1);
+      want(&col_first[c], u * 4, true); want(&col_rank[c], u * 4); want(&cp.order, u * 4);
+    }
+  }
+  size_t total = 0, ff_bytes = 0;
+  for (auto& r : reqs) { total += r.bytes; if (r.ff) ff_bytes += r.bytes; }
+  CK(a->d_arena.ensure(std::max<size_t>(total, 256)));
+  {
+    size_t off_ff = 0, off = ff_bytes;  // 0xFF-initialised regions first, contiguous
+    for (auto& r : reqs) {
+      if (r.ff) { *r.pp = a->d_arena.as<uint8_t>() + off_ff; off_ff += r.bytes; } else { *r.pp = a->d_arena.as<uint8_t>() + off; off += r.bytes; }
+    }
+  }
+  a->lo.type_key = a->sd_keys[0]; a->lo.map_key = a->sd_keys[1]; a->lo.bid_key = a->sd_keys[2]; a->lo.func_key = a->fn_keys;
+
+  Counters* ctr = a->d_ctr.as<Counters>();
+  StackSlot* tab = a->d_table.as<StackSlot>();
+  const uint32_t mask = (uint32_t)(cap - 1);
+  const int G = a->G;
+
+  CK(cudaEventRecord(a->tm[T_TOTAL].a, s));
+  CK(cudaMemsetAsync(ctr, 0, sizeof(Counters), s));
+  CK(cudaMemsetAsync(tab, 0, (cap + 2) * sizeof(StackSlot), s));
+  if (ff_bytes) CK(cudaMemsetAsync(a->d_arena.p, 0xFF, ff_bytes, s));
+
+  // ---- per chunk: header split (+insert in provided mode), then hash+insert
+  const bool provided = a->cfg.hash_mode == PA_HASH_PROVIDED;
+  // When the whole batch is already resident (pa_agg_stage) the two passes run back to back and
+  // are timed separately; during an overlapped flush they interleave per chunk as copies land.
+  const bool resident = a->chunk_ev.empty() || a->chunk_rows.empty() || cudaEventQuery(a->chunk_ev[a->chunk_rows.size() - 1]) == cudaSuccess;
+  a->hash_timed = resident && !provided;
+  auto launch_header = [&](size_t k) {
+    HeaderArgs h{};
+    h.hdr = a->d_hdr.as<uint4>(); h.row0 = (uint32_t)a->chunk_rows[k].first; h.row1 = (uint32_t)a->chunk_rows[k].second;
+    h.timestamp = a->d_ts.as<long long>(); h.value = a->d_value.as<long long>(); h.uuid = a->d_uuid.as<uint8_t>();
+    h.kind = a->d_kind.as<uint8_t>(); h.nframes = a->d_nfr.as<uint16_t>(); h.frame_off = a->d_foff.as<unsigned long long>();
+    h.ls = a->d_ls.as<uint32_t>(); h.cpu = a->d_cpu.as<uint32_t>(); h.tid = a->d_tid.as<uint32_t>(); h.comm = a->d_comm.as<uint32_t>();
+    h.sid2cid = a->m_sid2cid.ptr(); h.n_sids = (uint32_t)a->sp.sid2cid.size(); h.n_labelsets = (uint32_t)a->ls.sets.size();
+    h.n_frame_ids = a->chunk_frames_end[k]; h.provided = provided ? 1 : 0; h.tab = tab; h.mask = mask; h.slot_of_row = a->d_slot.as<uint32_t>(); h.ctr = ctr;
+    uint32_t rows = h.row1 - h.row0;
+    int hb = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)G * 2);
+    k_header<<<std::max(hb, 1), kThreads, 0, s>>>(h);
+    a->tm[T_HEADER].launches++;
+  };
+  auto launch_hash = [&](size_t k) {
+    HashArgs ha{};
+    ha.frames = a->d_frames.as<unsigned long long>(); ha.frame_off = a->d_foff.as<unsigned long long>(); ha.nframes = a->d_nfr.as<uint16_t>();
+    ha.row0 = (uint32_t)a->chunk_rows[k].first; ha.row1 = (uint32_t)a->chunk_rows[k].second; ha.uuid = a->d_uuid.as<uint8_t>();
+    ha.slot_of_row = a->d_slot.as<uint32_t>(); ha.tab = tab; ha.mask = mask; ha.ctr = ctr;
+    uint32_t rows = ha.row1 - ha.row0;
+    int blocks = (int)std::min<uint64_t>(((uint64_t)rows * 4 + kThreads - 1) / kThreads, (uint64_t)a->sms * 8);
+    k_hash_insert_direct<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
+    a->tm[T_HASH].launches++;
+  };
+  CK(cudaEventRecord(a->tm[T_HEADER].a, s));
+  if (resident) {
+    for (size_t k = 0; k < a->chunk_rows.size(); k++) launch_header(k);
+    CK(cudaEventRecord(a->tm[T_HEADER].b, s));
+    CK(cudaEventRecord(a->tm[T_HASH].a, s));
+    if (!provided) for (size_t k = 0; k < a->chunk_rows.size(); k++) launch_hash(k);
+    CK(cudaEventRecord(a->tm[T_HASH].b, s));
+  } else {
+    for (size_t k = 0; k < a->chunk_rows.size(); k++) {
+      CK(cudaStreamWaitEvent(s, a->chunk_ev[k], 0));
+      launch_header(k);
+      if (!provided) launch_hash(k);
+    }
+    CK(cudaEventRecord(a->tm[T_HEADER].b, s));
+  }
+
+  // ---- unique stacks: first-occurrence ordinal, offsets, per-row (offset,size), gather
+  CK(cudaEventRecord(a->tm[T_RANK].a, s));
+  RowFirstF rf{(uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(), a->d_uniq_count.as<uint32_t>(), ctr};
+  launch_scan(a, rf, 1, a->tm[T_RANK]);
+  k_rows_materialize<<<G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>());
+  k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, a->d_frames.as<unsigned long long>(),
+                                         a->d_foff.as<unsigned long long>(), n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr);
+  a->tm[T_RANK].launches += 2;
+  CK(cudaEventRecord(a->tm[T_RANK].b, s));
+
+  // ---- dictionaries: jobs table
+  std::vector<FoJob> jobs;
+  auto job = [&](const uint32_t* keys, const uint32_t* n_ptr, uint32_t* first, uint32_t* rank, uint32_t* order, uint32_t* out, uint32_t* validity,
+                 uint32_t* n_unique, uint32_t* n_null, bool nullable, bool skip_min) {
+    FoJob j{};
+    j.keys = keys; j.n_ptr = n_ptr; j.first = first; j.rank = rank; j.order = order; j.out = out; j.validity = validity;
+    j.n_unique = n_unique; j.n_null = n_null; j.nullable = nullable; j.skip_min = skip_min;
+    jobs.push_back(j);
+    return (int)jobs.size() - 1;
+  };
+  static_assert(sizeof(unsigned long long) == 8, "");
+  // the low 32 bits of n_indices64 are the index count (overflow is flagged separately)
+  const uint32_t* n_idx_ptr = (const uint32_t*)&ctr->n_indices64;
+  int j_loc = job(a->d_ustream.as<uint32_t>(), n_idx_ptr, a->loc_first, a->loc_rank, a->loc_order, a->d_ustream.as<uint32_t>(), nullptr, &ctr->n_locations, nullptr, false, true);
+  int j_type = job(a->sd_keys[0], &ctr->n_locations, a->sd_first[0], a->sd_rank[0], a->sd_order[0], a->sd_keys[0], nullptr, &ctr->n_dict_type, nullptr, false, false);
+  job(a->sd_keys[1], &ctr->n_locations, a->sd_first[1], a->sd_rank[1], a->sd_order[1], a->sd_keys[1], nullptr, &ctr->n_dict_map, nullptr, false, false);
+  job(a->sd_keys[2], &ctr->n_locations, a->sd_first[2], a->sd_rank[2], a->sd_order[2], a->sd_keys[2], a->sd_valid[2], &ctr->n_dict_bid, &ctr->null_bid, true, false);
+  job(a->fn_keys, &ctr->n_lines, a->fn_first, a->fn_rank, a->fn_order, a->fn_keys, nullptr, &ctr->n_functions, nullptr, false, false);
+  int j_file = job(a->sd_keys[3], &ctr->n_functions, a->sd_first[3], a->sd_rank[3], a->sd_order[3], a->sd_keys[3], a->sd_valid[3], &ctr->n_dict_file, &ctr->null_file, true, false);
+  int j_lab0 = (int)jobs.size();
+  for (uint32_t c = 0; c < nlab; c++) {
+    ColPlan& cp = a->cols[c];
+    bool nullable = cp.type == COL_LS || cp.type == COL_COMM;
+    int ji = job(cp.run_keys, &ctr->n_runs[c], col_first[c], col_rank[c], cp.order, cp.run_keys, cp.validity, &ctr->n_dict[c], &ctr->n_null[c], nullable, false);
+    if (cp.type == COL_TID) { jobs[ji].hashed = 1; jobs[ji].hslots = a->tid_slots; jobs[ji].hmask = a->tid_mask; jobs[ji].rank = a->tid_rank; }
+  }
+  CK(a->d_jobs.ensure(jobs.size() * sizeof(FoJob)));
+  CK(cudaMemcpyAsync(a->d_jobs.p, jobs.data(), jobs.size() * sizeof(FoJob), cudaMemcpyHostToDevice, s));
+  const FoJob* djobs = a->d_jobs.as<FoJob>();
+  auto run_jobs = [&](int first, int count, Timer& t) {
+    dim3 grid(G, count);
+    k_fo_min<<<grid, kThreads, 0, s>>>(djobs + first);
+    launch_scan(a, FoF{djobs + first}, count, t);
+    k_fo_map<<<grid, kThreads, 0, s>>>(djobs + first);
+    t.launches += 2;
+  };
+
+  CK(cudaEventRecord(a->tm[T_LOC].a, s));
+  run_jobs(j_loc, 1, a->tm[T_LOC]);  // location index per unique-stack frame (in place over the gathered stream)
+  FrameTable ftd{(const unsigned long long*)a->m_addr.ptr(), a->m_type.ptr(), a->m_map.ptr(), a->m_bid.ptr(), (const unsigned long long*)a->m_line.ptr(), a->m_func.ptr()};
+  launch_scan(a, LocLinesF{ctr, ctr, a->loc_order, ftd, a->lo}, 1, a->tm[T_LOC]);
+  k_line_validity<<<std::max(1, std::min(G, (int)(P / 256 + 1))), kThreads, 0, s>>>(ctr, a->lo.line_size, a->lo.line_valid);
+  run_jobs(j_type, 4, a->tm[T_LOC]);  // frame_type, mapping_file, mapping_build_id, function
+  k_func_keys<<<std::max(1, std::min(G, (int)(FN / 256 + 1))), kThreads, 0, s>>>(ctr, a->fn_order, a->m_fnfile.ptr(), a->sd_keys[3]);
+  run_jobs(j_file, 1, a->tm[T_LOC]);  // function.filename
+  a->tm[T_LOC].launches += 2;
+  CK(cudaEventRecord(a->tm[T_LOC].b, s));
+
+  // ---- run-end encoding of label + constant columns
+  CK(cudaEventRecord(a->tm[T_LABELS].a, s));
+  std::vector<ReeCol> rc(ncols);
+  for (uint32_t c = 0; c < ncols; c++) rc[c] = ReeCol{a->cols[c].type, a->cols[c].param, a->cols[c].run_ends, a->cols[c].run_keys};
+  CK(a->d_cols.ensure(rc.size() * sizeof(ReeCol)));
+  CK(cudaMemcpyAsync(a->d_cols.p, rc.data(), rc.size() * sizeof(ReeCol), cudaMemcpyHostToDevice, s));
+  ReeArgs ra{};
+  ra.n_rows = (uint32_t)N; ra.ncols = ncols; ra.cols = a->d_cols.as<ReeCol>();
+  ra.ls = a->d_ls.as<uint32_t>(); ra.cpu = a->d_cpu.as<uint32_t>(); ra.tid = a->d_tid.as<uint32_t>(); ra.comm = a->d_comm.as<uint32_t>(); ra.kind = a->d_kind.as<uint8_t>();
+  ra.lsmat = a->d_lsmat.as<uint32_t>(); ra.n_lscols = std::max<uint32_t>(1, a->n_lscols); ra.kindtab = a->d_kindtab.as<uint32_t>();
+  ra.partial = a->d_partial.as<uint32_t>(); ra.ctr = ctr;
+  k_ree_count<<<G, kThreads, 0, s>>>(ra);
+  k_ree_scan_partials<<<ncols, 32, 0, s>>>(ra, G);
+  k_ree_emit<<<G, kThreads, 0, s>>>(ra);
+  a->tm[T_LABELS].launches += 3;
+  CK(cudaEventRecord(a->tm[T_LABELS].b, s));
+
+  CK(cudaEventRecord(a->tm[T_DICTS].a, s));
+  if (nlab) run_jobs(j_lab0, (int)nlab, a->tm[T_DICTS]);  // label dictionaries over the runs
+  CK(cudaEventRecord(a->tm[T_DICTS].b, s));
+
+  CK(cudaMemcpyAsync(a->h_ctr_pinned, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(a->tm[T_TOTAL].b, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  a->h_ctr = *a->h_ctr_pinned;
+  a->launches = 0;
+  for (int t = 0; t < T_TOTAL; t++) {
+    float ms = 0;
+    if (a->tm[t].launches && (t != T_HASH || a->hash_timed)) { cudaEventElapsedTime(&ms, a->tm[t].a, a->tm[t].b); }
+    a->tm[t].ms = ms;
+    a->launches += a->tm[t].launches;
+  }
+  float tot = 0;
+  cudaEventElapsedTime(&tot, a->tm[T_TOTAL].a, a->tm[T_TOTAL].b);
+  a->tm[T_TOTAL].ms = tot;
+  a->tm[T_TOTAL].launches = a->launches;
+  return PA_OK;
+}
+
+static int process(pa_agg* a) {
+  if (a->staged < 0) return a->fail(PA_EINVAL, "nothing staged");
+  CK(cudaSetDevice(a->device));
+  if (a->N == 0) { a->processed = true; memset(&a->h_ctr, 0, sizeof a->h_ctr); return PA_OK; }
+  int rc = upload_tables(a);
+  if (rc) return rc;
+  for (int attempt = 0; attempt < 6; attempt++) {
+    rc = process_once(a);
+    if (rc) return rc;
+    if (!(a->h_ctr.err & ERR_TABLE_FULL)) break;
+    a->retry_cap = a->table_cap * 4;  // unique-stack estimate was too small: grow and redo the batch
+  }
+  uint32_t e = a->h_ctr.err;
+  if (e & ERR_TABLE_FULL) return a->fail(PA_ENOMEM, "stack table overflow");
+  if (e & ERR_INDEX_OVERFLOW) return a->fail(PA_ERANGE, "location-index stream exceeds int32 (reporter/arrow_v2.go:233)");
+  if (e & ERR_BAD_FRAME_ID) return a->fail(PA_EINVAL, "sample refers to an unregistered frame id");
+  if (e & ERR_BAD_STRING_ID) return a->fail(PA_EINVAL, "sample refers to an unregistered string id");
+  if (e & ERR_BAD_LABELSET) return a->fail(PA_EINVAL, "sample refers to an unregistered labelset id");
+  if (e & ERR_BAD_KIND) return a->fail(PA_EINVAL, "sample kind out of range");
+  if (e & ERR_BAD_CPU) return a->fail(PA_EINVAL, "cpu id >= 65536");
+  if (e & ERR_BAD_FRAME_RANGE) return a->fail(PA_EINVAL, "sample frame range outside the staged frames (frame_off must ascend with the rows)");
+  a->prev_unique = a->h_ctr.n_unique;
+  a->retry_cap = 0;
+  a->processed = true;
+  return PA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// collect: counters -> layout -> D2H of every device-resident Arrow buffer into its final place
+namespace {
+
+struct HostCol {  // a label column materialised on the host (only when an external label touches it)
+  std::vector<int32_t> run_ends;
+  std::vector<uint32_t> idx;
+  std::vector<uint8_t> valid;
+  std::vector<std::string> dict;
+  int64_t len = 0;  // ree.Len()
+};
+
+std::vector<uint8_t>& keep(pa_agg* a, std::vector<uint8_t>&& v) { a->hostbufs.push_back(std::move(v)); return a->hostbufs.back(); }
+template <class T>
+BufRef host_ref(pa_agg* a, const std::vector<T>& v) {
+  std::vector<uint8_t> b(v.size() * sizeof(T));
+  if (!v.empty()) memcpy(b.data(), v.data(), b.size());
+  auto& k = keep(a, std::move(b));
+  return BufRef::host(k.data(), k.size());
+}
+
+Node int_node(const char* name, int bits, bool sgn, bool nullable, int64_t len, BufRef data) {
+  Node n; n.ty = Ty::Int; n.name = name; n.bits = bits; n.is_signed = sgn; n.nullable = nullable; n.length = len; n.bufs = {data};
+  return n;
+}
+// utf8 array from a list of strings
+Node utf8_node(pa_agg* a, const char* name, bool nullable, const std::vector<std::pair<const uint8_t*, uint32_t>>& strs,
+               const std::vector<uint8_t>* valid = nullptr) {
+  std::vector<int32_t> off(strs.size() + 1, 0);
+  uint64_t tot = 0;
+  for (size_t i = 0; i < strs.size(); i++) { tot += strs[i].second; off[i + 1] = (int32_t)tot; }
+  std::vector<uint8_t> data(tot);
+  for (size_t i = 0; i < strs.size(); i++) if (strs[i].second) memcpy(data.data() + off[i], strs[i].first, strs[i].second);
+  Node n; n.ty = Ty::Utf8; n.name = name; n.nullable = nullable; n.length = (int64_t)strs.size();
+  n.bufs = {host_ref(a, off), BufRef::host(keep(a, std::move(data)).data(), tot)};
+  if (valid) {
+    std::vector<uint8_t> bits((strs.size() + 7) / 8, 0);
+    int64_t nulls = 0;
+    for (size_t i = 0; i < strs.size(); i++) { if ((*valid)[i]) bits[i >> 3] |= (uint8_t)(1u << (i & 7)); else nulls++; }
+    n.null_count = nulls;
+    if (nulls) { auto& k = keep(a, std::move(bits)); n.validity = BufRef::host(k.data(), k.size()); }
+  }
+  return n;
+}
+Node dict_node(const char* name, bool nullable, int64_t len, int64_t nulls, BufRef validity, BufRef indices, Node values) {
+  Node n; n.ty = Ty::DictU32; n.name = name; n.nullable = nullable; n.length = len; n.null_count = nulls; n.validity = validity; n.bufs = {indices};
+  n.dict.reset(new Node(std::move(values)));
+  return n;
+}
+Node ree_node(const std::string& name, bool nullable, int64_t len, int64_t n_runs, BufRef run_ends, Node values) {
+  Node n; n.ty = Ty::RunEnd; n.name = name; n.nullable = nullable; n.length = len;
+  n.kids.push_back(int_node("run_ends", 32, true, false, n_runs, run_ends));
+  values.name = "values"; values.nullable = true;
+  n.kids.push_back(std::move(values));
+  return n;
+}
+
+}  // namespace
+
+static int d2h_vec(pa_agg* a, std::vector<uint32_t>& dst, const uint32_t* src, size_t n) {
+  dst.resize(n);
+  if (n) CK(cudaMemcpyAsync(dst.data(), src, n * 4, cudaMemcpyDeviceToHost, a->s_comp));
+  return PA_OK;
+}
+
+static int collect(pa_agg* a, pa_agg_result* res) {
+  memset(res, 0, sizeof *res);
+  if (!a->processed) return a->fail(PA_EINVAL, "collect before process");
+  CK(cudaSetDevice(a->device));
+  const uint64_t N = a->N;
+  a->hostbufs.clear();
+  if (N == 0) { a->staged = -1; return PA_OK; }  // reference skips empty batches (:1775-1778)
+  double t0 = now_ms();
+  const Counters& c = a->h_ctr;
+  const uint32_t nlab = a->n_label_cols;
+  const uint32_t n_loc = c.n_locations, n_lines = c.n_lines, n_fn = c.n_functions, n_idx = (uint32_t)c.n_indices64;
+
+  // ---- small D2H: dictionary orders, constant-column run keys, function order
+  std::vector<uint32_t> ord_type, ord_map, ord_bid, ord_file, ord_fn;
+  std::vector<std::vector<uint32_t>> ord_lab(nlab), kind_keys(8);
+  int rc;
+  if ((rc = d2h_vec(a, ord_type, a->sd_order[0], c.n_dict_type)) || (rc = d2h_vec(a, ord_map, a->sd_order[1], c.n_dict_map)) ||
+      (rc = d2h_vec(a, ord_bid, a->sd_order[2], c.n_dict_bid)) || (rc = d2h_vec(a, ord_file, a->sd_order[3], c.n_dict_file)) ||
+      (rc = d2h_vec(a, ord_fn, a->fn_order, n_fn)))
+    return rc;
+  for (uint32_t i = 0; i < nlab; i++)
+    if (c.last_nonnull_plus1[i] && (rc = d2h_vec(a, ord_lab[i], a->cols[i].order, c.n_dict[i]))) return rc;
+  for (uint32_t t = 0; t < 8; t++)
+    if ((rc = d2h_vec(a, kind_keys[t], a->cols[nlab + t].run_keys, c.n_runs[nlab + t]))) return rc;
+  CK(cudaStreamSynchronize(a->s_comp));
+
+  std::lock_guard<std::mutex> g(a->reg_mu);
+  const StringPool& sp = a->sp;
+  auto cstr = [&sp](uint32_t cid) { return std::make_pair(sp.ptr(cid), sp.len(cid)); };
+  auto strs_of = [&](const std::vector<uint32_t>& ord) {
+    std::vector<std::pair<const uint8_t*, uint32_t>> v;
+    v.reserve(ord.size());
+    for (uint32_t cid : ord) v.push_back(cstr(cid));
+    return v;
+  };
+
+  // ---- label columns (sorted by name, slices.Sort in NewRecord arrow_v2.go:613-614)
+  struct LabelOut { std::string name; Node node; };
+  std::vector<LabelOut> labels;
+  std::map<std::string, HostCol> touched;  // columns modified by external labels
+  // resolve external labels (sid -> canonical id) now that all strings are registered
+  std::vector<std::pair<std::string, std::string>> ext;
+  for (auto& e : a->external) {
+    if (e.first >= sp.sid2cid.size() || e.second >= sp.sid2cid.size()) return a->fail(PA_EINVAL, "external label refers to an unregistered string id");
+    uint32_t n = sp.sid2cid[e.first], v = sp.sid2cid[e.second];
+    ext.emplace_back(std::string((const char*)sp.ptr(n), sp.len(n)), std::string((const char*)sp.ptr(v), sp.len(v)));
+  }
+  auto label_dict_strings = [&](uint32_t i, std::vector<std::string>& decimals) {
+    const ColPlan& cp = a->cols[i];
+    std::vector<std::pair<const uint8_t*, uint32_t>> v;
+    const auto& ord = ord_lab[i];
+    if (cp.type == COL_CPU || cp.type == COL_TID) {
+      decimals.resize(ord.size());
+      for (size_t k = 0; k < ord.size(); k++) decimals[k] = std::to_string(ord[k]);  // fmt.Sprint(cpu|tid) (:618,:621)
+      for (auto& s : decimals) v.emplace_back((const uint8_t*)s.data(), (uint32_t)s.size());
+    } else if (cp.type == COL_LS) {
+      for (uint32_t local : ord) v.push_back(cstr(cp.vals[local]));
+    } else {
+      for (uint32_t cid : ord) v.push_back(cstr(cid));
+    }
+    return v;
+  };
+  for (uint32_t i = 0; i < nlab; i++) {
+    const ColPlan& cp = a->cols[i];
+    if (!c.last_nonnull_plus1[i]) continue;  // no sample carried this label: the reference never created the builder
+    bool is_ext = false;
+    for (auto& e : ext) is_ext |= e.first == cp.name;
+    std::vector<std::string> decimals;
+    auto strs = label_dict_strings(i, decimals);
+    if (is_ext) {  // bring the column to the host; LabelAll is applied below
+      HostCol hc;
+      uint32_t nr = c.n_runs[i];
+      std::vector<uint32_t> idx(nr), vw((nr + 31) / 32);
+      hc.run_ends.resize(nr);
+      CK(cudaMemcpy(hc.run_ends.data(), cp.run_ends, (size_t)nr * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(idx.data(), cp.run_keys, (size_t)nr * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(vw.data(), cp.validity, vw.size() * 4, cudaMemcpyDeviceToHost));
+      hc.idx = idx;
+      hc.valid.resize(nr);
+      for (uint32_t k = 0; k < nr; k++) hc.valid[k] = (vw[k >> 5] >> (k & 31)) & 1u;
+      for (auto& s : strs) hc.dict.emplace_back((const char*)s.first, s.second);
+      // EnsureLength was only ever called up to the last row that carried the label: drop the
+      // trailing one-row null runs the device produced beyond it (arrow_v2.go:550, :562)
+      uint32_t len = c.last_nonnull_plus1[i];
+      uint32_t trailing = (uint32_t)N - len;
+      hc.run_ends.resize(nr - trailing); hc.idx.resize(nr - trailing); hc.valid.resize(nr - trailing);
+      hc.len = len;
+      touched.emplace(cp.name, std::move(hc));
+      continue;
+    }
+    Node dictv = utf8_node(a, "values", true, strs);
+    uint32_t nr = c.n_runs[i];
+    Node values = dict_node("values", true, nr, c.n_null[i], BufRef::dev(cp.validity, (nr + 7) / 8), BufRef::dev(cp.run_keys, (uint64_t)nr * 4), std::move(dictv));
+    labels.push_back(LabelOut{cp.name, ree_node(cp.name, true, (int64_t)N, nr, BufRef::dev(cp.run_ends, (uint64_t)nr * 4), std::move(values))});
+  }
+  for (auto& e : ext) {  // LabelAll (arrow_v2.go:555-564), in flag order
+    HostCol& hc = touched[e.first];
+    // ree.Append(rows - len): finishRun closes the previous run at len (already stored as its run
+    // end), then one run — possibly of length zero — covers [len, rows) with the external value
+    hc.run_ends.push_back((int32_t)N);
+    auto it = std::find(hc.dict.begin(), hc.dict.end(), e.second);
+    if (it == hc.dict.end()) { hc.dict.push_back(e.second); it = hc.dict.end() - 1; }
+    hc.idx.push_back((uint32_t)(it - hc.dict.begin()));
+    hc.valid.push_back(1);
+    hc.len = (int64_t)N;
+  }
+  for (auto& kv : touched) {
+    HostCol& hc = kv.second;
+    std::vector<std::pair<const uint8_t*, uint32_t>> strs;
+    for (auto& s : hc.dict) strs.emplace_back((const uint8_t*)s.data(), (uint32_t)s.size());
+    Node dictv = utf8_node(a, "values", true, strs);
+    int64_t nulls = 0;
+    std::vector<uint8_t> bits((hc.valid.size() + 7) / 8, 0);
+    for (size_t k = 0; k < hc.valid.size(); k++) { if (hc.valid[k]) bits[k >> 3] |= (uint8_t)(1u << (k & 7)); else nulls++; }
+    BufRef vref = BufRef::none();
+    if (nulls) { auto& kb = keep(a, std::move(bits)); vref = BufRef::host(kb.data(), kb.size()); }
+    Node values = dict_node("values", true, (int64_t)hc.idx.size(), nulls, vref, host_ref(a, hc.idx), std::move(dictv));
+    labels.push_back(LabelOut{kv.first, ree_node(kv.first, true, (int64_t)N, (int64_t)hc.run_ends.size(), host_ref(a, hc.run_ends), std::move(values))});
+  }
+  std::sort(labels.begin(), labels.end(), [](const LabelOut& x, const LabelOut& y) { return x.name < y.name; });
+
+  std::vector<Node> cols;
+  {
+    Node ln; ln.ty = Ty::Struct; ln.name = "labels"; ln.nullable = false; ln.length = (int64_t)N;
+    for (auto& l : labels) ln.kids.push_back(std::move(l.node));
+    cols.push_back(std::move(ln));
+  }
+
+  // ---- stacktrace: ListView<Dict<u32, Location>> (arrow_v2.go:345-481)
+  {
+    // function dictionary values
+    std::vector<uint8_t> views((size_t)n_fn * 16, 0), fvalid(n_fn, 1);
+    std::vector<std::vector<uint8_t>> blocks;  // StringView data blocks: 32 KiB, first block with room wins
+    std::vector<size_t> bcap;
+    size_t cur = 0;
+    int64_t sys_nulls = 0;
+    for (uint32_t k = 0; k < n_fn; k++) {
+      uint32_t sys = a->ft.fn_sys_cid[ord_fn[k]];
+      if (sys == kNoId) { fvalid[k] = 0; sys_nulls++; continue; }
+      const uint8_t* p = sp.ptr(sys);
+      int32_t len = (int32_t)sp.len(sys);
+      uint8_t* v = views.data() + (size_t)k * 16;
+      memcpy(v, &len, 4);
+      if (len <= 12) { memcpy(v + 4, p, (size_t)len); continue; }
+      size_t need = (size_t)len;
+      auto fresh = [&] { size_t cap = std::max<size_t>(need, 32 << 10); cap = (cap + 63) & ~(size_t)63; blocks.emplace_back(); blocks.back().reserve(cap); bcap.push_back(cap); cur = blocks.size() - 1; };
+      if (blocks.empty()) fresh();
+      else if (need > bcap[cur] - blocks[cur].size()) {
+        bool found = false;
+        for (size_t b = 0; b < blocks.size(); b++) if (need <= bcap[b] - blocks[b].size()) { cur = b; found = true; break; }
+        if (!found) fresh();
+      }
+      int32_t bi = (int32_t)cur, of = (int32_t)blocks[cur].size();
+      memcpy(v + 4, p, 4); memcpy(v + 8, &bi, 4); memcpy(v + 12, &of, 4);
+      blocks[cur].insert(blocks[cur].end(), p, p + len);
+    }
+    Node sysn; sysn.ty = Ty::Utf8View; sysn.name = "system_name"; sysn.nullable = true; sysn.length = n_fn; sysn.null_count = sys_nulls;
+    if (sys_nulls) {
+      std::vector<uint8_t> bits((n_fn + 7) / 8, 0);
+      for (uint32_t k = 0; k < n_fn; k++) if (fvalid[k]) bits[k >> 3] |= (uint8_t)(1u << (k & 7));
+      auto& kb = keep(a, std::move(bits)); sysn.validity = BufRef::host(kb.data(), kb.size());
+    }
+    { auto& kv = keep(a, std::move(views)); sysn.bufs.push_back(BufRef::host(kv.data(), kv.size())); }
+    for (auto& b : blocks) { size_t n = b.size(); auto& kb = keep(a, std::move(b)); sysn.bufs.push_back(BufRef::host(kb.data(), n)); }
+    Node filen = dict_node("filename", true, n_fn, c.null_file, BufRef::dev(a->sd_valid[3], (n_fn + 7) / 8), BufRef::dev(a->sd_keys[3], (uint64_t)n_fn * 4),
+                           utf8_node(a, "filename", true, strs_of(ord_file)));
+    Node fstruct; fstruct.ty = Ty::Struct; fstruct.name = "function"; fstruct.length = n_fn;
+    fstruct.kids.push_back(std::move(sysn));
+    fstruct.kids.push_back(std::move(filen));
+    fstruct.kids.push_back(int_node("start_line", 64, false, false, n_fn, BufRef::zeros((uint64_t)n_fn * 8)));
+    Node fdict = dict_node("function", false, n_lines, 0, BufRef::none(), BufRef::dev(a->fn_keys, (uint64_t)n_lines * 4), std::move(fstruct));
+
+    Node lstruct; lstruct.ty = Ty::Struct; lstruct.name = "item"; lstruct.nullable = true; lstruct.length = n_lines;
+    lstruct.kids.push_back(int_node("line", 64, false, false, n_lines, BufRef::dev(a->lo.line_no, (uint64_t)n_lines * 8)));
+    lstruct.kids.push_back(int_node("column", 64, false, false, n_lines, BufRef::zeros((uint64_t)n_lines * 8)));
+    lstruct.kids.push_back(std::move(fdict));
+    Node lines; lines.ty = Ty::ListView; lines.name = "lines"; lines.nullable = true; lines.length = n_loc; lines.null_count = (int64_t)n_loc - n_lines;
+    lines.validity = BufRef::dev(a->lo.line_valid, (n_loc + 7) / 8);
+    lines.bufs = {BufRef::dev(a->lo.line_off, (uint64_t)n_loc * 4), BufRef::dev(a->lo.line_size, (uint64_t)n_loc * 4)};
+    lines.kids.push_back(std::move(lstruct));
+
+    Node loc; loc.ty = Ty::Struct; loc.name = "item"; loc.nullable = true; loc.length = n_loc;
+    loc.kids.push_back(int_node("address", 64, false, false, n_loc, BufRef::dev(a->lo.address, (uint64_t)n_loc * 8)));
+    loc.kids.push_back(dict_node("frame_type", true, n_loc, 0, BufRef::none(), BufRef::dev(a->sd_keys[0], (uint64_t)n_loc * 4), utf8_node(a, "frame_type", true, strs_of(ord_type))));
+    loc.kids.push_back(dict_node("mapping_file", true, n_loc, 0, BufRef::none(), BufRef::dev(a->sd_keys[1], (uint64_t)n_loc * 4), utf8_node(a, "mapping_file", true, strs_of(ord_map))));
+    loc.kids.push_back(dict_node("mapping_build_id", true, n_loc, c.null_bid, BufRef::dev(a->sd_valid[2], (n_loc + 7) / 8), BufRef::dev(a->sd_keys[2], (uint64_t)n_loc * 4),
+                                 utf8_node(a, "mapping_build_id", true, strs_of(ord_bid))));
+    loc.kids.push_back(std::move(lines));
+    Node locd = dict_node("item", true, n_idx, 0, BufRef::none(), BufRef::dev(a->d_ustream.p, (uint64_t)n_idx * 4), std::move(loc));
+    Node st; st.ty = Ty::ListView; st.name = "stacktrace"; st.nullable = true; st.length = (int64_t)N;
+    st.bufs = {BufRef::dev(a->d_stoff.p, N * 4), BufRef::dev(a->d_stsize.p, N * 4)};
+    st.kids.push_back(std::move(locd));
+    cols.push_back(std::move(st));
+  }
+  {
+    Node id; id.ty = Ty::FixedBinary; id.name = "stacktrace_id"; id.byte_width = 16; id.length = (int64_t)N; id.bufs = {BufRef::dev(a->d_uuid.p, N * 16)};
+    id.metadata = {{"ARROW:extension:name", "arrow.uuid"}, {"ARROW:extension:metadata", ""}};
+    cols.push_back(std::move(id));
+  }
+  cols.push_back(int_node("value", 64, true, false, (int64_t)N, BufRef::dev(a->d_value.p, N * 8)));
+  // constant-ish columns: values per run built from the class of each run
+  static const char* fixed_names[6] = {"producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality"};
+  auto ree_run_ends = [&](uint32_t t) { return BufRef::dev(a->cols[nlab + t].run_ends, (uint64_t)c.n_runs[nlab + t] * 4); };
+  auto string_col = [&](uint32_t t) {
+    const auto& keys = kind_keys[t];
+    std::vector<std::pair<const uint8_t*, uint32_t>> strs;
+    std::vector<uint8_t> valid(keys.size(), 1);
+    for (size_t i = 0; i < keys.size(); i++) {
+      if (keys[i] == kNull) { valid[i] = 0; strs.emplace_back(nullptr, 0); continue; }
+      const std::string& s = a->kind_strings[t][keys[i]];
+      strs.emplace_back((const uint8_t*)s.data(), (uint32_t)s.size());
+    }
+    return ree_node(fixed_names[t], t == 5, (int64_t)N, (int64_t)keys.size(), ree_run_ends(t), utf8_node(a, "values", true, strs, &valid));
+  };
+  for (uint32_t t = 0; t < 6; t++) cols.push_back(string_col(t));
+  {
+    std::vector<int64_t> pv; for (uint32_t k : kind_keys[6]) pv.push_back(a->period_vals[k]);
+    std::vector<uint64_t> dv; for (uint32_t k : kind_keys[7]) dv.push_back(a->duration_vals[k]);
+    cols.push_back(ree_node("period", false, (int64_t)N, (int64_t)pv.size(), ree_run_ends(6), int_node("values", 64, true, true, (int64_t)pv.size(), host_ref(a, pv))));
+    cols.push_back(ree_node("duration", false, (int64_t)N, (int64_t)dv.size(), ree_run_ends(7), int_node("values", 64, false, true, (int64_t)dv.size(), host_ref(a, dv))));
+  }
+  {
+    Node ts; ts.ty = Ty::TimestampNsUtc; ts.name = "timestamp"; ts.length = (int64_t)N; ts.bufs = {BufRef::dev(a->d_ts.p, N * 8)};
+    cols.push_back(std::move(ts));
+  }
+
+  // ---- plan the stream and fill it
+  StreamPlan plan;
+  plan.build(cols, {{"parca_write_schema_version", "v2"}}, (int64_t)N);
+  if (plan.total > a->out_cap) {
+    if (a->out) cudaFreeHost(a->out);
+    a->out = nullptr;
+    a->out_cap = 0;
+    uint64_t want = plan.total + plan.total / 4 + 4096;
+    if (cudaHostAlloc((void**)&a->out, want, cudaHostAllocDefault) != cudaSuccess) return a->fail(PA_ENOMEM, "pinned output allocation failed");
+    a->out_cap = want;
+  }
+  double t1 = now_ms();
+  cudaEvent_t d0 = a->ev_d2h0, d1 = a->ev_d2h1;
+  CK(cudaEventRecord(d0, a->s_comp));
+  for (auto& p : plan.placements)
+    if (p.src.kind == BufRef::DEVICE && p.src.len) CK(cudaMemcpyAsync(a->out + p.at, p.src.ptr, p.src.len, cudaMemcpyDeviceToHost, a->s_comp));
+  CK(cudaEventRecord(d1, a->s_comp));
+  plan.write_host_parts(a->out);  // metadata, host-built buffers, zero fills and padding overlap the D2H
+  CK(cudaStreamSynchronize(a->s_comp));
+  double t2 = now_ms();
+  float d2h = 0, h2d = 0;
+  cudaEventElapsedTime(&d2h, d0, d1);
+  cudaEventElapsedTime(&h2d, a->ev_h2d0, a->ev_h2d1);
+  res->ipc = a->out; res->ipc_len = plan.total; res->n_rows = N; res->n_unique_stacks = c.n_unique; res->n_locations = n_loc;
+  res->n_functions = n_fn; res->n_location_indices = n_idx; res->gpu_launches = a->launches;
+  res->h2d_ms = h2d; res->gpu_ms = a->tm[T_TOTAL].ms; res->d2h_ms = d2h; res->host_ms = (t1 - t0) + (t2 - t1) - d2h;
+  a->staged = -1;
+  return PA_OK;
+}
+
+extern "C" {
+
+int pa_agg_stage(pa_agg* a) {
+  if (!a) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  int rc = stage_async(a);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(a->s_copy));
+  return PA_OK;
+}
+int pa_agg_process(pa_agg* a) {
+  if (!a) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  return process(a);
+}
+int pa_agg_collect(pa_agg* a, pa_agg_result* out) {
+  if (!a || !out) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  return collect(a, out);
+}
+int pa_agg_flush(pa_agg* a, pa_agg_result* out) {
+  if (!a || !out) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  int rc = stage_async(a);  // copies keep running while process() consumes the chunks already resident
+  if (rc) return rc;
+  rc = process(a);
+  if (rc) { cudaStreamSynchronize(a->s_copy); return rc; }
+  return collect(a, out);
+}
+void pa_agg_release(pa_agg* a, pa_agg_result* res) {
+  if (!a || !res) return;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  a->hostbufs.clear();
+  memset(res, 0, sizeof *res);
+}
+int pa_agg_last_kernel_ms(const pa_agg* a, const char* name, double* ms, uint32_t* launches) {
+  if (!a || !name) return PA_EINVAL;
+  for (int t = 0; t < T_COUNT; t++)
+    if (!strcmp(name, kTimerNames[t])) {
+      if (ms) *ms = a->tm[t].ms;
+      if (launches) *launches = a->tm[t].launches;
+      return PA_OK;
+    }
+  return PA_EINVAL;
+}
+int pa_agg_debug_stack_ids(pa_agg* a, uint8_t* out, uint64_t n_rows) {
+  if (!a || !out || n_rows > a->N) return PA_EINVAL;
+  CK(cudaSetDevice(a->device));
+  CK(cudaMemcpy(out, a->d_uuid.p, n_rows * 16, cudaMemcpyDeviceToHost));
+  return PA_OK;
+}
+int pa_agg_debug_stack_counts(pa_agg* a, uint32_t* out, uint64_t n) {
+  if (!a || !out || n > a->h_ctr.n_unique) return PA_EINVAL;
+  CK(cudaSetDevice(a->device));
+  CK(cudaMemcpy(out, a->d_uniq_count.p, n * 4, cudaMemcpyDeviceToHost));
+  return PA_OK;
+}
+
+// ---- host helpers ------------------------------------------------------------------------------
+static bool valid_utf8(const uint8_t* s, uint64_t n) {  // unicode/utf8.ValidString
+  uint64_t i = 0;
+  while (i < n) {
+    uint8_t b = s[i];
+    if (b < 0x80) { i++; continue; }
+    int extra; uint32_t cp, lo;
+    if (b >= 0xC2 && b <= 0xDF) { extra = 1; cp = b & 0x1Fu; lo = 0x80; }
+    else if (b >= 0xE0 && b <= 0xEF) { extra = 2; cp = b & 0x0Fu; lo = 0x800; }
+    else if (b >= 0xF0 && b <= 0xF4) { extra = 3; cp = b & 0x07u; lo = 0x10000; }
+    else return false;
+    if (i + (uint64_t)extra >= n) return false;
+    for (int k = 1; k <= extra; k++) {
+      uint8_t cb = s[i + k];
+      if ((cb & 0xC0) != 0x80) return false;
+      cp = (cp << 6) | (cb & 0x3Fu);
+    }
+    if (cp < lo || cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) return false;
+    i += (uint64_t)extra + 1;
+  }
+  return true;
+}
+// maybeFixTruncation, reporter/parca_reporter.go:190-216
+int64_t pa_fix_truncation(const uint8_t* s, uint64_t len, uint64_t max_len) {
+  if (valid_utf8(s, len)) return (int64_t)len;
+  if (len != max_len) return -1;
+  for (uint64_t back = 1; back <= 2 && back <= len; back++) {
+    uint64_t idx = max_len - back;
+    if ((s[idx] & 0xC0) != 0x80) return valid_utf8(s, idx) ? (int64_t)idx : -1;
+  }
+  return -1;
+}
+uint64_t pa_xxh64(const void* data, uint64_t len, uint64_t seed) {
+  const uint8_t* p = (const uint8_t*)data;
+  const uint8_t* const end = p + len;
+  auto rd64 = [](const uint8_t* q) { uint64_t v; memcpy(&v, q, 8); return v; };
+  auto rot = [](uint64_t x, int r) { return (x << r) | (x >> (64 - r)); };
+  const uint64_t P1 = 11400714785074694791ULL, P2 = 14029467366897019727ULL, P3 = 1609587929392839161ULL, P4 = 9650029242287828579ULL, P5 = 2870177450012600261ULL;
+  uint64_t h;
+  if (len >= 32) {
+    uint64_t v[4] = {seed + P1 + P2, seed + P2, seed, seed - P1};
+    for (; p + 32 <= end; p += 32)
+      for (int k = 0; k < 4; k++) v[k] = rot(v[k] + rd64(p + 8 * k) * P2, 31) * P1;
+    h = rot(v[0], 1) + rot(v[1], 7) + rot(v[2], 12) + rot(v[3], 18);
+    for (int k = 0; k < 4; k++) h = (h ^ (rot(v[k] * P2, 31) * P1)) * P1 + P4;
+  } else {
+    h = seed + P5;
+  }
+  h += len;
+  for (; p + 8 <= end; p += 8) h = rot(h ^ (rot(rd64(p) * P2, 31) * P1), 27) * P1 + P4;
+  if (p + 4 <= end) { uint32_t w; memcpy(&w, p, 4); h = rot(h ^ (w * P1), 23) * P2 + P3; p += 4; }
+  for (; p < end; p++) h = rot(h ^ (*p * P5), 11) * P1;
+  h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+  return h;
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+"""ctypes binding of libparcaagg.so (include/parcaagg.h) — the product's only compute path.
+
+There is deliberately no CPU fallback: if the CUDA library is missing or no device is usable,
+importing/constructing fails loudly. Nothing here imports the test oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libparcaagg.so")
+_LIB = None
+
+EXPORTS = [
+    "pa_agg_create", "pa_agg_destroy", "pa_agg_last_error", "pa_agg_abi_version", "pa_agg_register_strings",
+    "pa_agg_register_frames", "pa_agg_register_labelsets", "pa_agg_acquire", "pa_agg_commit", "pa_agg_submit",
+    "pa_agg_flush", "pa_agg_release", "pa_agg_stage", "pa_agg_process", "pa_agg_collect", "pa_agg_last_kernel_ms",
+    "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_fix_truncation", "pa_xxh64",
+]
+
+
+class PaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libparcaagg error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libparcaagg.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                               "there is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, u32p, u64p = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+        L.pa_agg_create.argtypes = [C.POINTER(abi.PaAggConfig), C.POINTER(vp)]
+        L.pa_agg_destroy.argtypes = [vp]
+        L.pa_agg_destroy.restype = None
+        L.pa_agg_last_error.argtypes = [vp]
+        L.pa_agg_last_error.restype = C.c_char_p
+        L.pa_agg_abi_version.restype = C.c_uint32
+        L.pa_agg_register_strings.argtypes = [vp, C.c_char_p, vp, C.c_uint32, u32p]
+        L.pa_agg_register_frames.argtypes = [vp, vp, C.c_uint32, u64p]
+        L.pa_agg_register_labelsets.argtypes = [vp, vp, vp, C.c_uint32, u32p]
+        L.pa_agg_acquire.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(vp), C.POINTER(vp), u64p]
+        L.pa_agg_commit.argtypes = [vp, C.c_uint64]
+        L.pa_agg_submit.argtypes = [vp, vp, vp, C.c_uint64]
+        L.pa_agg_flush.argtypes = [vp, C.POINTER(abi.PaAggResult)]
+        L.pa_agg_release.argtypes = [vp, C.POINTER(abi.PaAggResult)]
+        L.pa_agg_release.restype = None
+        L.pa_agg_stage.argtypes = [vp]
+        L.pa_agg_process.argtypes = [vp]
+        L.pa_agg_collect.argtypes = [vp, C.POINTER(abi.PaAggResult)]
+        L.pa_agg_last_kernel_ms.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), u32p]
+        L.pa_agg_debug_stack_ids.argtypes = [vp, vp, C.c_uint64]
+        L.pa_agg_debug_stack_counts.argtypes = [vp, vp, C.c_uint64]
+        L.pa_fix_truncation.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64]
+        L.pa_fix_truncation.restype = C.c_int64
+        L.pa_xxh64.argtypes = [vp, C.c_uint64, C.c_uint64]
+        L.pa_xxh64.restype = C.c_uint64
+        _LIB = L
+    return _LIB
+
+
+class Result:
+    """One flushed batch. `ipc` is a zero-copy view of library-owned pinned memory, valid until the next flush."""
+
+    def __init__(self, raw):
+        self.n_rows = int(raw.n_rows)
+        self.n_unique_stacks = int(raw.n_unique_stacks)
+        self.n_locations = int(raw.n_locations)
+        self.n_functions = int(raw.n_functions)
+        self.n_location_indices = int(raw.n_location_indices)
+        self.gpu_launches = int(raw.gpu_launches)
+        self.h2d_ms, self.gpu_ms, self.d2h_ms, self.host_ms = raw.h2d_ms, raw.gpu_ms, raw.d2h_ms, raw.host_ms
+        n = int(raw.ipc_len)
+        self.ipc_len = n
+        self.ipc = np.ctypeslib.as_array(raw.ipc, shape=(n,)) if n else np.zeros(0, np.uint8)
+
+    def ipc_bytes(self):
+        return self.ipc.tobytes()
+
+
+class Aggregator:
+    """Thin object wrapper over one pa_agg handle."""
+
+    def __init__(self, device=0, hash_mode=abi.PA_HASH_XXH64X2, label_flags=0, samples_per_second=19, external_labels=(),
+                 max_samples=1 << 20, max_frames=0, chunk_samples=0):
+        L = lib()
+        ext = (abi.PaLabelPair * max(1, len(external_labels)))()
+        for i, (n, v) in enumerate(external_labels):
+            ext[i].name_sid, ext[i].value_sid = int(n), int(v)
+        cfg = abi.PaAggConfig(abi_version=abi.PA_ABI_VERSION, device=device, hash_mode=hash_mode, label_flags=label_flags,
+                              samples_per_second=samples_per_second, n_external_labels=len(external_labels), external_labels=ext,
+                              max_samples=max_samples, max_frames=max_frames, chunk_samples=chunk_samples)
+        h = C.c_void_p()
+        rc = L.pa_agg_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise PaError(rc, "pa_agg_create failed (no CUDA device, bad config or out of memory)")
+        self.h = h
+        self.max_samples = max_samples
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PaError(rc, (lib().pa_agg_last_error(self.h) or b"").decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pa_agg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- registration
+    def register_strings(self, strs):
+        blob, offs = abi.pack_strings(list(strs))
+        first = C.c_uint32()
+        self._ck(lib().pa_agg_register_strings(self.h, blob, offs.ctypes.data, len(strs), C.byref(first)))
+        return first.value
+
+    def register_frames(self, descs):
+        descs = np.ascontiguousarray(descs, dtype=abi.FRAME_DTYPE)
+        first = C.c_uint64()
+        self._ck(lib().pa_agg_register_frames(self.h, descs.ctypes.data, len(descs), C.byref(first)))
+        return first.value
+
+    def register_labelsets(self, labelsets):
+        pairs, offs = abi.pack_labelsets(labelsets)
+        first = C.c_uint32()
+        self._ck(lib().pa_agg_register_labelsets(self.h, pairs.ctypes.data, offs.ctypes.data, len(labelsets), C.byref(first)))
+        return first.value
+
+    # ---- ingest
+    def submit(self, hdrs, frame_ids):
+        hdrs = np.ascontiguousarray(hdrs, dtype=abi.HDR_DTYPE)
+        frame_ids = np.ascontiguousarray(frame_ids, dtype=np.uint64)
+        self._keep = (hdrs, frame_ids)
+        self._ck(lib().pa_agg_submit(self.h, hdrs.ctypes.data, frame_ids.ctypes.data, len(hdrs)))
+
+    def acquire(self, n_rows, n_frames):
+        """Reserve ring space; returns (hdr view, frame-id view, frame_base). Write, then commit()."""
+        ph, pf, base = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._ck(lib().pa_agg_acquire(self.h, n_rows, n_frames, C.byref(ph), C.byref(pf), C.byref(base)))
+        hv = np.ctypeslib.as_array(C.cast(ph, C.POINTER(C.c_uint8)), shape=(max(n_rows, 1) * 64,))[:n_rows * 64].view(abi.HDR_DTYPE)
+        fv = np.ctypeslib.as_array(C.cast(pf, C.POINTER(C.c_uint64)), shape=(max(n_frames, 1),))[:n_frames]
+        return hv, fv, base.value
+
+    def commit(self, n_rows):
+        self._ck(lib().pa_agg_commit(self.h, n_rows))
+
+    # ---- flush and its three stages
+    def _result(self, fn):
+        raw = abi.PaAggResult()
+        self._ck(fn(self.h, C.byref(raw)))
+        return Result(raw)
+
+    def flush(self):
+        return self._result(lib().pa_agg_flush)
+
+    def stage(self):
+        self._ck(lib().pa_agg_stage(self.h))
+
+    def process(self):
+        self._ck(lib().pa_agg_process(self.h))
+
+    def collect(self):
+        return self._result(lib().pa_agg_collect)
+
+    def kernel_ms(self, name):
+        ms, n = C.c_double(), C.c_uint32()
+        self._ck(lib().pa_agg_last_kernel_ms(self.h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def debug_stack_ids(self, n_rows):
+        out = np.zeros((n_rows, 16), dtype=np.uint8)
+        self._ck(lib().pa_agg_debug_stack_ids(self.h, out.ctypes.data, n_rows))
+        return out
+
+    def debug_stack_counts(self, n):
+        out = np.zeros(n, dtype=np.uint32)
+        self._ck(lib().pa_agg_debug_stack_counts(self.h, out.ctypes.data, n))
+        return out
+
+
+def from_workload(w, device=0, max_samples=None, max_frames=None, chunk_samples=0):
+    """Aggregator with the workload's dictionaries registered (string id 0 == "" is implicit)."""
+    n = max(1, w.n if max_samples is None else max_samples)
+    nf = max(1, w.n_frame_ids if max_frames is None else max_frames)
+    a = Aggregator(device=device, hash_mode=w.hash_mode, label_flags=w.label_flags, samples_per_second=w.samples_per_second,
+                   external_labels=w.external_labels, max_samples=n, max_frames=nf, chunk_samples=chunk_samples)
+    first = a.register_strings(w.strings[1:])
+    assert first == 1, first
+    a.register_frames(w.frames)
+    a.register_labelsets(w.labelsets)
+    return a
+
+
+def load(a, w):
+    """Write the workload's rows straight into the pinned ring (no intermediate copy of the frame stream)."""
+    hv, fv, base = a.acquire(w.n, w.n_frame_ids)
+    hv[:] = w.hdrs
+    if base:
+        hv["frame_off"] += np.uint64(base)
+    if w.n_frame_ids:
+        w.write_frames(fv)
+    a.commit(w.n)
+
+
+def run(w, device=0, chunk_samples=0):
+    """Whole-batch convenience used by tests: returns (ipc bytes, Result)."""
+    a = from_workload(w, device=device, chunk_samples=chunk_samples)
+    load(a, w)
+    r = a.flush()
+    data = r.ipc_bytes()
+    a.close()
+    return data, r
+
+
+def fix_truncation(s, max_len):
+    n = lib().pa_fix_truncation(s, len(s), max_len)
+    return (None, False) if n < 0 else (s[:n], True)
+
+
+def xxh64(data, seed=0):
+    buf = (C.c_char * len(data)).from_buffer_copy(data) if data else None
+    return int(lib().pa_xxh64(buf, len(data), seed))
