@@ -565,14 +565,14 @@ static int process_once(pa_agg* a) {
     k_header<<<std::max(hb, 1), kThreads, 0, s>>>(h);
     a->tm[T_HEADER].launches++;
   };
-  auto launch_hash = [&](size_t k) {
+  auto launch_hash = [&](uint64_t r0, uint64_t r1) {
     HashArgs ha{};
     ha.frames = a->d_frames.as<unsigned long long>(); ha.frame_off = a->d_foff.as<unsigned long long>(); ha.nframes = a->d_nfr.as<uint16_t>();
-    ha.row0 = (uint32_t)a->chunk_rows[k].first; ha.row1 = (uint32_t)a->chunk_rows[k].second; ha.uuid = a->d_uuid.as<uint8_t>();
+    ha.row0 = (uint32_t)r0; ha.row1 = (uint32_t)r1; ha.uuid = a->d_uuid.as<uint8_t>();
     ha.slot_of_row = a->d_slot.as<uint32_t>(); ha.tab = tab; ha.mask = mask; ha.ctr = ctr;
-    uint32_t rows = ha.row1 - ha.row0;
-    int blocks = (int)std::min<uint64_t>(((uint64_t)rows * 4 + kThreads - 1) / kThreads, (uint64_t)a->sms * 8);
-    k_hash_insert_direct<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
+    uint64_t rows = r1 - r0;
+    int blocks = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)a->sms * 3);
+    k_hash_insert<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     a->tm[T_HASH].launches++;
   };
   CK(cudaEventRecord(a->tm[T_HEADER].a, s));
@@ -580,13 +580,13 @@ static int process_once(pa_agg* a) {
     for (size_t k = 0; k < a->chunk_rows.size(); k++) launch_header(k);
     CK(cudaEventRecord(a->tm[T_HEADER].b, s));
     CK(cudaEventRecord(a->tm[T_HASH].a, s));
-    if (!provided) for (size_t k = 0; k < a->chunk_rows.size(); k++) launch_hash(k);
+    if (!provided) launch_hash(0, N);  // whole resident batch in one persistent launch
     CK(cudaEventRecord(a->tm[T_HASH].b, s));
   } else {
     for (size_t k = 0; k < a->chunk_rows.size(); k++) {
       CK(cudaStreamWaitEvent(s, a->chunk_ev[k], 0));
       launch_header(k);
-      if (!provided) launch_hash(k);
+      if (!provided) launch_hash(a->chunk_rows[k].first, a->chunk_rows[k].second);
     }
     CK(cudaEventRecord(a->tm[T_HEADER].b, s));
   }

@@ -310,6 +310,85 @@ __global__ void __launch_bounds__(kThreads) k_hash_insert_direct(HashArgs a) {
   }
 }
 
+// Variant B (default): one warp-iteration covers 32 consecutive samples. The XXH64 rounds still run
+// with 4 lanes per sample (8 samples at a time, 4 sub-iterations), but the per-sample epilogue —
+// accumulator merge, avalanche, 16-byte id store, table insert — runs once with one *thread per
+// sample* after a shuffle transpose, so its cost is amortised over 32 samples instead of 8 and
+// the id store / slot store are fully coalesced (512 B / 128 B per warp).
+__device__ __forceinline__ unsigned long long xxh_finish_own(const unsigned long long (&v)[4], unsigned long long seed, uint32_t n,
+                                                             unsigned long long t0, unsigned long long t1, unsigned long long t2) {
+  unsigned long long h;
+  if (n >= 4) {
+    h = rotl64(v[0], 1) + rotl64(v[1], 7) + rotl64(v[2], 12) + rotl64(v[3], 18);
+    h = xxh_merge(h, v[0]); h = xxh_merge(h, v[1]); h = xxh_merge(h, v[2]); h = xxh_merge(h, v[3]);
+  } else {
+    h = seed + XP5;
+  }
+  h += (unsigned long long)n * 8ull;
+  uint32_t t = n & 3u;
+  if (t > 0) { h ^= rotl64(t0 * XP2, 31) * XP1; h = rotl64(h, 27) * XP1 + XP4; }
+  if (t > 1) { h ^= rotl64(t1 * XP2, 31) * XP1; h = rotl64(h, 27) * XP1 + XP4; }
+  if (t > 2) { h ^= rotl64(t2 * XP2, 31) * XP1; h = rotl64(h, 27) * XP1 + XP4; }
+  return xxh_avalanche(h);
+}
+
+__global__ void __launch_bounds__(kThreads, 3) k_hash_insert(HashArgs a) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, j = lane & 3, g = lane >> 2;
+  const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+  const uint32_t span = a.row1 - a.row0;
+  const uint32_t iters = (span + nwarps * 32 - 1) / (nwarps * 32);
+  for (uint32_t it = 0; it < iters; it++) {
+    const uint32_t r = a.row0 + (it * nwarps + warp) * 32 + lane;  // the sample this lane finishes
+    const bool valid = r < a.row1;
+    const uint32_t n_me = valid ? a.nframes[r] : 0u;
+    const unsigned long long off_me = valid ? a.frame_off[r] : 0ull;
+    unsigned long long v0[4], v1[4];
+#pragma unroll
+    for (int sub = 0; sub < 4; sub++) {
+      const int src = sub * 8 + g;  // lane that owns the sample my 4-lane group hashes now
+      const uint32_t n = __shfl_sync(full, n_me, src);
+      const unsigned long long off = __shfl_sync(full, off_me, src);
+      const unsigned long long* q = a.frames + off + j;
+      unsigned long long a0 = xxh_lane_init(0ull, j), a1 = xxh_lane_init(kSeedLo, j);
+      const uint32_t ns = n >> 2;
+      uint32_t s = 0;
+      for (; s + 8 <= ns; s += 8) {  // 8 stripes = 8 independent 8-byte loads in flight per lane
+        unsigned long long w[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) w[u] = ldg_stream64(q + 4 * (s + u));
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          unsigned long long m = w[u] * XP2;
+          a0 = xxh_round_pre(a0, m);
+          a1 = xxh_round_pre(a1, m);
+        }
+      }
+      for (; s < ns; s++) {
+        unsigned long long m = ldg_stream64(q + 4 * s) * XP2;
+        a0 = xxh_round_pre(a0, m);
+        a1 = xxh_round_pre(a1, m);
+      }
+      __syncwarp(full);
+      // transpose: lane L (in octet `sub`) receives accumulator lane jj of sample L from lane 4*(L&7)+jj
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        unsigned long long x0 = __shfl_sync(full, a0, 4 * (lane & 7) + jj), x1 = __shfl_sync(full, a1, 4 * (lane & 7) + jj);
+        if ((lane >> 3) == sub) { v0[jj] = x0; v1[jj] = x1; }
+      }
+    }
+    const uint32_t nt = n_me & 3u;
+    const unsigned long long* tp = a.frames + off_me + (n_me & ~3u);
+    unsigned long long t0 = nt > 0 ? ldg_stream64(tp) : 0ull, t1 = nt > 1 ? ldg_stream64(tp + 1) : 0ull, t2 = nt > 2 ? ldg_stream64(tp + 2) : 0ull;
+    Key128 k;
+    k.hi = xxh_finish_own(v0, 0ull, n_me, t0, t1, t2);
+    k.lo = xxh_finish_own(v1, kSeedLo, n_me, t0, t1, t2);
+    if (valid) *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = make_ulonglong2(bswap64(k.hi), bswap64(k.lo));
+    uint32_t slot = warp_insert(a.tab, a.mask, k, r, valid, a.ctr);
+    if (valid) a.slot_of_row[r] = slot;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // block-wide exclusive scan (kThreads threads). T needs operator+ and a zero-initialised T().
 struct Pair { uint32_t cnt; unsigned long long fr; };
@@ -318,6 +397,8 @@ __device__ __forceinline__ uint32_t shfl_up_t(uint32_t v, int d) { return __shfl
 __device__ __forceinline__ Pair shfl_up_t(Pair v, int d) {
   return Pair{__shfl_up_sync(0xFFFFFFFFu, v.cnt, d), __shfl_up_sync(0xFFFFFFFFu, v.fr, d)};
 }
+__device__ __forceinline__ uint32_t shfl_idx_t(uint32_t v, int l) { return __shfl_sync(0xFFFFFFFFu, v, l); }
+__device__ __forceinline__ Pair shfl_idx_t(Pair v, int l) { return Pair{__shfl_sync(0xFFFFFFFFu, v.cnt, l), __shfl_sync(0xFFFFFFFFu, v.fr, l)}; }
 __device__ __forceinline__ uint32_t zero_of(uint32_t) { return 0u; }
 __device__ __forceinline__ Pair zero_of(Pair) { return Pair{0u, 0ull}; }
 
@@ -363,13 +444,28 @@ __global__ void __launch_bounds__(kThreads) k_scan_reduce(F f, typename F::T* pa
   if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = tot;
 }
 template <class F>
-__global__ void k_scan_partials(F f, typename F::T* partial, int g) {  // grid = njobs blocks, 32 threads
+__global__ void k_scan_partials(F f, typename F::T* partial, int g) {  // grid = njobs blocks, 32 threads: warp scan over the block totals
   typedef typename F::T T;
-  if (threadIdx.x != 0) return;
-  T run = zero_of(T());
   T* p = partial + (size_t)blockIdx.x * g;
-  for (int i = 0; i < g; i++) { T t = p[i]; p[i] = run; run = run + t; }
-  f.total(blockIdx.x, run);
+  int lane = threadIdx.x;
+  T run = zero_of(T());
+  for (int base = 0; base < g; base += 32) {
+    int i = base + lane;
+    T v = i < g ? p[i] : zero_of(T());
+    T inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      T o = shfl_up_t(inc, d);
+      if (lane >= d) inc = o + inc;
+    }
+    T ex = shfl_up_t(inc, 1);
+    if (lane == 0) ex = zero_of(T());
+    if (i < g) p[i] = run + ex;
+    T tot = inc;  // lane 31 holds the chunk total
+    tot = shfl_idx_t(tot, 31);
+    run = run + tot;
+  }
+  if (lane == 0) f.total(blockIdx.x, run);
 }
 template <class F>
 __global__ void __launch_bounds__(kThreads) k_scan_emit(F f, const typename F::T* partial) {
@@ -673,13 +769,22 @@ __global__ void __launch_bounds__(kThreads) k_ree_count(ReeArgs a) {
     if (s_last[threadIdx.x]) atomicMax(&a.ctr->last_nonnull_plus1[threadIdx.x], s_last[threadIdx.x]);
   }
 }
-__global__ void k_ree_scan_partials(ReeArgs a, int g) {  // grid = ncols
-  if (threadIdx.x != 0) return;
+__global__ void k_ree_scan_partials(ReeArgs a, int g) {  // grid = ncols, 32 threads
   uint32_t* p = a.partial + (size_t)blockIdx.x * g;
+  int lane = threadIdx.x;
   uint32_t run = 0;
-  for (int i = 0; i < g; i++) { uint32_t t = p[i]; p[i] = run; run += t; }
-  a.ctr->n_runs[blockIdx.x] = run;
-  if (run) a.cols[blockIdx.x].run_ends[run - 1] = (int)a.n_rows;  // the last run ends at the row count
+  for (int base = 0; base < g; base += 32) {
+    int i = base + lane;
+    uint32_t v = i < g ? p[i] : 0u, inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
+    if (i < g) p[i] = run + inc - v;
+    run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+  }
+  if (lane == 0) {
+    a.ctr->n_runs[blockIdx.x] = run;
+    if (run) a.cols[blockIdx.x].run_ends[run - 1] = (int)a.n_rows;  // the last run ends at the row count
+  }
 }
 __global__ void __launch_bounds__(kThreads) k_ree_emit(ReeArgs a) {
   __shared__ uint32_t s_base[kMaxCols];

@@ -215,23 +215,44 @@ def config3(n=10_000_000, hash_mode=abi.PA_HASH_XXH64X2, u=200_000, p=131_072, n
                           0.6, 0.0, "cuda", kind=abi.PA_KIND_CUDA, zipf=True, labelsets_per_pid=lsets, hash_mode=hash_mode)
 
 
-def config4_shard(rank, world, n_total=100_000_000, u=1_000_000, p=1_048_576, hash_mode=abi.PA_HASH_XXH64X2):
-    """Config 4 shard for one rank: samples whose xxh64(pid) mod world == rank, in arrival order.
+_M64 = (1 << 64) - 1
 
-    Each rank generates only its own ~n_total/world rows (same seed family; the pid population is
-    partitioned first so shards are disjoint by construction).
-    """
-    npids = 65_536
-    from .hostref import xxh64_u32  # host-side shard function (same as the library's)
+
+def xxh64_u32(x, seed=0):
+    """XXH64 of one little-endian uint32 (the pid shard key, north_star: shard = xxh64(pid) mod G)."""
+    p1, p2, p3, p5 = 11400714785074694791, 14029467366897019727, 1609587929392839161, 2870177450012600261
+    h = (seed + p5 + 4) & _M64
+    h ^= (x * p1) & _M64
+    h = ((((h << 23) | (h >> 41)) & _M64) * p2 + p3) & _M64
+    h ^= h >> 33
+    h = (h * p2) & _M64
+    h ^= h >> 29
+    h = (h * p3) & _M64
+    h ^= h >> 32
+    return h
+
+
+def _pid_shard(name, seed, rank, world, n, u, p, pids_per_rank, hash_mode):
+    """Rows of one rank: the pids with xxh64(pid) % world == rank, `n` samples drawn among them."""
+    npids = pids_per_rank * world
     owner = np.array([xxh64_u32(1000 + q) % world for q in range(npids)], dtype=np.int64)
     mine = np.nonzero(owner == rank)[0]
-    n = n_total // world
-    w = _uniform_batch("cfg4_shard%d_of_%d" % (rank, world), 0x5EED0004 + rank, n, 64, u, p, len(mine), 16, 192, 0.8, 0.1, "python",
+    w = _uniform_batch("%s_shard%d_of_%d" % (name, rank, world), seed + rank, n, 64, u, p, len(mine), 16, 192, 0.8, 0.1, "python",
                        hash_mode=hash_mode)
-    # remap local pid index → global pid so shards are disjoint in pid space
     local = (w.hdrs["pid"] - 1000).astype(np.int64)
-    w.hdrs["pid"] = 1000 + mine[local]
+    w.hdrs["pid"] = 1000 + mine[local]  # global pid space: shards are disjoint by construction
+    w.meta.update(rank=rank, world=world)
     return w
+
+
+def config2_shard(rank, world, n=10_000_000, hash_mode=abi.PA_HASH_XXH64X2):
+    """Weak-scaling shard of the headline config: every rank aggregates `n` samples of its own pids."""
+    return _pid_shard("cfg2", 0x5EED0002, rank, world, n, 100_000, 262_144, 4_096, hash_mode)
+
+
+def config4_shard(rank, world, n_total=100_000_000, hash_mode=abi.PA_HASH_XXH64X2):
+    """Config 4: 100M samples, 1M unique stacks, 65,536 pids sharded by xxh64(pid) mod world."""
+    return _pid_shard("cfg4", 0x5EED0004, rank, world, n_total // world, 1_000_000 // world * 2, 1_048_576, 65_536 // world, hash_mode)
 
 
 def edge_workload(seed=7, n=600, hash_mode=abi.PA_HASH_PROVIDED, label_flags=0, external=True):
