@@ -137,7 +137,7 @@ struct pa_agg {
   // ---- device batch buffers
   DBuf d_hdr, d_frames, d_ts, d_value, d_uuid, d_stoff, d_stsize, d_slot, d_kind, d_nfr, d_foff, d_ls, d_cpu, d_tid, d_comm;
   DBuf d_ustream, d_uniq_row, d_uniq_count, d_table, d_ctr, d_arena, d_partial;
-  uint64_t table_cap = 0, retry_cap = 0;
+  uint64_t table_cap = 0, retry_cap = 0, tid_cap = 0, retry_tcap = 0, prev_tids = 0;
   uint64_t prev_unique = 0;
   Counters h_ctr{};
   Counters* h_ctr_pinned = nullptr;
@@ -302,7 +302,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   need(a->d_ustream, std::min<uint64_t>(NF, 0x7FFFFFFFull) * 4 + 256);
   need(a->d_uniq_row, N * 4); need(a->d_uniq_count, N * 4);
   need(a->d_ctr, sizeof(Counters));
-  need(a->d_partial, (uint64_t)a->G * kMaxCols * sizeof(Pair) + 256);
+  need(a->d_partial, (uint64_t)a->G * kWarps * kMaxCols * sizeof(uint32_t) + (uint64_t)a->G * kMaxCols * 16 + 256);
   if (!ok) return bail(PA_ENOMEM);
   *out = a;
   return PA_OK;
@@ -485,54 +485,68 @@ static int process_once(pa_agg* a) {
   cudaStream_t s = a->s_comp;
   for (int t = 0; t < T_COUNT; t++) { a->tm[t].launches = 0; a->tm[t].ms = 0; }
 
-  // ---- stack table capacity: 2x an upper bound on this batch's unique stacks
+  // ---- stack table capacity: 2x an upper bound on this batch's unique stacks (adaptive, retried on overflow)
   uint64_t bound = N;
   if (a->prev_unique && N > (1u << 20)) bound = std::min<uint64_t>(N, std::max<uint64_t>(a->prev_unique * 4, 1u << 20));
   uint64_t cap = std::max<uint64_t>(pow2_at_least(2 * std::max<uint64_t>(bound, 1)), 1024);
-  if (cap < a->retry_cap) cap = a->retry_cap;  // grown by an overflow retry of this batch
+  if (cap < a->retry_cap) cap = a->retry_cap;
   a->table_cap = cap;
   CK(a->d_table.ensure((cap + 2) * sizeof(StackSlot)));
+  // thread_id dictionary table (hashed): same policy
+  uint64_t tbound = N;
+  if (a->prev_tids && N > (1u << 18)) tbound = std::min<uint64_t>(N, std::max<uint64_t>(a->prev_tids * 4, 1u << 16));
+  uint64_t tcap = std::max<uint64_t>(pow2_at_least(2 * std::max<uint64_t>(tbound, 16)), 1024);
+  if (tcap < a->retry_tcap) tcap = a->retry_tcap;
+  a->tid_cap = tcap;
+  a->tid_mask = (uint32_t)(tcap - 1);
 
-  // ---- arena: per-flush scratch and small output buffers
-  struct Req { void** pp; size_t bytes; bool ff; };
+  // ---- arena: per-flush scratch and small output buffers; three classes (0xFF / zero / uninitialised)
+  struct Req { void** pp; size_t bytes; int cls; };
   std::vector<Req> reqs;
-  auto want = [&reqs](auto** pp, size_t bytes, bool ff = false) { reqs.push_back(Req{(void**)pp, (bytes + 255) & ~(size_t)255, ff}); };
+  auto want = [&reqs](auto** pp, size_t bytes, int cls = 2) { reqs.push_back(Req{(void**)pp, (bytes + 255) & ~(size_t)255, cls}); };
   const size_t P = std::max<uint32_t>(n_frames, 1), S = std::max<uint32_t>(n_cstr, 1), FN = std::max<uint32_t>(n_funcs, 1);
-  want(&a->loc_first, P * 4, true); want(&a->loc_rank, P * 4); want(&a->loc_order, P * 4);
+  const size_t NI = (size_t)std::min<uint64_t>(std::max<uint64_t>(a->NF, 1), 0x7FFFFFFFull);
+  const size_t Nn = (size_t)std::max<uint64_t>(N, 1);
+  uint32_t *rowbits = nullptr, *row_wprefix = nullptr, *uniq_slot = nullptr, *uniq_size = nullptr;
+  want(&rowbits, (Nn / 32 + 2) * 4, 1); want(&row_wprefix, (Nn / 32 + 2) * 4); want(&uniq_slot, Nn * 4); want(&uniq_size, Nn * 4);
+  uint32_t *loc_bits = nullptr, *loc_wp = nullptr;
+  want(&a->loc_first, P * 4, 0); want(&a->loc_rank, P * 4); want(&a->loc_order, P * 4);
+  want(&loc_bits, (NI / 32 + 2) * 4); want(&loc_wp, (NI / 32 + 2) * 4);
+  uint32_t *sd_bits[4] = {}, *sd_wp[4] = {}, *fn_bits = nullptr, *fn_wp = nullptr;
   for (int d = 0; d < 4; d++) {
     size_t n = d == 3 ? FN : P;
-    want(&a->sd_first[d], S * 4, true); want(&a->sd_rank[d], S * 4); want(&a->sd_order[d], S * 4);
+    want(&a->sd_first[d], S * 4, 0); want(&a->sd_rank[d], S * 4); want(&a->sd_order[d], S * 4);
     want(&a->sd_keys[d], n * 4); want(&a->sd_valid[d], (n / 32 + 2) * 4);
+    want(&sd_bits[d], (n / 32 + 2) * 4); want(&sd_wp[d], (n / 32 + 2) * 4);
   }
-  want(&a->fn_first, FN * 4, true); want(&a->fn_rank, FN * 4); want(&a->fn_order, FN * 4); want(&a->fn_keys, P * 4);
+  want(&a->fn_first, FN * 4, 0); want(&a->fn_rank, FN * 4); want(&a->fn_order, FN * 4); want(&a->fn_keys, P * 4);
+  want(&fn_bits, (P / 32 + 2) * 4); want(&fn_wp, (P / 32 + 2) * 4);
   want(&a->lo.address, P * 8); want(&a->lo.line_off, P * 4); want(&a->lo.line_size, P * 4); want(&a->lo.line_valid, (P / 32 + 2) * 4);
   want(&a->lo.line_no, P * 8);
-  a->tid_mask = (uint32_t)pow2_at_least(2 * std::max<uint64_t>(N, 16)) - 1;
-  std::vector<uint32_t*> col_first(ncols, nullptr), col_rank(ncols, nullptr);
+  std::vector<uint32_t*> col_first(ncols, nullptr), col_rank(ncols, nullptr), col_bits(ncols, nullptr), col_wp(ncols, nullptr);
   for (uint32_t c = 0; c < ncols; c++) {
     ColPlan& cp = a->cols[c];
-    want(&cp.run_ends, std::max<uint64_t>(N, 1) * 4);
-    want(&cp.run_keys, std::max<uint64_t>(N, 1) * 4);
+    want(&cp.run_ends, Nn * 4);
+    want(&cp.run_keys, Nn * 4);
     if (c >= nlab) continue;
-    want(&cp.validity, (N / 32 + 2) * 4);
+    want(&cp.validity, (Nn / 32 + 2) * 4);
+    want(&col_bits[c], (Nn / 32 + 2) * 4); want(&col_wp[c], (Nn / 32 + 2) * 4);
     if (cp.type == COL_COMM) cp.universe = n_cstr;
     if (cp.type == COL_TID) {
-      want(&a->tid_slots, ((size_t)a->tid_mask + 1) * 8, true);
-      want(&a->tid_rank, ((size_t)a->tid_mask + 1) * 4);
-      want(&cp.order, std::max<uint64_t>(N, 1) * 4);
+      want(&a->tid_slots, (size_t)tcap * 8, 0);
+      want(&a->tid_rank, (size_t)tcap * 4);
+      want(&cp.order, Nn * 4);
     } else {
       size_t u = std::max<uint32_t>(cp.universe, 1);
-      want(&col_first[c], u * 4, true); want(&col_rank[c], u * 4); want(&cp.order, u * 4);
+      want(&col_first[c], u * 4, 0); want(&col_rank[c], u * 4); want(&cp.order, u * 4);
     }
   }
-  size_t total = 0, ff_bytes = 0;
-  for (auto& r : reqs) { total += r.bytes; if (r.ff) ff_bytes += r.bytes; }
-  CK(a->d_arena.ensure(std::max<size_t>(total, 256)));
+  size_t cls_bytes[3] = {0, 0, 0};
+  for (auto& r : reqs) cls_bytes[r.cls] += r.bytes;
+  CK(a->d_arena.ensure(std::max<size_t>(cls_bytes[0] + cls_bytes[1] + cls_bytes[2], 256)));
   {
-    size_t off_ff = 0, off = ff_bytes;  // 0xFF-initialised regions first, contiguous
-    for (auto& r : reqs) {
-      if (r.ff) { *r.pp = a->d_arena.as<uint8_t>() + off_ff; off_ff += r.bytes; } else { *r.pp = a->d_arena.as<uint8_t>() + off; off += r.bytes; }
-    }
+    size_t off[3] = {0, cls_bytes[0], cls_bytes[0] + cls_bytes[1]};  // [0xFF region][zero region][rest]
+    for (auto& r : reqs) { *r.pp = a->d_arena.as<uint8_t>() + off[r.cls]; off[r.cls] += r.bytes; }
   }
   a->lo.type_key = a->sd_keys[0]; a->lo.map_key = a->sd_keys[1]; a->lo.bid_key = a->sd_keys[2]; a->lo.func_key = a->fn_keys;
 
@@ -544,23 +558,24 @@ static int process_once(pa_agg* a) {
   CK(cudaEventRecord(a->tm[T_TOTAL].a, s));
   CK(cudaMemsetAsync(ctr, 0, sizeof(Counters), s));
   CK(cudaMemsetAsync(tab, 0, (cap + 2) * sizeof(StackSlot), s));
-  if (ff_bytes) CK(cudaMemsetAsync(a->d_arena.p, 0xFF, ff_bytes, s));
+  if (cls_bytes[0]) CK(cudaMemsetAsync(a->d_arena.p, 0xFF, cls_bytes[0], s));
+  if (cls_bytes[1]) CK(cudaMemsetAsync(a->d_arena.as<uint8_t>() + cls_bytes[0], 0, cls_bytes[1], s));
 
-  // ---- per chunk: header split (+insert in provided mode), then hash+insert
+  // ---- header split (+insert in provided mode), then hash+insert
   const bool provided = a->cfg.hash_mode == PA_HASH_PROVIDED;
   // When the whole batch is already resident (pa_agg_stage) the two passes run back to back and
   // are timed separately; during an overlapped flush they interleave per chunk as copies land.
   const bool resident = a->chunk_ev.empty() || a->chunk_rows.empty() || cudaEventQuery(a->chunk_ev[a->chunk_rows.size() - 1]) == cudaSuccess;
   a->hash_timed = resident && !provided;
-  auto launch_header = [&](size_t k) {
+  auto launch_header = [&](uint64_t r0, uint64_t r1, uint64_t frames_end) {
     HeaderArgs h{};
-    h.hdr = a->d_hdr.as<uint4>(); h.row0 = (uint32_t)a->chunk_rows[k].first; h.row1 = (uint32_t)a->chunk_rows[k].second;
+    h.hdr = a->d_hdr.as<uint4>(); h.row0 = (uint32_t)r0; h.row1 = (uint32_t)r1;
     h.timestamp = a->d_ts.as<long long>(); h.value = a->d_value.as<long long>(); h.uuid = a->d_uuid.as<uint8_t>();
     h.kind = a->d_kind.as<uint8_t>(); h.nframes = a->d_nfr.as<uint16_t>(); h.frame_off = a->d_foff.as<unsigned long long>();
     h.ls = a->d_ls.as<uint32_t>(); h.cpu = a->d_cpu.as<uint32_t>(); h.tid = a->d_tid.as<uint32_t>(); h.comm = a->d_comm.as<uint32_t>();
     h.sid2cid = a->m_sid2cid.ptr(); h.n_sids = (uint32_t)a->sp.sid2cid.size(); h.n_labelsets = (uint32_t)a->ls.sets.size();
-    h.n_frame_ids = a->chunk_frames_end[k]; h.provided = provided ? 1 : 0; h.tab = tab; h.mask = mask; h.slot_of_row = a->d_slot.as<uint32_t>(); h.ctr = ctr;
-    uint32_t rows = h.row1 - h.row0;
+    h.n_frame_ids = frames_end; h.provided = provided ? 1 : 0; h.tab = tab; h.mask = mask; h.slot_of_row = a->d_slot.as<uint32_t>(); h.ctr = ctr;
+    uint64_t rows = r1 - r0;
     int hb = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)G * 2);
     k_header<<<std::max(hb, 1), kThreads, 0, s>>>(h);
     a->tm[T_HEADER].launches++;
@@ -577,97 +592,115 @@ static int process_once(pa_agg* a) {
   };
   CK(cudaEventRecord(a->tm[T_HEADER].a, s));
   if (resident) {
-    for (size_t k = 0; k < a->chunk_rows.size(); k++) launch_header(k);
+    launch_header(0, N, a->NF);  // whole resident batch: one launch per pass
     CK(cudaEventRecord(a->tm[T_HEADER].b, s));
     CK(cudaEventRecord(a->tm[T_HASH].a, s));
-    if (!provided) launch_hash(0, N);  // whole resident batch in one persistent launch
+    if (!provided) launch_hash(0, N);
     CK(cudaEventRecord(a->tm[T_HASH].b, s));
   } else {
     for (size_t k = 0; k < a->chunk_rows.size(); k++) {
       CK(cudaStreamWaitEvent(s, a->chunk_ev[k], 0));
-      launch_header(k);
+      launch_header(a->chunk_rows[k].first, a->chunk_rows[k].second, a->chunk_frames_end[k]);
       if (!provided) launch_hash(a->chunk_rows[k].first, a->chunk_rows[k].second);
     }
     CK(cudaEventRecord(a->tm[T_HEADER].b, s));
   }
 
-  // ---- unique stacks: first-occurrence ordinal, offsets, per-row (offset,size), gather
+  // ---- unique stacks: ordinals from the first-row bitmap, offsets from a scan over the unique list
   CK(cudaEventRecord(a->tm[T_RANK].a, s));
-  RowFirstF rf{(uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(), a->d_uniq_count.as<uint32_t>(), ctr};
-  launch_scan(a, rf, 1, a->tm[T_RANK]);
+  const uint32_t nslots = (uint32_t)(cap + 2);
+  const int Gs = std::max(1, (int)std::min<uint64_t>(G, (nslots + kThreads - 1) / kThreads));
+  k_stack_bits<<<Gs, kThreads, 0, s>>>(tab, nslots, rowbits);
+  launch_scan(a, WordsF{rowbits, row_wprefix, (uint32_t)((N + 31) / 32), &ctr->n_unique}, 1, a->tm[T_RANK]);
+  k_stack_assign<<<Gs, kThreads, 0, s>>>(tab, nslots, rowbits, row_wprefix, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(),
+                                         a->d_uniq_count.as<uint32_t>(), uniq_slot, uniq_size);
+  launch_scan(a, UniqOffsetF{ctr, ctr, uniq_size, uniq_slot, tab}, 1, a->tm[T_RANK]);
   k_rows_materialize<<<G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>());
   k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, a->d_frames.as<unsigned long long>(),
                                          a->d_foff.as<unsigned long long>(), n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr);
-  a->tm[T_RANK].launches += 2;
+  a->tm[T_RANK].launches += 4;
   CK(cudaEventRecord(a->tm[T_RANK].b, s));
 
   // ---- dictionaries: jobs table
   std::vector<FoJob> jobs;
-  auto job = [&](const uint32_t* keys, const uint32_t* n_ptr, uint32_t* first, uint32_t* rank, uint32_t* order, uint32_t* out, uint32_t* validity,
-                 uint32_t* n_unique, uint32_t* n_null, bool nullable, bool skip_min) {
+  auto job = [&](const uint32_t* keys, const uint32_t* n_ptr, uint32_t* first, uint32_t universe, uint32_t* rank, uint32_t* order, uint32_t* out,
+                 uint32_t* validity, uint32_t* bitmap, uint32_t* wprefix, uint32_t* n_unique, uint32_t* n_null, bool nullable, bool skip_min) {
     FoJob j{};
-    j.keys = keys; j.n_ptr = n_ptr; j.first = first; j.rank = rank; j.order = order; j.out = out; j.validity = validity;
-    j.n_unique = n_unique; j.n_null = n_null; j.nullable = nullable; j.skip_min = skip_min;
+    j.keys = keys; j.n_ptr = n_ptr; j.first = first; j.universe = universe; j.rank = rank; j.order = order; j.out = out; j.validity = validity;
+    j.bitmap = bitmap; j.wprefix = wprefix; j.n_unique = n_unique; j.n_null = n_null; j.nullable = nullable; j.skip_min = skip_min; j.ctr = ctr;
     jobs.push_back(j);
     return (int)jobs.size() - 1;
   };
-  static_assert(sizeof(unsigned long long) == 8, "");
   // the low 32 bits of n_indices64 are the index count (overflow is flagged separately)
   const uint32_t* n_idx_ptr = (const uint32_t*)&ctr->n_indices64;
-  int j_loc = job(a->d_ustream.as<uint32_t>(), n_idx_ptr, a->loc_first, a->loc_rank, a->loc_order, a->d_ustream.as<uint32_t>(), nullptr, &ctr->n_locations, nullptr, false, true);
-  int j_type = job(a->sd_keys[0], &ctr->n_locations, a->sd_first[0], a->sd_rank[0], a->sd_order[0], a->sd_keys[0], nullptr, &ctr->n_dict_type, nullptr, false, false);
-  job(a->sd_keys[1], &ctr->n_locations, a->sd_first[1], a->sd_rank[1], a->sd_order[1], a->sd_keys[1], nullptr, &ctr->n_dict_map, nullptr, false, false);
-  job(a->sd_keys[2], &ctr->n_locations, a->sd_first[2], a->sd_rank[2], a->sd_order[2], a->sd_keys[2], a->sd_valid[2], &ctr->n_dict_bid, &ctr->null_bid, true, false);
-  job(a->fn_keys, &ctr->n_lines, a->fn_first, a->fn_rank, a->fn_order, a->fn_keys, nullptr, &ctr->n_functions, nullptr, false, false);
-  int j_file = job(a->sd_keys[3], &ctr->n_functions, a->sd_first[3], a->sd_rank[3], a->sd_order[3], a->sd_keys[3], a->sd_valid[3], &ctr->n_dict_file, &ctr->null_file, true, false);
+  int j_loc = job(a->d_ustream.as<uint32_t>(), n_idx_ptr, a->loc_first, n_frames, a->loc_rank, a->loc_order, a->d_ustream.as<uint32_t>(), nullptr,
+                  loc_bits, loc_wp, &ctr->n_locations, nullptr, false, true);
+  int j_type = job(a->sd_keys[0], &ctr->n_locations, a->sd_first[0], n_cstr, a->sd_rank[0], a->sd_order[0], a->sd_keys[0], nullptr, sd_bits[0], sd_wp[0], &ctr->n_dict_type, nullptr, false, false);
+  job(a->sd_keys[1], &ctr->n_locations, a->sd_first[1], n_cstr, a->sd_rank[1], a->sd_order[1], a->sd_keys[1], nullptr, sd_bits[1], sd_wp[1], &ctr->n_dict_map, nullptr, false, false);
+  job(a->sd_keys[2], &ctr->n_locations, a->sd_first[2], n_cstr, a->sd_rank[2], a->sd_order[2], a->sd_keys[2], a->sd_valid[2], sd_bits[2], sd_wp[2], &ctr->n_dict_bid, &ctr->null_bid, true, false);
+  job(a->fn_keys, &ctr->n_lines, a->fn_first, n_funcs, a->fn_rank, a->fn_order, a->fn_keys, nullptr, fn_bits, fn_wp, &ctr->n_functions, nullptr, false, false);
+  int j_file = job(a->sd_keys[3], &ctr->n_functions, a->sd_first[3], n_cstr, a->sd_rank[3], a->sd_order[3], a->sd_keys[3], a->sd_valid[3], sd_bits[3], sd_wp[3], &ctr->n_dict_file, &ctr->null_file, true, false);
   int j_lab0 = (int)jobs.size();
   for (uint32_t c = 0; c < nlab; c++) {
     ColPlan& cp = a->cols[c];
     bool nullable = cp.type == COL_LS || cp.type == COL_COMM;
-    int ji = job(cp.run_keys, &ctr->n_runs[c], col_first[c], col_rank[c], cp.order, cp.run_keys, cp.validity, &ctr->n_dict[c], &ctr->n_null[c], nullable, false);
+    // first positions are recorded by the REE emit pass (skip_min)
+    int ji = job(cp.run_keys, &ctr->n_runs[c], col_first[c], cp.universe, col_rank[c], cp.order, cp.run_keys, cp.validity, col_bits[c], col_wp[c],
+                 &ctr->n_dict[c], &ctr->n_null[c], nullable, true);
     if (cp.type == COL_TID) { jobs[ji].hashed = 1; jobs[ji].hslots = a->tid_slots; jobs[ji].hmask = a->tid_mask; jobs[ji].rank = a->tid_rank; }
   }
   CK(a->d_jobs.ensure(jobs.size() * sizeof(FoJob)));
   CK(cudaMemcpyAsync(a->d_jobs.p, jobs.data(), jobs.size() * sizeof(FoJob), cudaMemcpyHostToDevice, s));
   const FoJob* djobs = a->d_jobs.as<FoJob>();
-  auto run_jobs = [&](int first, int count, Timer& t) {
+  auto run_jobs = [&](int first, int count, bool need_min, Timer& t) {
     dim3 grid(G, count);
-    k_fo_min<<<grid, kThreads, 0, s>>>(djobs + first);
-    launch_scan(a, FoF{djobs + first}, count, t);
+    k_fo_zero<<<grid, kThreads, 0, s>>>(djobs + first);
+    if (need_min) { k_fo_min<<<grid, kThreads, 0, s>>>(djobs + first); t.launches++; }
+    k_fo_bits<<<grid, kThreads, 0, s>>>(djobs + first);
+    launch_scan(a, FoWordsF{djobs + first}, count, t);
+    k_fo_assign<<<grid, kThreads, 0, s>>>(djobs + first);
     k_fo_map<<<grid, kThreads, 0, s>>>(djobs + first);
-    t.launches += 2;
+    t.launches += 4;
   };
 
   CK(cudaEventRecord(a->tm[T_LOC].a, s));
-  run_jobs(j_loc, 1, a->tm[T_LOC]);  // location index per unique-stack frame (in place over the gathered stream)
+  run_jobs(j_loc, 1, false, a->tm[T_LOC]);  // location index per unique-stack frame (in place over the gathered stream)
   FrameTable ftd{(const unsigned long long*)a->m_addr.ptr(), a->m_type.ptr(), a->m_map.ptr(), a->m_bid.ptr(), (const unsigned long long*)a->m_line.ptr(), a->m_func.ptr()};
   launch_scan(a, LocLinesF{ctr, ctr, a->loc_order, ftd, a->lo}, 1, a->tm[T_LOC]);
   k_line_validity<<<std::max(1, std::min(G, (int)(P / 256 + 1))), kThreads, 0, s>>>(ctr, a->lo.line_size, a->lo.line_valid);
-  run_jobs(j_type, 4, a->tm[T_LOC]);  // frame_type, mapping_file, mapping_build_id, function
+  run_jobs(j_type, 4, true, a->tm[T_LOC]);  // frame_type, mapping_file, mapping_build_id, function
   k_func_keys<<<std::max(1, std::min(G, (int)(FN / 256 + 1))), kThreads, 0, s>>>(ctr, a->fn_order, a->m_fnfile.ptr(), a->sd_keys[3]);
-  run_jobs(j_file, 1, a->tm[T_LOC]);  // function.filename
+  run_jobs(j_file, 1, true, a->tm[T_LOC]);  // function.filename
   a->tm[T_LOC].launches += 2;
   CK(cudaEventRecord(a->tm[T_LOC].b, s));
 
-  // ---- run-end encoding of label + constant columns
+  // ---- run-end encoding of label + constant columns (dictionary first positions recorded on the fly)
   CK(cudaEventRecord(a->tm[T_LABELS].a, s));
   std::vector<ReeCol> rc(ncols);
-  for (uint32_t c = 0; c < ncols; c++) rc[c] = ReeCol{a->cols[c].type, a->cols[c].param, a->cols[c].run_ends, a->cols[c].run_keys};
+  ReeArgs ra{};
+  ra.c_cpu = ra.c_tid = ra.c_comm = -1;
+  for (uint32_t c = 0; c < ncols; c++) {
+    const ColPlan& cp = a->cols[c];
+    rc[c] = ReeCol{cp.type, cp.param, cp.run_ends, cp.run_keys, c < nlab ? col_first[c] : nullptr, nullptr, 0, 0};
+    if (cp.type == COL_TID) { rc[c].hslots = a->tid_slots; rc[c].hmask = a->tid_mask; }
+    if (cp.type == COL_CPU) ra.c_cpu = (int)c;
+    if (cp.type == COL_TID) ra.c_tid = (int)c;
+    if (cp.type == COL_COMM) ra.c_comm = (int)c;
+  }
   CK(a->d_cols.ensure(rc.size() * sizeof(ReeCol)));
   CK(cudaMemcpyAsync(a->d_cols.p, rc.data(), rc.size() * sizeof(ReeCol), cudaMemcpyHostToDevice, s));
-  ReeArgs ra{};
-  ra.n_rows = (uint32_t)N; ra.ncols = ncols; ra.cols = a->d_cols.as<ReeCol>();
+  ra.n_rows = (uint32_t)N; ra.ncols = ncols; ra.n_ls = a->n_lscols; ra.c_kind = nlab; ra.cols = a->d_cols.as<ReeCol>();
   ra.ls = a->d_ls.as<uint32_t>(); ra.cpu = a->d_cpu.as<uint32_t>(); ra.tid = a->d_tid.as<uint32_t>(); ra.comm = a->d_comm.as<uint32_t>(); ra.kind = a->d_kind.as<uint8_t>();
   ra.lsmat = a->d_lsmat.as<uint32_t>(); ra.n_lscols = std::max<uint32_t>(1, a->n_lscols); ra.kindtab = a->d_kindtab.as<uint32_t>();
   ra.partial = a->d_partial.as<uint32_t>(); ra.ctr = ctr;
-  k_ree_count<<<G, kThreads, 0, s>>>(ra);
-  k_ree_scan_partials<<<ncols, 32, 0, s>>>(ra, G);
-  k_ree_emit<<<G, kThreads, 0, s>>>(ra);
+  k_ree_pass<false><<<G, kThreads, 0, s>>>(ra);
+  k_ree_scan_partials<<<ncols, 32, 0, s>>>(ra, G * kWarps);
+  k_ree_pass<true><<<G, kThreads, 0, s>>>(ra);
   a->tm[T_LABELS].launches += 3;
   CK(cudaEventRecord(a->tm[T_LABELS].b, s));
 
   CK(cudaEventRecord(a->tm[T_DICTS].a, s));
-  if (nlab) run_jobs(j_lab0, (int)nlab, a->tm[T_DICTS]);  // label dictionaries over the runs
+  if (nlab) run_jobs(j_lab0, (int)nlab, false, a->tm[T_DICTS]);  // label dictionaries over the runs
   CK(cudaEventRecord(a->tm[T_DICTS].b, s));
 
   CK(cudaMemcpyAsync(a->h_ctr_pinned, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
@@ -699,7 +732,8 @@ static int process(pa_agg* a) {
     rc = process_once(a);
     if (rc) return rc;
     if (!(a->h_ctr.err & ERR_TABLE_FULL)) break;
-    a->retry_cap = a->table_cap * 4;  // unique-stack estimate was too small: grow and redo the batch
+    a->retry_cap = a->table_cap * 4;  // unique-stack / thread-id estimate was too small: grow and redo the batch
+    a->retry_tcap = a->tid_cap * 4;
   }
   uint32_t e = a->h_ctr.err;
   if (e & ERR_TABLE_FULL) return a->fail(PA_ENOMEM, "stack table overflow");
@@ -711,7 +745,10 @@ static int process(pa_agg* a) {
   if (e & ERR_BAD_CPU) return a->fail(PA_EINVAL, "cpu id >= 65536");
   if (e & ERR_BAD_FRAME_RANGE) return a->fail(PA_EINVAL, "sample frame range outside the staged frames (frame_off must ascend with the rows)");
   a->prev_unique = a->h_ctr.n_unique;
+  a->prev_tids = 0;
+  for (uint32_t c = 0; c < a->n_label_cols; c++) if (a->cols[c].type == COL_TID) a->prev_tids = a->h_ctr.n_dict[c];
   a->retry_cap = 0;
+  a->retry_tcap = 0;
   a->processed = true;
   return PA_OK;
 }

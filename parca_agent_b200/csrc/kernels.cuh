@@ -397,6 +397,9 @@ __device__ __forceinline__ uint32_t shfl_up_t(uint32_t v, int d) { return __shfl
 __device__ __forceinline__ Pair shfl_up_t(Pair v, int d) {
   return Pair{__shfl_up_sync(0xFFFFFFFFu, v.cnt, d), __shfl_up_sync(0xFFFFFFFFu, v.fr, d)};
 }
+__device__ __forceinline__ unsigned long long shfl_up_t(unsigned long long v, int d) { return __shfl_up_sync(0xFFFFFFFFu, v, d); }
+__device__ __forceinline__ unsigned long long shfl_idx_t(unsigned long long v, int l) { return __shfl_sync(0xFFFFFFFFu, v, l); }
+__device__ __forceinline__ unsigned long long zero_of(unsigned long long) { return 0ull; }
 __device__ __forceinline__ uint32_t shfl_idx_t(uint32_t v, int l) { return __shfl_sync(0xFFFFFFFFu, v, l); }
 __device__ __forceinline__ Pair shfl_idx_t(Pair v, int l) { return Pair{__shfl_sync(0xFFFFFFFFu, v.cnt, l), __shfl_sync(0xFFFFFFFFu, v.fr, l)}; }
 __device__ __forceinline__ uint32_t zero_of(uint32_t) { return 0u; }
@@ -485,37 +488,57 @@ __global__ void __launch_bounds__(kThreads) k_scan_emit(F f, const typename F::T
 }
 
 // ---------------------------------------------------------------------------------------------
-// (1) unique stacks in first-occurrence order: ordinal + start offset of each first occurrence
-struct RowFirstF {
-  typedef Pair T;
-  uint32_t n_rows;
-  const uint32_t* slot_of_row;
+// (1) unique stacks in first-occurrence order. The table holds each stack's first row; ordinals
+// come from a bitmap over rows (one bit per first occurrence) + a popcount prefix over its words,
+// so only table-sized and N/32-sized passes are needed (no scan over all rows).
+__global__ void __launch_bounds__(kThreads) k_stack_bits(const StackSlot* tab, uint32_t nslots, uint32_t* rowbits) {
+  for (uint32_t sidx = blockIdx.x * kThreads + threadIdx.x; sidx < nslots; sidx += gridDim.x * kThreads) {
+    uint32_t inv = tab[sidx].first_inv;
+    if (inv) { uint32_t f = 0xFFFFFFFFu - inv; atomicOr(&rowbits[f >> 5], 1u << (f & 31)); }
+  }
+}
+struct WordsF {  // exclusive popcount prefix over bitmap words
+  typedef uint32_t T;
+  const uint32_t* bits;
+  uint32_t* wprefix;
+  uint32_t n_words;
+  uint32_t* total_out;
+  __device__ uint32_t n() const { return n_words; }
+  __device__ uint32_t value(uint32_t i) const { return (uint32_t)__popc(bits[i]); }
+  __device__ void emit(uint32_t i, uint32_t ex, uint32_t) const { wprefix[i] = ex; }
+  __device__ void total(int, uint32_t t) const { *total_out = t; }
+};
+__global__ void __launch_bounds__(kThreads) k_stack_assign(StackSlot* tab, uint32_t nslots, const uint32_t* rowbits, const uint32_t* wprefix,
+                                                           const uint16_t* nframes, uint32_t* uniq_row, uint32_t* uniq_count,
+                                                           uint32_t* uniq_slot, uint32_t* uniq_size) {
+  for (uint32_t sidx = blockIdx.x * kThreads + threadIdx.x; sidx < nslots; sidx += gridDim.x * kThreads) {
+    uint32_t inv = tab[sidx].first_inv;
+    if (!inv) continue;
+    uint32_t f = 0xFFFFFFFFu - inv;
+    uint32_t ord = wprefix[f >> 5] + (uint32_t)__popc(rowbits[f >> 5] & ((1u << (f & 31)) - 1u));
+    uniq_row[ord] = f;
+    uniq_count[ord] = tab[sidx].count;
+    uniq_slot[ord] = sidx;
+    uniq_size[ord] = nframes[f];
+  }
+}
+struct UniqOffsetF {  // startOffset := indices.Len() at each first occurrence (arrow_v2.go:302)
+  typedef unsigned long long T;
+  const Counters* ctr;
+  Counters* ctr_w;
+  const uint32_t* uniq_size;
+  const uint32_t* uniq_slot;
   StackSlot* tab;
-  const uint16_t* nframes;
-  uint32_t* uniq_row;     // [ordinal] -> first row
-  uint32_t* uniq_count;   // [ordinal] -> occurrences
-  Counters* ctr;
-  __device__ uint32_t n() const { return n_rows; }
-  __device__ bool first(uint32_t r, uint32_t* s) const {
-    *s = slot_of_row[r];
-    return *s != kNull && (0xFFFFFFFFu - tab[*s].first_inv) == r;
+  __device__ uint32_t n() const { return ctr->n_unique; }
+  __device__ unsigned long long value(uint32_t u) const { return uniq_size[u]; }
+  __device__ void emit(uint32_t u, unsigned long long ex, unsigned long long v) const {
+    StackSlot* e = &tab[uniq_slot[u]];
+    e->offset = (uint32_t)ex;
+    e->size = (uint32_t)v;
   }
-  __device__ Pair value(uint32_t r) const {
-    uint32_t s;
-    return first(r, &s) ? Pair{1u, (unsigned long long)nframes[r]} : Pair{0u, 0ull};
-  }
-  __device__ void emit(uint32_t r, Pair ex, Pair v) const {
-    if (!v.cnt) return;
-    uint32_t s = slot_of_row[r];
-    uniq_row[ex.cnt] = r;
-    uniq_count[ex.cnt] = tab[s].count;
-    tab[s].offset = (uint32_t)ex.fr;  // startOffset := indices.Len() (arrow_v2.go:302)
-    tab[s].size = nframes[r];
-  }
-  __device__ void total(int, Pair t) const {
-    ctr->n_unique = t.cnt;
-    ctr->n_indices64 = t.fr;
-    if (t.fr > 0x7FFFFFFFull) atomicOr(&ctr->err, ERR_INDEX_OVERFLOW);  // ListView offsets are int32 (arrow_v2.go:233)
+  __device__ void total(int, unsigned long long t) const {
+    ctr_w->n_indices64 = t;
+    if (t > 0x7FFFFFFFull) atomicOr(&ctr_w->err, ERR_INDEX_OVERFLOW);  // ListView offsets are int32 (arrow_v2.go:233)
   }
 };
 
@@ -556,26 +579,50 @@ __global__ void __launch_bounds__(kThreads) k_gather_unique(const Counters* ctr,
 
 // ---------------------------------------------------------------------------------------------
 // first-occurrence ranking of 32-bit keys (dictionary index assignment). Batched: blockIdx.y = job.
+//   min    : first[key] = min position            (element-sized; fused into the producer where possible)
+//   bits   : bitmap[first[key]] = 1 for every present key         (table-sized)
+//   words  : exclusive popcount prefix over the bitmap words      (n/32-sized)
+//   assign : rank[key] = prefix + popc(below), order[rank] = key  (table-sized)
+//   map    : out[i] = rank[keys[i]] (+ validity bitmap)           (element-sized)
 struct FoJob {
   const uint32_t* keys;
   const uint32_t* n_ptr;   // element count lives on the device
-  uint32_t* first;         // direct: [universe] first position (memset 0xFF). hashed: unused
+  uint32_t* first;         // direct: [universe] first position (memset 0xFF)
   unsigned long long* hslots;  // hashed: (key<<32 | first position), memset 0xFF
   uint32_t hmask;
   uint32_t hashed;
+  uint32_t universe;       // direct table entries
   uint32_t nullable;       // keys == kNull are nulls (skipped, mapped to index 0 + validity 0)
   uint32_t skip_min;       // first[] already filled by a producer kernel
   uint32_t* rank;          // direct: [universe], hashed: [hmask+1]
   uint32_t* order;         // [n_unique] key by rank
   uint32_t* out;           // [n] rank per element (may alias keys); nullptr = skip
   uint32_t* validity;      // [ceil(n/32)] bitmap words; nullptr = skip
+  uint32_t* bitmap;        // [ceil(n_max/32)+1] zeroed
+  uint32_t* wprefix;       // [ceil(n_max/32)+1]
   uint32_t* n_unique;      // -> Counters
   uint32_t* n_null;        // -> Counters (may be nullptr)
+  Counters* ctr;
 };
 __device__ __forceinline__ uint32_t fo_hfind(const FoJob& j, uint32_t key) {
   uint32_t idx = mix32(key) & j.hmask;
   while ((uint32_t)(j.hslots[idx] >> 32) != key) idx = (idx + 1) & j.hmask;
   return idx;
+}
+// bounded linear-probe insert of (key, pos) keeping the minimum pos; false = table full
+__device__ __forceinline__ bool hashed_min_insert(unsigned long long* hslots, uint32_t hmask, uint32_t key, uint32_t pos) {
+  unsigned long long packed = ((unsigned long long)key << 32) | pos;
+  uint32_t idx = mix32(key) & hmask;
+  for (uint32_t probe = 0; probe <= hmask; probe++) {
+    unsigned long long cur = hslots[idx];
+    if (cur == ~0ull) {
+      cur = atomicCAS(&hslots[idx], ~0ull, packed);
+      if (cur == ~0ull) return true;
+    }
+    if ((uint32_t)(cur >> 32) == key) { if (cur > packed) atomicMin(&hslots[idx], packed); return true; }
+    idx = (idx + 1) & hmask;
+  }
+  return false;
 }
 __global__ void __launch_bounds__(kThreads) k_fo_min(const FoJob* jobs) {
   const FoJob& j = jobs[blockIdx.y];
@@ -586,42 +633,47 @@ __global__ void __launch_bounds__(kThreads) k_fo_min(const FoJob* jobs) {
     if (j.nullable && key == kNull) continue;
     if (!j.hashed) {
       if (j.first[key] > i) atomicMin(&j.first[key], i);
-    } else {
-      unsigned long long packed = ((unsigned long long)key << 32) | i;
-      uint32_t idx = mix32(key) & j.hmask;
-      while (true) {
-        unsigned long long cur = j.hslots[idx];
-        if (cur == ~0ull) {
-          cur = atomicCAS(&j.hslots[idx], ~0ull, packed);
-          if (cur == ~0ull) break;
-        }
-        if ((uint32_t)(cur >> 32) == key) { if (cur > packed) atomicMin(&j.hslots[idx], packed); break; }
-        idx = (idx + 1) & j.hmask;
-      }
+    } else if (!hashed_min_insert(j.hslots, j.hmask, key, i)) {
+      atomicOr(&j.ctr->err, ERR_TABLE_FULL);
     }
   }
 }
-struct FoF {
+__global__ void __launch_bounds__(kThreads) k_fo_zero(const FoJob* jobs) {  // clear only the bitmap words this batch will use
+  const FoJob& j = jobs[blockIdx.y];
+  uint32_t nw = *j.n_ptr / 32 + 1;
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < nw; i += gridDim.x * kThreads) j.bitmap[i] = 0u;
+}
+__global__ void __launch_bounds__(kThreads) k_fo_bits(const FoJob* jobs) {
+  const FoJob& j = jobs[blockIdx.y];
+  uint32_t entries = j.hashed ? j.hmask + 1 : j.universe;
+  for (uint32_t e = blockIdx.x * kThreads + threadIdx.x; e < entries; e += gridDim.x * kThreads) {
+    uint32_t f;
+    if (j.hashed) { unsigned long long sl = j.hslots[e]; if (sl == ~0ull) continue; f = (uint32_t)sl; }
+    else { f = j.first[e]; if (f == kNull) continue; }
+    atomicOr(&j.bitmap[f >> 5], 1u << (f & 31));
+  }
+}
+struct FoWordsF {
   typedef uint32_t T;
   const FoJob* jobs;
-  __device__ uint32_t n() const { return *jobs[blockIdx.y].n_ptr; }
-  __device__ uint32_t value(uint32_t i) const {
-    const FoJob& j = jobs[blockIdx.y];
-    uint32_t key = j.keys[i];
-    if (j.nullable && key == kNull) return 0;
-    if (!j.hashed) return j.first[key] == i;
-    return (uint32_t)(j.hslots[fo_hfind(j, key)] & 0xFFFFFFFFull) == i;
-  }
-  __device__ void emit(uint32_t i, uint32_t ex, uint32_t v) const {
-    if (!v) return;
-    const FoJob& j = jobs[blockIdx.y];
-    uint32_t key = j.keys[i];
-    j.rank[j.hashed ? fo_hfind(j, key) : key] = ex;
-    j.order[ex] = key;
-  }
+  __device__ uint32_t n() const { return (*jobs[blockIdx.y].n_ptr + 31) / 32; }
+  __device__ uint32_t value(uint32_t i) const { return (uint32_t)__popc(jobs[blockIdx.y].bitmap[i]); }
+  __device__ void emit(uint32_t i, uint32_t ex, uint32_t) const { jobs[blockIdx.y].wprefix[i] = ex; }
   __device__ void total(int job, uint32_t t) const { *jobs[job].n_unique = t; }
 };
-// element -> dictionary index (+ validity bitmap, null count). Runs after k_scan_emit<FoF>.
+__global__ void __launch_bounds__(kThreads) k_fo_assign(const FoJob* jobs) {
+  const FoJob& j = jobs[blockIdx.y];
+  uint32_t entries = j.hashed ? j.hmask + 1 : j.universe;
+  for (uint32_t e = blockIdx.x * kThreads + threadIdx.x; e < entries; e += gridDim.x * kThreads) {
+    uint32_t f, key;
+    if (j.hashed) { unsigned long long sl = j.hslots[e]; if (sl == ~0ull) continue; f = (uint32_t)sl; key = (uint32_t)(sl >> 32); }
+    else { f = j.first[e]; if (f == kNull) continue; key = e; }
+    uint32_t r = j.wprefix[f >> 5] + (uint32_t)__popc(j.bitmap[f >> 5] & ((1u << (f & 31)) - 1u));
+    j.rank[e] = r;
+    j.order[r] = key;
+  }
+}
+// element -> dictionary index (+ validity bitmap, null count)
 __global__ void __launch_bounds__(kThreads) k_fo_map(const FoJob* jobs) {
   const FoJob& j = jobs[blockIdx.y];
   if (!j.out) return;
@@ -710,63 +762,147 @@ __global__ void __launch_bounds__(kThreads) k_func_keys(const Counters* ctr, con
 
 // ---------------------------------------------------------------------------------------------
 // run-end encoding of every REE column in two fused passes over the rows
-// (label columns: reporter/arrow.go:97-131; constant-ish columns: arrow.go:50-59,:166-207)
+// (label columns: reporter/arrow.go:97-131; constant-ish columns: arrow.go:50-59,:166-207).
+// Rows are partitioned into one contiguous range per WARP, so neither pass needs a block barrier:
+// the previous row's inputs come from the neighbouring lane (shuffle) or are carried across steps.
+// Column order is fixed by the host: [labelset-derived LS columns][cpu][thread_id][thread_name][8 kind columns].
 enum : uint32_t { COL_LS = 0, COL_CPU = 1, COL_TID = 2, COL_COMM = 3, COL_KIND = 4 };
 struct ReeCol {
   uint32_t type, param;
   int* run_ends;       // Arrow: run_ends child
   uint32_t* run_keys;  // key of each run (kNull = null run)
+  uint32_t* first;     // dictionary first-position table (direct), fused fo_min
+  unsigned long long* hslots;  // hashed variant (thread_id)
+  uint32_t hmask;
+  uint32_t pad;
 };
 struct ReeArgs {
   uint32_t n_rows, ncols;
+  uint32_t n_ls;                 // LS columns are 0..n_ls-1
+  int c_cpu, c_tid, c_comm;      // column index or -1
+  uint32_t c_kind;               // first of the 8 kind columns
   const ReeCol* cols;
   const uint32_t* ls; const uint32_t* cpu; const uint32_t* tid; const uint32_t* comm; const uint8_t* kind;
-  const uint32_t* lsmat; uint32_t n_lscols;   // [labelset][label column] -> value local id or kNull
-  const uint32_t* kindtab;                    // [column param][8] -> class id or kNull
-  uint32_t* partial;                          // [ncols][grid]
+  const uint32_t* lsmat; uint32_t n_lscols;   // [labelset][LS column] -> value local id or kNull
+  const uint32_t* kindtab;                    // [8][8] -> class id or kNull
+  uint32_t* partial;                          // [ncols][total warps]
   Counters* ctr;
 };
-__device__ __forceinline__ uint32_t ree_key(const ReeArgs& a, const ReeCol& c, uint32_t r, bool* null) {
-  uint32_t v;
-  switch (c.type) {
-    case COL_LS: v = a.lsmat[(size_t)a.ls[r] * a.n_lscols + c.param]; *null = v == kNull; break;
-    case COL_CPU: v = a.cpu[r]; *null = false; break;
-    case COL_TID: v = a.tid[r]; *null = false; break;
-    case COL_COMM: v = a.comm[r]; *null = v == 0; break;  // labels.Builder.Set(name, "") deletes the label
-    default: v = a.kindtab[c.param * 8 + a.kind[r]]; *null = v == kNull; break;
-  }
-  return v;
+struct RowIn { uint32_t ls, cpu, tid, comm, kind; };
+__device__ __forceinline__ RowIn ree_load(const ReeArgs& a, uint32_t r) {
+  return RowIn{a.ls[r], a.cpu[r], a.tid[r], a.comm[r], (uint32_t)a.kind[r]};
 }
-__device__ __forceinline__ bool ree_boundary(const ReeArgs& a, const ReeCol& c, uint32_t r, uint32_t* key, bool* null) {
-  *key = ree_key(a, c, r, null);
-  if (r == 0 || *null) return true;
-  bool pnull;
-  uint32_t pk = ree_key(a, c, r - 1, &pnull);
-  return pnull || pk != *key;
+__device__ __forceinline__ RowIn ree_shfl(const RowIn& x, int srclane) {
+  const unsigned full = 0xFFFFFFFFu;
+  return RowIn{__shfl_sync(full, x.ls, srclane), __shfl_sync(full, x.cpu, srclane), __shfl_sync(full, x.tid, srclane),
+               __shfl_sync(full, x.comm, srclane), __shfl_sync(full, x.kind, srclane)};
 }
-__global__ void __launch_bounds__(kThreads) k_ree_count(ReeArgs a) {
-  __shared__ uint32_t s_cnt[kMaxCols], s_last[kMaxCols];
-  if (threadIdx.x < kMaxCols) { s_cnt[threadIdx.x] = 0; s_last[threadIdx.x] = 0; }
+__device__ __forceinline__ RowIn ree_shfl_up1(const RowIn& x) {
+  const unsigned full = 0xFFFFFFFFu;
+  return RowIn{__shfl_up_sync(full, x.ls, 1), __shfl_up_sync(full, x.cpu, 1), __shfl_up_sync(full, x.tid, 1),
+               __shfl_up_sync(full, x.comm, 1), __shfl_up_sync(full, x.kind, 1)};
+}
+__device__ __forceinline__ void warp_range(uint32_t n, uint32_t* begin, uint32_t* end, uint32_t* wg) {
+  uint32_t nw = gridDim.x * kWarps;
+  uint32_t w = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  uint32_t per = (n + nw - 1) / nw;
+  per = (per + 31) / 32 * 32;
+  unsigned long long b = (unsigned long long)w * per, e = b + per;
+  *begin = b < n ? (uint32_t)b : n;
+  *end = e < n ? (uint32_t)e : n;
+  *wg = w;
+}
+// EMIT = false: count boundaries per (column, warp) and track the last row carrying each label.
+// EMIT = true : write run ends / run keys at their final positions and record dictionary first positions.
+template <bool EMIT>
+__global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
+  __shared__ uint32_t s_acc[kMaxCols][kWarps];   // count (pass 1) or running output position (pass 2)
+  __shared__ uint32_t s_last[kMaxCols][kWarps];
+  __shared__ uint32_t s_kind[64];
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x < 64) s_kind[threadIdx.x] = a.kindtab[threadIdx.x];
+  uint32_t begin, end, wg;
+  warp_range(a.n_rows, &begin, &end, &wg);
+  const uint32_t nwarps = gridDim.x * kWarps;
+  for (uint32_t c = lane; c < a.ncols; c += 32) { s_acc[c][w] = EMIT ? a.partial[c * nwarps + wg] : 0u; s_last[c][w] = 0u; }
   __syncthreads();
-  uint32_t begin, end;
-  block_range(a.n_rows, &begin, &end);
-  int lane = threadIdx.x & 31;
-  for (uint32_t tile = begin; tile < end; tile += kThreads) {
-    uint32_t r = tile + threadIdx.x;
-    bool in = r < end;
-    for (uint32_t c = 0; c < a.ncols; c++) {
-      uint32_t key; bool null = true; bool b = false;
-      if (in) b = ree_boundary(a, a.cols[c], r, &key, &null);
-      unsigned nn = __ballot_sync(0xFFFFFFFFu, in && !null);
-      if (lane == 0 && nn) atomicMax(&s_last[c], tile + (threadIdx.x & ~31u) + (32 - __clz(nn)));
-      int cnt = __syncthreads_count(b);
-      if (threadIdx.x == 0) s_cnt[c] += (uint32_t)cnt;
+  RowIn carry{0, 0, 0, 0, 0};
+  if (begin < end && begin > 0) carry = ree_load(a, begin - 1);  // every lane loads the same row (broadcast)
+  const unsigned lt = (1u << lane) - 1u;
+  for (uint32_t base = begin; base < end; base += 32) {
+    const uint32_t r = base + lane;
+    const bool in = r < end;
+    RowIn x = in ? ree_load(a, r) : RowIn{0, 0, 0, 0, 0};
+    RowIn p = ree_shfl_up1(x);
+    if (lane == 0) p = carry;
+    const bool first_row = r == 0;
+    // one column: ballot, rank inside the warp, write
+    auto column = [&](uint32_t c, bool boundary, bool null, uint32_t key, bool has_dict) {
+      boundary = boundary && in;
+      unsigned m = __ballot_sync(full, boundary);
+      unsigned nn = __ballot_sync(full, in && !null);
+      if (!EMIT) {
+        if (lane == 0) {
+          if (m) s_acc[c][w] += (uint32_t)__popc(m);
+          if (nn) s_last[c][w] = base + (32 - __clz(nn));
+        }
+      } else {
+        if (m == 0) return;
+        uint32_t pos0 = s_acc[c][w];
+        if (boundary) {
+          const ReeCol& col = a.cols[c];
+          uint32_t k = pos0 + (uint32_t)__popc(m & lt);
+          if (k > 0) col.run_ends[k - 1] = (int)r;  // run k starts at r => run k-1 ends at r
+          col.run_keys[k] = null ? kNull : key;
+          if (has_dict && !null) {  // dictionary memo: first run that carries this value
+            if (col.hslots) { if (!hashed_min_insert(col.hslots, col.hmask, key, k)) atomicOr(&a.ctr->err, ERR_TABLE_FULL); }
+            else if (col.first[key] > k) atomicMin(&col.first[key], k);
+          }
+        }
+        __syncwarp(full);
+        if (lane == 0) s_acc[c][w] = pos0 + (uint32_t)__popc(m);
+        __syncwarp(full);
+      }
+    };
+    // ---- labelset-derived columns
+    const bool same_ls = !first_row && x.ls == p.ls;
+    for (uint32_t c = 0; c < a.n_ls; c++) {
+      uint32_t v = in ? a.lsmat[(size_t)x.ls * a.n_lscols + c] : kNull;
+      bool null = v == kNull;
+      bool b = true;
+      if (!null && !first_row) {
+        uint32_t pv = same_ls ? v : a.lsmat[(size_t)p.ls * a.n_lscols + c];
+        b = pv != v;  // also true when the previous row had no value (pv == kNull)
+      }
+      column(c, b, null, v, true);
     }
+    if (a.c_cpu >= 0) column((uint32_t)a.c_cpu, first_row || x.cpu != p.cpu, false, x.cpu, true);
+    if (a.c_tid >= 0) column((uint32_t)a.c_tid, first_row || x.tid != p.tid, false, x.tid, true);
+    if (a.c_comm >= 0) {  // labels.Builder.Set(name, "") deletes the label: "" => null
+      bool null = x.comm == 0;
+      column((uint32_t)a.c_comm, first_row || null || p.comm == 0 || x.comm != p.comm, null, x.comm, true);
+    }
+    // ---- the 8 constant-ish columns depend on the sample kind only: skip them all when nothing changes
+    bool kchange = in && (first_row || x.kind != p.kind || x.kind >= 3u);  // kinds >= 3 carry a null temporality
+    if (__ballot_sync(full, kchange)) {
+      for (uint32_t t = 0; t < 8; t++) {
+        uint32_t v = s_kind[t * 8 + x.kind], pv = s_kind[t * 8 + p.kind];
+        bool null = v == kNull;
+        column(a.c_kind + t, first_row || null || pv == kNull || pv != v, null, v, false);
+      }
+    } else if (!EMIT) {
+      unsigned nn = __ballot_sync(full, in);
+      if (lane == 0 && nn) for (uint32_t t = 0; t < 8; t++) s_last[a.c_kind + t][w] = base + (32 - __clz(nn));
+    }
+    carry = ree_shfl(x, 31);
   }
-  __syncthreads();
-  if (threadIdx.x < a.ncols) {
-    a.partial[threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x];
-    if (s_last[threadIdx.x]) atomicMax(&a.ctr->last_nonnull_plus1[threadIdx.x], s_last[threadIdx.x]);
+  if (!EMIT) {
+    __syncwarp(full);
+    for (uint32_t c = lane; c < a.ncols; c += 32) {
+      a.partial[c * nwarps + wg] = s_acc[c][w];
+      if (s_last[c][w]) atomicMax(&a.ctr->last_nonnull_plus1[c], s_last[c][w]);
+    }
   }
 }
 __global__ void k_ree_scan_partials(ReeArgs a, int g) {  // grid = ncols, 32 threads
@@ -784,43 +920,6 @@ __global__ void k_ree_scan_partials(ReeArgs a, int g) {  // grid = ncols, 32 thr
   if (lane == 0) {
     a.ctr->n_runs[blockIdx.x] = run;
     if (run) a.cols[blockIdx.x].run_ends[run - 1] = (int)a.n_rows;  // the last run ends at the row count
-  }
-}
-__global__ void __launch_bounds__(kThreads) k_ree_emit(ReeArgs a) {
-  __shared__ uint32_t s_base[kMaxCols];
-  __shared__ uint32_t s_wt[kMaxCols][kWarps];
-  if (threadIdx.x < a.ncols) s_base[threadIdx.x] = a.partial[threadIdx.x * gridDim.x + blockIdx.x];
-  __syncthreads();
-  uint32_t begin, end;
-  block_range(a.n_rows, &begin, &end);
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (uint32_t tile = begin; tile < end; tile += kThreads) {
-    uint32_t r = tile + threadIdx.x;
-    bool in = r < end;
-    for (uint32_t c = 0; c < a.ncols; c++) {  // pass 1: per-warp boundary counts
-      uint32_t key; bool null; bool b = in && ree_boundary(a, a.cols[c], r, &key, &null);
-      unsigned m = __ballot_sync(0xFFFFFFFFu, b);
-      if (lane == 0) s_wt[c][w] = (uint32_t)__popc(m);
-    }
-    __syncthreads();
-    for (uint32_t c = 0; c < a.ncols; c++) {  // pass 2: rank within the column and write
-      const ReeCol& col = a.cols[c];
-      uint32_t key = 0; bool null = false; bool b = in && ree_boundary(a, col, r, &key, &null);
-      unsigned m = __ballot_sync(0xFFFFFFFFu, b);
-      if (b) {
-        uint32_t k = s_base[c] + (uint32_t)__popc(m & ((1u << lane) - 1u));
-        for (int i = 0; i < w; i++) k += s_wt[c][i];
-        if (k > 0) col.run_ends[k - 1] = (int)r;  // run k starts at r => run k-1 ends at r
-        col.run_keys[k] = null ? kNull : key;
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x < a.ncols) {
-      uint32_t t = 0;
-      for (int i = 0; i < kWarps; i++) t += s_wt[threadIdx.x][i];
-      s_base[threadIdx.x] += t;
-    }
-    __syncthreads();
   }
 }
 
