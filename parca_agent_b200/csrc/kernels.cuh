@@ -545,12 +545,19 @@ struct UniqOffsetF {  // startOffset := indices.Len() at each first occurrence (
 // (2) per-row ListView offset/size: hit => reuse the first occurrence's (offset,size) (arrow_v2.go:293-299)
 __global__ void __launch_bounds__(kThreads) k_rows_materialize(uint32_t n_rows, const uint32_t* slot_of_row, const StackSlot* tab,
                                                                int* st_offsets, int* st_sizes) {
-  for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < n_rows; r += gridDim.x * kThreads) {
-    uint32_t s = slot_of_row[r];
-    int o = 0, z = 0;
-    if (s != kNull) { o = (int)tab[s].offset; z = (int)tab[s].size; }
-    st_offsets[r] = o;
-    st_sizes[r] = z;
+  const uint32_t stride = gridDim.x * kThreads * 4;
+  for (uint32_t base = blockIdx.x * kThreads * 4; base < n_rows; base += stride) {
+    uint32_t sl[4];
+    uint2 os[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { uint32_t r = base + u * kThreads + threadIdx.x; sl[u] = r < n_rows ? slot_of_row[r] : kNull; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) os[u] = sl[u] != kNull ? *reinterpret_cast<const uint2*>(&tab[sl[u]].offset) : make_uint2(0u, 0u);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      uint32_t r = base + u * kThreads + threadIdx.x;
+      if (r < n_rows) { st_offsets[r] = (int)os[u].x; st_sizes[r] = (int)os[u].y; }
+    }
   }
 }
 
@@ -604,25 +611,25 @@ struct FoJob {
   uint32_t* n_null;        // -> Counters (may be nullptr)
   Counters* ctr;
 };
-__device__ __forceinline__ uint32_t fo_hfind(const FoJob& j, uint32_t key) {
-  uint32_t idx = mix32(key) & j.hmask;
-  while ((uint32_t)(j.hslots[idx] >> 32) != key) idx = (idx + 1) & j.hmask;
+__device__ __forceinline__ uint32_t fo_hfind(const unsigned long long* hslots, uint32_t hmask, uint32_t key) {
+  uint32_t idx = mix32(key) & hmask;
+  while ((uint32_t)(hslots[idx] >> 32) != key) idx = (idx + 1) & hmask;
   return idx;
 }
-// bounded linear-probe insert of (key, pos) keeping the minimum pos; false = table full
-__device__ __forceinline__ bool hashed_min_insert(unsigned long long* hslots, uint32_t hmask, uint32_t key, uint32_t pos) {
+// bounded linear-probe insert of (key, pos) keeping the minimum pos; returns the slot, kNull = table full
+__device__ __forceinline__ uint32_t hashed_min_insert(unsigned long long* hslots, uint32_t hmask, uint32_t key, uint32_t pos) {
   unsigned long long packed = ((unsigned long long)key << 32) | pos;
   uint32_t idx = mix32(key) & hmask;
   for (uint32_t probe = 0; probe <= hmask; probe++) {
     unsigned long long cur = hslots[idx];
     if (cur == ~0ull) {
       cur = atomicCAS(&hslots[idx], ~0ull, packed);
-      if (cur == ~0ull) return true;
+      if (cur == ~0ull) return idx;
     }
-    if ((uint32_t)(cur >> 32) == key) { if (cur > packed) atomicMin(&hslots[idx], packed); return true; }
+    if ((uint32_t)(cur >> 32) == key) { if (cur > packed) atomicMin(&hslots[idx], packed); return idx; }
     idx = (idx + 1) & hmask;
   }
-  return false;
+  return kNull;
 }
 __global__ void __launch_bounds__(kThreads) k_fo_min(const FoJob* jobs) {
   const FoJob& j = jobs[blockIdx.y];
@@ -631,11 +638,7 @@ __global__ void __launch_bounds__(kThreads) k_fo_min(const FoJob* jobs) {
   for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     uint32_t key = j.keys[i];
     if (j.nullable && key == kNull) continue;
-    if (!j.hashed) {
-      if (j.first[key] > i) atomicMin(&j.first[key], i);
-    } else if (!hashed_min_insert(j.hslots, j.hmask, key, i)) {
-      atomicOr(&j.ctr->err, ERR_TABLE_FULL);
-    }
+    if (j.first[key] > i) atomicMin(&j.first[key], i);  // hashed jobs record first positions in their producer (k_ree_pass)
   }
 }
 __global__ void __launch_bounds__(kThreads) k_fo_zero(const FoJob* jobs) {  // clear only the bitmap words this batch will use
@@ -673,25 +676,32 @@ __global__ void __launch_bounds__(kThreads) k_fo_assign(const FoJob* jobs) {
     j.order[r] = key;
   }
 }
-// element -> dictionary index (+ validity bitmap, null count)
+// element -> dictionary index (+ validity bitmap, null count). Four independent elements per thread
+// keep enough loads in flight.
 __global__ void __launch_bounds__(kThreads) k_fo_map(const FoJob* jobs) {
   const FoJob& j = jobs[blockIdx.y];
   if (!j.out) return;
   uint32_t n = *j.n_ptr, begin, end;
   block_range(n, &begin, &end);
   uint32_t nulls = 0;
-  for (uint32_t tile = begin; tile < end; tile += kThreads) {
-    uint32_t i = tile + threadIdx.x;
-    bool in = i < end;
-    bool valid = false;
-    if (in) {
-      uint32_t key = j.keys[i];
-      valid = !(j.nullable && key == kNull);
-      j.out[i] = valid ? j.rank[j.hashed ? fo_hfind(j, key) : key] : 0u;
-      nulls += valid ? 0u : 1u;
+  for (uint32_t tile = begin; tile < end; tile += 4 * kThreads) {
+    uint32_t key[4], val[4];
+    bool valid[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      uint32_t i = tile + u * kThreads + threadIdx.x;
+      key[u] = i < end ? j.keys[i] : kNull;
+      valid[u] = i < end && !(j.nullable && key[u] == kNull);
     }
-    unsigned bits = __ballot_sync(0xFFFFFFFFu, valid);
-    if (j.validity && (threadIdx.x & 31) == 0 && tile + (threadIdx.x & ~31) < end) j.validity[i >> 5] = bits;
+#pragma unroll
+    for (int u = 0; u < 4; u++) val[u] = valid[u] ? j.rank[j.hashed ? fo_hfind(j.hslots, j.hmask, key[u]) : key[u]] : 0u;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      uint32_t i = tile + u * kThreads + threadIdx.x;
+      if (i < end) { j.out[i] = val[u]; nulls += valid[u] ? 0u : 1u; }
+      unsigned bits = __ballot_sync(0xFFFFFFFFu, valid[u]);
+      if (j.validity && (threadIdx.x & 31) == 0 && (i & ~31u) < end) j.validity[i >> 5] = bits;
+    }
   }
   if (j.n_null) {
     for (int d = 16; d > 0; d >>= 1) nulls += __shfl_down_sync(0xFFFFFFFFu, nulls, d);
@@ -856,7 +866,7 @@ __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
           if (k > 0) col.run_ends[k - 1] = (int)r;  // run k starts at r => run k-1 ends at r
           col.run_keys[k] = null ? kNull : key;
           if (has_dict && !null) {  // dictionary memo: first run that carries this value
-            if (col.hslots) { if (!hashed_min_insert(col.hslots, col.hmask, key, k)) atomicOr(&a.ctr->err, ERR_TABLE_FULL); }
+            if (col.hslots) { if (hashed_min_insert(col.hslots, col.hmask, key, k) == kNull) atomicOr(&a.ctr->err, ERR_TABLE_FULL); }
             else if (col.first[key] > k) atomicMin(&col.first[key], k);
           }
         }
