@@ -1,0 +1,42 @@
+"""Multi-rank path (mode A): pid-hash sharding, per-rank batches, max-over-ranks timing.
+CPU: gloo, world size 2. GPU: each shard through the CUDA path equals the oracle on that sub-stream."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from parca_agent_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_function_matches_xxh64(oracle):
+    for pid in [0, 1, 1000, 65535, 4242424, 2**32 - 1]:
+        assert synth.xxh64_u32(pid) == oracle.xxh64(int(pid).to_bytes(4, "little"), 0)
+
+
+def test_shards_partition_the_pid_space():
+    owners = {}
+    for rank in range(4):
+        w = synth._pid_shard("t", 1, rank, 4, 500, 50, 128, 16, synth.abi.PA_HASH_PROVIDED)
+        for p in np.unique(w.hdrs["pid"]):
+            assert owners.setdefault(int(p), rank) == rank
+            assert synth.xxh64_u32(int(p)) % 4 == rank
+
+
+def test_world_size_2_gloo():
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29513", os.path.join(ROOT, "tests", "dist_shard_check.py")], capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "shard-check ok world=2" in p.stdout
+
+
+@pytest.mark.gpu
+def test_each_shard_matches_oracle_on_gpu(oracle):
+    from parca_agent_b200 import lib
+    for rank in range(2):
+        w = synth._pid_shard("t", 0x5EED0002, rank, 2, 50_000, 2_000, 4_096, 64, synth.abi.PA_HASH_XXH64X2)
+        assert lib.run(w)[0] == oracle.run(w)[0]
