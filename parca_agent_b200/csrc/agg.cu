@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <condition_variable>
 #include <map>
 #include <mutex>
@@ -153,6 +154,8 @@ struct pa_agg {
   // ---- output
   uint8_t* out = nullptr;
   uint64_t out_cap = 0;
+  uint8_t* h_desc = nullptr;
+  size_t h_desc_cap = 0;
   std::vector<std::vector<uint8_t>> hostbufs;  // host-built Arrow buffers of the current result
   Timer tm[T_COUNT];
   uint32_t launches = 0;
@@ -302,7 +305,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   need(a->d_ustream, std::min<uint64_t>(NF, 0x7FFFFFFFull) * 4 + 256);
   need(a->d_uniq_row, N * 4); need(a->d_uniq_count, N * 4);
   need(a->d_ctr, sizeof(Counters));
-  need(a->d_partial, (uint64_t)a->G * kWarps * kMaxCols * sizeof(uint32_t) + (uint64_t)a->G * kMaxCols * 16 + 256);
+  need(a->d_partial, (uint64_t)a->sms * 8 * kWarps * kMaxCols * sizeof(uint32_t) + (uint64_t)a->G * kMaxCols * 16 + 256);
   if (!ok) return bail(PA_ENOMEM);
   *out = a;
   return PA_OK;
@@ -316,6 +319,7 @@ void pa_agg_destroy(pa_agg* a) {
   for (int r = 0; r < 2; r++) { if (a->ring[r].hdr) cudaFreeHost(a->ring[r].hdr); if (a->ring[r].frames) cudaFreeHost(a->ring[r].frames); }
   if (a->h_ctr_pinned) cudaFreeHost(a->h_ctr_pinned);
   if (a->out) cudaFreeHost(a->out);
+  if (a->h_desc) cudaFreeHost(a->h_desc);
   DBuf* all[] = {&a->d_hdr, &a->d_frames, &a->d_ts, &a->d_value, &a->d_uuid, &a->d_stoff, &a->d_stsize, &a->d_slot, &a->d_kind, &a->d_nfr,
                  &a->d_foff, &a->d_ls, &a->d_cpu, &a->d_tid, &a->d_comm, &a->d_ustream, &a->d_uniq_row, &a->d_uniq_count, &a->d_table, &a->d_ctr,
                  &a->d_arena, &a->d_partial, &a->d_lsmat, &a->d_kindtab, &a->d_cols, &a->d_jobs,
@@ -555,6 +559,65 @@ static int process_once(pa_agg* a) {
   const uint32_t mask = (uint32_t)(cap - 1);
   const int G = a->G;
 
+  // ---- dictionaries: jobs table
+  std::vector<FoJob> jobs;
+  auto job = [&](const uint32_t* keys, const uint32_t* n_ptr, uint32_t* first, uint32_t universe, uint32_t* rank, uint32_t* order, uint32_t* out,
+                 uint32_t* validity, uint32_t* bitmap, uint32_t* wprefix, uint32_t* n_unique, uint32_t* n_null, bool nullable, bool skip_min) {
+    FoJob j{};
+    j.keys = keys; j.n_ptr = n_ptr; j.first = first; j.universe = universe; j.rank = rank; j.order = order; j.out = out; j.validity = validity;
+    j.bitmap = bitmap; j.wprefix = wprefix; j.n_unique = n_unique; j.n_null = n_null; j.nullable = nullable; j.skip_min = skip_min; j.ctr = ctr;
+    jobs.push_back(j);
+    return (int)jobs.size() - 1;
+  };
+  // the low 32 bits of n_indices64 are the index count (overflow is flagged separately)
+  const uint32_t* n_idx_ptr = (const uint32_t*)&ctr->n_indices64;
+  int j_loc = job(a->d_ustream.as<uint32_t>(), n_idx_ptr, a->loc_first, n_frames, a->loc_rank, a->loc_order, a->d_ustream.as<uint32_t>(), nullptr,
+                  loc_bits, loc_wp, &ctr->n_locations, nullptr, false, true);
+  int j_type = job(a->sd_keys[0], &ctr->n_locations, a->sd_first[0], n_cstr, a->sd_rank[0], a->sd_order[0], a->sd_keys[0], nullptr, sd_bits[0], sd_wp[0], &ctr->n_dict_type, nullptr, false, false);
+  job(a->sd_keys[1], &ctr->n_locations, a->sd_first[1], n_cstr, a->sd_rank[1], a->sd_order[1], a->sd_keys[1], nullptr, sd_bits[1], sd_wp[1], &ctr->n_dict_map, nullptr, false, false);
+  job(a->sd_keys[2], &ctr->n_locations, a->sd_first[2], n_cstr, a->sd_rank[2], a->sd_order[2], a->sd_keys[2], a->sd_valid[2], sd_bits[2], sd_wp[2], &ctr->n_dict_bid, &ctr->null_bid, true, false);
+  job(a->fn_keys, &ctr->n_lines, a->fn_first, n_funcs, a->fn_rank, a->fn_order, a->fn_keys, nullptr, fn_bits, fn_wp, &ctr->n_functions, nullptr, false, false);
+  int j_file = job(a->sd_keys[3], &ctr->n_functions, a->sd_first[3], n_cstr, a->sd_rank[3], a->sd_order[3], a->sd_keys[3], a->sd_valid[3], sd_bits[3], sd_wp[3], &ctr->n_dict_file, &ctr->null_file, true, false);
+  int j_lab0 = (int)jobs.size();
+  for (uint32_t c = 0; c < nlab; c++) {
+    ColPlan& cp = a->cols[c];
+    bool nullable = cp.type == COL_LS || cp.type == COL_COMM;
+    // first positions are recorded by the REE emit pass (skip_min)
+    int ji = job(cp.run_keys, &ctr->n_runs[c], col_first[c], cp.universe, col_rank[c], cp.order, cp.run_keys, cp.validity, col_bits[c], col_wp[c],
+                 &ctr->n_dict[c], &ctr->n_null[c], nullable, true);
+    if (cp.type == COL_TID) { jobs[ji].hashed = 1; jobs[ji].hslots = a->tid_slots; jobs[ji].hmask = a->tid_mask; jobs[ji].rank = a->tid_rank; }
+  }
+  std::vector<ReeCol> rc(ncols);
+  ReeArgs ra{};
+  ra.c_cpu = ra.c_tid = ra.c_comm = -1;
+  for (uint32_t c = 0; c < ncols; c++) {
+    const ColPlan& cp = a->cols[c];
+    rc[c] = ReeCol{cp.type, cp.param, cp.run_ends, cp.run_keys, c < nlab ? col_first[c] : nullptr, nullptr, 0, 0};
+    if (cp.type == COL_TID) { rc[c].hslots = a->tid_slots; rc[c].hmask = a->tid_mask; }
+    if (cp.type == COL_CPU) ra.c_cpu = (int)c;
+    if (cp.type == COL_TID) ra.c_tid = (int)c;
+    if (cp.type == COL_COMM) ra.c_comm = (int)c;
+  }
+  // descriptor tables go up first, from pinned staging: a pageable cudaMemcpyAsync would synchronise the
+  // stream in the middle of the pipeline and leave the tail launch-bound
+  {
+    size_t jb = jobs.size() * sizeof(FoJob), cb = rc.size() * sizeof(ReeCol);
+    if (jb + cb > a->h_desc_cap) {
+      if (a->h_desc) cudaFreeHost(a->h_desc);
+      a->h_desc = nullptr;
+      a->h_desc_cap = 0;
+      CK(cudaHostAlloc((void**)&a->h_desc, (jb + cb) * 2, cudaHostAllocDefault));
+      a->h_desc_cap = (jb + cb) * 2;
+    }
+    memcpy(a->h_desc, jobs.data(), jb);
+    memcpy(a->h_desc + jb, rc.data(), cb);
+    CK(a->d_jobs.ensure(jb));
+    CK(a->d_cols.ensure(cb));
+    CK(cudaMemcpyAsync(a->d_jobs.p, a->h_desc, jb, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(a->d_cols.p, a->h_desc + jb, cb, cudaMemcpyHostToDevice, s));
+  }
+  const FoJob* djobs = a->d_jobs.as<FoJob>();
+
   CK(cudaEventRecord(a->tm[T_TOTAL].a, s));
   CK(cudaMemsetAsync(ctr, 0, sizeof(Counters), s));
   CK(cudaMemsetAsync(tab, 0, (cap + 2) * sizeof(StackSlot), s));
@@ -621,37 +684,6 @@ static int process_once(pa_agg* a) {
   a->tm[T_RANK].launches += 4;
   CK(cudaEventRecord(a->tm[T_RANK].b, s));
 
-  // ---- dictionaries: jobs table
-  std::vector<FoJob> jobs;
-  auto job = [&](const uint32_t* keys, const uint32_t* n_ptr, uint32_t* first, uint32_t universe, uint32_t* rank, uint32_t* order, uint32_t* out,
-                 uint32_t* validity, uint32_t* bitmap, uint32_t* wprefix, uint32_t* n_unique, uint32_t* n_null, bool nullable, bool skip_min) {
-    FoJob j{};
-    j.keys = keys; j.n_ptr = n_ptr; j.first = first; j.universe = universe; j.rank = rank; j.order = order; j.out = out; j.validity = validity;
-    j.bitmap = bitmap; j.wprefix = wprefix; j.n_unique = n_unique; j.n_null = n_null; j.nullable = nullable; j.skip_min = skip_min; j.ctr = ctr;
-    jobs.push_back(j);
-    return (int)jobs.size() - 1;
-  };
-  // the low 32 bits of n_indices64 are the index count (overflow is flagged separately)
-  const uint32_t* n_idx_ptr = (const uint32_t*)&ctr->n_indices64;
-  int j_loc = job(a->d_ustream.as<uint32_t>(), n_idx_ptr, a->loc_first, n_frames, a->loc_rank, a->loc_order, a->d_ustream.as<uint32_t>(), nullptr,
-                  loc_bits, loc_wp, &ctr->n_locations, nullptr, false, true);
-  int j_type = job(a->sd_keys[0], &ctr->n_locations, a->sd_first[0], n_cstr, a->sd_rank[0], a->sd_order[0], a->sd_keys[0], nullptr, sd_bits[0], sd_wp[0], &ctr->n_dict_type, nullptr, false, false);
-  job(a->sd_keys[1], &ctr->n_locations, a->sd_first[1], n_cstr, a->sd_rank[1], a->sd_order[1], a->sd_keys[1], nullptr, sd_bits[1], sd_wp[1], &ctr->n_dict_map, nullptr, false, false);
-  job(a->sd_keys[2], &ctr->n_locations, a->sd_first[2], n_cstr, a->sd_rank[2], a->sd_order[2], a->sd_keys[2], a->sd_valid[2], sd_bits[2], sd_wp[2], &ctr->n_dict_bid, &ctr->null_bid, true, false);
-  job(a->fn_keys, &ctr->n_lines, a->fn_first, n_funcs, a->fn_rank, a->fn_order, a->fn_keys, nullptr, fn_bits, fn_wp, &ctr->n_functions, nullptr, false, false);
-  int j_file = job(a->sd_keys[3], &ctr->n_functions, a->sd_first[3], n_cstr, a->sd_rank[3], a->sd_order[3], a->sd_keys[3], a->sd_valid[3], sd_bits[3], sd_wp[3], &ctr->n_dict_file, &ctr->null_file, true, false);
-  int j_lab0 = (int)jobs.size();
-  for (uint32_t c = 0; c < nlab; c++) {
-    ColPlan& cp = a->cols[c];
-    bool nullable = cp.type == COL_LS || cp.type == COL_COMM;
-    // first positions are recorded by the REE emit pass (skip_min)
-    int ji = job(cp.run_keys, &ctr->n_runs[c], col_first[c], cp.universe, col_rank[c], cp.order, cp.run_keys, cp.validity, col_bits[c], col_wp[c],
-                 &ctr->n_dict[c], &ctr->n_null[c], nullable, true);
-    if (cp.type == COL_TID) { jobs[ji].hashed = 1; jobs[ji].hslots = a->tid_slots; jobs[ji].hmask = a->tid_mask; jobs[ji].rank = a->tid_rank; }
-  }
-  CK(a->d_jobs.ensure(jobs.size() * sizeof(FoJob)));
-  CK(cudaMemcpyAsync(a->d_jobs.p, jobs.data(), jobs.size() * sizeof(FoJob), cudaMemcpyHostToDevice, s));
-  const FoJob* djobs = a->d_jobs.as<FoJob>();
   auto run_jobs = [&](int first, int count, bool need_min, Timer& t) {
     dim3 grid(G, count);
     k_fo_zero<<<grid, kThreads, 0, s>>>(djobs + first);
@@ -675,30 +707,20 @@ static int process_once(pa_agg* a) {
   CK(cudaEventRecord(a->tm[T_LOC].b, s));
 
   // ---- run-end encoding of label + constant columns (dictionary first positions recorded on the fly)
+  if (getenv("PA_DEBUG_SYNC")) CK(cudaStreamSynchronize(s));
   CK(cudaEventRecord(a->tm[T_LABELS].a, s));
-  std::vector<ReeCol> rc(ncols);
-  ReeArgs ra{};
-  ra.c_cpu = ra.c_tid = ra.c_comm = -1;
-  for (uint32_t c = 0; c < ncols; c++) {
-    const ColPlan& cp = a->cols[c];
-    rc[c] = ReeCol{cp.type, cp.param, cp.run_ends, cp.run_keys, c < nlab ? col_first[c] : nullptr, nullptr, 0, 0};
-    if (cp.type == COL_TID) { rc[c].hslots = a->tid_slots; rc[c].hmask = a->tid_mask; }
-    if (cp.type == COL_CPU) ra.c_cpu = (int)c;
-    if (cp.type == COL_TID) ra.c_tid = (int)c;
-    if (cp.type == COL_COMM) ra.c_comm = (int)c;
-  }
-  CK(a->d_cols.ensure(rc.size() * sizeof(ReeCol)));
-  CK(cudaMemcpyAsync(a->d_cols.p, rc.data(), rc.size() * sizeof(ReeCol), cudaMemcpyHostToDevice, s));
   ra.n_rows = (uint32_t)N; ra.ncols = ncols; ra.n_ls = a->n_lscols; ra.c_kind = nlab; ra.cols = a->d_cols.as<ReeCol>();
   ra.ls = a->d_ls.as<uint32_t>(); ra.cpu = a->d_cpu.as<uint32_t>(); ra.tid = a->d_tid.as<uint32_t>(); ra.comm = a->d_comm.as<uint32_t>(); ra.kind = a->d_kind.as<uint8_t>();
   ra.lsmat = a->d_lsmat.as<uint32_t>(); ra.n_lscols = std::max<uint32_t>(1, a->n_lscols); ra.kindtab = a->d_kindtab.as<uint32_t>();
   ra.partial = a->d_partial.as<uint32_t>(); ra.ctr = ctr;
-  k_ree_pass<false><<<G, kThreads, 0, s>>>(ra);
-  k_ree_scan_partials<<<ncols, 32, 0, s>>>(ra, G * kWarps);
-  k_ree_pass<true><<<G, kThreads, 0, s>>>(ra);
+  const int Gr = a->sms * 8;  // latency-bound passes: fill every warp slot
+  k_ree_pass<false><<<Gr, kThreads, 0, s>>>(ra);
+  k_ree_scan_partials<<<ncols, 32, 0, s>>>(ra, Gr * kWarps);
+  k_ree_pass<true><<<Gr, kThreads, 0, s>>>(ra);
   a->tm[T_LABELS].launches += 3;
   CK(cudaEventRecord(a->tm[T_LABELS].b, s));
 
+  if (getenv("PA_DEBUG_SYNC")) CK(cudaStreamSynchronize(s));
   CK(cudaEventRecord(a->tm[T_DICTS].a, s));
   if (nlab) run_jobs(j_lab0, (int)nlab, false, a->tm[T_DICTS]);  // label dictionaries over the runs
   CK(cudaEventRecord(a->tm[T_DICTS].b, s));

@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(kThreads) k_gather_unique(const Counters* ctr,
       uint32_t pos = e.offset + jx;
       if (fid >= n_frames_registered) { atomicOr(&ctr_w->err, ERR_BAD_FRAME_ID); fid = 0; }
       ustream[pos] = (uint32_t)fid;
-      atomicMin(&loc_first[(uint32_t)fid], pos);
+      if (loc_first[(uint32_t)fid] > pos) atomicMin(&loc_first[(uint32_t)fid], pos);
     }
   }
 }
@@ -831,7 +831,9 @@ __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
   __shared__ uint32_t s_kind[64];
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __shared__ ReeCol s_cols[kMaxCols];  // column descriptors: no dependent global loads on the write path
   if (threadIdx.x < 64) s_kind[threadIdx.x] = a.kindtab[threadIdx.x];
+  for (uint32_t c = threadIdx.x; c < a.ncols; c += kThreads) s_cols[c] = a.cols[c];
   uint32_t begin, end, wg;
   warp_range(a.n_rows, &begin, &end, &wg);
   const uint32_t nwarps = gridDim.x * kWarps;
@@ -840,10 +842,12 @@ __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
   RowIn carry{0, 0, 0, 0, 0};
   if (begin < end && begin > 0) carry = ree_load(a, begin - 1);  // every lane loads the same row (broadcast)
   const unsigned lt = (1u << lane) - 1u;
+  RowIn nx = (begin + lane < end) ? ree_load(a, begin + lane) : RowIn{0, 0, 0, 0, 0};
   for (uint32_t base = begin; base < end; base += 32) {
     const uint32_t r = base + lane;
     const bool in = r < end;
-    RowIn x = in ? ree_load(a, r) : RowIn{0, 0, 0, 0, 0};
+    RowIn x = nx;
+    if (r + 32 < end) nx = ree_load(a, r + 32);  // next step's inputs are in flight while this step is encoded
     RowIn p = ree_shfl_up1(x);
     if (lane == 0) p = carry;
     const bool first_row = r == 0;
@@ -861,7 +865,7 @@ __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
         if (m == 0) return;
         uint32_t pos0 = s_acc[c][w];
         if (boundary) {
-          const ReeCol& col = a.cols[c];
+          const ReeCol& col = s_cols[c];
           uint32_t k = pos0 + (uint32_t)__popc(m & lt);
           if (k > 0) col.run_ends[k - 1] = (int)r;  // run k starts at r => run k-1 ends at r
           col.run_keys[k] = null ? kNull : key;
@@ -878,11 +882,11 @@ __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
     // ---- labelset-derived columns
     const bool same_ls = !first_row && x.ls == p.ls;
     for (uint32_t c = 0; c < a.n_ls; c++) {
-      uint32_t v = in ? a.lsmat[(size_t)x.ls * a.n_lscols + c] : kNull;
+      uint32_t v = in ? __ldg(&a.lsmat[(size_t)x.ls * a.n_lscols + c]) : kNull;
       bool null = v == kNull;
       bool b = true;
       if (!null && !first_row) {
-        uint32_t pv = same_ls ? v : a.lsmat[(size_t)p.ls * a.n_lscols + c];
+        uint32_t pv = same_ls ? v : __ldg(&a.lsmat[(size_t)p.ls * a.n_lscols + c]);
         b = pv != v;  // also true when the previous row had no value (pv == kNull)
       }
       column(c, b, null, v, true);
