@@ -134,6 +134,7 @@ struct pa_agg {
   std::vector<uint64_t> chunk_frames_end;
   cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_d2h0 = nullptr, ev_d2h1 = nullptr;
   bool processed = false, hash_timed = false;
+  int hash_variant = 0;  // 0 = direct global loads (default, faster), 1 = cp.async-staged (PA_HASH_VARIANT=direct|staged)
 
   // ---- device batch buffers
   DBuf d_hdr, d_frames, d_ts, d_value, d_uuid, d_stoff, d_stsize, d_slot, d_kind, d_nfr, d_foff, d_ls, d_cpu, d_tid, d_comm;
@@ -283,6 +284,8 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   for (uint32_t i = 0; i < cfg->n_external_labels; i++) {  // resolved to canonical ids lazily at flush (strings may come later)
     a->external.emplace_back(cfg->external_labels[i].name_sid, cfg->external_labels[i].value_sid);
   }
+  if (const char* hv = getenv("PA_HASH_VARIANT")) a->hash_variant = strcmp(hv, "staged") == 0 ? 1 : 0;
+  if (cudaFuncSetAttribute(k_hash_insert_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashStagedSmem) != cudaSuccess) return bail(PA_EIO);
   if (cudaStreamCreateWithFlags(&a->s_copy, cudaStreamNonBlocking) != cudaSuccess) return bail(PA_EIO);
   if (cudaStreamCreateWithFlags(&a->s_comp, cudaStreamNonBlocking) != cudaSuccess) return bail(PA_EIO);
   cudaEventCreate(&a->ev_h2d0);
@@ -649,8 +652,9 @@ static int process_once(pa_agg* a) {
     ha.row0 = (uint32_t)r0; ha.row1 = (uint32_t)r1; ha.uuid = a->d_uuid.as<uint8_t>();
     ha.slot_of_row = a->d_slot.as<uint32_t>(); ha.tab = tab; ha.mask = mask; ha.ctr = ctr;
     uint64_t rows = r1 - r0;
-    int blocks = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)a->sms * 3);
-    k_hash_insert<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
+    int blocks = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)a->sms * (a->hash_variant == 1 ? 3 : 4));
+    if (a->hash_variant == 1) k_hash_insert_staged<<<std::max(blocks, 1), kThreads, kHashStagedSmem, s>>>(ha);
+    else k_hash_insert<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     a->tm[T_HASH].launches++;
   };
   CK(cudaEventRecord(a->tm[T_HEADER].a, s));

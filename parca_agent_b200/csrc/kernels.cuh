@@ -332,7 +332,7 @@ __device__ __forceinline__ unsigned long long xxh_finish_own(const unsigned long
   return xxh_avalanche(h);
 }
 
-__global__ void __launch_bounds__(kThreads, 3) k_hash_insert(HashArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) k_hash_insert(HashArgs a) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, j = lane & 3, g = lane >> 2;
   const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
@@ -387,6 +387,127 @@ __global__ void __launch_bounds__(kThreads, 3) k_hash_insert(HashArgs a) {
     uint32_t slot = warp_insert(a.tab, a.mask, k, r, valid, a.ctr);
     if (valid) a.slot_of_row[r] = slot;
   }
+}
+
+// Variant C: same arithmetic and epilogue as k_hash_insert, but the frame ids reach the XXH64 lanes
+// through shared memory: every warp owns a two-stage ring (8 samples x 544 B per stage) that it fills
+// with cp.async (LDGSTS, 16 B per lane = one coalesced 512-B sample per instruction, no registers
+// held) one sub-step ahead of the one it is hashing. Loads are therefore in flight *all the time*
+// instead of only between compute bursts, and the 8-byte LDS reads are bank-conflict free thanks to
+// the 32-byte pad per sample slot (half-warp = 4 samples x 4 lanes -> 32 distinct banks).
+constexpr int kSlotBytes = 64 * 8 + 32;          // one sample of up to 64 frames + pad
+constexpr int kStageBytes = 8 * kSlotBytes;      // 8 samples
+constexpr int kHashStagedSmem = kWarps * 2 * kStageBytes;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ unsigned long long lds64(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+// stage the 8 samples owned by lanes sub*8 .. sub*8+7 (n <= 64 frames each) into `stage`
+__device__ __forceinline__ void stage_samples(const unsigned long long* frames, uint32_t n_me, unsigned long long off_me, int sub, uint32_t stage,
+                                              int lane) {
+  const unsigned full = 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t n = __shfl_sync(full, n_me, sub * 8 + i);
+    const unsigned long long off = __shfl_sync(full, off_me, sub * 8 + i);
+    const unsigned long long* src = frames + off;
+    const uint32_t dst = stage + i * kSlotBytes;
+    if ((off & 1ull) == 0) {  // 16-byte aligned source: one 16-byte copy per lane covers words 2l, 2l+1
+      const uint32_t w = 2u * lane;
+      if (w + 1 < n) cp_async16(dst + 8 * w, src + w);
+      else if (w < n) cp_async8(dst + 8 * w, src + w);
+    } else {                  // odd word offset: 8-byte copies
+      if ((uint32_t)lane < n) cp_async8(dst + 8 * lane, src + lane);
+      if ((uint32_t)lane + 32 < n) cp_async8(dst + 8 * (lane + 32), src + lane + 32);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 3) k_hash_insert_staged(HashArgs a) {
+  extern __shared__ __align__(16) uint8_t hsmem[];
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, j = lane & 3, g = lane >> 2, wib = threadIdx.x >> 5;
+  const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+  const uint32_t span = a.row1 - a.row0;
+  const uint32_t iters = (span + nwarps * 32 - 1) / (nwarps * 32);
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(hsmem) + wib * 2 * kStageBytes;
+
+  auto batch_row = [&](uint32_t it) { return a.row0 + (it * nwarps + warp) * 32 + lane; };
+  uint32_t r = batch_row(0);
+  bool valid = r < a.row1;
+  uint32_t n_me = valid ? a.nframes[r] : 0u;
+  unsigned long long off_me = valid ? a.frame_off[r] : 0ull;
+  bool staged = __all_sync(full, n_me <= 64u);
+  if (iters && staged) stage_samples(a.frames, n_me, off_me, 0, ring, lane);
+  cp_async_commit();
+
+  for (uint32_t it = 0; it < iters; it++) {
+    // the next batch's sizes/offsets (its first sub-step is staged during this batch's last one)
+    uint32_t r_nx = batch_row(it + 1);
+    bool valid_nx = (it + 1 < iters) && r_nx < a.row1;
+    uint32_t n_nx = valid_nx ? a.nframes[r_nx] : 0u;
+    unsigned long long off_nx = valid_nx ? a.frame_off[r_nx] : 0ull;
+    bool staged_nx = __all_sync(full, n_nx <= 64u);
+
+    unsigned long long v0[4], v1[4];
+#pragma unroll
+    for (int sub = 0; sub < 4; sub++) {
+      const uint32_t cur = ring + (sub & 1) * kStageBytes, nxt = ring + ((sub + 1) & 1) * kStageBytes;
+      if (sub < 3) { if (staged) stage_samples(a.frames, n_me, off_me, sub + 1, nxt, lane); }
+      else if (it + 1 < iters && staged_nx) stage_samples(a.frames, n_nx, off_nx, 0, nxt, lane);
+      cp_async_commit();
+      cp_async_wait<1>();  // everything but the group just committed has landed
+      __syncwarp(full);
+      const int src = sub * 8 + g;
+      const uint32_t n = __shfl_sync(full, n_me, src);
+      const unsigned long long off = __shfl_sync(full, off_me, src);
+      unsigned long long a0 = xxh_lane_init(0ull, j), a1 = xxh_lane_init(kSeedLo, j);
+      const uint32_t ns = n >> 2;
+      if (staged) {
+        const uint32_t q = cur + g * kSlotBytes + 8 * j;
+        uint32_t s = 0;
+        for (; s + 8 <= ns; s += 8) {
+          unsigned long long w[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) w[u] = lds64(q + 32 * (s + u));
+#pragma unroll
+          for (int u = 0; u < 8; u++) { unsigned long long m = w[u] * XP2; a0 = xxh_round_pre(a0, m); a1 = xxh_round_pre(a1, m); }
+        }
+        for (; s < ns; s++) { unsigned long long m = lds64(q + 32 * s) * XP2; a0 = xxh_round_pre(a0, m); a1 = xxh_round_pre(a1, m); }
+      } else {  // a stack deeper than one slot in this batch: stream it from global memory
+        const unsigned long long* q = a.frames + off + j;
+        for (uint32_t s = 0; s < ns; s++) { unsigned long long m = ldg_stream64(q + 4 * s) * XP2; a0 = xxh_round_pre(a0, m); a1 = xxh_round_pre(a1, m); }
+      }
+      __syncwarp(full);  // all lanes are done with `cur` before the next sub-step refills it
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        unsigned long long x0 = __shfl_sync(full, a0, 4 * (lane & 7) + jj), x1 = __shfl_sync(full, a1, 4 * (lane & 7) + jj);
+        if ((lane >> 3) == sub) { v0[jj] = x0; v1[jj] = x1; }
+      }
+    }
+    const uint32_t nt = n_me & 3u;
+    const unsigned long long* tp = a.frames + off_me + (n_me & ~3u);
+    unsigned long long t0 = nt > 0 ? ldg_stream64(tp) : 0ull, t1 = nt > 1 ? ldg_stream64(tp + 1) : 0ull, t2 = nt > 2 ? ldg_stream64(tp + 2) : 0ull;
+    Key128 k;
+    k.hi = xxh_finish_own(v0, 0ull, n_me, t0, t1, t2);
+    k.lo = xxh_finish_own(v1, kSeedLo, n_me, t0, t1, t2);
+    if (valid) *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = make_ulonglong2(bswap64(k.hi), bswap64(k.lo));
+    uint32_t slot = warp_insert(a.tab, a.mask, k, r, valid, a.ctr);
+    if (valid) a.slot_of_row[r] = slot;
+    r = r_nx; valid = valid_nx; n_me = n_nx; off_me = off_nx; staged = staged_nx;
+  }
+  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------

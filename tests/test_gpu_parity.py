@@ -149,3 +149,62 @@ def test_bad_ids_are_reported(gpu):
     with pytest.raises(gpu.PaError):
         a.flush()
     a.close()
+
+
+@pytest.mark.parametrize("variant", ["direct", "staged"])
+def test_hash_kernel_variants(oracle, gpu, variant, monkeypatch):
+    """Both hash kernels (direct global loads / cp.async-staged) must produce identical bytes, including
+    ragged stacks, odd frame offsets (8-byte staging path) and stacks deeper than one staging slot."""
+    monkeypatch.setenv("PA_HASH_VARIANT", variant)
+    assert_same(oracle, gpu, synth.edge_workload(seed=41, n=5000, hash_mode=abi.PA_HASH_XXH64X2))
+    assert_same(oracle, gpu, synth.config1())
+    # 100-frame stacks exceed the 64-frame staging slot: the kernel must fall back per batch
+    rng = np.random.Generator(np.random.PCG64(5))
+    w = synth.config1().head(4000)
+    deep = rng.integers(0, 4096, (4000, 100), dtype=np.uint64)
+    w.stack_table, w.stack_choice = None, None
+    w._frame_ids = deep.reshape(-1)
+    w.hdrs["nframes"] = 100
+    w.hdrs["frame_off"] = np.arange(4000, dtype=np.uint64) * np.uint64(100)
+    w.hdrs["nframes"][::7] = 63  # mixed depths inside one warp batch (frames stay where they are)
+    assert_same(oracle, gpu, w)
+
+
+def test_large_batch_properties(oracle, gpu):
+    """Size-independent properties on a batch too large for the oracle to be the only check
+    (2M samples x 64 frames): unique counts, ListView consistency, ids == XXH64x2 of the frames on a
+    sample of rows, run-end monotonicity, dictionary uniqueness, and an oracle comparison on a prefix."""
+    w = synth.config2(n=2_000_000, u=50_000, p=65_536)
+    a = gpu.from_workload(w, chunk_samples=1 << 18)
+    gpu.load(a, w)
+    res = a.flush()
+    assert res.n_rows == w.n and res.n_unique_stacks == len(np.unique(w.stack_choice))
+    t = pa.ipc.open_stream(pa.py_buffer(res.ipc)).read_all()
+    assert t.num_rows == w.n
+    st = t.column("stacktrace").chunk(0)
+    off, size = st.offsets.to_numpy(), st.sizes.to_numpy()
+    assert (size == 64).all() and off.min() == 0 and off.max() + 64 == len(st.values) == res.n_location_indices
+    # rows with the same stack share (offset, size); first occurrences appear in increasing offset order
+    first = {}
+    for r in range(0, w.n, 997):
+        first.setdefault(int(w.stack_choice[r]), int(off[r]))
+        assert first[int(w.stack_choice[r])] == int(off[r])
+    uniq_off = off[np.sort(np.unique(w.stack_choice, return_index=True)[1])]
+    assert (np.diff(uniq_off) == 64).all()
+    ids = t.column("stacktrace_id").chunk(0).storage
+    fr = w.stack_table
+    for r in range(0, w.n, 100_003):
+        data = fr[w.stack_choice[r]].astype("<u8").tobytes()
+        want = oracle.xxh64(data, 0).to_bytes(8, "big") + oracle.xxh64(data, abi.PA_XXH_SEED_LO).to_bytes(8, "big")
+        assert ids[r].as_py() == want
+    labels = t.column("labels").chunk(0)
+    for i in range(labels.type.num_fields):
+        col = labels.field(i)
+        re_ = col.run_ends.to_numpy()
+        assert (np.diff(re_) > 0).all() and re_[-1] == w.n
+        d = col.values.dictionary.to_pylist()
+        assert len(d) == len(set(d))
+    assert t.column("timestamp").chunk(0).cast(pa.int64()).to_numpy().tolist()[:3] == w.hdrs["timestamp_ns"][:3].tolist()
+    a.close()
+    sub = w.head(50_000)
+    assert gpu.run(sub)[0] == oracle.run(sub)[0]
