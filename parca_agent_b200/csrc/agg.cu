@@ -138,7 +138,7 @@ struct pa_agg {
 
   // ---- device batch buffers
   DBuf d_hdr, d_frames, d_ts, d_value, d_uuid, d_stoff, d_stsize, d_slot, d_kind, d_nfr, d_foff, d_ls, d_cpu, d_tid, d_comm;
-  DBuf d_ustream, d_uniq_row, d_uniq_count, d_table, d_ctr, d_arena, d_partial;
+  DBuf d_ustream, d_uniq_row, d_uniq_count, d_table, d_ctr, d_arena, d_partial, d_ree_partial;
   uint64_t table_cap = 0, retry_cap = 0, tid_cap = 0, retry_tcap = 0, prev_tids = 0;
   uint64_t prev_unique = 0;
   Counters h_ctr{};
@@ -308,7 +308,8 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   need(a->d_ustream, std::min<uint64_t>(NF, 0x7FFFFFFFull) * 4 + 256);
   need(a->d_uniq_row, N * 4); need(a->d_uniq_count, N * 4);
   need(a->d_ctr, sizeof(Counters));
-  need(a->d_partial, (uint64_t)a->sms * 8 * kWarps * kMaxCols * sizeof(uint32_t) + (uint64_t)a->G * kMaxCols * 16 + 256);
+  need(a->d_partial, (uint64_t)a->G * kMaxCols * 16 + 256);
+  need(a->d_ree_partial, (uint64_t)a->sms * 8 * kWarps * kMaxCols * sizeof(uint32_t) + 256);  // lives across the ranking launches between the two REE passes
   if (!ok) return bail(PA_ENOMEM);
   *out = a;
   return PA_OK;
@@ -325,7 +326,7 @@ void pa_agg_destroy(pa_agg* a) {
   if (a->h_desc) cudaFreeHost(a->h_desc);
   DBuf* all[] = {&a->d_hdr, &a->d_frames, &a->d_ts, &a->d_value, &a->d_uuid, &a->d_stoff, &a->d_stsize, &a->d_slot, &a->d_kind, &a->d_nfr,
                  &a->d_foff, &a->d_ls, &a->d_cpu, &a->d_tid, &a->d_comm, &a->d_ustream, &a->d_uniq_row, &a->d_uniq_count, &a->d_table, &a->d_ctr,
-                 &a->d_arena, &a->d_partial, &a->d_lsmat, &a->d_kindtab, &a->d_cols, &a->d_jobs,
+                 &a->d_arena, &a->d_partial, &a->d_ree_partial, &a->d_lsmat, &a->d_kindtab, &a->d_cols, &a->d_jobs,
                  &a->m_addr.buf, &a->m_line.buf, &a->m_type.buf, &a->m_map.buf, &a->m_bid.buf, &a->m_func.buf, &a->m_fnfile.buf, &a->m_sid2cid.buf};
   for (DBuf* b : all) b->release();
   for (auto e : a->chunk_ev) cudaEventDestroy(e);
@@ -458,14 +459,17 @@ static int stage_async(pa_agg* a) {
 }
 
 template <class F>
-static void launch_scan(pa_agg* a, F f, int njobs, Timer& t) {
-  dim3 grid(a->G, njobs);
+static void launch_scan(pa_agg* a, F f, int njobs, Timer& t, int gx = 0) {
+  if (gx <= 0) gx = a->G;
+  dim3 grid(gx, njobs);
   typename F::T* partial = a->d_partial.as<typename F::T>();
   k_scan_reduce<F><<<grid, kThreads, 0, a->s_comp>>>(f, partial);
-  k_scan_partials<F><<<njobs, 32, 0, a->s_comp>>>(f, partial, a->G);
+  k_scan_partials<F><<<njobs, 32, 0, a->s_comp>>>(f, partial, gx);
   k_scan_emit<F><<<grid, kThreads, 0, a->s_comp>>>(f, partial);
   t.launches += 3;
 }
+// grid for a pass over at most `bound` elements: >= 2048 elements per CTA, never more than the full grid
+static int small_grid(const pa_agg* a, uint64_t bound) { return (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)a->G, (bound + 2047) / 2048)); }
 
 static int upload_tables(pa_agg* a) {
   std::lock_guard<std::mutex> g(a->reg_mu);
@@ -536,7 +540,7 @@ static int process_once(pa_agg* a) {
     want(&cp.run_ends, Nn * 4);
     want(&cp.run_keys, Nn * 4);
     if (c >= nlab) continue;
-    want(&cp.validity, (Nn / 32 + 2) * 4);
+    want(&cp.validity, (Nn / 32 + 2) * 4, 1);
     want(&col_bits[c], (Nn / 32 + 2) * 4); want(&col_wp[c], (Nn / 32 + 2) * 4);
     if (cp.type == COL_COMM) cp.universe = n_cstr;
     if (cp.type == COL_TID) {
@@ -585,9 +589,10 @@ static int process_once(pa_agg* a) {
   for (uint32_t c = 0; c < nlab; c++) {
     ColPlan& cp = a->cols[c];
     bool nullable = cp.type == COL_LS || cp.type == COL_COMM;
-    // first positions are recorded by the REE emit pass (skip_min)
-    int ji = job(cp.run_keys, &ctr->n_runs[c], col_first[c], cp.universe, col_rank[c], cp.order, cp.run_keys, cp.validity, col_bits[c], col_wp[c],
-                 &ctr->n_dict[c], &ctr->n_null[c], nullable, true);
+    // first ROWS are recorded by the REE count pass (skip_min); the emit pass applies the ranks itself (no map pass)
+    int ji = job(nullptr, nullptr, col_first[c], cp.universe, col_rank[c], cp.order, nullptr, nullptr, col_bits[c], col_wp[c],
+                 &ctr->n_dict[c], nullptr, nullable, true);
+    jobs[ji].n_imm = (uint32_t)N;
     if (cp.type == COL_TID) { jobs[ji].hashed = 1; jobs[ji].hslots = a->tid_slots; jobs[ji].hmask = a->tid_mask; jobs[ji].rank = a->tid_rank; }
   }
   std::vector<ReeCol> rc(ncols);
@@ -595,8 +600,9 @@ static int process_once(pa_agg* a) {
   ra.c_cpu = ra.c_tid = ra.c_comm = -1;
   for (uint32_t c = 0; c < ncols; c++) {
     const ColPlan& cp = a->cols[c];
-    rc[c] = ReeCol{cp.type, cp.param, cp.run_ends, cp.run_keys, c < nlab ? col_first[c] : nullptr, nullptr, 0, 0};
-    if (cp.type == COL_TID) { rc[c].hslots = a->tid_slots; rc[c].hmask = a->tid_mask; }
+    rc[c] = ReeCol{cp.type, cp.param, cp.run_ends, cp.run_keys, c < nlab ? col_first[c] : nullptr, nullptr, 0,
+                   (cp.type == COL_LS || cp.type == COL_COMM) ? 1u : 0u, c < nlab ? col_rank[c] : nullptr, c < nlab ? cp.validity : nullptr};
+    if (cp.type == COL_TID) { rc[c].hslots = a->tid_slots; rc[c].hmask = a->tid_mask; rc[c].rank = a->tid_rank; }
     if (cp.type == COL_CPU) ra.c_cpu = (int)c;
     if (cp.type == COL_TID) ra.c_tid = (int)c;
     if (cp.type == COL_COMM) ra.c_comm = (int)c;
@@ -676,38 +682,40 @@ static int process_once(pa_agg* a) {
   // ---- unique stacks: ordinals from the first-row bitmap, offsets from a scan over the unique list
   CK(cudaEventRecord(a->tm[T_RANK].a, s));
   const uint32_t nslots = (uint32_t)(cap + 2);
-  const int Gs = std::max(1, (int)std::min<uint64_t>(G, (nslots + kThreads - 1) / kThreads));
-  k_stack_bits<<<Gs, kThreads, 0, s>>>(tab, nslots, rowbits);
-  launch_scan(a, WordsF{rowbits, row_wprefix, (uint32_t)((N + 31) / 32), &ctr->n_unique}, 1, a->tm[T_RANK]);
-  k_stack_assign<<<Gs, kThreads, 0, s>>>(tab, nslots, rowbits, row_wprefix, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(),
-                                         a->d_uniq_count.as<uint32_t>(), uniq_slot, uniq_size);
-  launch_scan(a, UniqOffsetF{ctr, ctr, uniq_size, uniq_slot, tab}, 1, a->tm[T_RANK]);
+  const int Gs = small_grid(a, nslots), Gw = small_grid(a, N / 32 + 1), Gu = small_grid(a, std::min<uint64_t>(N, cap / 2));
+    k_stack_bits<<<Gs, kThreads, 0, s>>>(tab, nslots, rowbits);
+    launch_scan(a, WordsF{rowbits, row_wprefix, (uint32_t)((N + 31) / 32), &ctr->n_unique}, 1, a->tm[T_RANK], Gw);
+    k_stack_assign<<<Gs, kThreads, 0, s>>>(tab, nslots, rowbits, row_wprefix, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(),
+                                           a->d_uniq_count.as<uint32_t>(), uniq_slot, uniq_size);
+    launch_scan(a, UniqOffsetF{ctr, ctr, uniq_size, uniq_slot, tab}, 1, a->tm[T_RANK], Gu);
+    a->tm[T_RANK].launches += 2;
   k_rows_materialize<<<G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>());
   k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, a->d_frames.as<unsigned long long>(),
                                          a->d_foff.as<unsigned long long>(), n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr);
-  a->tm[T_RANK].launches += 4;
+  a->tm[T_RANK].launches += 2;
   CK(cudaEventRecord(a->tm[T_RANK].b, s));
 
-  auto run_jobs = [&](int first, int count, bool need_min, Timer& t) {
-    dim3 grid(G, count);
-    k_fo_zero<<<grid, kThreads, 0, s>>>(djobs + first);
-    if (need_min) { k_fo_min<<<grid, kThreads, 0, s>>>(djobs + first); t.launches++; }
-    k_fo_bits<<<grid, kThreads, 0, s>>>(djobs + first);
-    launch_scan(a, FoWordsF{djobs + first}, count, t);
-    k_fo_assign<<<grid, kThreads, 0, s>>>(djobs + first);
-    k_fo_map<<<grid, kThreads, 0, s>>>(djobs + first);
-    t.launches += 4;
+  // elem_bound: upper bound on elements per job; table_bound: on table entries; both pick right-sized grids
+  auto run_jobs = [&](int first, int count, bool need_min, Timer& t, uint64_t elem_bound, uint64_t table_bound, bool do_map = true) {
+    const int ge = small_grid(a, elem_bound), gt = small_grid(a, table_bound), gw = small_grid(a, elem_bound / 32 + 1);
+    k_fo_zero<<<dim3(gw, count), kThreads, 0, s>>>(djobs + first);
+    if (need_min) { k_fo_min<<<dim3(ge, count), kThreads, 0, s>>>(djobs + first); t.launches++; }
+    k_fo_bits<<<dim3(gt, count), kThreads, 0, s>>>(djobs + first);
+    launch_scan(a, FoWordsF{djobs + first, -1}, count, t, gw);
+    k_fo_assign<<<dim3(gt, count), kThreads, 0, s>>>(djobs + first);
+    if (do_map) { k_fo_map<<<dim3(ge, count), kThreads, 0, s>>>(djobs + first); t.launches++; }
+    t.launches += 3;
   };
 
   CK(cudaEventRecord(a->tm[T_LOC].a, s));
-  run_jobs(j_loc, 1, false, a->tm[T_LOC]);  // location index per unique-stack frame (in place over the gathered stream)
   FrameTable ftd{(const unsigned long long*)a->m_addr.ptr(), a->m_type.ptr(), a->m_map.ptr(), a->m_bid.ptr(), (const unsigned long long*)a->m_line.ptr(), a->m_func.ptr()};
-  launch_scan(a, LocLinesF{ctr, ctr, a->loc_order, ftd, a->lo}, 1, a->tm[T_LOC]);
-  k_line_validity<<<std::max(1, std::min(G, (int)(P / 256 + 1))), kThreads, 0, s>>>(ctr, a->lo.line_size, a->lo.line_valid);
-  run_jobs(j_type, 4, true, a->tm[T_LOC]);  // frame_type, mapping_file, mapping_build_id, function
-  k_func_keys<<<std::max(1, std::min(G, (int)(FN / 256 + 1))), kThreads, 0, s>>>(ctr, a->fn_order, a->m_fnfile.ptr(), a->sd_keys[3]);
-  run_jobs(j_file, 1, true, a->tm[T_LOC]);  // function.filename
-  a->tm[T_LOC].launches += 2;
+    run_jobs(j_loc, 1, false, a->tm[T_LOC], std::min<uint64_t>(NI, cap * 32), P);  // location index per unique-stack frame (in place over the gathered stream)
+    launch_scan(a, LocLinesF{ctr, ctr, a->loc_order, ftd, a->lo}, 1, a->tm[T_LOC], small_grid(a, P));
+    k_line_validity<<<std::max(1, std::min(G, (int)(P / 256 + 1))), kThreads, 0, s>>>(ctr, a->lo.line_size, a->lo.line_valid);
+    run_jobs(j_type, 4, true, a->tm[T_LOC], P, std::max(S, FN));  // frame_type, mapping_file, mapping_build_id, function
+    k_func_keys<<<std::max(1, std::min(G, (int)(FN / 256 + 1))), kThreads, 0, s>>>(ctr, a->fn_order, a->m_fnfile.ptr(), a->sd_keys[3]);
+    run_jobs(j_file, 1, true, a->tm[T_LOC], FN, S);  // function.filename
+    a->tm[T_LOC].launches += 2;
   CK(cudaEventRecord(a->tm[T_LOC].b, s));
 
   // ---- run-end encoding of label + constant columns (dictionary first positions recorded on the fly)
@@ -716,18 +724,17 @@ static int process_once(pa_agg* a) {
   ra.n_rows = (uint32_t)N; ra.ncols = ncols; ra.n_ls = a->n_lscols; ra.c_kind = nlab; ra.cols = a->d_cols.as<ReeCol>();
   ra.ls = a->d_ls.as<uint32_t>(); ra.cpu = a->d_cpu.as<uint32_t>(); ra.tid = a->d_tid.as<uint32_t>(); ra.comm = a->d_comm.as<uint32_t>(); ra.kind = a->d_kind.as<uint8_t>();
   ra.lsmat = a->d_lsmat.as<uint32_t>(); ra.n_lscols = std::max<uint32_t>(1, a->n_lscols); ra.kindtab = a->d_kindtab.as<uint32_t>();
-  ra.partial = a->d_partial.as<uint32_t>(); ra.ctr = ctr;
+  ra.partial = a->d_ree_partial.as<uint32_t>(); ra.ctr = ctr;
   const int Gr = a->sms * 8;  // latency-bound passes: fill every warp slot
-  k_ree_pass<false><<<Gr, kThreads, 0, s>>>(ra);
+  k_ree_pass<false><<<Gr, kThreads, 0, s>>>(ra);  // run counts + first row of every dictionary value
   k_ree_scan_partials<<<ncols, 32, 0, s>>>(ra, Gr * kWarps);
-  k_ree_pass<true><<<Gr, kThreads, 0, s>>>(ra);
-  a->tm[T_LABELS].launches += 3;
-  CK(cudaEventRecord(a->tm[T_LABELS].b, s));
-
-  if (getenv("PA_DEBUG_SYNC")) CK(cudaStreamSynchronize(s));
+  a->tm[T_LABELS].launches += 2;
   CK(cudaEventRecord(a->tm[T_DICTS].a, s));
-  if (nlab) run_jobs(j_lab0, (int)nlab, false, a->tm[T_DICTS]);  // label dictionaries over the runs
+  if (nlab) run_jobs(j_lab0, (int)nlab, false, a->tm[T_DICTS], N, std::max<uint64_t>(std::max<uint64_t>(S, 65536), tcap), false);  // label dictionary ranks
   CK(cudaEventRecord(a->tm[T_DICTS].b, s));
+  k_ree_pass<true><<<Gr, kThreads, 0, s>>>(ra);   // run ends + final dictionary indices + validity bits
+  a->tm[T_LABELS].launches += 1;
+  CK(cudaEventRecord(a->tm[T_LABELS].b, s));
 
   CK(cudaMemcpyAsync(a->h_ctr_pinned, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(a->tm[T_TOTAL].b, s));
@@ -741,6 +748,7 @@ static int process_once(pa_agg* a) {
     a->tm[t].ms = ms;
     a->launches += a->tm[t].launches;
   }
+  a->tm[T_LABELS].ms = std::max(0.0, a->tm[T_LABELS].ms - a->tm[T_DICTS].ms);  // the dictionary ranking runs between the two REE passes
   float tot = 0;
   cudaEventElapsedTime(&tot, a->tm[T_TOTAL].a, a->tm[T_TOTAL].b);
   a->tm[T_TOTAL].ms = tot;

@@ -554,10 +554,11 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T* total) {
 }
 
 // Generic fixed-grid reduce-then-scan. F provides:
-//   typedef T; uint32_t n(); T value(uint32_t i); void emit(uint32_t i, T exclusive, T v); void total(T t);
-// blockIdx.y selects an independent job (F indexes its own job table with it).
+//   typedef T; uint32_t n(); T value(uint32_t i); void emit(uint32_t i, T exclusive, T v); void total(int job, T t);
+// blockIdx.y selects an independent job. (A cooperative single-launch variant with grid-wide barriers
+// between the phases was measured and was slower than these pipelined launches: DESIGN.md section 7.)
 template <class F>
-__global__ void __launch_bounds__(kThreads) k_scan_reduce(F f, typename F::T* partial) {
+__device__ __forceinline__ void scan_reduce_dev(const F& f, typename F::T* partial_of_job) {
   typedef typename F::T T;
   uint32_t n = f.n(), begin, end;
   block_range(n, &begin, &end);
@@ -565,13 +566,12 @@ __global__ void __launch_bounds__(kThreads) k_scan_reduce(F f, typename F::T* pa
   for (uint32_t i = begin + threadIdx.x; i < end; i += kThreads) acc = acc + f.value(i);
   T tot;
   block_exclusive_scan(acc, &tot);
-  if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+  if (threadIdx.x == 0) partial_of_job[blockIdx.x] = tot;
 }
 template <class F>
-__global__ void k_scan_partials(F f, typename F::T* partial, int g) {  // grid = njobs blocks, 32 threads: warp scan over the block totals
+__device__ __forceinline__ void scan_partials_dev(const F& f, typename F::T* p, int g, int job) {  // one warp
   typedef typename F::T T;
-  T* p = partial + (size_t)blockIdx.x * g;
-  int lane = threadIdx.x;
+  int lane = threadIdx.x & 31;
   T run = zero_of(T());
   for (int base = 0; base < g; base += 32) {
     int i = base + lane;
@@ -585,18 +585,16 @@ __global__ void k_scan_partials(F f, typename F::T* partial, int g) {  // grid =
     T ex = shfl_up_t(inc, 1);
     if (lane == 0) ex = zero_of(T());
     if (i < g) p[i] = run + ex;
-    T tot = inc;  // lane 31 holds the chunk total
-    tot = shfl_idx_t(tot, 31);
-    run = run + tot;
+    run = run + shfl_idx_t(inc, 31);
   }
-  if (lane == 0) f.total(blockIdx.x, run);
+  if (lane == 0) f.total(job, run);
 }
 template <class F>
-__global__ void __launch_bounds__(kThreads) k_scan_emit(F f, const typename F::T* partial) {
+__device__ __forceinline__ void scan_emit_dev(const F& f, const typename F::T* partial_of_job) {
   typedef typename F::T T;
   uint32_t n = f.n(), begin, end;
   block_range(n, &begin, &end);
-  T run = partial[blockIdx.y * gridDim.x + blockIdx.x];
+  T run = partial_of_job[blockIdx.x];
   for (uint32_t tile = begin; tile < end; tile += kThreads) {
     uint32_t i = tile + threadIdx.x;
     bool in = i < end;
@@ -606,6 +604,18 @@ __global__ void __launch_bounds__(kThreads) k_scan_emit(F f, const typename F::T
     if (in) f.emit(i, run + ex, v);
     run = run + tot;
   }
+}
+template <class F>
+__global__ void __launch_bounds__(kThreads) k_scan_reduce(F f, typename F::T* partial) {
+  scan_reduce_dev(f, partial + (size_t)blockIdx.y * gridDim.x);
+}
+template <class F>
+__global__ void k_scan_partials(F f, typename F::T* partial, int g) {  // grid = njobs blocks, 32 threads
+  scan_partials_dev(f, partial + (size_t)blockIdx.x * g, g, (int)blockIdx.x);
+}
+template <class F>
+__global__ void __launch_bounds__(kThreads) k_scan_emit(F f, const typename F::T* partial) {
+  scan_emit_dev(f, partial + (size_t)blockIdx.y * gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -714,7 +724,8 @@ __global__ void __launch_bounds__(kThreads) k_gather_unique(const Counters* ctr,
 //   map    : out[i] = rank[keys[i]] (+ validity bitmap)           (element-sized)
 struct FoJob {
   const uint32_t* keys;
-  const uint32_t* n_ptr;   // element count lives on the device
+  const uint32_t* n_ptr;   // element count lives on the device (nullptr: use n_imm)
+  uint32_t n_imm;
   uint32_t* first;         // direct: [universe] first position (memset 0xFF)
   unsigned long long* hslots;  // hashed: (key<<32 | first position), memset 0xFF
   uint32_t hmask;
@@ -752,25 +763,25 @@ __device__ __forceinline__ uint32_t hashed_min_insert(unsigned long long* hslots
   }
   return kNull;
 }
-__global__ void __launch_bounds__(kThreads) k_fo_min(const FoJob* jobs) {
-  const FoJob& j = jobs[blockIdx.y];
+__device__ __forceinline__ uint32_t gtid() { return blockIdx.x * kThreads + threadIdx.x; }
+__device__ __forceinline__ uint32_t gstride() { return gridDim.x * kThreads; }
+
+__device__ __forceinline__ void fo_min_dev(const FoJob& j) {
   if (j.skip_min) return;
-  uint32_t n = *j.n_ptr;
-  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+  uint32_t n = j.n_ptr ? *j.n_ptr : j.n_imm;
+  for (uint32_t i = gtid(); i < n; i += gstride()) {
     uint32_t key = j.keys[i];
     if (j.nullable && key == kNull) continue;
     if (j.first[key] > i) atomicMin(&j.first[key], i);  // hashed jobs record first positions in their producer (k_ree_pass)
   }
 }
-__global__ void __launch_bounds__(kThreads) k_fo_zero(const FoJob* jobs) {  // clear only the bitmap words this batch will use
-  const FoJob& j = jobs[blockIdx.y];
-  uint32_t nw = *j.n_ptr / 32 + 1;
-  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < nw; i += gridDim.x * kThreads) j.bitmap[i] = 0u;
+__device__ __forceinline__ void fo_zero_dev(const FoJob& j) {  // clear only the bitmap words this batch will use
+  uint32_t nw = (j.n_ptr ? *j.n_ptr : j.n_imm) / 32 + 1;
+  for (uint32_t i = gtid(); i < nw; i += gstride()) j.bitmap[i] = 0u;
 }
-__global__ void __launch_bounds__(kThreads) k_fo_bits(const FoJob* jobs) {
-  const FoJob& j = jobs[blockIdx.y];
+__device__ __forceinline__ void fo_bits_dev(const FoJob& j) {
   uint32_t entries = j.hashed ? j.hmask + 1 : j.universe;
-  for (uint32_t e = blockIdx.x * kThreads + threadIdx.x; e < entries; e += gridDim.x * kThreads) {
+  for (uint32_t e = gtid(); e < entries; e += gstride()) {
     uint32_t f;
     if (j.hashed) { unsigned long long sl = j.hslots[e]; if (sl == ~0ull) continue; f = (uint32_t)sl; }
     else { f = j.first[e]; if (f == kNull) continue; }
@@ -780,15 +791,16 @@ __global__ void __launch_bounds__(kThreads) k_fo_bits(const FoJob* jobs) {
 struct FoWordsF {
   typedef uint32_t T;
   const FoJob* jobs;
-  __device__ uint32_t n() const { return (*jobs[blockIdx.y].n_ptr + 31) / 32; }
-  __device__ uint32_t value(uint32_t i) const { return (uint32_t)__popc(jobs[blockIdx.y].bitmap[i]); }
-  __device__ void emit(uint32_t i, uint32_t ex, uint32_t) const { jobs[blockIdx.y].wprefix[i] = ex; }
-  __device__ void total(int job, uint32_t t) const { *jobs[job].n_unique = t; }
+  int sel;  // >= 0: that job; < 0: blockIdx.y (stand-alone batched kernels)
+  __device__ const FoJob& J() const { return jobs[sel >= 0 ? sel : (int)blockIdx.y]; }
+  __device__ uint32_t n() const { const FoJob& j = J(); return ((j.n_ptr ? *j.n_ptr : j.n_imm) + 31) / 32; }
+  __device__ uint32_t value(uint32_t i) const { return (uint32_t)__popc(J().bitmap[i]); }
+  __device__ void emit(uint32_t i, uint32_t ex, uint32_t) const { J().wprefix[i] = ex; }
+  __device__ void total(int job, uint32_t t) const { *jobs[sel >= 0 ? sel : job].n_unique = t; }
 };
-__global__ void __launch_bounds__(kThreads) k_fo_assign(const FoJob* jobs) {
-  const FoJob& j = jobs[blockIdx.y];
+__device__ __forceinline__ void fo_assign_dev(const FoJob& j) {
   uint32_t entries = j.hashed ? j.hmask + 1 : j.universe;
-  for (uint32_t e = blockIdx.x * kThreads + threadIdx.x; e < entries; e += gridDim.x * kThreads) {
+  for (uint32_t e = gtid(); e < entries; e += gstride()) {
     uint32_t f, key;
     if (j.hashed) { unsigned long long sl = j.hslots[e]; if (sl == ~0ull) continue; f = (uint32_t)sl; key = (uint32_t)(sl >> 32); }
     else { f = j.first[e]; if (f == kNull) continue; key = e; }
@@ -799,10 +811,9 @@ __global__ void __launch_bounds__(kThreads) k_fo_assign(const FoJob* jobs) {
 }
 // element -> dictionary index (+ validity bitmap, null count). Four independent elements per thread
 // keep enough loads in flight.
-__global__ void __launch_bounds__(kThreads) k_fo_map(const FoJob* jobs) {
-  const FoJob& j = jobs[blockIdx.y];
+__device__ __forceinline__ void fo_map_dev(const FoJob& j) {
   if (!j.out) return;
-  uint32_t n = *j.n_ptr, begin, end;
+  uint32_t n = j.n_ptr ? *j.n_ptr : j.n_imm, begin, end;
   block_range(n, &begin, &end);
   uint32_t nulls = 0;
   for (uint32_t tile = begin; tile < end; tile += 4 * kThreads) {
@@ -829,6 +840,11 @@ __global__ void __launch_bounds__(kThreads) k_fo_map(const FoJob* jobs) {
     if ((threadIdx.x & 31) == 0 && nulls) atomicAdd(j.n_null, nulls);
   }
 }
+__global__ void __launch_bounds__(kThreads) k_fo_min(const FoJob* jobs) { fo_min_dev(jobs[blockIdx.y]); }
+__global__ void __launch_bounds__(kThreads) k_fo_zero(const FoJob* jobs) { fo_zero_dev(jobs[blockIdx.y]); }
+__global__ void __launch_bounds__(kThreads) k_fo_bits(const FoJob* jobs) { fo_bits_dev(jobs[blockIdx.y]); }
+__global__ void __launch_bounds__(kThreads) k_fo_assign(const FoJob* jobs) { fo_assign_dev(jobs[blockIdx.y]); }
+__global__ void __launch_bounds__(kThreads) k_fo_map(const FoJob* jobs) { fo_map_dev(jobs[blockIdx.y]); }
 
 // ---------------------------------------------------------------------------------------------
 // location dictionary: resolved per-frame attributes gathered in location order
@@ -902,10 +918,12 @@ struct ReeCol {
   uint32_t type, param;
   int* run_ends;       // Arrow: run_ends child
   uint32_t* run_keys;  // key of each run (kNull = null run)
-  uint32_t* first;     // dictionary first-position table (direct), fused fo_min
-  unsigned long long* hslots;  // hashed variant (thread_id)
+  uint32_t* first;     // dictionary first-ROW table (direct), filled by the count pass
+  unsigned long long* hslots;  // hashed variant (thread_id): (key << 32 | first row)
   uint32_t hmask;
-  uint32_t pad;
+  uint32_t nullable;
+  const uint32_t* rank;  // dictionary index per key (direct) / per slot (hashed), ready before the emit pass
+  uint32_t* validity;    // Arrow validity words of the run values (zeroed; only for nullable columns)
 };
 struct ReeArgs {
   uint32_t n_rows, ncols;
@@ -949,6 +967,7 @@ template <bool EMIT>
 __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
   __shared__ uint32_t s_acc[kMaxCols][kWarps];   // count (pass 1) or running output position (pass 2)
   __shared__ uint32_t s_last[kMaxCols][kWarps];
+  __shared__ uint32_t s_null[kMaxCols][kWarps];
   __shared__ uint32_t s_kind[64];
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -958,7 +977,7 @@ __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
   uint32_t begin, end, wg;
   warp_range(a.n_rows, &begin, &end, &wg);
   const uint32_t nwarps = gridDim.x * kWarps;
-  for (uint32_t c = lane; c < a.ncols; c += 32) { s_acc[c][w] = EMIT ? a.partial[c * nwarps + wg] : 0u; s_last[c][w] = 0u; }
+  for (uint32_t c = lane; c < a.ncols; c += 32) { s_acc[c][w] = EMIT ? a.partial[c * nwarps + wg] : 0u; s_last[c][w] = 0u; s_null[c][w] = 0u; }
   __syncthreads();
   RowIn carry{0, 0, 0, 0, 0};
   if (begin < end && begin > 0) carry = ree_load(a, begin - 1);  // every lane loads the same row (broadcast)
@@ -976,24 +995,36 @@ __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
     auto column = [&](uint32_t c, bool boundary, bool null, uint32_t key, bool has_dict) {
       boundary = boundary && in;
       unsigned m = __ballot_sync(full, boundary);
-      unsigned nn = __ballot_sync(full, in && !null);
       if (!EMIT) {
+        unsigned nn = __ballot_sync(full, in && !null);
+        unsigned nb = __ballot_sync(full, boundary && null);
         if (lane == 0) {
           if (m) s_acc[c][w] += (uint32_t)__popc(m);
           if (nn) s_last[c][w] = base + (32 - __clz(nn));
+          if (nb) s_null[c][w] += (uint32_t)__popc(nb);
+        }
+        if (has_dict && boundary && !null) {  // dictionary memo: the first ROW that opens a run with this value
+          const ReeCol& col = s_cols[c];
+          if (col.hslots) { if (hashed_min_insert(col.hslots, col.hmask, key, r) == kNull) atomicOr(&a.ctr->err, ERR_TABLE_FULL); }
+          else if (col.first[key] > r) atomicMin(&col.first[key], r);
         }
       } else {
         if (m == 0) return;
+        const ReeCol& col = s_cols[c];
         uint32_t pos0 = s_acc[c][w];
+        uint32_t k = pos0 + (uint32_t)__popc(m & lt);
         if (boundary) {
-          const ReeCol& col = s_cols[c];
-          uint32_t k = pos0 + (uint32_t)__popc(m & lt);
           if (k > 0) col.run_ends[k - 1] = (int)r;  // run k starts at r => run k-1 ends at r
-          col.run_keys[k] = null ? kNull : key;
-          if (has_dict && !null) {  // dictionary memo: first run that carries this value
-            if (col.hslots) { if (hashed_min_insert(col.hslots, col.hmask, key, k) == kNull) atomicOr(&a.ctr->err, ERR_TABLE_FULL); }
-            else if (col.first[key] > k) atomicMin(&col.first[key], k);
-          }
+          uint32_t stored = key;                    // constant-ish columns keep the class id
+          if (has_dict) stored = null ? 0u : col.rank[col.hslots ? fo_hfind(col.hslots, col.hmask, key) : key];
+          col.run_keys[k] = stored;
+        }
+        if (has_dict && col.nullable) {  // validity bits of runs pos0 .. pos0+cnt-1 span at most two words
+          uint32_t w0 = pos0 >> 5;
+          bool v = boundary && !null;
+          unsigned m0 = __reduce_or_sync(full, (v && (k >> 5) == w0) ? (1u << (k & 31)) : 0u);
+          unsigned m1 = __reduce_or_sync(full, (v && (k >> 5) != w0) ? (1u << (k & 31)) : 0u);
+          if (lane == 0) { if (m0) atomicOr(&col.validity[w0], m0); if (m1) atomicOr(&col.validity[w0 + 1], m1); }
         }
         __syncwarp(full);
         if (lane == 0) s_acc[c][w] = pos0 + (uint32_t)__popc(m);
@@ -1037,6 +1068,7 @@ __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
     for (uint32_t c = lane; c < a.ncols; c += 32) {
       a.partial[c * nwarps + wg] = s_acc[c][w];
       if (s_last[c][w]) atomicMax(&a.ctr->last_nonnull_plus1[c], s_last[c][w]);
+      if (s_null[c][w]) atomicAdd(&a.ctr->n_null[c], s_null[c][w]);
     }
   }
 }

@@ -208,3 +208,5 @@ def test_large_batch_properties(oracle, gpu):
     a.close()
     sub = w.head(50_000)
     assert gpu.run(sub)[0] == oracle.run(sub)[0]
+
+
