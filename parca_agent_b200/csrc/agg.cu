@@ -518,7 +518,8 @@ static int process_once(pa_agg* a) {
   const size_t P = std::max<uint32_t>(n_frames, 1), S = std::max<uint32_t>(n_cstr, 1), FN = std::max<uint32_t>(n_funcs, 1);
   const size_t NI = (size_t)std::min<uint64_t>(std::max<uint64_t>(a->NF, 1), 0x7FFFFFFFull);
   const size_t Nn = (size_t)std::max<uint64_t>(N, 1);
-  uint32_t *rowbits = nullptr, *row_wprefix = nullptr, *uniq_slot = nullptr, *uniq_size = nullptr;
+  uint32_t *rowbits = nullptr, *row_wprefix = nullptr, *uniq_slot = nullptr, *uniq_size = nullptr, *first_ls = nullptr;
+  want(&first_ls, std::max<size_t>(a->ls.sets.size(), 1) * 4, 0);
   want(&rowbits, (Nn / 32 + 2) * 4, 1); want(&row_wprefix, (Nn / 32 + 2) * 4); want(&uniq_slot, Nn * 4); want(&uniq_size, Nn * 4);
   uint32_t *loc_bits = nullptr, *loc_wp = nullptr;
   want(&a->loc_first, P * 4, 0); want(&a->loc_rank, P * 4); want(&a->loc_order, P * 4);
@@ -647,6 +648,12 @@ static int process_once(pa_agg* a) {
     h.ls = a->d_ls.as<uint32_t>(); h.cpu = a->d_cpu.as<uint32_t>(); h.tid = a->d_tid.as<uint32_t>(); h.comm = a->d_comm.as<uint32_t>();
     h.sid2cid = a->m_sid2cid.ptr(); h.n_sids = (uint32_t)a->sp.sid2cid.size(); h.n_labelsets = (uint32_t)a->ls.sets.size();
     h.n_frame_ids = frames_end; h.provided = provided ? 1 : 0; h.tab = tab; h.mask = mask; h.slot_of_row = a->d_slot.as<uint32_t>(); h.ctr = ctr;
+    h.first_ls = a->n_lscols ? first_ls : nullptr;
+    for (uint32_t c = 0; c < nlab; c++) {
+      if (a->cols[c].type == COL_CPU) h.first_cpu = col_first[c];
+      if (a->cols[c].type == COL_TID) { h.tid_slots = a->tid_slots; h.tid_mask = a->tid_mask; }
+      if (a->cols[c].type == COL_COMM) h.first_comm = col_first[c];
+    }
     uint64_t rows = r1 - r0;
     int hb = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)G * 2);
     k_header<<<std::max(hb, 1), kThreads, 0, s>>>(h);
@@ -726,7 +733,15 @@ static int process_once(pa_agg* a) {
   ra.lsmat = a->d_lsmat.as<uint32_t>(); ra.n_lscols = std::max<uint32_t>(1, a->n_lscols); ra.kindtab = a->d_kindtab.as<uint32_t>();
   ra.partial = a->d_ree_partial.as<uint32_t>(); ra.ctr = ctr;
   const int Gr = a->sms * 8;  // latency-bound passes: fill every warp slot
-  k_ree_pass<false><<<Gr, kThreads, 0, s>>>(ra);  // run counts + first row of every dictionary value
+  if (a->n_lscols) {  // first rows of the labelset-derived values, from the per-labelset memo of k_header
+    LsFirstArgs lf{};
+    lf.first_ls = first_ls; lf.n_labelsets = (uint32_t)a->ls.sets.size(); lf.lsmat = a->d_lsmat.as<uint32_t>();
+    lf.n_lscols = std::max<uint32_t>(1, a->n_lscols); lf.n_ls = a->n_lscols;
+    for (uint32_t c = 0; c < a->n_lscols; c++) lf.col_first[c] = col_first[c];
+    k_ls_first<<<small_grid(a, (uint64_t)lf.n_labelsets * lf.n_ls), kThreads, 0, s>>>(lf);
+    a->tm[T_LABELS].launches++;
+  }
+  k_ree_pass<false><<<Gr, kThreads, 0, s>>>(ra);  // run counts
   k_ree_scan_partials<<<ncols, 32, 0, s>>>(ra, Gr * kWarps);
   a->tm[T_LABELS].launches += 2;
   CK(cudaEventRecord(a->tm[T_DICTS].a, s));

@@ -140,6 +140,28 @@ __device__ __forceinline__ uint32_t warp_insert(StackSlot* tab, uint32_t mask, K
   return own ? idx : (agree ? lidx : kNull);
 }
 
+// hashed first-position table for 32-bit keys with an unbounded universe (thread ids)
+__device__ __forceinline__ uint32_t fo_hfind(const unsigned long long* hslots, uint32_t hmask, uint32_t key) {
+  uint32_t idx = mix32(key) & hmask;
+  while ((uint32_t)(hslots[idx] >> 32) != key) idx = (idx + 1) & hmask;
+  return idx;
+}
+// bounded linear-probe insert of (key, pos) keeping the minimum pos; returns the slot, kNull = table full
+__device__ __forceinline__ uint32_t hashed_min_insert(unsigned long long* hslots, uint32_t hmask, uint32_t key, uint32_t pos) {
+  unsigned long long packed = ((unsigned long long)key << 32) | pos;
+  uint32_t idx = mix32(key) & hmask;
+  for (uint32_t probe = 0; probe <= hmask; probe++) {
+    unsigned long long cur = hslots[idx];
+    if (cur == ~0ull) {
+      cur = atomicCAS(&hslots[idx], ~0ull, packed);
+      if (cur == ~0ull) return idx;
+    }
+    if ((uint32_t)(cur >> 32) == key) { if (cur > packed) atomicMin(&hslots[idx], packed); return idx; }
+    idx = (idx + 1) & hmask;
+  }
+  return kNull;
+}
+
 // ---------------------------------------------------------------------------------------------
 // header pass: 64-byte AoS sample headers -> Arrow row columns + compact SoA side arrays.
 // Replaces the per-sample appends of writeSampleV2 (reporter/parca_reporter.go:394-405).
@@ -164,6 +186,14 @@ struct HeaderArgs {
   uint32_t mask;
   uint32_t* slot_of_row;
   Counters* ctr;
+  // dictionary memo of the label columns: first row carrying each value. The first row of a value always
+  // opens a run, so min over all rows == min over run starts; rows ascend with the grid here, which keeps the
+  // atomics rare, and this DRAM-bound kernel has the issue slots to spare. nullptr = column disabled.
+  uint32_t* first_ls;            // per labelset id (expanded to the labelset-derived columns by k_ls_first)
+  uint32_t* first_cpu;
+  unsigned long long* tid_slots;
+  uint32_t tid_mask;
+  uint32_t* first_comm;
 };
 
 __global__ void __launch_bounds__(kThreads) k_header(HeaderArgs a) {
@@ -200,7 +230,12 @@ __global__ void __launch_bounds__(kThreads) k_header(HeaderArgs a) {
       a.ls[r] = ls;
       a.cpu[r] = cpu;
       a.tid[r] = tid;
-      a.comm[r] = a.sid2cid[comm_sid];
+      const uint32_t comm_cid = a.sid2cid[comm_sid];
+      a.comm[r] = comm_cid;
+      if (a.first_ls && a.first_ls[ls] > r) atomicMin(&a.first_ls[ls], r);
+      if (a.first_cpu && a.first_cpu[cpu] > r) atomicMin(&a.first_cpu[cpu], r);
+      if (a.tid_slots && hashed_min_insert(a.tid_slots, a.tid_mask, tid, r) == kNull) atomicOr(&a.ctr->err, ERR_TABLE_FULL);
+      if (a.first_comm && comm_cid != 0 && a.first_comm[comm_cid] > r) atomicMin(&a.first_comm[comm_cid], r);
       if (a.provided) {  // trace.Hash.Bytes(): big-endian hi||lo
         ulonglong2 id = make_ulonglong2(bswap64(k.hi), bswap64(k.lo));
         *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = id;
@@ -743,26 +778,6 @@ struct FoJob {
   uint32_t* n_null;        // -> Counters (may be nullptr)
   Counters* ctr;
 };
-__device__ __forceinline__ uint32_t fo_hfind(const unsigned long long* hslots, uint32_t hmask, uint32_t key) {
-  uint32_t idx = mix32(key) & hmask;
-  while ((uint32_t)(hslots[idx] >> 32) != key) idx = (idx + 1) & hmask;
-  return idx;
-}
-// bounded linear-probe insert of (key, pos) keeping the minimum pos; returns the slot, kNull = table full
-__device__ __forceinline__ uint32_t hashed_min_insert(unsigned long long* hslots, uint32_t hmask, uint32_t key, uint32_t pos) {
-  unsigned long long packed = ((unsigned long long)key << 32) | pos;
-  uint32_t idx = mix32(key) & hmask;
-  for (uint32_t probe = 0; probe <= hmask; probe++) {
-    unsigned long long cur = hslots[idx];
-    if (cur == ~0ull) {
-      cur = atomicCAS(&hslots[idx], ~0ull, packed);
-      if (cur == ~0ull) return idx;
-    }
-    if ((uint32_t)(cur >> 32) == key) { if (cur > packed) atomicMin(&hslots[idx], packed); return idx; }
-    idx = (idx + 1) & hmask;
-  }
-  return kNull;
-}
 __device__ __forceinline__ uint32_t gtid() { return blockIdx.x * kThreads + threadIdx.x; }
 __device__ __forceinline__ uint32_t gstride() { return gridDim.x * kThreads; }
 
@@ -907,6 +922,24 @@ __global__ void __launch_bounds__(kThreads) k_func_keys(const Counters* ctr, con
   for (uint32_t k = blockIdx.x * kThreads + threadIdx.x; k < n; k += gridDim.x * kThreads) file_key[k] = fn_file_cid[func_order[k]];
 }
 
+// labelset-derived label columns: first row of each value = min over the labelsets carrying it of the
+// labelset's first row (recorded by k_header). One thread per (labelset, column) matrix cell.
+struct LsFirstArgs {
+  const uint32_t* first_ls; uint32_t n_labelsets;
+  const uint32_t* lsmat; uint32_t n_lscols, n_ls;
+  uint32_t* col_first[kMaxCols];
+};
+__global__ void __launch_bounds__(kThreads) k_ls_first(LsFirstArgs a) {
+  uint32_t cells = a.n_labelsets * a.n_ls;
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < cells; i += gridDim.x * kThreads) {
+    uint32_t ls = i / a.n_ls, c = i % a.n_ls;
+    uint32_t f = a.first_ls[ls];
+    if (f == kNull) continue;  // labelset not used by this batch
+    uint32_t v = a.lsmat[(size_t)ls * a.n_lscols + c];
+    if (v != kNull && a.col_first[c][v] > f) atomicMin(&a.col_first[c][v], f);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // run-end encoding of every REE column in two fused passes over the rows
 // (label columns: reporter/arrow.go:97-131; constant-ish columns: arrow.go:50-59,:166-207).
@@ -918,7 +951,7 @@ struct ReeCol {
   uint32_t type, param;
   int* run_ends;       // Arrow: run_ends child
   uint32_t* run_keys;  // key of each run (kNull = null run)
-  uint32_t* first;     // dictionary first-ROW table (direct), filled by the count pass
+  uint32_t* first;     // dictionary first-ROW table (direct), filled by k_header / k_ls_first
   unsigned long long* hslots;  // hashed variant (thread_id): (key << 32 | first row)
   uint32_t hmask;
   uint32_t nullable;
@@ -1002,11 +1035,6 @@ __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
           if (m) s_acc[c][w] += (uint32_t)__popc(m);
           if (nn) s_last[c][w] = base + (32 - __clz(nn));
           if (nb) s_null[c][w] += (uint32_t)__popc(nb);
-        }
-        if (has_dict && boundary && !null) {  // dictionary memo: the first ROW that opens a run with this value
-          const ReeCol& col = s_cols[c];
-          if (col.hslots) { if (hashed_min_insert(col.hslots, col.hmask, key, r) == kNull) atomicOr(&a.ctr->err, ERR_TABLE_FULL); }
-          else if (col.first[key] > r) atomicMin(&col.first[key], r);
         }
       } else {
         if (m == 0) return;
