@@ -143,8 +143,13 @@ __device__ __forceinline__ uint32_t warp_insert(StackSlot* tab, uint32_t mask, K
 // hashed first-position table for 32-bit keys with an unbounded universe (thread ids)
 __device__ __forceinline__ uint32_t fo_hfind(const unsigned long long* hslots, uint32_t hmask, uint32_t key) {
   uint32_t idx = mix32(key) & hmask;
-  while ((uint32_t)(hslots[idx] >> 32) != key) idx = (idx + 1) & hmask;
-  return idx;
+  for (uint32_t probe = 0; probe <= hmask; probe++) {  // bounded: a key lost to a full table must not hang the kernel
+    unsigned long long sl = hslots[idx];
+    if ((uint32_t)(sl >> 32) == key && sl != ~0ull) return idx;
+    if (sl == ~0ull) break;  // linear probing: an empty slot ends the cluster
+    idx = (idx + 1) & hmask;
+  }
+  return 0;  // only reachable after ERR_TABLE_FULL was raised; the batch is redone with a larger table
 }
 // bounded linear-probe insert of (key, pos) keeping the minimum pos; returns the slot, kNull = table full
 __device__ __forceinline__ uint32_t hashed_min_insert(unsigned long long* hslots, uint32_t hmask, uint32_t key, uint32_t pos) {

@@ -210,3 +210,43 @@ def test_large_batch_properties(oracle, gpu):
     assert gpu.run(sub)[0] == oracle.run(sub)[0]
 
 
+
+
+def test_table_overflow_retry(gpu):
+    """Adaptive table sizing: batch 2 has far more unique stacks and thread ids than batch 1 predicted, so
+    the first attempt overflows both hash tables and process() must redo the batch with larger ones."""
+    F = 2
+    rng = np.random.Generator(np.random.PCG64(9))
+    base = synth.config1(hash_mode=abi.PA_HASH_PROVIDED)
+
+    def batch(n, unique):
+        hd = np.zeros(n, dtype=abi.HDR_DTYPE)
+        sid = np.arange(n, dtype=np.uint64) if unique else rng.integers(0, 10, n).astype(np.uint64)
+        hd["hash_hi"] = synth.splitmix64(sid)
+        hd["hash_lo"] = synth.splitmix64(sid + np.uint64(12345))
+        hd["timestamp_ns"] = np.arange(n)
+        hd["tid"] = np.arange(n) if unique else 7
+        hd["pid"] = 1
+        hd["comm_sid"] = 0
+        hd["labelset_id"] = 0
+        hd["cpu"] = 1
+        hd["nframes"] = F
+        hd["frame_off"] = np.arange(n, dtype=np.uint64) * np.uint64(F)
+        fr = (np.repeat(sid, F) * np.uint64(7) + np.tile(np.arange(F, dtype=np.uint64), n)) % np.uint64(4096)
+        return synth.Workload("ovf", base.strings, base.frames, base.labelsets, hd, _frame_ids=fr, hash_mode=abi.PA_HASH_PROVIDED)
+
+    w1, w2 = batch(1_200_000, False), batch(2_600_000, True)
+    a = gpu.from_workload(w2)
+    gpu.load(a, w1)
+    r1 = a.flush()
+    assert r1.n_rows == w1.n and r1.n_unique_stacks == 10
+    gpu.load(a, w2)
+    r2 = a.flush()
+    assert r2.n_rows == w2.n and r2.n_unique_stacks == w2.n and r2.n_location_indices == w2.n * F
+    t = pa.ipc.open_stream(pa.py_buffer(r2.ipc)).read_all()
+    tid = t.column("labels").chunk(0).field("thread_id")
+    assert len(tid.values.dictionary) == w2.n and tid.run_ends.to_numpy()[-1] == w2.n
+    assert tid.values.dictionary[12345].as_py() == "12345"  # first-occurrence order == row order here
+    st = t.column("stacktrace").chunk(0)
+    assert (st.offsets.to_numpy() == np.arange(w2.n) * F).all()
+    a.close()
