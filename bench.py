@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="rows of the batch (a prefix) timed on the CPU port for cpu_baseline")
     ap.add_argument("--ref-sample", type=int, default=2_000_000, help="rows per step of the --impl reference arm")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="BASELINE.json config: 2 = headline (default), 3 = Zipf/CUDA-origin/50k labelsets")
     return ap.parse_args()
 
 
@@ -82,6 +83,8 @@ def measured_peak():
 
 def shard_workload(args, rank, world):
     from parca_agent_b200 import synth
+    if args.config == 3:
+        return synth.config3(n=args.samples)
     if world == 1:
         return synth.config2(n=args.samples)
     # weak scaling: every rank owns the pids with xxh64(pid) % world == rank and aggregates `samples` rows of them
@@ -227,8 +230,8 @@ def main():
             "metric": "samples/sec aggregated", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": "config2: %d samples x %d frames per GPU, %d unique stacks, %d distinct frames, pid-sharded across %d GPU(s)"
-                                   % (w.n, F, w.meta["U"], w.meta["P"], world),
+            "config": {"workload": "config%d: %d samples x %d frames per GPU, %d unique stacks, %d distinct frames, pid-sharded across %d GPU(s)"
+                                   % (args.config, w.n, F, w.meta["U"], w.meta["P"], world),
                        "hash_mode": "xxh64x2", "l2": "inputs (%.2f GB/GPU) far exceed the 126 MB L2; no explicit flush" % (h2d_b / 1e9),
                        "timing": "CUDA events on the library's compute stream, max over ranks", "wall_s_for_steps": wall_max},
             "gpu_launches": int(launches),

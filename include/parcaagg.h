@@ -184,7 +184,8 @@ int pa_agg_last_kernel_ms(const pa_agg* a, const char* name, double* ms, uint32_
 /* copies the per-row 128-bit stack ids (big-endian hi‖lo, 16 B per row) of the staged batch. */
 int pa_agg_debug_stack_ids(pa_agg* a, uint8_t* out, uint64_t n_rows);
 /* per-unique-stack occurrence counts in first-occurrence order (the "count per stack" side table;
- * not part of the reference's record — see SURVEY §0.2). out has n_unique_stacks entries. */
+ * not part of the reference's record — see SURVEY §0.2 — and therefore computed on demand by a separate
+ * kernel over the batch most recently processed, not on the flush path). out has n_unique_stacks entries. */
 int pa_agg_debug_stack_counts(pa_agg* a, uint32_t* out, uint64_t n);
 
 /* host helpers restating reference functions (no GPU involved) */

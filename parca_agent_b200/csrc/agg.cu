@@ -692,8 +692,7 @@ static int process_once(pa_agg* a) {
   const int Gs = small_grid(a, nslots), Gw = small_grid(a, N / 32 + 1), Gu = small_grid(a, std::min<uint64_t>(N, cap / 2));
     k_stack_bits<<<Gs, kThreads, 0, s>>>(tab, nslots, rowbits);
     launch_scan(a, WordsF{rowbits, row_wprefix, (uint32_t)((N + 31) / 32), &ctr->n_unique}, 1, a->tm[T_RANK], Gw);
-    k_stack_assign<<<Gs, kThreads, 0, s>>>(tab, nslots, rowbits, row_wprefix, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(),
-                                           a->d_uniq_count.as<uint32_t>(), uniq_slot, uniq_size);
+    k_stack_assign<<<Gs, kThreads, 0, s>>>(tab, nslots, rowbits, row_wprefix, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(), uniq_slot, uniq_size);
     launch_scan(a, UniqOffsetF{ctr, ctr, uniq_size, uniq_slot, tab}, 1, a->tm[T_RANK], Gu);
     a->tm[T_RANK].launches += 2;
   k_rows_materialize<<<G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>());
@@ -1175,9 +1174,14 @@ int pa_agg_debug_stack_ids(pa_agg* a, uint8_t* out, uint64_t n_rows) {
   return PA_OK;
 }
 int pa_agg_debug_stack_counts(pa_agg* a, uint32_t* out, uint64_t n) {
-  if (!a || !out || n > a->h_ctr.n_unique) return PA_EINVAL;
+  if (!a || !out || n > a->h_ctr.n_unique || !a->N) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
   CK(cudaSetDevice(a->device));
-  CK(cudaMemcpy(out, a->d_uniq_count.p, n * 4, cudaMemcpyDeviceToHost));
+  // computed on demand from the staged batch (rows -> table slot -> first-occurrence ordinal)
+  CK(cudaMemsetAsync(a->d_uniq_count.p, 0, (size_t)a->h_ctr.n_unique * 4, a->s_comp));
+  k_count_stacks<<<a->G, kThreads, 0, a->s_comp>>>((uint32_t)a->N, a->d_slot.as<uint32_t>(), a->d_table.as<StackSlot>(), a->d_uniq_count.as<uint32_t>());
+  CK(cudaMemcpyAsync(out, a->d_uniq_count.p, n * 4, cudaMemcpyDeviceToHost, a->s_comp));
+  CK(cudaStreamSynchronize(a->s_comp));
   return PA_OK;
 }
 

@@ -28,7 +28,7 @@ struct __align__(16) Key128 { unsigned long long hi, lo; };
 struct __align__(32) StackSlot {
   Key128 key;          // (0,0) = empty; claimed once by a 128-bit CAS, never changes afterwards
   uint32_t first_inv;  // 0xFFFFFFFF - first row, maintained with atomicMax (memset-0 = none yet)
-  uint32_t count;      // occurrences (side table, not part of the reference's record)
+  uint32_t ordinal;    // first-occurrence ordinal of this stack (set by k_stack_assign)
   uint32_t offset;     // start of this stack's run in the location-index stream
   uint32_t size;       // nframes of the first occurrence (listEntryRef.listSize)
 };
@@ -114,8 +114,10 @@ __device__ __forceinline__ uint32_t stack_find_or_insert(StackSlot* tab, uint32_
 }
 
 // Warp-aggregated insert: lanes carrying the same id elect the lowest lane (== lowest row, rows
-// ascend with the lane), which does one table walk, one atomicMax (first row) and one atomicAdd
-// (count) for the whole group. All 32 lanes must call this converged.
+// ascend with the lane), which does one table walk and one atomicMax (first row)
+// for the whole group. All 32 lanes must call this converged. (Occurrence counts are NOT maintained here:
+// on skewed batches the per-stack atomicAdd serialised on a few hot L2 lines and cost more than the
+// hashing itself; they are computed on demand by k_count_stacks.)
 __device__ __forceinline__ uint32_t warp_insert(StackSlot* tab, uint32_t mask, Key128 k, uint32_t row, bool valid, Counters* ctr) {
   const unsigned full = 0xFFFFFFFFu;
   int lane = threadIdx.x & 31;
@@ -125,7 +127,6 @@ __device__ __forceinline__ uint32_t warp_insert(StackSlot* tab, uint32_t mask, K
   unsigned long long lhi = __shfl_sync(full, k.hi, leader), llo = __shfl_sync(full, k.lo, leader);
   int lvalid = __shfl_sync(full, (int)valid, leader);
   bool agree = valid && lvalid && lhi == k.hi && llo == k.lo;
-  unsigned agree_mask = __ballot_sync(full, agree) & grp;
   bool own = valid && (lane == leader || !agree);  // tag collisions between different ids fall back to a private insert
   uint32_t idx = kNull;
   if (own) {
@@ -133,7 +134,6 @@ __device__ __forceinline__ uint32_t warp_insert(StackSlot* tab, uint32_t mask, K
     if (idx != kNull) {
       uint32_t inv = 0xFFFFFFFFu - row;
       if (*(volatile uint32_t*)&tab[idx].first_inv < inv) atomicMax(&tab[idx].first_inv, inv);
-      atomicAdd(&tab[idx].count, (lane == leader) ? (uint32_t)__popc(agree_mask) : 1u);
     }
   }
   uint32_t lidx = __shfl_sync(full, idx, leader);
@@ -680,15 +680,14 @@ struct WordsF {  // exclusive popcount prefix over bitmap words
   __device__ void total(int, uint32_t t) const { *total_out = t; }
 };
 __global__ void __launch_bounds__(kThreads) k_stack_assign(StackSlot* tab, uint32_t nslots, const uint32_t* rowbits, const uint32_t* wprefix,
-                                                           const uint16_t* nframes, uint32_t* uniq_row, uint32_t* uniq_count,
-                                                           uint32_t* uniq_slot, uint32_t* uniq_size) {
+                                                           const uint16_t* nframes, uint32_t* uniq_row, uint32_t* uniq_slot, uint32_t* uniq_size) {
   for (uint32_t sidx = blockIdx.x * kThreads + threadIdx.x; sidx < nslots; sidx += gridDim.x * kThreads) {
     uint32_t inv = tab[sidx].first_inv;
     if (!inv) continue;
     uint32_t f = 0xFFFFFFFFu - inv;
     uint32_t ord = wprefix[f >> 5] + (uint32_t)__popc(rowbits[f >> 5] & ((1u << (f & 31)) - 1u));
     uniq_row[ord] = f;
-    uniq_count[ord] = tab[sidx].count;
+    tab[sidx].ordinal = ord;
     uniq_slot[ord] = sidx;
     uniq_size[ord] = nframes[f];
   }
@@ -729,6 +728,21 @@ __global__ void __launch_bounds__(kThreads) k_rows_materialize(uint32_t n_rows, 
       uint32_t r = base + u * kThreads + threadIdx.x;
       if (r < n_rows) { st_offsets[r] = (int)os[u].x; st_sizes[r] = (int)os[u].y; }
     }
+  }
+}
+
+// On-demand side table: occurrences per unique stack, in first-occurrence order (the reference emits one
+// row per sample and never counts — SURVEY section 0.2 — so this stays off the flush path). Lanes of a
+// warp that hit the same stack are aggregated before the atomicAdd.
+__global__ void __launch_bounds__(kThreads) k_count_stacks(uint32_t n_rows, const uint32_t* slot_of_row, const StackSlot* tab, uint32_t* counts) {
+  const unsigned full = 0xFFFFFFFFu;
+  uint32_t stride = gridDim.x * kThreads, iters = (n_rows + stride - 1) / stride;
+  int lane = threadIdx.x & 31;
+  for (uint32_t it = 0; it < iters; it++) {
+    uint32_t r = it * stride + blockIdx.x * kThreads + threadIdx.x;
+    uint32_t sl = r < n_rows ? slot_of_row[r] : kNull;
+    unsigned grp = __match_any_sync(full, sl);
+    if (sl != kNull && lane == __ffs(grp) - 1) atomicAdd(&counts[tab[sl].ordinal], (uint32_t)__popc(grp));
   }
 }
 
