@@ -134,7 +134,7 @@ struct pa_agg {
   std::vector<uint64_t> chunk_frames_end;
   cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_d2h0 = nullptr, ev_d2h1 = nullptr;
   bool processed = false, hash_timed = false;
-  int hash_variant = 0;  // 0 = direct global loads (default, faster), 1 = cp.async-staged (PA_HASH_VARIANT=direct|staged)
+  int hash_variant = 2;  // 2 = wide (default: 2 lanes/sample, 16-byte loads), 0 = direct (4 lanes/sample), 1 = cp.async-staged; PA_HASH_VARIANT=wide|direct|staged
 
   // ---- device batch buffers
   DBuf d_hdr, d_frames, d_ts, d_value, d_uuid, d_stoff, d_stsize, d_slot, d_kind, d_nfr, d_foff, d_ls, d_cpu, d_tid, d_comm;
@@ -284,7 +284,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   for (uint32_t i = 0; i < cfg->n_external_labels; i++) {  // resolved to canonical ids lazily at flush (strings may come later)
     a->external.emplace_back(cfg->external_labels[i].name_sid, cfg->external_labels[i].value_sid);
   }
-  if (const char* hv = getenv("PA_HASH_VARIANT")) a->hash_variant = strcmp(hv, "staged") == 0 ? 1 : 0;
+  if (const char* hv = getenv("PA_HASH_VARIANT")) a->hash_variant = strcmp(hv, "staged") == 0 ? 1 : (strcmp(hv, "direct") == 0 ? 0 : 2);
   if (cudaFuncSetAttribute(k_hash_insert_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashStagedSmem) != cudaSuccess) return bail(PA_EIO);
   if (cudaStreamCreateWithFlags(&a->s_copy, cudaStreamNonBlocking) != cudaSuccess) return bail(PA_EIO);
   if (cudaStreamCreateWithFlags(&a->s_comp, cudaStreamNonBlocking) != cudaSuccess) return bail(PA_EIO);
@@ -667,6 +667,7 @@ static int process_once(pa_agg* a) {
     uint64_t rows = r1 - r0;
     int blocks = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)a->sms * (a->hash_variant == 1 ? 3 : 4));
     if (a->hash_variant == 1) k_hash_insert_staged<<<std::max(blocks, 1), kThreads, kHashStagedSmem, s>>>(ha);
+    else if (a->hash_variant == 2) k_hash_insert_wide<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     else k_hash_insert<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     a->tm[T_HASH].launches++;
   };

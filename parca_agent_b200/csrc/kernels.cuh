@@ -429,6 +429,85 @@ __global__ void __launch_bounds__(kThreads, 4) k_hash_insert(HashArgs a) {
   }
 }
 
+// Variant B2: two lanes per sample, each owning two of the four XXH64 accumulator lanes and loading
+// 16 bytes per stripe (LDG.128): four independent multiply chains per lane (2 accumulators x 2 seeds),
+// half the load / address / shuffle instructions of variant B. 16 samples per sub-step, 2 sub-steps
+// per 32-sample warp batch; the epilogue is the same thread-per-sample code.
+__device__ __forceinline__ ulonglong2 ldg_stream128(const unsigned long long* p) {
+  ulonglong2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
+#ifndef PA_WIDE_UNROLL
+#define PA_WIDE_UNROLL 8
+#endif
+constexpr int kWideUnroll = PA_WIDE_UNROLL;
+__global__ void __launch_bounds__(kThreads, 4) k_hash_insert_wide(HashArgs a) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, h = lane & 1, g = lane >> 1;  // h: which half of the stripe, g: sample within the sub-step
+  const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+  const uint32_t span = a.row1 - a.row0;
+  const uint32_t iters = (span + nwarps * 32 - 1) / (nwarps * 32);
+  for (uint32_t it = 0; it < iters; it++) {
+    const uint32_t r = a.row0 + (it * nwarps + warp) * 32 + lane;
+    const bool valid = r < a.row1;
+    const uint32_t n_me = valid ? a.nframes[r] : 0u;
+    const unsigned long long off_me = valid ? a.frame_off[r] : 0ull;
+    unsigned long long v0[4], v1[4];
+#pragma unroll
+    for (int sub = 0; sub < 2; sub++) {
+      const int src = sub * 16 + g;
+      const uint32_t n = __shfl_sync(full, n_me, src);
+      const unsigned long long off = __shfl_sync(full, off_me, src);
+      const unsigned long long* q = a.frames + off + 2 * h;
+      const bool aligned = (off & 1ull) == 0;  // 16-byte loads need an even word offset
+      unsigned long long a0 = xxh_lane_init(0ull, 2 * h), b0 = xxh_lane_init(0ull, 2 * h + 1);
+      unsigned long long a1 = xxh_lane_init(kSeedLo, 2 * h), b1 = xxh_lane_init(kSeedLo, 2 * h + 1);
+      const uint32_t ns = n >> 2;
+      uint32_t s = 0;
+      if (aligned) {
+        for (; s + kWideUnroll <= ns; s += kWideUnroll) {
+          ulonglong2 w[kWideUnroll];
+#pragma unroll
+          for (int u = 0; u < kWideUnroll; u++) w[u] = ldg_stream128(q + 4 * (s + u));
+#pragma unroll
+          for (int u = 0; u < kWideUnroll; u++) {
+            unsigned long long mx = w[u].x * XP2, my = w[u].y * XP2;
+            a0 = xxh_round_pre(a0, mx); a1 = xxh_round_pre(a1, mx);
+            b0 = xxh_round_pre(b0, my); b1 = xxh_round_pre(b1, my);
+          }
+        }
+      }
+      for (; s < ns; s++) {
+        unsigned long long mx = ldg_stream64(q + 4 * s) * XP2, my = ldg_stream64(q + 4 * s + 1) * XP2;
+        a0 = xxh_round_pre(a0, mx); a1 = xxh_round_pre(a1, mx);
+        b0 = xxh_round_pre(b0, my); b1 = xxh_round_pre(b1, my);
+      }
+      __syncwarp(full);
+      // transpose: lane L (in half `sub`) gets accumulators 0,1 from lane 2*(L&15) and 2,3 from lane 2*(L&15)+1
+      const int s0 = 2 * (lane & 15), s1 = s0 + 1;
+      unsigned long long x;
+      x = __shfl_sync(full, a0, s0); if ((lane >> 4) == sub) v0[0] = x;
+      x = __shfl_sync(full, b0, s0); if ((lane >> 4) == sub) v0[1] = x;
+      x = __shfl_sync(full, a0, s1); if ((lane >> 4) == sub) v0[2] = x;
+      x = __shfl_sync(full, b0, s1); if ((lane >> 4) == sub) v0[3] = x;
+      x = __shfl_sync(full, a1, s0); if ((lane >> 4) == sub) v1[0] = x;
+      x = __shfl_sync(full, b1, s0); if ((lane >> 4) == sub) v1[1] = x;
+      x = __shfl_sync(full, a1, s1); if ((lane >> 4) == sub) v1[2] = x;
+      x = __shfl_sync(full, b1, s1); if ((lane >> 4) == sub) v1[3] = x;
+    }
+    const uint32_t nt = n_me & 3u;
+    const unsigned long long* tp = a.frames + off_me + (n_me & ~3u);
+    unsigned long long t0 = nt > 0 ? ldg_stream64(tp) : 0ull, t1 = nt > 1 ? ldg_stream64(tp + 1) : 0ull, t2 = nt > 2 ? ldg_stream64(tp + 2) : 0ull;
+    Key128 k;
+    k.hi = xxh_finish_own(v0, 0ull, n_me, t0, t1, t2);
+    k.lo = xxh_finish_own(v1, kSeedLo, n_me, t0, t1, t2);
+    if (valid) *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = make_ulonglong2(bswap64(k.hi), bswap64(k.lo));
+    uint32_t slot = warp_insert(a.tab, a.mask, k, r, valid, a.ctr);
+    if (valid) a.slot_of_row[r] = slot;
+  }
+}
+
 // Variant C: same arithmetic and epilogue as k_hash_insert, but the frame ids reach the XXH64 lanes
 // through shared memory: every warp owns a two-stage ring (8 samples x 544 B per stage) that it fills
 // with cp.async (LDGSTS, 16 B per lane = one coalesced 512-B sample per instruction, no registers
