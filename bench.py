@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="rows of the batch (a prefix) timed on the CPU port for cpu_baseline")
     ap.add_argument("--ref-sample", type=int, default=2_000_000, help="rows per step of the --impl reference arm")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--hash-mode", default="xxh64x2", choices=["xxh64x2", "provided"],
+                    help="xxh64x2 = GPU hashes every stack (headline); provided = trace.Hash arrives with the sample, as in the reference")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="BASELINE.json config: 2 = headline (default), 3 = Zipf/CUDA-origin/50k labelsets")
     return ap.parse_args()
 
@@ -82,13 +84,14 @@ def measured_peak():
 
 
 def shard_workload(args, rank, world):
-    from parca_agent_b200 import synth
+    from parca_agent_b200 import abi, synth
+    mode = abi.PA_HASH_PROVIDED if args.hash_mode == "provided" else abi.PA_HASH_XXH64X2
     if args.config == 3:
-        return synth.config3(n=args.samples)
+        return synth.config3(n=args.samples, hash_mode=mode)
     if world == 1:
-        return synth.config2(n=args.samples)
+        return synth.config2(n=args.samples, hash_mode=mode)
     # weak scaling: every rank owns the pids with xxh64(pid) % world == rank and aggregates `samples` rows of them
-    return synth.config2_shard(rank, world, n=args.samples)
+    return synth.config2_shard(rank, world, n=args.samples, hash_mode=mode)
 
 
 def time_cpu_port(w, n_rows):
@@ -190,7 +193,9 @@ def main():
     value = total_rows * args.steps / dev_s_max
 
     # ---- end to end through the C ABI with host buffers (refill of the pinned ring is untimed)
-    e2e_times, h2d_b, d2h_b = [], w.n * 64 + w.n_frame_ids * 8, 0
+    provided = args.hash_mode == "provided"
+    # provided-hash mode uploads headers only; the unique stacks' frames are read in place from the pinned ring
+    e2e_times, h2d_b, d2h_b = [], (w.n * 64 if provided else w.n * 64 + w.n_frame_ids * 8), 0
     for i in range(max(1, args.e2e_steps) + 1):
         lib.load(a, w)
         barrier()
@@ -213,10 +218,16 @@ def main():
         hash_bytes = w.n * F * 8 + w.n * 16  # algorithmic: every frame id read once + one 16-byte stack id written per sample
         hm = float(np.mean(hash_ms))
         hash_launches = groups["hash"][0][1]
+        kernel_name = "k_hash_insert_wide (XXH64x2 + stack-table insert)"
+        if provided:  # no hash kernel in this mode: the dominant kernel is the header pass (64 B read + 63 B written per sample, + insert)
+            hash_bytes = w.n * (64 + 63)
+            hm = float(np.mean([x[0] for x in groups["header"]]))
+            hash_launches = groups["header"][0][1]
+            kernel_name = "k_header (header split + stack-table insert, provided-hash mode)"
         achieved = hash_bytes / (hm * 1e-3) / 1e9 if hm > 0 else None
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_latest.json"))).get("hash_dram_bytes_per_launch")
+            traffic = None if provided or args.config != 2 else json.load(open(os.path.join(ROOT, "profiles", "roofline_latest.json"))).get("hash_dram_bytes_per_launch")
         except Exception:
             pass
         cpu = None
@@ -232,12 +243,12 @@ def main():
             "data": "synthetic",
             "config": {"workload": "config%d: %d samples x %d frames per GPU, %d unique stacks, %d distinct frames, pid-sharded across %d GPU(s)"
                                    % (args.config, w.n, F, w.meta["U"], w.meta["P"], world),
-                       "hash_mode": "xxh64x2", "l2": "inputs (%.2f GB/GPU) far exceed the 126 MB L2; no explicit flush" % (h2d_b / 1e9),
+                       "hash_mode": args.hash_mode, "l2": "inputs (%.2f GB/GPU) far exceed the 126 MB L2; no explicit flush" % ((w.n * 64 + w.n_frame_ids * 8) / 1e9),
                        "timing": "CUDA events on the library's compute stream, max over ranks", "wall_s_for_steps": wall_max},
             "gpu_launches": int(launches),
             "kernel_groups_ms": {g: float(np.mean([x[0] for x in v])) for g, v in groups.items()},
             "kernel_groups_launches": {g: int(v[0][1]) for g, v in groups.items()},
-            "roofline": {"bound": "hbm", "kernel": "k_hash_insert (XXH64x2 + stack-table insert)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes": hash_bytes, "launches_per_step": hash_launches, "avg_launch_ms": hm / max(1, hash_launches)},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),

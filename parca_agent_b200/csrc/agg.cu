@@ -120,7 +120,7 @@ struct pa_agg {
   DBuf d_lsmat, d_kindtab, d_cols, d_jobs;
 
   // ---- ring (pinned host), double buffered
-  struct Ring { pa_sample_hdr* hdr = nullptr; uint64_t* frames = nullptr; uint64_t rows = 0, nfr = 0; } ring[2];
+  struct Ring { pa_sample_hdr* hdr = nullptr; uint64_t* frames = nullptr; const uint64_t* frames_dev = nullptr; uint64_t rows = 0, nfr = 0; } ring[2];
   int active = 0, inflight = 0;
   std::mutex ring_mu;
   std::condition_variable ring_cv;
@@ -296,12 +296,16 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   const uint64_t N = a->cfg.max_samples, NF = a->cfg.max_frames;
   for (int r = 0; r < 2; r++) {
     if (cudaHostAlloc((void**)&a->ring[r].hdr, N * sizeof(pa_sample_hdr), cudaHostAllocDefault) != cudaSuccess) return bail(PA_ENOMEM);
-    if (cudaHostAlloc((void**)&a->ring[r].frames, std::max<uint64_t>(NF, 1) * 8, cudaHostAllocDefault) != cudaSuccess) return bail(PA_ENOMEM);
+    if (cudaHostAlloc((void**)&a->ring[r].frames, std::max<uint64_t>(NF, 1) * 8, cudaHostAllocMapped) != cudaSuccess) return bail(PA_ENOMEM);
+    void* dp = nullptr;  // device alias of the pinned frame ring (provided-hash mode gathers unique stacks straight from it)
+    if (cudaHostGetDevicePointer(&dp, a->ring[r].frames, 0) != cudaSuccess) return bail(PA_EIO);
+    a->ring[r].frames_dev = (const uint64_t*)dp;
   }
   if (cudaHostAlloc((void**)&a->h_ctr_pinned, sizeof(Counters), cudaHostAllocDefault) != cudaSuccess) return bail(PA_ENOMEM);
   bool ok = true;
   auto need = [&](DBuf& b, uint64_t bytes) { ok = ok && b.ensure(std::max<uint64_t>(bytes, 256)) == cudaSuccess; };
-  need(a->d_hdr, N * 64); need(a->d_frames, NF * 8);
+  need(a->d_hdr, N * 64);
+  if (a->cfg.hash_mode == PA_HASH_XXH64X2) need(a->d_frames, NF * 8);  // provided-hash mode never uploads the frame stream
   need(a->d_ts, N * 8); need(a->d_value, N * 8); need(a->d_uuid, N * 16); need(a->d_stoff, N * 4); need(a->d_stsize, N * 4);
   need(a->d_slot, N * 4); need(a->d_kind, N); need(a->d_nfr, N * 2); need(a->d_foff, N * 8);
   need(a->d_ls, N * 4); need(a->d_cpu, N * 4); need(a->d_tid, N * 4); need(a->d_comm, N * 4);
@@ -448,7 +452,11 @@ static int stage_async(pa_agg* a) {
     uint64_t fend = (r1 < a->N) ? std::min<uint64_t>(r.hdr[r1].frame_off, a->NF) : a->NF;
     if (fend < fdone) fend = fdone;
     CK(cudaMemcpyAsync(a->d_hdr.as<uint8_t>() + r0 * 64, r.hdr + r0, (r1 - r0) * 64, cudaMemcpyHostToDevice, a->s_copy));
-    if (fend > fdone) CK(cudaMemcpyAsync(a->d_frames.as<uint64_t>() + fdone, r.frames + fdone, (fend - fdone) * 8, cudaMemcpyHostToDevice, a->s_copy));
+    // The stack id arrives with the sample in PA_HASH_PROVIDED mode (the reference's dataflow, parca_reporter.go:224):
+    // frames are only needed for each stack's FIRST occurrence, so nothing is uploaded here and k_gather_unique
+    // reads those few stacks from the mapped pinned ring over PCIe (U*F*8 bytes instead of N*F*8).
+    if (fend > fdone && a->cfg.hash_mode == PA_HASH_XXH64X2)
+      CK(cudaMemcpyAsync(a->d_frames.as<uint64_t>() + fdone, r.frames + fdone, (fend - fdone) * 8, cudaMemcpyHostToDevice, a->s_copy));
     fdone = fend;
     CK(cudaEventRecord(a->chunk_ev[k], a->s_copy));
     a->chunk_rows.emplace_back(r0, r1);
@@ -697,7 +705,8 @@ static int process_once(pa_agg* a) {
     launch_scan(a, UniqOffsetF{ctr, ctr, uniq_size, uniq_slot, tab}, 1, a->tm[T_RANK], Gu);
     a->tm[T_RANK].launches += 2;
   k_rows_materialize<<<G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>());
-  k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, a->d_frames.as<unsigned long long>(),
+  const unsigned long long* gather_src = provided ? (const unsigned long long*)a->ring[a->staged].frames_dev : a->d_frames.as<unsigned long long>();
+  k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, gather_src,
                                          a->d_foff.as<unsigned long long>(), n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr);
   a->tm[T_RANK].launches += 2;
   CK(cudaEventRecord(a->tm[T_RANK].b, s));
