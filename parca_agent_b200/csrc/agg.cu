@@ -425,6 +425,8 @@ int pa_agg_submit(pa_agg* a, const pa_sample_hdr* hdrs, const uint64_t* frames, 
 // stage: swap ring buffers, start the chunked H2D copies
 static int stage_async(pa_agg* a) {
   CK(cudaSetDevice(a->device));
+  // the detached ring buffer stays in use until collect() (provided-hash mode reads frames from it in place)
+  if (a->staged >= 0) return a->fail(PA_EINVAL, "the previously staged batch has not been collected");
   int buf;
   {
     std::unique_lock<std::mutex> g(a->ring_mu);
@@ -1158,8 +1160,10 @@ int pa_agg_flush(pa_agg* a, pa_agg_result* out) {
   int rc = stage_async(a);  // copies keep running while process() consumes the chunks already resident
   if (rc) return rc;
   rc = process(a);
-  if (rc) { cudaStreamSynchronize(a->s_copy); return rc; }
-  return collect(a, out);
+  if (rc) { cudaStreamSynchronize(a->s_copy); a->staged = -1; return rc; }  // a failed flush drops the interval's data (:1218-1220)
+  rc = collect(a, out);
+  if (rc) a->staged = -1;
+  return rc;
 }
 void pa_agg_release(pa_agg* a, pa_agg_result* res) {
   if (!a || !res) return;

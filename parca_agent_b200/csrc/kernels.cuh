@@ -273,27 +273,6 @@ __device__ __forceinline__ unsigned long long xxh_avalanche(unsigned long long h
 __device__ __forceinline__ unsigned long long xxh_lane_init(unsigned long long seed, int j) {
   return j == 0 ? seed + XP1 + XP2 : (j == 1 ? seed + XP2 : (j == 2 ? seed : seed - XP1));
 }
-// finish one sample given the 4 lane accumulators of its group (all 4 lanes call this)
-__device__ __forceinline__ unsigned long long xxh_finish(unsigned long long acc, unsigned long long seed, uint32_t n,
-                                                         unsigned long long t0, unsigned long long t1, unsigned long long t2, int gbase) {
-  const unsigned full = 0xFFFFFFFFu;
-  unsigned long long v0 = __shfl_sync(full, acc, gbase), v1 = __shfl_sync(full, acc, gbase + 1),
-                     v2 = __shfl_sync(full, acc, gbase + 2), v3 = __shfl_sync(full, acc, gbase + 3);
-  unsigned long long h;
-  if (n >= 4) {
-    h = rotl64(v0, 1) + rotl64(v1, 7) + rotl64(v2, 12) + rotl64(v3, 18);
-    h = xxh_merge(h, v0); h = xxh_merge(h, v1); h = xxh_merge(h, v2); h = xxh_merge(h, v3);
-  } else {
-    h = seed + XP5;
-  }
-  h += (unsigned long long)n * 8ull;
-  uint32_t t = n & 3u;  // up to three trailing 8-byte words after the last full stripe
-  if (t > 0) { h ^= rotl64(t0 * XP2, 31) * XP1; h = rotl64(h, 27) * XP1 + XP4; }
-  if (t > 1) { h ^= rotl64(t1 * XP2, 31) * XP1; h = rotl64(h, 27) * XP1 + XP4; }
-  if (t > 2) { h ^= rotl64(t2 * XP2, 31) * XP1; h = rotl64(h, 27) * XP1 + XP4; }
-  return xxh_avalanche(h);
-}
-
 struct HashArgs {
   const unsigned long long* frames;
   const unsigned long long* frame_off;
@@ -306,52 +285,8 @@ struct HashArgs {
   Counters* ctr;
 };
 
-// Variant A: 4 lanes per sample (one XXH64 accumulator lane each), 8 samples per warp, frame ids
-// streamed straight from global memory (each lane reads one 8-byte word of every 32-byte stripe).
-__global__ void __launch_bounds__(kThreads) k_hash_insert_direct(HashArgs a) {
-  const unsigned full = 0xFFFFFFFFu;
-  int lane = threadIdx.x & 31, j = lane & 3, g = lane >> 2, gbase = lane & ~3;
-  uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
-  uint32_t span = a.row1 - a.row0;
-  uint32_t iters = (span + nwarps * 8 - 1) / (nwarps * 8);
-  for (uint32_t it = 0; it < iters; it++) {
-    uint32_t r = a.row0 + (it * nwarps + warp) * 8 + g;
-    bool valid = r < a.row1;
-    uint32_t n = valid ? a.nframes[r] : 0;
-    const unsigned long long* p = a.frames + (valid ? a.frame_off[r] : 0ull);
-    unsigned long long a0 = xxh_lane_init(0ull, j), a1 = xxh_lane_init(kSeedLo, j);
-    uint32_t ns = n >> 2;
-    const unsigned long long* q = p + j;
-    uint32_t s = 0;
-    for (; s + 4 <= ns; s += 4) {
-      unsigned long long w0 = ldg_stream64(q + 4 * s), w1 = ldg_stream64(q + 4 * s + 4), w2 = ldg_stream64(q + 4 * s + 8),
-                         w3 = ldg_stream64(q + 4 * s + 12);
-      unsigned long long m0 = w0 * XP2, m1 = w1 * XP2, m2 = w2 * XP2, m3 = w3 * XP2;
-      a0 = xxh_round_pre(a0, m0); a1 = xxh_round_pre(a1, m0);
-      a0 = xxh_round_pre(a0, m1); a1 = xxh_round_pre(a1, m1);
-      a0 = xxh_round_pre(a0, m2); a1 = xxh_round_pre(a1, m2);
-      a0 = xxh_round_pre(a0, m3); a1 = xxh_round_pre(a1, m3);
-    }
-    for (; s < ns; s++) {
-      unsigned long long m = ldg_stream64(q + 4 * s) * XP2;
-      a0 = xxh_round_pre(a0, m); a1 = xxh_round_pre(a1, m);
-    }
-    const uint32_t nt = n & 3u;
-    unsigned long long t0 = nt > 0 ? ldg_stream64(p + 4 * ns) : 0ull, t1 = nt > 1 ? ldg_stream64(p + 4 * ns + 1) : 0ull,
-                       t2 = nt > 2 ? ldg_stream64(p + 4 * ns + 2) : 0ull;
-    __syncwarp(full);
-    Key128 k;
-    k.hi = xxh_finish(a0, 0ull, n, t0, t1, t2, gbase);
-    k.lo = xxh_finish(a1, kSeedLo, n, t0, t1, t2, gbase);
-    bool mine = valid && j == 0;
-    if (mine) *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = make_ulonglong2(bswap64(k.hi), bswap64(k.lo));
-    uint32_t slot = warp_insert(a.tab, a.mask, k, r, mine, a.ctr);
-    if (mine) a.slot_of_row[r] = slot;
-  }
-}
-
-// Variant B (default): one warp-iteration covers 32 consecutive samples. The XXH64 rounds still run
-// with 4 lanes per sample (8 samples at a time, 4 sub-iterations), but the per-sample epilogue —
+// Variant B ("direct"): one warp-iteration covers 32 consecutive samples. The XXH64 rounds run with 4 lanes
+// per sample (one accumulator lane each, 8 samples at a time, 4 sub-iterations) and the per-sample epilogue —
 // accumulator merge, avalanche, 16-byte id store, table insert — runs once with one *thread per
 // sample* after a shuffle transpose, so its cost is amortised over 32 samples instead of 8 and
 // the id store / slot store are fully coalesced (512 B / 128 B per warp).
@@ -429,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_hash_insert(HashArgs a) {
   }
 }
 
-// Variant B2: two lanes per sample, each owning two of the four XXH64 accumulator lanes and loading
+// Variant B2 ("wide", the default): two lanes per sample, each owning two of the four XXH64 accumulator lanes and loading
 // 16 bytes per stripe (LDG.128): four independent multiply chains per lane (2 accumulators x 2 seeds),
 // half the load / address / shuffle instructions of variant B. 16 samples per sub-step, 2 sub-steps
 // per 32-sample warp batch; the epilogue is the same thread-per-sample code.

@@ -250,3 +250,13 @@ def test_table_overflow_retry(gpu):
     st = t.column("stacktrace").chunk(0)
     assert (st.offsets.to_numpy() == np.arange(w2.n) * F).all()
     a.close()
+
+
+def test_randomized_sweep(oracle, gpu):
+    """40 random small batches: random size, hash mode, label flags and external labels."""
+    rng = np.random.Generator(np.random.PCG64(2024))
+    for i in range(40):
+        n = int(rng.integers(1, 2500))
+        mode = abi.PA_HASH_PROVIDED if rng.random() < 0.5 else abi.PA_HASH_XXH64X2
+        w = synth.edge_workload(seed=1000 + i, n=n, hash_mode=mode, label_flags=int(rng.integers(0, 8)), external=bool(rng.random() < 0.5))
+        assert_same(oracle, gpu, w, chunk_samples=int(rng.choice([0, 97, 512])))
