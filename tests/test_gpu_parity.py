@@ -260,3 +260,30 @@ def test_randomized_sweep(oracle, gpu):
         mode = abi.PA_HASH_PROVIDED if rng.random() < 0.5 else abi.PA_HASH_XXH64X2
         w = synth.edge_workload(seed=1000 + i, n=n, hash_mode=mode, label_flags=int(rng.integers(0, 8)), external=bool(rng.random() < 0.5))
         assert_same(oracle, gpu, w, chunk_samples=int(rng.choice([0, 97, 512])))
+
+
+def test_two_aggregators_concurrently(oracle, gpu):
+    """Two instances on one GPU, flushed from two host threads at once (the streaming bench mode)."""
+    import threading
+    ws = [synth.config1().head(30000), synth.edge_workload(seed=77, n=20000, hash_mode=abi.PA_HASH_XXH64X2)]
+    want = [oracle.run(w)[0] for w in ws]
+    aggs = [gpu.from_workload(w) for w in ws]
+    errors = []
+
+    def worker(i):
+        try:
+            for _ in range(6):
+                gpu.load(aggs[i], ws[i])
+                if aggs[i].flush().ipc_bytes() != want[i]:
+                    errors.append("instance %d produced different bytes" % i)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for a in aggs:
+        a.close()
+    assert not errors, errors
