@@ -71,6 +71,9 @@ enum {
 #define PA_LABEL_DISABLE_THREAD_ID 0x2u   /* --metadata-disable-thread-id-label (:318) */
 #define PA_LABEL_DISABLE_THREAD_COMM 0x4u /* --metadata-disable-thread-comm-label (:319) */
 
+#define PA_SCHEMA_V2 0u /* inline stacktraces, reporter/arrow_v2.go */
+#define PA_SCHEMA_V1 1u /* stacktrace ids only, reporter/arrow.go:260-332 + parca_reporter.go:246-328 (sample record) */
+
 #define PA_NO_STRING 0xFFFFFFFFu /* "no value"; string id 0 is always the empty string "" */
 
 /* One sample = one (trace, meta) pair handed to ReportTraceEvent (:219): 64 bytes. */
@@ -126,7 +129,8 @@ typedef struct pa_agg_config {
   uint64_t max_samples;        /* ring capacity in rows (per buffer; two buffers are kept) */
   uint64_t max_frames;         /* ring capacity in frame ids (per buffer) */
   uint32_t chunk_samples;      /* H2D/compute overlap granularity; 0 = default */
-  uint32_t reserved;
+  uint32_t schema;             /* PA_SCHEMA_V2 (0, default here) or PA_SCHEMA_V1 (--remote-store-use-v2-schema=false,
+                                  flags/flags.go:349): which sample record pa_agg_flush builds */
 } pa_agg_config;
 
 /* Result of one flush; memory is library-owned (pinned host) until pa_agg_release. */

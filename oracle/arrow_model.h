@@ -21,7 +21,7 @@
 
 namespace orc {
 
-enum TypeId { T_INT, T_UTF8, T_UTF8VIEW, T_FSB, T_TIMESTAMP_NS_UTC, T_STRUCT, T_LISTVIEW, T_REE, T_DICT_U32 };
+enum TypeId { T_INT, T_UTF8, T_UTF8VIEW, T_FSB, T_TIMESTAMP_NS_UTC, T_STRUCT, T_LISTVIEW, T_REE, T_DICT_U32, T_BINARY };
 
 struct DType;
 using TypeP = std::shared_ptr<DType>;
@@ -119,9 +119,9 @@ struct StringBuilder {
   std::string_view Value(int i) const {
     return std::string_view((const char*)data.data() + off[i], (size_t)(off[i + 1] - off[i]));
   }
-  ArrayData NewArray() {
+  ArrayData NewArray(TypeId id = T_UTF8) {  // T_UTF8 (string) or T_BINARY: identical layout, different type tag
     ArrayData a;
-    a.type = mk(T_UTF8);
+    a.type = mk(id);
     a.len = (int64_t)valid.size();
     a.nulls = nulls;
     a.bufs = {pack_validity(valid, nulls), buf_of(off), buf_of(data)};
@@ -151,11 +151,11 @@ struct BinaryDictBuilder {
   void AppendNull() { idx.AppendNull(); }
   int Len() const { return idx.Len(); }
   const std::string& Value(uint32_t i) const { return values[i]; }
-  ArrayData NewArray() {
+  ArrayData NewArray(TypeId value_id = T_UTF8) {
     StringBuilder sb;
     for (auto& s : values) sb.Append(s);
-    auto d = std::make_shared<ArrayData>(sb.NewArray());
-    ArrayData a = idx.NewArray(dict_t(mk(T_UTF8)));
+    auto d = std::make_shared<ArrayData>(sb.NewArray(value_id));
+    ArrayData a = idx.NewArray(dict_t(mk(value_id)));
     a.dict = d;
     memo.clear(); values.clear();
     return a;

@@ -111,7 +111,7 @@ class FBB {
 };
 
 // ---- Arrow flatbuffer enums -------------------------------------------------------------
-enum FbType { FB_Int = 2, FB_Utf8 = 5, FB_Timestamp = 10, FB_Struct = 13, FB_FSB = 15, FB_REE = 22, FB_Utf8View = 24, FB_ListView = 25 };
+enum FbType { FB_Int = 2, FB_Binary = 4, FB_Utf8 = 5, FB_Timestamp = 10, FB_Struct = 13, FB_FSB = 15, FB_REE = 22, FB_Utf8View = 24, FB_ListView = 25 };
 enum FbHeader { FB_Schema = 1, FB_DictionaryBatch = 2, FB_RecordBatch = 3 };
 
 class IpcWriter {
@@ -181,6 +181,7 @@ class IpcWriter {
     switch (t.id) {
       case T_INT: b.start(2); b.scalar<int32_t>(0, t.bits, 0); b.scalar<uint8_t>(1, t.sgn ? 1 : 0, 0); *to = b.end(); *tt = FB_Int; break;
       case T_UTF8: b.start(0); *to = b.end(); *tt = FB_Utf8; break;
+      case T_BINARY: b.start(0); *to = b.end(); *tt = FB_Binary; break;
       case T_UTF8VIEW: b.start(0); *to = b.end(); *tt = FB_Utf8View; break;
       case T_FSB: b.start(1); b.scalar<int32_t>(0, t.width, 0); *to = b.end(); *tt = FB_FSB; break;
       case T_TIMESTAMP_NS_UTC: {
@@ -261,7 +262,7 @@ class IpcWriter {
       case T_INT: case T_FSB: case T_TIMESTAMP_NS_UTC: case T_DICT_U32:
         put(body, a.bufs[1]);
         break;
-      case T_UTF8: case T_LISTVIEW:
+      case T_UTF8: case T_BINARY: case T_LISTVIEW:
         put(body, a.bufs[1]);
         put(body, a.bufs[2]);
         break;

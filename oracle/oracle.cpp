@@ -59,7 +59,7 @@ struct BinaryDictionaryRunEndBuilder {
     ree.Append(1);
     bd.Append(v);
   }
-  ArrayData NewArray() { ree.finishRun(); return ree.wrap(dict_t(mk(T_UTF8)), bd.NewArray()); }
+  ArrayData NewArray(TypeId value_id = T_UTF8) { ree.finishRun(); return ree.wrap(dict_t(mk(value_id)), bd.NewArray(value_id)); }
 };
 
 // reporter/arrow.go:153-177 / :179-207 — Uint64RunEndBuilder / Int64RunEndBuilder
@@ -262,6 +262,30 @@ struct SampleWriterV2 {
   }
 };
 
+// reporter/arrow.go:260-332 — SampleWriter (v1 schema: stacktrace ids only, every column run-end encoded)
+struct SampleWriter {
+  std::unordered_map<std::string, BinaryDictionaryRunEndBuilder*> labelBuilders;
+  BinaryDictionaryRunEndBuilder StacktraceID;
+  PrimBuilder<int64_t> Value;
+  BinaryDictionaryRunEndBuilder Producer, SampleType, SampleUnit, PeriodType, PeriodUnit, Temporality;
+  IntRunEndBuilder<int64_t> Period, Duration, Timestamp;
+  ~SampleWriter() { for (auto& e : labelBuilders) delete e.second; }
+  BinaryDictionaryRunEndBuilder* Label(const std::string& name) {  // arrow.go:523-532
+    auto it = labelBuilders.find(name);
+    BinaryDictionaryRunEndBuilder* b;
+    if (it == labelBuilders.end()) { b = new BinaryDictionaryRunEndBuilder(); labelBuilders.emplace(name, b); } else b = it->second;
+    b->EnsureLength(Value.Len());
+    return b;
+  }
+  void LabelAll(const std::string& name, const std::string& value) {  // arrow.go:534-543
+    auto it = labelBuilders.find(name);
+    BinaryDictionaryRunEndBuilder* b;
+    if (it == labelBuilders.end()) { b = new BinaryDictionaryRunEndBuilder(); labelBuilders.emplace(name, b); } else b = it->second;
+    b->ree.Append((uint64_t)(Value.Len() - b->ree.Len()));
+    b->bd.Append(value);
+  }
+};
+
 // ------------------------------------------------------------------------------------------
 struct Stats { uint64_t rows, unique_stacks, locations, functions, location_indices, empty_samples; };
 
@@ -273,6 +297,7 @@ struct Reporter {
   std::vector<std::vector<std::pair<std::string, std::string>>> labelsets;  // the labels LRU content (:569)
   std::unordered_map<TraceHash, std::pair<const uint64_t*, int>, TraceHashHasher> stacks;  // r.stacks LRU (:224-227)
   SampleWriterV2* w = new SampleWriterV2();
+  SampleWriter* w1 = new SampleWriter();  // v1 schema writer (r.sampleWriter)
   uint64_t emptySamples = 0;
   std::vector<uint8_t> ipc;
   Stats last{};
@@ -405,6 +430,7 @@ struct Reporter {
     if (stacks.find(hash) == stacks.end()) stacks.emplace(hash, std::make_pair(fr, (int)h.nframes));  // :224-227
     auto labels = labelsForTID(h.tid, h.labelset_id, S(h.comm_sid), h.cpu);                            // :229
     if (h.nframes == 0) emptySamples++;                                                                 // :237-239
+    if (cfg.schema == PA_SCHEMA_V1) { reportTraceEventV1(hash, h, labels); return; }                     // :242-328
     const uint64_t second = 1000000000ull;
     const int64_t memPeriod = 512 * 1024;
     switch (h.kind) {  // :338-363
@@ -434,8 +460,90 @@ struct Reporter {
     }
   }
 
+  // reporter/parca_reporter.go:246-328 — the v1 branch of ReportTraceEvent (writeSample closure + Origin switch)
+  void reportTraceEventV1(TraceHash hash, const pa_sample_hdr& h, const std::vector<std::pair<std::string, std::string>>& labels) {
+    char buf[16];  // trace.Hash.PutBytes16
+    for (int i = 0; i < 8; i++) { buf[i] = (char)(hash.hi >> (56 - 8 * i)); buf[8 + i] = (char)(hash.lo >> (56 - 8 * i)); }
+    auto writeSample = [&](int64_t value, int64_t duration, int64_t per, const char* producer, const char* sampleType, const char* sampleUnit,
+                           const char* periodType, const char* periodUnit) {
+      for (auto& lbl : labels) w1->Label(lbl.first)->Append(lbl.second);
+      w1->StacktraceID.Append(std::string_view(buf, 16));
+      w1->Timestamp.Append(h.timestamp_ns);
+      w1->Value.Append(value);
+      w1->SampleType.Append(sampleType);
+      w1->SampleUnit.Append(sampleUnit);
+      w1->PeriodType.Append(periodType);
+      w1->PeriodUnit.Append(periodUnit);
+      w1->Producer.Append(producer);
+      w1->Duration.Append(duration);
+      w1->Period.Append(per);
+    };
+    const int64_t second = 1000000000ll, persec = 1000000000ll / (int64_t)cfg.samples_per_second, memPeriod = 512 * 1024;
+    switch (h.kind) {
+      case PA_KIND_CPU:  // :284-287
+        writeSample(1, second, persec, "parca_agent", "samples", "count", "cpu", "nanoseconds");
+        w1->Temporality.Append("delta");
+        break;
+      case PA_KIND_OFFCPU:  // :288-291 (the v1 path keeps period = 1e9/Hz here, unlike v2)
+        writeSample(h.value, second, persec, "parca_agent", "wallclock", "nanoseconds", "samples", "count");
+        w1->Temporality.Append("delta");
+        break;
+      case PA_KIND_CUDA:  // :321-324
+        writeSample(h.value, second, persec, "parca_agent", "cuda", "nanoseconds", "cuda", "nanoseconds");
+        w1->Temporality.Append("delta");
+        break;
+      case PA_KIND_MEM_INUSE_OBJECTS: w1->Temporality.AppendNull(); writeSample(h.value, 0, memPeriod, "memory", "inuse_objects", "count", "space", "bytes"); break;
+      case PA_KIND_MEM_INUSE_SPACE: w1->Temporality.AppendNull(); writeSample(h.value, 0, memPeriod, "memory", "inuse_space", "bytes", "space", "bytes"); break;
+      case PA_KIND_MEM_ALLOC_OBJECTS: w1->Temporality.AppendNull(); writeSample(h.value, 0, memPeriod, "memory", "alloc_objects", "count", "space", "bytes"); break;
+      case PA_KIND_MEM_ALLOC_SPACE: w1->Temporality.AppendNull(); writeSample(h.value, 0, memPeriod, "memory", "alloc_space", "bytes", "space", "bytes"); break;
+      default: break;
+    }
+  }
+
+  // reporter/parca_reporter.go:1528-1543 (buildSampleRecord) + reporter/arrow.go:274-316 (NewRecord) + IPC :1390-1400
+  void flushV1() {
+    SampleWriter* cur = w1;
+    w1 = new SampleWriter();
+    stacks.clear();
+    for (auto& l : externalLabels) cur->LabelAll(l.first, l.second);  // writeCommonLabels :1515-1519
+    last = Stats{(uint64_t)cur->Value.Len(), (uint64_t)cur->StacktraceID.bd.values.size(), 0, 0, 0, emptySamples};
+    emptySamples = 0;
+    ipc.clear();
+    if (cur->Value.Len() == 0) { delete cur; return; }  // :1387-1390
+    std::vector<std::string> labelNames;
+    for (auto& e : cur->labelBuilders) labelNames.push_back(e.first);
+    std::sort(labelNames.begin(), labelNames.end());
+    int64_t length = cur->Value.Len();
+    TypeP dictBin = ree_t(dict_t(mk(T_BINARY)));
+    std::vector<Field> fields;
+    std::vector<ArrayData> cols;
+    for (auto& name : labelNames) {
+      BinaryDictionaryRunEndBuilder* b = cur->labelBuilders[name];
+      b->EnsureLength(length);
+      fields.push_back(Field{"labels." + name, dictBin, true, {}});  // ColumnLabelsPrefix, arrow.go:515-521
+      cols.push_back(b->NewArray(T_BINARY));
+    }
+    auto add = [&](const char* name, TypeP t, ArrayData a) { fields.push_back(Field{name, std::move(t), false, {}}); cols.push_back(std::move(a)); };
+    add("stacktrace_id", dictBin, cur->StacktraceID.NewArray(T_BINARY));  // ArrowSamplesField arrow.go:484-503
+    add("value", int_t(64, true), cur->Value.NewArray(int_t(64, true)));
+    add("producer", dictBin, cur->Producer.NewArray(T_BINARY));
+    add("sample_type", dictBin, cur->SampleType.NewArray(T_BINARY));
+    add("sample_unit", dictBin, cur->SampleUnit.NewArray(T_BINARY));
+    add("period_type", dictBin, cur->PeriodType.NewArray(T_BINARY));
+    add("period_unit", dictBin, cur->PeriodUnit.NewArray(T_BINARY));
+    add("temporality", dictBin, cur->Temporality.NewArray(T_BINARY));
+    add("period", ree_t(int_t(64, true)), cur->Period.NewArray(true));
+    add("duration", ree_t(int_t(64, true)), cur->Duration.NewArray(true));
+    add("timestamp", ree_t(int_t(64, true)), cur->Timestamp.NewArray(true));
+    IpcWriter iw;
+    iw.write_stream(fields, {{"parca_write_schema_version", "v1"}}, cols, length);
+    ipc.swap(iw.out);
+    delete cur;
+  }
+
   // reporter/parca_reporter.go:1742-1764 + reporter/arrow_v2.go:612-663 + IPC :1779-1790
   void flush() {
+    if (cfg.schema == PA_SCHEMA_V1) { flushV1(); return; }
     SampleWriterV2* cur = w;
     w = new SampleWriterV2();
     stacks.clear();
@@ -541,7 +649,7 @@ void* orc_create(const pa_agg_config* cfg) {
   r->cfg = *cfg;
   return r;
 }
-void orc_destroy(void* p) { if (!p) return; Reporter* r = (Reporter*)p; delete r->w; delete r; }
+void orc_destroy(void* p) { if (!p) return; Reporter* r = (Reporter*)p; delete r->w; delete r->w1; delete r; }
 
 int orc_register_strings(void* p, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, uint32_t* first_id) {
   Reporter* r = (Reporter*)p;

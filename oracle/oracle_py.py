@@ -59,7 +59,7 @@ class Oracle:
     def __init__(self, w):
         L = lib()
         cfg = abi.PaAggConfig(abi_version=abi.PA_ABI_VERSION, device=0, hash_mode=w.hash_mode, label_flags=w.label_flags,
-                              samples_per_second=w.samples_per_second)
+                              samples_per_second=w.samples_per_second, schema=getattr(w, "schema", 0))
         self.h = L.orc_create(C.byref(cfg))
         assert self.h
         blob, offs = abi.pack_strings(w.strings[1:])  # id 0 == "" is implicit

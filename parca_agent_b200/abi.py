@@ -19,6 +19,7 @@ PA_HASH_PROVIDED, PA_HASH_XXH64X2 = 0, 1
 PA_XXH_SEED_LO = 0x9E3779B97F4A7C15
 
 PA_LABEL_DISABLE_CPU, PA_LABEL_DISABLE_THREAD_ID, PA_LABEL_DISABLE_THREAD_COMM = 1, 2, 4
+PA_SCHEMA_V2, PA_SCHEMA_V1 = 0, 1
 PA_NO_STRING = 0xFFFFFFFF
 
 # struct pa_sample_hdr (64 B)
@@ -50,7 +51,7 @@ class PaAggConfig(C.Structure):
         ("abi_version", C.c_uint32), ("device", C.c_int32), ("hash_mode", C.c_uint32), ("label_flags", C.c_uint32),
         ("samples_per_second", C.c_uint32), ("n_external_labels", C.c_uint32),
         ("external_labels", C.POINTER(PaLabelPair)),
-        ("max_samples", C.c_uint64), ("max_frames", C.c_uint64), ("chunk_samples", C.c_uint32), ("reserved", C.c_uint32),
+        ("max_samples", C.c_uint64), ("max_frames", C.c_uint64), ("chunk_samples", C.c_uint32), ("schema", C.c_uint32),
     ]
 
 

@@ -88,14 +88,14 @@ class Aggregator:
     """Thin object wrapper over one pa_agg handle."""
 
     def __init__(self, device=0, hash_mode=abi.PA_HASH_XXH64X2, label_flags=0, samples_per_second=19, external_labels=(),
-                 max_samples=1 << 20, max_frames=0, chunk_samples=0):
+                 max_samples=1 << 20, max_frames=0, chunk_samples=0, schema=abi.PA_SCHEMA_V2):
         L = lib()
         ext = (abi.PaLabelPair * max(1, len(external_labels)))()
         for i, (n, v) in enumerate(external_labels):
             ext[i].name_sid, ext[i].value_sid = int(n), int(v)
         cfg = abi.PaAggConfig(abi_version=abi.PA_ABI_VERSION, device=device, hash_mode=hash_mode, label_flags=label_flags,
                               samples_per_second=samples_per_second, n_external_labels=len(external_labels), external_labels=ext,
-                              max_samples=max_samples, max_frames=max_frames, chunk_samples=chunk_samples)
+                              max_samples=max_samples, max_frames=max_frames, chunk_samples=chunk_samples, schema=schema)
         h = C.c_void_p()
         rc = L.pa_agg_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -194,7 +194,7 @@ def from_workload(w, device=0, max_samples=None, max_frames=None, chunk_samples=
     n = max(1, w.n if max_samples is None else max_samples)
     nf = max(1, w.n_frame_ids if max_frames is None else max_frames)
     a = Aggregator(device=device, hash_mode=w.hash_mode, label_flags=w.label_flags, samples_per_second=w.samples_per_second,
-                   external_labels=w.external_labels, max_samples=n, max_frames=nf, chunk_samples=chunk_samples)
+                   external_labels=w.external_labels, max_samples=n, max_frames=nf, chunk_samples=chunk_samples, schema=getattr(w, "schema", 0))
     first = a.register_strings(w.strings[1:])
     assert first == 1, first
     a.register_frames(w.frames)

@@ -45,6 +45,7 @@ class Workload:
     samples_per_second: int = 19
     external_labels: list = field(default_factory=list)  # [(name_sid, value_sid)]
     meta: dict = field(default_factory=dict)
+    schema: int = abi.PA_SCHEMA_V2    # which sample record the reporter builds (v1 = stacktrace ids only)
 
     @property
     def n(self):
@@ -75,7 +76,7 @@ class Workload:
         n = min(n, self.n)
         w = Workload(self.name + "[:%d]" % n, self.strings, self.frames, self.labelsets, self.hdrs[:n].copy(),
                      hash_mode=self.hash_mode, label_flags=self.label_flags, samples_per_second=self.samples_per_second,
-                     external_labels=list(self.external_labels), meta=dict(self.meta))
+                     external_labels=list(self.external_labels), meta=dict(self.meta), schema=self.schema)
         if self._frame_ids is None:
             w.stack_table, w.stack_choice = self.stack_table, self.stack_choice[:n]
         else:
@@ -93,7 +94,7 @@ class Workload:
             off[1:] = np.cumsum(nf)[:-1]
         w = Workload(self.name + "[subset]", self.strings, self.frames, self.labelsets, hd,
                      hash_mode=self.hash_mode, label_flags=self.label_flags, samples_per_second=self.samples_per_second,
-                     external_labels=list(self.external_labels), meta=dict(self.meta))
+                     external_labels=list(self.external_labels), meta=dict(self.meta), schema=self.schema)
         if self._frame_ids is None:
             w.stack_table, w.stack_choice = self.stack_table, self.stack_choice[idx]
         else:

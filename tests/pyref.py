@@ -430,3 +430,96 @@ def diff(a, b, path=""):
                 return "%s[%d]: %r != %r" % (path, i, x if not isinstance(x, bytes) else x[:40], y if not isinstance(y, bytes) else y[:40])
         return None
     return None if a == b else "%s: %r != %r" % (path, a, b)
+
+
+# ================================================================================================
+# v1 schema (reporter/parca_reporter.go:246-328 + reporter/arrow.go:260-332, :484-521)
+V1_KIND_TABLE = {  # (value_from_hdr, duration, period|None=1e9/sps, delta, 5 strings); v1 keeps period=1e9/Hz for off-CPU and CUDA
+    abi.PA_KIND_CPU: (False, 10**9, None, True, "parca_agent", "samples", "count", "cpu", "nanoseconds"),
+    abi.PA_KIND_OFFCPU: (True, 10**9, None, True, "parca_agent", "wallclock", "nanoseconds", "samples", "count"),
+    abi.PA_KIND_CUDA: (True, 10**9, None, True, "parca_agent", "cuda", "nanoseconds", "cuda", "nanoseconds"),
+    abi.PA_KIND_MEM_INUSE_OBJECTS: (True, 0, 512 * 1024, False, "memory", "inuse_objects", "count", "space", "bytes"),
+    abi.PA_KIND_MEM_INUSE_SPACE: (True, 0, 512 * 1024, False, "memory", "inuse_space", "bytes", "space", "bytes"),
+    abi.PA_KIND_MEM_ALLOC_OBJECTS: (True, 0, 512 * 1024, False, "memory", "alloc_objects", "count", "space", "bytes"),
+    abi.PA_KIND_MEM_ALLOC_SPACE: (True, 0, 512 * 1024, False, "memory", "alloc_space", "bytes", "space", "bytes"),
+}
+
+
+def reference_record_v1(w):
+    S = lambda sid: w.strings[int(sid)]  # noqa: E731
+    labels = {}
+    stid = _DictRee()
+    names = ["producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality"]
+    cols = {n: _DictRee() for n in names}
+    period, duration, timestamp = _ValRee(), _ValRee(), _ValRee()
+    value = []
+    frame_ids = w.frame_ids
+    for r in range(w.n):
+        h = w.hdrs[r]
+        if w.hash_mode == abi.PA_HASH_XXH64X2:
+            fr = [int(x) for x in frame_ids[int(h["frame_off"]):int(h["frame_off"]) + int(h["nframes"])]]
+            key = (xxh64_words(fr, 0), xxh64_words(fr, abi.PA_XXH_SEED_LO))
+        else:
+            key = (int(h["hash_hi"]), int(h["hash_lo"]))
+        nrows = len(value)
+        for name, v in labels_for_tid(w, h, S):
+            b = labels.setdefault(name, _DictRee())
+            b.ensure(nrows)
+            b.append(v)
+        from_hdr, dur, per, delta, prod, stype, sunit, ptype, punit = V1_KIND_TABLE[int(h["kind"])]
+        stid.append(key[0].to_bytes(8, "big") + key[1].to_bytes(8, "big"))
+        timestamp.append(int(h["timestamp_ns"]))
+        value.append(int(h["value"]) if from_hdr else 1)
+        cols["sample_type"].append(stype.encode())
+        cols["sample_unit"].append(sunit.encode())
+        cols["period_type"].append(ptype.encode())
+        cols["period_unit"].append(punit.encode())
+        cols["producer"].append(prod.encode())
+        duration.append(dur)
+        period.append(10**9 // w.samples_per_second if per is None else per)
+        if delta:
+            cols["temporality"].append(b"delta")
+        else:
+            cols["temporality"].null()
+    rows = len(value)
+    for n_sid, v_sid in w.external_labels:
+        b = labels.setdefault(S(n_sid), _DictRee())
+        b.ree.append(rows - b.ree.length)
+        b._bd_append(S(v_sid))
+    for b in labels.values():
+        b.ensure(rows)
+    out = {"rows": rows, "labels": {k.decode(): v.out() for k, v in sorted(labels.items())}, "stacktrace_id": stid.out(), "value": value,
+           "period": period.out(), "duration": duration.out(), "timestamp": timestamp.out()}
+    for n in names:
+        out[n] = cols[n].out()
+    return out
+
+
+def extract_v1(batch):
+    if isinstance(batch, pa.Table):
+        batch = batch.combine_chunks().to_batches()[0]
+    col = {f.name: batch.column(i) for i, f in enumerate(batch.schema)}
+
+    def dict_ree(a):
+        d = _dict_out(a.values)
+        return {"run_ends": a.run_ends.to_pylist(), "indices": d["indices"], "dict": d["dict"]}
+
+    out = {"rows": batch.num_rows, "labels": {}, "value": col["value"].to_pylist()}
+    for name, a in col.items():
+        if name.startswith("labels."):
+            out["labels"][name[len("labels."):]] = dict_ree(a)
+    for n in ("stacktrace_id", "producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality"):
+        out[n] = dict_ree(col[n])
+    for n in ("period", "duration", "timestamp"):
+        out[n] = _ree_out(col[n])
+    return out
+
+
+def expected_schema_v1(label_names):
+    lab = pa.run_end_encoded(pa.int32(), pa.dictionary(pa.uint32(), pa.binary()))
+    ri = pa.run_end_encoded(pa.int32(), pa.int64())
+    fields = [pa.field("labels." + n, lab, True) for n in label_names]
+    fields += [pa.field("stacktrace_id", lab, False), pa.field("value", pa.int64(), False)]
+    fields += [pa.field(n, lab, False) for n in ("producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality")]
+    fields += [pa.field("period", ri, False), pa.field("duration", ri, False), pa.field("timestamp", ri, False)]
+    return pa.schema(fields, metadata={"parca_write_schema_version": "v1"})

@@ -84,3 +84,33 @@ def test_string_view_blocks(oracle):
     nl = len(msgs[0]["fields"][0]["children"])
     fb = [m for m in msgs if m["header"] == "DictionaryBatch" and m["id"] == nl + 4][0]
     assert fb["batch"]["variadic"][0] >= 1
+
+
+# ---- v1 schema (the reference's default, --remote-store-use-v2-schema=false) --------------------
+def check_v1(oracle, w):
+    w.schema = abi.PA_SCHEMA_V1
+    data, st = oracle.run(w)
+    t = pa.ipc.open_stream(data).read_all()
+    got = pyref.extract_v1(t)
+    want = pyref.reference_record_v1(w)
+    d = pyref.diff(want, got)
+    assert d is None, d
+    assert t.schema.equals(pyref.expected_schema_v1(list(want["labels"].keys())), check_metadata=True)
+    assert st["rows"] == w.n and st["unique_stacks"] == len(want["stacktrace_id"]["dict"])
+    return t
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("mode", [abi.PA_HASH_PROVIDED, abi.PA_HASH_XXH64X2])
+def test_v1_edge_batches(oracle, seed, mode):
+    check_v1(oracle, synth.edge_workload(seed=seed, hash_mode=mode))
+    t = check_v1(oracle, synth.edge_workload(seed=seed, hash_mode=mode, external=False))
+    t.validate(full=True)
+
+
+def test_v1_config1_prefix(oracle):
+    t = check_v1(oracle, synth.config1().head(3000))
+    t.validate(full=True)
+    row = t.slice(0, 1).to_pylist()[0]
+    assert row["period"] == 10**9 // 19 and row["duration"] == 10**9 and row["producer"] == b"parca_agent" and row["temporality"] == b"delta"
+    assert len(row["stacktrace_id"]) == 16
