@@ -148,6 +148,10 @@ struct pa_agg {
   uint32_t *sd_first[4] = {}, *sd_rank[4] = {}, *sd_order[4] = {}, *sd_keys[4] = {}, *sd_valid[4] = {};  // type,map,bid,file
   uint32_t *fn_first = nullptr, *fn_rank = nullptr, *fn_order = nullptr, *fn_keys = nullptr;
   LocOut lo{};
+  uint32_t *v1_ord = nullptr, *v1_first_kind = nullptr, *v1_kindrank = nullptr, *v1_kind_order = nullptr, *v1_n_kind_dict = nullptr;
+  long long* v1_ts_vals = nullptr;
+  uint8_t* v1_ids = nullptr;
+  int* v1_id_off = nullptr;
   unsigned long long* tid_slots = nullptr;
   uint32_t* tid_rank = nullptr;
   uint32_t tid_mask = 0;
@@ -198,7 +202,9 @@ static void build_kind_tables(pa_agg* a) {
       if (it == v.end()) { v.push_back(tabs[t][k]); it = v.end() - 1; }
       a->kindtab[t * 8 + k] = (uint32_t)(it - v.begin());
     }
-  int64_t per[7] = {1000000000ll / (int64_t)a->cfg.samples_per_second, 0, 1, 524288, 524288, 524288, 524288};
+  const int64_t persec = 1000000000ll / (int64_t)a->cfg.samples_per_second;
+  const bool v1 = a->cfg.schema == PA_SCHEMA_V1;  // the v1 writer keeps period = 1e9/Hz for off-CPU and CUDA (parca_reporter.go:289, :322)
+  int64_t per[7] = {persec, v1 ? persec : 0, v1 ? persec : 1, 524288, 524288, 524288, 524288};
   uint64_t dur[7] = {1000000000ull, 1000000000ull, 1000000000ull, 0, 0, 0, 0};
   a->period_vals.clear();
   a->duration_vals.clear();
@@ -250,9 +256,13 @@ static int build_columns(pa_agg* a) {
   if (on_tid) add("thread_id", COL_TID, 0);
   if (on_comm) add("thread_name", COL_COMM, 0 /* = canonical string count, set per flush */);
   a->n_label_cols = (uint32_t)a->cols.size();
-  if (a->n_label_cols + 8 > (uint32_t)kMaxCols) return a->fail(PA_ERANGE, "too many distinct label names for one batch (limit 40)");
+  if (a->n_label_cols + 10 > (uint32_t)kMaxCols) return a->fail(PA_ERANGE, "too many distinct label names for one batch (limit 38)");
   static const char* fixed[8] = {"producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality", "period", "duration"};
   for (uint32_t t = 0; t < 8; t++) { ColPlan c; c.name = fixed[t]; c.type = COL_KIND; c.param = t; a->cols.push_back(std::move(c)); }
+  if (a->cfg.schema == PA_SCHEMA_V1) {  // v1: stacktrace_id and timestamp are run-end encoded too (arrow.go:395-400, :471-474)
+    ColPlan o; o.name = "stacktrace_id"; o.type = COL_ORD; a->cols.push_back(std::move(o));
+    ColPlan t; t.name = "timestamp"; t.type = COL_TS; a->cols.push_back(std::move(t));
+  }
   build_kind_tables(a);
   a->cols_dirty = false;
   return PA_OK;
@@ -265,7 +275,7 @@ uint32_t pa_agg_abi_version(void) { return PA_ABI_VERSION; }
 const char* pa_agg_last_error(const pa_agg* a) { return a ? a->err.c_str() : "null handle"; }
 
 int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
-  if (!cfg || !out || cfg->abi_version != PA_ABI_VERSION || cfg->samples_per_second == 0 || cfg->max_samples == 0 || cfg->hash_mode > 1) return PA_EINVAL;
+  if (!cfg || !out || cfg->abi_version != PA_ABI_VERSION || cfg->samples_per_second == 0 || cfg->max_samples == 0 || cfg->hash_mode > 1 || cfg->schema > 1) return PA_EINVAL;
   if (cfg->max_samples > 0x7FFFFFFFull) return PA_ERANGE;  // run ends / ListView offsets are int32
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return PA_ENODEV;
@@ -503,6 +513,7 @@ static int process_once(pa_agg* a) {
   const uint64_t N = a->N;
   const uint32_t n_cstr = a->sp.count(), n_frames = a->ft.count(), n_funcs = a->ft.n_funcs();
   const uint32_t ncols = (uint32_t)a->cols.size(), nlab = a->n_label_cols;
+  const bool v1 = a->cfg.schema == PA_SCHEMA_V1;
   cudaStream_t s = a->s_comp;
   for (int t = 0; t < T_COUNT; t++) { a->tm[t].launches = 0; a->tm[t].ms = 0; }
 
@@ -530,6 +541,10 @@ static int process_once(pa_agg* a) {
   const size_t Nn = (size_t)std::max<uint64_t>(N, 1);
   uint32_t *rowbits = nullptr, *row_wprefix = nullptr, *uniq_slot = nullptr, *uniq_size = nullptr, *first_ls = nullptr;
   want(&first_ls, std::max<size_t>(a->ls.sets.size(), 1) * 4, 0);
+  if (v1) {
+    want(&a->v1_ord, Nn * 4); want(&a->v1_ts_vals, Nn * 8); want(&a->v1_ids, Nn * 16); want(&a->v1_id_off, (Nn + 1) * 4);
+    want(&a->v1_first_kind, 8 * 4, 0); want(&a->v1_kindrank, 64 * 4); want(&a->v1_kind_order, 64 * 4); want(&a->v1_n_kind_dict, 8 * 4);
+  }
   want(&rowbits, (Nn / 32 + 2) * 4, 1); want(&row_wprefix, (Nn / 32 + 2) * 4); want(&uniq_slot, Nn * 4); want(&uniq_size, Nn * 4);
   uint32_t *loc_bits = nullptr, *loc_wp = nullptr;
   want(&a->loc_first, P * 4, 0); want(&a->loc_rank, P * 4); want(&a->loc_order, P * 4);
@@ -550,6 +565,7 @@ static int process_once(pa_agg* a) {
     ColPlan& cp = a->cols[c];
     want(&cp.run_ends, Nn * 4);
     want(&cp.run_keys, Nn * 4);
+    if (v1 && cp.type == COL_KIND && cp.param == 5) want(&cp.validity, (Nn / 32 + 2) * 4, 1);  // temporality has null runs
     if (c >= nlab) continue;
     want(&cp.validity, (Nn / 32 + 2) * 4, 1);
     want(&col_bits[c], (Nn / 32 + 2) * 4); want(&col_wp[c], (Nn / 32 + 2) * 4);
@@ -608,7 +624,7 @@ static int process_once(pa_agg* a) {
   }
   std::vector<ReeCol> rc(ncols);
   ReeArgs ra{};
-  ra.c_cpu = ra.c_tid = ra.c_comm = -1;
+  ra.c_cpu = ra.c_tid = ra.c_comm = ra.c_ord = ra.c_ts = -1;
   for (uint32_t c = 0; c < ncols; c++) {
     const ColPlan& cp = a->cols[c];
     rc[c] = ReeCol{cp.type, cp.param, cp.run_ends, cp.run_keys, c < nlab ? col_first[c] : nullptr, nullptr, 0,
@@ -617,7 +633,11 @@ static int process_once(pa_agg* a) {
     if (cp.type == COL_CPU) ra.c_cpu = (int)c;
     if (cp.type == COL_TID) ra.c_tid = (int)c;
     if (cp.type == COL_COMM) ra.c_comm = (int)c;
+    if (cp.type == COL_ORD) ra.c_ord = (int)c;
+    if (cp.type == COL_TS) ra.c_ts = (int)c;
+    if (v1 && cp.type == COL_KIND && cp.param == 5) { rc[c].nullable = 1; rc[c].validity = cp.validity; }
   }
+  if (v1) { ra.ord = a->v1_ord; ra.ts = a->d_ts.as<long long>(); ra.ts_vals = a->v1_ts_vals; ra.kindrank = a->v1_kindrank; ra.kind_dict_mask = 0x3Fu; }
   // descriptor tables go up first, from pinned staging: a pageable cudaMemcpyAsync would synchronise the
   // stream in the middle of the pipeline and leave the tail launch-bound
   {
@@ -664,6 +684,7 @@ static int process_once(pa_agg* a) {
       if (a->cols[c].type == COL_TID) { h.tid_slots = a->tid_slots; h.tid_mask = a->tid_mask; }
       if (a->cols[c].type == COL_COMM) h.first_comm = col_first[c];
     }
+    h.first_kind = v1 ? a->v1_first_kind : nullptr;
     uint64_t rows = r1 - r0;
     int hb = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)G * 2);
     k_header<<<std::max(hb, 1), kThreads, 0, s>>>(h);
@@ -706,10 +727,14 @@ static int process_once(pa_agg* a) {
     k_stack_assign<<<Gs, kThreads, 0, s>>>(tab, nslots, rowbits, row_wprefix, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(), uniq_slot, uniq_size);
     launch_scan(a, UniqOffsetF{ctr, ctr, uniq_size, uniq_slot, tab}, 1, a->tm[T_RANK], Gu);
     a->tm[T_RANK].launches += 2;
-  k_rows_materialize<<<G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>());
-  const unsigned long long* gather_src = provided ? (const unsigned long long*)a->ring[a->staged].frames_dev : a->d_frames.as<unsigned long long>();
-  k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, gather_src,
-                                         a->d_foff.as<unsigned long long>(), n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr);
+  k_rows_materialize<<<G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>(), v1 ? a->v1_ord : nullptr);
+  if (v1) {  // v1 has no inline stacktraces: only the dictionary of unique stack ids
+    k_gather_ids<<<small_grid(a, std::min<uint64_t>(N, cap / 2) + 1), kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_uuid.as<uint8_t>(), a->v1_ids, a->v1_id_off);
+  } else {
+    const unsigned long long* gather_src = provided ? (const unsigned long long*)a->ring[a->staged].frames_dev : a->d_frames.as<unsigned long long>();
+    k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, gather_src,
+                                           a->d_foff.as<unsigned long long>(), n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr);
+  }
   a->tm[T_RANK].launches += 2;
   CK(cudaEventRecord(a->tm[T_RANK].b, s));
 
@@ -727,6 +752,7 @@ static int process_once(pa_agg* a) {
 
   CK(cudaEventRecord(a->tm[T_LOC].a, s));
   FrameTable ftd{(const unsigned long long*)a->m_addr.ptr(), a->m_type.ptr(), a->m_map.ptr(), a->m_bid.ptr(), (const unsigned long long*)a->m_line.ptr(), a->m_func.ptr()};
+  if (!v1) {  // v1 carries no locations in the sample record
     run_jobs(j_loc, 1, false, a->tm[T_LOC], std::min<uint64_t>(NI, cap * 32), P);  // location index per unique-stack frame (in place over the gathered stream)
     launch_scan(a, LocLinesF{ctr, ctr, a->loc_order, ftd, a->lo}, 1, a->tm[T_LOC], small_grid(a, P));
     k_line_validity<<<std::max(1, std::min(G, (int)(P / 256 + 1))), kThreads, 0, s>>>(ctr, a->lo.line_size, a->lo.line_valid);
@@ -734,6 +760,7 @@ static int process_once(pa_agg* a) {
     k_func_keys<<<std::max(1, std::min(G, (int)(FN / 256 + 1))), kThreads, 0, s>>>(ctr, a->fn_order, a->m_fnfile.ptr(), a->sd_keys[3]);
     run_jobs(j_file, 1, true, a->tm[T_LOC], FN, S);  // function.filename
     a->tm[T_LOC].launches += 2;
+  }
   CK(cudaEventRecord(a->tm[T_LOC].b, s));
 
   // ---- run-end encoding of label + constant columns (dictionary first positions recorded on the fly)
@@ -752,6 +779,7 @@ static int process_once(pa_agg* a) {
     k_ls_first<<<small_grid(a, (uint64_t)lf.n_labelsets * lf.n_ls), kThreads, 0, s>>>(lf);
     a->tm[T_LABELS].launches++;
   }
+  if (v1) { k_kind_ranks<<<1, 32, 0, s>>>(a->v1_first_kind, a->d_kindtab.as<uint32_t>(), a->v1_kindrank, a->v1_kind_order, a->v1_n_kind_dict); a->tm[T_LABELS].launches++; }
   k_ree_pass<false><<<Gr, kThreads, 0, s>>>(ra);  // run counts
   k_ree_scan_partials<<<ncols, 32, 0, s>>>(ra, Gr * kWarps);
   a->tm[T_LABELS].launches += 2;
@@ -840,13 +868,13 @@ Node int_node(const char* name, int bits, bool sgn, bool nullable, int64_t len, 
 }
 // utf8 array from a list of strings
 Node utf8_node(pa_agg* a, const char* name, bool nullable, const std::vector<std::pair<const uint8_t*, uint32_t>>& strs,
-               const std::vector<uint8_t>* valid = nullptr) {
+               const std::vector<uint8_t>* valid = nullptr, Ty ty = Ty::Utf8) {
   std::vector<int32_t> off(strs.size() + 1, 0);
   uint64_t tot = 0;
   for (size_t i = 0; i < strs.size(); i++) { tot += strs[i].second; off[i + 1] = (int32_t)tot; }
   std::vector<uint8_t> data(tot);
   for (size_t i = 0; i < strs.size(); i++) if (strs[i].second) memcpy(data.data() + off[i], strs[i].first, strs[i].second);
-  Node n; n.ty = Ty::Utf8; n.name = name; n.nullable = nullable; n.length = (int64_t)strs.size();
+  Node n; n.ty = ty; n.name = name; n.nullable = nullable; n.length = (int64_t)strs.size();  // Utf8 and Binary share one layout
   n.bufs = {host_ref(a, off), BufRef::host(keep(a, std::move(data)).data(), tot)};
   if (valid) {
     std::vector<uint8_t> bits((strs.size() + 7) / 8, 0);
@@ -888,6 +916,9 @@ static int collect(pa_agg* a, pa_agg_result* res) {
   double t0 = now_ms();
   const Counters& c = a->h_ctr;
   const uint32_t nlab = a->n_label_cols;
+  const bool v1 = a->cfg.schema == PA_SCHEMA_V1;
+  const Ty lab_ty = v1 ? Ty::Binary : Ty::Utf8;                 // v1 label dictionaries hold binary values (arrow.go:465-471)
+  const std::string lab_prefix = v1 ? "labels." : "";           // v1: top-level columns "labels.<name>" (ColumnLabelsPrefix)
   const uint32_t n_loc = c.n_locations, n_lines = c.n_lines, n_fn = c.n_functions, n_idx = (uint32_t)c.n_indices64;
 
   // ---- small D2H: dictionary orders, constant-column run keys, function order
@@ -900,8 +931,10 @@ static int collect(pa_agg* a, pa_agg_result* res) {
     return rc;
   for (uint32_t i = 0; i < nlab; i++)
     if (c.last_nonnull_plus1[i] && (rc = d2h_vec(a, ord_lab[i], a->cols[i].order, c.n_dict[i]))) return rc;
-  for (uint32_t t = 0; t < 8; t++)
+  for (uint32_t t = v1 ? 6 : 0; t < 8; t++)  // v1: the six string columns stay on the device as dictionary indices
     if ((rc = d2h_vec(a, kind_keys[t], a->cols[nlab + t].run_keys, c.n_runs[nlab + t]))) return rc;
+  std::vector<uint32_t> kind_order, n_kind_dict;
+  if (v1 && ((rc = d2h_vec(a, kind_order, a->v1_kind_order, 64)) || (rc = d2h_vec(a, n_kind_dict, a->v1_n_kind_dict, 8)))) return rc;
   CK(cudaStreamSynchronize(a->s_comp));
 
   std::lock_guard<std::mutex> g(a->reg_mu);
@@ -968,10 +1001,10 @@ static int collect(pa_agg* a, pa_agg_result* res) {
       touched.emplace(cp.name, std::move(hc));
       continue;
     }
-    Node dictv = utf8_node(a, "values", true, strs);
+    Node dictv = utf8_node(a, "values", true, strs, nullptr, lab_ty);
     uint32_t nr = c.n_runs[i];
     Node values = dict_node("values", true, nr, c.n_null[i], BufRef::dev(cp.validity, (nr + 7) / 8), BufRef::dev(cp.run_keys, (uint64_t)nr * 4), std::move(dictv));
-    labels.push_back(LabelOut{cp.name, ree_node(cp.name, true, (int64_t)N, nr, BufRef::dev(cp.run_ends, (uint64_t)nr * 4), std::move(values))});
+    labels.push_back(LabelOut{cp.name, ree_node(lab_prefix + cp.name, true, (int64_t)N, nr, BufRef::dev(cp.run_ends, (uint64_t)nr * 4), std::move(values))});
   }
   for (auto& e : ext) {  // LabelAll (arrow_v2.go:555-564), in flag order
     HostCol& hc = touched[e.first];
@@ -988,18 +1021,56 @@ static int collect(pa_agg* a, pa_agg_result* res) {
     HostCol& hc = kv.second;
     std::vector<std::pair<const uint8_t*, uint32_t>> strs;
     for (auto& s : hc.dict) strs.emplace_back((const uint8_t*)s.data(), (uint32_t)s.size());
-    Node dictv = utf8_node(a, "values", true, strs);
+    Node dictv = utf8_node(a, "values", true, strs, nullptr, lab_ty);
     int64_t nulls = 0;
     std::vector<uint8_t> bits((hc.valid.size() + 7) / 8, 0);
     for (size_t k = 0; k < hc.valid.size(); k++) { if (hc.valid[k]) bits[k >> 3] |= (uint8_t)(1u << (k & 7)); else nulls++; }
     BufRef vref = BufRef::none();
     if (nulls) { auto& kb = keep(a, std::move(bits)); vref = BufRef::host(kb.data(), kb.size()); }
     Node values = dict_node("values", true, (int64_t)hc.idx.size(), nulls, vref, host_ref(a, hc.idx), std::move(dictv));
-    labels.push_back(LabelOut{kv.first, ree_node(kv.first, true, (int64_t)N, (int64_t)hc.run_ends.size(), host_ref(a, hc.run_ends), std::move(values))});
+    labels.push_back(LabelOut{kv.first, ree_node(lab_prefix + kv.first, true, (int64_t)N, (int64_t)hc.run_ends.size(), host_ref(a, hc.run_ends), std::move(values))});
   }
   std::sort(labels.begin(), labels.end(), [](const LabelOut& x, const LabelOut& y) { return x.name < y.name; });
 
   std::vector<Node> cols;
+  auto ree_run_ends_of = [&](uint32_t col) { return BufRef::dev(a->cols[col].run_ends, (uint64_t)c.n_runs[col] * 4); };
+  if (v1) {
+    // ---- v1 sample record (reporter/arrow.go:274-316, ArrowSamplesField :484-503): label columns first, then the 11 fixed columns
+    for (auto& l : labels) cols.push_back(std::move(l.node));
+    const uint32_t c_ord = nlab + 8, c_ts = nlab + 9, nu = c.n_unique;
+    {
+      Node ids; ids.ty = Ty::Binary; ids.name = "values"; ids.nullable = true; ids.length = nu;
+      ids.bufs = {BufRef::dev(a->v1_id_off, ((uint64_t)nu + 1) * 4), BufRef::dev(a->v1_ids, (uint64_t)nu * 16)};
+      uint32_t nr = c.n_runs[c_ord];  // run key == stack ordinal == dictionary index
+      cols.push_back(ree_node("stacktrace_id", false, (int64_t)N, nr, ree_run_ends_of(c_ord),
+                              dict_node("values", true, nr, 0, BufRef::none(), BufRef::dev(a->cols[c_ord].run_keys, (uint64_t)nr * 4), std::move(ids))));
+    }
+    cols.push_back(int_node("value", 64, true, false, (int64_t)N, BufRef::dev(a->d_value.p, N * 8)));
+    static const char* names[6] = {"producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality"};
+    for (uint32_t t = 0; t < 6; t++) {
+      std::vector<std::pair<const uint8_t*, uint32_t>> strs;
+      for (uint32_t k = 0; k < n_kind_dict[t]; k++) {
+        const std::string& sv = a->kind_strings[t][kind_order[t * 8 + k]];
+        strs.emplace_back((const uint8_t*)sv.data(), (uint32_t)sv.size());
+      }
+      const ColPlan& cp = a->cols[nlab + t];
+      uint32_t nr = c.n_runs[nlab + t];
+      int64_t nulls = t == 5 ? (int64_t)c.n_null[nlab + t] : 0;  // memory samples carry a null temporality
+      cols.push_back(ree_node(names[t], false, (int64_t)N, nr, ree_run_ends_of(nlab + t),
+                              dict_node("values", true, nr, nulls, nulls ? BufRef::dev(cp.validity, (nr + 7) / 8) : BufRef::none(),
+                                        BufRef::dev(cp.run_keys, (uint64_t)nr * 4), utf8_node(a, "values", true, strs, nullptr, Ty::Binary))));
+    }
+    {
+      std::vector<int64_t> pv; for (uint32_t k : kind_keys[6]) pv.push_back(a->period_vals[k]);
+      std::vector<int64_t> dv; for (uint32_t k : kind_keys[7]) dv.push_back((int64_t)a->duration_vals[k]);
+      cols.push_back(ree_node("period", false, (int64_t)N, (int64_t)pv.size(), ree_run_ends_of(nlab + 6), int_node("values", 64, true, true, (int64_t)pv.size(), host_ref(a, pv))));
+      cols.push_back(ree_node("duration", false, (int64_t)N, (int64_t)dv.size(), ree_run_ends_of(nlab + 7), int_node("values", 64, true, true, (int64_t)dv.size(), host_ref(a, dv))));
+    }
+    {
+      uint32_t nr = c.n_runs[c_ts];
+      cols.push_back(ree_node("timestamp", false, (int64_t)N, nr, ree_run_ends_of(c_ts), int_node("values", 64, true, true, nr, BufRef::dev(a->v1_ts_vals, (uint64_t)nr * 8))));
+    }
+  } else {
   {
     Node ln; ln.ty = Ty::Struct; ln.name = "labels"; ln.nullable = false; ln.length = (int64_t)N;
     for (auto& l : labels) ln.kids.push_back(std::move(l.node));
@@ -1104,9 +1175,11 @@ static int collect(pa_agg* a, pa_agg_result* res) {
     cols.push_back(std::move(ts));
   }
 
+  }
+
   // ---- plan the stream and fill it
   StreamPlan plan;
-  plan.build(cols, {{"parca_write_schema_version", "v2"}}, (int64_t)N);
+  plan.build(cols, {{"parca_write_schema_version", v1 ? "v1" : "v2"}}, (int64_t)N);
   if (plan.total > a->out_cap) {
     if (a->out) cudaFreeHost(a->out);
     a->out = nullptr;

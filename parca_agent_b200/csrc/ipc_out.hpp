@@ -33,7 +33,7 @@ struct BufRef {
   static BufRef zeros(uint64_t n) { return BufRef{ZEROS, nullptr, n}; }
 };
 
-enum class Ty : uint8_t { Int, Utf8, Utf8View, FixedBinary, TimestampNsUtc, Struct, ListView, RunEnd, DictU32 };
+enum class Ty : uint8_t { Int, Utf8, Utf8View, FixedBinary, TimestampNsUtc, Struct, ListView, RunEnd, DictU32, Binary };
 
 // One node = one Arrow field + its array. For Ty::DictU32 the node itself carries the uint32
 // indices and `dict` is the dictionary *value* node (whose type becomes the field's type).
@@ -220,6 +220,7 @@ class StreamPlan {
     switch (n.ty) {
       case Ty::Int: b.begin(2); b.field<int32_t>(0, n.bits, 0); b.field<uint8_t>(1, n.is_signed ? 1 : 0, 0); *tab = b.end(); *tag = 2; break;
       case Ty::Utf8: b.begin(0); *tab = b.end(); *tag = 5; break;
+      case Ty::Binary: b.begin(0); *tab = b.end(); *tag = 4; break;
       case Ty::Utf8View: b.begin(0); *tab = b.end(); *tag = 24; break;
       case Ty::FixedBinary: b.begin(1); b.field<int32_t>(0, n.byte_width, 0); *tab = b.end(); *tag = 15; break;
       case Ty::TimestampNsUtc: { uint32_t tz = b.str("UTC"); b.begin(2); b.field<int16_t>(0, 3, 0); b.ref(1, tz); *tab = b.end(); *tag = 10; break; }

@@ -199,6 +199,7 @@ struct HeaderArgs {
   unsigned long long* tid_slots;
   uint32_t tid_mask;
   uint32_t* first_comm;
+  uint32_t* first_kind;          // [8] first row of each sample kind (v1: the kind-derived columns are dictionary encoded)
 };
 
 __global__ void __launch_bounds__(kThreads) k_header(HeaderArgs a) {
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(kThreads) k_header(HeaderArgs a) {
       if (a.first_cpu && a.first_cpu[cpu] > r) atomicMin(&a.first_cpu[cpu], r);
       if (a.tid_slots && hashed_min_insert(a.tid_slots, a.tid_mask, tid, r) == kNull) atomicOr(&a.ctr->err, ERR_TABLE_FULL);
       if (a.first_comm && comm_cid != 0 && a.first_comm[comm_cid] > r) atomicMin(&a.first_comm[comm_cid], r);
+      if (a.first_kind && a.first_kind[knd] > r) atomicMin(&a.first_kind[knd], r);
       if (a.provided) {  // trace.Hash.Bytes(): big-endian hi||lo
         ulonglong2 id = make_ulonglong2(bswap64(k.hi), bswap64(k.lo));
         *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = id;
@@ -727,22 +729,61 @@ struct UniqOffsetF {  // startOffset := indices.Len() at each first occurrence (
 };
 
 // (2) per-row ListView offset/size: hit => reuse the first occurrence's (offset,size) (arrow_v2.go:293-299)
+// v2: the ListView (offset, size) of each row; v1 (ord_out != nullptr): the row's stack ordinal, which is
+// both the run key and the dictionary index of the stacktrace_id column.
 __global__ void __launch_bounds__(kThreads) k_rows_materialize(uint32_t n_rows, const uint32_t* slot_of_row, const StackSlot* tab,
-                                                               int* st_offsets, int* st_sizes) {
+                                                               int* st_offsets, int* st_sizes, uint32_t* ord_out) {
   const uint32_t stride = gridDim.x * kThreads * 4;
   for (uint32_t base = blockIdx.x * kThreads * 4; base < n_rows; base += stride) {
     uint32_t sl[4];
     uint2 os[4];
+    uint32_t od[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) { uint32_t r = base + u * kThreads + threadIdx.x; sl[u] = r < n_rows ? slot_of_row[r] : kNull; }
 #pragma unroll
-    for (int u = 0; u < 4; u++) os[u] = sl[u] != kNull ? *reinterpret_cast<const uint2*>(&tab[sl[u]].offset) : make_uint2(0u, 0u);
+    for (int u = 0; u < 4; u++) {
+      if (ord_out) od[u] = sl[u] != kNull ? tab[sl[u]].ordinal : 0u;
+      else os[u] = sl[u] != kNull ? *reinterpret_cast<const uint2*>(&tab[sl[u]].offset) : make_uint2(0u, 0u);
+    }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       uint32_t r = base + u * kThreads + threadIdx.x;
-      if (r < n_rows) { st_offsets[r] = (int)os[u].x; st_sizes[r] = (int)os[u].y; }
+      if (r >= n_rows) continue;
+      if (ord_out) ord_out[r] = od[u];
+      else { st_offsets[r] = (int)os[u].x; st_sizes[r] = (int)os[u].y; }
     }
   }
+}
+// v1: dictionary values of the stacktrace_id column = the 16-byte ids of the unique stacks in ordinal order
+__global__ void __launch_bounds__(kThreads) k_gather_ids(const Counters* ctr, const uint32_t* uniq_row, const uint8_t* uuid, uint8_t* out, int* offsets) {
+  uint32_t nu = ctr->n_unique;
+  for (uint32_t u = blockIdx.x * kThreads + threadIdx.x; u <= nu; u += gridDim.x * kThreads) {
+    offsets[u] = (int)(16u * u);
+    if (u < nu) *reinterpret_cast<ulonglong2*>(out + 16ull * u) = *reinterpret_cast<const ulonglong2*>(uuid + 16ull * uniq_row[u]);
+  }
+}
+// v1: dictionary order of the kind-derived string columns. A class enters a column's dictionary at the first
+// row whose kind maps to it; with at most 7 kinds this is a one-warp job.
+__global__ void k_kind_ranks(const uint32_t* first_kind, const uint32_t* kindtab, uint32_t* kindrank, uint32_t* kind_order, uint32_t* n_kind_dict) {
+  int t = threadIdx.x;  // one thread per kind-derived column (6 string columns)
+  if (t >= 6) return;
+  uint32_t first_class[8];
+  for (int c = 0; c < 8; c++) first_class[c] = kNull;
+  for (int k = 0; k < 7; k++) {
+    uint32_t c = kindtab[t * 8 + k];
+    if (c != kNull && first_kind[k] < first_class[c]) first_class[c] = first_kind[k];
+  }
+  uint32_t n = 0;
+  for (int c = 0; c < 8; c++) {
+    kindrank[t * 8 + c] = kNull;
+    if (first_class[c] == kNull) continue;
+    uint32_t r = 0;
+    for (int o = 0; o < 8; o++) r += (first_class[o] < first_class[c]) ? 1u : 0u;
+    kindrank[t * 8 + c] = r;
+    kind_order[t * 8 + r] = (uint32_t)c;
+    n++;
+  }
+  n_kind_dict[t] = n;
 }
 
 // On-demand side table: occurrences per unique stack, in first-occurrence order (the reference emits one
@@ -979,7 +1020,7 @@ __global__ void __launch_bounds__(kThreads) k_ls_first(LsFirstArgs a) {
 // Rows are partitioned into one contiguous range per WARP, so neither pass needs a block barrier:
 // the previous row's inputs come from the neighbouring lane (shuffle) or are carried across steps.
 // Column order is fixed by the host: [labelset-derived LS columns][cpu][thread_id][thread_name][8 kind columns].
-enum : uint32_t { COL_LS = 0, COL_CPU = 1, COL_TID = 2, COL_COMM = 3, COL_KIND = 4 };
+enum : uint32_t { COL_LS = 0, COL_CPU = 1, COL_TID = 2, COL_COMM = 3, COL_KIND = 4, COL_ORD = 5, COL_TS = 6 };
 struct ReeCol {
   uint32_t type, param;
   int* run_ends;       // Arrow: run_ends child
@@ -1002,20 +1043,29 @@ struct ReeArgs {
   const uint32_t* kindtab;                    // [8][8] -> class id or kNull
   uint32_t* partial;                          // [ncols][total warps]
   Counters* ctr;
+  // v1 schema only (nullptr / -1 otherwise)
+  const uint32_t* ord;       // stack ordinal per row -> stacktrace_id column (run key == dictionary index)
+  const long long* ts;       // timestamp per row -> run-end encoded int64 column
+  long long* ts_vals;        // value of every timestamp run
+  int c_ord, c_ts;
+  const uint32_t* kindrank;  // [6][8] class -> dictionary index of the kind-derived string columns
+  uint32_t kind_dict_mask;   // bit t: kind column t is dictionary encoded
 };
-struct RowIn { uint32_t ls, cpu, tid, comm, kind; };
+struct RowIn { uint32_t ls, cpu, tid, comm, kind, ord; long long ts; };
 __device__ __forceinline__ RowIn ree_load(const ReeArgs& a, uint32_t r) {
-  return RowIn{a.ls[r], a.cpu[r], a.tid[r], a.comm[r], (uint32_t)a.kind[r]};
+  return RowIn{a.ls[r], a.cpu[r], a.tid[r], a.comm[r], (uint32_t)a.kind[r], a.ord ? a.ord[r] : 0u, a.ts ? a.ts[r] : 0ll};
 }
 __device__ __forceinline__ RowIn ree_shfl(const RowIn& x, int srclane) {
   const unsigned full = 0xFFFFFFFFu;
   return RowIn{__shfl_sync(full, x.ls, srclane), __shfl_sync(full, x.cpu, srclane), __shfl_sync(full, x.tid, srclane),
-               __shfl_sync(full, x.comm, srclane), __shfl_sync(full, x.kind, srclane)};
+               __shfl_sync(full, x.comm, srclane), __shfl_sync(full, x.kind, srclane), __shfl_sync(full, x.ord, srclane),
+               __shfl_sync(full, x.ts, srclane)};
 }
 __device__ __forceinline__ RowIn ree_shfl_up1(const RowIn& x) {
   const unsigned full = 0xFFFFFFFFu;
   return RowIn{__shfl_up_sync(full, x.ls, 1), __shfl_up_sync(full, x.cpu, 1), __shfl_up_sync(full, x.tid, 1),
-               __shfl_up_sync(full, x.comm, 1), __shfl_up_sync(full, x.kind, 1)};
+               __shfl_up_sync(full, x.comm, 1), __shfl_up_sync(full, x.kind, 1), __shfl_up_sync(full, x.ord, 1),
+               __shfl_up_sync(full, x.ts, 1)};
 }
 __device__ __forceinline__ void warp_range(uint32_t n, uint32_t* begin, uint32_t* end, uint32_t* wg) {
   uint32_t nw = gridDim.x * kWarps;
@@ -1038,17 +1088,18 @@ __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   __shared__ ReeCol s_cols[kMaxCols];  // column descriptors: no dependent global loads on the write path
-  if (threadIdx.x < 64) s_kind[threadIdx.x] = a.kindtab[threadIdx.x];
+  __shared__ uint32_t s_krank[64];
+  if (threadIdx.x < 64) { s_kind[threadIdx.x] = a.kindtab[threadIdx.x]; s_krank[threadIdx.x] = (EMIT && a.kindrank && threadIdx.x < 48) ? a.kindrank[threadIdx.x] : 0u; }
   for (uint32_t c = threadIdx.x; c < a.ncols; c += kThreads) s_cols[c] = a.cols[c];
   uint32_t begin, end, wg;
   warp_range(a.n_rows, &begin, &end, &wg);
   const uint32_t nwarps = gridDim.x * kWarps;
   for (uint32_t c = lane; c < a.ncols; c += 32) { s_acc[c][w] = EMIT ? a.partial[c * nwarps + wg] : 0u; s_last[c][w] = 0u; s_null[c][w] = 0u; }
   __syncthreads();
-  RowIn carry{0, 0, 0, 0, 0};
+  RowIn carry{0, 0, 0, 0, 0, 0, 0};
   if (begin < end && begin > 0) carry = ree_load(a, begin - 1);  // every lane loads the same row (broadcast)
   const unsigned lt = (1u << lane) - 1u;
-  RowIn nx = (begin + lane < end) ? ree_load(a, begin + lane) : RowIn{0, 0, 0, 0, 0};
+  RowIn nx = (begin + lane < end) ? ree_load(a, begin + lane) : RowIn{0, 0, 0, 0, 0, 0, 0};
   for (uint32_t base = begin; base < end; base += 32) {
     const uint32_t r = base + lane;
     const bool in = r < end;
@@ -1076,11 +1127,12 @@ __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
         uint32_t k = pos0 + (uint32_t)__popc(m & lt);
         if (boundary) {
           if (k > 0) col.run_ends[k - 1] = (int)r;  // run k starts at r => run k-1 ends at r
-          uint32_t stored = key;                    // constant-ish columns keep the class id
+          uint32_t stored = key;                    // constant-ish / ordinal columns: the caller already passes the final key
           if (has_dict) stored = null ? 0u : col.rank[col.hslots ? fo_hfind(col.hslots, col.hmask, key) : key];
           col.run_keys[k] = stored;
+          if ((int)c == a.c_ts) a.ts_vals[k] = x.ts;
         }
-        if (has_dict && col.nullable) {  // validity bits of runs pos0 .. pos0+cnt-1 span at most two words
+        if (col.validity && col.nullable) {  // validity bits of runs pos0 .. pos0+cnt-1 span at most two words
           uint32_t w0 = pos0 >> 5;
           bool v = boundary && !null;
           unsigned m0 = __reduce_or_sync(full, (v && (k >> 5) == w0) ? (1u << (k & 31)) : 0u);
@@ -1116,12 +1168,16 @@ __global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
       for (uint32_t t = 0; t < 8; t++) {
         uint32_t v = s_kind[t * 8 + x.kind], pv = s_kind[t * 8 + p.kind];
         bool null = v == kNull;
-        column(a.c_kind + t, first_row || null || pv == kNull || pv != v, null, v, false);
+        bool b = first_row || null || pv == kNull || pv != v;
+        if (EMIT && (a.kind_dict_mask >> t) & 1u) v = null ? 0u : s_krank[t * 8 + v];  // v1: dictionary index of the class
+        column(a.c_kind + t, b, null, v, false);
       }
     } else if (!EMIT) {
       unsigned nn = __ballot_sync(full, in);
       if (lane == 0 && nn) for (uint32_t t = 0; t < 8; t++) s_last[a.c_kind + t][w] = base + (32 - __clz(nn));
     }
+    if (a.c_ord >= 0) column((uint32_t)a.c_ord, first_row || x.ord != p.ord, false, x.ord, false);  // bytes.Equal on the 16-byte id
+    if (a.c_ts >= 0) column((uint32_t)a.c_ts, first_row || x.ts != p.ts, false, 0u, false);        // Int64RunEndBuilder.Append
     carry = ree_shfl(x, 31);
   }
   if (!EMIT) {
