@@ -42,6 +42,7 @@ def parse():
                          "reports sustained end-to-end samples/s")
     ap.add_argument("--hash-mode", default="xxh64x2", choices=["xxh64x2", "provided"],
                     help="xxh64x2 = GPU hashes every stack (headline); provided = trace.Hash arrives with the sample, as in the reference")
+    ap.add_argument("--schema", default="v2", choices=["v2", "v1"], help="sample record schema (v1 = the reference's default, stacktrace ids only)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="BASELINE.json config: 2 = headline (default), 3 = Zipf/CUDA-origin/50k labelsets")
     return ap.parse_args()
 
@@ -90,11 +91,13 @@ def shard_workload(args, rank, world):
     from parca_agent_b200 import abi, synth
     mode = abi.PA_HASH_PROVIDED if args.hash_mode == "provided" else abi.PA_HASH_XXH64X2
     if args.config == 3:
-        return synth.config3(n=args.samples, hash_mode=mode)
-    if world == 1:
-        return synth.config2(n=args.samples, hash_mode=mode)
-    # weak scaling: every rank owns the pids with xxh64(pid) % world == rank and aggregates `samples` rows of them
-    return synth.config2_shard(rank, world, n=args.samples, hash_mode=mode)
+        w = synth.config3(n=args.samples, hash_mode=mode)
+    elif world == 1:
+        w = synth.config2(n=args.samples, hash_mode=mode)
+    else:  # weak scaling: every rank owns the pids with xxh64(pid) % world == rank and aggregates `samples` rows of them
+        w = synth.config2_shard(rank, world, n=args.samples, hash_mode=mode)
+    w.schema = abi.PA_SCHEMA_V1 if args.schema == "v1" else abi.PA_SCHEMA_V2
+    return w
 
 
 def time_cpu_port(w, n_rows):
@@ -294,7 +297,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "config%d: %d samples x %d frames per GPU, %d unique stacks, %d distinct frames, pid-sharded across %d GPU(s)"
                                    % (args.config, w.n, F, w.meta["U"], w.meta["P"], world),
-                       "hash_mode": args.hash_mode, "l2": "inputs (%.2f GB/GPU) far exceed the 126 MB L2; no explicit flush" % ((w.n * 64 + w.n_frame_ids * 8) / 1e9),
+                       "hash_mode": args.hash_mode, "schema": args.schema, "l2": "inputs (%.2f GB/GPU) far exceed the 126 MB L2; no explicit flush" % ((w.n * 64 + w.n_frame_ids * 8) / 1e9),
                        "timing": "CUDA events on the library's compute stream, max over ranks", "wall_s_for_steps": wall_max},
             "gpu_launches": int(launches),
             "kernel_groups_ms": {g: float(np.mean([x[0] for x in v])) for g, v in groups.items()},
