@@ -768,7 +768,11 @@ __global__ void k_kind_ranks(const uint32_t* first_kind, const uint32_t* kindtab
   int t = threadIdx.x;  // one thread per kind-derived column (6 string columns)
   if (t >= 6) return;
   uint32_t first_class[8];
-  for (int c = 0; c < 8; c++) first_class[c] = kNull;
+  for (int c = 0; c < 8; c++) { first_class[c] = kNull; kind_order[t * 8 + c] = kNull; }
+  if (t < 2) {  // rows 6,7 (period, duration) are not dictionary encoded: keep them defined
+    for (int c = 0; c < 8; c++) { kindrank[(6 + t) * 8 + c] = kNull; kind_order[(6 + t) * 8 + c] = kNull; }
+    n_kind_dict[6 + t] = 0;
+  }
   for (int k = 0; k < 7; k++) {
     uint32_t c = kindtab[t * 8 + k];
     if (c != kNull && first_kind[k] < first_class[c]) first_class[c] = first_kind[k];
