@@ -323,3 +323,73 @@ def test_v1_scaled_and_repeated(oracle, gpu):
         gpu.load(a, w)
         assert a.flush().ipc_bytes() == want
     a.close()
+
+
+def wide_label_workload(n_names, n=1500, seed=5):
+    """Many distinct label names (sorted byte-wise incl. non-ASCII), sparse presence, deep stacks with repeated frames."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base = synth.edge_workload(seed=seed, n=n, hash_mode=abi.PA_HASH_XXH64X2, external=False)
+    st = synth.StringTable()
+    st.strings, st.index = list(base.strings), {s: i for i, s in enumerate(base.strings)}
+    names = ["lbl_%02d" % i for i in range(n_names - 3)] + ["zzé中", "Aardvark", "a"]
+    name_sids = [st.sid(x) for x in names]
+    vals = [st.sid("v%d" % i) for i in range(17)] + [st.sid("x" * 70)]
+    labelsets = []
+    for _ in range(24):
+        chosen = sorted(rng.choice(len(names), size=int(rng.integers(0, len(names) + 1)), replace=False), key=lambda i: st.strings[name_sids[i]])
+        labelsets.append([(name_sids[i], vals[int(rng.integers(0, len(vals)))]) for i in chosen])
+    hd = base.hdrs.copy()
+    hd["labelset_id"] = rng.integers(0, len(labelsets), n)
+    # deep stacks (up to 200 frames, repeated frame ids inside one stack)
+    P = len(base.frames)
+    stream, off = [], 0
+    for i in range(n):
+        k = int(rng.choice([0, 1, 3, 64, 65, 129, 200]))
+        fr = rng.integers(0, min(P, 7), k).astype(np.uint64)
+        hd["nframes"][i], hd["frame_off"][i] = k, off
+        stream.append(fr)
+        off += k
+    w = synth.Workload("wide_labels_%d" % n_names, st.strings, base.frames, labelsets, hd, _frame_ids=np.concatenate(stream),
+                       hash_mode=abi.PA_HASH_XXH64X2, samples_per_second=97)
+    return w
+
+
+@pytest.mark.parametrize("n_names", [5, 35])
+def test_many_label_columns_and_deep_stacks(oracle, gpu, n_names):
+    w = wide_label_workload(n_names)
+    assert_same(oracle, gpu, w)
+    w.schema = abi.PA_SCHEMA_V1
+    assert_same(oracle, gpu, w)
+
+
+def test_too_many_label_names_is_an_error(gpu):
+    w = wide_label_workload(45, n=50)
+    a = gpu.from_workload(w)
+    gpu.load(a, w)
+    with pytest.raises(gpu.PaError) as e:
+        a.flush()
+    assert e.value.code == -34  # PA_ERANGE
+    a.close()
+
+
+def test_ring_full_and_invalid_inputs(gpu):
+    w = synth.edge_workload(seed=2, n=100)
+    a = gpu.from_workload(w, max_samples=100)
+    gpu.load(a, w)
+    with pytest.raises(gpu.PaError) as e:
+        a.acquire(1, 0)
+    assert e.value.code == -28  # PA_ENOSPC: the caller must flush
+    assert a.flush().n_rows == 100
+    bad = synth.edge_workload(seed=2, n=100)
+    bad.hdrs["cpu"][5] = 70000
+    gpu.load(a, bad)
+    with pytest.raises(gpu.PaError):
+        a.flush()
+    bad = synth.edge_workload(seed=2, n=100)
+    bad.hdrs["kind"][7] = 9
+    gpu.load(a, bad)
+    with pytest.raises(gpu.PaError):
+        a.flush()
+    gpu.load(a, w)  # the aggregator stays usable after rejected batches
+    assert a.flush().n_rows == 100
+    a.close()
