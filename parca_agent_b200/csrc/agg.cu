@@ -780,13 +780,20 @@ static int process_once(pa_agg* a) {
     a->tm[T_LABELS].launches++;
   }
   if (v1) { k_kind_ranks<<<1, 32, 0, s>>>(a->v1_first_kind, a->d_kindtab.as<uint32_t>(), a->v1_kindrank, a->v1_kind_order, a->v1_n_kind_dict); a->tm[T_LABELS].launches++; }
-  k_ree_pass<false><<<Gr, kThreads, 0, s>>>(ra);  // run counts
-  k_ree_scan_partials<<<ncols, 32, 0, s>>>(ra, Gr * kWarps);
+  ReeGroups rg{};  // one launch row per column (the 8 kind-derived columns form one group)
+  for (uint32_t c = 0; c < ncols; c++) {
+    const ColPlan& cp = a->cols[c];
+    if (cp.type == COL_KIND && cp.param != 0) continue;
+    rg.g[rg.n++] = ReeGroup{cp.type, c, cp.param};
+  }
+  const dim3 ree_grid(Gr, rg.n);
+  k_ree_col<false><<<ree_grid, kThreads, 0, s>>>(ra, rg);  // run counts
+  k_ree_scan_partials<<<ncols, kThreads, 0, s>>>(ra, Gr * kWarps);
   a->tm[T_LABELS].launches += 2;
   CK(cudaEventRecord(a->tm[T_DICTS].a, s));
   if (nlab) run_jobs(j_lab0, (int)nlab, false, a->tm[T_DICTS], N, std::max<uint64_t>(std::max<uint64_t>(S, 65536), tcap), false);  // label dictionary ranks
   CK(cudaEventRecord(a->tm[T_DICTS].b, s));
-  k_ree_pass<true><<<Gr, kThreads, 0, s>>>(ra);   // run ends + final dictionary indices + validity bits
+  k_ree_col<true><<<ree_grid, kThreads, 0, s>>>(ra, rg);   // run ends + final dictionary indices + validity bits
   a->tm[T_LABELS].launches += 1;
   CK(cudaEventRecord(a->tm[T_LABELS].b, s));
 

@@ -865,7 +865,7 @@ __device__ __forceinline__ void fo_min_dev(const FoJob& j) {
   for (uint32_t i = gtid(); i < n; i += gstride()) {
     uint32_t key = j.keys[i];
     if (j.nullable && key == kNull) continue;
-    if (j.first[key] > i) atomicMin(&j.first[key], i);  // hashed jobs record first positions in their producer (k_ree_pass)
+    if (j.first[key] > i) atomicMin(&j.first[key], i);  // hashed jobs (thread ids) record first rows in k_header
   }
 }
 __device__ __forceinline__ void fo_zero_dev(const FoJob& j) {  // clear only the bitmap words this batch will use
@@ -1055,22 +1055,6 @@ struct ReeArgs {
   const uint32_t* kindrank;  // [6][8] class -> dictionary index of the kind-derived string columns
   uint32_t kind_dict_mask;   // bit t: kind column t is dictionary encoded
 };
-struct RowIn { uint32_t ls, cpu, tid, comm, kind, ord; long long ts; };
-__device__ __forceinline__ RowIn ree_load(const ReeArgs& a, uint32_t r) {
-  return RowIn{a.ls[r], a.cpu[r], a.tid[r], a.comm[r], (uint32_t)a.kind[r], a.ord ? a.ord[r] : 0u, a.ts ? a.ts[r] : 0ll};
-}
-__device__ __forceinline__ RowIn ree_shfl(const RowIn& x, int srclane) {
-  const unsigned full = 0xFFFFFFFFu;
-  return RowIn{__shfl_sync(full, x.ls, srclane), __shfl_sync(full, x.cpu, srclane), __shfl_sync(full, x.tid, srclane),
-               __shfl_sync(full, x.comm, srclane), __shfl_sync(full, x.kind, srclane), __shfl_sync(full, x.ord, srclane),
-               __shfl_sync(full, x.ts, srclane)};
-}
-__device__ __forceinline__ RowIn ree_shfl_up1(const RowIn& x) {
-  const unsigned full = 0xFFFFFFFFu;
-  return RowIn{__shfl_up_sync(full, x.ls, 1), __shfl_up_sync(full, x.cpu, 1), __shfl_up_sync(full, x.tid, 1),
-               __shfl_up_sync(full, x.comm, 1), __shfl_up_sync(full, x.kind, 1), __shfl_up_sync(full, x.ord, 1),
-               __shfl_up_sync(full, x.ts, 1)};
-}
 __device__ __forceinline__ void warp_range(uint32_t n, uint32_t* begin, uint32_t* end, uint32_t* wg) {
   uint32_t nw = gridDim.x * kWarps;
   uint32_t w = blockIdx.x * kWarps + (threadIdx.x >> 5);
@@ -1082,130 +1066,197 @@ __device__ __forceinline__ void warp_range(uint32_t n, uint32_t* begin, uint32_t
   *wg = w;
 }
 // EMIT = false: count boundaries per (column, warp) and track the last row carrying each label.
-// EMIT = true : write run ends / run keys at their final positions and record dictionary first positions.
-template <bool EMIT>
-__global__ void __launch_bounds__(kThreads) k_ree_pass(ReeArgs a) {
-  __shared__ uint32_t s_acc[kMaxCols][kWarps];   // count (pass 1) or running output position (pass 2)
-  __shared__ uint32_t s_last[kMaxCols][kWarps];
-  __shared__ uint32_t s_null[kMaxCols][kWarps];
-  __shared__ uint32_t s_kind[64];
+// EMIT = true : write run ends / final dictionary indices / validity bits at their final positions.
+// Column-parallel: blockIdx.y selects a column group, so a warp encodes ONE
+// column (or the 8 kind-derived columns, which share their skip test) over its row range with all of its
+// state in registers, and different columns progress concurrently on different warps instead of being
+// walked one after the other inside every row step.
+struct ReeGroup { uint32_t type, col, param; };
+struct ReeGroups { uint32_t n; ReeGroup g[kMaxCols]; };
+
+constexpr int kReeUnroll = 4;  // 32-row sub-steps per iteration: their key loads / rank lookups are in flight together
+
+template <bool EMIT, class KeyT, class K>
+__device__ __forceinline__ void ree_single(const ReeArgs& a, uint32_t c, bool has_dict, K kf) {
   const unsigned full = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  __shared__ ReeCol s_cols[kMaxCols];  // column descriptors: no dependent global loads on the write path
-  __shared__ uint32_t s_krank[64];
-  if (threadIdx.x < 64) { s_kind[threadIdx.x] = a.kindtab[threadIdx.x]; s_krank[threadIdx.x] = (EMIT && a.kindrank && threadIdx.x < 48) ? a.kindrank[threadIdx.x] : 0u; }
-  for (uint32_t c = threadIdx.x; c < a.ncols; c += kThreads) s_cols[c] = a.cols[c];
+  const int lane = threadIdx.x & 31;
   uint32_t begin, end, wg;
   warp_range(a.n_rows, &begin, &end, &wg);
   const uint32_t nwarps = gridDim.x * kWarps;
-  for (uint32_t c = lane; c < a.ncols; c += 32) { s_acc[c][w] = EMIT ? a.partial[c * nwarps + wg] : 0u; s_last[c][w] = 0u; s_null[c][w] = 0u; }
-  __syncthreads();
-  RowIn carry{0, 0, 0, 0, 0, 0, 0};
-  if (begin < end && begin > 0) carry = ree_load(a, begin - 1);  // every lane loads the same row (broadcast)
+  const ReeCol col = a.cols[c];
+  uint32_t acc = EMIT ? a.partial[c * nwarps + wg] : 0u, last = 0, nulls = 0;
+  KeyT ckey = 0; bool cnull = true;                 // previous row of lane 0
+  if (begin < end && begin > 0) kf.get(begin - 1, ckey, cnull);
   const unsigned lt = (1u << lane) - 1u;
-  RowIn nx = (begin + lane < end) ? ree_load(a, begin + lane) : RowIn{0, 0, 0, 0, 0, 0, 0};
+  for (uint32_t base = begin; base < end; base += 32 * kReeUnroll) {
+    KeyT key[kReeUnroll]; bool null[kReeUnroll], in[kReeUnroll], bnd[kReeUnroll];
+    unsigned m[kReeUnroll];
+#pragma unroll
+    for (int u = 0; u < kReeUnroll; u++) {
+      const uint32_t r = base + u * 32 + lane;
+      in[u] = r < end; key[u] = 0; null[u] = true;
+      if (in[u]) kf.get(r, key[u], null[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kReeUnroll; u++) {
+      const uint32_t r = base + u * 32 + lane;
+      KeyT pk = __shfl_up_sync(full, key[u], 1); int pn = __shfl_up_sync(full, (int)null[u], 1);
+      if (lane == 0) { pk = ckey; pn = cnull; }
+      bnd[u] = in[u] && (r == 0 || null[u] || pn || pk != key[u]);
+      m[u] = __ballot_sync(full, bnd[u]);
+      ckey = __shfl_sync(full, key[u], 31); cnull = __shfl_sync(full, (int)null[u], 31);
+    }
+    if (!EMIT) {
+#pragma unroll
+      for (int u = 0; u < kReeUnroll; u++) {
+        acc += (uint32_t)__popc(m[u]);
+        unsigned nn = __ballot_sync(full, in[u] && !null[u]);
+        if (nn) last = base + u * 32 + (32 - __clz(nn));
+        nulls += (uint32_t)__popc(__ballot_sync(full, bnd[u] && null[u]));
+      }
+    } else {
+      uint32_t k[kReeUnroll], stored[kReeUnroll];
+      uint32_t run = acc;
+#pragma unroll
+      for (int u = 0; u < kReeUnroll; u++) { k[u] = run + (uint32_t)__popc(m[u] & lt); run += (uint32_t)__popc(m[u]); }
+#pragma unroll
+      for (int u = 0; u < kReeUnroll; u++) {  // all dictionary lookups of the iteration are issued before any is consumed
+        stored[u] = (uint32_t)key[u];
+        if (has_dict && bnd[u]) stored[u] = null[u] ? 0u : col.rank[col.hslots ? fo_hfind(col.hslots, col.hmask, (uint32_t)key[u]) : (uint32_t)key[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < kReeUnroll; u++) {
+        if (bnd[u]) {
+          if (k[u] > 0) col.run_ends[k[u] - 1] = (int)(base + u * 32 + lane);  // run k starts here => run k-1 ends here
+          if (sizeof(KeyT) == 8) a.ts_vals[k[u]] = (long long)key[u]; else col.run_keys[k[u]] = stored[u];
+        }
+      }
+      if (col.validity && col.nullable) {  // validity bits of the runs emitted by one sub-step span at most two words
+        uint32_t pos = acc;
+#pragma unroll
+        for (int u = 0; u < kReeUnroll; u++) {
+          if (m[u]) {
+            const uint32_t w0 = pos >> 5;
+            const bool v = bnd[u] && !null[u];
+            unsigned m0 = __reduce_or_sync(full, (v && (k[u] >> 5) == w0) ? (1u << (k[u] & 31)) : 0u);
+            unsigned m1 = __reduce_or_sync(full, (v && (k[u] >> 5) != w0) ? (1u << (k[u] & 31)) : 0u);
+            if (lane == 0) { if (m0) atomicOr(&col.validity[w0], m0); if (m1) atomicOr(&col.validity[w0 + 1], m1); }
+          }
+          pos += (uint32_t)__popc(m[u]);
+        }
+      }
+      acc = run;
+    }
+  }
+  if (!EMIT && lane == 0) {
+    a.partial[c * nwarps + wg] = acc;
+    if (last) atomicMax(&a.ctr->last_nonnull_plus1[c], last);
+    if (nulls) atomicAdd(&a.ctr->n_null[c], nulls);
+  }
+}
+struct KeyLs { const uint32_t* ls; const uint32_t* lsmat; uint32_t stride, c;
+  __device__ __forceinline__ void get(uint32_t r, uint32_t& k, bool& n) const { k = __ldg(&lsmat[(size_t)ls[r] * stride + c]); n = k == kNull; } };
+struct KeyU32 { const uint32_t* v;
+  __device__ __forceinline__ void get(uint32_t r, uint32_t& k, bool& n) const { k = v[r]; n = false; } };
+struct KeyComm { const uint32_t* v;  // labels.Builder.Set(name, "") deletes the label: "" => null
+  __device__ __forceinline__ void get(uint32_t r, uint32_t& k, bool& n) const { k = v[r]; n = k == 0; } };
+struct KeyTs { const long long* v;
+  __device__ __forceinline__ void get(uint32_t r, long long& k, bool& n) const { k = v[r]; n = false; } };
+
+// the 8 kind-derived columns: one warp, eight running positions in registers, one skip test per step
+template <bool EMIT>
+__device__ __forceinline__ void ree_kinds(const ReeArgs& a, const uint32_t* s_kind, const uint32_t* s_krank) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  uint32_t begin, end, wg;
+  warp_range(a.n_rows, &begin, &end, &wg);
+  const uint32_t nwarps = gridDim.x * kWarps;
+  uint32_t acc[8], nulls[8];
+#pragma unroll
+  for (int t = 0; t < 8; t++) { acc[t] = EMIT ? a.partial[(a.c_kind + t) * nwarps + wg] : 0u; nulls[t] = 0; }
+  uint32_t ckind = 0;
+  if (begin < end && begin > 0) ckind = a.kind[begin - 1];
+  uint32_t nk = (begin + lane < end) ? a.kind[begin + lane] : 0u;
+  const unsigned lt = (1u << lane) - 1u;
   for (uint32_t base = begin; base < end; base += 32) {
     const uint32_t r = base + lane;
     const bool in = r < end;
-    RowIn x = nx;
-    if (r + 32 < end) nx = ree_load(a, r + 32);  // next step's inputs are in flight while this step is encoded
-    RowIn p = ree_shfl_up1(x);
-    if (lane == 0) p = carry;
+    const uint32_t kind = nk;
+    if (r + 32 < end) nk = a.kind[r + 32];
+    uint32_t pkind = __shfl_up_sync(full, kind, 1);
+    if (lane == 0) pkind = ckind;
     const bool first_row = r == 0;
-    // one column: ballot, rank inside the warp, write
-    auto column = [&](uint32_t c, bool boundary, bool null, uint32_t key, bool has_dict) {
-      boundary = boundary && in;
-      unsigned m = __ballot_sync(full, boundary);
-      if (!EMIT) {
-        unsigned nn = __ballot_sync(full, in && !null);
-        unsigned nb = __ballot_sync(full, boundary && null);
-        if (lane == 0) {
-          if (m) s_acc[c][w] += (uint32_t)__popc(m);
-          if (nn) s_last[c][w] = base + (32 - __clz(nn));
-          if (nb) s_null[c][w] += (uint32_t)__popc(nb);
-        }
-      } else {
-        if (m == 0) return;
-        const ReeCol& col = s_cols[c];
-        uint32_t pos0 = s_acc[c][w];
-        uint32_t k = pos0 + (uint32_t)__popc(m & lt);
-        if (boundary) {
-          if (k > 0) col.run_ends[k - 1] = (int)r;  // run k starts at r => run k-1 ends at r
-          uint32_t stored = key;                    // constant-ish / ordinal columns: the caller already passes the final key
-          if (has_dict) stored = null ? 0u : col.rank[col.hslots ? fo_hfind(col.hslots, col.hmask, key) : key];
-          col.run_keys[k] = stored;
-          if ((int)c == a.c_ts) a.ts_vals[k] = x.ts;
-        }
-        if (col.validity && col.nullable) {  // validity bits of runs pos0 .. pos0+cnt-1 span at most two words
-          uint32_t w0 = pos0 >> 5;
-          bool v = boundary && !null;
-          unsigned m0 = __reduce_or_sync(full, (v && (k >> 5) == w0) ? (1u << (k & 31)) : 0u);
-          unsigned m1 = __reduce_or_sync(full, (v && (k >> 5) != w0) ? (1u << (k & 31)) : 0u);
-          if (lane == 0) { if (m0) atomicOr(&col.validity[w0], m0); if (m1) atomicOr(&col.validity[w0 + 1], m1); }
-        }
-        __syncwarp(full);
-        if (lane == 0) s_acc[c][w] = pos0 + (uint32_t)__popc(m);
-        __syncwarp(full);
-      }
-    };
-    // ---- labelset-derived columns
-    const bool same_ls = !first_row && x.ls == p.ls;
-    for (uint32_t c = 0; c < a.n_ls; c++) {
-      uint32_t v = in ? __ldg(&a.lsmat[(size_t)x.ls * a.n_lscols + c]) : kNull;
-      bool null = v == kNull;
-      bool b = true;
-      if (!null && !first_row) {
-        uint32_t pv = same_ls ? v : __ldg(&a.lsmat[(size_t)p.ls * a.n_lscols + c]);
-        b = pv != v;  // also true when the previous row had no value (pv == kNull)
-      }
-      column(c, b, null, v, true);
-    }
-    if (a.c_cpu >= 0) column((uint32_t)a.c_cpu, first_row || x.cpu != p.cpu, false, x.cpu, true);
-    if (a.c_tid >= 0) column((uint32_t)a.c_tid, first_row || x.tid != p.tid, false, x.tid, true);
-    if (a.c_comm >= 0) {  // labels.Builder.Set(name, "") deletes the label: "" => null
-      bool null = x.comm == 0;
-      column((uint32_t)a.c_comm, first_row || null || p.comm == 0 || x.comm != p.comm, null, x.comm, true);
-    }
-    // ---- the 8 constant-ish columns depend on the sample kind only: skip them all when nothing changes
-    bool kchange = in && (first_row || x.kind != p.kind || x.kind >= 3u);  // kinds >= 3 carry a null temporality
+    const bool kchange = in && (first_row || kind != pkind || kind >= 3u);  // kinds >= 3 carry a null temporality
     if (__ballot_sync(full, kchange)) {
-      for (uint32_t t = 0; t < 8; t++) {
-        uint32_t v = s_kind[t * 8 + x.kind], pv = s_kind[t * 8 + p.kind];
-        bool null = v == kNull;
-        bool b = first_row || null || pv == kNull || pv != v;
-        if (EMIT && (a.kind_dict_mask >> t) & 1u) v = null ? 0u : s_krank[t * 8 + v];  // v1: dictionary index of the class
-        column(a.c_kind + t, b, null, v, false);
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        uint32_t v = s_kind[t * 8 + kind], pv = s_kind[t * 8 + pkind];
+        const bool null = v == kNull;
+        const bool boundary = in && (first_row || null || pv == kNull || pv != v);
+        const unsigned m = __ballot_sync(full, boundary);
+        if (!EMIT) {
+          acc[t] += (uint32_t)__popc(m);
+          nulls[t] += (uint32_t)__popc(__ballot_sync(full, boundary && null));
+        } else if (m) {
+          const ReeCol& col = a.cols[a.c_kind + t];
+          const uint32_t k = acc[t] + (uint32_t)__popc(m & lt);
+          if ((a.kind_dict_mask >> t) & 1u) v = null ? 0u : s_krank[t * 8 + v];  // v1: dictionary index of the class
+          if (boundary) {
+            if (k > 0) col.run_ends[k - 1] = (int)r;
+            col.run_keys[k] = v;
+          }
+          if (col.validity && col.nullable) {
+            const uint32_t w0 = acc[t] >> 5;
+            const bool ok = boundary && !null;
+            unsigned m0 = __reduce_or_sync(full, (ok && (k >> 5) == w0) ? (1u << (k & 31)) : 0u);
+            unsigned m1 = __reduce_or_sync(full, (ok && (k >> 5) != w0) ? (1u << (k & 31)) : 0u);
+            if (lane == 0) { if (m0) atomicOr(&col.validity[w0], m0); if (m1) atomicOr(&col.validity[w0 + 1], m1); }
+          }
+          acc[t] += (uint32_t)__popc(m);
+        }
       }
-    } else if (!EMIT) {
-      unsigned nn = __ballot_sync(full, in);
-      if (lane == 0 && nn) for (uint32_t t = 0; t < 8; t++) s_last[a.c_kind + t][w] = base + (32 - __clz(nn));
     }
-    if (a.c_ord >= 0) column((uint32_t)a.c_ord, first_row || x.ord != p.ord, false, x.ord, false);  // bytes.Equal on the 16-byte id
-    if (a.c_ts >= 0) column((uint32_t)a.c_ts, first_row || x.ts != p.ts, false, 0u, false);        // Int64RunEndBuilder.Append
-    carry = ree_shfl(x, 31);
+    ckind = __shfl_sync(full, kind, 31);
   }
-  if (!EMIT) {
-    __syncwarp(full);
-    for (uint32_t c = lane; c < a.ncols; c += 32) {
-      a.partial[c * nwarps + wg] = s_acc[c][w];
-      if (s_last[c][w]) atomicMax(&a.ctr->last_nonnull_plus1[c], s_last[c][w]);
-      if (s_null[c][w]) atomicAdd(&a.ctr->n_null[c], s_null[c][w]);
+  if (!EMIT && lane == 0) {
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      a.partial[(a.c_kind + t) * nwarps + wg] = acc[t];
+      if (nulls[t]) atomicAdd(&a.ctr->n_null[a.c_kind + t], nulls[t]);
     }
   }
 }
-__global__ void k_ree_scan_partials(ReeArgs a, int g) {  // grid = ncols, 32 threads
-  uint32_t* p = a.partial + (size_t)blockIdx.x * g;
-  int lane = threadIdx.x;
-  uint32_t run = 0;
-  for (int base = 0; base < g; base += 32) {
-    int i = base + lane;
-    uint32_t v = i < g ? p[i] : 0u, inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
-    if (i < g) p[i] = run + inc - v;
-    run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kThreads) k_ree_col(ReeArgs a, ReeGroups groups) {
+  __shared__ uint32_t s_kind[64], s_krank[64];
+  const ReeGroup g = groups.g[blockIdx.y];
+  if (g.type == COL_KIND) {
+    if (threadIdx.x < 64) { s_kind[threadIdx.x] = a.kindtab[threadIdx.x]; s_krank[threadIdx.x] = (EMIT && a.kindrank && threadIdx.x < 48) ? a.kindrank[threadIdx.x] : 0u; }
+    __syncthreads();
+    ree_kinds<EMIT>(a, s_kind, s_krank);
+    return;
   }
-  if (lane == 0) {
+  switch (g.type) {
+    case COL_LS: ree_single<EMIT, uint32_t>(a, g.col, true, KeyLs{a.ls, a.lsmat, a.n_lscols, g.param}); break;
+    case COL_CPU: ree_single<EMIT, uint32_t>(a, g.col, true, KeyU32{a.cpu}); break;
+    case COL_TID: ree_single<EMIT, uint32_t>(a, g.col, true, KeyU32{a.tid}); break;
+    case COL_COMM: ree_single<EMIT, uint32_t>(a, g.col, true, KeyComm{a.comm}); break;
+    case COL_ORD: ree_single<EMIT, uint32_t>(a, g.col, false, KeyU32{a.ord}); break;  // bytes.Equal on the 16-byte id
+    default: ree_single<EMIT, long long>(a, g.col, false, KeyTs{a.ts}); break;           // COL_TS: Int64RunEndBuilder.Append
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_ree_scan_partials(ReeArgs a, int g) {  // grid = ncols, kThreads threads
+  uint32_t* p = a.partial + (size_t)blockIdx.x * g;
+  uint32_t run = 0;
+  for (int base = 0; base < g; base += kThreads) {  // block-wide exclusive scan, kThreads partials per round
+    int i = base + threadIdx.x;
+    uint32_t v = i < g ? p[i] : 0u, tot;
+    uint32_t ex = block_exclusive_scan(v, &tot);
+    if (i < g) p[i] = run + ex;
+    run += tot;
+  }
+  if (threadIdx.x == 0) {
     a.ctr->n_runs[blockIdx.x] = run;
     if (run) a.cols[blockIdx.x].run_ends[run - 1] = (int)a.n_rows;  // the last run ends at the row count
   }
