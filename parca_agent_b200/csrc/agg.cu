@@ -484,9 +484,8 @@ static void launch_scan(pa_agg* a, F f, int njobs, Timer& t, int gx = 0) {
   dim3 grid(gx, njobs);
   typename F::T* partial = a->d_partial.as<typename F::T>();
   k_scan_reduce<F><<<grid, kThreads, 0, a->s_comp>>>(f, partial);
-  k_scan_partials<F><<<njobs, 32, 0, a->s_comp>>>(f, partial, gx);
   k_scan_emit<F><<<grid, kThreads, 0, a->s_comp>>>(f, partial);
-  t.launches += 3;
+  t.launches += 2;
 }
 // grid for a pass over at most `bound` elements: >= 2048 elements per CTA, never more than the full grid
 static int small_grid(const pa_agg* a, uint64_t bound) { return (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)a->G, (bound + 2047) / 2048)); }

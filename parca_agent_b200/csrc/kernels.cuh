@@ -611,7 +611,7 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T* total) {
 
 // Generic fixed-grid reduce-then-scan. F provides:
 //   typedef T; uint32_t n(); T value(uint32_t i); void emit(uint32_t i, T exclusive, T v); void total(int job, T t);
-// blockIdx.y selects an independent job. (A cooperative single-launch variant with grid-wide barriers
+// blockIdx.y selects an independent job; two launches per scan (reduce, emit). (A cooperative single-launch variant with grid-wide barriers
 // between the phases was measured and was slower than these pipelined launches: DESIGN.md section 7.)
 template <class F>
 __device__ __forceinline__ void scan_reduce_dev(const F& f, typename F::T* partial_of_job) {
@@ -624,33 +624,19 @@ __device__ __forceinline__ void scan_reduce_dev(const F& f, typename F::T* parti
   block_exclusive_scan(acc, &tot);
   if (threadIdx.x == 0) partial_of_job[blockIdx.x] = tot;
 }
+// Emit phase. `partial_of_job` holds the per-block TOTALS written by scan_reduce_dev; every block sums the
+// totals of its predecessors itself (at most a few hundred values), which removes the separate
+// "scan the partials" launch; the last block also publishes the grand total.
 template <class F>
-__device__ __forceinline__ void scan_partials_dev(const F& f, typename F::T* p, int g, int job) {  // one warp
-  typedef typename F::T T;
-  int lane = threadIdx.x & 31;
-  T run = zero_of(T());
-  for (int base = 0; base < g; base += 32) {
-    int i = base + lane;
-    T v = i < g ? p[i] : zero_of(T());
-    T inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      T o = shfl_up_t(inc, d);
-      if (lane >= d) inc = o + inc;
-    }
-    T ex = shfl_up_t(inc, 1);
-    if (lane == 0) ex = zero_of(T());
-    if (i < g) p[i] = run + ex;
-    run = run + shfl_idx_t(inc, 31);
-  }
-  if (lane == 0) f.total(job, run);
-}
-template <class F>
-__device__ __forceinline__ void scan_emit_dev(const F& f, const typename F::T* partial_of_job) {
+__device__ __forceinline__ void scan_emit_dev(const F& f, const typename F::T* partial_of_job, int job) {
   typedef typename F::T T;
   uint32_t n = f.n(), begin, end;
   block_range(n, &begin, &end);
-  T run = partial_of_job[blockIdx.x];
+  T mine = zero_of(T());
+  for (uint32_t b = threadIdx.x; b < blockIdx.x; b += kThreads) mine = mine + partial_of_job[b];
+  T run;
+  block_exclusive_scan(mine, &run);  // run = sum of all preceding blocks' totals
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) f.total(job, run + partial_of_job[blockIdx.x]);
   for (uint32_t tile = begin; tile < end; tile += kThreads) {
     uint32_t i = tile + threadIdx.x;
     bool in = i < end;
@@ -666,12 +652,8 @@ __global__ void __launch_bounds__(kThreads) k_scan_reduce(F f, typename F::T* pa
   scan_reduce_dev(f, partial + (size_t)blockIdx.y * gridDim.x);
 }
 template <class F>
-__global__ void k_scan_partials(F f, typename F::T* partial, int g) {  // grid = njobs blocks, 32 threads
-  scan_partials_dev(f, partial + (size_t)blockIdx.x * g, g, (int)blockIdx.x);
-}
-template <class F>
 __global__ void __launch_bounds__(kThreads) k_scan_emit(F f, const typename F::T* partial) {
-  scan_emit_dev(f, partial + (size_t)blockIdx.y * gridDim.x);
+  scan_emit_dev(f, partial + (size_t)blockIdx.y * gridDim.x, (int)blockIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------
