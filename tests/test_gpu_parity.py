@@ -393,3 +393,18 @@ def test_ring_full_and_invalid_inputs(gpu):
     gpu.load(a, w)  # the aggregator stays usable after rejected batches
     assert a.flush().n_rows == 100
     a.close()
+
+
+def test_adaptive_tables_across_flushes(oracle, gpu):
+    """Batches above 2^20 rows switch the stack / thread-id tables to capacities predicted from the previous
+    interval; flush the same 1.2M-row batch three times (worst-case, then adaptive sizes) and compare each
+    result with the oracle, in both schemas."""
+    for schema in (abi.PA_SCHEMA_V2, abi.PA_SCHEMA_V1):
+        w = synth.config2(n=1_200_000, u=30_000, p=32_768)
+        w.schema = schema
+        want, _ = oracle.run(w)
+        a = gpu.from_workload(w, chunk_samples=1 << 18)
+        for i in range(3):
+            gpu.load(a, w)
+            assert a.flush().ipc_bytes() == want, "flush %d differs (schema %d)" % (i, schema)
+        a.close()
