@@ -379,6 +379,44 @@ __device__ __forceinline__ ulonglong2 ldg_stream128(const unsigned long long* p)
 #define PA_WIDE_UNROLL 8
 #endif
 constexpr int kWideUnroll = PA_WIDE_UNROLL;
+// All stripes of one sample half: tiers of kWideUnroll, 4 and up to 3 stripes, each tier with its loads in flight
+// together. kAllAligned: every lane of the warp can use 16-byte loads (no predicated 8-byte fallbacks are emitted).
+template <bool kAllAligned>
+__device__ __forceinline__ void wide_stripes(const unsigned long long* q, uint32_t ns, bool aligned, unsigned long long& a0,
+                                             unsigned long long& a1, unsigned long long& b0, unsigned long long& b1) {
+  auto load2 = [&](const unsigned long long* p) -> ulonglong2 {
+    if (kAllAligned || aligned) return ldg_stream128(p);
+    return make_ulonglong2(ldg_stream64(p), ldg_stream64(p + 1));
+  };
+  auto rounds = [&](const ulonglong2& w) {
+    unsigned long long mx = w.x * XP2, my = w.y * XP2;
+    a0 = xxh_round_pre(a0, mx); a1 = xxh_round_pre(a1, mx);
+    b0 = xxh_round_pre(b0, my); b1 = xxh_round_pre(b1, my);
+  };
+  uint32_t s = 0;
+  for (; s + kWideUnroll <= ns; s += kWideUnroll) {
+    ulonglong2 w[kWideUnroll];
+#pragma unroll
+    for (int u = 0; u < kWideUnroll; u++) w[u] = load2(q + 4 * (s + u));
+#pragma unroll
+    for (int u = 0; u < kWideUnroll; u++) rounds(w[u]);
+  }
+  if (s + 4 <= ns) {
+    ulonglong2 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) w[u] = load2(q + 4 * (s + u));
+#pragma unroll
+    for (int u = 0; u < 4; u++) rounds(w[u]);
+    s += 4;
+  }
+  if (s < ns) {  // up to three trailing stripes, still loaded together
+    ulonglong2 w[3];
+#pragma unroll
+    for (int u = 0; u < 3; u++) w[u] = (s + u < ns) ? load2(q + 4 * (s + u)) : make_ulonglong2(0ull, 0ull);
+#pragma unroll
+    for (int u = 0; u < 3; u++) if (s + u < ns) rounds(w[u]);
+  }
+}
 __global__ void __launch_bounds__(kThreads, 4) k_hash_insert_wide(HashArgs a) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, h = lane & 1, g = lane >> 1;  // h: which half of the stripe, g: sample within the sub-step
@@ -397,29 +435,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_hash_insert_wide(HashArgs a) {
       const uint32_t n = __shfl_sync(full, n_me, src);
       const unsigned long long off = __shfl_sync(full, off_me, src);
       const unsigned long long* q = a.frames + off + 2 * h;
-      const bool aligned = (off & 1ull) == 0;  // 16-byte loads need an even word offset
       unsigned long long a0 = xxh_lane_init(0ull, 2 * h), b0 = xxh_lane_init(0ull, 2 * h + 1);
       unsigned long long a1 = xxh_lane_init(kSeedLo, 2 * h), b1 = xxh_lane_init(kSeedLo, 2 * h + 1);
-      const uint32_t ns = n >> 2;
-      uint32_t s = 0;
-      if (aligned) {
-        for (; s + kWideUnroll <= ns; s += kWideUnroll) {
-          ulonglong2 w[kWideUnroll];
-#pragma unroll
-          for (int u = 0; u < kWideUnroll; u++) w[u] = ldg_stream128(q + 4 * (s + u));
-#pragma unroll
-          for (int u = 0; u < kWideUnroll; u++) {
-            unsigned long long mx = w[u].x * XP2, my = w[u].y * XP2;
-            a0 = xxh_round_pre(a0, mx); a1 = xxh_round_pre(a1, mx);
-            b0 = xxh_round_pre(b0, my); b1 = xxh_round_pre(b1, my);
-          }
-        }
-      }
-      for (; s < ns; s++) {
-        unsigned long long mx = ldg_stream64(q + 4 * s) * XP2, my = ldg_stream64(q + 4 * s + 1) * XP2;
-        a0 = xxh_round_pre(a0, mx); a1 = xxh_round_pre(a1, mx);
-        b0 = xxh_round_pre(b0, my); b1 = xxh_round_pre(b1, my);
-      }
+      const bool aligned = (off & 1ull) == 0;  // 16-byte loads need an even word offset
+      if (__all_sync(full, aligned)) wide_stripes<true>(q, n >> 2, true, a0, a1, b0, b1);   // uniform batches: pure LDG.128
+      else wide_stripes<false>(q, n >> 2, aligned, a0, a1, b0, b1);                          // ragged: per-lane 16-byte or 2 x 8-byte loads
       __syncwarp(full);
       // transpose: lane L (in half `sub`) gets accumulators 0,1 from lane 2*(L&15) and 2,3 from lane 2*(L&15)+1
       const int s0 = 2 * (lane & 15), s1 = s0 + 1;

@@ -256,6 +256,26 @@ def config4_shard(rank, world, n_total=100_000_000, hash_mode=abi.PA_HASH_XXH64X
     return _pid_shard("cfg4", 0x5EED0004, rank, world, n_total // world, 1_000_000 // world * 2, 1_048_576, 65_536 // world, hash_mode)
 
 
+def ragged(n=2_000_000, u=50_000, p=65_536, max_depth=127, seed=0x5EED00AA, hash_mode=abi.PA_HASH_XXH64X2):
+    """Real-world-like stack depths: every unique stack has its own depth in 1..max_depth (not a BASELINE config; used
+    to check that the ragged code paths of the hash kernel stay fast and exact)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base = _uniform_batch("ragged", seed, n, 1, u, p, 256, 8, 64, 0.8, 0.1, "python", hash_mode=hash_mode)
+    depth = rng.integers(1, max_depth + 1, u)
+    starts = np.zeros(u + 1, dtype=np.int64)
+    starts[1:] = np.cumsum(depth)
+    pool = rng.integers(0, p, int(starts[-1]), dtype=np.uint64)
+    choice = base.stack_choice
+    nf = depth[choice]
+    off = np.zeros(n, dtype=np.uint64)
+    off[1:] = np.cumsum(nf)[:-1]
+    idx = np.repeat(starts[choice], nf) + (np.arange(int(nf.sum())) - np.repeat(off.astype(np.int64), nf))
+    base.hdrs["nframes"] = nf
+    base.hdrs["frame_off"] = off
+    return Workload("ragged_%d" % n, base.strings, base.frames, base.labelsets, base.hdrs, _frame_ids=pool[idx], hash_mode=hash_mode,
+                    meta={"N": n, "U": u, "P": p, "F": "1..%d" % max_depth})
+
+
 def edge_workload(seed=7, n=600, hash_mode=abi.PA_HASH_PROVIDED, label_flags=0, external=True):
     """Small adversarial batch: ragged stacks (0..9 frames), every sample kind, every frame kind,
     labelsets with missing names (null back-fill), empty comm (thread_name dropped), hash

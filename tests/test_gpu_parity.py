@@ -408,3 +408,9 @@ def test_adaptive_tables_across_flushes(oracle, gpu):
             gpu.load(a, w)
             assert a.flush().ipc_bytes() == want, "flush %d differs (schema %d)" % (i, schema)
         a.close()
+
+
+def test_ragged_depths(oracle, gpu):
+    """Every stack has its own depth (1..127 frames): remainder tiers of the hash kernel, odd offsets, all variants."""
+    w = synth.ragged(n=150_000, u=4_000, p=8_192)
+    assert_same(oracle, gpu, w)
