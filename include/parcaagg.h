@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PA_ABI_VERSION 1u
+#define PA_ABI_VERSION 2u
 
 /* ---- error codes -------------------------------------------------------------------------- */
 #define PA_OK 0
@@ -72,7 +72,8 @@ enum {
 #define PA_LABEL_DISABLE_THREAD_COMM 0x4u /* --metadata-disable-thread-comm-label (:319) */
 
 #define PA_SCHEMA_V2 0u /* inline stacktraces, reporter/arrow_v2.go */
-#define PA_SCHEMA_V1 1u /* stacktrace ids only, reporter/arrow.go:260-332 + parca_reporter.go:246-328 (sample record) */
+#define PA_SCHEMA_V1 1u /* stacktrace ids only, reporter/arrow.go:260-332 + parca_reporter.go:246-328 (sample record);
+                           the follow-up record with the full stacktraces comes from pa_agg_stacktraces */
 
 #define PA_NO_STRING 0xFFFFFFFFu /* "no value"; string id 0 is always the empty string "" */
 
@@ -94,7 +95,7 @@ typedef struct pa_sample_hdr {
   uint8_t flags;         /* reserved, 0 */
 } pa_sample_hdr;
 
-/* One distinct libpf.Frame value (the dedup key of appendLocationV2, :421): 56 bytes.
+/* One distinct libpf.Frame value (the dedup key of appendLocationV2, :421): 64 bytes.
  * frame ids are dense: the i-th registered frame has id i. The shim guarantees
  * frame-id equality == libpf.Frame value equality (it interns unique.Handle → id). */
 typedef struct pa_frame_desc {
@@ -108,9 +109,11 @@ typedef struct pa_frame_desc {
   uint32_t source_line;        /* frame.SourceLine */
   uint32_t exec_file_name_sid; /* execInfo.FileName when PA_FRAME_F_EXEC_KNOWN */
   uint32_t exec_build_id_sid;  /* execInfo.BuildID ("" → FileID hex, :467-471) */
-  uint32_t reserved1;
+  uint32_t source_column;      /* frame.SourceColumn (v1 stacktrace record only, :1680, :1727) */
   uint64_t file_id_hi;         /* mf.FileID */
   uint64_t file_id_lo;
+  uint32_t mapping_file_name_sid; /* frame.Mapping.File.FileName — v1 interpreted frames with a GNU build id (:1716-1719) */
+  uint32_t gnu_build_id_sid;      /* frame.Mapping.File.GnuBuildID ("" = 0: fall back to the frame-type string) */
 } pa_frame_desc;
 
 typedef struct pa_label_pair {
@@ -131,6 +134,12 @@ typedef struct pa_agg_config {
   uint32_t chunk_samples;      /* H2D/compute overlap granularity; 0 = default */
   uint32_t schema;             /* PA_SCHEMA_V2 (0, default here) or PA_SCHEMA_V1 (--remote-store-use-v2-schema=false,
                                   flags/flags.go:349): which sample record pa_agg_flush builds */
+  uint64_t stack_cache_entries; /* v1 only: capacity of the known-stacks store (the `stacks` LRU, cacheSize at
+                                  parca_reporter.go:876; main.go:630 keeps it >= 65536). 0 = max(65536, max_samples) */
+  uint64_t stack_cache_frames;  /* v1 only: capacity of the store's frame arena, in frames. 0 = 64 per entry (4 bytes each) */
+  uint32_t unknown_frame_type_sid; /* v1 only: string id of libpf.UnknownFrame.String() for the "missing stacktrace"
+                                  row (:1561); 0 = the literal "unknown" */
+  uint32_t reserved;
 } pa_agg_config;
 
 /* Result of one flush; memory is library-owned (pinned host) until pa_agg_release. */
@@ -175,6 +184,18 @@ int pa_agg_submit(pa_agg* a, const pa_sample_hdr* hdrs, const uint64_t* frames, 
  * lock, run the GPU pipeline on the detached buffer, return the finished IPC stream. */
 int pa_agg_flush(pa_agg* a, pa_agg_result* out);
 void pa_agg_release(pa_agg* a, pa_agg_result* res);
+
+/* v1 schema only — buildStacktraceRecord (:1545-1739) + LocationsWriter.NewRecord (arrow.go:230-254) + IPC
+ * (:1336-1349 offline, :1470-1500 gRPC): the record {stacktrace_id: Binary, is_complete: Bool, locations:
+ * List<Struct<...>>} for n_ids 16-byte stack ids (big-endian hi||lo, as in the sample record's stacktrace_id
+ * dictionary), resolved against the device-resident store of known stacks that every v1 flush feeds (the
+ * `stacks` LRU, :224-227). An id that is not (or no longer) in the store yields the reference's
+ * "missing stacktrace" row (:1556-1573). out->n_rows = n_ids, out->n_locations = flattened locations.
+ * The result replaces the previous flush/stacktraces result (same pinned output buffer). */
+int pa_agg_stacktraces(pa_agg* a, const uint8_t* ids, uint64_t n_ids, pa_agg_result* out);
+/* v1: the unique stack ids of the batch most recently processed, first-occurrence order (== the stacktrace_id
+ * dictionary of its sample record, the ids the reference walks at :1307-1328). out has 16*n bytes. */
+int pa_agg_last_stack_ids(pa_agg* a, uint8_t* out, uint64_t n);
 
 /* bench / profiling hooks: the same pipeline split in its three stages.
  * stage = swap + H2D only; process = kernels only on the HBM-resident batch (repeatable);

@@ -21,7 +21,7 @@
 
 namespace orc {
 
-enum TypeId { T_INT, T_UTF8, T_UTF8VIEW, T_FSB, T_TIMESTAMP_NS_UTC, T_STRUCT, T_LISTVIEW, T_REE, T_DICT_U32, T_BINARY };
+enum TypeId { T_INT, T_UTF8, T_UTF8VIEW, T_FSB, T_TIMESTAMP_NS_UTC, T_STRUCT, T_LISTVIEW, T_REE, T_DICT_U32, T_BINARY, T_LIST, T_BOOL };
 
 struct DType;
 using TypeP = std::shared_ptr<DType>;
@@ -45,6 +45,8 @@ inline TypeP dict_t(TypeP v) { auto t = mk(T_DICT_U32); t->dict_value = std::mov
 inline TypeP struct_t(std::vector<Field> f) { auto t = mk(T_STRUCT); t->kids = std::move(f); return t; }
 // arrow.ListViewOf(t): element field "item", nullable
 inline TypeP listview_t(TypeP v) { auto t = mk(T_LISTVIEW); t->kids = {Field{"item", std::move(v), true, {}}}; return t; }
+// arrow.ListOf(t): element field "item", nullable
+inline TypeP list_t(TypeP v) { auto t = mk(T_LIST); t->kids = {Field{"item", std::move(v), true, {}}}; return t; }
 // arrow.RunEndEncodedOf(runEnds, values): children "run_ends" (non-null) and "values" (nullable)
 inline TypeP ree_t(TypeP v) {
   auto t = mk(T_REE);
@@ -98,6 +100,41 @@ struct PrimBuilder {
     a.nulls = nulls;
     a.bufs = {pack_validity(valid, nulls), buf_of(v)};
     v.clear(); valid.clear(); nulls = 0;
+    return a;
+  }
+};
+
+// array.BooleanBuilder (no nulls on this path): one bit per value
+struct BoolBuilder {
+  std::vector<uint8_t> v;
+  void Append(bool x) { v.push_back(x ? 1 : 0); }
+  ArrayData NewArray() {
+    ArrayData a;
+    a.type = mk(T_BOOL);
+    a.len = (int64_t)v.size();
+    a.bufs = {nullptr, pack_validity(v, 1)};
+    if (!a.bufs[1]) a.bufs[1] = mkbuf(0);
+    v.clear();
+    return a;
+  }
+};
+
+// array.ListBuilder: Append(valid) records the child length as the entry's start offset; the closing offset
+// is appended when the array is built (n+1 int32 offsets). The child array is supplied by the caller.
+struct ListBuilder {
+  std::vector<int32_t> off;
+  std::vector<uint8_t> valid;
+  int64_t nulls = 0;
+  void Append(bool v, int64_t child_len) { off.push_back((int32_t)child_len); valid.push_back(v ? 1 : 0); if (!v) nulls++; }
+  ArrayData NewArray(TypeP type, ArrayData child) {
+    off.push_back((int32_t)child.len);
+    ArrayData a;
+    a.type = std::move(type);
+    a.len = (int64_t)valid.size();
+    a.nulls = nulls;
+    a.bufs = {pack_validity(valid, nulls), buf_of(off)};
+    a.kids = {std::move(child)};
+    off.clear(); valid.clear(); nulls = 0;
     return a;
   }
 };

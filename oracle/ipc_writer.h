@@ -111,7 +111,7 @@ class FBB {
 };
 
 // ---- Arrow flatbuffer enums -------------------------------------------------------------
-enum FbType { FB_Int = 2, FB_Binary = 4, FB_Utf8 = 5, FB_Timestamp = 10, FB_Struct = 13, FB_FSB = 15, FB_REE = 22, FB_Utf8View = 24, FB_ListView = 25 };
+enum FbType { FB_Int = 2, FB_Binary = 4, FB_Bool = 6, FB_List = 12, FB_Utf8 = 5, FB_Timestamp = 10, FB_Struct = 13, FB_FSB = 15, FB_REE = 22, FB_Utf8View = 24, FB_ListView = 25 };
 enum FbHeader { FB_Schema = 1, FB_DictionaryBatch = 2, FB_RecordBatch = 3 };
 
 class IpcWriter {
@@ -190,6 +190,8 @@ class IpcWriter {
       }
       case T_STRUCT: b.start(0); *to = b.end(); *tt = FB_Struct; break;
       case T_LISTVIEW: b.start(0); *to = b.end(); *tt = FB_ListView; break;
+      case T_LIST: b.start(0); *to = b.end(); *tt = FB_List; break;
+      case T_BOOL: b.start(0); *to = b.end(); *tt = FB_Bool; break;
       case T_REE: b.start(0); *to = b.end(); *tt = FB_REE; break;
       case T_DICT_U32: assert(false); break;
     }
@@ -259,7 +261,7 @@ class IpcWriter {
     TypeId id = a.type->id;
     if (id != T_REE) put(body, a.nulls ? a.bufs[0] : nullptr);
     switch (id) {
-      case T_INT: case T_FSB: case T_TIMESTAMP_NS_UTC: case T_DICT_U32:
+      case T_INT: case T_FSB: case T_TIMESTAMP_NS_UTC: case T_DICT_U32: case T_BOOL: case T_LIST:
         put(body, a.bufs[1]);
         break;
       case T_UTF8: case T_BINARY: case T_LISTVIEW:

@@ -67,9 +67,10 @@ template <class T>
 struct IntRunEndBuilder {
   ReeCore ree;
   PrimBuilder<T> vb;
-  void Append(T v) {
-    if (vb.Len() > 0 && v == vb.Value(vb.Len() - 1)) { ree.ContinueRun(1); return; }
-    ree.Append(1);
+  void Append(T v) { AppendN(v, 1); }
+  void AppendN(T v, uint64_t n) {  // arrow.go:170-177
+    if (vb.Len() > 0 && v == vb.Value(vb.Len() - 1)) { ree.ContinueRun(n); return; }
+    ree.Append(n);
     vb.Append(v);
   }
   ArrayData NewArray(bool sgn) { ree.finishRun(); return ree.wrap(int_t(64, sgn), vb.NewArray(int_t(64, sgn))); }
@@ -286,6 +287,55 @@ struct SampleWriter {
   }
 };
 
+// reporter/arrow.go:209-254, :545-589 — LocationsWriter (v1 stacktrace record) and its schema (:332-388)
+static TypeP DictBinT() { return dict_t(mk(T_BINARY)); }
+static TypeP LineStructT() {
+  return struct_t({Field{"line", int_t(64, true), false, {}}, Field{"column", int_t(64, false), false, {}},
+                   Field{"function_name", DictBinT(), false, {}}, Field{"function_system_name", DictBinT(), false, {}},
+                   Field{"function_filename", ree_t(DictBinT()), false, {}}, Field{"function_start_line", int_t(64, true), false, {}}});
+}
+static TypeP LocationStructT() {
+  return struct_t({Field{"address", int_t(64, false), false, {}}, Field{"frame_type", ree_t(DictBinT()), false, {}},
+                   Field{"mapping_start", ree_t(int_t(64, false)), false, {}}, Field{"mapping_limit", ree_t(int_t(64, false)), false, {}},
+                   Field{"mapping_offset", ree_t(int_t(64, false)), false, {}}, Field{"mapping_file", ree_t(DictBinT()), false, {}},
+                   Field{"mapping_build_id", ree_t(DictBinT()), false, {}}, Field{"lines", list_t(LineStructT()), false, {}}});
+}
+struct LocationsWriter {
+  BoolBuilder IsComplete;
+  ListBuilder LocationsList;
+  int64_t Locations = 0;  // StructBuilder: every Append(true) is one valid struct slot
+  PrimBuilder<uint64_t> Address;
+  BinaryDictionaryRunEndBuilder FrameType, MappingFile, MappingBuildID, FunctionFilename;
+  IntRunEndBuilder<uint64_t> MappingStart, MappingLimit, MappingOffset;
+  ListBuilder Lines;
+  int64_t Line = 0;
+  PrimBuilder<int64_t> LineNumber, FunctionStartLine;
+  PrimBuilder<uint64_t> ColumnNumber;
+  BinaryDictBuilder FunctionName, FunctionSystemName;
+
+  // NewRecord (arrow.go:230-254) minus the stacktrace_id column, which the caller owns
+  ArrayData NewLocations() {
+    uint64_t numMappings = (uint64_t)MappingFile.Len();
+    MappingStart.AppendN(0, numMappings);
+    MappingLimit.AppendN(0, numMappings);
+    MappingOffset.AppendN(0, numMappings);
+    ArrayData line;
+    line.type = LineStructT();
+    line.len = Line;
+    line.bufs = {nullptr};
+    line.kids = {LineNumber.NewArray(int_t(64, true)), ColumnNumber.NewArray(int_t(64, false)), FunctionName.NewArray(T_BINARY),
+                 FunctionSystemName.NewArray(T_BINARY), FunctionFilename.NewArray(T_BINARY), FunctionStartLine.NewArray(int_t(64, true))};
+    ArrayData lines = Lines.NewArray(list_t(LineStructT()), std::move(line));
+    ArrayData loc;
+    loc.type = LocationStructT();
+    loc.len = Locations;
+    loc.bufs = {nullptr};
+    loc.kids = {Address.NewArray(int_t(64, false)), FrameType.NewArray(T_BINARY), MappingStart.NewArray(false), MappingLimit.NewArray(false),
+                MappingOffset.NewArray(false), MappingFile.NewArray(T_BINARY), MappingBuildID.NewArray(T_BINARY), std::move(lines)};
+    return LocationsList.NewArray(list_t(LocationStructT()), std::move(loc));
+  }
+};
+
 // ------------------------------------------------------------------------------------------
 struct Stats { uint64_t rows, unique_stacks, locations, functions, location_indices, empty_samples; };
 
@@ -295,7 +345,10 @@ struct Reporter {
   std::vector<std::string> strings{std::string()};  // id 0 == ""
   std::vector<pa_frame_desc> frames;
   std::vector<std::vector<std::pair<std::string, std::string>>> labelsets;  // the labels LRU content (:569)
-  std::unordered_map<TraceHash, std::pair<const uint64_t*, int>, TraceHashHasher> stacks;  // r.stacks LRU (:224-227)
+  std::unordered_map<TraceHash, std::pair<const uint64_t*, int>, TraceHashHasher> stacks;  // r.stacks LRU (:224-227), v2: never read
+  // v1: the same LRU, persistent across intervals and read by buildStacktraceRecord. Eviction is not modelled
+  // (an evicted stack and a never-seen one produce the same "missing stacktrace" row).
+  std::unordered_map<TraceHash, std::vector<uint64_t>, TraceHashHasher> known;
   SampleWriterV2* w = new SampleWriterV2();
   SampleWriter* w1 = new SampleWriter();  // v1 schema writer (r.sampleWriter)
   uint64_t emptySamples = 0;
@@ -427,7 +480,9 @@ struct Reporter {
       hash.hi = orc_xxh64_impl(fr, (uint64_t)h.nframes * 8, 0);
       hash.lo = orc_xxh64_impl(fr, (uint64_t)h.nframes * 8, PA_XXH_SEED_LO);
     }
-    if (stacks.find(hash) == stacks.end()) stacks.emplace(hash, std::make_pair(fr, (int)h.nframes));  // :224-227
+    if (cfg.schema == PA_SCHEMA_V1) {
+      if (known.find(hash) == known.end()) known.emplace(hash, std::vector<uint64_t>(fr, fr + h.nframes));        // :224-227
+    } else if (stacks.find(hash) == stacks.end()) stacks.emplace(hash, std::make_pair(fr, (int)h.nframes));
     auto labels = labelsForTID(h.tid, h.labelset_id, S(h.comm_sid), h.cpu);                            // :229
     if (h.nframes == 0) emptySamples++;                                                                 // :237-239
     if (cfg.schema == PA_SCHEMA_V1) { reportTraceEventV1(hash, h, labels); return; }                     // :242-328
@@ -498,6 +553,137 @@ struct Reporter {
       case PA_KIND_MEM_ALLOC_SPACE: w1->Temporality.AppendNull(); writeSample(h.value, 0, memPeriod, "memory", "alloc_space", "bytes", "space", "bytes"); break;
       default: break;
     }
+  }
+
+  // reporter/parca_reporter.go:1545-1739 — buildStacktraceRecord, branch by branch; ids = n 16-byte big-endian hashes
+  void buildStacktraceRecord(const uint8_t* ids, uint64_t n) {
+    LocationsWriter w;
+    const std::string unknownType = cfg.unknown_frame_type_sid ? S(cfg.unknown_frame_type_sid) : std::string("unknown");
+    for (uint64_t i = 0; i < n; i++) {
+      bool isComplete = true;
+      TraceHash th{0, 0};  // libpf.TraceHashFromBytes
+      for (int k = 0; k < 8; k++) { th.hi = (th.hi << 8) | ids[16 * i + k]; th.lo = (th.lo << 8) | ids[16 * i + 8 + k]; }
+      auto it = known.find(th);
+      if (it == known.end()) {  // :1556-1573
+        w.LocationsList.Append(true, w.Locations);
+        w.Locations++;
+        w.Address.Append(0);
+        w.FrameType.Append(unknownType);
+        w.MappingFile.AppendNull();
+        w.MappingBuildID.AppendNull();
+        w.Lines.Append(true, w.Line);
+        w.Line++;
+        w.LineNumber.Append(0);
+        w.ColumnNumber.Append(0);
+        w.FunctionName.Append("missing stacktrace");
+        w.FunctionSystemName.Append("");
+        w.FunctionFilename.AppendNull();
+        w.FunctionStartLine.Append(0);
+        w.IsComplete.Append(false);
+        continue;
+      }
+      const std::vector<uint64_t>& traceInfo = it->second;
+      w.LocationsList.Append(!traceInfo.empty(), w.Locations);  // :1576-1580
+      for (uint64_t frame_id : traceInfo) {
+        const pa_frame_desc& f = frames[frame_id];
+        w.Locations++;
+        w.Address.Append(f.address_or_lineno);
+        auto line = [&](int64_t lineNumber, uint64_t column, std::string_view fn, const std::string* filename) {
+          w.Lines.Append(true, w.Line);
+          w.Line++;
+          w.LineNumber.Append(lineNumber);
+          w.ColumnNumber.Append(column);
+          w.FunctionName.Append(fn);
+          w.FunctionSystemName.Append("");
+          if (filename) w.FunctionFilename.Append(*filename); else w.FunctionFilename.AppendNull();
+          w.FunctionStartLine.Append(0);
+        };
+        bool exists = (f.flags & PA_FRAME_F_MAPPING_FILE) && (f.flags & PA_FRAME_F_EXEC_KNOWN);
+        if (f.kind == PA_FRAME_ABORT) {  // :1586-1604
+          w.FrameType.Append(S(f.type_name_sid));
+          w.MappingFile.Append("agent-internal-error-frame");
+          w.MappingBuildID.AppendNull();
+          line(0, 0, "aborted", nullptr);
+          continue;
+        }
+        switch (f.kind) {
+          case PA_FRAME_NATIVE:  // :1606-1643
+            w.FrameType.Append(S(f.type_name_sid));
+            if (exists) {
+              w.MappingFile.Append(S(f.exec_file_name_sid));
+              if (!S(f.exec_build_id_sid).empty()) {
+                w.MappingBuildID.Append(S(f.exec_build_id_sid));
+              } else {
+                char hex[40];
+                snprintf(hex, sizeof hex, "%016llx%016llx", (unsigned long long)f.file_id_hi, (unsigned long long)f.file_id_lo);
+                w.MappingBuildID.Append(hex);
+              }
+            } else {
+              w.MappingFile.Append("UNKNOWN");
+              w.MappingBuildID.AppendNull();
+              isComplete = false;
+            }
+            w.Lines.Append(false, w.Line);
+            break;
+          case PA_FRAME_KERNEL: {  // :1644-1687
+            w.FrameType.Append(S(f.type_name_sid));
+            std::string moduleName = exists ? S(f.exec_file_name_sid) : std::string("vmlinux");
+            std::string symbol;
+            int64_t lineNumber = 0;
+            if (!S(f.function_name_sid).empty()) { symbol = S(f.function_name_sid); lineNumber = (int64_t)f.source_line; }
+            else { symbol = "UNKNOWN"; isComplete = false; }
+            w.MappingBuildID.AppendNull();
+            line(lineNumber, f.source_column, symbol, &moduleName);
+            w.MappingFile.Append("[kernel.kallsyms]");
+            break;
+          }
+          case PA_FRAME_OOMPROF:  // :1688-1694
+            w.FrameType.Append(S(f.type_name_sid));
+            w.MappingFile.Append(S(f.source_file_sid));
+            w.MappingBuildID.Append(S(f.function_name_sid));
+            w.Lines.Append(false, w.Line);
+            isComplete = false;
+            break;
+          default: {  // :1695-1733
+            w.FrameType.Append(S(f.type_name_sid));
+            int64_t lineNumber = 0;
+            std::string functionName, filePath;
+            if (!S(f.function_name_sid).empty()) {
+              functionName = S(f.function_name_sid);
+              filePath = S(f.source_file_sid);
+              lineNumber = (int64_t)f.source_line;
+            } else {
+              functionName = "UNREPORTED";
+              filePath = "UNREPORTED";
+              isComplete = false;
+            }
+            if (filePath.empty()) filePath = "UNKNOWN";
+            if (!S(f.gnu_build_id_sid).empty()) {
+              w.MappingFile.Append(S(f.mapping_file_name_sid));
+              w.MappingBuildID.Append(S(f.gnu_build_id_sid));
+            } else {
+              w.MappingFile.Append(S(f.type_name_sid));
+              w.MappingBuildID.AppendNull();
+            }
+            line(lineNumber, f.source_column, functionName, &filePath);
+          }
+        }
+      }
+      w.IsComplete.Append(isComplete);
+    }
+    // LocationsWriter.NewRecord (arrow.go:230-254) + IPC (:1336-1349)
+    StringBuilder idb;
+    for (uint64_t i = 0; i < n; i++) idb.Append(std::string_view((const char*)ids + 16 * i, 16));
+    std::vector<Field> fields = {Field{"stacktrace_id", mk(T_BINARY), false, {}}, Field{"is_complete", mk(T_BOOL), false, {}},
+                                 Field{"locations", list_t(LocationStructT()), false, {}}};
+    std::vector<ArrayData> cols;
+    cols.push_back(idb.NewArray(T_BINARY));
+    cols.push_back(w.IsComplete.NewArray());
+    cols.push_back(w.NewLocations());
+    last = Stats{n, 0, (uint64_t)cols[2].kids[0].len, 0, 0, 0};
+    IpcWriter iw;
+    iw.write_stream(fields, {{"parca_write_schema_version", "v1"}}, cols, (int64_t)n);
+    ipc.swap(iw.out);
   }
 
   // reporter/parca_reporter.go:1528-1543 (buildSampleRecord) + reporter/arrow.go:274-316 (NewRecord) + IPC :1390-1400
@@ -695,6 +881,15 @@ int orc_flush(void* p, const uint8_t** ipc, uint64_t* len, uint64_t* stats6) {
     stats6[0] = r->last.rows; stats6[1] = r->last.unique_stacks; stats6[2] = r->last.locations;
     stats6[3] = r->last.functions; stats6[4] = r->last.location_indices; stats6[5] = r->last.empty_samples;
   }
+  return 0;
+}
+// v1: buildStacktraceRecord for n 16-byte ids against the stacks seen so far
+int orc_stacktraces(void* p, const uint8_t* ids, uint64_t n, const uint8_t** ipc, uint64_t* len, uint64_t* n_locations) {
+  Reporter* r = (Reporter*)p;
+  r->buildStacktraceRecord(ids, n);
+  *ipc = r->ipc.data();
+  *len = r->ipc.size();
+  if (n_locations) *n_locations = r->last.locations;
   return 0;
 }
 uint64_t orc_xxh64(const void* data, uint64_t len, uint64_t seed) { return orc_xxh64_impl(data, len, seed); }

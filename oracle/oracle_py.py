@@ -37,6 +37,7 @@ def lib():
         L.orc_set_external_labels.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.orc_ingest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_flush.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.orc_stacktraces.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.orc_xxh64.restype = C.c_uint64
         L.orc_xxh64.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.orc_fix_truncation.restype = C.c_int64
@@ -59,7 +60,8 @@ class Oracle:
     def __init__(self, w):
         L = lib()
         cfg = abi.PaAggConfig(abi_version=abi.PA_ABI_VERSION, device=0, hash_mode=w.hash_mode, label_flags=w.label_flags,
-                              samples_per_second=w.samples_per_second, schema=getattr(w, "schema", 0))
+                              samples_per_second=w.samples_per_second, schema=getattr(w, "schema", 0),
+                              unknown_frame_type_sid=getattr(w, "unknown_frame_type_sid", 0))
         self.h = L.orc_create(C.byref(cfg))
         assert self.h
         blob, offs = abi.pack_strings(w.strings[1:])  # id 0 == "" is implicit
@@ -87,6 +89,14 @@ class Oracle:
         lib().orc_flush(self.h, C.byref(p), C.byref(n), st)
         data = C.string_at(p, n.value) if n.value else b""
         return data, dict(zip(STAT_NAMES, [int(x) for x in st]))
+
+    def stacktraces(self, ids):
+        """v1: buildStacktraceRecord for the concatenated 16-byte ids; returns (ipc bytes, n_locations)."""
+        ids = bytes(ids)
+        assert len(ids) % 16 == 0
+        p, n, nl = C.POINTER(C.c_uint8)(), C.c_uint64(), C.c_uint64()
+        lib().orc_stacktraces(self.h, ids, len(ids) // 16, C.byref(p), C.byref(n), C.byref(nl))
+        return C.string_at(p, n.value), int(nl.value)
 
     def close(self):
         if self.h:

@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-PA_ABI_VERSION = 1
+PA_ABI_VERSION = 2
 
 PA_KIND_CPU, PA_KIND_OFFCPU, PA_KIND_CUDA = 0, 1, 2
 PA_KIND_MEM_INUSE_OBJECTS, PA_KIND_MEM_INUSE_SPACE, PA_KIND_MEM_ALLOC_OBJECTS, PA_KIND_MEM_ALLOC_SPACE = 3, 4, 5, 6
@@ -30,14 +30,14 @@ HDR_DTYPE = np.dtype([
 ])
 assert HDR_DTYPE.itemsize == 64
 
-# struct pa_frame_desc (56 B)
+# struct pa_frame_desc (64 B)
 FRAME_DTYPE = np.dtype([
     ("kind", "u1"), ("flags", "u1"), ("reserved0", "<u2"), ("type_name_sid", "<u4"),
     ("address_or_lineno", "<u8"), ("function_name_sid", "<u4"), ("source_file_sid", "<u4"),
-    ("source_line", "<u4"), ("exec_file_name_sid", "<u4"), ("exec_build_id_sid", "<u4"), ("reserved1", "<u4"),
-    ("file_id_hi", "<u8"), ("file_id_lo", "<u8"),
+    ("source_line", "<u4"), ("exec_file_name_sid", "<u4"), ("exec_build_id_sid", "<u4"), ("source_column", "<u4"),
+    ("file_id_hi", "<u8"), ("file_id_lo", "<u8"), ("mapping_file_name_sid", "<u4"), ("gnu_build_id_sid", "<u4"),
 ])
-assert FRAME_DTYPE.itemsize == 56
+assert FRAME_DTYPE.itemsize == 64
 
 PAIR_DTYPE = np.dtype([("name_sid", "<u4"), ("value_sid", "<u4")])
 
@@ -52,6 +52,7 @@ class PaAggConfig(C.Structure):
         ("samples_per_second", C.c_uint32), ("n_external_labels", C.c_uint32),
         ("external_labels", C.POINTER(PaLabelPair)),
         ("max_samples", C.c_uint64), ("max_frames", C.c_uint64), ("chunk_samples", C.c_uint32), ("schema", C.c_uint32),
+        ("stack_cache_entries", C.c_uint64), ("stack_cache_frames", C.c_uint64), ("unknown_frame_type_sid", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 

@@ -118,6 +118,13 @@ struct pa_agg {
   Mirror<uint64_t> m_addr, m_line;
   Mirror<uint32_t> m_type, m_map, m_bid, m_func, m_fnfile, m_sid2cid;
   DBuf d_lsmat, d_kindtab, d_cols, d_jobs;
+  // v1: frames resolved by the buildStacktraceRecord rules + the device-resident store of known stacks
+  Mirror<uint32_t> m1_map, m1_bid, m1_fn, m1_file;
+  Mirror<uint64_t> m1_line, m1_col;
+  Mirror<uint8_t> m1_complete;
+  DBuf d_store, d_store_arena, d_store_ctl, d_v1_ids, d_st1;
+  uint64_t store_entries = 0, store_slots = 0, store_frames = 0, last_unique = 0;
+  uint32_t cid_unknown = 0, cid_missing = 0;  // "unknown" (libpf.UnknownFrame.String()) and "missing stacktrace" (:1561, :1568)
 
   // ---- ring (pinned host), double buffered
   struct Ring { pa_sample_hdr* hdr = nullptr; uint64_t* frames = nullptr; const uint64_t* frames_dev = nullptr; uint64_t rows = 0, nfr = 0; } ring[2];
@@ -173,13 +180,13 @@ struct pa_agg {
   }
 };
 
+static uint64_t pow2_at_least(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
+
 #define CK(expr)                                                        \
   do {                                                                  \
     cudaError_t e_ = (expr);                                            \
     if (e_ != cudaSuccess) return a->fail(PA_EIO, #expr, e_);           \
   } while (0)
-
-static uint64_t pow2_at_least(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
 
 // ---------------------------------------------------------------------------------------------
 // column plan: which REE columns exist and how each row's key is derived
@@ -324,6 +331,19 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   need(a->d_ctr, sizeof(Counters));
   need(a->d_partial, (uint64_t)a->G * kMaxCols * 16 + 256);
   need(a->d_ree_partial, (uint64_t)a->sms * 8 * kWarps * kMaxCols * sizeof(uint32_t) + 256);  // lives across the ranking launches between the two REE passes
+  if (a->cfg.schema == PA_SCHEMA_V1) {  // the `stacks` LRU (parca_reporter.go:876): known stacks stay resident in HBM
+    a->cid_unknown = a->sp.intern("unknown");
+    a->cid_missing = a->sp.intern("missing stacktrace");
+    a->store_entries = cfg->stack_cache_entries ? cfg->stack_cache_entries : std::min<uint64_t>(std::max<uint64_t>(65536, N), 1ull << 24);
+    if (a->store_entries > (1ull << 30)) return bail(PA_ERANGE);
+    a->store_slots = pow2_at_least(2 * a->store_entries);
+    a->store_frames = cfg->stack_cache_frames ? cfg->stack_cache_frames : a->store_entries * 64;
+    need(a->d_store, (a->store_slots + 2) * sizeof(StoreSlot));
+    need(a->d_store_arena, a->store_frames * 4);
+    need(a->d_store_ctl, sizeof(StoreCtl));
+    need(a->d_v1_ids, N * 16);
+    if (ok) ok = cudaMemset(a->d_store.p, 0, (a->store_slots + 2) * sizeof(StoreSlot)) == cudaSuccess && cudaMemset(a->d_store_ctl.p, 0, sizeof(StoreCtl)) == cudaSuccess;
+  }
   if (!ok) return bail(PA_ENOMEM);
   *out = a;
   return PA_OK;
@@ -341,7 +361,9 @@ void pa_agg_destroy(pa_agg* a) {
   DBuf* all[] = {&a->d_hdr, &a->d_frames, &a->d_ts, &a->d_value, &a->d_uuid, &a->d_stoff, &a->d_stsize, &a->d_slot, &a->d_kind, &a->d_nfr,
                  &a->d_foff, &a->d_ls, &a->d_cpu, &a->d_tid, &a->d_comm, &a->d_ustream, &a->d_uniq_row, &a->d_uniq_count, &a->d_table, &a->d_ctr,
                  &a->d_arena, &a->d_partial, &a->d_ree_partial, &a->d_lsmat, &a->d_kindtab, &a->d_cols, &a->d_jobs,
-                 &a->m_addr.buf, &a->m_line.buf, &a->m_type.buf, &a->m_map.buf, &a->m_bid.buf, &a->m_func.buf, &a->m_fnfile.buf, &a->m_sid2cid.buf};
+                 &a->m_addr.buf, &a->m_line.buf, &a->m_type.buf, &a->m_map.buf, &a->m_bid.buf, &a->m_func.buf, &a->m_fnfile.buf, &a->m_sid2cid.buf,
+                 &a->m1_map.buf, &a->m1_bid.buf, &a->m1_fn.buf, &a->m1_file.buf, &a->m1_line.buf, &a->m1_col.buf, &a->m1_complete.buf,
+                 &a->d_store, &a->d_store_arena, &a->d_store_ctl, &a->d_v1_ids, &a->d_st1};
   for (DBuf* b : all) b->release();
   for (auto e : a->chunk_ev) cudaEventDestroy(e);
   if (a->ev_h2d0) cudaEventDestroy(a->ev_h2d0);
@@ -496,6 +518,11 @@ static int upload_tables(pa_agg* a) {
   CK(a->m_addr.sync(a->ft.addr, s)); CK(a->m_line.sync(a->ft.line, s)); CK(a->m_type.sync(a->ft.type_cid, s));
   CK(a->m_map.sync(a->ft.map_cid, s)); CK(a->m_bid.sync(a->ft.bid_cid, s)); CK(a->m_func.sync(a->ft.func, s));
   CK(a->m_fnfile.sync(a->ft.fn_file_cid, s)); CK(a->m_sid2cid.sync(a->sp.sid2cid, s));
+  if (a->cfg.schema == PA_SCHEMA_V1) {
+    CK(a->m1_map.sync(a->ft.v1_map_cid, s)); CK(a->m1_bid.sync(a->ft.v1_bid_cid, s)); CK(a->m1_fn.sync(a->ft.v1_fn_cid, s));
+    CK(a->m1_file.sync(a->ft.v1_file_cid, s)); CK(a->m1_line.sync(a->ft.v1_line, s)); CK(a->m1_col.sync(a->ft.v1_col, s));
+    CK(a->m1_complete.sync(a->ft.v1_complete, s));
+  }
   if (a->cols_dirty) {
     int rc = build_columns(a);
     if (rc) return rc;
@@ -506,6 +533,53 @@ static int upload_tables(pa_agg* a) {
     CK(cudaStreamSynchronize(s));  // lsmat/kindtab host vectors may be rebuilt later
   }
   return PA_OK;
+}
+
+// first-occurrence ranking of a batch of FoJobs (blockIdx.y = job). elem_bound: upper bound on elements per job;
+// table_bound: on table entries; both pick right-sized grids
+static void run_fo_jobs(pa_agg* a, const FoJob* djobs, int first, int count, bool need_min, Timer& t, uint64_t elem_bound, uint64_t table_bound,
+                        bool do_map = true) {
+  cudaStream_t s = a->s_comp;
+  const int ge = small_grid(a, elem_bound), gt = small_grid(a, table_bound), gw = small_grid(a, elem_bound / 32 + 1);
+  k_fo_zero<<<dim3(gw, count), kThreads, 0, s>>>(djobs + first);
+  if (need_min) { k_fo_min<<<dim3(ge, count), kThreads, 0, s>>>(djobs + first); t.launches++; }
+  k_fo_bits<<<dim3(gt, count), kThreads, 0, s>>>(djobs + first);
+  launch_scan(a, FoWordsF{djobs + first, -1}, count, t, gw);
+  k_fo_assign<<<dim3(gt, count), kThreads, 0, s>>>(djobs + first);
+  if (do_map) { k_fo_map<<<dim3(ge, count), kThreads, 0, s>>>(djobs + first); t.launches++; }
+  t.launches += 3;
+}
+
+// descriptor tables go up from pinned staging: a pageable cudaMemcpyAsync would synchronise the stream in the
+// middle of the pipeline and leave the tail launch-bound
+static int upload_descriptors(pa_agg* a, const void* jobs, size_t jb, const void* cols, size_t cb) {
+  if (jb + cb > a->h_desc_cap) {
+    if (a->h_desc) cudaFreeHost(a->h_desc);
+    a->h_desc = nullptr;
+    a->h_desc_cap = 0;
+    CK(cudaHostAlloc((void**)&a->h_desc, (jb + cb) * 2, cudaHostAllocDefault));
+    a->h_desc_cap = (jb + cb) * 2;
+  }
+  memcpy(a->h_desc, jobs, jb);
+  if (cb) memcpy(a->h_desc + jb, cols, cb);
+  CK(a->d_jobs.ensure(std::max<size_t>(jb, 256)));
+  CK(a->d_cols.ensure(std::max<size_t>(cb, 256)));
+  CK(cudaMemcpyAsync(a->d_jobs.p, a->h_desc, jb, cudaMemcpyHostToDevice, a->s_comp));
+  if (cb) CK(cudaMemcpyAsync(a->d_cols.p, a->h_desc + jb, cb, cudaMemcpyHostToDevice, a->s_comp));
+  return PA_OK;
+}
+
+// v1: add this batch's new unique stacks to the known-stacks store (parca_reporter.go:224-227)
+static void launch_store_insert(pa_agg* a) {
+  StoreInsertArgs sa{};
+  Counters* ctr = a->d_ctr.as<Counters>();
+  sa.ctr = ctr; sa.uniq_row = a->d_uniq_row.as<uint32_t>(); sa.slot_of_row = a->d_slot.as<uint32_t>(); sa.tab = a->d_table.as<StackSlot>();
+  sa.nframes = a->d_nfr.as<uint16_t>(); sa.frame_off = a->d_foff.as<unsigned long long>();
+  sa.frames = a->cfg.hash_mode == PA_HASH_PROVIDED ? (const unsigned long long*)a->ring[a->staged].frames_dev : a->d_frames.as<unsigned long long>();
+  sa.n_frames_registered = a->ft.count();
+  sa.st = a->d_store.as<StoreSlot>(); sa.mask = (uint32_t)(a->store_slots - 1); sa.arena = a->d_store_arena.as<uint32_t>();
+  sa.cap_frames = a->store_frames; sa.cap_entries = (uint32_t)a->store_entries; sa.ctl = a->d_store_ctl.as<StoreCtl>(); sa.ctr_w = ctr;
+  k_store_insert<<<a->G, kThreads, 0, a->s_comp>>>(sa);
 }
 
 static int process_once(pa_agg* a) {
@@ -541,7 +615,8 @@ static int process_once(pa_agg* a) {
   uint32_t *rowbits = nullptr, *row_wprefix = nullptr, *uniq_slot = nullptr, *uniq_size = nullptr, *first_ls = nullptr;
   want(&first_ls, std::max<size_t>(a->ls.sets.size(), 1) * 4, 0);
   if (v1) {
-    want(&a->v1_ord, Nn * 4); want(&a->v1_ts_vals, Nn * 8); want(&a->v1_ids, Nn * 16); want(&a->v1_id_off, (Nn + 1) * 4);
+    want(&a->v1_ord, Nn * 4); want(&a->v1_ts_vals, Nn * 8); want(&a->v1_id_off, (Nn + 1) * 4);
+    a->v1_ids = a->d_v1_ids.as<uint8_t>();  // outlives the arena: pa_agg_last_stack_ids / pa_agg_stacktraces run after the flush
     want(&a->v1_first_kind, 8 * 4, 0); want(&a->v1_kindrank, 64 * 4); want(&a->v1_kind_order, 64 * 4); want(&a->v1_n_kind_dict, 8 * 4);
   }
   want(&rowbits, (Nn / 32 + 2) * 4, 1); want(&row_wprefix, (Nn / 32 + 2) * 4); want(&uniq_slot, Nn * 4); want(&uniq_size, Nn * 4);
@@ -637,23 +712,9 @@ static int process_once(pa_agg* a) {
     if (v1 && cp.type == COL_KIND && cp.param == 5) { rc[c].nullable = 1; rc[c].validity = cp.validity; }
   }
   if (v1) { ra.ord = a->v1_ord; ra.ts = a->d_ts.as<long long>(); ra.ts_vals = a->v1_ts_vals; ra.kindrank = a->v1_kindrank; ra.kind_dict_mask = 0x3Fu; }
-  // descriptor tables go up first, from pinned staging: a pageable cudaMemcpyAsync would synchronise the
-  // stream in the middle of the pipeline and leave the tail launch-bound
-  {
-    size_t jb = jobs.size() * sizeof(FoJob), cb = rc.size() * sizeof(ReeCol);
-    if (jb + cb > a->h_desc_cap) {
-      if (a->h_desc) cudaFreeHost(a->h_desc);
-      a->h_desc = nullptr;
-      a->h_desc_cap = 0;
-      CK(cudaHostAlloc((void**)&a->h_desc, (jb + cb) * 2, cudaHostAllocDefault));
-      a->h_desc_cap = (jb + cb) * 2;
-    }
-    memcpy(a->h_desc, jobs.data(), jb);
-    memcpy(a->h_desc + jb, rc.data(), cb);
-    CK(a->d_jobs.ensure(jb));
-    CK(a->d_cols.ensure(cb));
-    CK(cudaMemcpyAsync(a->d_jobs.p, a->h_desc, jb, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(a->d_cols.p, a->h_desc + jb, cb, cudaMemcpyHostToDevice, s));
+  {  // descriptor tables go up first
+    int rcu = upload_descriptors(a, jobs.data(), jobs.size() * sizeof(FoJob), rc.data(), rc.size() * sizeof(ReeCol));
+    if (rcu) return rcu;
   }
   const FoJob* djobs = a->d_jobs.as<FoJob>();
 
@@ -729,6 +790,8 @@ static int process_once(pa_agg* a) {
   k_rows_materialize<<<G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>(), v1 ? a->v1_ord : nullptr);
   if (v1) {  // v1 has no inline stacktraces: only the dictionary of unique stack ids
     k_gather_ids<<<small_grid(a, std::min<uint64_t>(N, cap / 2) + 1), kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_uuid.as<uint8_t>(), a->v1_ids, a->v1_id_off);
+    launch_store_insert(a);
+    a->tm[T_RANK].launches++;
   } else {
     const unsigned long long* gather_src = provided ? (const unsigned long long*)a->ring[a->staged].frames_dev : a->d_frames.as<unsigned long long>();
     k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, gather_src,
@@ -737,16 +800,8 @@ static int process_once(pa_agg* a) {
   a->tm[T_RANK].launches += 2;
   CK(cudaEventRecord(a->tm[T_RANK].b, s));
 
-  // elem_bound: upper bound on elements per job; table_bound: on table entries; both pick right-sized grids
   auto run_jobs = [&](int first, int count, bool need_min, Timer& t, uint64_t elem_bound, uint64_t table_bound, bool do_map = true) {
-    const int ge = small_grid(a, elem_bound), gt = small_grid(a, table_bound), gw = small_grid(a, elem_bound / 32 + 1);
-    k_fo_zero<<<dim3(gw, count), kThreads, 0, s>>>(djobs + first);
-    if (need_min) { k_fo_min<<<dim3(ge, count), kThreads, 0, s>>>(djobs + first); t.launches++; }
-    k_fo_bits<<<dim3(gt, count), kThreads, 0, s>>>(djobs + first);
-    launch_scan(a, FoWordsF{djobs + first, -1}, count, t, gw);
-    k_fo_assign<<<dim3(gt, count), kThreads, 0, s>>>(djobs + first);
-    if (do_map) { k_fo_map<<<dim3(ge, count), kThreads, 0, s>>>(djobs + first); t.launches++; }
-    t.launches += 3;
+    run_fo_jobs(a, djobs, first, count, need_min, t, elem_bound, table_bound, do_map);
   };
 
   CK(cudaEventRecord(a->tm[T_LOC].a, s));
@@ -838,6 +893,18 @@ static int process(pa_agg* a) {
   if (e & ERR_BAD_KIND) return a->fail(PA_EINVAL, "sample kind out of range");
   if (e & ERR_BAD_CPU) return a->fail(PA_EINVAL, "cpu id >= 65536");
   if (e & ERR_BAD_FRAME_RANGE) return a->fail(PA_EINVAL, "sample frame range outside the staged frames (frame_off must ascend with the rows)");
+  if (a->cfg.schema == PA_SCHEMA_V1) {
+    if (a->h_ctr.store_overflow) {
+      // the store is full: start a new generation (every older stack becomes "missing", as after an LRU eviction)
+      // and add this batch's stacks again; whatever still does not fit stays marked as dropped
+      CK(cudaMemsetAsync(a->d_store.p, 0, (a->store_slots + 2) * sizeof(StoreSlot), a->s_comp));
+      CK(cudaMemsetAsync(a->d_store_ctl.p, 0, sizeof(StoreCtl), a->s_comp));
+      launch_store_insert(a);
+      CK(cudaStreamSynchronize(a->s_comp));
+      CK(cudaGetLastError());
+    }
+    a->last_unique = a->h_ctr.n_unique;
+  }
   a->prev_unique = a->h_ctr.n_unique;
   a->prev_tids = 0;
   for (uint32_t c = 0; c < a->n_label_cols; c++) if (a->cols[c].type == COL_TID) a->prev_tids = a->h_ctr.n_dict[c];
@@ -1213,7 +1280,242 @@ static int collect(pa_agg* a, pa_agg_result* res) {
   return PA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// v1 stacktrace record: buildStacktraceRecord (parca_reporter.go:1545-1739) + LocationsWriter.NewRecord
+// (arrow.go:230-254) + IPC. Off the per-interval hot path (it runs for the stacks the server asks for, or for
+// the stacks not yet logged in offline mode), but the same building blocks: scans, gathers, first-occurrence ranks.
+static int stacktraces(pa_agg* a, const uint8_t* ids, uint64_t n, pa_agg_result* res) {
+  memset(res, 0, sizeof *res);
+  if (a->cfg.schema != PA_SCHEMA_V1) return a->fail(PA_EINVAL, "pa_agg_stacktraces needs a PA_SCHEMA_V1 aggregator");
+  if (a->staged >= 0) return a->fail(PA_EINVAL, "collect the staged batch before asking for stacktraces");
+  if (n && !ids) return a->fail(PA_EINVAL, "null ids");
+  if (n > 0x7FFFFFFFull / 16) return a->fail(PA_ERANGE, "stacktrace_id offsets exceed int32");
+  CK(cudaSetDevice(a->device));
+  const double t0 = now_ms();
+  a->hostbufs.clear();
+  int rc = upload_tables(a);  // frames may have been registered since the last flush
+  if (rc) return rc;
+  cudaStream_t s = a->s_comp;
+  const uint32_t n32 = (uint32_t)n;
+  const size_t Nn = std::max<size_t>(n, 1);
+  Counters* ctr = a->d_ctr.as<Counters>();
+  Timer tm{};
+
+  // ---- phase 1: look the ids up, size the flattened location list
+  uint8_t *d_ids = nullptr, *complete_b = nullptr, *listv_b = nullptr;
+  uint32_t *q_slot = nullptr, *q_nloc = nullptr, *complete_w = nullptr, *listv_w = nullptr;
+  int* loc_off = nullptr;
+  {
+    struct Req { void** pp; size_t bytes; };
+    std::vector<Req> reqs;
+    auto want = [&reqs](auto** pp, size_t bytes) { reqs.push_back(Req{(void**)pp, (bytes + 255) & ~(size_t)255}); };
+    want(&d_ids, Nn * 16); want(&q_slot, Nn * 4); want(&q_nloc, Nn * 4); want(&loc_off, (Nn + 1) * 4); want(&complete_b, Nn); want(&listv_b, Nn);
+    want(&complete_w, (Nn / 32 + 2) * 4); want(&listv_w, (Nn / 32 + 2) * 4);
+    size_t tot = 0;
+    for (auto& r : reqs) tot += r.bytes;
+    CK(a->d_st1.ensure(tot));
+    size_t off = 0;
+    for (auto& r : reqs) { *r.pp = a->d_st1.as<uint8_t>() + off; off += r.bytes; }
+  }
+  // host copy: also the stacktrace_id column's data (the inner buffer stays put when hostbufs grows)
+  const uint8_t* ids_host = keep(a, std::vector<uint8_t>(ids, ids + n * 16)).data();
+  CK(cudaEventRecord(a->tm[T_TOTAL].a, s));
+  CK(cudaMemsetAsync(ctr, 0, sizeof(Counters), s));
+  if (n) CK(cudaMemcpyAsync(d_ids, ids_host, n * 16, cudaMemcpyHostToDevice, s));
+  const StoreSlot* st = a->d_store.as<StoreSlot>();
+  const uint32_t smask = (uint32_t)(a->store_slots - 1);
+  k_st_lookup<<<small_grid(a, n), kThreads, 0, s>>>(d_ids, n32, st, smask, q_slot, q_nloc);
+  launch_scan(a, StLocF{q_nloc, n32, loc_off, ctr}, 1, tm, small_grid(a, n));
+  tm.launches += 1;
+  CK(cudaMemcpyAsync(a->h_ctr_pinned, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  if (a->h_ctr_pinned->err & ERR_INDEX_OVERFLOW) return a->fail(PA_ERANGE, "flattened locations exceed int32 list offsets");
+  const uint64_t L = a->h_ctr_pinned->n_locations;
+
+  // ---- phase 2: per-location and per-line columns, run-end encoding, dictionaries
+  const size_t Ln = std::max<size_t>(L, 1);
+  uint32_t unknown_cid = a->cid_unknown;
+  size_t S2;
+  {
+    std::lock_guard<std::mutex> g(a->reg_mu);
+    if (a->cfg.unknown_frame_type_sid) {
+      if (a->cfg.unknown_frame_type_sid >= a->sp.sid2cid.size()) return a->fail(PA_EINVAL, "unknown_frame_type_sid is not a registered string id");
+      unknown_cid = a->sp.sid2cid[a->cfg.unknown_frame_type_sid];
+    }
+    S2 = std::max<uint32_t>(a->sp.count(), 1);
+  }
+  const uint32_t missing_cid = a->cid_missing;
+  uint32_t* loc_fid = nullptr;
+  StLocOut o{};
+  uint32_t *hasline_w = nullptr, *run_key[4] = {}, *run_valid[4] = {}, *d_first[5] = {}, *d_rank[5] = {}, *d_order[5] = {}, *d_bits[5] = {}, *d_wp[5] = {};
+  int* run_end[4] = {};
+  size_t ff_bytes = 0;
+  {
+    struct Req { void** pp; size_t bytes; int cls; };
+    std::vector<Req> reqs;
+    auto want = [&reqs](auto** pp, size_t bytes, int cls = 1) { reqs.push_back(Req{(void**)pp, (bytes + 255) & ~(size_t)255, cls}); };
+    for (int d = 0; d < 5; d++) want(&d_first[d], S2 * 4, 0);
+    want(&loc_fid, Ln * 4); want(&o.address, Ln * 8); want(&o.type_key, Ln * 4); want(&o.map_key, Ln * 4); want(&o.bid_key, Ln * 4);
+    want(&o.line_off, (Ln + 1) * 4); want(&o.has_line, Ln); want(&hasline_w, (Ln / 32 + 2) * 4); want(&o.line_no, Ln * 8); want(&o.column, Ln * 8);
+    want(&o.fn_key, Ln * 4); want(&o.file_key, Ln * 4);
+    for (int c = 0; c < 4; c++) { want(&run_key[c], Ln * 4); want(&run_end[c], Ln * 4); want(&run_valid[c], (Ln / 32 + 2) * 4); }
+    for (int d = 0; d < 5; d++) { want(&d_rank[d], S2 * 4); want(&d_order[d], S2 * 4); want(&d_bits[d], (Ln / 32 + 2) * 4); want(&d_wp[d], (Ln / 32 + 2) * 4); }
+    size_t cls_bytes[2] = {0, 0};
+    for (auto& r : reqs) cls_bytes[r.cls] += r.bytes;
+    CK(a->d_arena.ensure(cls_bytes[0] + cls_bytes[1]));
+    size_t off[2] = {0, cls_bytes[0]};
+    for (auto& r : reqs) { *r.pp = a->d_arena.as<uint8_t>() + off[r.cls]; off[r.cls] += r.bytes; }
+    ff_bytes = cls_bytes[0];
+  }
+  std::vector<FoJob> jobs(5);
+  const uint32_t* job_n[5] = {&ctr->n_runs[0], &ctr->n_runs[1], &ctr->n_runs[2], &ctr->n_runs[3], &ctr->n_lines};
+  for (int d = 0; d < 5; d++) {
+    FoJob j{};
+    j.keys = d < 4 ? run_key[d] : o.fn_key; j.n_ptr = job_n[d]; j.first = d_first[d]; j.universe = (uint32_t)S2; j.rank = d_rank[d]; j.order = d_order[d];
+    j.out = d < 4 ? run_key[d] : o.fn_key; j.validity = d < 4 ? run_valid[d] : nullptr; j.bitmap = d_bits[d]; j.wprefix = d_wp[d];
+    j.n_unique = &ctr->n_dict[d]; j.n_null = d < 4 ? &ctr->n_null[d] : nullptr; j.nullable = d < 4 ? 1u : 0u; j.ctr = ctr;
+    jobs[d] = j;
+  }
+  rc = upload_descriptors(a, jobs.data(), jobs.size() * sizeof(FoJob), nullptr, 0);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(a->d_arena.p, 0xFF, ff_bytes, s));
+  FrameTableV1 ft1{(const unsigned long long*)a->m_addr.ptr(), a->m_type.ptr(), a->m1_map.ptr(), a->m1_bid.ptr(), a->m1_fn.ptr(), a->m1_file.ptr(),
+                   (const unsigned long long*)a->m1_line.ptr(), (const unsigned long long*)a->m1_col.ptr(), a->m1_complete.ptr()};
+  k_st_expand<<<small_grid(a, std::max<uint64_t>(n * 32, L)), kThreads, 0, s>>>(n32, q_slot, loc_off, st, a->d_store_arena.as<uint32_t>(), ft1.complete, loc_fid,
+                                                                                    complete_b, listv_b, ctr);
+  k_pack_bits<<<small_grid(a, n), kThreads, 0, s>>>(complete_b, nullptr, n32, complete_w);
+  k_pack_bits<<<small_grid(a, n), kThreads, 0, s>>>(listv_b, nullptr, n32, listv_w);
+  launch_scan(a, StLinesF{ctr, ctr, loc_fid, ft1, o, unknown_cid, missing_cid}, 1, tm, small_grid(a, L));
+  k_pack_bits<<<small_grid(a, L), kThreads, 0, s>>>(o.has_line, &ctr->n_locations, 0, hasline_w);
+  StRunF rf{};
+  rf.c[0] = StRunCol{o.type_key, &ctr->n_locations, run_key[0], run_end[0]};
+  rf.c[1] = StRunCol{o.map_key, &ctr->n_locations, run_key[1], run_end[1]};
+  rf.c[2] = StRunCol{o.bid_key, &ctr->n_locations, run_key[2], run_end[2]};
+  rf.c[3] = StRunCol{o.file_key, &ctr->n_lines, run_key[3], run_end[3]};
+  rf.ctr_w = ctr;
+  launch_scan(a, rf, 4, tm, small_grid(a, L));
+  run_fo_jobs(a, a->d_jobs.as<FoJob>(), 0, 5, true, tm, Ln, S2);
+  tm.launches += 4;
+  CK(cudaMemcpyAsync(a->h_ctr_pinned, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(a->tm[T_TOTAL].b, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  const Counters c = *a->h_ctr_pinned;
+  const uint64_t NL = c.n_lines;
+
+  // ---- phase 3: dictionary values (host strings in rank order) and the IPC stream
+  std::vector<uint32_t> ord[5];
+  for (int d = 0; d < 5; d++) if ((rc = d2h_vec(a, ord[d], d_order[d], c.n_dict[d]))) return rc;
+  CK(cudaStreamSynchronize(s));
+  std::lock_guard<std::mutex> g(a->reg_mu);
+  const StringPool& sp = a->sp;
+  auto strs_of = [&sp](const std::vector<uint32_t>& v) {
+    std::vector<std::pair<const uint8_t*, uint32_t>> out;
+    out.reserve(v.size());
+    for (uint32_t cid : v) out.emplace_back(sp.ptr(cid), sp.len(cid));
+    return out;
+  };
+  auto dict_ree = [&](const char* name, int d, uint64_t len) {
+    uint32_t nr = c.n_runs[d];
+    Node values = dict_node("values", true, nr, c.n_null[d], c.n_null[d] ? BufRef::dev(run_valid[d], (nr + 7) / 8) : BufRef::none(),
+                            BufRef::dev(run_key[d], (uint64_t)nr * 4), utf8_node(a, "values", true, strs_of(ord[d]), nullptr, Ty::Binary));
+    return ree_node(name, false, (int64_t)len, nr, BufRef::dev(run_end[d], (uint64_t)nr * 4), std::move(values));
+  };
+  auto zero_ree = [&](const char* name) {  // AppendN(0, numMappings) (arrow.go:231-238): one run over every location, or none
+    std::vector<int32_t> re;
+    if (L) re.push_back((int32_t)L);
+    std::vector<uint64_t> zero{0};
+    return ree_node(name, false, (int64_t)L, (int64_t)re.size(), host_ref(a, re), int_node("values", 64, false, true, 1, host_ref(a, zero)));
+  };
+  Node line; line.ty = Ty::Struct; line.name = "item"; line.nullable = true; line.length = (int64_t)NL;
+  line.kids.push_back(int_node("line", 64, true, false, (int64_t)NL, BufRef::dev(o.line_no, NL * 8)));
+  line.kids.push_back(int_node("column", 64, false, false, (int64_t)NL, BufRef::dev(o.column, NL * 8)));
+  line.kids.push_back(dict_node("function_name", false, (int64_t)NL, 0, BufRef::none(), BufRef::dev(o.fn_key, NL * 4),
+                                utf8_node(a, "values", true, strs_of(ord[4]), nullptr, Ty::Binary)));
+  {
+    std::vector<std::pair<const uint8_t*, uint32_t>> empty_name;
+    if (NL) empty_name.emplace_back(sp.ptr(0), 0u);  // FunctionSystemName.AppendString("") for every line
+    line.kids.push_back(dict_node("function_system_name", false, (int64_t)NL, 0, BufRef::none(), BufRef::zeros(NL * 4),
+                                  utf8_node(a, "values", true, empty_name, nullptr, Ty::Binary)));
+  }
+  line.kids.push_back(dict_ree("function_filename", 3, NL));
+  line.kids.push_back(int_node("function_start_line", 64, true, false, (int64_t)NL, BufRef::zeros(NL * 8)));
+  Node lines; lines.ty = Ty::List; lines.name = "lines"; lines.nullable = false; lines.length = (int64_t)L; lines.null_count = (int64_t)(L - NL);
+  lines.validity = BufRef::dev(hasline_w, (L + 7) / 8);
+  lines.bufs = {BufRef::dev(o.line_off, (L + 1) * 4)};
+  lines.kids.push_back(std::move(line));
+  Node loc; loc.ty = Ty::Struct; loc.name = "item"; loc.nullable = true; loc.length = (int64_t)L;
+  loc.kids.push_back(int_node("address", 64, false, false, (int64_t)L, BufRef::dev(o.address, L * 8)));
+  loc.kids.push_back(dict_ree("frame_type", 0, L));
+  loc.kids.push_back(zero_ree("mapping_start"));
+  loc.kids.push_back(zero_ree("mapping_limit"));
+  loc.kids.push_back(zero_ree("mapping_offset"));
+  loc.kids.push_back(dict_ree("mapping_file", 1, L));
+  loc.kids.push_back(dict_ree("mapping_build_id", 2, L));
+  loc.kids.push_back(std::move(lines));
+  Node locs; locs.ty = Ty::List; locs.name = "locations"; locs.nullable = false; locs.length = (int64_t)n; locs.null_count = c.st_null_lists;
+  locs.validity = BufRef::dev(listv_w, (n + 7) / 8);
+  locs.bufs = {BufRef::dev(loc_off, (n + 1) * 4)};
+  locs.kids.push_back(std::move(loc));
+  std::vector<Node> cols;
+  {
+    std::vector<int32_t> off(n + 1);
+    for (uint64_t i = 0; i <= n; i++) off[i] = (int32_t)(16 * i);
+    Node id; id.ty = Ty::Binary; id.name = "stacktrace_id"; id.nullable = false; id.length = (int64_t)n;
+    id.bufs = {host_ref(a, off), BufRef::host(ids_host, n * 16)};
+    cols.push_back(std::move(id));
+  }
+  {
+    Node ic; ic.ty = Ty::Bool; ic.name = "is_complete"; ic.nullable = false; ic.length = (int64_t)n; ic.bufs = {BufRef::dev(complete_w, (n + 7) / 8)};
+    cols.push_back(std::move(ic));
+  }
+  cols.push_back(std::move(locs));
+
+  StreamPlan plan;
+  plan.build(cols, {{"parca_write_schema_version", "v1"}}, (int64_t)n);
+  if (plan.total > a->out_cap) {
+    if (a->out) cudaFreeHost(a->out);
+    a->out = nullptr;
+    a->out_cap = 0;
+    uint64_t want = plan.total + plan.total / 4 + 4096;
+    if (cudaHostAlloc((void**)&a->out, want, cudaHostAllocDefault) != cudaSuccess) return a->fail(PA_ENOMEM, "pinned output allocation failed");
+    a->out_cap = want;
+  }
+  const double t1 = now_ms();
+  CK(cudaEventRecord(a->ev_d2h0, s));
+  for (auto& p : plan.placements)
+    if (p.src.kind == BufRef::DEVICE && p.src.len) CK(cudaMemcpyAsync(a->out + p.at, p.src.ptr, p.src.len, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(a->ev_d2h1, s));
+  plan.write_host_parts(a->out);
+  CK(cudaStreamSynchronize(s));
+  const double t2 = now_ms();
+  float d2h = 0, gpu = 0;
+  cudaEventElapsedTime(&d2h, a->ev_d2h0, a->ev_d2h1);
+  cudaEventElapsedTime(&gpu, a->tm[T_TOTAL].a, a->tm[T_TOTAL].b);
+  res->ipc = a->out; res->ipc_len = plan.total; res->n_rows = n; res->n_unique_stacks = n; res->n_locations = L; res->n_functions = c.n_dict[4];
+  res->n_location_indices = NL; res->gpu_launches = tm.launches; res->gpu_ms = gpu; res->d2h_ms = d2h; res->host_ms = (t2 - t0) - gpu - d2h;
+  if (res->host_ms < 0) res->host_ms = 0;
+  (void)t1;
+  return PA_OK;
+}
+
 extern "C" {
+
+int pa_agg_stacktraces(pa_agg* a, const uint8_t* ids, uint64_t n_ids, pa_agg_result* out) {
+  if (!a || !out) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  return stacktraces(a, ids, n_ids, out);
+}
+int pa_agg_last_stack_ids(pa_agg* a, uint8_t* out, uint64_t n) {
+  if (!a || (n && !out)) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  if (a->cfg.schema != PA_SCHEMA_V1) return a->fail(PA_EINVAL, "pa_agg_last_stack_ids needs a PA_SCHEMA_V1 aggregator");
+  if (n > a->last_unique) return a->fail(PA_EINVAL, "more ids requested than the last batch had unique stacks");
+  CK(cudaSetDevice(a->device));
+  if (n) CK(cudaMemcpy(out, a->d_v1_ids.p, n * 16, cudaMemcpyDeviceToHost));
+  return PA_OK;
+}
 
 int pa_agg_stage(pa_agg* a) {
   if (!a) return PA_EINVAL;

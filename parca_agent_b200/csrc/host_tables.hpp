@@ -56,6 +56,14 @@ struct FrameTableHost {
   std::vector<uint32_t> fn_sys_cid;   // kNoId never happens in practice ("" -> null system_name)
   std::vector<uint32_t> fn_file_cid;  // kNoId = null filename ("" in FunctionV2)
   std::unordered_map<uint64_t, uint32_t> fn_index;
+  // v1 stacktrace record (buildStacktraceRecord, :1583-1735): the same frames resolved by the v1 rules
+  std::vector<uint32_t> v1_map_cid;   // mapping_file
+  std::vector<uint32_t> v1_bid_cid;   // mapping_build_id, kNoId = null
+  std::vector<uint32_t> v1_fn_cid;    // line.function_name, kNoId = the location has no line (null lines entry)
+  std::vector<uint32_t> v1_file_cid;  // line.function_filename, kNoId = null
+  std::vector<uint64_t> v1_line;      // line.line (int64 bit pattern)
+  std::vector<uint64_t> v1_col;       // line.column
+  std::vector<uint8_t> v1_complete;   // 0 = this frame clears is_complete
   uint32_t count() const { return (uint32_t)addr.size(); }
   uint32_t n_funcs() const { return (uint32_t)fn_sys_cid.size(); }
 
@@ -79,6 +87,7 @@ struct FrameTableHost {
     bool ok = true;
     uint32_t type = cid(f.type_name_sid, &ok), fn = cid(f.function_name_sid, &ok), file = cid(f.source_file_sid, &ok);
     uint32_t exec_file = cid(f.exec_file_name_sid, &ok), exec_bid = cid(f.exec_build_id_sid, &ok);
+    uint32_t mfile = cid(f.mapping_file_name_sid, &ok), gnu = cid(f.gnu_build_id_sid, &ok);
     if (!ok) return false;
     bool exists = (f.flags & PA_FRAME_F_MAPPING_FILE) && (f.flags & PA_FRAME_F_EXEC_KNOWN);  // :456-462, :486-492
     uint32_t map = 0, bid = kNoId, func_id = kNoId;
@@ -121,6 +130,38 @@ struct FrameTableHost {
         if (path == 0) path = sp.intern("UNKNOWN");  // "Empty path causes the backend to crash" (:540-543)
         func_id = function(name, path);
       }
+    }
+    {  // the v1 rules differ in the details (mapping file of interpreted frames, columns, plain function names)
+      uint32_t m1 = 0, b1 = kNoId, fn1 = kNoId, file1 = kNoId;
+      uint64_t ln1 = 0, col1 = 0;
+      uint8_t complete = 1;
+      switch (f.kind) {
+        case PA_FRAME_ABORT:  // :1586-1604
+          m1 = sp.intern("agent-internal-error-frame");
+          fn1 = sp.intern("aborted");
+          break;
+        case PA_FRAME_NATIVE:  // :1606-1643
+          m1 = map; b1 = bid;
+          complete = exists ? 1 : 0;
+          break;
+        case PA_FRAME_KERNEL:  // :1644-1687
+          m1 = map;
+          file1 = exists ? exec_file : sp.intern("vmlinux");
+          if (fn != 0) { fn1 = fn; ln1 = f.source_line; } else { fn1 = sp.intern("UNKNOWN"); complete = 0; }
+          col1 = f.source_column;
+          break;
+        case PA_FRAME_OOMPROF:  // :1688-1694
+          m1 = file; b1 = fn;
+          complete = 0;
+          break;
+        default:  // :1695-1733
+          if (fn != 0) { fn1 = fn; file1 = file; ln1 = f.source_line; } else { fn1 = sp.intern("UNREPORTED"); file1 = fn1; complete = 0; }
+          if (file1 == 0) file1 = sp.intern("UNKNOWN");
+          if (gnu != 0) { m1 = mfile; b1 = gnu; } else { m1 = type; }
+          col1 = f.source_column;
+      }
+      v1_map_cid.push_back(m1); v1_bid_cid.push_back(b1); v1_fn_cid.push_back(fn1); v1_file_cid.push_back(file1);
+      v1_line.push_back(ln1); v1_col.push_back(col1); v1_complete.push_back(complete);
     }
     addr.push_back(f.address_or_lineno);
     type_cid.push_back(type);

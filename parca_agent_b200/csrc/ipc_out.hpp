@@ -33,7 +33,7 @@ struct BufRef {
   static BufRef zeros(uint64_t n) { return BufRef{ZEROS, nullptr, n}; }
 };
 
-enum class Ty : uint8_t { Int, Utf8, Utf8View, FixedBinary, TimestampNsUtc, Struct, ListView, RunEnd, DictU32, Binary };
+enum class Ty : uint8_t { Int, Utf8, Utf8View, FixedBinary, TimestampNsUtc, Struct, ListView, RunEnd, DictU32, Binary, List, Bool };
 
 // One node = one Arrow field + its array. For Ty::DictU32 the node itself carries the uint32
 // indices and `dict` is the dictionary *value* node (whose type becomes the field's type).
@@ -226,6 +226,8 @@ class StreamPlan {
       case Ty::TimestampNsUtc: { uint32_t tz = b.str("UTC"); b.begin(2); b.field<int16_t>(0, 3, 0); b.ref(1, tz); *tab = b.end(); *tag = 10; break; }
       case Ty::Struct: b.begin(0); *tab = b.end(); *tag = 13; break;
       case Ty::ListView: b.begin(0); *tab = b.end(); *tag = 25; break;
+      case Ty::List: b.begin(0); *tab = b.end(); *tag = 12; break;
+      case Ty::Bool: b.begin(0); *tab = b.end(); *tag = 6; break;
       case Ty::RunEnd: b.begin(0); *tab = b.end(); *tag = 22; break;
       case Ty::DictU32: break;
     }

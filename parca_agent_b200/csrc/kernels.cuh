@@ -41,7 +41,8 @@ struct Counters {
   uint32_t n_locations, n_lines, n_functions;
   uint32_t n_dict_type, n_dict_map, n_dict_bid, n_dict_file;
   uint32_t null_bid, null_file;
-  uint32_t pad0;
+  uint32_t store_overflow;  // v1: the known-stacks store ran out of entries or frame space during this flush
+  uint32_t st_null_lists;   // v1 stacktrace record: known stacks with zero frames (null list entries)
   uint32_t n_runs[kMaxCols];
   uint32_t n_dict[kMaxCols];
   uint32_t n_null[kMaxCols];
@@ -1263,5 +1264,246 @@ __global__ void __launch_bounds__(kThreads) k_ree_scan_partials(ReeArgs a, int g
     if (run) a.cols[blockIdx.x].run_ends[run - 1] = (int)a.n_rows;  // the last run ends at the row count
   }
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// v1 schema: device-resident store of known stacks — the `stacks` LRU of the reference
+// (reporter/parca_reporter.go:105, filled at :224-227, read by buildStacktraceRecord :1555). Every v1
+// flush adds the batch's NEW unique stacks (first occurrence wins, exactly like "if !exists { Add }");
+// the store is append-only and is cleared as a whole when it runs out of room (an evicted stack and a
+// never-seen one both produce the reference's "missing stacktrace" row).
+struct __align__(32) StoreSlot {
+  Key128 key;              // (0,0) = empty; claimed by a 128-bit CAS
+  unsigned long long off;  // first frame in the store's frame arena
+  uint32_t size;           // frames; kNull = claimed but dropped (no room)
+  uint32_t claimed;        // only used by the dedicated all-zero-id slot (index mask+1)
+};
+struct StoreCtl { unsigned long long used_frames; uint32_t entries; uint32_t pad; };
+
+__device__ __forceinline__ uint32_t store_find(const StoreSlot* st, uint32_t mask, Key128 k) {
+  if (key_zero(k)) return st[mask + 1].claimed ? mask + 1 : kNull;
+  uint32_t idx = mix_slot(k) & mask;
+  for (uint32_t probe = 0; probe <= mask; probe++) {
+    Key128 cur = st[idx].key;
+    if (key_eq(cur, k)) return idx;
+    if (key_zero(cur)) return kNull;  // never deleted from: an empty slot ends the cluster
+    idx = (idx + 1) & mask;
+  }
+  return kNull;
+}
+
+struct StoreInsertArgs {
+  const Counters* ctr;
+  const uint32_t* uniq_row;
+  const uint32_t* slot_of_row;
+  const StackSlot* tab;
+  const uint16_t* nframes;
+  const unsigned long long* frame_off;
+  const unsigned long long* frames;  // device copy, or the mapped pinned ring in provided-hash mode
+  uint32_t n_frames_registered;
+  StoreSlot* st;
+  uint32_t mask;
+  uint32_t* arena;
+  unsigned long long cap_frames;
+  uint32_t cap_entries;
+  StoreCtl* ctl;
+  Counters* ctr_w;
+};
+// one warp per unique stack of the batch (unique within the launch, so a key is claimed by at most one warp)
+__global__ void __launch_bounds__(kThreads) k_store_insert(StoreInsertArgs a) {
+  const unsigned full = 0xFFFFFFFFu;
+  uint32_t nu = a.ctr->n_unique;
+  int lane = threadIdx.x & 31;
+  uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+  const Key128 zero{0ull, 0ull};
+  for (uint32_t u = warp; u < nu; u += nwarps) {
+    uint32_t r = a.uniq_row[u];
+    uint32_t size = a.nframes[r];
+    unsigned long long off = 0;
+    int fresh = 0;
+    if (lane == 0) {
+      Key128 k = a.tab[a.slot_of_row[r]].key;
+      uint32_t idx = kNull;
+      if (key_zero(k)) {
+        idx = a.mask + 1;
+        fresh = atomicCAS(&a.st[idx].claimed, 0u, 1u) == 0u;
+      } else {
+        uint32_t p = mix_slot(k) & a.mask;
+        for (uint32_t probe = 0; probe <= a.mask; probe++) {
+          Key128 cur = ld_key(&a.st[p].key);
+          if (cur.hi == 0 || cur.lo == 0) cur = cas128(&a.st[p].key, zero, k);
+          if (key_zero(cur)) { idx = p; fresh = 1; break; }
+          if (key_eq(cur, k)) { idx = p; break; }
+          p = (p + 1) & a.mask;
+        }
+      }
+      if (fresh) {
+        uint32_t e = atomicAdd(&a.ctl->entries, 1u);
+        off = atomicAdd(&a.ctl->used_frames, (unsigned long long)size);
+        if (e >= a.cap_entries || off + size > a.cap_frames) {
+          a.st[idx].size = kNull;
+          atomicOr(&a.ctr_w->store_overflow, 1u);
+          fresh = 0;
+        } else {
+          a.st[idx].off = off;
+          a.st[idx].size = size;
+        }
+      }
+    }
+    fresh = __shfl_sync(full, fresh, 0);
+    if (!fresh) continue;
+    off = __shfl_sync(full, off, 0);
+    const unsigned long long* src = a.frames + a.frame_off[r];
+    for (uint32_t j = lane; j < size; j += 32) {
+      unsigned long long fid = src[j];
+      if (fid >= a.n_frames_registered) { atomicOr(&a.ctr_w->err, ERR_BAD_FRAME_ID); fid = 0; }
+      a.arena[off + j] = (uint32_t)fid;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// v1 stacktrace record (buildStacktraceRecord, parca_reporter.go:1545-1739): requested ids -> flattened
+// locations -> lines, every column of LocationsWriter (arrow.go:209-254) built by scans and gathers.
+__global__ void __launch_bounds__(kThreads) k_st_lookup(const uint8_t* ids, uint32_t n, const StoreSlot* st, uint32_t mask, uint32_t* q_slot,
+                                                        uint32_t* q_nloc) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    ulonglong2 raw = *reinterpret_cast<const ulonglong2*>(ids + 16ull * i);  // libpf.TraceHashFromBytes: big-endian hi||lo
+    Key128 k{bswap64(raw.x), bswap64(raw.y)};
+    uint32_t sl = store_find(st, mask, k);
+    if (sl != kNull && st[sl].size == kNull) sl = kNull;
+    q_slot[i] = sl;
+    q_nloc[i] = sl == kNull ? 1u : st[sl].size;  // a missing stack still yields one placeholder location (:1556-1573)
+  }
+}
+struct StLocF {  // LocationsList offsets: exclusive scan of the per-stack location counts
+  typedef unsigned long long T;
+  const uint32_t* q_nloc;
+  uint32_t n_ids;
+  int* loc_off;
+  Counters* ctr_w;
+  __device__ uint32_t n() const { return n_ids; }
+  __device__ unsigned long long value(uint32_t i) const { return q_nloc[i]; }
+  __device__ void emit(uint32_t i, unsigned long long ex, unsigned long long) const { loc_off[i] = (int)ex; }
+  __device__ void total(int, unsigned long long t) const {
+    loc_off[n_ids] = (int)t;
+    ctr_w->n_indices64 = t;
+    ctr_w->n_locations = (uint32_t)t;
+    if (t > 0x7FFFFFFFull) atomicOr(&ctr_w->err, ERR_INDEX_OVERFLOW);  // List offsets are int32
+  }
+};
+struct FrameTableV1 {  // device mirror of FrameTableHost's v1 columns
+  const unsigned long long* addr;
+  const uint32_t* type_cid;
+  const uint32_t* map_cid;
+  const uint32_t* bid_cid;
+  const uint32_t* fn_cid;    // kNull = no line
+  const uint32_t* file_cid;
+  const unsigned long long* line;
+  const unsigned long long* col;
+  const uint8_t* complete;
+};
+// one warp per requested stack: its frames' ids in location order, is_complete, list validity
+__global__ void __launch_bounds__(kThreads) k_st_expand(uint32_t n_ids, const uint32_t* q_slot, const int* loc_off, const StoreSlot* st,
+                                                        const uint32_t* arena, const uint8_t* frame_complete, uint32_t* loc_fid,
+                                                        uint8_t* complete, uint8_t* list_valid, Counters* ctr_w) {
+  const unsigned full = 0xFFFFFFFFu;
+  int lane = threadIdx.x & 31;
+  uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+  for (uint32_t i = warp; i < n_ids; i += nwarps) {
+    uint32_t sl = q_slot[i];
+    uint32_t base = (uint32_t)loc_off[i];
+    if (sl == kNull) {
+      if (lane == 0) { loc_fid[base] = kNull; complete[i] = 0; list_valid[i] = 1; }
+      continue;
+    }
+    unsigned long long off = st[sl].off;
+    uint32_t size = st[sl].size;
+    int ok = 1;
+    for (uint32_t j = lane; j < size; j += 32) {
+      uint32_t fid = arena[off + j];
+      loc_fid[base + j] = fid;
+      ok &= (int)frame_complete[fid];
+    }
+    ok = __all_sync(full, ok);
+    if (lane == 0) {
+      complete[i] = (uint8_t)ok;
+      list_valid[i] = size != 0;  // LocationsList.Append(false) for an empty trace (:1576-1580)
+      if (size == 0) atomicAdd(&ctr_w->st_null_lists, 1u);
+    }
+  }
+}
+// bytes (0/1) -> Arrow bitmap words; n may live on the device
+__global__ void __launch_bounds__(kThreads) k_pack_bits(const uint8_t* src, const uint32_t* n_ptr, uint32_t n_imm, uint32_t* words) {
+  uint32_t n = n_ptr ? *n_ptr : n_imm;
+  uint32_t nw = (n + 31) / 32;
+  int lane = threadIdx.x & 31;
+  uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+  for (uint32_t w = warp; w < nw; w += nwarps) {
+    uint32_t i = w * 32 + lane;
+    unsigned bits = __ballot_sync(0xFFFFFFFFu, i < n && src[i] != 0);
+    if (lane == 0) words[w] = bits;
+  }
+}
+struct StLocOut {
+  unsigned long long* address;
+  uint32_t* type_key;
+  uint32_t* map_key;   // kNull = null
+  uint32_t* bid_key;   // kNull = null
+  int* line_off;       // [L+1]
+  uint8_t* has_line;   // lines validity source
+  long long* line_no;
+  unsigned long long* column;
+  uint32_t* fn_key;
+  uint32_t* file_key;  // kNull = null
+};
+struct StLinesF {  // per-location gather fused into the scan that assigns the Lines offsets
+  typedef uint32_t T;
+  const Counters* ctr;
+  Counters* ctr_w;
+  const uint32_t* loc_fid;
+  FrameTableV1 ft;
+  StLocOut o;
+  uint32_t unknown_type_cid, missing_fn_cid;
+  __device__ uint32_t n() const { return ctr->n_locations; }
+  __device__ uint32_t value(uint32_t i) const { uint32_t fid = loc_fid[i]; return fid == kNull ? 1u : (ft.fn_cid[fid] != kNull ? 1u : 0u); }
+  __device__ void emit(uint32_t i, uint32_t ex, uint32_t v) const {
+    uint32_t fid = loc_fid[i];
+    o.line_off[i] = (int)ex;
+    o.has_line[i] = (uint8_t)v;
+    if (fid == kNull) {  // the "missing stacktrace" placeholder (:1557-1571)
+      o.address[i] = 0ull; o.type_key[i] = unknown_type_cid; o.map_key[i] = kNull; o.bid_key[i] = kNull;
+      o.line_no[ex] = 0ll; o.column[ex] = 0ull; o.fn_key[ex] = missing_fn_cid; o.file_key[ex] = kNull;
+      return;
+    }
+    o.address[i] = ft.addr[fid]; o.type_key[i] = ft.type_cid[fid]; o.map_key[i] = ft.map_cid[fid]; o.bid_key[i] = ft.bid_cid[fid];
+    if (v) { o.line_no[ex] = (long long)ft.line[fid]; o.column[ex] = ft.col[fid]; o.fn_key[ex] = ft.fn_cid[fid]; o.file_key[ex] = ft.file_cid[fid]; }
+  }
+  __device__ void total(int, uint32_t t) const { ctr_w->n_lines = t; o.line_off[n()] = (int)t; }
+};
+// run-end encoding of a materialised key column (BinaryDictionaryRunEndBuilder, arrow.go:97-131): a run starts
+// at row 0, at every null (AppendNull always opens a run) and wherever the key changes. blockIdx.y = column.
+struct StRunCol { const uint32_t* keys; const uint32_t* n_ptr; uint32_t* run_key; int* run_end; };
+struct StRunF {
+  typedef uint32_t T;
+  StRunCol c[4];
+  Counters* ctr_w;
+  __device__ uint32_t n() const { return *c[blockIdx.y].n_ptr; }
+  __device__ uint32_t value(uint32_t i) const {
+    const uint32_t* k = c[blockIdx.y].keys;
+    uint32_t cur = k[i];
+    return (i == 0 || cur == kNull || cur != k[i - 1]) ? 1u : 0u;
+  }
+  __device__ void emit(uint32_t i, uint32_t ex, uint32_t v) const {
+    if (!v) return;
+    const StRunCol& col = c[blockIdx.y];
+    col.run_key[ex] = col.keys[i];
+    if (ex) col.run_end[ex - 1] = (int)i;
+  }
+  __device__ void total(int job, uint32_t t) const {
+    ctr_w->n_runs[job] = t;
+    if (t) c[job].run_end[t - 1] = (int)*c[job].n_ptr;
+  }
+};
 
 }  // namespace pa

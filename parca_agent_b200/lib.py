@@ -18,7 +18,7 @@ EXPORTS = [
     "pa_agg_create", "pa_agg_destroy", "pa_agg_last_error", "pa_agg_abi_version", "pa_agg_register_strings",
     "pa_agg_register_frames", "pa_agg_register_labelsets", "pa_agg_acquire", "pa_agg_commit", "pa_agg_submit",
     "pa_agg_flush", "pa_agg_release", "pa_agg_stage", "pa_agg_process", "pa_agg_collect", "pa_agg_last_kernel_ms",
-    "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_fix_truncation", "pa_xxh64",
+    "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_agg_stacktraces", "pa_agg_last_stack_ids", "pa_fix_truncation", "pa_xxh64",
 ]
 
 
@@ -57,6 +57,8 @@ def lib():
         L.pa_agg_last_kernel_ms.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), u32p]
         L.pa_agg_debug_stack_ids.argtypes = [vp, vp, C.c_uint64]
         L.pa_agg_debug_stack_counts.argtypes = [vp, vp, C.c_uint64]
+        L.pa_agg_stacktraces.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(abi.PaAggResult)]
+        L.pa_agg_last_stack_ids.argtypes = [vp, vp, C.c_uint64]
         L.pa_fix_truncation.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64]
         L.pa_fix_truncation.restype = C.c_int64
         L.pa_xxh64.argtypes = [vp, C.c_uint64, C.c_uint64]
@@ -88,14 +90,16 @@ class Aggregator:
     """Thin object wrapper over one pa_agg handle."""
 
     def __init__(self, device=0, hash_mode=abi.PA_HASH_XXH64X2, label_flags=0, samples_per_second=19, external_labels=(),
-                 max_samples=1 << 20, max_frames=0, chunk_samples=0, schema=abi.PA_SCHEMA_V2):
+                 max_samples=1 << 20, max_frames=0, chunk_samples=0, schema=abi.PA_SCHEMA_V2, stack_cache_entries=0, stack_cache_frames=0,
+                 unknown_frame_type_sid=0):
         L = lib()
         ext = (abi.PaLabelPair * max(1, len(external_labels)))()
         for i, (n, v) in enumerate(external_labels):
             ext[i].name_sid, ext[i].value_sid = int(n), int(v)
         cfg = abi.PaAggConfig(abi_version=abi.PA_ABI_VERSION, device=device, hash_mode=hash_mode, label_flags=label_flags,
                               samples_per_second=samples_per_second, n_external_labels=len(external_labels), external_labels=ext,
-                              max_samples=max_samples, max_frames=max_frames, chunk_samples=chunk_samples, schema=schema)
+                              max_samples=max_samples, max_frames=max_frames, chunk_samples=chunk_samples, schema=schema,
+                              stack_cache_entries=stack_cache_entries, stack_cache_frames=stack_cache_frames, unknown_frame_type_sid=unknown_frame_type_sid)
         h = C.c_void_p()
         rc = L.pa_agg_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -173,6 +177,19 @@ class Aggregator:
     def collect(self):
         return self._result(lib().pa_agg_collect)
 
+    def stacktraces(self, ids):
+        """v1: the stacktrace record for the concatenated 16-byte ids (buildStacktraceRecord)."""
+        ids = bytes(ids)
+        assert len(ids) % 16 == 0
+        raw = abi.PaAggResult()
+        self._ck(lib().pa_agg_stacktraces(self.h, ids, len(ids) // 16, C.byref(raw)))
+        return Result(raw)
+
+    def last_stack_ids(self, n):
+        out = np.zeros((n, 16), dtype=np.uint8)
+        self._ck(lib().pa_agg_last_stack_ids(self.h, out.ctypes.data, n))
+        return out
+
     def kernel_ms(self, name):
         ms, n = C.c_double(), C.c_uint32()
         self._ck(lib().pa_agg_last_kernel_ms(self.h, name.encode(), C.byref(ms), C.byref(n)))
@@ -189,12 +206,12 @@ class Aggregator:
         return out
 
 
-def from_workload(w, device=0, max_samples=None, max_frames=None, chunk_samples=0):
+def from_workload(w, device=0, max_samples=None, max_frames=None, chunk_samples=0, **kw):
     """Aggregator with the workload's dictionaries registered (string id 0 == "" is implicit)."""
     n = max(1, w.n if max_samples is None else max_samples)
     nf = max(1, w.n_frame_ids if max_frames is None else max_frames)
     a = Aggregator(device=device, hash_mode=w.hash_mode, label_flags=w.label_flags, samples_per_second=w.samples_per_second,
-                   external_labels=w.external_labels, max_samples=n, max_frames=nf, chunk_samples=chunk_samples, schema=getattr(w, "schema", 0))
+                   external_labels=w.external_labels, max_samples=n, max_frames=nf, chunk_samples=chunk_samples, schema=getattr(w, "schema", 0), **kw)
     first = a.register_strings(w.strings[1:])
     assert first == 1, first
     a.register_frames(w.frames)

@@ -151,6 +151,16 @@ def _frame_table(rng, st, P, native, kernel, interp_name):
     fr["function_name_sid"] = np.where(sym & ~unsym, fname, 0)
     fr["source_file_sid"] = np.where((kind == abi.PA_FRAME_INTERP) & ~unsym, ifile[fidx % len(ifile)], 0)
     fr["source_line"] = np.where(sym, rng.integers(1, 5000, P), 0)
+    # v1-only attributes, derived without touching the generator so every v2 workload stays byte-identical:
+    # a source column on symbolised frames, and a GNU build id + mapping file name on a quarter of the interpreted ones
+    ix = np.arange(P, dtype=np.uint64)
+    fr["source_column"] = np.where(sym, (splitmix64(ix + np.uint64(77)) % np.uint64(160)).astype(np.uint32), 0)
+    libs = np.array([st.sid("/usr/lib/%s/lib%s-ext-%02d.so" % (interp_name, interp_name, i)) for i in range(16)], dtype=np.uint32)
+    gnus = np.array([st.sid("%040x" % (0x9e0000 + i * 104729)) for i in range(16)], dtype=np.uint32)
+    has_gnu = (kind == abi.PA_FRAME_INTERP) & (ix % np.uint64(4) == 0)
+    pick = (splitmix64(ix + np.uint64(991)) % np.uint64(16)).astype(np.int64)
+    fr["mapping_file_name_sid"] = np.where(has_gnu, libs[pick], 0)
+    fr["gnu_build_id_sid"] = np.where(has_gnu, gnus[pick], 0)
     return fr
 
 
@@ -294,7 +304,7 @@ def edge_workload(seed=7, n=600, hash_mode=abi.PA_HASH_PROVIDED, label_flags=0, 
 
     def add(kind, **kw):
         d = dict(kind=kind, flags=0, type_name_sid=0, address_or_lineno=0, function_name_sid=0, source_file_sid=0, source_line=0,
-                 exec_file_name_sid=0, exec_build_id_sid=0, file_id_hi=0, file_id_lo=0)
+                 exec_file_name_sid=0, exec_build_id_sid=0, file_id_hi=0, file_id_lo=0, source_column=0, mapping_file_name_sid=0, gnu_build_id_sid=0)
         d.update(kw)
         descs.append(d)
 
@@ -305,13 +315,15 @@ def edge_workload(seed=7, n=600, hash_mode=abi.PA_HASH_PROVIDED, label_flags=0, 
             exec_build_id_sid=e[1], file_id_hi=0x0123456789abcdef + i, file_id_lo=0xfedcba9876543210 - i)
     for i in range(10):  # kernel: named/unnamed, module known/unknown
         add(abi.PA_FRAME_KERNEL, flags=(3 if i % 3 == 0 else 0), type_name_sid=t["kernel"], address_or_lineno=0xffffffff81000000 + i,
-            function_name_sid=(fnames[i % len(fnames)] if i % 4 else 0), source_line=100 + i, exec_file_name_sid=exe[2][0])
+            function_name_sid=(fnames[i % len(fnames)] if i % 4 else 0), source_line=100 + i, exec_file_name_sid=exe[2][0], source_column=(7 * i) % 5)
     add(abi.PA_FRAME_ABORT, type_name_sid=t["abort-marker"], address_or_lineno=0)
     add(abi.PA_FRAME_ABORT, type_name_sid=t["abort-marker"], address_or_lineno=1)
     add(abi.PA_FRAME_OOMPROF, type_name_sid=t["native"], address_or_lineno=0x77, source_file_sid=files[1], function_name_sid=st.sid("buildid-oom"))
-    for i in range(14):  # interpreted: python/ruby, with/without function name, empty file path
+    gnu = [(st.sid("/usr/lib/libpython3.11.so.1.0"), st.sid("gnubuildid-aaaa")), (st.sid("/usr/lib/libruby.so.3.2"), st.sid("gnubuildid-bbbb"))]
+    for i in range(14):  # interpreted: python/ruby, with/without function name, empty file path, with/without a GNU build id (v1)
         add(abi.PA_FRAME_INTERP, type_name_sid=t["python" if i % 2 else "ruby"], address_or_lineno=10 + i,
-            function_name_sid=(fnames[(i * 3) % len(fnames)] if i % 5 else 0), source_file_sid=files[i % 3], source_line=i)
+            function_name_sid=(fnames[(i * 3) % len(fnames)] if i % 5 else 0), source_file_sid=files[i % 3], source_line=i, source_column=i % 4,
+            mapping_file_name_sid=(gnu[i % 2][0] if i % 3 == 0 else 0), gnu_build_id_sid=(gnu[i % 2][1] if i % 3 == 0 else 0))
     frames = np.zeros(len(descs), dtype=abi.FRAME_DTYPE)
     for i, d in enumerate(descs):
         for k, v in d.items():

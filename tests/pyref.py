@@ -523,3 +523,175 @@ def expected_schema_v1(label_names):
     fields += [pa.field(n, lab, False) for n in ("producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality")]
     fields += [pa.field("period", ri, False), pa.field("duration", ri, False), pa.field("timestamp", ri, False)]
     return pa.schema(fields, metadata={"parca_write_schema_version": "v1"})
+
+
+# ---- v1 stacktrace record: buildStacktraceRecord (reporter/parca_reporter.go:1545-1739) ----------
+def known_stacks(w, known=None):
+    """The `stacks` LRU after ingesting w (:224-227): hash bytes -> frame ids of the FIRST occurrence."""
+    known = {} if known is None else known
+    frame_ids = w.frame_ids
+    for r in range(w.n):
+        h = w.hdrs[r]
+        fr = [int(x) for x in frame_ids[int(h["frame_off"]):int(h["frame_off"]) + int(h["nframes"])]]
+        if w.hash_mode == abi.PA_HASH_XXH64X2:
+            key = (xxh64_words(fr, 0), xxh64_words(fr, abi.PA_XXH_SEED_LO))
+        else:
+            key = (int(h["hash_hi"]), int(h["hash_lo"]))
+        kb = key[0].to_bytes(8, "big") + key[1].to_bytes(8, "big")
+        if kb not in known:
+            known[kb] = fr
+    return known
+
+
+class _List:  # array.ListBuilder
+    def __init__(self):
+        self.offsets, self.valid = [], []
+
+    def append(self, v, child_len):
+        self.offsets.append(child_len)
+        self.valid.append(bool(v))
+
+    def out(self, child_len):
+        return {"offsets": self.offsets + [child_len], "valid": self.valid}
+
+
+def reference_stacktraces(w, ids, known, unknown_type=b"unknown"):
+    S = lambda sid: w.strings[int(sid)]  # noqa: E731
+    is_complete, loc_list, lines = [], _List(), _List()
+    address, line_no, column, start_line = [], [], [], []
+    frame_type, mapping_file, mapping_build_id, fn_filename = _DictRee(), _DictRee(), _DictRee(), _DictRee()
+    fn_name, fn_sys = _Dict(), _Dict()
+
+    def line(n, col, fn, filename):
+        lines.append(True, len(line_no))
+        line_no.append(n)
+        column.append(col)
+        fn_name.append(fn)
+        fn_sys.append(b"")
+        if filename is None:
+            fn_filename.null()
+        else:
+            fn_filename.append(filename)
+        start_line.append(0)
+
+    for sid in ids:
+        complete = True
+        if sid not in known:  # :1556-1573
+            loc_list.append(True, len(address))
+            address.append(0)
+            frame_type.append(unknown_type)
+            mapping_file.null()
+            mapping_build_id.null()
+            line(0, 0, b"missing stacktrace", None)
+            is_complete.append(False)
+            continue
+        trace = known[sid]
+        loc_list.append(len(trace) != 0, len(address))
+        for fid in trace:
+            f = w.frames[fid]
+            address.append(int(f["address_or_lineno"]))
+            kind = int(f["kind"])
+            exists = (int(f["flags"]) & 3) == 3
+            if kind == abi.PA_FRAME_ABORT:
+                frame_type.append(S(f["type_name_sid"]))
+                mapping_file.append(b"agent-internal-error-frame")
+                mapping_build_id.null()
+                line(0, 0, b"aborted", None)
+                continue
+            if kind == abi.PA_FRAME_NATIVE:
+                frame_type.append(S(f["type_name_sid"]))
+                if exists:
+                    mapping_file.append(S(f["exec_file_name_sid"]))
+                    bid = S(f["exec_build_id_sid"])
+                    mapping_build_id.append(bid if bid else b"%016x%016x" % (int(f["file_id_hi"]), int(f["file_id_lo"])))
+                else:
+                    mapping_file.append(b"UNKNOWN")
+                    mapping_build_id.null()
+                    complete = False
+                lines.append(False, len(line_no))
+            elif kind == abi.PA_FRAME_KERNEL:
+                frame_type.append(S(f["type_name_sid"]))
+                module = S(f["exec_file_name_sid"]) if exists else b"vmlinux"
+                if S(f["function_name_sid"]):
+                    symbol, n = S(f["function_name_sid"]), int(f["source_line"])
+                else:
+                    symbol, n = b"UNKNOWN", 0
+                    complete = False
+                mapping_build_id.null()
+                line(n, int(f["source_column"]), symbol, module)
+                mapping_file.append(b"[kernel.kallsyms]")
+            elif kind == abi.PA_FRAME_OOMPROF:
+                frame_type.append(S(f["type_name_sid"]))
+                mapping_file.append(S(f["source_file_sid"]))
+                mapping_build_id.append(S(f["function_name_sid"]))
+                lines.append(False, len(line_no))
+                complete = False
+            else:
+                frame_type.append(S(f["type_name_sid"]))
+                if S(f["function_name_sid"]):
+                    name, path, n = S(f["function_name_sid"]), S(f["source_file_sid"]), int(f["source_line"])
+                else:
+                    name, path, n = b"UNREPORTED", b"UNREPORTED", 0
+                    complete = False
+                if not path:
+                    path = b"UNKNOWN"
+                if S(f["gnu_build_id_sid"]):
+                    mapping_file.append(S(f["mapping_file_name_sid"]))
+                    mapping_build_id.append(S(f["gnu_build_id_sid"]))
+                else:
+                    mapping_file.append(S(f["type_name_sid"]))
+                    mapping_build_id.null()
+                line(n, int(f["source_column"]), name, path)
+        is_complete.append(complete)
+    nloc = len(address)
+    zero_ree = {"run_ends": [nloc] if nloc else [], "values": [0]}  # AppendN(0, numMappings), arrow.go:231-238
+    return {
+        "rows": len(ids), "stacktrace_id": list(ids), "is_complete": is_complete,
+        "locations": dict(loc_list.out(nloc), address=address, frame_type=frame_type.out(), mapping_start=zero_ree, mapping_limit=zero_ree,
+                          mapping_offset=zero_ree, mapping_file=mapping_file.out(), mapping_build_id=mapping_build_id.out(),
+                          lines=dict(lines.out(len(line_no)), line=line_no, column=column, function_name=fn_name.out(),
+                                     function_system_name=fn_sys.out(), function_filename=fn_filename.out(), function_start_line=start_line)),
+    }
+
+
+def extract_stacktraces(batch):
+    if isinstance(batch, (bytes, bytearray)):  # the stream holds exactly one record batch, possibly with zero rows
+        batch = list(pa.ipc.open_stream(batch))[0]
+    col = {f.name: batch.column(i) for i, f in enumerate(batch.schema)}
+
+    def dict_ree(a):
+        d = _dict_out(a.values)
+        return {"run_ends": a.run_ends.to_pylist(), "indices": d["indices"], "dict": d["dict"]}
+
+    def lst(a):
+        return {"offsets": a.offsets.to_pylist(), "valid": a.is_valid().to_pylist()}
+
+    ll = col["locations"]
+    loc = ll.values
+    f = {loc.type.field(i).name: loc.field(i) for i in range(loc.type.num_fields)}
+    lines = f["lines"]
+    ln = lines.values
+    g = {ln.type.field(i).name: ln.field(i) for i in range(ln.type.num_fields)}
+    return {
+        "rows": batch.num_rows, "stacktrace_id": col["stacktrace_id"].to_pylist(), "is_complete": col["is_complete"].to_pylist(),
+        "locations": dict(lst(ll), address=f["address"].to_pylist(), frame_type=dict_ree(f["frame_type"]), mapping_start=_ree_out(f["mapping_start"]),
+                          mapping_limit=_ree_out(f["mapping_limit"]), mapping_offset=_ree_out(f["mapping_offset"]),
+                          mapping_file=dict_ree(f["mapping_file"]), mapping_build_id=dict_ree(f["mapping_build_id"]),
+                          lines=dict(lst(lines), line=g["line"].to_pylist(), column=g["column"].to_pylist(), function_name=_dict_out(g["function_name"]),
+                                     function_system_name=_dict_out(g["function_system_name"]), function_filename=dict_ree(g["function_filename"]),
+                                     function_start_line=g["function_start_line"].to_pylist())),
+    }
+
+
+def expected_schema_stacktraces():
+    db = pa.dictionary(pa.uint32(), pa.binary())
+    rd = pa.run_end_encoded(pa.int32(), db)
+    ru = pa.run_end_encoded(pa.int32(), pa.uint64())
+    line = pa.struct([pa.field("line", pa.int64(), False), pa.field("column", pa.uint64(), False), pa.field("function_name", db, False),
+                      pa.field("function_system_name", db, False), pa.field("function_filename", rd, False),
+                      pa.field("function_start_line", pa.int64(), False)])
+    loc = pa.struct([pa.field("address", pa.uint64(), False), pa.field("frame_type", rd, False), pa.field("mapping_start", ru, False),
+                     pa.field("mapping_limit", ru, False), pa.field("mapping_offset", ru, False), pa.field("mapping_file", rd, False),
+                     pa.field("mapping_build_id", rd, False), pa.field("lines", pa.list_(pa.field("item", line, True)), False)])
+    return pa.schema([pa.field("stacktrace_id", pa.binary(), False), pa.field("is_complete", pa.bool_(), False),
+                      pa.field("locations", pa.list_(pa.field("item", loc, True)), False)], metadata={"parca_write_schema_version": "v1"})

@@ -414,3 +414,127 @@ def test_ragged_depths(oracle, gpu):
     """Every stack has its own depth (1..127 frames): remainder tiers of the hash kernel, odd offsets, all variants."""
     w = synth.ragged(n=150_000, u=4_000, p=8_192)
     assert_same(oracle, gpu, w)
+
+
+# ---- v1 stacktrace record (buildStacktraceRecord + the device-resident store of known stacks) ----
+def missing_ids(k):
+    return [bytes([0xEE, i]) * 8 for i in range(k)]
+
+
+def assert_same_stacktraces(o, a, ids):
+    """o: oracle.Oracle, a: Aggregator, both fed the same intervals; ids: list of 16-byte ids."""
+    want, nloc = o.stacktraces(b"".join(ids))
+    r = a.stacktraces(b"".join(ids))
+    got = r.ipc_bytes()
+    if got != want:
+        d = pyref.diff(pyref.extract_stacktraces(want), pyref.extract_stacktraces(got))
+        raise AssertionError("stacktrace record bytes differ (len %d vs %d); first logical difference: %s" % (len(want), len(got), d))
+    assert (r.n_rows, r.n_locations) == (len(ids), nloc)
+    return r
+
+
+def feed_both(oracle, gpu, w, o=None, a=None, **kw_agg):
+    """One v1 interval through both sides; returns (o, a, this interval's unique ids in first-occurrence order)."""
+    as_v1(w)
+    o = o or oracle.Oracle(w)
+    a = a or gpu.from_workload(w, **kw_agg)
+    o.ingest(w.hdrs, w.frame_ids)
+    want, st = o.flush()
+    gpu.load(a, w)
+    r = a.flush()
+    assert r.ipc_bytes() == want
+    ids = a.last_stack_ids(r.n_unique_stacks)
+    dict_ids = pa.ipc.open_stream(want).read_all().column("stacktrace_id").chunk(0).values.dictionary.to_pylist() if want else []
+    assert [bytes(x) for x in ids] == dict_ids  # == the ids the reference walks at parca_reporter.go:1307-1328
+    return o, a, dict_ids
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("mode", [abi.PA_HASH_PROVIDED, abi.PA_HASH_XXH64X2])
+def test_stacktrace_record_edge(oracle, gpu, seed, mode):
+    o, a, ids = feed_both(oracle, gpu, synth.edge_workload(seed=seed, hash_mode=mode))
+    assert_same_stacktraces(o, a, ids)                                   # offline mode: every new stack of the interval
+    mixed = list(ids)
+    for i, m in enumerate(missing_ids(4)):
+        mixed.insert((5 * i) % (len(mixed) + 1), m)
+    assert_same_stacktraces(o, a, mixed + ids[:3])                       # unknown ids and repeats, as a server may ask
+    assert_same_stacktraces(o, a, list(reversed(ids)))
+    a.close(); o.close()
+
+
+def test_stacktrace_record_degenerate(oracle, gpu):
+    w = synth.edge_workload(seed=5)
+    o, a, ids = feed_both(oracle, gpu, w)
+    assert_same_stacktraces(o, a, [])                                    # an empty record is still written (:1332)
+    assert_same_stacktraces(o, a, missing_ids(1))
+    assert_same_stacktraces(o, a, missing_ids(70))
+    known = pyref.known_stacks(w)
+    empties = [k for k, v in known.items() if len(v) == 0]
+    assert empties
+    assert_same_stacktraces(o, a, empties)                               # zero locations, null list entries only
+    assert_same_stacktraces(o, a, empties + ids[:1] + empties)
+    a.close(); o.close()
+
+
+def test_stacktrace_record_configs(oracle, gpu):
+    for w in (synth.config1(), synth.config1(hash_mode=abi.PA_HASH_PROVIDED).head(20_000), synth.ragged(n=30_000, u=2_000, p=4_096)):
+        o, a, ids = feed_both(oracle, gpu, w)
+        r = assert_same_stacktraces(o, a, ids)
+        assert r.n_locations > len(ids) and r.gpu_launches > 0
+        assert_same_stacktraces(o, a, ids[::7] + missing_ids(2))
+        a.close(); o.close()
+
+
+def test_stacktrace_store_persists_across_intervals(oracle, gpu):
+    """The store is the `stacks` LRU: first occurrence wins (also across intervals), later intervals only add."""
+    w = synth.edge_workload(seed=41, n=3000)
+    o, a, ids1 = feed_both(oracle, gpu, w.head(1200), max_samples=4000, max_frames=40000)
+    _, _, ids2 = feed_both(oracle, gpu, w.rows(np.arange(1200, 3000)), o=o, a=a)
+    assert set(ids1) & set(ids2)
+    both = ids1 + [i for i in ids2 if i not in set(ids1)]
+    assert_same_stacktraces(o, a, both + missing_ids(2))
+    _, _, ids3 = feed_both(oracle, gpu, w.head(0), o=o, a=a)               # an empty interval changes nothing
+    assert ids3 == []
+    assert_same_stacktraces(o, a, both)
+    a.close(); o.close()
+
+
+def test_stacktrace_store_overflow_starts_a_new_generation(oracle, gpu):
+    """Out of entries (or frame space): the store is cleared and refilled from the current batch, so it then behaves
+    like a reporter that has only seen that batch — older stacks come back as "missing stacktrace" rows, exactly what
+    the reference answers for an evicted LRU entry (:1556-1573)."""
+    big = synth.config2(n=12_000, u=10_000, p=8_192)                      # 64-frame stacks, ~3.6k distinct per 4.5k rows
+    w1, w2 = big.head(4500), big.rows(np.arange(6000, 10_500))
+    for kw_agg in (dict(stack_cache_entries=4096), dict(stack_cache_entries=1 << 16, stack_cache_frames=4096 * 64)):
+        o, a, ids1 = feed_both(oracle, gpu, w1, max_samples=8000, max_frames=8000 * 64, **kw_agg)
+        assert 2048 < len(ids1) <= 4096
+        assert_same_stacktraces(o, a, ids1)
+        _, _, ids2 = feed_both(oracle, gpu, w2, o=o, a=a)
+        assert len(set(ids1) | set(ids2)) > 4096
+        o2 = oracle.Oracle(as_v1(w2))                                     # a reporter that only ever saw the second batch
+        o2.ingest(w2.hdrs, w2.frame_ids)
+        o2.flush()
+        assert_same_stacktraces(o2, a, ids2 + ids1[:50] + missing_ids(1))
+        a.close(); o.close(); o2.close()
+
+
+def test_stacktrace_custom_unknown_type_and_errors(oracle, gpu):
+    w = as_v1(synth.edge_workload(seed=8))
+    sid = len(w.strings)
+    w.strings = list(w.strings) + [b"unknown-frame-type-from-libpf"]
+    w.unknown_frame_type_sid = sid
+    o, a, ids = feed_both(oracle, gpu, w, unknown_frame_type_sid=sid)
+    assert_same_stacktraces(o, a, missing_ids(2) + ids[:5])
+    gpu.load(a, w)
+    a.stage()
+    with pytest.raises(gpu.PaError) as e:                                  # the staged batch still owns the scratch arena
+        a.stacktraces(b"".join(ids[:1]))
+    assert e.value.code == -22
+    a.process(); a.collect()
+    a.close(); o.close()
+    w2 = synth.edge_workload(seed=8)                                      # v2 aggregators keep no store
+    a2 = gpu.from_workload(w2)
+    with pytest.raises(gpu.PaError) as e:
+        a2.stacktraces(b"\x00" * 16)
+    assert e.value.code == -22
+    a2.close()

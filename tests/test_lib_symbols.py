@@ -4,6 +4,7 @@ import ctypes
 import json
 import os
 import re
+import subprocess
 
 import numpy as np
 
@@ -28,10 +29,18 @@ def test_exports_every_declared_symbol():
     assert L.pa_agg_abi_version() == abi.PA_ABI_VERSION
 
 
-def test_struct_sizes_match_header():
-    assert abi.HDR_DTYPE.itemsize == 64 and abi.FRAME_DTYPE.itemsize == 56
-    assert ctypes.sizeof(abi.PaAggConfig) == 56
-    assert ctypes.sizeof(abi.PaAggResult) == 96
+def test_struct_sizes_match_header(tmp_path):
+    """The numpy/ctypes mirrors against what a C compiler makes of include/parcaagg.h (sizes and a few offsets)."""
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "parcaagg.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                   "sizeof(pa_sample_hdr), sizeof(pa_frame_desc), sizeof(pa_agg_config), sizeof(pa_agg_result),"
+                   "offsetof(pa_frame_desc, file_id_hi), offsetof(pa_frame_desc, gnu_build_id_sid), offsetof(pa_agg_config, stack_cache_entries));return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert got == [abi.HDR_DTYPE.itemsize, abi.FRAME_DTYPE.itemsize, ctypes.sizeof(abi.PaAggConfig), ctypes.sizeof(abi.PaAggResult),
+                   abi.FRAME_DTYPE.fields["file_id_hi"][1], abi.FRAME_DTYPE.fields["gnu_build_id_sid"][1], abi.PaAggConfig.stack_cache_entries.offset]
+    assert got[:2] == [64, 64]
 
 
 def test_host_xxh64_known_answers():

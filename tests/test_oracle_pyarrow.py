@@ -114,3 +114,59 @@ def test_v1_config1_prefix(oracle):
     row = t.slice(0, 1).to_pylist()[0]
     assert row["period"] == 10**9 // 19 and row["duration"] == 10**9 and row["producer"] == b"parca_agent" and row["temporality"] == b"delta"
     assert len(row["stacktrace_id"]) == 16
+
+
+# ---- v1 stacktrace record (buildStacktraceRecord, parca_reporter.go:1545-1739) -------------------
+def stacktrace_ids(w, known, extra_missing=3):
+    """The ids a server would ask for: every stack of the batch in first-occurrence order, plus ids nobody has seen."""
+    ids = list(known.keys())
+    for i in range(extra_missing):
+        ids.insert((i * 7) % (len(ids) + 1), bytes([0xEE, i]) * 8)
+    return ids
+
+
+def check_stacktraces(oracle, w, ids=None):
+    w.schema = abi.PA_SCHEMA_V1
+    o = oracle.Oracle(w)
+    o.ingest(w.hdrs, w.frame_ids)
+    o.flush()
+    known = pyref.known_stacks(w)
+    ids = stacktrace_ids(w, known) if ids is None else ids
+    data, nloc = o.stacktraces(b"".join(ids))
+    o.close()
+    t = pa.ipc.open_stream(data).read_all()
+    want = pyref.reference_stacktraces(w, ids, known)
+    got = pyref.extract_stacktraces(data)
+    d = pyref.diff(want, got)
+    assert d is None, d
+    assert t.schema.equals(pyref.expected_schema_stacktraces(), check_metadata=True)
+    assert nloc == len(want["locations"]["address"])
+    return t, want
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("mode", [abi.PA_HASH_PROVIDED, abi.PA_HASH_XXH64X2])
+def test_stacktrace_record_edge(oracle, seed, mode):
+    t, want = check_stacktraces(oracle, synth.edge_workload(seed=seed, hash_mode=mode))
+    t.validate(full=True)
+    assert not all(want["is_complete"]) and any(want["is_complete"])
+    assert b"missing stacktrace" in want["locations"]["lines"]["function_name"]["dict"]
+    assert False in want["locations"]["valid"]  # an empty stack is a null list entry (:1576-1580)
+
+
+def test_stacktrace_record_config1(oracle):
+    t, want = check_stacktraces(oracle, synth.config1().head(400))
+    t.validate(full=True)
+    row = t.slice(1, 1).to_pylist()[0]
+    assert len(row["stacktrace_id"]) == 16 and len(row["locations"]) == 16
+    assert row["locations"][0]["mapping_start"] == 0 and row["locations"][0]["mapping_limit"] == 0
+
+
+def test_stacktrace_record_degenerate(oracle):
+    w = synth.edge_workload(seed=5)
+    check_stacktraces(oracle, w, ids=[])                      # no new stacks this interval: an empty record is still written (:1332)
+    check_stacktraces(oracle, w, ids=[b"\x01" * 16])           # only a missing stack
+    known = pyref.known_stacks(w)
+    empties = [k for k, v in known.items() if len(v) == 0]
+    assert empties
+    check_stacktraces(oracle, w, ids=empties)                 # only empty stacks: zero locations, null list entries
