@@ -31,6 +31,8 @@ struct AggSink final : Sink {
   int Submit(const pa_sample_hdr& hdr, const uint64_t* frame_ids) override { return pa_agg_submit(a, &hdr, frame_ids, 1); }
   int Flush(pa_agg_result* out) override { return pa_agg_flush(a, out); }
   void Release(pa_agg_result* res) override { pa_agg_release(a, res); }
+  int LastStackIds(uint8_t* out, uint64_t n) override { return pa_agg_last_stack_ids(a, out, n); }
+  int Stacktraces(const uint8_t* ids, uint64_t n, pa_agg_result* out) override { return pa_agg_stacktraces(a, ids, n, out); }
 };
 }  // namespace
 Sink* NewAggSink(pa_agg* agg) { return new AggSink(agg); }
@@ -97,7 +99,8 @@ uint64_t ParcaReporter::frameId(const Frame& f) {
   auto put = [&key](const void* p, size_t n) { key.append((const char*)p, n); };
   put(&f.Type.kind, 1); key += f.Type.name; key.push_back('\0');
   key += f.FunctionName; key.push_back('\0'); key += f.SourceFile; key.push_back('\0');
-  put(&f.SourceLine, 4); put(&f.AddressOrLineno, 8);
+  put(&f.SourceLine, 4); put(&f.SourceColumn, 4); put(&f.AddressOrLineno, 8);
+  key += f.MappingFileName; key.push_back('\0'); key += f.MappingGnuBuildID; key.push_back('\0');
   uint8_t mv = (uint8_t)((f.MappingValid ? 1 : 0) | (f.MappingHasFile ? 2 : 0));
   put(&mv, 1); put(&f.MappingFileID, sizeof(FileID));
   auto it = frames_.find(key);
@@ -111,6 +114,11 @@ uint64_t ParcaReporter::frameId(const Frame& f) {
   d.function_name_sid = sid(f.FunctionName);
   d.source_file_sid = sid(f.SourceFile);
   d.source_line = f.SourceLine;
+  d.source_column = f.SourceColumn;
+  if (f.MappingValid && !f.MappingGnuBuildID.empty()) {  // :1716
+    d.mapping_file_name_sid = sid(f.MappingFileName);
+    d.gnu_build_id_sid = sid(f.MappingGnuBuildID);
+  }
   d.file_id_hi = f.MappingFileID.hi;
   d.file_id_lo = f.MappingFileID.lo;
   const bool has_file = f.MappingValid && f.MappingHasFile;  // :456-462
@@ -241,8 +249,32 @@ int64_t ParcaReporter::FlushOnce() {
     sampleWrites += res.n_rows;               // :1869
     sampleWriteRequestBytes += res.ipc_len;   // :1870
   }
+  const uint64_t n_unique = res.n_unique_stacks;
   sink_->Release(&res);
+  if (rows && cfg_.offlineV1Stacktraces) {
+    // :1300-1349 — walk the sample record's stacktrace_id dictionary in order, keep the ids this log has not
+    // seen, and write their stacktrace record right behind the sample record (even when there are none)
+    std::vector<uint8_t> ids(n_unique * 16), fresh;
+    if ((rc = sink_->LastStackIds(ids.data(), n_unique)) != PA_OK) { droppedBatches++; return rc; }
+    for (uint64_t i = 0; i < n_unique; i++) {
+      std::string key((const char*)ids.data() + 16 * i, 16);
+      bool& seen = logged_stacks_[key];
+      if (seen) continue;
+      seen = true;
+      fresh.insert(fresh.end(), key.begin(), key.end());
+    }
+    pa_agg_result st;
+    if ((rc = sink_->Stacktraces(fresh.data(), fresh.size() / 16, &st)) != PA_OK) { droppedBatches++; return rc; }
+    if (cfg_.onBatch) cfg_.onBatch(st.ipc, st.ipc_len, st.n_rows);
+    stacktraceWriteRequestBytes += st.ipc_len;  // :1351
+    sink_->Release(&st);
+  }
   return rows;
+}
+
+void ParcaReporter::ResetLoggedStacks() {
+  std::lock_guard<std::mutex> g(mu_);
+  logged_stacks_.clear();
 }
 
 int ParcaReporter::Start() {

@@ -41,11 +41,12 @@ struct FrameType {
 struct Frame {  // libpf.Frame — the dedup key of appendLocationV2 (parca_reporter.go:421)
   FrameType Type;
   std::string FunctionName, SourceFile;
-  uint32_t SourceLine = 0;
+  uint32_t SourceLine = 0, SourceColumn = 0;
   uint64_t AddressOrLineno = 0;
   bool MappingValid = false;     // frame.Mapping.Valid()
   bool MappingHasFile = false;   // m.File != (libpf.FrameMappingFile{})
   FileID MappingFileID;          // mf.FileID
+  std::string MappingFileName, MappingGnuBuildID;  // mf.FileName / mf.GnuBuildID (v1 stacktrace record, :1716-1719)
 };
 struct Trace {  // libpf.Trace
   TraceHash Hash;
@@ -76,6 +77,9 @@ struct Sink {
   virtual int Submit(const pa_sample_hdr& hdr, const uint64_t* frame_ids) = 0;
   virtual int Flush(pa_agg_result* out) = 0;
   virtual void Release(pa_agg_result* res) = 0;
+  // v1 schema only: the ids of the last flushed batch's unique stacks, and the stacktrace record for a set of ids
+  virtual int LastStackIds(uint8_t* /*out*/, uint64_t /*n*/) { return PA_EINVAL; }
+  virtual int Stacktraces(const uint8_t* /*ids*/, uint64_t /*n*/, pa_agg_result* /*out*/) { return PA_EINVAL; }
 };
 Sink* NewAggSink(pa_agg* agg);  // owns nothing; forwards to the C ABI
 
@@ -89,6 +93,9 @@ struct Config {
   std::function<bool(uint32_t pid, Labels* lb)> labelsForPID;
   // receives each non-empty interval's IPC stream (what WriteArrowRequest.IpcBuffer / the offline log carry)
   std::function<void(const uint8_t* ipc, uint64_t len, uint64_t rows)> onBatch;
+  // v1 schema in offline mode (:1262-1349): after every sample record, the stacktrace record of the stacks this log
+  // has not seen yet is appended as a second batch. The aggregator behind the sink must be a PA_SCHEMA_V1 one.
+  bool offlineV1Stacktraces = false;
 };
 
 class ParcaReporter {
@@ -109,10 +116,11 @@ class ParcaReporter {
   void Stop();                                                                     // :802
   // one tick of the loop at :1199-1225: buildSampleRecordV2 + serialise; returns rows flushed or <0
   int64_t FlushOnce();
+  void ResetLoggedStacks();  // log rotation purges offlineModeLoggedStacks (:1131-1133)
 
   // counters mirroring :899-941
   std::atomic<uint64_t> cpuSamples{0}, offcpuSamples{0}, memorySamples{0}, gpuSamples{0}, emptySamples{0}, skippedByRelabeling{0},
-      sampleWrites{0}, sampleWriteRequestBytes{0}, droppedBatches{0};
+      sampleWrites{0}, sampleWriteRequestBytes{0}, droppedBatches{0}, stacktraceWriteRequestBytes{0};
 
  private:
   struct PidLabels { uint32_t labelset = 0; bool keep = true; Labels base; };
@@ -125,6 +133,7 @@ class ParcaReporter {
   std::map<FileID, std::vector<std::string>> unknown_by_file_;  // frames interned while their executable was unknown
   std::unordered_map<uint32_t, PidLabels> labels_;            // r.labels LRU content (:569)
   std::unordered_map<std::string, uint32_t> labelsets_;       // serialised Labels -> labelset id
+  std::unordered_map<std::string, bool> logged_stacks_;       // offlineModeLoggedStacks (:168, :1313-1318)
   std::thread ticker_;
   std::mutex tick_mu_;
   std::condition_variable tick_cv_;

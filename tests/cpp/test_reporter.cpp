@@ -173,8 +173,41 @@ static int runGpu(const char* out_path) {  // TestSampleWriterV2_MultipleFrameTy
   return stream.empty() ? 4 : 0;
 }
 
+// v1 schema, offline mode: two identical intervals -> .padata log with [samples, stacktraces(2 new), samples, stacktraces(0 new)]
+static int runGpuV1(const char* out_path) {
+  pa_agg_config c;
+  memset(&c, 0, sizeof c);
+  c.abi_version = PA_ABI_VERSION; c.device = 0; c.hash_mode = PA_HASH_PROVIDED; c.samples_per_second = 19; c.max_samples = 1024; c.max_frames = 4096;
+  c.label_flags = PA_LABEL_DISABLE_CPU | PA_LABEL_DISABLE_THREAD_ID | PA_LABEL_DISABLE_THREAD_COMM;
+  c.schema = PA_SCHEMA_V1;
+  pa_agg* agg = nullptr;
+  if (pa_agg_create(&c, &agg) != PA_OK) { fprintf(stderr, "pa_agg_create failed\n"); return 2; }
+  Sink* sink = NewAggSink(agg);
+  Config cfg; cfg.nodeName = ""; cfg.offlineV1Stacktraces = true;
+  OfflineLog log;
+  cfg.onBatch = [&](const uint8_t* p, uint64_t n, uint64_t) { log.Append(p, n); };
+  {
+    ParcaReporter r(sink, cfg);
+    FileID fid{1, 2};
+    r.ReportExecutable(ExecutableMetadata{fid, "/usr/bin/app", "build123"});
+    Trace t1; t1.Hash = {1, 1}; t1.Frames = {nativeFrame(0x1000, true, fid)};
+    Trace t2; t2.Hash = {2, 2}; t2.Frames = {kernelFrame(0x2000, "do_syscall_64", 100)};
+    for (int interval = 0; interval < 2; interval++) {
+      TraceEventMeta m; m.Timestamp = 1234567890; r.ReportTraceEvent(&t1, &m);
+      m.Timestamp = 1234567891; r.ReportTraceEvent(&t2, &m);
+      if (r.FlushOnce() != 2) { fprintf(stderr, "flush failed: %s\n", pa_agg_last_error(agg)); return 3; }
+    }
+    if (r.stacktraceWriteRequestBytes == 0) return 5;
+  }
+  std::ofstream(out_path, std::ios::binary).write((const char*)log.Bytes().data(), (std::streamsize)log.Bytes().size());
+  delete sink;
+  pa_agg_destroy(agg);
+  return log.Batches() == 4 ? 0 : 4;
+}
+
 int main(int argc, char** argv) {
   if (argc >= 3 && !strcmp(argv[1], "--gpu")) return runGpu(argv[2]);
+  if (argc >= 3 && !strcmp(argv[1], "--gpu-v1")) return runGpuV1(argv[2]);
   testMaybeFixTruncation();
   testLabelsAndInterning();
   testOrigins();

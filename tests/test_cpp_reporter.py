@@ -36,3 +36,27 @@ def test_reporter_through_c_abi_matches_oracle(oracle, tmp_path):
     assert p.returncode == 0, p.stderr
     want, _ = oracle.run(kw.multiple_frame_types())
     assert open(out_file, "rb").read() == want
+
+
+@pytest.mark.gpu
+def test_reporter_v1_offline_log_matches_oracle(oracle, tmp_path):
+    """v1 schema + offline mode (parca_reporter.go:1262-1349): every interval logs its sample record followed by the
+    stacktrace record of the stacks the log has not seen yet — an empty one when there are none."""
+    import pyarrow as pa
+
+    from parca_agent_b200 import abi, padata
+    out_file = str(tmp_path / "log.padata")
+    p = subprocess.run([build_bin(), "--gpu-v1", out_file], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    version, batches = padata.read(open(out_file, "rb").read())
+    assert version == 0 and len(batches) == 4
+    w = kw.multiple_frame_types()
+    w.schema = abi.PA_SCHEMA_V1
+    o = oracle.Oracle(w)
+    want = []
+    for interval in range(2):
+        o.ingest(w.hdrs, w.frame_ids)
+        sample, _ = o.flush()
+        ids = pa.ipc.open_stream(sample).read_all().column("stacktrace_id").chunk(0).values.dictionary.to_pylist()
+        want += [sample, o.stacktraces(b"".join(ids if interval == 0 else []))[0]]
+    assert [bytes(b) for b in batches] == want
