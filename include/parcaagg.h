@@ -212,6 +212,10 @@ int pa_agg_debug_stack_ids(pa_agg* a, uint8_t* out, uint64_t n_rows);
  * not part of the reference's record — see SURVEY §0.2 — and therefore computed on demand by a separate
  * kernel over the batch most recently processed, not on the flush path). out has n_unique_stacks entries. */
 int pa_agg_debug_stack_counts(pa_agg* a, uint32_t* out, uint64_t n);
+/* the same batch as (labelset, stack) -> count: one entry per distinct pair in first-occurrence order; stack is the
+ * first-occurrence ordinal of the stack (index into the counts above). Also on demand and off the flush path. Up to
+ * `cap` entries are written; *n_pairs receives the number of distinct pairs (call again with a larger cap if it is bigger). */
+int pa_agg_debug_pair_counts(pa_agg* a, uint32_t* labelset_ids, uint32_t* stack_ordinals, uint32_t* counts, uint64_t cap, uint64_t* n_pairs);
 
 /* host helpers restating reference functions (no GPU involved) */
 /* maybeFixTruncation (reporter/parca_reporter.go:190-216): returns the fixed length, or -1. */

@@ -1580,6 +1580,56 @@ int pa_agg_debug_stack_counts(pa_agg* a, uint32_t* out, uint64_t n) {
   return PA_OK;
 }
 
+int pa_agg_debug_pair_counts(pa_agg* a, uint32_t* labelset_ids, uint32_t* stack_ordinals, uint32_t* counts, uint64_t cap, uint64_t* n_pairs) {
+  if (!a || !n_pairs || (cap && (!labelset_ids || !stack_ordinals || !counts))) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  if (!a->processed) return a->fail(PA_EINVAL, "pair counts need a processed batch");
+  *n_pairs = 0;
+  const uint64_t N = a->N;
+  if (!N) return PA_OK;
+  CK(cudaSetDevice(a->device));
+  cudaStream_t s = a->s_comp;
+  // scratch of its own (the flush arena is still owned by the batch): pair table, first-row bitmap + prefix, outputs
+  const uint64_t slots = pow2_at_least(2 * N), words = N / 32 + 2, ocap = std::min<uint64_t>(cap, N);
+  DBuf scratch;
+  const size_t b_tab = slots * sizeof(PairSlot), b_words = ((words * 4 + 255) & ~(size_t)255), b_out = ((std::max<uint64_t>(ocap, 1) * 4 + 255) & ~(size_t)255);
+  CK(scratch.ensure(b_tab + 2 * b_words + 3 * b_out + 256));
+  uint8_t* base = scratch.as<uint8_t>();
+  PairSlot* pt = (PairSlot*)base;
+  uint32_t* bits = (uint32_t*)(base + b_tab);
+  uint32_t* wp = (uint32_t*)(base + b_tab + b_words);
+  uint32_t* o_ls = (uint32_t*)(base + b_tab + 2 * b_words);
+  uint32_t* o_st = (uint32_t*)(base + b_tab + 2 * b_words + b_out);
+  uint32_t* o_ct = (uint32_t*)(base + b_tab + 2 * b_words + 2 * b_out);
+  uint32_t* flags = (uint32_t*)(base + b_tab + 2 * b_words + 3 * b_out);  // [0] overflow, [1] distinct pairs
+  int rc = PA_OK;
+  auto run = [&]() -> int {
+    CK(cudaMemsetAsync(base, 0, b_tab + b_words, s));
+    CK(cudaMemsetAsync(flags, 0, 8, s));
+    k_pair_count<<<a->G, kThreads, 0, s>>>((uint32_t)N, a->d_ls.as<uint32_t>(), a->d_slot.as<uint32_t>(), a->d_table.as<StackSlot>(), pt, (uint32_t)(slots - 1), flags);
+    k_pair_bits<<<small_grid(a, slots), kThreads, 0, s>>>(pt, (uint32_t)slots, bits);
+    Timer t{};
+    launch_scan(a, WordsF{bits, wp, (uint32_t)((N + 31) / 32), flags + 1}, 1, t, small_grid(a, N / 32 + 1));
+    k_pair_emit<<<small_grid(a, slots), kThreads, 0, s>>>(pt, (uint32_t)slots, bits, wp, (uint32_t)ocap, o_ls, o_st, o_ct);
+    uint32_t h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, flags, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (h[0]) return a->fail(PA_ENOMEM, "pair table overflow");
+    *n_pairs = h[1];
+    const uint64_t m = std::min<uint64_t>(h[1], ocap);
+    if (m) {
+      CK(cudaMemcpy(labelset_ids, o_ls, m * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(stack_ordinals, o_st, m * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(counts, o_ct, m * 4, cudaMemcpyDeviceToHost));
+    }
+    return PA_OK;
+  };
+  rc = run();
+  scratch.release();
+  return rc;
+}
+
 // ---- host helpers ------------------------------------------------------------------------------
 static bool valid_utf8(const uint8_t* s, uint64_t n) {  // unicode/utf8.ValidString
   uint64_t i = 0;

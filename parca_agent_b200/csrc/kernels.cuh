@@ -1506,4 +1506,66 @@ struct StRunF {
   }
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// On-demand side table: occurrences per (labelset, stack) pair, in first-occurrence order. Like k_count_stacks this
+// is NOT part of the reference's record (one row per sample, nothing is counted: SURVEY section 0.2); it is the
+// "hash-and-count" view of the same batch for callers that want pprof-style aggregated samples. Open addressing on the
+// 64-bit pair, warp-aggregated: lanes carrying the same pair elect their lowest lane (== lowest row), which does one
+// table walk, one atomicMax (first row) and one atomicAdd (group size) for the whole group.
+struct __align__(16) PairSlot {
+  unsigned long long key;  // ((labelset << 32) | stack ordinal) + 1; 0 = empty
+  uint32_t first_inv;      // 0xFFFFFFFF - first row
+  uint32_t count;
+};
+__global__ void __launch_bounds__(kThreads) k_pair_count(uint32_t n_rows, const uint32_t* ls, const uint32_t* slot_of_row, const StackSlot* tab,
+                                                         PairSlot* pt, uint32_t pmask, uint32_t* overflow) {
+  const unsigned full = 0xFFFFFFFFu;
+  uint32_t stride = gridDim.x * kThreads, iters = (n_rows + stride - 1) / stride;
+  int lane = threadIdx.x & 31;
+  for (uint32_t it = 0; it < iters; it++) {
+    uint32_t r = it * stride + blockIdx.x * kThreads + threadIdx.x;
+    bool valid = r < n_rows;
+    unsigned long long key = 0ull;
+    if (valid) {
+      uint32_t sl = slot_of_row[r];
+      key = (((unsigned long long)ls[r] << 32) | (sl != kNull ? tab[sl].ordinal : 0u)) + 1ull;
+    }
+    unsigned grp = __match_any_sync(full, key);
+    if (!valid || lane != __ffs(grp) - 1) continue;
+    uint32_t idx = mix_slot(Key128{key, key >> 32}) & pmask;
+    bool placed = false;
+    for (uint32_t probe = 0; probe <= pmask; probe++) {
+      unsigned long long cur = pt[idx].key;
+      if (cur == 0ull) cur = atomicCAS(&pt[idx].key, 0ull, key);
+      if (cur == 0ull || cur == key) { placed = true; break; }
+      idx = (idx + 1) & pmask;
+    }
+    if (!placed) { atomicOr(overflow, 1u); continue; }
+    atomicMax(&pt[idx].first_inv, 0xFFFFFFFFu - r);
+    atomicAdd(&pt[idx].count, (uint32_t)__popc(grp));
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_pair_bits(const PairSlot* pt, uint32_t nslots, uint32_t* rowbits) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < nslots; i += gridDim.x * kThreads) {
+    if (pt[i].key == 0ull) continue;
+    uint32_t f = 0xFFFFFFFFu - pt[i].first_inv;
+    atomicOr(&rowbits[f >> 5], 1u << (f & 31));
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_pair_emit(const PairSlot* pt, uint32_t nslots, const uint32_t* rowbits, const uint32_t* wprefix,
+                                                        uint32_t cap, uint32_t* out_ls, uint32_t* out_stack, uint32_t* out_count) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < nslots; i += gridDim.x * kThreads) {
+    PairSlot e = pt[i];
+    if (e.key == 0ull) continue;
+    uint32_t f = 0xFFFFFFFFu - e.first_inv;
+    uint32_t ord = wprefix[f >> 5] + (uint32_t)__popc(rowbits[f >> 5] & ((1u << (f & 31)) - 1u));
+    if (ord >= cap) continue;
+    unsigned long long pair = e.key - 1ull;
+    out_ls[ord] = (uint32_t)(pair >> 32);
+    out_stack[ord] = (uint32_t)pair;
+    out_count[ord] = e.count;
+  }
+}
+
 }  // namespace pa

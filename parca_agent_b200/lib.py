@@ -18,7 +18,7 @@ EXPORTS = [
     "pa_agg_create", "pa_agg_destroy", "pa_agg_last_error", "pa_agg_abi_version", "pa_agg_register_strings",
     "pa_agg_register_frames", "pa_agg_register_labelsets", "pa_agg_acquire", "pa_agg_commit", "pa_agg_submit",
     "pa_agg_flush", "pa_agg_release", "pa_agg_stage", "pa_agg_process", "pa_agg_collect", "pa_agg_last_kernel_ms",
-    "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_agg_stacktraces", "pa_agg_last_stack_ids", "pa_fix_truncation", "pa_xxh64",
+    "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_agg_debug_pair_counts", "pa_agg_stacktraces", "pa_agg_last_stack_ids", "pa_fix_truncation", "pa_xxh64",
 ]
 
 
@@ -57,6 +57,7 @@ def lib():
         L.pa_agg_last_kernel_ms.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), u32p]
         L.pa_agg_debug_stack_ids.argtypes = [vp, vp, C.c_uint64]
         L.pa_agg_debug_stack_counts.argtypes = [vp, vp, C.c_uint64]
+        L.pa_agg_debug_pair_counts.argtypes = [vp, vp, vp, vp, C.c_uint64, u64p]
         L.pa_agg_stacktraces.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(abi.PaAggResult)]
         L.pa_agg_last_stack_ids.argtypes = [vp, vp, C.c_uint64]
         L.pa_fix_truncation.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64]
@@ -176,6 +177,14 @@ class Aggregator:
 
     def collect(self):
         return self._result(lib().pa_agg_collect)
+
+    def debug_pair_counts(self, cap):
+        """(labelset id, stack ordinal, count) of every distinct pair of the processed batch, first-occurrence order."""
+        ls, st, ct = (np.zeros(max(cap, 1), dtype=np.uint32) for _ in range(3))
+        n = C.c_uint64()
+        self._ck(lib().pa_agg_debug_pair_counts(self.h, ls.ctypes.data, st.ctypes.data, ct.ctypes.data, cap, C.byref(n)))
+        m = min(int(n.value), cap)
+        return ls[:m], st[:m], ct[:m], int(n.value)
 
     def stacktraces(self, ids):
         """v1: the stacktrace record for the concatenated 16-byte ids (buildStacktraceRecord)."""

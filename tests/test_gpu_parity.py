@@ -116,6 +116,35 @@ def test_stack_ids_match_xxh64(oracle, gpu):
     a.close()
 
 
+@pytest.mark.parametrize("make", [lambda: synth.edge_workload(seed=9, n=5000), lambda: synth.config3(n=120_000, u=5_000, p=4_096, npids=200, lsets=6),
+                                  lambda: synth.config1(hash_mode=abi.PA_HASH_PROVIDED)])
+def test_pair_counts_side_table(gpu, make):
+    """(labelset, stack) -> count, first-occurrence order: the hash-and-count view of a batch (not part of the reference's
+    record, which keeps one row per sample). Checked against a plain dictionary walk over the rows."""
+    w = make()
+    a = gpu.from_workload(w)
+    gpu.load(a, w)
+    a.stage()
+    a.process()
+    ids = a.debug_stack_ids(w.n)
+    stack_ord, pairs = {}, {}
+    for r in range(w.n):
+        sid = ids[r].tobytes()
+        o = stack_ord.setdefault(sid, len(stack_ord))
+        key = (int(w.hdrs["labelset_id"][r]), o)
+        pairs[key] = pairs.get(key, 0) + 1
+    ls, st, ct, n = a.debug_pair_counts(w.n)
+    assert n == len(pairs) and len(ls) == n
+    assert list(zip(ls.tolist(), st.tolist())) == list(pairs.keys()) and ct.tolist() == list(pairs.values())
+    assert int(ct.sum()) == w.n
+    ls2, st2, ct2, n2 = a.debug_pair_counts(3)          # a short buffer reports the total and fills what fits
+    assert n2 == n and ls2.tolist() == ls[:3].tolist() and ct2.tolist() == ct[:3].tolist()
+    res = a.collect()
+    per_stack = a.debug_stack_counts(res.n_unique_stacks)
+    assert np.array_equal(np.bincount(st, weights=ct, minlength=res.n_unique_stacks).astype(np.uint32), per_stack)
+    a.close()
+
+
 def test_staged_pipeline_equals_flush_and_repeats(oracle, gpu):
     """stage/process/collect == flush; process() is repeatable; the ring double-buffers across flushes."""
     w = synth.config1().head(30000)
