@@ -874,7 +874,7 @@ static int process_once(pa_agg* a) {
 static int process(pa_agg* a) {
   if (a->staged < 0) return a->fail(PA_EINVAL, "nothing staged");
   CK(cudaSetDevice(a->device));
-  if (a->N == 0) { a->processed = true; memset(&a->h_ctr, 0, sizeof a->h_ctr); return PA_OK; }
+  if (a->N == 0) { a->processed = true; a->last_unique = 0; memset(&a->h_ctr, 0, sizeof a->h_ctr); return PA_OK; }
   int rc = upload_tables(a);
   if (rc) return rc;
   for (int attempt = 0; attempt < 6; attempt++) {
