@@ -108,10 +108,18 @@ def time_cpu_port(w, n_rows):
     o = oracle_py.Oracle(sub)
     t0 = time.perf_counter()
     o.ingest(sub.hdrs, frames)
+    t1 = time.perf_counter()
     data, st = o.flush()
     dt = time.perf_counter() - t0
     o.close()
+    st = dict(st, ingest_s=t1 - t0, flush_s=dt - (t1 - t0))
     return sub.n / dt, dt, len(data), st
+
+
+def two_core_note(n, st):
+    """The reference runs ingest and flush on different goroutines (writer swap, parca_reporter.go:1743-1748): with both
+    perfectly overlapped the rate is bounded by the slower of the two. Reported beside the single-thread value."""
+    return {"ingest_s": st["ingest_s"], "flush_s": st["flush_s"], "idealised_2core_value": n / max(st["ingest_s"], st["flush_s"])}
 
 
 def run_reference(args, rank, world):
@@ -136,7 +144,8 @@ def run_reference(args, rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": "config2: 10M samples x 64 frames, 100k unique stacks (bounded prefix per step)", "hash_mode": "xxh64x2"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": 1, "kind": "port",
-                         "sample": sample + "; single thread because the reference serialises ingest on one mutex (parca_reporter.go:335)"},
+                         "sample": sample + "; single thread because the reference serialises ingest on one mutex (parca_reporter.go:335)",
+                         **two_core_note(w.n, st)},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -300,7 +309,8 @@ def main():
             cpu = {"value": rate, "unit": "samples/s", "cores": 1, "kind": "port",
                    "sample": "first %d rows of the same batch (every one of its 100k stacks occurs in the prefix), ingest+flush to IPC bytes in %.1f s; "
                              "C++ restatement of the reference Go path (Go toolchain unavailable), single thread as the reference serialises "
-                             "ingest (parca_reporter.go:335); host has %d cores" % (min(args.cpu_sample, w.n), dt, os.cpu_count())}
+                             "ingest (parca_reporter.go:335); host has %d cores" % (min(args.cpu_sample, w.n), dt, os.cpu_count()),
+                   **two_core_note(min(args.cpu_sample, w.n), st)}
         out = {
             "metric": "samples/sec aggregated", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
