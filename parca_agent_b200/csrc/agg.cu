@@ -592,7 +592,7 @@ static int process_once(pa_agg* a) {
 
   // ---- stack table capacity: 2x an upper bound on this batch's unique stacks (adaptive, retried on overflow)
   uint64_t bound = N;
-  if (a->prev_unique && N > (1u << 20)) bound = std::min<uint64_t>(N, std::max<uint64_t>(a->prev_unique * 4, 1u << 20));
+  if (a->prev_unique && N > (1u << 20)) bound = std::min<uint64_t>(N, std::max<uint64_t>(a->prev_unique * 4, 1u << 18));
   uint64_t cap = std::max<uint64_t>(pow2_at_least(2 * std::max<uint64_t>(bound, 1)), 1024);
   if (cap < a->retry_cap) cap = a->retry_cap;
   a->table_cap = cap;
@@ -612,7 +612,7 @@ static int process_once(pa_agg* a) {
   const size_t P = std::max<uint32_t>(n_frames, 1), S = std::max<uint32_t>(n_cstr, 1), FN = std::max<uint32_t>(n_funcs, 1);
   const size_t NI = (size_t)std::min<uint64_t>(std::max<uint64_t>(a->NF, 1), 0x7FFFFFFFull);
   const size_t Nn = (size_t)std::max<uint64_t>(N, 1);
-  uint32_t *rowbits = nullptr, *row_wprefix = nullptr, *uniq_slot = nullptr, *uniq_size = nullptr, *first_ls = nullptr;
+  uint32_t *rowbits = nullptr, *row_wprefix = nullptr, *uniq_slot = nullptr, *uniq_size = nullptr, *first_ls = nullptr, *claimed = nullptr;
   want(&first_ls, std::max<size_t>(a->ls.sets.size(), 1) * 4, 0);
   if (v1) {
     want(&a->v1_ord, Nn * 4); want(&a->v1_ts_vals, Nn * 8); want(&a->v1_id_off, (Nn + 1) * 4);
@@ -620,6 +620,7 @@ static int process_once(pa_agg* a) {
     want(&a->v1_first_kind, 8 * 4, 0); want(&a->v1_kindrank, 64 * 4); want(&a->v1_kind_order, 64 * 4); want(&a->v1_n_kind_dict, 8 * 4);
   }
   want(&rowbits, (Nn / 32 + 2) * 4, 1); want(&row_wprefix, (Nn / 32 + 2) * 4); want(&uniq_slot, Nn * 4); want(&uniq_size, Nn * 4);
+  want(&claimed, Nn * 4);
   uint32_t *loc_bits = nullptr, *loc_wp = nullptr;
   want(&a->loc_first, P * 4, 0); want(&a->loc_rank, P * 4); want(&a->loc_order, P * 4);
   want(&loc_bits, (NI / 32 + 2) * 4); want(&loc_wp, (NI / 32 + 2) * 4);
@@ -737,7 +738,7 @@ static int process_once(pa_agg* a) {
     h.kind = a->d_kind.as<uint8_t>(); h.nframes = a->d_nfr.as<uint16_t>(); h.frame_off = a->d_foff.as<unsigned long long>();
     h.ls = a->d_ls.as<uint32_t>(); h.cpu = a->d_cpu.as<uint32_t>(); h.tid = a->d_tid.as<uint32_t>(); h.comm = a->d_comm.as<uint32_t>();
     h.sid2cid = a->m_sid2cid.ptr(); h.n_sids = (uint32_t)a->sp.sid2cid.size(); h.n_labelsets = (uint32_t)a->ls.sets.size();
-    h.n_frame_ids = frames_end; h.provided = provided ? 1 : 0; h.tab = tab; h.mask = mask; h.slot_of_row = a->d_slot.as<uint32_t>(); h.ctr = ctr;
+    h.n_frame_ids = frames_end; h.provided = provided ? 1 : 0; h.tab = tab; h.mask = mask; h.slot_of_row = a->d_slot.as<uint32_t>(); h.ctr = ctr; h.claimed = claimed;
     h.first_ls = a->n_lscols ? first_ls : nullptr;
     for (uint32_t c = 0; c < nlab; c++) {
       if (a->cols[c].type == COL_CPU) h.first_cpu = col_first[c];
@@ -754,7 +755,7 @@ static int process_once(pa_agg* a) {
     HashArgs ha{};
     ha.frames = a->d_frames.as<unsigned long long>(); ha.frame_off = a->d_foff.as<unsigned long long>(); ha.nframes = a->d_nfr.as<uint16_t>();
     ha.row0 = (uint32_t)r0; ha.row1 = (uint32_t)r1; ha.uuid = a->d_uuid.as<uint8_t>();
-    ha.slot_of_row = a->d_slot.as<uint32_t>(); ha.tab = tab; ha.mask = mask; ha.ctr = ctr;
+    ha.slot_of_row = a->d_slot.as<uint32_t>(); ha.tab = tab; ha.mask = mask; ha.ctr = ctr; ha.claimed = claimed;
     uint64_t rows = r1 - r0;
     int blocks = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)a->sms * (a->hash_variant == 1 ? 3 : 4));
     if (a->hash_variant == 1) k_hash_insert_staged<<<std::max(blocks, 1), kThreads, kHashStagedSmem, s>>>(ha);
@@ -780,11 +781,10 @@ static int process_once(pa_agg* a) {
 
   // ---- unique stacks: ordinals from the first-row bitmap, offsets from a scan over the unique list
   CK(cudaEventRecord(a->tm[T_RANK].a, s));
-  const uint32_t nslots = (uint32_t)(cap + 2);
-  const int Gs = small_grid(a, nslots), Gw = small_grid(a, N / 32 + 1), Gu = small_grid(a, std::min<uint64_t>(N, cap / 2));
-    k_stack_bits<<<Gs, kThreads, 0, s>>>(tab, nslots, rowbits);
+  const int Gw = small_grid(a, N / 32 + 1), Gu = small_grid(a, std::min<uint64_t>(N, cap / 2));
+    k_stack_bits<<<Gu, kThreads, 0, s>>>(tab, claimed, ctr, rowbits);
     launch_scan(a, WordsF{rowbits, row_wprefix, (uint32_t)((N + 31) / 32), &ctr->n_unique}, 1, a->tm[T_RANK], Gw);
-    k_stack_assign<<<Gs, kThreads, 0, s>>>(tab, nslots, rowbits, row_wprefix, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(), uniq_slot, uniq_size);
+    k_stack_assign<<<Gu, kThreads, 0, s>>>(tab, claimed, ctr, rowbits, row_wprefix, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(), uniq_slot, uniq_size);
     launch_scan(a, UniqOffsetF{ctr, ctr, uniq_size, uniq_slot, tab}, 1, a->tm[T_RANK], Gu);
     a->tm[T_RANK].launches += 2;
   k_rows_materialize<<<G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>(), v1 ? a->v1_ord : nullptr);

@@ -41,6 +41,8 @@ struct Counters {
   uint32_t n_locations, n_lines, n_functions;
   uint32_t n_dict_type, n_dict_map, n_dict_bid, n_dict_file;
   uint32_t null_bid, null_file;
+  uint32_t n_claimed;       // stack-table slots claimed so far == entries of the claimed-slot list
+  uint32_t zero_claimed;    // the dedicated all-zero-id slot is on the list
   uint32_t store_overflow;  // v1: the known-stacks store ran out of entries or frame space during this flush
   uint32_t st_null_lists;   // v1 stacktrace record: known stacks with zero frames (null list entries)
   uint32_t n_runs[kMaxCols];
@@ -100,14 +102,20 @@ __device__ __forceinline__ void block_range(uint32_t n, uint32_t* begin, uint32_
 
 // ---------------------------------------------------------------------------------------------
 // stack table: find-or-claim on the 128-bit stack id (StacktraceDictBuilderV2.index, arrow_v2.go:230)
-__device__ __forceinline__ uint32_t stack_find_or_insert(StackSlot* tab, uint32_t mask, Key128 k, Counters* ctr) {
-  if (key_zero(k)) return mask + 1;  // the all-zero id lives in a dedicated slot past the table
+// Every slot is appended to `claimed` by the one thread whose CAS claimed it, so the ranking passes walk the
+// unique stacks (U entries) instead of scanning the whole table.
+__device__ __forceinline__ uint32_t stack_find_or_insert(StackSlot* tab, uint32_t mask, Key128 k, Counters* ctr, uint32_t* claimed) {
+  if (key_zero(k)) {  // the all-zero id lives in a dedicated slot past the table
+    if (*(volatile uint32_t*)&ctr->zero_claimed == 0u && atomicExch(&ctr->zero_claimed, 1u) == 0u) claimed[atomicAdd(&ctr->n_claimed, 1u)] = mask + 1;
+    return mask + 1;
+  }
   uint32_t idx = mix_slot(k) & mask;
   const Key128 zero{0ull, 0ull};
   for (uint32_t probe = 0; probe <= mask; probe++) {
     Key128 cur = ld_key(&tab[idx].key);
     if (cur.hi == 0 || cur.lo == 0) cur = cas128(&tab[idx].key, zero, k);  // empty / possibly torn: CAS is authoritative
-    if (key_zero(cur) || key_eq(cur, k)) return idx;
+    if (key_zero(cur)) { claimed[atomicAdd(&ctr->n_claimed, 1u)] = idx; return idx; }
+    if (key_eq(cur, k)) return idx;
     idx = (idx + 1) & mask;
   }
   atomicOr(&ctr->err, ERR_TABLE_FULL);
@@ -119,7 +127,7 @@ __device__ __forceinline__ uint32_t stack_find_or_insert(StackSlot* tab, uint32_
 // for the whole group. All 32 lanes must call this converged. (Occurrence counts are NOT maintained here:
 // on skewed batches the per-stack atomicAdd serialised on a few hot L2 lines and cost more than the
 // hashing itself; they are computed on demand by k_count_stacks.)
-__device__ __forceinline__ uint32_t warp_insert(StackSlot* tab, uint32_t mask, Key128 k, uint32_t row, bool valid, Counters* ctr) {
+__device__ __forceinline__ uint32_t warp_insert(StackSlot* tab, uint32_t mask, Key128 k, uint32_t row, bool valid, Counters* ctr, uint32_t* claimed) {
   const unsigned full = 0xFFFFFFFFu;
   int lane = threadIdx.x & 31;
   unsigned long long tag = valid ? (k.lo ^ rotl64(k.hi, 29)) : (0xDEAD00000000ull + lane);
@@ -131,7 +139,7 @@ __device__ __forceinline__ uint32_t warp_insert(StackSlot* tab, uint32_t mask, K
   bool own = valid && (lane == leader || !agree);  // tag collisions between different ids fall back to a private insert
   uint32_t idx = kNull;
   if (own) {
-    idx = stack_find_or_insert(tab, mask, k, ctr);
+    idx = stack_find_or_insert(tab, mask, k, ctr, claimed);
     if (idx != kNull) {
       uint32_t inv = 0xFFFFFFFFu - row;
       if (*(volatile uint32_t*)&tab[idx].first_inv < inv) atomicMax(&tab[idx].first_inv, inv);
@@ -192,6 +200,7 @@ struct HeaderArgs {
   uint32_t mask;
   uint32_t* slot_of_row;
   Counters* ctr;
+  uint32_t* claimed;           // list of claimed table slots (see stack_find_or_insert)
   // dictionary memo of the label columns: first row carrying each value. The first row of a value always
   // opens a run, so min over all rows == min over run starts; rows ascend with the grid here, which keeps the
   // atomics rare, and this DRAM-bound kernel has the issue slots to spare. nullptr = column disabled.
@@ -250,7 +259,7 @@ __global__ void __launch_bounds__(kThreads) k_header(HeaderArgs a) {
       }
     }
     if (a.provided) {
-      uint32_t s = warp_insert(a.tab, a.mask, k, r, valid, a.ctr);
+      uint32_t s = warp_insert(a.tab, a.mask, k, r, valid, a.ctr, a.claimed);
       if (valid) a.slot_of_row[r] = s;
     }
   }
@@ -286,6 +295,7 @@ struct HashArgs {
   StackSlot* tab;
   uint32_t mask;
   Counters* ctr;
+  uint32_t* claimed;           // list of claimed table slots (see stack_find_or_insert)
 };
 
 // Variant B ("direct"): one warp-iteration covers 32 consecutive samples. The XXH64 rounds run with 4 lanes
@@ -362,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_hash_insert(HashArgs a) {
     k.hi = xxh_finish_own(v0, 0ull, n_me, t0, t1, t2);
     k.lo = xxh_finish_own(v1, kSeedLo, n_me, t0, t1, t2);
     if (valid) *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = make_ulonglong2(bswap64(k.hi), bswap64(k.lo));
-    uint32_t slot = warp_insert(a.tab, a.mask, k, r, valid, a.ctr);
+    uint32_t slot = warp_insert(a.tab, a.mask, k, r, valid, a.ctr, a.claimed);
     if (valid) a.slot_of_row[r] = slot;
   }
 }
@@ -461,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_hash_insert_wide(HashArgs a) {
     k.hi = xxh_finish_own(v0, 0ull, n_me, t0, t1, t2);
     k.lo = xxh_finish_own(v1, kSeedLo, n_me, t0, t1, t2);
     if (valid) *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = make_ulonglong2(bswap64(k.hi), bswap64(k.lo));
-    uint32_t slot = warp_insert(a.tab, a.mask, k, r, valid, a.ctr);
+    uint32_t slot = warp_insert(a.tab, a.mask, k, r, valid, a.ctr, a.claimed);
     if (valid) a.slot_of_row[r] = slot;
   }
 }
@@ -580,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_hash_insert_staged(HashArgs a) 
     k.hi = xxh_finish_own(v0, 0ull, n_me, t0, t1, t2);
     k.lo = xxh_finish_own(v1, kSeedLo, n_me, t0, t1, t2);
     if (valid) *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = make_ulonglong2(bswap64(k.hi), bswap64(k.lo));
-    uint32_t slot = warp_insert(a.tab, a.mask, k, r, valid, a.ctr);
+    uint32_t slot = warp_insert(a.tab, a.mask, k, r, valid, a.ctr, a.claimed);
     if (valid) a.slot_of_row[r] = slot;
     r = r_nx; valid = valid_nx; n_me = n_nx; off_me = off_nx; staged = staged_nx;
   }
@@ -681,10 +691,11 @@ __global__ void __launch_bounds__(kThreads) k_scan_emit(F f, const typename F::T
 // (1) unique stacks in first-occurrence order. The table holds each stack's first row; ordinals
 // come from a bitmap over rows (one bit per first occurrence) + a popcount prefix over its words,
 // so only table-sized and N/32-sized passes are needed (no scan over all rows).
-__global__ void __launch_bounds__(kThreads) k_stack_bits(const StackSlot* tab, uint32_t nslots, uint32_t* rowbits) {
-  for (uint32_t sidx = blockIdx.x * kThreads + threadIdx.x; sidx < nslots; sidx += gridDim.x * kThreads) {
-    uint32_t inv = tab[sidx].first_inv;
-    if (inv) { uint32_t f = 0xFFFFFFFFu - inv; atomicOr(&rowbits[f >> 5], 1u << (f & 31)); }
+__global__ void __launch_bounds__(kThreads) k_stack_bits(const StackSlot* tab, const uint32_t* claimed, const Counters* ctr, uint32_t* rowbits) {
+  const uint32_t n = ctr->n_claimed;
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    uint32_t f = 0xFFFFFFFFu - tab[claimed[i]].first_inv;
+    atomicOr(&rowbits[f >> 5], 1u << (f & 31));
   }
 }
 struct WordsF {  // exclusive popcount prefix over bitmap words
@@ -698,12 +709,13 @@ struct WordsF {  // exclusive popcount prefix over bitmap words
   __device__ void emit(uint32_t i, uint32_t ex, uint32_t) const { wprefix[i] = ex; }
   __device__ void total(int, uint32_t t) const { *total_out = t; }
 };
-__global__ void __launch_bounds__(kThreads) k_stack_assign(StackSlot* tab, uint32_t nslots, const uint32_t* rowbits, const uint32_t* wprefix,
-                                                           const uint16_t* nframes, uint32_t* uniq_row, uint32_t* uniq_slot, uint32_t* uniq_size) {
-  for (uint32_t sidx = blockIdx.x * kThreads + threadIdx.x; sidx < nslots; sidx += gridDim.x * kThreads) {
-    uint32_t inv = tab[sidx].first_inv;
-    if (!inv) continue;
-    uint32_t f = 0xFFFFFFFFu - inv;
+__global__ void __launch_bounds__(kThreads) k_stack_assign(StackSlot* tab, const uint32_t* claimed, const Counters* ctr, const uint32_t* rowbits,
+                                                           const uint32_t* wprefix, const uint16_t* nframes, uint32_t* uniq_row, uint32_t* uniq_slot,
+                                                           uint32_t* uniq_size) {
+  const uint32_t n = ctr->n_claimed;
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    uint32_t sidx = claimed[i];
+    uint32_t f = 0xFFFFFFFFu - tab[sidx].first_inv;
     uint32_t ord = wprefix[f >> 5] + (uint32_t)__popc(rowbits[f >> 5] & ((1u << (f & 31)) - 1u));
     uniq_row[ord] = f;
     tab[sidx].ordinal = ord;
