@@ -217,6 +217,25 @@ int pa_agg_debug_stack_counts(pa_agg* a, uint32_t* out, uint64_t n);
  * `cap` entries are written; *n_pairs receives the number of distinct pairs (call again with a larger cap if it is bigger). */
 int pa_agg_debug_pair_counts(pa_agg* a, uint32_t* labelset_ids, uint32_t* stack_ordinals, uint32_t* counts, uint64_t cap, uint64_t* n_pairs);
 
+/* ---- multi-GPU, one merged batch ("mode B") ------------------------------------------------
+ * The sample stream is sharded by pid hash, one aggregator per GPU. Per-shard batches (mode A) need nothing more. For
+ * ONE batch that is bit-identical to the unsharded stream's, every shard aggregator (PA_SCHEMA_V2) runs stage + process,
+ * exports its rows and the frames of its unique stacks into device buffers the caller owns, the caller moves them to
+ * the merging GPU (NCCL send/recv over NVLink: 64 B per row + 8 B per unique-stack frame) and places the rows at their
+ * positions in the global order, and a PA_HASH_PROVIDED aggregator there stages that union from device memory and
+ * runs the usual process + collect. All aggregators must have been registered the same strings / frames / labelsets. */
+/* sizes of what pa_agg_shard_export will write for the batch last processed (rows, frame ids) */
+int pa_agg_shard_sizes(pa_agg* a, uint64_t* n_rows, uint64_t* n_frames);
+/* hdr_out: n_rows pa_sample_hdr (device memory) with hash_hi/lo = the stack id, nframes = the kept stack's depth and
+ * frame_off = frame_base + offset of the stack's frames inside frames_out; frames_out: n_frames uint64 (device).
+ * Synchronous: the buffers are complete when the call returns. */
+int pa_agg_shard_export(pa_agg* a, uint64_t frame_base, pa_sample_hdr* hdr_out, uint64_t* frames_out);
+/* drop the staged batch without building its record (a shard whose rows have been exported does not need its own) */
+int pa_agg_discard(pa_agg* a);
+/* stage a batch that already lives in device memory (rows in final order, frame_off relative to frames) instead of the
+ * pinned ring; the caller's writes to both buffers must have completed. Follow with pa_agg_process + pa_agg_collect. */
+int pa_agg_stage_device(pa_agg* a, const pa_sample_hdr* hdr, uint64_t n_rows, const uint64_t* frames, uint64_t n_frames);
+
 /* host helpers restating reference functions (no GPU involved) */
 /* maybeFixTruncation (reporter/parca_reporter.go:190-216): returns the fixed length, or -1. */
 int64_t pa_fix_truncation(const uint8_t* s, uint64_t len, uint64_t max_len);

@@ -141,6 +141,7 @@ struct pa_agg {
   std::vector<uint64_t> chunk_frames_end;
   cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_d2h0 = nullptr, ev_d2h1 = nullptr;
   bool processed = false, hash_timed = false;
+  const unsigned long long* src_frames = nullptr;  // where the staged batch's frame ids can be read by kernels (set by stage / stage_device)
   int hash_variant = 2;  // 2 = wide (default: 2 lanes/sample, 16-byte loads), 0 = direct (4 lanes/sample), 1 = cp.async-staged; PA_HASH_VARIANT=wide|direct|staged
 
   // ---- device batch buffers
@@ -470,6 +471,7 @@ static int stage_async(pa_agg* a) {
   }
   pa_agg::Ring& r = a->ring[buf];
   a->staged = buf;
+  a->src_frames = a->cfg.hash_mode == PA_HASH_PROVIDED ? (const unsigned long long*)r.frames_dev : a->d_frames.as<unsigned long long>();
   a->N = r.rows;
   a->NF = r.nfr;
   a->processed = false;
@@ -575,7 +577,7 @@ static void launch_store_insert(pa_agg* a) {
   Counters* ctr = a->d_ctr.as<Counters>();
   sa.ctr = ctr; sa.uniq_row = a->d_uniq_row.as<uint32_t>(); sa.slot_of_row = a->d_slot.as<uint32_t>(); sa.tab = a->d_table.as<StackSlot>();
   sa.nframes = a->d_nfr.as<uint16_t>(); sa.frame_off = a->d_foff.as<unsigned long long>();
-  sa.frames = a->cfg.hash_mode == PA_HASH_PROVIDED ? (const unsigned long long*)a->ring[a->staged].frames_dev : a->d_frames.as<unsigned long long>();
+  sa.frames = a->src_frames;
   sa.n_frames_registered = a->ft.count();
   sa.st = a->d_store.as<StoreSlot>(); sa.mask = (uint32_t)(a->store_slots - 1); sa.arena = a->d_store_arena.as<uint32_t>();
   sa.cap_frames = a->store_frames; sa.cap_entries = (uint32_t)a->store_entries; sa.ctl = a->d_store_ctl.as<StoreCtl>(); sa.ctr_w = ctr;
@@ -793,7 +795,7 @@ static int process_once(pa_agg* a) {
     launch_store_insert(a);
     a->tm[T_RANK].launches++;
   } else {
-    const unsigned long long* gather_src = provided ? (const unsigned long long*)a->ring[a->staged].frames_dev : a->d_frames.as<unsigned long long>();
+    const unsigned long long* gather_src = a->src_frames;
     k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, gather_src,
                                            a->d_foff.as<unsigned long long>(), n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr);
   }
@@ -1500,7 +1502,74 @@ static int stacktraces(pa_agg* a, const uint8_t* ids, uint64_t n, pa_agg_result*
   return PA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// mode B building blocks (see include/parcaagg.h): export a processed shard, stage a merged batch from device memory
+static int stage_device(pa_agg* a, const pa_sample_hdr* hdr, uint64_t n_rows, const uint64_t* frames, uint64_t n_frames) {
+  CK(cudaSetDevice(a->device));
+  if (a->staged >= 0) return a->fail(PA_EINVAL, "the previously staged batch has not been collected");
+  if (n_rows > a->cfg.max_samples || n_frames > a->cfg.max_frames) return a->fail(PA_ENOSPC, "device batch exceeds max_samples / max_frames");
+  if ((n_rows && !hdr) || (n_frames && !frames)) return a->fail(PA_EINVAL, "null device buffer");
+  CK(a->d_frames.ensure(std::max<uint64_t>(n_frames, 1) * 8));  // provided-hash aggregators do not own a frame buffer until now
+  a->staged = a->active;  // no ring buffer is detached: ingest into the ring continues untouched
+  a->src_frames = a->d_frames.as<unsigned long long>();
+  a->N = n_rows;
+  a->NF = n_frames;
+  a->processed = false;
+  a->chunk_rows.clear();
+  a->chunk_frames_end.clear();
+  CK(cudaEventRecord(a->ev_h2d0, a->s_copy));
+  if (n_rows) CK(cudaMemcpyAsync(a->d_hdr.p, hdr, n_rows * 64, cudaMemcpyDeviceToDevice, a->s_copy));
+  if (n_frames) CK(cudaMemcpyAsync(a->d_frames.p, frames, n_frames * 8, cudaMemcpyDeviceToDevice, a->s_copy));
+  CK(cudaEventRecord(a->ev_h2d1, a->s_copy));
+  CK(cudaStreamSynchronize(a->s_copy));
+  return PA_OK;
+}
+
+static int shard_export(pa_agg* a, uint64_t frame_base, pa_sample_hdr* hdr_out, uint64_t* frames_out) {
+  if (a->cfg.schema != PA_SCHEMA_V2) return a->fail(PA_EINVAL, "shard export needs a PA_SCHEMA_V2 aggregator (the v2 pipeline gathers the unique stacks)");
+  if (a->staged < 0 || !a->processed) return a->fail(PA_EINVAL, "shard export needs a processed, not yet collected batch");
+  if (!a->N) return PA_OK;
+  if (!hdr_out || (a->h_ctr.n_indices64 && !frames_out)) return a->fail(PA_EINVAL, "null device buffer");
+  CK(cudaSetDevice(a->device));
+  cudaStream_t s = a->s_comp;
+  k_shard_export_rows<<<a->G, kThreads, 0, s>>>((uint32_t)a->N, a->d_hdr.as<uint4>(), a->d_uuid.as<uint8_t>(), a->d_slot.as<uint32_t>(), a->d_table.as<StackSlot>(),
+                                                frame_base, (uint4*)hdr_out);
+  k_shard_export_frames<<<small_grid(a, a->h_ctr.n_indices64), kThreads, 0, s>>>(a->d_ctr.as<Counters>(), a->d_ustream.as<uint32_t>(), a->loc_order,
+                                                                                   (unsigned long long*)frames_out);
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  return PA_OK;
+}
+
 extern "C" {
+
+int pa_agg_shard_sizes(pa_agg* a, uint64_t* n_rows, uint64_t* n_frames) {
+  if (!a || !n_rows || !n_frames) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  if (a->staged < 0 || !a->processed) return a->fail(PA_EINVAL, "shard sizes need a processed, not yet collected batch");
+  *n_rows = a->N;
+  *n_frames = a->N ? a->h_ctr.n_indices64 : 0;
+  return PA_OK;
+}
+int pa_agg_shard_export(pa_agg* a, uint64_t frame_base, pa_sample_hdr* hdr_out, uint64_t* frames_out) {
+  if (!a) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  return shard_export(a, frame_base, hdr_out, frames_out);
+}
+int pa_agg_discard(pa_agg* a) {
+  if (!a) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  CK(cudaSetDevice(a->device));
+  CK(cudaStreamSynchronize(a->s_copy));
+  CK(cudaStreamSynchronize(a->s_comp));
+  a->staged = -1;
+  return PA_OK;
+}
+int pa_agg_stage_device(pa_agg* a, const pa_sample_hdr* hdr, uint64_t n_rows, const uint64_t* frames, uint64_t n_frames) {
+  if (!a) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  return stage_device(a, hdr, n_rows, frames, n_frames);
+}
 
 int pa_agg_stacktraces(pa_agg* a, const uint8_t* ids, uint64_t n_ids, pa_agg_result* out) {
   if (!a || !out) return PA_EINVAL;

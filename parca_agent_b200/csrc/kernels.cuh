@@ -1580,4 +1580,37 @@ __global__ void __launch_bounds__(kThreads) k_pair_emit(const PairSlot* pt, uint
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU mode B (one merged batch): every shard hashes and deduplicates its own rows, then
+// exports (1) its rows as 64-byte headers that carry the computed stack id and point at (2) the frames of its
+// UNIQUE stacks only. The merging GPU receives 64 B per row plus U*F*8 B per shard over NVLink and runs the
+// provided-id pipeline on the union in global row order, so every dictionary comes out in the order the
+// reference would produce on the unsharded stream.
+__global__ void __launch_bounds__(kThreads) k_shard_export_rows(uint32_t n_rows, const uint4* hdr_in, const uint8_t* uuid, const uint32_t* slot_of_row,
+                                                                const StackSlot* tab, unsigned long long frame_base, uint4* hdr_out) {
+  for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < n_rows; r += gridDim.x * kThreads) {
+    const uint4* h = hdr_in + 4ull * r;
+    uint4 q1 = __ldg(h + 1), q2 = __ldg(h + 2), q3 = __ldg(h + 3);
+    ulonglong2 id = *reinterpret_cast<const ulonglong2*>(uuid + 16ull * r);  // big-endian hi||lo
+    unsigned long long hi = bswap64(id.x), lo = bswap64(id.y);
+    uint32_t sl = slot_of_row[r];
+    StackSlot e = tab[sl];
+    unsigned long long foff = frame_base + e.offset;  // every row of a stack points at the shard's single copy of its frames
+    uint4 q0 = make_uint4((uint32_t)hi, (uint32_t)(hi >> 32), (uint32_t)lo, (uint32_t)(lo >> 32));
+    q3.x = (uint32_t)foff;
+    q3.y = (uint32_t)(foff >> 32);
+    q3.w = (q3.w & 0xFFFF0000u) | (e.size & 0xFFFFu);  // nframes of the stack's first occurrence (what the record keeps)
+    uint4* o = hdr_out + 4ull * r;
+    o[0] = q0; o[1] = q1; o[2] = q2; o[3] = q3;
+  }
+}
+// frames of the unique stacks, first-occurrence order, as frame ids again (the location ranking rewrote the
+// gathered stream in place with location indices; loc_order maps an index back to its frame id)
+__global__ void __launch_bounds__(kThreads) k_shard_export_frames(const Counters* ctr, const uint32_t* ustream, const uint32_t* loc_order,
+                                                                  unsigned long long* out) {
+  const uint32_t n = (uint32_t)ctr->n_indices64;
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) out[i] = loc_order[ustream[i]];
+}
+
 }  // namespace pa

@@ -18,7 +18,7 @@ EXPORTS = [
     "pa_agg_create", "pa_agg_destroy", "pa_agg_last_error", "pa_agg_abi_version", "pa_agg_register_strings",
     "pa_agg_register_frames", "pa_agg_register_labelsets", "pa_agg_acquire", "pa_agg_commit", "pa_agg_submit",
     "pa_agg_flush", "pa_agg_release", "pa_agg_stage", "pa_agg_process", "pa_agg_collect", "pa_agg_last_kernel_ms",
-    "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_agg_debug_pair_counts", "pa_agg_stacktraces", "pa_agg_last_stack_ids", "pa_fix_truncation", "pa_xxh64",
+    "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_agg_debug_pair_counts", "pa_agg_stacktraces", "pa_agg_last_stack_ids", "pa_agg_shard_sizes", "pa_agg_shard_export", "pa_agg_stage_device", "pa_agg_discard", "pa_fix_truncation", "pa_xxh64",
 ]
 
 
@@ -58,6 +58,10 @@ def lib():
         L.pa_agg_debug_stack_ids.argtypes = [vp, vp, C.c_uint64]
         L.pa_agg_debug_stack_counts.argtypes = [vp, vp, C.c_uint64]
         L.pa_agg_debug_pair_counts.argtypes = [vp, vp, vp, vp, C.c_uint64, u64p]
+        L.pa_agg_shard_sizes.argtypes = [vp, u64p, u64p]
+        L.pa_agg_shard_export.argtypes = [vp, C.c_uint64, vp, vp]
+        L.pa_agg_discard.argtypes = [vp]
+        L.pa_agg_stage_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64]
         L.pa_agg_stacktraces.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(abi.PaAggResult)]
         L.pa_agg_last_stack_ids.argtypes = [vp, vp, C.c_uint64]
         L.pa_fix_truncation.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64]
@@ -185,6 +189,21 @@ class Aggregator:
         self._ck(lib().pa_agg_debug_pair_counts(self.h, ls.ctypes.data, st.ctypes.data, ct.ctypes.data, cap, C.byref(n)))
         m = min(int(n.value), cap)
         return ls[:m], st[:m], ct[:m], int(n.value)
+
+    # ---- mode B building blocks (device pointers are plain integers, e.g. torch.Tensor.data_ptr())
+    def shard_sizes(self):
+        nr, nf = C.c_uint64(), C.c_uint64()
+        self._ck(lib().pa_agg_shard_sizes(self.h, C.byref(nr), C.byref(nf)))
+        return int(nr.value), int(nf.value)
+
+    def shard_export(self, frame_base, hdr_ptr, frames_ptr):
+        self._ck(lib().pa_agg_shard_export(self.h, frame_base, hdr_ptr, frames_ptr))
+
+    def discard(self):
+        self._ck(lib().pa_agg_discard(self.h))
+
+    def stage_device(self, hdr_ptr, n_rows, frames_ptr, n_frames):
+        self._ck(lib().pa_agg_stage_device(self.h, hdr_ptr, n_rows, frames_ptr, n_frames))
 
     def stacktraces(self, ids):
         """v1: the stacktrace record for the concatenated 16-byte ids (buildStacktraceRecord)."""

@@ -567,3 +567,76 @@ def test_stacktrace_custom_unknown_type_and_errors(oracle, gpu):
         a2.stacktraces(b"\x00" * 16)
     assert e.value.code == -22
     a2.close()
+
+
+# ---- multi-GPU mode B: one merged batch from pid-hash shards (here: several shard aggregators on one GPU) ----------
+def merged_from_shards(gpu, w, world, schema):
+    from parca_agent_b200 import sharded
+    rows = sharded.shard_rows(w, world)
+    shards = []
+    for idx in rows:
+        part = w.rows(idx)
+        part.schema = abi.PA_SCHEMA_V2
+        a = gpu.from_workload(part)
+        gpu.load(a, part)
+        a.stage()
+        a.process()
+        shards.append((a, idx))
+    m = gpu.Aggregator(hash_mode=abi.PA_HASH_PROVIDED, label_flags=w.label_flags, samples_per_second=w.samples_per_second,
+                       external_labels=w.external_labels, max_samples=max(w.n, 1), max_frames=max(w.n_frame_ids, 1), schema=schema)
+    assert m.register_strings(w.strings[1:]) == 1
+    m.register_frames(w.frames)
+    m.register_labelsets(w.labelsets)
+    res = sharded.merge_local(shards, m)
+    data = res.ipc_bytes()
+    for a, _ in shards:
+        a.close()
+    return data, res, m, [len(i) for i in rows]
+
+
+@pytest.mark.parametrize("schema", [abi.PA_SCHEMA_V2, abi.PA_SCHEMA_V1])
+@pytest.mark.parametrize("world", [2, 3])
+def test_mode_b_merged_batch_equals_unsharded_oracle(oracle, gpu, schema, world):
+    """Shards hash and deduplicate on their own; the merged batch must be byte-for-byte what the reference path gives on
+    the unsharded stream (global first-occurrence order of every dictionary, run ends across shard boundaries, stacks
+    seen by several shards, provided-id collisions whose first occurrence sits on another shard)."""
+    cases = [synth.edge_workload(seed=21, n=4000, hash_mode=abi.PA_HASH_PROVIDED), synth.edge_workload(seed=22, n=4000, hash_mode=abi.PA_HASH_XXH64X2),
+             synth.config3(n=60_000, u=4_000, p=4_096, npids=64, lsets=6), synth.ragged(n=20_000, u=1_500, p=2_048)]
+    for w in cases:
+        w.schema = schema
+        want, st = oracle.run(w)
+        got, res, m, sizes = merged_from_shards(gpu, w, world, schema)
+        assert min(sizes) > 0 and sum(sizes) == w.n
+        if got != want:
+            ex = pyref.extract_v1 if schema == abi.PA_SCHEMA_V1 else pyref.extract
+            d = pyref.diff(ex(pa.ipc.open_stream(want).read_all()), ex(pa.ipc.open_stream(got).read_all()))
+            raise AssertionError("%s world=%d: merged IPC differs (len %d vs %d): %s" % (w.name, world, len(want), len(got), d))
+        assert res.n_rows == w.n and res.n_unique_stacks == st["unique_stacks"]
+        m.close()
+
+
+def test_mode_b_device_staging_rules(gpu):
+    w = synth.edge_workload(seed=3, n=300)
+    a = gpu.from_workload(w)
+    with pytest.raises(gpu.PaError):
+        a.shard_sizes()                                                   # nothing processed yet
+    gpu.load(a, w)
+    a.stage(); a.process()
+    n, nf = a.shard_sizes()
+    assert n == w.n and 0 < nf <= w.n_frame_ids
+    with pytest.raises(gpu.PaError) as e:
+        a.stage_device(0, 0, 0, 0)                                        # a staged batch is still pending
+    assert e.value.code == -22
+    a.collect()
+    a.stage_device(0, 0, 0, 0)                                            # an empty device batch behaves like an empty interval
+    a.process()
+    assert a.collect().n_rows == 0
+    a.close()
+    v1 = as_v1(synth.edge_workload(seed=3, n=300))
+    b = gpu.from_workload(v1)
+    gpu.load(b, v1)
+    b.stage(); b.process()
+    with pytest.raises(gpu.PaError) as e:
+        b.shard_export(0, 1, 1)                                           # v1 aggregators do not gather unique stacks
+    assert e.value.code == -22
+    b.collect(); b.close()

@@ -40,3 +40,14 @@ def test_each_shard_matches_oracle_on_gpu(oracle):
     for rank in range(2):
         w = synth._pid_shard("t", 0x5EED0002, rank, 2, 50_000, 2_000, 4_096, 64, synth.abi.PA_HASH_XXH64X2)
         assert lib.run(w)[0] == oracle.run(w)[0]
+
+
+@pytest.mark.gpu
+def test_mode_b_distributed_merge_two_ranks_one_gpu():
+    """sharded.merge_distributed with two ranks sharing the GPU (gloo, payload staged through host memory): the same
+    orchestration the NCCL path uses, runnable on a 1-GPU box. `PA_DIST_BACKEND=nccl` + one GPU per rank is the real thing."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", PA_DIST_BACKEND="gloo")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(ROOT, "tests", "dist_merge_check.py")], capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "merge-check ok world=2 backend=gloo" in p.stdout
