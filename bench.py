@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--hash-mode", default="xxh64x2", choices=["xxh64x2", "provided"],
                     help="xxh64x2 = GPU hashes every stack (headline); provided = trace.Hash arrives with the sample, as in the reference")
     ap.add_argument("--schema", default="v2", choices=["v2", "v1"], help="sample record schema (v1 = the reference's default, stacktrace ids only)")
+    ap.add_argument("--merge", action="store_true", help="N>1 only: additionally time mode B (one merged batch on rank 0: shards hash/dedup, "
+                    "NVLink send of 64 B/row + unique-stack frames, merged provided-id pass); reported under \"mode_b\", the headline stays mode A")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="BASELINE.json config: 2 = headline (default), 3 = Zipf/CUDA-origin/50k labelsets")
     return ap.parse_args()
 
@@ -196,6 +198,65 @@ def run_stream(args, local):
         a.close()
 
 
+def run_mode_b(args, rank, world, local, barrier):
+    """One merged batch (SURVEY 8e mode B) with inputs resident on every shard. Every rank builds the same global stream
+    (config 2 with samples x world rows), keeps the rows whose xxh64(pid) % world is its rank, and per step runs its own
+    pass, exports 64 B per row + its unique stacks' frames, sends them to rank 0 over NCCL; rank 0 scatters the rows to their
+    global positions and runs the provided-id pass over the union. Wall clock with a barrier and a device synchronize on both
+    sides, max over ranks (several streams and NCCL are involved, so not a single event pair)."""
+    import torch
+    import torch.distributed as dist
+    from parca_agent_b200 import abi, lib, sharded, synth
+    mode = abi.PA_HASH_PROVIDED if args.hash_mode == "provided" else abi.PA_HASH_XXH64X2
+    full = synth.config2(n=args.samples * world, hash_mode=mode)
+    gidx = sharded.shard_rows(full, world)[rank]
+    w = full.rows(gidx)
+    w.schema = abi.PA_SCHEMA_V2
+    a = lib.from_workload(w, device=local, max_samples=w.n, max_frames=w.n_frame_ids, chunk_samples=1 << 20)
+    lib.load(a, w)
+    a.stage()
+    a.process()
+    n, nf = a.shard_sizes()
+    tot = torch.tensor([n, nf], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot)
+    merged = None
+    if rank == 0:
+        merged = lib.Aggregator(device=local, hash_mode=abi.PA_HASH_PROVIDED, label_flags=full.label_flags, samples_per_second=full.samples_per_second,
+                                external_labels=full.external_labels, max_samples=int(tot[0]), max_frames=int(tot[1]) + 1024,
+                                schema=abi.PA_SCHEMA_V1 if args.schema == "v1" else abi.PA_SCHEMA_V2)
+        merged.register_strings(full.strings[1:])
+        merged.register_frames(full.frames)
+        merged.register_labelsets(full.labelsets)
+    gidx = torch.as_tensor(gidx, device="cuda")  # the global row index travels with the rows (8 B per row)
+    times, res = [], None
+    for it in range(args.warmup + args.steps):
+        if it:  # re-stage the shard's batch (untimed): merge_distributed discards it
+            lib.load(a, w)
+            a.stage()
+        barrier()
+        t0 = time.perf_counter()
+        a.process()
+        sharded.merge_distributed(a, gidx, merged, dst=0, device=local, collect=False)
+        barrier()
+        dt = time.perf_counter() - t0
+        if rank == 0:
+            ms, _ = merged.kernel_ms("total")
+            res = merged.collect()
+        if it >= args.warmup:
+            times.append(dt)
+    t = torch.tensor([float(np.sum(times))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        out = {"value": int(tot[0]) * len(times) / float(t[0]), "unit": "samples/s", "ms_per_step": 1e3 * float(t[0]) / len(times),
+               "merged_pass_ms_on_rank0": ms, "rows": res.n_rows, "unique_stacks": res.n_unique_stacks, "ipc_bytes": res.ipc_len,
+               "nvlink_bytes_per_step": int((int(tot[0]) - n) * 72 + (int(tot[1]) - nf) * 8),
+               "note": "inputs resident on the shards; one merged record on rank 0; all shards register the same tables"}
+        merged.close()
+    a.close()
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -334,8 +395,13 @@ def main():
         }
         if v1_st:
             out["v1_stacktrace_record"] = v1_st
-        print(json.dumps(out))
     a.close()
+    if args.merge and world > 1:
+        mode_b = run_mode_b(args, rank, world, local, barrier)
+        if rank == 0:
+            out["mode_b"] = mode_b
+    if rank == 0:
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

@@ -23,11 +23,11 @@ def _export(a, frame_base, device):
     return hdr[:n], frames[:nf]
 
 
-def _stage_merged(merged, hdr_all, frames_all, device):
+def _stage_merged(merged, hdr_all, frames_all, device, collect=True):
     torch.cuda.synchronize(device)
     merged.stage_device(hdr_all.data_ptr(), hdr_all.shape[0], frames_all.data_ptr(), frames_all.shape[0])
     merged.process()
-    return merged.collect()
+    return merged.collect() if collect else None
 
 
 def merge_local(shards, merged, device=0):
@@ -52,11 +52,12 @@ def merge_local(shards, merged, device=0):
     return _stage_merged(merged, hdr_all, frames_all[:nf_total], dev)
 
 
-def merge_distributed(a, gidx, merged=None, dst=0, device=None):
+def merge_distributed(a, gidx, merged=None, dst=0, device=None, collect=True):
     """One process per GPU (torch.distributed initialised). Every rank passes its processed shard aggregator and the global
     row indices of its rows; rank `dst` also passes the merging aggregator and gets the merged result, the others get None.
     NCCL: three point-to-point sends per rank to `dst`. With the gloo backend (CPU tests) the payload is staged through host
-    memory; the library calls are the same."""
+    memory; the library calls are the same. collect=False leaves the merged batch processed but uncollected on `dst`
+    (benchmarks that time the device-resident step; follow with merged.collect() or merged.discard())."""
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
@@ -69,7 +70,7 @@ def merge_distributed(a, gidx, merged=None, dst=0, device=None):
     allsz = [(int(t[0]), int(t[1])) for t in allsz]
     base = sum(s[1] for s in allsz[:rank])
     hdr, frames = _export(a, base, dev)
-    idx = torch.as_tensor(np.asarray(gidx, dtype=np.int64), device=dev)
+    idx = gidx.to(dev) if torch.is_tensor(gidx) else torch.as_tensor(np.asarray(gidx, dtype=np.int64), device=dev)
     a.discard()
     if rank != dst:
         for t in (hdr, idx, frames):
@@ -94,7 +95,7 @@ def merge_distributed(a, gidx, merged=None, dst=0, device=None):
             hdr_all[i] = h
         frames_all[off:off + rnf] = f
         off += rnf
-    return _stage_merged(merged, hdr_all, frames_all[:nf_total], dev)
+    return _stage_merged(merged, hdr_all, frames_all[:nf_total], dev, collect)
 
 
 def shard_rows(w, world):
