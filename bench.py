@@ -228,6 +228,10 @@ def run_mode_b(args, rank, world, local, barrier):
         merged.register_frames(full.frames)
         merged.register_labelsets(full.labelsets)
     gidx = torch.as_tensor(gidx, device="cuda")  # the global row index travels with the rows (8 B per row)
+    allsz = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(allsz, torch.tensor([n, nf], dtype=torch.int64, device="cuda"))
+    sizes = [(int(t[0]), int(t[1])) for t in allsz]  # the same batch is re-merged every step: sizes are known
+    phases = {} if os.environ.get("PA_MERGE_PROFILE") else None
     times, res = [], None
     for it in range(args.warmup + args.steps):
         if it:  # re-stage the shard's batch (untimed): merge_distributed discards it
@@ -236,7 +240,7 @@ def run_mode_b(args, rank, world, local, barrier):
         barrier()
         t0 = time.perf_counter()
         a.process()
-        sharded.merge_distributed(a, gidx, merged, dst=0, device=local, collect=False)
+        sharded.merge_distributed(a, gidx, merged, dst=0, device=local, collect=False, sizes=sizes, phases=phases if it >= args.warmup else None)
         barrier()
         dt = time.perf_counter() - t0
         if rank == 0:
@@ -252,6 +256,8 @@ def run_mode_b(args, rank, world, local, barrier):
                "merged_pass_ms_on_rank0": ms, "rows": res.n_rows, "unique_stacks": res.n_unique_stacks, "ipc_bytes": res.ipc_len,
                "nvlink_bytes_per_step": int((int(tot[0]) - n) * 72 + (int(tot[1]) - nf) * 8),
                "note": "inputs resident on the shards; one merged record on rank 0; all shards register the same tables"}
+        if phases:
+            out["phases_ms_per_step"] = {k: v / len(times) for k, v in phases.items()}
         merged.close()
     a.close()
     return out

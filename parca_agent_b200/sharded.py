@@ -38,64 +38,98 @@ def merge_local(shards, merged, device=0):
     dev = torch.device("cuda", device)
     sizes = [a.shard_sizes() for a, _ in shards]
     n_total, nf_total = sum(s[0] for s in sizes), sum(s[1] for s in sizes)
-    hdr_all = torch.empty((n_total, 64), dtype=torch.uint8, device=dev)
+    hdr_all = torch.empty((n_total, 8), dtype=torch.int64, device=dev)  # one 64-byte header = 8 words
     frames_all = torch.empty(max(nf_total, 1), dtype=torch.int64, device=dev)
     base = 0
     for (a, gidx), (n, nf) in zip(shards, sizes):
         hdr, frames = _export(a, base, dev)
         if n:
-            hdr_all[torch.as_tensor(np.asarray(gidx, dtype=np.int64), device=dev)] = hdr
+            hdr_all[torch.as_tensor(np.asarray(gidx, dtype=np.int64), device=dev)] = hdr.view(torch.int64).view(n, 8)
         frames_all[base:base + nf] = frames
         base += nf
     for a, _ in shards:
         a.discard()  # the shard's own record is not needed
-    return _stage_merged(merged, hdr_all, frames_all[:nf_total], dev)
+    return _stage_merged(merged, hdr_all.view(torch.uint8).view(n_total, 64), frames_all[:nf_total], dev)
 
 
-def merge_distributed(a, gidx, merged=None, dst=0, device=None, collect=True):
+def merge_distributed(a, gidx, merged=None, dst=0, device=None, collect=True, sizes=None, phases=None):
     """One process per GPU (torch.distributed initialised). Every rank passes its processed shard aggregator and the global
     row indices of its rows; rank `dst` also passes the merging aggregator and gets the merged result, the others get None.
-    NCCL: three point-to-point sends per rank to `dst`. With the gloo backend (CPU tests) the payload is staged through host
-    memory; the library calls are the same. collect=False leaves the merged batch processed but uncollected on `dst`
-    (benchmarks that time the device-resident step; follow with merged.collect() or merged.discard())."""
+    NCCL: one batched group of point-to-point sends per rank to `dst`. With the gloo backend (CPU tests) the payload is staged
+    through host memory; the library calls are the same. collect=False leaves the merged batch processed but uncollected on
+    `dst` (benchmarks that time the device-resident step; follow with merged.collect() or merged.discard()).
+    sizes: [(rows, frames)] per rank if already known (skips the all_gather). phases: a dict that receives wall-clock
+    milliseconds per phase (adds device synchronisations; profiling only)."""
+    import time
+
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
     via_host = dist.get_backend() != "nccl"
     comm_dev = torch.device("cpu") if via_host else dev
+    t_last = [time.perf_counter()]
+
+    def mark(name):
+        if phases is not None:
+            torch.cuda.synchronize(dev)
+            now = time.perf_counter()
+            phases[name] = phases.get(name, 0.0) + 1e3 * (now - t_last[0])
+            t_last[0] = now
+
     n, nf = a.shard_sizes()
-    mine = torch.tensor([n, nf], dtype=torch.int64, device=comm_dev)
-    allsz = [torch.zeros(2, dtype=torch.int64, device=comm_dev) for _ in range(world)]
-    dist.all_gather(allsz, mine)
-    allsz = [(int(t[0]), int(t[1])) for t in allsz]
-    base = sum(s[1] for s in allsz[:rank])
+    if sizes is None:
+        mine = torch.tensor([n, nf], dtype=torch.int64, device=comm_dev)
+        allsz = [torch.zeros(2, dtype=torch.int64, device=comm_dev) for _ in range(world)]
+        dist.all_gather(allsz, mine)
+        sizes = [(int(t[0]), int(t[1])) for t in allsz]
+    assert sizes[rank] == (n, nf)
+    base = sum(s[1] for s in sizes[:rank])
+    mark("sizes")
     hdr, frames = _export(a, base, dev)
     idx = gidx.to(dev) if torch.is_tensor(gidx) else torch.as_tensor(np.asarray(gidx, dtype=np.int64), device=dev)
     a.discard()
+    mark("export")
     if rank != dst:
-        for t in (hdr, idx, frames):
-            dist.send(t.to(comm_dev).contiguous(), dst)
+        payload = [t.to(comm_dev).contiguous() for t in (hdr, idx, frames)]
+        if via_host:
+            for t in payload:
+                dist.send(t, dst)
+        else:
+            for w_ in dist.batch_isend_irecv([dist.P2POp(dist.isend, t, dst) for t in payload if t.numel()]):
+                w_.wait()
+        mark("send")
         return None
-    n_total, nf_total = sum(s[0] for s in allsz), sum(s[1] for s in allsz)
-    hdr_all = torch.empty((n_total, 64), dtype=torch.uint8, device=dev)
+    n_total, nf_total = sum(s[0] for s in sizes), sum(s[1] for s in sizes)
+    hdr_all = torch.empty((n_total, 8), dtype=torch.int64, device=dev)  # one 64-byte header = 8 words: the scatter moves words, not bytes
     frames_all = torch.empty(max(nf_total, 1), dtype=torch.int64, device=dev)
+    recv, ops = {}, []
+    for r in range(world):
+        if r == dst:
+            continue
+        rn, rnf = sizes[r]
+        recv[r] = (torch.empty((rn, 64), dtype=torch.uint8, device=comm_dev), torch.empty(rn, dtype=torch.int64, device=comm_dev),
+                   torch.empty(rnf, dtype=torch.int64, device=comm_dev))
+        if via_host:
+            for t in recv[r]:
+                dist.recv(t, r)
+        else:
+            ops += [dist.P2POp(dist.irecv, t, r) for t in recv[r] if t.numel()]
+    if ops:
+        for w_ in dist.batch_isend_irecv(ops):
+            w_.wait()
+    mark("recv")
     off = 0
     for r in range(world):
-        rn, rnf = allsz[r]
-        if r == dst:
-            h, i, f = hdr, idx, frames
-        else:
-            h = torch.empty((rn, 64), dtype=torch.uint8, device=comm_dev)
-            i = torch.empty(rn, dtype=torch.int64, device=comm_dev)
-            f = torch.empty(rnf, dtype=torch.int64, device=comm_dev)
-            for t in (h, i, f):
-                dist.recv(t, r)
-            h, i, f = h.to(dev), i.to(dev), f.to(dev)
+        rn, rnf = sizes[r]
+        h, i, f = (hdr, idx, frames) if r == dst else tuple(t.to(dev) for t in recv[r])
         if rn:
-            hdr_all[i] = h
+            hdr_all[i] = h.view(torch.int64).view(rn, 8)
         frames_all[off:off + rnf] = f
         off += rnf
-    return _stage_merged(merged, hdr_all, frames_all[:nf_total], dev, collect)
+    mark("scatter")
+    out = _stage_merged(merged, hdr_all.view(torch.uint8).view(n_total, 64), frames_all[:nf_total], dev, collect)
+    mark("merged_pass")
+    return out
 
 
 def shard_rows(w, world):
