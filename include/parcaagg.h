@@ -236,6 +236,18 @@ int pa_agg_discard(pa_agg* a);
  * pinned ring; the caller's writes to both buffers must have completed. Follow with pa_agg_process + pa_agg_collect. */
 int pa_agg_stage_device(pa_agg* a, const pa_sample_hdr* hdr, uint64_t n_rows, const uint64_t* frames, uint64_t n_frames);
 
+/* the same, with the scatter to global row order done by the library: part p holds n_rows headers whose positions in the
+ * merged batch are global_row[i] (all parts together must cover 0..n_rows_total-1 exactly once) and the frames its
+ * headers' frame_off point into, already based so that the parts' frame blocks concatenate in part order. */
+typedef struct pa_device_part {
+  const pa_sample_hdr* hdr;
+  const uint64_t* global_row;
+  uint64_t n_rows;
+  const uint64_t* frames;
+  uint64_t n_frames;
+} pa_device_part;
+int pa_agg_stage_device_parts(pa_agg* a, const pa_device_part* parts, uint32_t n_parts, uint64_t n_rows_total);
+
 /* host helpers restating reference functions (no GPU involved) */
 /* maybeFixTruncation (reporter/parca_reporter.go:190-216): returns the fixed length, or -1. */
 int64_t pa_fix_truncation(const uint8_t* s, uint64_t len, uint64_t max_len);

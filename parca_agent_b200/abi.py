@@ -65,6 +65,10 @@ class PaAggResult(C.Structure):
     ]
 
 
+class PaDevicePart(C.Structure):
+    _fields_ = [("hdr", C.c_void_p), ("global_row", C.c_void_p), ("n_rows", C.c_uint64), ("frames", C.c_void_p), ("n_frames", C.c_uint64)]
+
+
 def pack_strings(strs):
     """list[bytes] → (bytes blob, uint32 offsets[n+1])."""
     offs = np.zeros(len(strs) + 1, dtype=np.uint32)

@@ -1525,6 +1525,48 @@ static int stage_device(pa_agg* a, const pa_sample_hdr* hdr, uint64_t n_rows, co
   return PA_OK;
 }
 
+static int stage_device_parts(pa_agg* a, const pa_device_part* parts, uint32_t n_parts, uint64_t n_total) {
+  CK(cudaSetDevice(a->device));
+  if (a->staged >= 0) return a->fail(PA_EINVAL, "the previously staged batch has not been collected");
+  if (n_parts && !parts) return a->fail(PA_EINVAL, "null parts");
+  uint64_t rows = 0, nfr = 0;
+  for (uint32_t p = 0; p < n_parts; p++) {
+    if ((parts[p].n_rows && (!parts[p].hdr || !parts[p].global_row)) || (parts[p].n_frames && !parts[p].frames)) return a->fail(PA_EINVAL, "null device buffer");
+    rows += parts[p].n_rows;
+    nfr += parts[p].n_frames;
+  }
+  if (rows != n_total) return a->fail(PA_EINVAL, "the parts do not add up to n_rows_total");
+  if (n_total > a->cfg.max_samples || nfr > a->cfg.max_frames) return a->fail(PA_ENOSPC, "device batch exceeds max_samples / max_frames");
+  CK(a->d_frames.ensure(std::max<uint64_t>(nfr, 1) * 8));
+  CK(a->d_st1.ensure(256));
+  uint32_t* bad = a->d_st1.as<uint32_t>();
+  cudaStream_t s = a->s_copy;
+  CK(cudaEventRecord(a->ev_h2d0, s));
+  CK(cudaMemsetAsync(bad, 0, 4, s));
+  uint64_t foff = 0;
+  for (uint32_t p = 0; p < n_parts; p++) {
+    if (parts[p].n_rows)
+      k_scatter_rows<<<small_grid(a, parts[p].n_rows * 4), kThreads, 0, s>>>((const uint4*)parts[p].hdr, (const unsigned long long*)parts[p].global_row, parts[p].n_rows,
+                                                                              n_total, a->d_hdr.as<uint4>(), bad);
+    if (parts[p].n_frames) CK(cudaMemcpyAsync(a->d_frames.as<uint64_t>() + foff, parts[p].frames, parts[p].n_frames * 8, cudaMemcpyDeviceToDevice, s));
+    foff += parts[p].n_frames;
+  }
+  uint32_t h_bad = 0;
+  CK(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(a->ev_h2d1, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  if (h_bad) return a->fail(PA_EINVAL, "global_row out of range");
+  a->staged = a->active;
+  a->src_frames = a->d_frames.as<unsigned long long>();
+  a->N = n_total;
+  a->NF = nfr;
+  a->processed = false;
+  a->chunk_rows.clear();
+  a->chunk_frames_end.clear();
+  return PA_OK;
+}
+
 static int shard_export(pa_agg* a, uint64_t frame_base, pa_sample_hdr* hdr_out, uint64_t* frames_out) {
   if (a->cfg.schema != PA_SCHEMA_V2) return a->fail(PA_EINVAL, "shard export needs a PA_SCHEMA_V2 aggregator (the v2 pipeline gathers the unique stacks)");
   if (a->staged < 0 || !a->processed) return a->fail(PA_EINVAL, "shard export needs a processed, not yet collected batch");
@@ -1555,6 +1597,11 @@ int pa_agg_shard_export(pa_agg* a, uint64_t frame_base, pa_sample_hdr* hdr_out, 
   if (!a) return PA_EINVAL;
   std::lock_guard<std::mutex> g(a->flush_mu);
   return shard_export(a, frame_base, hdr_out, frames_out);
+}
+int pa_agg_stage_device_parts(pa_agg* a, const pa_device_part* parts, uint32_t n_parts, uint64_t n_rows_total) {
+  if (!a) return PA_EINVAL;
+  std::lock_guard<std::mutex> g(a->flush_mu);
+  return stage_device_parts(a, parts, n_parts, n_rows_total);
 }
 int pa_agg_discard(pa_agg* a) {
   if (!a) return PA_EINVAL;

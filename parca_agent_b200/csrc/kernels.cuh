@@ -1613,4 +1613,16 @@ __global__ void __launch_bounds__(kThreads) k_shard_export_frames(const Counters
   for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) out[i] = loc_order[ustream[i]];
 }
 
+// merging GPU: rows of one shard -> their positions in the global order, written straight into the staging buffer
+// (four threads per 64-byte row: coalesced reads, one full row per scattered write)
+__global__ void __launch_bounds__(kThreads) k_scatter_rows(const uint4* src, const unsigned long long* global_row, unsigned long long n_rows,
+                                                           unsigned long long n_total, uint4* dst, uint32_t* bad) {
+  const unsigned long long n4 = n_rows * 4ull;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; t < n4; t += (unsigned long long)gridDim.x * kThreads) {
+    unsigned long long g = global_row[t >> 2];
+    if (g >= n_total) { *bad = 1u; continue; }
+    dst[g * 4ull + (t & 3ull)] = __ldg(src + t);
+  }
+}
+
 }  // namespace pa

@@ -18,7 +18,7 @@ EXPORTS = [
     "pa_agg_create", "pa_agg_destroy", "pa_agg_last_error", "pa_agg_abi_version", "pa_agg_register_strings",
     "pa_agg_register_frames", "pa_agg_register_labelsets", "pa_agg_acquire", "pa_agg_commit", "pa_agg_submit",
     "pa_agg_flush", "pa_agg_release", "pa_agg_stage", "pa_agg_process", "pa_agg_collect", "pa_agg_last_kernel_ms",
-    "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_agg_debug_pair_counts", "pa_agg_stacktraces", "pa_agg_last_stack_ids", "pa_agg_shard_sizes", "pa_agg_shard_export", "pa_agg_stage_device", "pa_agg_discard", "pa_fix_truncation", "pa_xxh64",
+    "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_agg_debug_pair_counts", "pa_agg_stacktraces", "pa_agg_last_stack_ids", "pa_agg_shard_sizes", "pa_agg_shard_export", "pa_agg_stage_device", "pa_agg_stage_device_parts", "pa_agg_discard", "pa_fix_truncation", "pa_xxh64",
 ]
 
 
@@ -61,6 +61,7 @@ def lib():
         L.pa_agg_shard_sizes.argtypes = [vp, u64p, u64p]
         L.pa_agg_shard_export.argtypes = [vp, C.c_uint64, vp, vp]
         L.pa_agg_discard.argtypes = [vp]
+        L.pa_agg_stage_device_parts.argtypes = [vp, C.POINTER(abi.PaDevicePart), C.c_uint32, C.c_uint64]
         L.pa_agg_stage_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64]
         L.pa_agg_stacktraces.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(abi.PaAggResult)]
         L.pa_agg_last_stack_ids.argtypes = [vp, vp, C.c_uint64]
@@ -198,6 +199,13 @@ class Aggregator:
 
     def shard_export(self, frame_base, hdr_ptr, frames_ptr):
         self._ck(lib().pa_agg_shard_export(self.h, frame_base, hdr_ptr, frames_ptr))
+
+    def stage_device_parts(self, parts, n_rows_total):
+        """parts: list of (hdr_ptr, global_row_ptr, n_rows, frames_ptr, n_frames) device buffers; rows are scattered to global order."""
+        arr = (abi.PaDevicePart * max(len(parts), 1))()
+        for i, (h, g, n, f, nf) in enumerate(parts):
+            arr[i] = abi.PaDevicePart(h, g, n, f, nf)
+        self._ck(lib().pa_agg_stage_device_parts(self.h, arr, len(parts), n_rows_total))
 
     def discard(self):
         self._ck(lib().pa_agg_discard(self.h))

@@ -30,6 +30,14 @@ def _stage_merged(merged, hdr_all, frames_all, device, collect=True):
     return merged.collect() if collect else None
 
 
+def _stage_parts(merged, parts, n_total, device, collect=True):
+    """rows -> global order inside the library's staging kernel (no intermediate merged copy), then the usual pass"""
+    torch.cuda.synchronize(device)
+    merged.stage_device_parts(parts, n_total)
+    merged.process()
+    return merged.collect() if collect else None
+
+
 def merge_local(shards, merged, device=0):
     """Single process, several aggregators on one GPU (tests, or one host feeding one GPU from several rings).
 
@@ -38,18 +46,16 @@ def merge_local(shards, merged, device=0):
     dev = torch.device("cuda", device)
     sizes = [a.shard_sizes() for a, _ in shards]
     n_total, nf_total = sum(s[0] for s in sizes), sum(s[1] for s in sizes)
-    hdr_all = torch.empty((n_total, 8), dtype=torch.int64, device=dev)  # one 64-byte header = 8 words
-    frames_all = torch.empty(max(nf_total, 1), dtype=torch.int64, device=dev)
-    base = 0
+    base, parts, keep = 0, [], []
     for (a, gidx), (n, nf) in zip(shards, sizes):
         hdr, frames = _export(a, base, dev)
-        if n:
-            hdr_all[torch.as_tensor(np.asarray(gidx, dtype=np.int64), device=dev)] = hdr.view(torch.int64).view(n, 8)
-        frames_all[base:base + nf] = frames
+        idx = torch.as_tensor(np.asarray(gidx, dtype=np.int64), device=dev)
+        keep.append((hdr, frames, idx))
+        parts.append((hdr.data_ptr(), idx.data_ptr(), n, frames.data_ptr(), nf))
         base += nf
     for a, _ in shards:
         a.discard()  # the shard's own record is not needed
-    return _stage_merged(merged, hdr_all.view(torch.uint8).view(n_total, 64), frames_all[:nf_total], dev)
+    return _stage_parts(merged, parts, n_total, dev)
 
 
 def merge_distributed(a, gidx, merged=None, dst=0, device=None, collect=True, sizes=None, phases=None):
@@ -100,15 +106,13 @@ def merge_distributed(a, gidx, merged=None, dst=0, device=None, collect=True, si
         mark("send")
         return None
     n_total, nf_total = sum(s[0] for s in sizes), sum(s[1] for s in sizes)
-    hdr_all = torch.empty((n_total, 8), dtype=torch.int64, device=dev)  # one 64-byte header = 8 words: the scatter moves words, not bytes
-    frames_all = torch.empty(max(nf_total, 1), dtype=torch.int64, device=dev)
     recv, ops = {}, []
     for r in range(world):
         if r == dst:
             continue
         rn, rnf = sizes[r]
-        recv[r] = (torch.empty((rn, 64), dtype=torch.uint8, device=comm_dev), torch.empty(rn, dtype=torch.int64, device=comm_dev),
-                   torch.empty(rnf, dtype=torch.int64, device=comm_dev))
+        recv[r] = (torch.empty((max(rn, 1), 64), dtype=torch.uint8, device=comm_dev)[:rn], torch.empty(max(rn, 1), dtype=torch.int64, device=comm_dev)[:rn],
+                   torch.empty(max(rnf, 1), dtype=torch.int64, device=comm_dev)[:rnf])
         if via_host:
             for t in recv[r]:
                 dist.recv(t, r)
@@ -118,17 +122,14 @@ def merge_distributed(a, gidx, merged=None, dst=0, device=None, collect=True, si
         for w_ in dist.batch_isend_irecv(ops):
             w_.wait()
     mark("recv")
-    off = 0
+    parts, keep = [], []
     for r in range(world):
         rn, rnf = sizes[r]
         h, i, f = (hdr, idx, frames) if r == dst else tuple(t.to(dev) for t in recv[r])
-        if rn:
-            hdr_all[i] = h.view(torch.int64).view(rn, 8)
-        frames_all[off:off + rnf] = f
-        off += rnf
-    mark("scatter")
-    out = _stage_merged(merged, hdr_all.view(torch.uint8).view(n_total, 64), frames_all[:nf_total], dev, collect)
-    mark("merged_pass")
+        keep.append((h, i, f))
+        parts.append((h.data_ptr(), i.data_ptr(), rn, f.data_ptr(), rnf))
+    out = _stage_parts(merged, parts, n_total, dev, collect)
+    mark("scatter_and_merged_pass")
     return out
 
 
