@@ -75,6 +75,9 @@ enum {
 #define PA_SCHEMA_V1 1u /* stacktrace ids only, reporter/arrow.go:260-332 + parca_reporter.go:246-328 (sample record);
                            the follow-up record with the full stacktraces comes from pa_agg_stacktraces */
 
+#define PA_IPC_PLAIN 0u
+#define PA_IPC_LZ4_FRAME 1u
+
 #define PA_NO_STRING 0xFFFFFFFFu /* "no value"; string id 0 is always the empty string "" */
 
 /* One sample = one (trace, meta) pair handed to ReportTraceEvent (:219): 64 bytes. */
@@ -139,7 +142,9 @@ typedef struct pa_agg_config {
   uint64_t stack_cache_frames;  /* v1 only: capacity of the store's frame arena, in frames. 0 = 64 per entry (4 bytes each) */
   uint32_t unknown_frame_type_sid; /* v1 only: string id of libpf.UnknownFrame.String() for the "missing stacktrace"
                                   row (:1561); 0 = the literal "unknown" */
-  uint32_t reserved;
+  uint32_t ipc_compression;    /* PA_IPC_PLAIN (0): uncompressed bodies == the offline-mode bytes (:1779-1790), the bit-exact mode.
+                                  PA_IPC_LZ4_FRAME (1): bodies wrapped like ipc.WithLZ4() (:1851, the gRPC path) — decodes to the
+                                  same record but is NOT byte-identical to the Go writer (different LZ4 encoder) */
 } pa_agg_config;
 
 /* Result of one flush; memory is library-owned (pinned host) until pa_agg_release. */
@@ -247,6 +252,12 @@ typedef struct pa_device_part {
   uint64_t n_frames;
 } pa_device_part;
 int pa_agg_stage_device_parts(pa_agg* a, const pa_device_part* parts, uint32_t n_parts, uint64_t n_rows_total);
+
+/* LZ4_FRAME body compression of a finished, uncompressed stream written by this library (what PA_IPC_LZ4_FRAME applies to
+ * every result). Host only; uses the system liblz4.so.1 through dlopen and fails with PA_EIO when it is missing. *out is
+ * malloc'ed; release it with pa_ipc_free. Flagged: not byte-identical to arrow-go + pierrec/lz4, only record-identical. */
+int pa_ipc_compress_lz4(const uint8_t* ipc, uint64_t len, uint8_t** out, uint64_t* out_len);
+void pa_ipc_free(uint8_t* p);
 
 /* host helpers restating reference functions (no GPU involved) */
 /* maybeFixTruncation (reporter/parca_reporter.go:190-216): returns the fixed length, or -1. */

@@ -20,6 +20,7 @@ PA_XXH_SEED_LO = 0x9E3779B97F4A7C15
 
 PA_LABEL_DISABLE_CPU, PA_LABEL_DISABLE_THREAD_ID, PA_LABEL_DISABLE_THREAD_COMM = 1, 2, 4
 PA_SCHEMA_V2, PA_SCHEMA_V1 = 0, 1
+PA_IPC_PLAIN, PA_IPC_LZ4_FRAME = 0, 1
 PA_NO_STRING = 0xFFFFFFFF
 
 # struct pa_sample_hdr (64 B)
@@ -52,7 +53,7 @@ class PaAggConfig(C.Structure):
         ("samples_per_second", C.c_uint32), ("n_external_labels", C.c_uint32),
         ("external_labels", C.POINTER(PaLabelPair)),
         ("max_samples", C.c_uint64), ("max_frames", C.c_uint64), ("chunk_samples", C.c_uint32), ("schema", C.c_uint32),
-        ("stack_cache_entries", C.c_uint64), ("stack_cache_frames", C.c_uint64), ("unknown_frame_type_sid", C.c_uint32), ("reserved", C.c_uint32),
+        ("stack_cache_entries", C.c_uint64), ("stack_cache_frames", C.c_uint64), ("unknown_frame_type_sid", C.c_uint32), ("ipc_compression", C.c_uint32),
     ]
 
 

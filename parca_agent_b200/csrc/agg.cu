@@ -19,6 +19,7 @@
 
 #include "../../include/parcaagg.h"
 #include "host_tables.hpp"
+#include "ipc_lz4.hpp"
 #include "ipc_out.hpp"
 #include "kernels.cuh"
 
@@ -170,6 +171,7 @@ struct pa_agg {
   uint8_t* h_desc = nullptr;
   size_t h_desc_cap = 0;
   std::vector<std::vector<uint8_t>> hostbufs;  // host-built Arrow buffers of the current result
+  std::vector<uint8_t> comp_out;               // PA_IPC_LZ4_FRAME: the re-encoded stream the result points at
   Timer tm[T_COUNT];
   uint32_t launches = 0;
   double h2d_ms = 0;
@@ -283,7 +285,7 @@ uint32_t pa_agg_abi_version(void) { return PA_ABI_VERSION; }
 const char* pa_agg_last_error(const pa_agg* a) { return a ? a->err.c_str() : "null handle"; }
 
 int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
-  if (!cfg || !out || cfg->abi_version != PA_ABI_VERSION || cfg->samples_per_second == 0 || cfg->max_samples == 0 || cfg->hash_mode > 1 || cfg->schema > 1) return PA_EINVAL;
+  if (!cfg || !out || cfg->abi_version != PA_ABI_VERSION || cfg->samples_per_second == 0 || cfg->max_samples == 0 || cfg->hash_mode > 1 || cfg->schema > 1 || cfg->ipc_compression > 1) return PA_EINVAL;
   if (cfg->max_samples > 0x7FFFFFFFull) return PA_ERANGE;  // run ends / ListView offsets are int32
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return PA_ENODEV;
@@ -1271,11 +1273,19 @@ static int collect(pa_agg* a, pa_agg_result* res) {
   CK(cudaEventRecord(d1, a->s_comp));
   plan.write_host_parts(a->out);  // metadata, host-built buffers, zero fills and padding overlap the D2H
   CK(cudaStreamSynchronize(a->s_comp));
+  const uint8_t* stream = a->out;
+  uint64_t stream_len = plan.total;
+  if (a->cfg.ipc_compression == PA_IPC_LZ4_FRAME) {  // network-path framing (ipc.WithLZ4(), :1851); host work, counted in host_ms
+    std::string why;
+    if (!ipc_compress_lz4(a->out, plan.total, a->comp_out, &why)) return a->fail(PA_EIO, why.c_str());
+    stream = a->comp_out.data();
+    stream_len = a->comp_out.size();
+  }
   double t2 = now_ms();
   float d2h = 0, h2d = 0;
   cudaEventElapsedTime(&d2h, d0, d1);
   cudaEventElapsedTime(&h2d, a->ev_h2d0, a->ev_h2d1);
-  res->ipc = a->out; res->ipc_len = plan.total; res->n_rows = N; res->n_unique_stacks = c.n_unique; res->n_locations = n_loc;
+  res->ipc = stream; res->ipc_len = stream_len; res->n_rows = N; res->n_unique_stacks = c.n_unique; res->n_locations = n_loc;
   res->n_functions = n_fn; res->n_location_indices = n_idx; res->gpu_launches = a->launches;
   res->h2d_ms = h2d; res->gpu_ms = a->tm[T_TOTAL].ms; res->d2h_ms = d2h; res->host_ms = (t1 - t0) + (t2 - t1) - d2h;
   a->staged = -1;
@@ -1491,11 +1501,19 @@ static int stacktraces(pa_agg* a, const uint8_t* ids, uint64_t n, pa_agg_result*
   CK(cudaEventRecord(a->ev_d2h1, s));
   plan.write_host_parts(a->out);
   CK(cudaStreamSynchronize(s));
+  const uint8_t* stream = a->out;
+  uint64_t stream_len = plan.total;
+  if (a->cfg.ipc_compression == PA_IPC_LZ4_FRAME) {
+    std::string why;
+    if (!ipc_compress_lz4(a->out, plan.total, a->comp_out, &why)) return a->fail(PA_EIO, why.c_str());
+    stream = a->comp_out.data();
+    stream_len = a->comp_out.size();
+  }
   const double t2 = now_ms();
   float d2h = 0, gpu = 0;
   cudaEventElapsedTime(&d2h, a->ev_d2h0, a->ev_d2h1);
   cudaEventElapsedTime(&gpu, a->tm[T_TOTAL].a, a->tm[T_TOTAL].b);
-  res->ipc = a->out; res->ipc_len = plan.total; res->n_rows = n; res->n_unique_stacks = n; res->n_locations = L; res->n_functions = c.n_dict[4];
+  res->ipc = stream; res->ipc_len = stream_len; res->n_rows = n; res->n_unique_stacks = n; res->n_locations = L; res->n_functions = c.n_dict[4];
   res->n_location_indices = NL; res->gpu_launches = tm.launches; res->gpu_ms = gpu; res->d2h_ms = d2h; res->host_ms = (t2 - t0) - gpu - d2h;
   if (res->host_ms < 0) res->host_ms = 0;
   (void)t1;
@@ -1745,6 +1763,20 @@ int pa_agg_debug_pair_counts(pa_agg* a, uint32_t* labelset_ids, uint32_t* stack_
   scratch.release();
   return rc;
 }
+
+int pa_ipc_compress_lz4(const uint8_t* ipc, uint64_t len, uint8_t** out, uint64_t* out_len) {
+  if (!ipc || !out || !out_len) return PA_EINVAL;
+  std::vector<uint8_t> v;
+  std::string why;
+  if (!ipc_compress_lz4(ipc, len, v, &why)) return why.find("liblz4") != std::string::npos || why.find("LZ4F") != std::string::npos ? PA_EIO : PA_EINVAL;
+  uint8_t* p = (uint8_t*)malloc(std::max<size_t>(v.size(), 1));
+  if (!p) return PA_ENOMEM;
+  memcpy(p, v.data(), v.size());
+  *out = p;
+  *out_len = v.size();
+  return PA_OK;
+}
+void pa_ipc_free(uint8_t* p) { free(p); }
 
 // ---- host helpers ------------------------------------------------------------------------------
 static bool valid_utf8(const uint8_t* s, uint64_t n) {  // unicode/utf8.ValidString

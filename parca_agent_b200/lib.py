@@ -18,7 +18,7 @@ EXPORTS = [
     "pa_agg_create", "pa_agg_destroy", "pa_agg_last_error", "pa_agg_abi_version", "pa_agg_register_strings",
     "pa_agg_register_frames", "pa_agg_register_labelsets", "pa_agg_acquire", "pa_agg_commit", "pa_agg_submit",
     "pa_agg_flush", "pa_agg_release", "pa_agg_stage", "pa_agg_process", "pa_agg_collect", "pa_agg_last_kernel_ms",
-    "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_agg_debug_pair_counts", "pa_agg_stacktraces", "pa_agg_last_stack_ids", "pa_agg_shard_sizes", "pa_agg_shard_export", "pa_agg_stage_device", "pa_agg_stage_device_parts", "pa_agg_discard", "pa_fix_truncation", "pa_xxh64",
+    "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_agg_debug_pair_counts", "pa_agg_stacktraces", "pa_agg_last_stack_ids", "pa_agg_shard_sizes", "pa_agg_shard_export", "pa_agg_stage_device", "pa_agg_stage_device_parts", "pa_agg_discard", "pa_ipc_compress_lz4", "pa_ipc_free", "pa_fix_truncation", "pa_xxh64",
 ]
 
 
@@ -61,6 +61,9 @@ def lib():
         L.pa_agg_shard_sizes.argtypes = [vp, u64p, u64p]
         L.pa_agg_shard_export.argtypes = [vp, C.c_uint64, vp, vp]
         L.pa_agg_discard.argtypes = [vp]
+        L.pa_ipc_compress_lz4.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.POINTER(C.c_uint8)), u64p]
+        L.pa_ipc_free.argtypes = [C.POINTER(C.c_uint8)]
+        L.pa_ipc_free.restype = None
         L.pa_agg_stage_device_parts.argtypes = [vp, C.POINTER(abi.PaDevicePart), C.c_uint32, C.c_uint64]
         L.pa_agg_stage_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64]
         L.pa_agg_stacktraces.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(abi.PaAggResult)]
@@ -97,7 +100,7 @@ class Aggregator:
 
     def __init__(self, device=0, hash_mode=abi.PA_HASH_XXH64X2, label_flags=0, samples_per_second=19, external_labels=(),
                  max_samples=1 << 20, max_frames=0, chunk_samples=0, schema=abi.PA_SCHEMA_V2, stack_cache_entries=0, stack_cache_frames=0,
-                 unknown_frame_type_sid=0):
+                 unknown_frame_type_sid=0, ipc_compression=abi.PA_IPC_PLAIN):
         L = lib()
         ext = (abi.PaLabelPair * max(1, len(external_labels)))()
         for i, (n, v) in enumerate(external_labels):
@@ -105,7 +108,8 @@ class Aggregator:
         cfg = abi.PaAggConfig(abi_version=abi.PA_ABI_VERSION, device=device, hash_mode=hash_mode, label_flags=label_flags,
                               samples_per_second=samples_per_second, n_external_labels=len(external_labels), external_labels=ext,
                               max_samples=max_samples, max_frames=max_frames, chunk_samples=chunk_samples, schema=schema,
-                              stack_cache_entries=stack_cache_entries, stack_cache_frames=stack_cache_frames, unknown_frame_type_sid=unknown_frame_type_sid)
+                              stack_cache_entries=stack_cache_entries, stack_cache_frames=stack_cache_frames, unknown_frame_type_sid=unknown_frame_type_sid,
+                              ipc_compression=ipc_compression)
         h = C.c_void_p()
         rc = L.pa_agg_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -274,6 +278,18 @@ def run(w, device=0, chunk_samples=0):
     data = r.ipc_bytes()
     a.close()
     return data, r
+
+
+def compress_lz4(ipc):
+    """LZ4_FRAME body compression of an uncompressed stream (host only; record-identical, not Go-byte-identical)."""
+    p, n = C.POINTER(C.c_uint8)(), C.c_uint64()
+    rc = lib().pa_ipc_compress_lz4(bytes(ipc), len(ipc), C.byref(p), C.byref(n))
+    if rc != 0:
+        raise PaError(rc, "pa_ipc_compress_lz4 failed")
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        lib().pa_ipc_free(p)
 
 
 def fix_truncation(s, max_len):
