@@ -51,3 +51,18 @@ def test_mode_b_distributed_merge_two_ranks_one_gpu():
                         "--master-port", "29517", os.path.join(ROOT, "tests", "dist_merge_check.py")], capture_output=True, text=True, env=env, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "merge-check ok world=2 backend=gloo" in p.stdout
+
+
+def test_shard_rows_partition_and_keep_order():
+    """sharded.shard_rows: every row lands on exactly one shard, a pid never straddles shards, row order inside a shard is
+    the global order (what makes the merged batch's first-occurrence ranks come out right)."""
+    from parca_agent_b200 import sharded
+    w = synth.config3(n=20_000, u=500, p=1_024, npids=200, lsets=3)
+    for world in (1, 2, 3, 8):
+        rows = sharded.shard_rows(w, world)
+        assert len(rows) == world
+        allr = np.concatenate(rows)
+        assert len(allr) == w.n and np.array_equal(np.sort(allr), np.arange(w.n))
+        for r, idx in enumerate(rows):
+            assert np.all(np.diff(idx) > 0)
+            assert all(synth.xxh64_u32(int(p)) % world == r for p in np.unique(w.hdrs["pid"][idx]))
