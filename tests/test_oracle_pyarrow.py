@@ -170,3 +170,19 @@ def test_stacktrace_record_degenerate(oracle):
     empties = [k for k, v in known.items() if len(v) == 0]
     assert empties
     check_stacktraces(oracle, w, ids=empties)                 # only empty stacks: zero locations, null list entries
+
+
+@pytest.mark.parametrize("seed", list(range(10, 22)))
+def test_stacktrace_record_random_batches(oracle, seed):
+    """More seeds of the adversarial generator, random request orders: the oracle's buildStacktraceRecord against the literal
+    Python transcription (the only pin this record has — the reference ships no test for it)."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    mode = abi.PA_HASH_PROVIDED if seed % 2 else abi.PA_HASH_XXH64X2
+    w = synth.edge_workload(seed=seed, n=int(rng.integers(50, 1500)), hash_mode=mode)
+    known = pyref.known_stacks(w)
+    ids = list(known.keys())
+    rng.shuffle(ids)
+    ids = ids[: int(rng.integers(0, len(ids) + 1))] + [bytes(rng.integers(0, 256, 16, dtype=np.uint8)) for _ in range(int(rng.integers(0, 3)))]
+    rng.shuffle(ids)
+    check_stacktraces(oracle, w, ids=ids)
