@@ -239,6 +239,31 @@ int ParcaReporter::ReportTraceEvent(const Trace* trace, const TraceEventMeta* me
   return 0;                                // the reference returns nil in every V2 branch (:365)
 }
 
+int ParcaReporter::SampleEvents(const std::vector<MemorySample>& samples, const OomprofSampleMeta& meta) {
+  TraceEventMeta m;
+  m.Timestamp = meta.Timestamp;
+  m.Comm = meta.Comm;
+  m.Origin = TraceOriginMemory;
+  m.PID = meta.PID;
+  m.TID = meta.PID;  // "For oomprof, TID is same as PID" (:725)
+  for (const MemorySample& sample : samples) {
+    Trace t;  // Hash is never set on this path: all oomprof traces share the zero id, as in the reference
+    for (uint64_t addr : sample.Addresses) {
+      Frame f;
+      f.Type = FrameType{PA_FRAME_OOMPROF, "native"};  // appendLocationV2 reports libpf.NativeFrame.String() for these (:518)
+      f.AddressOrLineno = addr;
+      f.FunctionName = meta.BuildID;
+      f.SourceFile = meta.ExecutablePath;
+      t.Frames.push_back(std::move(f));
+    }
+    t.CustomLabels = meta.CustomLabels;
+    m.OriginData = &sample;
+    int rc = ReportTraceEvent(&t, &m);
+    if (rc) return rc;  // "failed to report oomprof trace event" (:753)
+  }
+  return 0;
+}
+
 int64_t ParcaReporter::FlushOnce() {
   pa_agg_result res;
   int rc = sink_->Flush(&res);

@@ -54,7 +54,16 @@ struct Trace {  // libpf.Trace
   std::map<std::string, std::string> CustomLabels;
 };
 enum TraceOrigin { TraceOriginSampling = 0, TraceOriginOffCPU = 1, TraceOriginMemory = 2, TraceOriginCuda = 3 };
-struct MemorySample { uint64_t Allocs = 0, Frees = 0, AllocBytes = 0, FreeBytes = 0; };  // oomprof.Sample
+struct MemorySample {  // oomprof.Sample
+  uint64_t Allocs = 0, Frees = 0, AllocBytes = 0, FreeBytes = 0;
+  std::vector<uint64_t> Addresses;  // the allocation site's stack, read by SampleEvents (:728-735)
+};
+struct OomprofSampleMeta {  // oomprof.SampleMeta as read at :718-745
+  int64_t Timestamp = 0;
+  std::string Comm, ProcessName, ExecutablePath, BuildID;
+  uint32_t PID = 0;
+  std::map<std::string, std::string> CustomLabels;
+};
 struct TraceEventMeta {  // samples.TraceEventMeta
   int64_t Timestamp = 0;
   std::string Comm;
@@ -111,6 +120,10 @@ class ParcaReporter {
   bool ExecutableKnown(FileID id);                                                 // :643
   void ReportExecutable(const ExecutableMetadata& md);                             // :650
   void ReportHostMetadata(const std::map<std::string, std::string>&) {}            // :695 NOP
+  int ReportHostMetadataBlocking(const std::map<std::string, std::string>&, int, double) { return 0; }  // :700 NOP, nil
+  // oomprof.Reporter (:709-758): every sample becomes a memory-origin trace of oomprof frames (BuildID stashed in
+  // FunctionName, ExecutablePath in SourceFile) and goes through ReportTraceEvent; trace.Hash stays the zero value
+  int SampleEvents(const std::vector<MemorySample>& samples, const OomprofSampleMeta& meta);
   void ReportMetrics(uint32_t, const std::vector<uint32_t>&, const std::vector<int64_t>&) {}  // :761 (metric export is out of scope)
   int Start();                                                                     // :1176 — starts the report ticker
   void Stop();                                                                     // :802

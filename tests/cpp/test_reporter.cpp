@@ -130,6 +130,28 @@ static void testExecutables() {  // :449-476 with r.executables
   REQUIRE(sink.frames.size() == 2 && sink.row_frames[1] == sink.row_frames[2]);
 }
 
+static void testOomprofSampleEvents() {  // SampleEvents, parca_reporter.go:709-758
+  RecordingSink sink; Config cfg; cfg.nodeName = "n"; cfg.reportAllocs = false;
+  ParcaReporter r(&sink, cfg);
+  OomprofSampleMeta meta; meta.Timestamp = 99; meta.Comm = "victim"; meta.PID = 4242; meta.BuildID = "abcdef01"; meta.ExecutablePath = "/srv/bin/victim";
+  meta.CustomLabels = {{"tenant", "blue"}};
+  MemorySample a; a.Allocs = 10; a.Frees = 3; a.AllocBytes = 4096; a.FreeBytes = 96; a.Addresses = {0x1000, 0x2000, 0x1000};
+  MemorySample b; b.Allocs = 2; b.Frees = 2; b.AllocBytes = 64; b.FreeBytes = 0; b.Addresses = {0x3000};
+  REQUIRE(r.SampleEvents({a, b}, meta) == 0);
+  REQUIRE(sink.rows.size() == 3);  // a: inuse_objects + inuse_space; b: inuse_space only (allocs == frees)
+  REQUIRE(sink.rows[0].kind == PA_KIND_MEM_INUSE_OBJECTS && sink.rows[0].value == 7 && sink.rows[1].kind == PA_KIND_MEM_INUSE_SPACE && sink.rows[1].value == 4000);
+  REQUIRE(sink.rows[2].kind == PA_KIND_MEM_INUSE_SPACE && sink.rows[2].value == 64);
+  for (auto& h : sink.rows) REQUIRE(h.hash_hi == 0 && h.hash_lo == 0 && h.pid == 4242 && h.tid == 4242 && h.timestamp_ns == 99);
+  REQUIRE(sink.frames.size() == 3);  // 0x1000 interned once
+  REQUIRE(sink.row_frames[0].size() == 3 && sink.row_frames[0][0] == sink.row_frames[0][2] && sink.row_frames[2].size() == 1);
+  for (auto& f : sink.frames) {
+    REQUIRE(f.kind == PA_FRAME_OOMPROF && sink.strings[f.type_name_sid] == "native");
+    REQUIRE(sink.strings[f.function_name_sid] == "abcdef01" && sink.strings[f.source_file_sid] == "/srv/bin/victim");
+  }
+  REQUIRE(sink.label(sink.rows[0].labelset_id, "tenant") == "blue" && sink.label(sink.rows[0].labelset_id, "node") == "n");
+  REQUIRE(r.memorySamples == 2 && r.ReportHostMetadataBlocking({}, 0, 0.0) == 0);
+}
+
 static void testFlushAndOfflineLog() {
   RecordingSink sink; Config cfg; cfg.nodeName = "n";
   uint64_t seen_rows = 0;
@@ -213,6 +235,7 @@ int main(int argc, char** argv) {
   testOrigins();
   testExecutables();
   testFlushAndOfflineLog();
+  testOomprofSampleEvents();
   if (failures) { fprintf(stderr, "%d failure(s)\n", failures); return 1; }
   printf("ok\n");
   return 0;
