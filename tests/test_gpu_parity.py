@@ -640,3 +640,73 @@ def test_mode_b_device_staging_rules(gpu):
         b.shard_export(0, 1, 1)                                           # v1 aggregators do not gather unique stacks
     assert e.value.code == -22
     b.collect(); b.close()
+
+
+def test_concurrent_producers_and_flush_on_one_aggregator(gpu):
+    """reporter.Reporter's threading contract: ReportTraceEvent is called from many goroutines while the report
+    ticker flushes; the writer is swapped under the ingest lock (parca_reporter.go:1745-1748). Four producer threads submit
+    while a fifth flushes: every row must come out exactly once, batches must decode, and each producer's rows must keep
+    their order inside every batch (row order == lock acquisition order)."""
+    import threading
+    import time
+    w = synth.edge_workload(seed=77, n=24_000, hash_mode=abi.PA_HASH_XXH64X2)
+    w.hdrs["timestamp_ns"] = np.arange(w.n)                       # unique row tag
+    a = gpu.from_workload(w, max_samples=3_000, max_frames=40_000)    # small ring: producers hit PA_ENOSPC and retry
+    nprod, stop, batches, errors = 4, threading.Event(), [], []
+    fo = w.hdrs["frame_off"].astype(np.int64)
+    nf = w.hdrs["nframes"].astype(np.int64)
+    frames = w.frame_ids
+
+    def producer(p):
+        try:
+            rows = np.arange(p, w.n, nprod)
+            for s in range(0, len(rows), 50):
+                part = rows[s:s + 50]
+                hd = w.hdrs[part].copy()
+                fr = np.concatenate([frames[fo[r]:fo[r] + nf[r]] for r in part]) if len(part) else np.zeros(0, np.uint64)
+                while True:
+                    try:
+                        a.submit(hd, fr)
+                        break
+                    except gpu.PaError as e:
+                        if e.code != -28:
+                            raise
+                        time.sleep(0.001)                         # ring full: wait for the flusher
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    def flusher():
+        try:
+            while not stop.is_set():
+                r = a.flush()
+                if r.n_rows:
+                    batches.append(r.ipc_bytes())
+                time.sleep(0.002)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=producer, args=(p,)) for p in range(nprod)]
+    fl = threading.Thread(target=flusher)
+    fl.start()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    stop.set()
+    fl.join()
+    r = a.flush()
+    if r.n_rows:
+        batches.append(r.ipc_bytes())
+    a.close()
+    assert not errors, errors
+    assert len(batches) > 3
+    seen = []
+    for b in batches:
+        t = pa.ipc.open_stream(b).read_all()
+        tags = t.column("timestamp").cast(pa.int64()).to_numpy()  # nanoseconds since epoch == the row tag
+        for p in range(nprod):                                    # per-producer order inside the batch
+            mine = tags[tags % nprod == p]
+            assert np.all(np.diff(mine) > 0)
+        seen.append(tags)
+    allt = np.concatenate(seen)
+    assert len(allt) == w.n and np.array_equal(np.sort(allt), np.arange(w.n))
