@@ -42,28 +42,51 @@ struct Lz4Api {
   }
 };
 
-namespace fbread {  // just enough flatbuffer reading for Message / RecordBatch / DictionaryBatch
+namespace fbread {  // just enough flatbuffer reading for Message / RecordBatch / DictionaryBatch, every access bounds-checked
 inline uint32_t u32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 inline int32_t i32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
 inline int64_t i64(const uint8_t* p) { int64_t v; memcpy(&v, p, 8); return v; }
 inline uint16_t u16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
-inline const uint8_t* field(const uint8_t* table, int slot) {  // nullptr = absent (default)
-  const uint8_t* vt = table - i32(table);
-  uint16_t vts = u16(vt);
-  if (4 + 2 * slot >= (int)vts) return nullptr;
-  uint16_t off = u16(vt + 4 + 2 * slot);
-  return off ? table + off : nullptr;
-}
-inline const uint8_t* indirect(const uint8_t* p) { return p + u32(p); }  // offset field -> target
-inline std::vector<int64_t> longs(const uint8_t* vec_field, int per_elem) {
-  std::vector<int64_t> out;
-  if (!vec_field) return out;
-  const uint8_t* v = indirect(vec_field);
-  uint32_t n = u32(v);
-  out.resize((size_t)n * per_elem);
-  if (n) memcpy(out.data(), v + 4, out.size() * 8);  // vectors of 16-byte structs / int64 are 8-aligned after the count
-  return out;
-}
+struct Buf {  // one metadata flatbuffer; positions are byte offsets (0 = "absent"), `bad` latches on the first out-of-range access
+  const uint8_t* base;
+  uint32_t len;
+  bool bad = false;
+  bool ok(int64_t pos, uint64_t n) {
+    if (pos < 0 || (uint64_t)pos > len || (uint64_t)len - (uint64_t)pos < n) { bad = true; return false; }
+    return true;
+  }
+  int64_t root() { if (!ok(0, 4)) return 0; int64_t t = u32(base); return ok(t, 4) && t ? t : 0; }
+  int64_t field(int64_t table, int slot) {  // 0 = absent (default) or malformed (then bad is set)
+    if (!table || !ok(table, 4)) return 0;
+    int64_t vt = table - (int64_t)i32(base + table);
+    if (!ok(vt, 4)) return 0;
+    uint16_t vts = u16(base + vt);
+    if (vts < 4 || !ok(vt, vts)) { bad = true; return 0; }
+    if (4 + 2 * slot + 2 > (int)vts) return 0;
+    uint16_t off = u16(base + vt + 4 + 2 * slot);
+    if (!off) return 0;
+    int64_t f = table + off;
+    return ok(f, 1) ? f : 0;
+  }
+  int64_t indirect(int64_t p) {  // offset field -> target
+    if (!p || !ok(p, 4)) return 0;
+    int64_t t = p + (int64_t)u32(base + p);
+    return ok(t, 4) ? t : 0;
+  }
+  uint8_t byte(int64_t f) { return f && ok(f, 1) ? base[f] : (uint8_t)0; }
+  int64_t scalar64(int64_t f) { return f && ok(f, 8) ? i64(base + f) : 0; }
+  bool longs(int64_t vec_field, int per_elem, std::vector<int64_t>* out) {  // vectors of int64 / of 16-byte structs
+    out->clear();
+    if (!vec_field) return !bad;
+    int64_t v = indirect(vec_field);
+    if (!v) return false;
+    uint64_t n = u32(base + v), bytes = n * (uint64_t)per_elem * 8;
+    if (!ok(v + 4, bytes)) return false;
+    out->resize((size_t)(n * per_elem));
+    if (bytes) memcpy(out->data(), base + v + 4, (size_t)bytes);
+    return true;
+  }
+};
 }  // namespace fbread
 
 // Re-encodes `in` with LZ4_FRAME body compression into `out`. Returns false and sets *err on malformed input / missing liblz4.
@@ -81,10 +104,12 @@ inline bool ipc_compress_lz4(const uint8_t* in, uint64_t len, std::vector<uint8_
     if (mlen == 0) { eos = true; break; }
     if (pos + mlen > len) { *err = "truncated metadata"; return false; }
     const uint8_t* meta = in + pos;
-    const uint8_t* m = meta + fbread::u32(meta);
-    const uint8_t* ht = fbread::field(m, 1);
-    const uint8_t* bl = fbread::field(m, 3);
-    Msg x{ht ? *ht : (uint8_t)0, meta, mlen, in + pos + mlen, bl ? fbread::i64(bl) : 0};
+    fbread::Buf fb{meta, mlen};
+    int64_t m = fb.root();
+    uint8_t type = fb.byte(fb.field(m, 1));
+    int64_t body_len = fb.scalar64(fb.field(m, 3));
+    if (!m || fb.bad || body_len < 0) { *err = "malformed message metadata"; return false; }
+    Msg x{type, meta, mlen, in + pos + mlen, body_len};
     if (pos + mlen + (uint64_t)x.body_len > len) { *err = "truncated body"; return false; }
     msgs.push_back(x);
     pos += mlen + (uint64_t)x.body_len;
@@ -98,28 +123,24 @@ inline bool ipc_compress_lz4(const uint8_t* in, uint64_t len, std::vector<uint8_
   std::vector<Plan> plans(msgs.size());
   for (size_t i = 0; i < msgs.size(); i++) {
     if (msgs[i].type != 2 && msgs[i].type != 3) continue;
-    const uint8_t* m = msgs[i].meta + fbread::u32(msgs[i].meta);
-    const uint8_t* hdr = fbread::field(m, 2);
-    if (!hdr) { *err = "message without header"; return false; }
-    const uint8_t* rb = fbread::indirect(hdr);
+    fbread::Buf fb{msgs[i].meta, msgs[i].meta_len};
+    int64_t m = fb.root();
+    int64_t rb = fb.indirect(fb.field(m, 2));
+    if (!rb) { *err = "message without header"; return false; }
     Plan& p = plans[i];
     if (msgs[i].type == 2) {  // DictionaryBatch{id, data}
       p.is_dict = true;
-      const uint8_t* id = fbread::field(rb, 0);
-      p.dict_id = id ? fbread::i64(id) : 0;
-      const uint8_t* data = fbread::field(rb, 1);
-      if (!data) { *err = "dictionary batch without data"; return false; }
-      rb = fbread::indirect(data);
+      p.dict_id = fb.scalar64(fb.field(rb, 0));
+      rb = fb.indirect(fb.field(rb, 1));
+      if (!rb) { *err = "dictionary batch without data"; return false; }
     }
-    const uint8_t* l = fbread::field(rb, 0);
-    p.length = l ? fbread::i64(l) : 0;
-    p.nodes = fbread::longs(fbread::field(rb, 1), 2);
-    p.buffers = fbread::longs(fbread::field(rb, 2), 2);
-    p.variadic = fbread::longs(fbread::field(rb, 4), 1);
-    if (fbread::field(rb, 3)) { *err = "stream is already compressed"; return false; }
+    p.length = fb.scalar64(fb.field(rb, 0));
+    bool vec_ok = fb.longs(fb.field(rb, 1), 2, &p.nodes) && fb.longs(fb.field(rb, 2), 2, &p.buffers) && fb.longs(fb.field(rb, 4), 1, &p.variadic);
+    if (!vec_ok || fb.bad) { *err = "malformed record batch metadata"; return false; }
+    if (fb.field(rb, 3)) { *err = "stream is already compressed"; return false; }
     for (size_t b = 0; b + 1 < p.buffers.size(); b += 2) {
       int64_t off = p.buffers[b], n = p.buffers[b + 1];
-      if (off < 0 || n < 0 || off + n > msgs[i].body_len) { *err = "buffer outside its body"; return false; }
+      if (off < 0 || n < 0 || off > msgs[i].body_len || n > msgs[i].body_len - off) { *err = "buffer outside its body"; return false; }
       if (n == 0) { p.task_of_buffer.push_back(-1); continue; }
       p.task_of_buffer.push_back((int)tasks.size());
       tasks.push_back(Task{msgs[i].body + off, n, {}});

@@ -96,3 +96,27 @@ def test_aggregator_lz4_mode_matches_plain_mode():
             st = a.stacktraces(ids).ipc_bytes()
             assert list(pa.ipc.open_stream(st))[0].num_rows == r.n_unique_stacks
         a.close()
+
+
+def test_compress_survives_corrupted_streams(oracle):
+    """pa_ipc_compress_lz4 is an exported entry point: truncations and bit flips of a valid stream must give an error code
+    or a (possibly meaningless) stream, never a crash — its flatbuffer reader checks every offset against the metadata."""
+    import numpy as np
+    plain, _ = oracle.run(synth.edge_workload(seed=2, n=300))
+    rng = np.random.Generator(np.random.PCG64(5))
+    meta_end = ipc_inspect.messages(plain)[1]["body_at"]  # schema + first dictionary batch metadata: where the offsets live
+    outcomes = {"ok": 0, "err": 0}
+    for k in range(300):
+        b = bytearray(plain)
+        if k % 3 == 0:
+            b = b[: int(rng.integers(0, len(b)))]
+        else:
+            for _ in range(int(rng.integers(1, 4))):
+                pos = int(rng.integers(0, meta_end if k % 3 == 1 else len(b)))
+                b[pos] ^= 1 << int(rng.integers(0, 8))
+        try:
+            lib.compress_lz4(bytes(b))
+            outcomes["ok"] += 1
+        except lib.PaError:
+            outcomes["err"] += 1
+    assert outcomes["err"] > 50 and outcomes["ok"] + outcomes["err"] == 300
