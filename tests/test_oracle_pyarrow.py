@@ -186,3 +186,15 @@ def test_stacktrace_record_random_batches(oracle, seed):
     ids = ids[: int(rng.integers(0, len(ids) + 1))] + [bytes(rng.integers(0, 256, 16, dtype=np.uint8)) for _ in range(int(rng.integers(0, 3)))]
     rng.shuffle(ids)
     check_stacktraces(oracle, w, ids=ids)
+
+
+@pytest.mark.parametrize("seed", list(range(30, 42)))
+def test_sample_records_random_batches(oracle, seed):
+    """More seeds, sizes, label-flag combinations and external-label choices for both sample records: the C++ oracle against
+    the literal Python transcription (logical pin; the reference has no golden bytes for this path)."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    mode = abi.PA_HASH_PROVIDED if seed % 2 else abi.PA_HASH_XXH64X2
+    kw = dict(seed=seed, n=int(rng.integers(1, 1200)), hash_mode=mode, label_flags=int(rng.integers(0, 8)), external=bool(rng.random() < 0.5))
+    check(oracle, synth.edge_workload(**kw), validate=False)
+    check_v1(oracle, synth.edge_workload(**kw))
