@@ -34,8 +34,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--samples", type=int, default=10_000_000, help="rows per GPU (config 2 = 10M)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="rows of the batch (a prefix) timed on the CPU port for cpu_baseline")
-    ap.add_argument("--ref-sample", type=int, default=2_000_000, help="rows per step of the --impl reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="rows of the batch timed on the CPU port for cpu_baseline (0 = the whole batch, the default)")
+    ap.add_argument("--ref-sample", type=int, default=0, help="rows per step of the --impl reference arm (0 = the whole batch, the default)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--stream", type=int, default=0, metavar="WINDOWS",
                     help="streaming mode (config 5 style): WINDOWS back-to-back batches through two aggregators on one GPU, "
@@ -102,7 +102,16 @@ def shard_workload(args, rank, world):
     return w
 
 
-def time_cpu_port(w, n_rows):
+def config_of(args, w, world):
+    """The `config` object of the JSON line: identical in both arms (b200 / reference) for the same flags, so the two lines
+    describe the same workload word for word."""
+    F = int(w.stack_table.shape[1])
+    return {"workload": "config%d: %d samples x %d frames per GPU, %d unique stacks, %d distinct frames, pid-sharded across %d GPU(s)"
+                        % (args.config, w.n, F, w.meta["U"], w.meta["P"], world),
+            "hash_mode": args.hash_mode, "schema": args.schema, "rows_per_step_per_gpu": w.n}
+
+
+def time_cpu_port(w, n_rows, keep_bytes=False):
     """ingest + flush of the CPU port on the first n_rows of the workload, one thread."""
     from oracle import oracle_py
     sub = w.head(n_rows)
@@ -115,6 +124,9 @@ def time_cpu_port(w, n_rows):
     dt = time.perf_counter() - t0
     o.close()
     st = dict(st, ingest_s=t1 - t0, flush_s=dt - (t1 - t0))
+    if keep_bytes:
+        import hashlib
+        st["ipc_sha256"] = hashlib.sha256(data).hexdigest()
     return sub.n / dt, dt, len(data), st
 
 
@@ -125,30 +137,35 @@ def two_core_note(n, st):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's algorithm on host cores (CPU port; Go toolchain unavailable)."""
+    """--impl reference: the reference's algorithm on host cores (CPU port of the Go path; no Go toolchain here or on the box).
+    Every step is one pass over the SAME batch the b200 arm aggregates per GPU (rank 0's shard at N>1: the CPU rate in samples/s
+    does not depend on how many such shards exist), single thread because the reference serialises ingest on one mutex
+    (parca_reporter.go:335); warm-up steps run a 100k-row prefix (they only warm the allocator and page cache)."""
     if rank != 0:
         return
-    from parca_agent_b200 import synth
-    w = synth.config2(n=args.samples).head(min(args.samples, args.ref_sample))  # a prefix of the very same batch
+    import hashlib
+    w = shard_workload(args, 0, world)
+    n = w.n if args.ref_sample <= 0 else min(w.n, args.ref_sample)
     for _ in range(args.warmup):
         time_cpu_port(w, min(w.n, 100_000))
-    times = []
-    for _ in range(args.steps):
-        rate, dt, nbytes, st = time_cpu_port(w, w.n)
+    times, st, digest = [], None, None
+    for i in range(args.steps):
+        rate, dt, nbytes, st = time_cpu_port(w, n, keep_bytes=(i == 0))
+        digest = st.get("ipc_sha256", digest)
         times.append(dt)
     total = float(np.sum(times))
-    value = w.n * args.steps / total
-    sample = ("first %d rows of the config-2 batch per step (all 100k stacks occur in it; 5%% of its rows are first occurrences vs 1%% in the "
-              "full 10M batch, so this slightly under-states the CPU path); ingest+flush to IPC bytes" % w.n)
+    value = n * args.steps / total
+    sample = ("%d rows per step = %s config-%d batch of one GPU, ingest+flush to IPC bytes, %d steps in %.0f s; C++ restatement of the reference "
+              "Go path (Go toolchain unavailable), single thread as the reference serialises ingest (parca_reporter.go:335); host has %d cores"
+              % (n, "the whole" if n == w.n else "a prefix of the", args.config, args.steps, total, os.cpu_count()))
     print(json.dumps({
         "impl": "reference", "metric": "samples/sec aggregated", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "config2: 10M samples x 64 frames, 100k unique stacks (bounded prefix per step)", "hash_mode": "xxh64x2"},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": 1, "kind": "port",
-                         "sample": sample + "; single thread because the reference serialises ingest on one mutex (parca_reporter.go:335)",
-                         **two_core_note(w.n, st)},
+        "config": config_of(args, w, world),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": 1, "kind": "port", "sample": sample, **two_core_note(n, st)},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "result": {"rows": n, "ipc_sha256": digest},
     }))
 
 
@@ -336,6 +353,8 @@ def main():
         d2h_b = r.ipc_len
         if i > 0:  # first flush warms the pinned output buffer allocation
             e2e_times.append(dt)
+    import hashlib
+    gpu_digest = hashlib.sha256(r.ipc).hexdigest() if rank == 0 else None  # the stream the LAST TIMED end-to-end flush produced
     e2e_t = torch.tensor([float(np.sum(e2e_times))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -370,22 +389,23 @@ def main():
             traffic = None if provided or args.config != 2 else json.load(open(os.path.join(ROOT, "profiles", "roofline_latest.json"))).get("hash_dram_bytes_per_launch")
         except Exception:
             pass
-        cpu = None
+        cpu, cpu_digest = None, None
         if not args.no_cpu:
-            rate, dt, nbytes, st = time_cpu_port(w, min(args.cpu_sample, w.n))
+            ncpu = w.n if args.cpu_sample <= 0 else min(args.cpu_sample, w.n)
+            rate, dt, nbytes, st = time_cpu_port(w, ncpu, keep_bytes=True)
+            cpu_digest = st.get("ipc_sha256") if ncpu == w.n else None
             cpu = {"value": rate, "unit": "samples/s", "cores": 1, "kind": "port",
-                   "sample": "first %d rows of the same batch (every one of its 100k stacks occurs in the prefix), ingest+flush to IPC bytes in %.1f s; "
+                   "sample": "%s batch (%d rows), ingest+flush to IPC bytes in %.1f s, one pass; "
                              "C++ restatement of the reference Go path (Go toolchain unavailable), single thread as the reference serialises "
-                             "ingest (parca_reporter.go:335); host has %d cores" % (min(args.cpu_sample, w.n), dt, os.cpu_count()),
-                   **two_core_note(min(args.cpu_sample, w.n), st)}
+                             "ingest (parca_reporter.go:335); host has %d cores" % ("the whole" if ncpu == w.n else "a prefix of the", ncpu, dt, os.cpu_count()),
+                   **two_core_note(ncpu, st)}
         out = {
             "metric": "samples/sec aggregated", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": "config%d: %d samples x %d frames per GPU, %d unique stacks, %d distinct frames, pid-sharded across %d GPU(s)"
-                                   % (args.config, w.n, F, w.meta["U"], w.meta["P"], world),
-                       "hash_mode": args.hash_mode, "schema": args.schema, "l2": "inputs (%.2f GB/GPU) far exceed the 126 MB L2; no explicit flush" % ((w.n * 64 + w.n_frame_ids * 8) / 1e9),
-                       "timing": "CUDA events on the library's compute stream, max over ranks", "wall_s_for_steps": wall_max},
+            "config": config_of(args, w, world),
+            "notes": {"l2": "inputs (%.2f GB/GPU) far exceed the 126 MB L2; no explicit flush" % ((w.n * 64 + w.n_frame_ids * 8) / 1e9),
+                      "timing": "CUDA events on the library's compute stream, max over ranks", "wall_s_for_steps": wall_max},
             "gpu_launches": int(launches),
             "kernel_groups_ms": {g: float(np.mean([x[0] for x in v])) for g, v in groups.items()},
             "kernel_groups_launches": {g: int(v[0][1]) for g, v in groups.items()},
@@ -397,7 +417,8 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clk,
             "result": {"rows": res.n_rows, "unique_stacks": res.n_unique_stacks, "locations": res.n_locations, "functions": res.n_functions,
-                       "ipc_bytes": res.ipc_len},
+                       "ipc_bytes": res.ipc_len, "ipc_sha256": gpu_digest, "cpu_ipc_sha256": cpu_digest,
+                       "bit_exact_vs_cpu_port": (gpu_digest == cpu_digest) if cpu_digest else None},
         }
         if v1_st:
             out["v1_stacktrace_record"] = v1_st

@@ -97,6 +97,21 @@ def test_config3_scaled_zipf(oracle, gpu):
     assert_same(oracle, gpu, synth.config3(n=300_000, u=30_000, p=16_384, npids=500, lsets=10))
 
 
+def test_config2_full(oracle, gpu):
+    """BASELINE.json config 2 at its full size (10M samples x 64 frames, 100k stacks): the IPC stream of one flush through
+    the C ABI equals the oracle's byte for byte (the same comparison bench.py repeats on its timed end-to-end flush)."""
+    w = synth.config2()
+    r = assert_same(oracle, gpu, w, chunk_samples=1 << 20)
+    assert r.n_rows == 10_000_000 and r.n_unique_stacks == 100_000
+
+
+def test_config3_full(oracle, gpu):
+    """BASELINE.json config 3 at its full size (10M samples, Zipf-skewed 32-frame stacks, 50k labelsets, CUDA origin)."""
+    w = synth.config3()
+    r = assert_same(oracle, gpu, w, chunk_samples=1 << 20)
+    assert r.n_rows == 10_000_000 and r.n_unique_stacks == len(np.unique(w.stack_choice))
+
+
 def test_stack_ids_match_xxh64(oracle, gpu):
     w = synth.edge_workload(seed=5, hash_mode=abi.PA_HASH_XXH64X2)
     a = gpu.from_workload(w)
