@@ -38,13 +38,16 @@ def parse():
     ap.add_argument("--ref-sample", type=int, default=0, help="rows per step of the --impl reference arm (0 = the whole batch, the default)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--stream", type=int, default=0, metavar="WINDOWS",
-                    help="streaming mode (config 5 style): WINDOWS back-to-back batches through two aggregators on one GPU, "
-                         "reports sustained end-to-end samples/s")
+                    help="streaming mode (BASELINE config 5): WINDOWS back-to-back windows per GPU through two alternating aggregators, "
+                         "reports sustained end-to-end samples/s and the copy/compute overlap (run under torchrun for 2 GPUs)")
+    ap.add_argument("--stream-rows", type=int, default=47_500_000, help="rows per window per GPU in --stream mode (config 5 on 2 GPUs = 47.5M)")
     ap.add_argument("--hash-mode", default="xxh64x2", choices=["xxh64x2", "provided"],
                     help="xxh64x2 = GPU hashes every stack (headline); provided = trace.Hash arrives with the sample, as in the reference")
     ap.add_argument("--schema", default="v2", choices=["v2", "v1"], help="sample record schema (v1 = the reference's default, stacktrace ids only)")
-    ap.add_argument("--merge", action="store_true", help="N>1 only: additionally time mode B (one merged batch on rank 0: shards hash/dedup, "
-                    "NVLink send of 64 B/row + unique-stack frames, merged provided-id pass); reported under \"mode_b\", the headline stays mode A")
+    ap.add_argument("--no-merge", action="store_true", help="N>1: skip mode B (ONE merged record over all GPUs with an O(unique keys) NCCL dictionary "
+                    "exchange, BASELINE config 4 at N=8); by default it is timed after the headline (mode A) and reported under \"mode_b\"")
+    ap.add_argument("--merge-rows", type=int, default=12_500_000, help="mode B rows per GPU (config 4 = 100M / 8)")
+    ap.add_argument("--merge-timeout", type=int, default=600, help="seconds after which a stalled mode B leg is abandoned (the headline line is printed without it)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="BASELINE.json config: 2 = headline (default), 3 = Zipf/CUDA-origin/50k labelsets")
     return ap.parse_args()
 
@@ -169,13 +172,41 @@ def run_reference(args, rank, world):
     }))
 
 
-def run_stream(args, local):
-    """Back-to-back windows: two aggregator instances alternate, so window k's D2H/IPC assembly overlaps
-    window k+1's H2D and kernels (full-duplex PCIe + copy/compute overlap). Every window re-flushes a ring that
-    was filled once (acquire/commit without rewriting), i.e. the producer's writes are not part of the timing."""
+def pin_to_gpu_numa(local):
+    """Run this rank (and its first-touch allocations: the pinned rings) on the NUMA node its GPU hangs off."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001 — pinning is an optimisation
+        return {"error": repr(e)[:120]}
+
+
+def run_stream(args, rank, world, local):
+    """BASELINE config 5: back-to-back 5 s windows (19 Hz x 1M threads = 95M samples per window, 47.5M rows per GPU on 2 GPUs).
+    Per GPU two aggregator instances alternate, so window k's D2H / IPC assembly overlaps window k+1's H2D and kernels
+    (full-duplex PCIe + copy/compute overlap); every rank emits its own record per window (mode A). Every window re-flushes
+    a ring that was filled once (acquire/commit without rewriting), i.e. the producer's writes are not part of the timing."""
     import torch
-    from parca_agent_b200 import lib
-    w = shard_workload(args, 0, 1)
+    import torch.distributed as dist
+    from parca_agent_b200 import abi, lib, synth
+    numa = pin_to_gpu_numa(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mode = abi.PA_HASH_PROVIDED if args.hash_mode == "provided" else abi.PA_HASH_XXH64X2
+    w = synth.config5_part(rank, world, rows_per_gpu=args.stream_rows, hash_mode=mode)
     aggs = []
     for _ in range(2):
         a = lib.from_workload(w, device=local, max_samples=w.n, max_frames=w.n_frame_ids, chunk_samples=1 << 20)
@@ -190,10 +221,13 @@ def run_stream(args, local):
         for _ in range(windows):
             a.acquire(w.n, w.n_frame_ids)  # the ring already holds this batch
             a.commit(w.n)
+            t1 = time.perf_counter()
             r = a.flush()
-            results[i].append((r.n_rows, r.ipc_len, r.h2d_ms, r.gpu_ms, r.d2h_ms))
+            results[i].append((r.n_rows, r.ipc_len, r.h2d_ms, r.gpu_ms, r.d2h_ms, r.host_ms, 1e3 * (time.perf_counter() - t1)))
 
-    per = max(1, args.stream // 2)
+    per = max(1, (args.stream + 1) // 2)
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ts = [threading.Thread(target=worker, args=(i, per)) for i in range(2)]
@@ -203,80 +237,123 @@ def run_stream(args, local):
         t.join()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    rows = sum(x[0] for r in results for x in r)
-    single = float(np.mean([x[2] + x[4] for r in results for x in r]))
-    print(json.dumps({
-        "metric": "samples/sec aggregated (streaming, sustained end to end)", "value": rows / wall, "unit": "samples/s", "n_gpus": 1,
-        "windows": 2 * per, "rows_per_window": w.n, "wall_s": wall, "ms_per_window": 1e3 * wall / (2 * per), "hash_mode": args.hash_mode,
-        "config": {"workload": "config%d batch re-flushed back to back through two aggregators on one GPU" % args.config},
-        "h2d_plus_d2h_ms_per_window": single, "ipc_bytes_per_window": results[0][0][1],
-    }))
+    flat = [x for r in results for x in r]
+    rows = sum(x[0] for x in flat)
+    h2d, gpu, d2h, host = (float(np.sum([x[k] for x in flat])) / 1e3 for k in (2, 3, 4, 5))
+    # per flush, gpu_ms spans the whole device pass, which runs concurrently with the upload; what is left after the last
+    # chunk landed (tail kernels) + D2H + host framing is the part that has to hide under the OTHER instance's upload
+    hideable = d2h + host + max(0.0, gpu - h2d)
+    exposed = max(0.0, wall - h2d)
+    t = torch.tensor([wall, float(rows), h2d, hideable, exposed], dtype=torch.float64, device="cuda")
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        wall_max = float(tmax[0])
+        print(json.dumps({
+            "metric": "samples/sec aggregated (streaming, sustained end to end)", "value": float(t[1]) / wall_max, "unit": "samples/s", "n_gpus": world,
+            "windows_per_gpu": 2 * per, "rows_per_window_per_gpu": w.n, "rows_per_window": w.n * world, "wall_s": wall_max,
+            "ms_per_window": 1e3 * wall_max / (2 * per), "hash_mode": args.hash_mode,
+            "config": {"workload": "config5: 19 Hz x 1M threads, 5 s windows = %d samples per window over %d GPU(s), 64 frames, %d unique stacks, "
+                                   "two aggregators per GPU alternating" % (w.n * world, world, w.meta["U"])},
+            "required_realtime_rate": 19_000_000, "realtime_headroom": float(t[1]) / wall_max / 19e6,
+            "overlap": {"h2d_busy_s_max_rank": float(tmax[2]), "d2h_host_tail_s_max_rank": float(tmax[3]), "exposed_s_max_rank": float(tmax[4]),
+                        "overlap_fraction": 1.0 - float(tmax[4]) / max(float(tmax[3]), 1e-9),
+                        "definition": "H2D of the frame stream is the critical path (PCIe); D2H of the record, host framing and the kernels that run "
+                                      "after the last chunk landed are what must hide behind the other instance's upload; exposed = wall - H2D busy "
+                                      "time; overlap_fraction = 1 - exposed / (D2H + host + tail-kernel time)"},
+            "ipc_bytes_per_window_per_gpu": flat[0][1], "numa": numa,
+            "per_flush_ms_rank0": {"h2d": flat[0][2], "gpu": flat[0][3], "d2h": flat[0][4], "host": flat[0][5], "wall": flat[0][6]},
+        }))
     for a in aggs:
         a.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_mode_b(args, rank, world, local, barrier):
-    """One merged batch (SURVEY 8e mode B) with inputs resident on every shard. Every rank builds the same global stream
-    (config 2 with samples x world rows), keeps the rows whose xxh64(pid) % world is its rank, and per step runs its own
-    pass, exports 64 B per row + its unique stacks' frames, sends them to rank 0 over NCCL; rank 0 scatters the rows to their
-    global positions and runs the provided-id pass over the union. Wall clock with a barrier and a device synchronize on both
-    sides, max over ranks (several streams and NCCL are involved, so not a single event pair)."""
+    """ONE merged record batch over all GPUs (SURVEY 8e mode B) through the library's pa_merge_* group over NCCL: BASELINE
+    config 4 at 8 GPUs (100M samples x 64 frames, 1M unique stacks, pid-sharded), proportionally smaller below. Rows stay on
+    the GPU that ingested them; only dictionary keys cross NVLink (bytes reported). `value` = rows of the merged batch per
+    second of the device-resident merged pass (CUDA events on every rank's stream around the whole pass including the
+    exchanges, max over ranks); `e2e` = ring -> HBM -> merged pass -> stream in host shared memory, every GPU over its own
+    PCIe link, wall clock between barriers."""
+    import ctypes
+    from multiprocessing import shared_memory
+
     import torch
     import torch.distributed as dist
-    from parca_agent_b200 import abi, lib, sharded, synth
+    from parca_agent_b200 import abi, lib, synth
     mode = abi.PA_HASH_PROVIDED if args.hash_mode == "provided" else abi.PA_HASH_XXH64X2
-    full = synth.config2(n=args.samples * world, hash_mode=mode)
-    gidx = sharded.shard_rows(full, world)[rank]
-    w = full.rows(gidx)
-    w.schema = abi.PA_SCHEMA_V2
+    w = synth.config4_part(rank, world, rows_per_gpu=args.merge_rows, hash_mode=mode)
     a = lib.from_workload(w, device=local, max_samples=w.n, max_frames=w.n_frame_ids, chunk_samples=1 << 20)
+    ids = [lib.MergeGroup.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    g = lib.MergeGroup.nccl(a, ids[0], rank, world)
     lib.load(a, w)
     a.stage()
-    a.process()
-    n, nf = a.shard_sizes()
-    tot = torch.tensor([n, nf], dtype=torch.int64, device="cuda")
-    dist.all_reduce(tot)
-    merged = None
+    for _ in range(args.warmup):
+        g.process()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, groups, stats = [], {}, None
+    for _ in range(args.steps):
+        g.process()
+        dev_ms.append(a.kernel_ms("total")[0])
+        for name in ("header", "hash", "rank", "locations", "labels", "dicts"):
+            groups.setdefault(name, []).append(a.kernel_ms(name)[0])
+        stats = g.stats()
+    barrier()
+    wall = time.perf_counter() - t0
+    n = g.plan()
+    shm, names = None, [None]
     if rank == 0:
-        merged = lib.Aggregator(device=local, hash_mode=abi.PA_HASH_PROVIDED, label_flags=full.label_flags, samples_per_second=full.samples_per_second,
-                                external_labels=full.external_labels, max_samples=int(tot[0]), max_frames=int(tot[1]) + 1024,
-                                schema=abi.PA_SCHEMA_V1 if args.schema == "v1" else abi.PA_SCHEMA_V2)
-        merged.register_strings(full.strings[1:])
-        merged.register_frames(full.frames)
-        merged.register_labelsets(full.labelsets)
-    gidx = torch.as_tensor(gidx, device="cuda")  # the global row index travels with the rows (8 B per row)
-    allsz = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
-    dist.all_gather(allsz, torch.tensor([n, nf], dtype=torch.int64, device="cuda"))
-    sizes = [(int(t[0]), int(t[1])) for t in allsz]  # the same batch is re-merged every step: sizes are known
-    phases = {} if os.environ.get("PA_MERGE_PROFILE") else None
-    times, res = [], None
-    for it in range(args.warmup + args.steps):
-        if it:  # re-stage the shard's batch (untimed): merge_distributed discards it
-            lib.load(a, w)
-            a.stage()
+        shm = shared_memory.SharedMemory(create=True, size=n + 4096)
+        names[0] = shm.name
+    dist.broadcast_object_list(names, src=0)
+    if rank != 0:
+        shm = shared_memory.SharedMemory(name=names[0])
+    view = ctypes.c_char.from_buffer(shm.buf)
+    base = ctypes.addressof(view)
+    res = g.collect(base, n)  # first collect page-locks the shared buffer
+    e2e_times, stage_ms = [], None
+    for _ in range(max(1, args.e2e_steps - 1)):
+        lib.load(a, w)
         barrier()
-        t0 = time.perf_counter()
-        a.process()
-        sharded.merge_distributed(a, gidx, merged, dst=0, device=local, collect=False, sizes=sizes, phases=phases if it >= args.warmup else None)
+        t1 = time.perf_counter()
+        a.stage()
+        g.process()
+        g.plan()
+        res = g.collect(base, n)
         barrier()
-        dt = time.perf_counter() - t0
-        if rank == 0:
-            ms, _ = merged.kernel_ms("total")
-            res = merged.collect()
-        if it >= args.warmup:
-            times.append(dt)
-    t = torch.tensor([float(np.sum(times))], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_times.append(time.perf_counter() - t1)
+        stage_ms = {"h2d_ms": res.h2d_ms, "gpu_ms": res.gpu_ms, "d2h_ms": res.d2h_ms, "host_ms": res.host_ms}
+    t = torch.tensor([float(np.sum(dev_ms)) / 1e3, wall, float(np.sum(e2e_times)), float(stats["nvlink_bytes"])], dtype=torch.float64, device="cuda")
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
     out = None
     if rank == 0:
-        out = {"value": int(tot[0]) * len(times) / float(t[0]), "unit": "samples/s", "ms_per_step": 1e3 * float(t[0]) / len(times),
-               "merged_pass_ms_on_rank0": ms, "rows": res.n_rows, "unique_stacks": res.n_unique_stacks, "ipc_bytes": res.ipc_len,
-               "nvlink_bytes_per_step": int((int(tot[0]) - n) * 72 + (int(tot[1]) - nf) * 8),
-               "note": "inputs resident on the shards; one merged record on rank 0; all shards register the same tables"}
-        if phases:
-            out["phases_ms_per_step"] = {k: v / len(times) for k, v in phases.items()}
-        merged.close()
+        import hashlib
+        total = w.n * world
+        out = {"workload": "config4-style merged batch: %d samples x 64 frames over %d GPU(s) (%d per GPU), %d unique stacks, %d distinct frames, %d pids"
+                           % (total, world, w.n, w.meta["U"], w.meta["P"], len(w.labelsets)),
+               "value": total * len(dev_ms) / float(tmax[0]), "unit": "samples/s", "ms_per_step": 1e3 * float(tmax[0]) / len(dev_ms),
+               "wall_ms_per_step": 1e3 * float(tmax[1]) / len(dev_ms),
+               "e2e": {"value": total * len(e2e_times) / float(tmax[2]), "unit": "samples/s", "h2d_bytes_per_step": int((w.n * 64 + w.n_frame_ids * 8) * world),
+                       "d2h_bytes_per_step": int(n), "steps": len(e2e_times), "stages_ms_last_step_rank0": stage_ms},
+               "nvlink_payload_bytes_per_step_all_ranks": int(float(t[3])), "nvlink_payload_bytes_per_row": float(t[3]) / total,
+               "exchange_wait_ms_rank0": stats["exchange_wait_ms"], "kernel_groups_ms_rank0": {k: float(np.mean(v)) for k, v in groups.items()},
+               "rows": res.n_rows, "unique_stacks": res.n_unique_stacks, "locations": res.n_locations, "ipc_bytes": int(n),
+               "ipc_sha256": hashlib.sha256(shm.buf[:n]).hexdigest(),
+               "note": "one record for the stream [GPU0 rows, GPU1 rows, ...]; bit-exactness vs the oracle is held by tests/test_merge.py and tests/dist_merge_slices_check.py"}
+    del view
+    g.close()
     a.close()
+    shm.close()
+    if rank == 0:
+        shm.unlink()
     return out
 
 
@@ -293,7 +370,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local)
     if args.stream:
-        return run_stream(args, local)
+        return run_stream(args, rank, world, local)
+    numa = pin_to_gpu_numa(local)  # the rings are first-touched by this rank: keep them next to its GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -404,7 +482,7 @@ def main():
             "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
             "config": config_of(args, w, world),
-            "notes": {"l2": "inputs (%.2f GB/GPU) far exceed the 126 MB L2; no explicit flush" % ((w.n * 64 + w.n_frame_ids * 8) / 1e9),
+            "notes": {"numa": numa, "l2": "inputs (%.2f GB/GPU) far exceed the 126 MB L2; no explicit flush" % ((w.n * 64 + w.n_frame_ids * 8) / 1e9),
                       "timing": "CUDA events on the library's compute stream, max over ranks", "wall_s_for_steps": wall_max},
             "gpu_launches": int(launches),
             "kernel_groups_ms": {g: float(np.mean([x[0] for x in v])) for g, v in groups.items()},
@@ -423,8 +501,22 @@ def main():
         if v1_st:
             out["v1_stacktrace_record"] = v1_st
     a.close()
-    if args.merge and world > 1:
-        mode_b = run_mode_b(args, rank, world, local, barrier)
+    if world > 1 and not args.no_merge and args.config == 2 and args.schema == "v2":
+        # the extra leg must never cost the headline line: a watchdog prints what is there and ends the process if the merged
+        # run stalls (a rank that died inside a collective leaves the others waiting)
+        def bail():
+            if rank == 0:
+                out["mode_b"] = {"error": "mode B did not finish within %d s" % args.merge_timeout}
+                print(json.dumps(out), flush=True)
+            os._exit(0)
+        dog = threading.Timer(args.merge_timeout, bail)
+        dog.daemon = True
+        dog.start()
+        try:
+            mode_b = run_mode_b(args, rank, world, local, barrier)
+        except Exception as e:  # noqa: BLE001
+            mode_b = {"error": repr(e)[:500]}
+        dog.cancel()
         if rank == 0:
             out["mode_b"] = mode_b
     if rank == 0:

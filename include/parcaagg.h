@@ -222,7 +222,8 @@ int pa_agg_debug_stack_counts(pa_agg* a, uint32_t* out, uint64_t n);
  * `cap` entries are written; *n_pairs receives the number of distinct pairs (call again with a larger cap if it is bigger). */
 int pa_agg_debug_pair_counts(pa_agg* a, uint32_t* labelset_ids, uint32_t* stack_ordinals, uint32_t* counts, uint64_t cap, uint64_t* n_pairs);
 
-/* ---- multi-GPU, one merged batch ("mode B") ------------------------------------------------
+/* ---- multi-GPU, one merged batch for an ARBITRARY interleaving of the shards' rows (round-1 path; moves 72 B per row to
+ * the merging GPU — prefer pa_merge_* below, which exchanges dictionary keys only) -------------------------------------
  * The sample stream is sharded by pid hash, one aggregator per GPU. Per-shard batches (mode A) need nothing more. For
  * ONE batch that is bit-identical to the unsharded stream's, every shard aggregator (PA_SCHEMA_V2) runs stage + process,
  * exports its rows and the frames of its unique stacks into device buffers the caller owns, the caller moves them to
@@ -252,6 +253,36 @@ typedef struct pa_device_part {
   uint64_t n_frames;
 } pa_device_part;
 int pa_agg_stage_device_parts(pa_agg* a, const pa_device_part* parts, uint32_t n_parts, uint64_t n_rows_total);
+
+/* ---- multi-GPU, one merged batch with an O(unique keys) exchange ("mode B, slices") ------------------
+ * A group of shard aggregators (PA_SCHEMA_V2, identical string / frame / labelset registrations, one per GPU ring) builds
+ * ONE record batch: the reference's record (reporter/parca_reporter.go:1742-1790) for the sample stream
+ * [shard 0's rows, shard 1's rows, ...]. Rows never leave the GPU that ingested them; only dictionary keys cross NVLink
+ * (stack ids to their owner shard and back as one merged list, min-reductions of the first-occurrence tables, thread-id lists,
+ * per-column run edges). Every first-occurrence dictionary index (arrow_v2.go:191, :302; parca_reporter.go:425) and every run
+ * (arrow.go:97-131, merged across shard borders) comes out exactly as the reference would produce it on that stream.
+ *   pa_merge_create_local : every member in this process and on ONE device (device copies instead of NCCL)
+ *   pa_merge_create_nccl  : one member per call; NCCL (libnccl.so.2, loaded on first use) over NVLink / NVSwitch. Rank 0
+ *                           obtains the 128-byte id from pa_merge_nccl_unique_id and hands it to every rank (the host agent's job).
+ * Per interval, on every rank: pa_agg_stage (or ingest + pa_merge_flush) -> pa_merge_process -> pa_merge_plan -> pa_merge_collect.
+ * All three are collective. pa_merge_collect writes this process's members' parts of the stream into `base`, a buffer of at
+ * least *ipc_len bytes that ALL processes of the group share (e.g. a POSIX shared-memory mapping; it is page-locked on first
+ * use); rank 0 adds the dictionaries and the metadata, and gets out->ipc == base. base == NULL: groups whose members all live
+ * in this process use a library-owned pinned buffer. */
+typedef struct pa_merge pa_merge;
+int pa_merge_create_local(pa_agg* const* members, uint32_t n, pa_merge** out);
+int pa_merge_nccl_unique_id(uint8_t* id128);
+int pa_merge_create_nccl(pa_agg* member, const uint8_t* id128, uint32_t rank, uint32_t world, pa_merge** out);
+void pa_merge_destroy(pa_merge* m);
+const char* pa_merge_last_error(const pa_merge* m);
+int pa_merge_process(pa_merge* m);
+int pa_merge_plan(pa_merge* m, uint64_t* ipc_len);
+int pa_merge_collect(pa_merge* m, uint8_t* base, uint64_t cap, pa_agg_result* out);
+/* in-process groups: ring swap + H2D of every member, the merged pass, plan and collect in one call */
+int pa_merge_flush(pa_merge* m, pa_agg_result* out);
+/* wall-clock of the last pa_merge_process, the part of it spent waiting in the three size exchanges, the payload bytes this
+ * process's members sent to other ranks (NCCL groups), and the merged row count */
+int pa_merge_last_stats(const pa_merge* m, double* wall_ms, double* exchange_wait_ms, uint64_t* nvlink_bytes, uint64_t* n_rows_total);
 
 /* LZ4_FRAME body compression of a finished, uncompressed stream written by this library (what PA_IPC_LZ4_FRAME applies to
  * every result). Host only; uses the system liblz4.so.1 through dlopen and fails with PA_EIO when it is missing. *out is

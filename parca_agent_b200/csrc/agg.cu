@@ -7,6 +7,9 @@
 // ranks/gathers dictionaries, run-end encodes the label and constant columns, and finally copies
 // each finished Arrow buffer device->host straight into its place in the IPC stream.
 #include <cuda_runtime.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -95,11 +98,41 @@ enum { T_HEADER, T_HASH, T_RANK, T_LOC, T_LABELS, T_DICTS, T_TOTAL, T_COUNT };
 
 using namespace pa;
 
+// this aggregator as shard `rank` of a merged batch (mode B): its rows are the global rows row_base .. row_base+N-1
+struct MergeDims { uint32_t world = 1, rank = 0; uint64_t row_base = 0, n_total = 0, nf_total = 0; const uint32_t* slice_len_ptr = nullptr; };
+
+// everything the stages of one pass share (valid from pass_plan until the batch is collected)
+struct Pass {
+  // registration state as mirrored to the device for this batch (snapshot taken under reg_mu in upload_tables)
+  uint32_t n_cstr = 0, n_frames = 0, n_funcs = 0, n_sids = 0, n_labelsets = 0;
+  uint64_t N = 0, NT = 0, row_base = 0;
+  uint32_t world = 1, rank = 0, ncols = 0, nlab = 0;
+  bool v1 = false, provided = false, merged = false;
+  uint64_t cap = 0, tcap = 0;
+  uint32_t mask = 0;
+  size_t Pn = 1, S = 1, FN = 1, NI = 1;
+  size_t cls_bytes[3] = {0, 0, 0};
+  uint32_t *rowbits = nullptr, *row_wprefix = nullptr, *uniq_slot = nullptr, *uniq_size = nullptr, *first_ls = nullptr, *claimed = nullptr;
+  uint32_t *loc_bits = nullptr, *loc_wp = nullptr, *sd_bits[4] = {}, *sd_wp[4] = {}, *fn_bits = nullptr, *fn_wp = nullptr, *edge_keys = nullptr;
+  uint32_t* red_block = nullptr;  // [first_ls | first_cpu | first_comm]: the direct first-row tables mode B all-reduces
+  size_t red_count = 0;
+  std::vector<uint32_t*> col_first, col_rank, col_bits, col_wp;
+  int j_loc = 0, j_type = 0, j_file = 0, j_lab0 = 0;
+  std::vector<FoJob> jobs;
+  std::vector<ReeCol> rc;
+  ReeArgs ra{};
+  ReeGroups rg{};
+};
+
 struct pa_agg {
   pa_agg_config cfg{};
   std::string err;
   int device = 0, sms = 148, G = 592;
-  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool serial = false;       // PA_SERIAL=1: the label chain stays on the compute stream (per-group timings do not overlap)
+  Pass P;
+  bool merged_part = false;  // the processed batch is one shard of a merged record (collected through pa_merge_collect)
 
   // ---- registration state
   std::mutex reg_mu;
@@ -143,11 +176,13 @@ struct pa_agg {
   cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_d2h0 = nullptr, ev_d2h1 = nullptr;
   bool processed = false, hash_timed = false;
   const unsigned long long* src_frames = nullptr;  // where the staged batch's frame ids can be read by kernels (set by stage / stage_device)
-  int hash_variant = 2;  // 2 = wide (default: 2 lanes/sample, 16-byte loads), 0 = direct (4 lanes/sample), 1 = cp.async-staged; PA_HASH_VARIANT=wide|direct|staged
+  int hash_variant = 2;  // 2 = wide (default: 2 lanes/sample, 16-byte loads), 0 = direct (4 lanes/sample), 1 = cp.async-staged,
+                         // 3 / 4 = cp.async.bulk + mbarrier staged, thread-per-sample (4 warps x 3 stages / 6 warps x 2 stages per SM);
+                         // PA_HASH_VARIANT=wide|direct|staged|bulk|bulk6x2
 
   // ---- device batch buffers
   DBuf d_hdr, d_frames, d_ts, d_value, d_uuid, d_stoff, d_stsize, d_slot, d_kind, d_nfr, d_foff, d_ls, d_cpu, d_tid, d_comm;
-  DBuf d_ustream, d_uniq_row, d_uniq_count, d_table, d_ctr, d_arena, d_partial, d_ree_partial;
+  DBuf d_ustream, d_uniq_row, d_uniq_count, d_table, d_ctr, d_arena, d_partial, d_partial2, d_ree_partial;
   uint64_t table_cap = 0, retry_cap = 0, tid_cap = 0, retry_tcap = 0, prev_tids = 0;
   uint64_t prev_unique = 0;
   Counters h_ctr{};
@@ -183,6 +218,16 @@ struct pa_agg {
   }
 };
 
+// PA_BACKTRACE=1: print the native call stack of a fatal signal (addresses are offsets into libparcaagg.so: addr2line -e)
+static void fatal_backtrace(int sig) {
+  void* frames[64];
+  int n = backtrace(frames, 64);
+  const char msg[] = "libparcaagg: fatal signal, native backtrace:\n";
+  if (write(2, msg, sizeof msg - 1) < 0) {}
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
 static uint64_t pow2_at_least(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
 
 #define CK(expr)                                                        \
@@ -266,7 +311,7 @@ static int build_columns(pa_agg* a) {
   if (on_tid) add("thread_id", COL_TID, 0);
   if (on_comm) add("thread_name", COL_COMM, 0 /* = canonical string count, set per flush */);
   a->n_label_cols = (uint32_t)a->cols.size();
-  if (a->n_label_cols + 10 > (uint32_t)kMaxCols) return a->fail(PA_ERANGE, "too many distinct label names for one batch (limit 38)");
+  if (a->n_label_cols + 10 > (uint32_t)kMaxCols) return a->fail(PA_ERANGE, "too many distinct label names (limit 246)");
   static const char* fixed[8] = {"producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality", "period", "duration"};
   for (uint32_t t = 0; t < 8; t++) { ColPlan c; c.name = fixed[t]; c.type = COL_KIND; c.param = t; a->cols.push_back(std::move(c)); }
   if (a->cfg.schema == PA_SCHEMA_V1) {  // v1: stacktrace_id and timestamp are run-end encoded too (arrow.go:395-400, :471-474)
@@ -289,6 +334,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   if (cfg->max_samples > 0x7FFFFFFFull) return PA_ERANGE;  // run ends / ListView offsets are int32
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return PA_ENODEV;
+  if (getenv("PA_BACKTRACE")) { signal(SIGSEGV, fatal_backtrace); signal(SIGABRT, fatal_backtrace); signal(SIGBUS, fatal_backtrace); }
   pa_agg* a = new pa_agg();
   a->cfg = *cfg;
   a->cfg.external_labels = nullptr;
@@ -304,10 +350,21 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   for (uint32_t i = 0; i < cfg->n_external_labels; i++) {  // resolved to canonical ids lazily at flush (strings may come later)
     a->external.emplace_back(cfg->external_labels[i].name_sid, cfg->external_labels[i].value_sid);
   }
-  if (const char* hv = getenv("PA_HASH_VARIANT")) a->hash_variant = strcmp(hv, "staged") == 0 ? 1 : (strcmp(hv, "direct") == 0 ? 0 : 2);
+  if (const char* hv = getenv("PA_HASH_VARIANT"))
+    a->hash_variant = strcmp(hv, "staged") == 0 ? 1 : (strcmp(hv, "direct") == 0 ? 0 : (strcmp(hv, "bulk") == 0 ? 3 : (strcmp(hv, "bulk6x2") == 0 ? 4 : 2)));
   if (cudaFuncSetAttribute(k_hash_insert_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashStagedSmem) != cudaSuccess) return bail(PA_EIO);
+  if (cudaFuncSetAttribute(k_hash_insert_bulk<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BulkSmem<4, 3>)) != cudaSuccess) return bail(PA_EIO);
+  if (cudaFuncSetAttribute(k_hash_insert_bulk<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BulkSmem<6, 2>)) != cudaSuccess) return bail(PA_EIO);
   if (cudaStreamCreateWithFlags(&a->s_copy, cudaStreamNonBlocking) != cudaSuccess) return bail(PA_EIO);
-  if (cudaStreamCreateWithFlags(&a->s_comp, cudaStreamNonBlocking) != cudaSuccess) return bail(PA_EIO);
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
+  // the compute stream carries the chain of short dependent launches (stack rank, dictionaries): its blocks are scheduled
+  // ahead of the label chain's large run-end grids, which fill whatever is left
+  if (cudaStreamCreateWithPriority(&a->s_comp, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(PA_EIO);
+  if (cudaStreamCreateWithPriority(&a->s_aux, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return bail(PA_EIO);
+  cudaEventCreateWithFlags(&a->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&a->ev_join, cudaEventDisableTiming);
+  if (const char* sv = getenv("PA_SERIAL")) a->serial = sv[0] == '1';
   cudaEventCreate(&a->ev_h2d0);
   cudaEventCreate(&a->ev_h2d1);
   cudaEventCreate(&a->ev_d2h0);
@@ -325,7 +382,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   bool ok = true;
   auto need = [&](DBuf& b, uint64_t bytes) { ok = ok && b.ensure(std::max<uint64_t>(bytes, 256)) == cudaSuccess; };
   need(a->d_hdr, N * 64);
-  if (a->cfg.hash_mode == PA_HASH_XXH64X2) need(a->d_frames, NF * 8);  // provided-hash mode never uploads the frame stream
+  if (a->cfg.hash_mode == PA_HASH_XXH64X2) need(a->d_frames, NF * 8 + 64);  // provided-hash mode never uploads the frame stream (+ slack: bulk copies round up to 16 B)
   need(a->d_ts, N * 8); need(a->d_value, N * 8); need(a->d_uuid, N * 16); need(a->d_stoff, N * 4); need(a->d_stsize, N * 4);
   need(a->d_slot, N * 4); need(a->d_kind, N); need(a->d_nfr, N * 2); need(a->d_foff, N * 8);
   need(a->d_ls, N * 4); need(a->d_cpu, N * 4); need(a->d_tid, N * 4); need(a->d_comm, N * 4);
@@ -333,6 +390,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   need(a->d_uniq_row, N * 4); need(a->d_uniq_count, N * 4);
   need(a->d_ctr, sizeof(Counters));
   need(a->d_partial, (uint64_t)a->G * kMaxCols * 16 + 256);
+  need(a->d_partial2, (uint64_t)a->G * kMaxCols * 16 + 256);
   need(a->d_ree_partial, (uint64_t)a->sms * 8 * kWarps * kMaxCols * sizeof(uint32_t) + 256);  // lives across the ranking launches between the two REE passes
   if (a->cfg.schema == PA_SCHEMA_V1) {  // the `stacks` LRU (parca_reporter.go:876): known stacks stay resident in HBM
     a->cid_unknown = a->sp.intern("unknown");
@@ -356,6 +414,7 @@ void pa_agg_destroy(pa_agg* a) {
   if (!a) return;
   cudaSetDevice(a->device);
   if (a->s_comp) cudaStreamSynchronize(a->s_comp);
+  if (a->s_aux) cudaStreamSynchronize(a->s_aux);
   if (a->s_copy) cudaStreamSynchronize(a->s_copy);
   for (int r = 0; r < 2; r++) { if (a->ring[r].hdr) cudaFreeHost(a->ring[r].hdr); if (a->ring[r].frames) cudaFreeHost(a->ring[r].frames); }
   if (a->h_ctr_pinned) cudaFreeHost(a->h_ctr_pinned);
@@ -363,7 +422,7 @@ void pa_agg_destroy(pa_agg* a) {
   if (a->h_desc) cudaFreeHost(a->h_desc);
   DBuf* all[] = {&a->d_hdr, &a->d_frames, &a->d_ts, &a->d_value, &a->d_uuid, &a->d_stoff, &a->d_stsize, &a->d_slot, &a->d_kind, &a->d_nfr,
                  &a->d_foff, &a->d_ls, &a->d_cpu, &a->d_tid, &a->d_comm, &a->d_ustream, &a->d_uniq_row, &a->d_uniq_count, &a->d_table, &a->d_ctr,
-                 &a->d_arena, &a->d_partial, &a->d_ree_partial, &a->d_lsmat, &a->d_kindtab, &a->d_cols, &a->d_jobs,
+                 &a->d_arena, &a->d_partial, &a->d_partial2, &a->d_ree_partial, &a->d_lsmat, &a->d_kindtab, &a->d_cols, &a->d_jobs,
                  &a->m_addr.buf, &a->m_line.buf, &a->m_type.buf, &a->m_map.buf, &a->m_bid.buf, &a->m_func.buf, &a->m_fnfile.buf, &a->m_sid2cid.buf,
                  &a->m1_map.buf, &a->m1_bid.buf, &a->m1_fn.buf, &a->m1_file.buf, &a->m1_line.buf, &a->m1_col.buf, &a->m1_complete.buf,
                  &a->d_store, &a->d_store_arena, &a->d_store_ctl, &a->d_v1_ids, &a->d_st1};
@@ -374,8 +433,11 @@ void pa_agg_destroy(pa_agg* a) {
   if (a->ev_d2h0) cudaEventDestroy(a->ev_d2h0);
   if (a->ev_d2h1) cudaEventDestroy(a->ev_d2h1);
   for (int t = 0; t < T_COUNT; t++) { if (a->tm[t].a) cudaEventDestroy(a->tm[t].a); if (a->tm[t].b) cudaEventDestroy(a->tm[t].b); }
+  if (a->ev_fork) cudaEventDestroy(a->ev_fork);
+  if (a->ev_join) cudaEventDestroy(a->ev_join);
   if (a->s_copy) cudaStreamDestroy(a->s_copy);
   if (a->s_comp) cudaStreamDestroy(a->s_comp);
+  if (a->s_aux) cudaStreamDestroy(a->s_aux);
   delete a;
 }
 
@@ -505,12 +567,12 @@ static int stage_async(pa_agg* a) {
 }
 
 template <class F>
-static void launch_scan(pa_agg* a, F f, int njobs, Timer& t, int gx = 0) {
+static void launch_scan(pa_agg* a, F f, int njobs, Timer& t, int gx, cudaStream_t s, DBuf& scratch) {
   if (gx <= 0) gx = a->G;
   dim3 grid(gx, njobs);
-  typename F::T* partial = a->d_partial.as<typename F::T>();
-  k_scan_reduce<F><<<grid, kThreads, 0, a->s_comp>>>(f, partial);
-  k_scan_emit<F><<<grid, kThreads, 0, a->s_comp>>>(f, partial);
+  typename F::T* partial = scratch.as<typename F::T>();  // per-block totals: two concurrent scans need two scratch buffers
+  k_scan_reduce<F><<<grid, kThreads, 0, s>>>(f, partial);
+  k_scan_emit<F><<<grid, kThreads, 0, s>>>(f, partial);
   t.launches += 2;
 }
 // grid for a pass over at most `bound` elements: >= 2048 elements per CTA, never more than the full grid
@@ -527,9 +589,13 @@ static int upload_tables(pa_agg* a) {
     CK(a->m1_file.sync(a->ft.v1_file_cid, s)); CK(a->m1_line.sync(a->ft.v1_line, s)); CK(a->m1_col.sync(a->ft.v1_col, s));
     CK(a->m1_complete.sync(a->ft.v1_complete, s));
   }
+  // what the device mirrors now hold: the pass uses these counts only (registration may continue concurrently)
+  a->P.n_cstr = a->sp.count(); a->P.n_frames = a->ft.count(); a->P.n_funcs = a->ft.n_funcs();
+  a->P.n_sids = (uint32_t)a->sp.sid2cid.size(); a->P.n_labelsets = (uint32_t)a->ls.sets.size();
   if (a->cols_dirty) {
     int rc = build_columns(a);
     if (rc) return rc;
+    a->P.n_cstr = a->sp.count();  // the column plan may intern label names
     CK(a->d_lsmat.ensure(a->lsmat.size() * 4));
     CK(cudaMemcpyAsync(a->d_lsmat.p, a->lsmat.data(), a->lsmat.size() * 4, cudaMemcpyHostToDevice, s));
     CK(a->d_kindtab.ensure(a->kindtab.size() * 4));
@@ -542,13 +608,12 @@ static int upload_tables(pa_agg* a) {
 // first-occurrence ranking of a batch of FoJobs (blockIdx.y = job). elem_bound: upper bound on elements per job;
 // table_bound: on table entries; both pick right-sized grids
 static void run_fo_jobs(pa_agg* a, const FoJob* djobs, int first, int count, bool need_min, Timer& t, uint64_t elem_bound, uint64_t table_bound,
-                        bool do_map = true) {
-  cudaStream_t s = a->s_comp;
+                        bool do_map, cudaStream_t s, DBuf& scratch) {
   const int ge = small_grid(a, elem_bound), gt = small_grid(a, table_bound), gw = small_grid(a, elem_bound / 32 + 1);
   k_fo_zero<<<dim3(gw, count), kThreads, 0, s>>>(djobs + first);
   if (need_min) { k_fo_min<<<dim3(ge, count), kThreads, 0, s>>>(djobs + first); t.launches++; }
   k_fo_bits<<<dim3(gt, count), kThreads, 0, s>>>(djobs + first);
-  launch_scan(a, FoWordsF{djobs + first, -1}, count, t, gw);
+  launch_scan(a, FoWordsF{djobs + first, -1}, count, t, gw, s, scratch);
   k_fo_assign<<<dim3(gt, count), kThreads, 0, s>>>(djobs + first);
   if (do_map) { k_fo_map<<<dim3(ge, count), kThreads, 0, s>>>(djobs + first); t.launches++; }
   t.launches += 3;
@@ -580,100 +645,137 @@ static void launch_store_insert(pa_agg* a) {
   sa.ctr = ctr; sa.uniq_row = a->d_uniq_row.as<uint32_t>(); sa.slot_of_row = a->d_slot.as<uint32_t>(); sa.tab = a->d_table.as<StackSlot>();
   sa.nframes = a->d_nfr.as<uint16_t>(); sa.frame_off = a->d_foff.as<unsigned long long>();
   sa.frames = a->src_frames;
-  sa.n_frames_registered = a->ft.count();
+  sa.n_frames_registered = a->P.n_frames;
   sa.st = a->d_store.as<StoreSlot>(); sa.mask = (uint32_t)(a->store_slots - 1); sa.arena = a->d_store_arena.as<uint32_t>();
   sa.cap_frames = a->store_frames; sa.cap_entries = (uint32_t)a->store_entries; sa.ctl = a->d_store_ctl.as<StoreCtl>(); sa.ctr_w = ctr;
   k_store_insert<<<a->G, kThreads, 0, a->s_comp>>>(sa);
 }
 
-static int process_once(pa_agg* a) {
+// ---------------------------------------------------------------------------------------------
+// The per-interval pass, in stages. A single aggregator runs them back to back (process_once); a group of shard
+// aggregators that builds ONE merged record (mode B, merge_impl.hpp) runs the same stages with its exchanges in between.
+static uint64_t table_bound(uint64_t n, uint64_t prev, uint64_t big, uint64_t floor_) {
+  return (prev && n > big) ? std::min<uint64_t>(n, std::max<uint64_t>(prev * 4, floor_)) : n;
+}
+
+// sizes, arena layout, job / column descriptor tables for the staged batch. md != nullptr: this aggregator is shard
+// md->rank of a merged batch (row-indexed bitmaps and dictionary tables are sized for the whole batch)
+static int pass_plan(pa_agg* a, const MergeDims* md) {
+  Pass& P = a->P;
   const uint64_t N = a->N;
-  const uint32_t n_cstr = a->sp.count(), n_frames = a->ft.count(), n_funcs = a->ft.n_funcs();
-  const uint32_t ncols = (uint32_t)a->cols.size(), nlab = a->n_label_cols;
-  const bool v1 = a->cfg.schema == PA_SCHEMA_V1;
-  cudaStream_t s = a->s_comp;
-  for (int t = 0; t < T_COUNT; t++) { a->tm[t].launches = 0; a->tm[t].ms = 0; }
+  P.N = N;
+  P.merged = md != nullptr;
+  P.row_base = md ? md->row_base : 0;
+  P.NT = md ? md->n_total : N;
+  P.world = md ? md->world : 1;
+  P.rank = md ? md->rank : 0;
+  P.ncols = (uint32_t)a->cols.size();
+  P.nlab = a->n_label_cols;
+  P.v1 = a->cfg.schema == PA_SCHEMA_V1;
+  P.provided = a->cfg.hash_mode == PA_HASH_PROVIDED;
+  const uint32_t ncols = P.ncols, nlab = P.nlab;
+  const bool v1 = P.v1;
 
   // ---- stack table capacity: 2x an upper bound on this batch's unique stacks (adaptive, retried on overflow)
-  uint64_t bound = N;
-  if (a->prev_unique && N > (1u << 20)) bound = std::min<uint64_t>(N, std::max<uint64_t>(a->prev_unique * 4, 1u << 18));
+  uint64_t bound = table_bound(N, a->prev_unique, 1u << 20, 1u << 18);
   uint64_t cap = std::max<uint64_t>(pow2_at_least(2 * std::max<uint64_t>(bound, 1)), 1024);
   if (cap < a->retry_cap) cap = a->retry_cap;
+  if (cap > (1ull << 31)) cap = 1ull << 31;  // slot index mask+1 must stay below 2^32
   a->table_cap = cap;
+  P.cap = cap;
+  P.mask = (uint32_t)(cap - 1);
   CK(a->d_table.ensure((cap + 2) * sizeof(StackSlot)));
-  // thread_id dictionary table (hashed): same policy
-  uint64_t tbound = N;
-  if (a->prev_tids && N > (1u << 18)) tbound = std::min<uint64_t>(N, std::max<uint64_t>(a->prev_tids * 4, 1u << 16));
+  // thread_id dictionary table (hashed): same policy; a merged batch holds every shard's thread ids
+  uint64_t tbound = table_bound(P.NT, a->prev_tids, 1u << 18, 1u << 16);
   uint64_t tcap = std::max<uint64_t>(pow2_at_least(2 * std::max<uint64_t>(tbound, 16)), 1024);
   if (tcap < a->retry_tcap) tcap = a->retry_tcap;
+  if (tcap > (1ull << 31)) tcap = 1ull << 31;
   a->tid_cap = tcap;
   a->tid_mask = (uint32_t)(tcap - 1);
+  P.tcap = tcap;
 
   // ---- arena: per-flush scratch and small output buffers; three classes (0xFF / zero / uninitialised)
   struct Req { void** pp; size_t bytes; int cls; };
   std::vector<Req> reqs;
   auto want = [&reqs](auto** pp, size_t bytes, int cls = 2) { reqs.push_back(Req{(void**)pp, (bytes + 255) & ~(size_t)255, cls}); };
-  const size_t P = std::max<uint32_t>(n_frames, 1), S = std::max<uint32_t>(n_cstr, 1), FN = std::max<uint32_t>(n_funcs, 1);
-  const size_t NI = (size_t)std::min<uint64_t>(std::max<uint64_t>(a->NF, 1), 0x7FFFFFFFull);
-  const size_t Nn = (size_t)std::max<uint64_t>(N, 1);
-  uint32_t *rowbits = nullptr, *row_wprefix = nullptr, *uniq_slot = nullptr, *uniq_size = nullptr, *first_ls = nullptr, *claimed = nullptr;
-  want(&first_ls, std::max<size_t>(a->ls.sets.size(), 1) * 4, 0);
+  const size_t Pn = std::max<uint32_t>(P.n_frames, 1), S = std::max<uint32_t>(P.n_cstr, 1), FN = std::max<uint32_t>(P.n_funcs, 1);
+  const uint64_t nf_all = md ? md->nf_total : a->NF;
+  const size_t NI = (size_t)std::min<uint64_t>(std::max<uint64_t>(nf_all, 1), 0x7FFFFFFFull);
+  const size_t Nn = (size_t)std::max<uint64_t>(N, 1), NTn = (size_t)std::max<uint64_t>(P.NT, 1);
+  P.Pn = Pn; P.S = S; P.FN = FN; P.NI = NI;
+  // direct first-row tables that a merged batch all-reduces (min) in one go: [labelset | cpu | comm], contiguous
+  uint32_t *first_cpu = nullptr, *first_comm = nullptr;
+  bool has_cpu = false, has_comm = false;
+  for (uint32_t c = 0; c < nlab; c++) { has_cpu |= a->cols[c].type == COL_CPU; has_comm |= a->cols[c].type == COL_COMM; }
+  want(&P.first_ls, std::max<size_t>(P.n_labelsets, 1) * 4, 0);
+  if (has_cpu) want(&first_cpu, 65536 * 4, 0);
+  if (has_comm) want(&first_comm, S * 4, 0);
+  size_t red_bytes = 0;
+  for (auto& r : reqs) red_bytes += r.bytes;
   if (v1) {
     want(&a->v1_ord, Nn * 4); want(&a->v1_ts_vals, Nn * 8); want(&a->v1_id_off, (Nn + 1) * 4);
     a->v1_ids = a->d_v1_ids.as<uint8_t>();  // outlives the arena: pa_agg_last_stack_ids / pa_agg_stacktraces run after the flush
     want(&a->v1_first_kind, 8 * 4, 0); want(&a->v1_kindrank, 64 * 4); want(&a->v1_kind_order, 64 * 4); want(&a->v1_n_kind_dict, 8 * 4);
   }
-  want(&rowbits, (Nn / 32 + 2) * 4, 1); want(&row_wprefix, (Nn / 32 + 2) * 4); want(&uniq_slot, Nn * 4); want(&uniq_size, Nn * 4);
-  want(&claimed, Nn * 4);
-  uint32_t *loc_bits = nullptr, *loc_wp = nullptr;
-  want(&a->loc_first, P * 4, 0); want(&a->loc_rank, P * 4); want(&a->loc_order, P * 4);
-  want(&loc_bits, (NI / 32 + 2) * 4); want(&loc_wp, (NI / 32 + 2) * 4);
-  uint32_t *sd_bits[4] = {}, *sd_wp[4] = {}, *fn_bits = nullptr, *fn_wp = nullptr;
+  want(&P.rowbits, (NTn / 32 + 2) * 4, 1); want(&P.row_wprefix, (NTn / 32 + 2) * 4);
+  if (!md) { want(&P.uniq_slot, Nn * 4); want(&P.uniq_size, Nn * 4); }  // merged: sized by the merged dictionary (merge_impl.hpp)
+  want(&P.claimed, Nn * 4);
+  want(&a->loc_first, Pn * 4, 0); want(&a->loc_rank, Pn * 4); want(&a->loc_order, Pn * 4);
+  want(&P.loc_bits, (NI / 32 + 2) * 4); want(&P.loc_wp, (NI / 32 + 2) * 4);
   for (int d = 0; d < 4; d++) {
-    size_t n = d == 3 ? FN : P;
+    size_t n = d == 3 ? FN : Pn;
     want(&a->sd_first[d], S * 4, 0); want(&a->sd_rank[d], S * 4); want(&a->sd_order[d], S * 4);
     want(&a->sd_keys[d], n * 4); want(&a->sd_valid[d], (n / 32 + 2) * 4);
-    want(&sd_bits[d], (n / 32 + 2) * 4); want(&sd_wp[d], (n / 32 + 2) * 4);
+    want(&P.sd_bits[d], (n / 32 + 2) * 4); want(&P.sd_wp[d], (n / 32 + 2) * 4);
   }
-  want(&a->fn_first, FN * 4, 0); want(&a->fn_rank, FN * 4); want(&a->fn_order, FN * 4); want(&a->fn_keys, P * 4);
-  want(&fn_bits, (P / 32 + 2) * 4); want(&fn_wp, (P / 32 + 2) * 4);
-  want(&a->lo.address, P * 8); want(&a->lo.line_off, P * 4); want(&a->lo.line_size, P * 4); want(&a->lo.line_valid, (P / 32 + 2) * 4);
-  want(&a->lo.line_no, P * 8);
-  std::vector<uint32_t*> col_first(ncols, nullptr), col_rank(ncols, nullptr), col_bits(ncols, nullptr), col_wp(ncols, nullptr);
+  want(&a->fn_first, FN * 4, 0); want(&a->fn_rank, FN * 4); want(&a->fn_order, FN * 4); want(&a->fn_keys, Pn * 4);
+  want(&P.fn_bits, (Pn / 32 + 2) * 4); want(&P.fn_wp, (Pn / 32 + 2) * 4);
+  want(&a->lo.address, Pn * 8); want(&a->lo.line_off, Pn * 4); want(&a->lo.line_size, Pn * 4); want(&a->lo.line_valid, (Pn / 32 + 2) * 4);
+  want(&a->lo.line_no, Pn * 8);
+  if (md) want(&P.edge_keys, (size_t)ncols * 16, 1);
+  P.col_first.assign(ncols, nullptr); P.col_rank.assign(ncols, nullptr); P.col_bits.assign(ncols, nullptr); P.col_wp.assign(ncols, nullptr);
+  a->tid_slots = nullptr; a->tid_rank = nullptr;
   for (uint32_t c = 0; c < ncols; c++) {
     ColPlan& cp = a->cols[c];
+    cp.validity = nullptr; cp.order = nullptr;
     want(&cp.run_ends, Nn * 4);
     want(&cp.run_keys, Nn * 4);
-    if (v1 && cp.type == COL_KIND && cp.param == 5) want(&cp.validity, (Nn / 32 + 2) * 4, 1);  // temporality has null runs
+    if (v1 && cp.type == COL_KIND && cp.param == 5) want(&cp.validity, (Nn / 32 + 3) * 4, 1);  // temporality has null runs
     if (c >= nlab) continue;
-    want(&cp.validity, (Nn / 32 + 2) * 4, 1);
-    want(&col_bits[c], (Nn / 32 + 2) * 4); want(&col_wp[c], (Nn / 32 + 2) * 4);
-    if (cp.type == COL_COMM) cp.universe = n_cstr;
+    want(&cp.validity, (Nn / 32 + 3) * 4, 1);
+    want(&P.col_bits[c], (NTn / 32 + 2) * 4); want(&P.col_wp[c], (NTn / 32 + 2) * 4);
+    if (cp.type == COL_COMM) cp.universe = P.n_cstr;
     if (cp.type == COL_TID) {
       want(&a->tid_slots, (size_t)tcap * 8, 0);
       want(&a->tid_rank, (size_t)tcap * 4);
-      want(&cp.order, Nn * 4);
+      want(&cp.order, (size_t)std::min<uint64_t>(NTn, tcap) * 4);
     } else {
       size_t u = std::max<uint32_t>(cp.universe, 1);
-      want(&col_first[c], u * 4, 0); want(&col_rank[c], u * 4); want(&cp.order, u * 4);
+      if (cp.type == COL_CPU) P.col_first[c] = first_cpu;
+      else if (cp.type == COL_COMM) P.col_first[c] = first_comm;
+      else want(&P.col_first[c], u * 4, 0);
+      want(&P.col_rank[c], u * 4); want(&cp.order, u * 4);
     }
   }
-  size_t cls_bytes[3] = {0, 0, 0};
-  for (auto& r : reqs) cls_bytes[r.cls] += r.bytes;
-  CK(a->d_arena.ensure(std::max<size_t>(cls_bytes[0] + cls_bytes[1] + cls_bytes[2], 256)));
+  P.cls_bytes[0] = P.cls_bytes[1] = P.cls_bytes[2] = 0;
+  for (auto& r : reqs) P.cls_bytes[r.cls] += r.bytes;
+  CK(a->d_arena.ensure(std::max<size_t>(P.cls_bytes[0] + P.cls_bytes[1] + P.cls_bytes[2], 256)));
   {
-    size_t off[3] = {0, cls_bytes[0], cls_bytes[0] + cls_bytes[1]};  // [0xFF region][zero region][rest]
+    size_t off[3] = {0, P.cls_bytes[0], P.cls_bytes[0] + P.cls_bytes[1]};  // [0xFF region][zero region][rest]
     for (auto& r : reqs) { *r.pp = a->d_arena.as<uint8_t>() + off[r.cls]; off[r.cls] += r.bytes; }
   }
+  for (uint32_t c = 0; c < nlab; c++) {  // the shared tables were carved before the loop
+    if (a->cols[c].type == COL_CPU) P.col_first[c] = first_cpu;
+    if (a->cols[c].type == COL_COMM) P.col_first[c] = first_comm;
+  }
+  P.red_block = P.first_ls;
+  P.red_count = red_bytes / 4;
   a->lo.type_key = a->sd_keys[0]; a->lo.map_key = a->sd_keys[1]; a->lo.bid_key = a->sd_keys[2]; a->lo.func_key = a->fn_keys;
 
   Counters* ctr = a->d_ctr.as<Counters>();
-  StackSlot* tab = a->d_table.as<StackSlot>();
-  const uint32_t mask = (uint32_t)(cap - 1);
-  const int G = a->G;
-
   // ---- dictionaries: jobs table
-  std::vector<FoJob> jobs;
+  std::vector<FoJob>& jobs = P.jobs;
+  jobs.clear();
   auto job = [&](const uint32_t* keys, const uint32_t* n_ptr, uint32_t* first, uint32_t universe, uint32_t* rank, uint32_t* order, uint32_t* out,
                  uint32_t* validity, uint32_t* bitmap, uint32_t* wprefix, uint32_t* n_unique, uint32_t* n_null, bool nullable, bool skip_min) {
     FoJob j{};
@@ -684,30 +786,33 @@ static int process_once(pa_agg* a) {
   };
   // the low 32 bits of n_indices64 are the index count (overflow is flagged separately)
   const uint32_t* n_idx_ptr = (const uint32_t*)&ctr->n_indices64;
-  int j_loc = job(a->d_ustream.as<uint32_t>(), n_idx_ptr, a->loc_first, n_frames, a->loc_rank, a->loc_order, a->d_ustream.as<uint32_t>(), nullptr,
-                  loc_bits, loc_wp, &ctr->n_locations, nullptr, false, true);
-  int j_type = job(a->sd_keys[0], &ctr->n_locations, a->sd_first[0], n_cstr, a->sd_rank[0], a->sd_order[0], a->sd_keys[0], nullptr, sd_bits[0], sd_wp[0], &ctr->n_dict_type, nullptr, false, false);
-  job(a->sd_keys[1], &ctr->n_locations, a->sd_first[1], n_cstr, a->sd_rank[1], a->sd_order[1], a->sd_keys[1], nullptr, sd_bits[1], sd_wp[1], &ctr->n_dict_map, nullptr, false, false);
-  job(a->sd_keys[2], &ctr->n_locations, a->sd_first[2], n_cstr, a->sd_rank[2], a->sd_order[2], a->sd_keys[2], a->sd_valid[2], sd_bits[2], sd_wp[2], &ctr->n_dict_bid, &ctr->null_bid, true, false);
-  job(a->fn_keys, &ctr->n_lines, a->fn_first, n_funcs, a->fn_rank, a->fn_order, a->fn_keys, nullptr, fn_bits, fn_wp, &ctr->n_functions, nullptr, false, false);
-  int j_file = job(a->sd_keys[3], &ctr->n_functions, a->sd_first[3], n_cstr, a->sd_rank[3], a->sd_order[3], a->sd_keys[3], a->sd_valid[3], sd_bits[3], sd_wp[3], &ctr->n_dict_file, &ctr->null_file, true, false);
-  int j_lab0 = (int)jobs.size();
+  const uint32_t n_cstr = P.n_cstr;
+  P.j_loc = job(a->d_ustream.as<uint32_t>(), n_idx_ptr, a->loc_first, P.n_frames, a->loc_rank, a->loc_order, a->d_ustream.as<uint32_t>(), nullptr,
+                P.loc_bits, P.loc_wp, &ctr->n_locations, nullptr, false, true);
+  P.j_type = job(a->sd_keys[0], &ctr->n_locations, a->sd_first[0], n_cstr, a->sd_rank[0], a->sd_order[0], a->sd_keys[0], nullptr, P.sd_bits[0], P.sd_wp[0], &ctr->n_dict_type, nullptr, false, false);
+  job(a->sd_keys[1], &ctr->n_locations, a->sd_first[1], n_cstr, a->sd_rank[1], a->sd_order[1], a->sd_keys[1], nullptr, P.sd_bits[1], P.sd_wp[1], &ctr->n_dict_map, nullptr, false, false);
+  job(a->sd_keys[2], &ctr->n_locations, a->sd_first[2], n_cstr, a->sd_rank[2], a->sd_order[2], a->sd_keys[2], a->sd_valid[2], P.sd_bits[2], P.sd_wp[2], &ctr->n_dict_bid, &ctr->null_bid, true, false);
+  job(a->fn_keys, &ctr->n_lines, a->fn_first, P.n_funcs, a->fn_rank, a->fn_order, a->fn_keys, nullptr, P.fn_bits, P.fn_wp, &ctr->n_functions, nullptr, false, false);
+  P.j_file = job(a->sd_keys[3], &ctr->n_functions, a->sd_first[3], n_cstr, a->sd_rank[3], a->sd_order[3], a->sd_keys[3], a->sd_valid[3], P.sd_bits[3], P.sd_wp[3], &ctr->n_dict_file, &ctr->null_file, true, false);
+  P.j_lab0 = (int)jobs.size();
   for (uint32_t c = 0; c < nlab; c++) {
     ColPlan& cp = a->cols[c];
     bool nullable = cp.type == COL_LS || cp.type == COL_COMM;
-    // first ROWS are recorded by the REE count pass (skip_min); the emit pass applies the ranks itself (no map pass)
-    int ji = job(nullptr, nullptr, col_first[c], cp.universe, col_rank[c], cp.order, nullptr, nullptr, col_bits[c], col_wp[c],
+    // first ROWS are recorded by k_header / k_ls_first (skip_min); the emit pass applies the ranks itself (no map pass)
+    int ji = job(nullptr, nullptr, P.col_first[c], cp.universe, P.col_rank[c], cp.order, nullptr, nullptr, P.col_bits[c], P.col_wp[c],
                  &ctr->n_dict[c], nullptr, nullable, true);
-    jobs[ji].n_imm = (uint32_t)N;
+    jobs[ji].n_imm = (uint32_t)P.NT;
     if (cp.type == COL_TID) { jobs[ji].hashed = 1; jobs[ji].hslots = a->tid_slots; jobs[ji].hmask = a->tid_mask; jobs[ji].rank = a->tid_rank; }
   }
-  std::vector<ReeCol> rc(ncols);
-  ReeArgs ra{};
+  std::vector<ReeCol>& rc = P.rc;
+  rc.assign(ncols, ReeCol{});
+  ReeArgs& ra = P.ra;
+  ra = ReeArgs{};
   ra.c_cpu = ra.c_tid = ra.c_comm = ra.c_ord = ra.c_ts = -1;
   for (uint32_t c = 0; c < ncols; c++) {
     const ColPlan& cp = a->cols[c];
-    rc[c] = ReeCol{cp.type, cp.param, cp.run_ends, cp.run_keys, c < nlab ? col_first[c] : nullptr, nullptr, 0,
-                   (cp.type == COL_LS || cp.type == COL_COMM) ? 1u : 0u, c < nlab ? col_rank[c] : nullptr, c < nlab ? cp.validity : nullptr};
+    rc[c] = ReeCol{cp.type, cp.param, cp.run_ends, cp.run_keys, c < nlab ? P.col_first[c] : nullptr, nullptr, 0,
+                   (cp.type == COL_LS || cp.type == COL_COMM) ? 1u : 0u, c < nlab ? P.col_rank[c] : nullptr, c < nlab ? cp.validity : nullptr};
     if (cp.type == COL_TID) { rc[c].hslots = a->tid_slots; rc[c].hmask = a->tid_mask; rc[c].rank = a->tid_rank; }
     if (cp.type == COL_CPU) ra.c_cpu = (int)c;
     if (cp.type == COL_TID) ra.c_tid = (int)c;
@@ -717,39 +822,58 @@ static int process_once(pa_agg* a) {
     if (v1 && cp.type == COL_KIND && cp.param == 5) { rc[c].nullable = 1; rc[c].validity = cp.validity; }
   }
   if (v1) { ra.ord = a->v1_ord; ra.ts = a->d_ts.as<long long>(); ra.ts_vals = a->v1_ts_vals; ra.kindrank = a->v1_kindrank; ra.kind_dict_mask = 0x3Fu; }
-  {  // descriptor tables go up first
-    int rcu = upload_descriptors(a, jobs.data(), jobs.size() * sizeof(FoJob), rc.data(), rc.size() * sizeof(ReeCol));
-    if (rcu) return rcu;
+  ra.n_rows = (uint32_t)N; ra.ncols = ncols; ra.n_ls = a->n_lscols; ra.c_kind = nlab; ra.cols = nullptr /* set after the upload */;
+  ra.ls = a->d_ls.as<uint32_t>(); ra.cpu = a->d_cpu.as<uint32_t>(); ra.tid = a->d_tid.as<uint32_t>(); ra.comm = a->d_comm.as<uint32_t>(); ra.kind = a->d_kind.as<uint8_t>();
+  ra.lsmat = a->d_lsmat.as<uint32_t>(); ra.n_lscols = std::max<uint32_t>(1, a->n_lscols); ra.kindtab = a->d_kindtab.as<uint32_t>();
+  ra.partial = a->d_ree_partial.as<uint32_t>(); ra.ctr = ctr;
+  ra.row_base = (uint32_t)P.row_base; ra.edge_keys = md ? P.edge_keys : nullptr; ra.mc = nullptr;
+  ReeGroups& rg = P.rg;  // one launch row per column (the 8 kind-derived columns form one group)
+  rg = ReeGroups{};
+  for (uint32_t c = 0; c < ncols; c++) {
+    const ColPlan& cp = a->cols[c];
+    if (cp.type == COL_KIND && cp.param != 0) continue;
+    rg.g[rg.n++] = ReeGroup{cp.type, c, cp.param};
   }
-  const FoJob* djobs = a->d_jobs.as<FoJob>();
+  int rcu = upload_descriptors(a, jobs.data(), jobs.size() * sizeof(FoJob), rc.data(), rc.size() * sizeof(ReeCol));
+  if (rcu) return rcu;
+  ra.cols = a->d_cols.as<ReeCol>();
+  for (int t = 0; t < T_COUNT; t++) { a->tm[t].launches = 0; a->tm[t].ms = 0; }
+  return PA_OK;
+}
 
+// memsets, header split (+insert in provided mode), hash+insert
+static int pass_front(pa_agg* a) {
+  Pass& P = a->P;
+  const uint64_t N = P.N;
+  cudaStream_t s = a->s_comp;
+  Counters* ctr = a->d_ctr.as<Counters>();
+  StackSlot* tab = a->d_table.as<StackSlot>();
+  const int G = a->G;
   CK(cudaEventRecord(a->tm[T_TOTAL].a, s));
   CK(cudaMemsetAsync(ctr, 0, sizeof(Counters), s));
-  CK(cudaMemsetAsync(tab, 0, (cap + 2) * sizeof(StackSlot), s));
-  if (cls_bytes[0]) CK(cudaMemsetAsync(a->d_arena.p, 0xFF, cls_bytes[0], s));
-  if (cls_bytes[1]) CK(cudaMemsetAsync(a->d_arena.as<uint8_t>() + cls_bytes[0], 0, cls_bytes[1], s));
-
-  // ---- header split (+insert in provided mode), then hash+insert
-  const bool provided = a->cfg.hash_mode == PA_HASH_PROVIDED;
+  CK(cudaMemsetAsync(tab, 0, (P.cap + 2) * sizeof(StackSlot), s));
+  if (P.cls_bytes[0]) CK(cudaMemsetAsync(a->d_arena.p, 0xFF, P.cls_bytes[0], s));
+  if (P.cls_bytes[1]) CK(cudaMemsetAsync(a->d_arena.as<uint8_t>() + P.cls_bytes[0], 0, P.cls_bytes[1], s));
+  const bool provided = P.provided;
   // When the whole batch is already resident (pa_agg_stage) the two passes run back to back and
   // are timed separately; during an overlapped flush they interleave per chunk as copies land.
   const bool resident = a->chunk_ev.empty() || a->chunk_rows.empty() || cudaEventQuery(a->chunk_ev[a->chunk_rows.size() - 1]) == cudaSuccess;
   a->hash_timed = resident && !provided;
   auto launch_header = [&](uint64_t r0, uint64_t r1, uint64_t frames_end) {
     HeaderArgs h{};
-    h.hdr = a->d_hdr.as<uint4>(); h.row0 = (uint32_t)r0; h.row1 = (uint32_t)r1;
+    h.hdr = a->d_hdr.as<uint4>(); h.row0 = (uint32_t)r0; h.row1 = (uint32_t)r1; h.row_base = (uint32_t)P.row_base;
     h.timestamp = a->d_ts.as<long long>(); h.value = a->d_value.as<long long>(); h.uuid = a->d_uuid.as<uint8_t>();
     h.kind = a->d_kind.as<uint8_t>(); h.nframes = a->d_nfr.as<uint16_t>(); h.frame_off = a->d_foff.as<unsigned long long>();
     h.ls = a->d_ls.as<uint32_t>(); h.cpu = a->d_cpu.as<uint32_t>(); h.tid = a->d_tid.as<uint32_t>(); h.comm = a->d_comm.as<uint32_t>();
-    h.sid2cid = a->m_sid2cid.ptr(); h.n_sids = (uint32_t)a->sp.sid2cid.size(); h.n_labelsets = (uint32_t)a->ls.sets.size();
-    h.n_frame_ids = frames_end; h.provided = provided ? 1 : 0; h.tab = tab; h.mask = mask; h.slot_of_row = a->d_slot.as<uint32_t>(); h.ctr = ctr; h.claimed = claimed;
-    h.first_ls = a->n_lscols ? first_ls : nullptr;
-    for (uint32_t c = 0; c < nlab; c++) {
-      if (a->cols[c].type == COL_CPU) h.first_cpu = col_first[c];
+    h.sid2cid = a->m_sid2cid.ptr(); h.n_sids = P.n_sids; h.n_labelsets = P.n_labelsets;
+    h.n_frame_ids = frames_end; h.provided = provided ? 1 : 0; h.tab = tab; h.mask = P.mask; h.slot_of_row = a->d_slot.as<uint32_t>(); h.ctr = ctr; h.claimed = P.claimed;
+    h.first_ls = a->n_lscols ? P.first_ls : nullptr;
+    for (uint32_t c = 0; c < P.nlab; c++) {
+      if (a->cols[c].type == COL_CPU) h.first_cpu = P.col_first[c];
       if (a->cols[c].type == COL_TID) { h.tid_slots = a->tid_slots; h.tid_mask = a->tid_mask; }
-      if (a->cols[c].type == COL_COMM) h.first_comm = col_first[c];
+      if (a->cols[c].type == COL_COMM) h.first_comm = P.col_first[c];
     }
-    h.first_kind = v1 ? a->v1_first_kind : nullptr;
+    h.first_kind = P.v1 ? a->v1_first_kind : nullptr;
     uint64_t rows = r1 - r0;
     int hb = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)G * 2);
     k_header<<<std::max(hb, 1), kThreads, 0, s>>>(h);
@@ -759,20 +883,22 @@ static int process_once(pa_agg* a) {
     HashArgs ha{};
     ha.frames = a->d_frames.as<unsigned long long>(); ha.frame_off = a->d_foff.as<unsigned long long>(); ha.nframes = a->d_nfr.as<uint16_t>();
     ha.row0 = (uint32_t)r0; ha.row1 = (uint32_t)r1; ha.uuid = a->d_uuid.as<uint8_t>();
-    ha.slot_of_row = a->d_slot.as<uint32_t>(); ha.tab = tab; ha.mask = mask; ha.ctr = ctr; ha.claimed = claimed;
+    ha.slot_of_row = a->d_slot.as<uint32_t>(); ha.tab = tab; ha.mask = P.mask; ha.ctr = ctr; ha.claimed = P.claimed;
     uint64_t rows = r1 - r0;
     int blocks = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)a->sms * (a->hash_variant == 1 ? 3 : 4));
-    if (a->hash_variant == 1) k_hash_insert_staged<<<std::max(blocks, 1), kThreads, kHashStagedSmem, s>>>(ha);
+    if (a->hash_variant == 3) k_hash_insert_bulk<4, 3><<<(int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 127) / 128, (uint64_t)a->sms)), 128, sizeof(BulkSmem<4, 3>), s>>>(ha);
+    else if (a->hash_variant == 4) k_hash_insert_bulk<6, 2><<<(int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 191) / 192, (uint64_t)a->sms)), 192, sizeof(BulkSmem<6, 2>), s>>>(ha);
+    else if (a->hash_variant == 1) k_hash_insert_staged<<<std::max(blocks, 1), kThreads, kHashStagedSmem, s>>>(ha);
     else if (a->hash_variant == 2) k_hash_insert_wide<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     else k_hash_insert<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     a->tm[T_HASH].launches++;
   };
   CK(cudaEventRecord(a->tm[T_HEADER].a, s));
   if (resident) {
-    launch_header(0, N, a->NF);  // whole resident batch: one launch per pass
+    if (N) launch_header(0, N, a->NF);  // whole resident batch: one launch per pass
     CK(cudaEventRecord(a->tm[T_HEADER].b, s));
     CK(cudaEventRecord(a->tm[T_HASH].a, s));
-    if (!provided) launch_hash(0, N);
+    if (!provided && N) launch_hash(0, N);
     CK(cudaEventRecord(a->tm[T_HASH].b, s));
   } else {
     for (size_t k = 0; k < a->chunk_rows.size(); k++) {
@@ -782,79 +908,106 @@ static int process_once(pa_agg* a) {
     }
     CK(cudaEventRecord(a->tm[T_HEADER].b, s));
   }
+  return PA_OK;
+}
 
-  // ---- unique stacks: ordinals from the first-row bitmap, offsets from a scan over the unique list
+// unique stacks of ONE aggregator: ordinals from the first-row bitmap, offsets from a scan over the unique list,
+// per-row ListView (offset, size), gather of the unique stacks' frames
+static int pass_rank_single(pa_agg* a) {
+  Pass& P = a->P;
+  const uint64_t N = P.N;
+  cudaStream_t s = a->s_comp;
+  Counters* ctr = a->d_ctr.as<Counters>();
+  StackSlot* tab = a->d_table.as<StackSlot>();
+  const int G = a->G;
   CK(cudaEventRecord(a->tm[T_RANK].a, s));
-  const int Gw = small_grid(a, N / 32 + 1), Gu = small_grid(a, std::min<uint64_t>(N, cap / 2));
-    k_stack_bits<<<Gu, kThreads, 0, s>>>(tab, claimed, ctr, rowbits);
-    launch_scan(a, WordsF{rowbits, row_wprefix, (uint32_t)((N + 31) / 32), &ctr->n_unique}, 1, a->tm[T_RANK], Gw);
-    k_stack_assign<<<Gu, kThreads, 0, s>>>(tab, claimed, ctr, rowbits, row_wprefix, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(), uniq_slot, uniq_size);
-    launch_scan(a, UniqOffsetF{ctr, ctr, uniq_size, uniq_slot, tab}, 1, a->tm[T_RANK], Gu);
-    a->tm[T_RANK].launches += 2;
-  k_rows_materialize<<<G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>(), v1 ? a->v1_ord : nullptr);
-  if (v1) {  // v1 has no inline stacktraces: only the dictionary of unique stack ids
-    k_gather_ids<<<small_grid(a, std::min<uint64_t>(N, cap / 2) + 1), kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_uuid.as<uint8_t>(), a->v1_ids, a->v1_id_off);
+  const int Gw = small_grid(a, N / 32 + 1), Gu = small_grid(a, std::min<uint64_t>(N, P.cap / 2));
+  k_stack_bits<<<Gu, kThreads, 0, s>>>(tab, P.claimed, &ctr->n_claimed, P.rowbits);
+  launch_scan(a, WordsF{P.rowbits, P.row_wprefix, (uint32_t)((N + 31) / 32), &ctr->n_unique}, 1, a->tm[T_RANK], Gw, s, a->d_partial);
+  k_stack_assign<<<Gu, kThreads, 0, s>>>(tab, P.claimed, &ctr->n_claimed, P.rowbits, P.row_wprefix, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(), P.uniq_slot, P.uniq_size);
+  launch_scan(a, UniqOffsetF{ctr, ctr, P.uniq_size, P.uniq_slot, tab}, 1, a->tm[T_RANK], Gu, s, a->d_partial);
+  a->tm[T_RANK].launches += 2;
+  k_rows_materialize<<<G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>(), P.v1 ? a->v1_ord : nullptr);
+  if (P.v1) {  // v1 has no inline stacktraces: only the dictionary of unique stack ids
+    k_gather_ids<<<small_grid(a, std::min<uint64_t>(N, P.cap / 2) + 1), kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_uuid.as<uint8_t>(), a->v1_ids, a->v1_id_off);
     launch_store_insert(a);
     a->tm[T_RANK].launches++;
   } else {
-    const unsigned long long* gather_src = a->src_frames;
-    k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, gather_src,
-                                           a->d_foff.as<unsigned long long>(), n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr);
+    k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, a->src_frames,
+                                           a->d_foff.as<unsigned long long>(), P.n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr);
   }
   a->tm[T_RANK].launches += 2;
   CK(cudaEventRecord(a->tm[T_RANK].b, s));
+  return PA_OK;
+}
 
-  auto run_jobs = [&](int first, int count, bool need_min, Timer& t, uint64_t elem_bound, uint64_t table_bound, bool do_map = true) {
-    run_fo_jobs(a, djobs, first, count, need_min, t, elem_bound, table_bound, do_map);
-  };
-
+// location / function / string dictionaries from the (merged) unique-stack frame stream
+static int pass_locations(pa_agg* a) {
+  Pass& P = a->P;
+  cudaStream_t s = a->s_comp;
+  Counters* ctr = a->d_ctr.as<Counters>();
+  const FoJob* djobs = a->d_jobs.as<FoJob>();
+  const int G = a->G;
+  const size_t Pn = P.Pn, S = P.S, FN = P.FN;
   CK(cudaEventRecord(a->tm[T_LOC].a, s));
   FrameTable ftd{(const unsigned long long*)a->m_addr.ptr(), a->m_type.ptr(), a->m_map.ptr(), a->m_bid.ptr(), (const unsigned long long*)a->m_line.ptr(), a->m_func.ptr()};
-  if (!v1) {  // v1 carries no locations in the sample record
-    run_jobs(j_loc, 1, false, a->tm[T_LOC], std::min<uint64_t>(NI, cap * 32), P);  // location index per unique-stack frame (in place over the gathered stream)
-    launch_scan(a, LocLinesF{ctr, ctr, a->loc_order, ftd, a->lo}, 1, a->tm[T_LOC], small_grid(a, P));
-    k_line_validity<<<std::max(1, std::min(G, (int)(P / 256 + 1))), kThreads, 0, s>>>(ctr, a->lo.line_size, a->lo.line_valid);
-    run_jobs(j_type, 4, true, a->tm[T_LOC], P, std::max(S, FN));  // frame_type, mapping_file, mapping_build_id, function
+  if (!P.v1) {  // v1 carries no locations in the sample record
+    run_fo_jobs(a, djobs, P.j_loc, 1, false, a->tm[T_LOC], std::min<uint64_t>(P.NI, P.merged ? P.NI : P.cap * 32), Pn, true, s, a->d_partial);  // location index per unique-stack frame (in place over the gathered stream)
+    launch_scan(a, LocLinesF{ctr, ctr, a->loc_order, ftd, a->lo}, 1, a->tm[T_LOC], small_grid(a, Pn), s, a->d_partial);
+    k_line_validity<<<std::max(1, std::min(G, (int)(Pn / 256 + 1))), kThreads, 0, s>>>(ctr, a->lo.line_size, a->lo.line_valid);
+    run_fo_jobs(a, djobs, P.j_type, 4, true, a->tm[T_LOC], Pn, std::max(S, FN), true, s, a->d_partial);  // frame_type, mapping_file, mapping_build_id, function
     k_func_keys<<<std::max(1, std::min(G, (int)(FN / 256 + 1))), kThreads, 0, s>>>(ctr, a->fn_order, a->m_fnfile.ptr(), a->sd_keys[3]);
-    run_jobs(j_file, 1, true, a->tm[T_LOC], FN, S);  // function.filename
+    run_fo_jobs(a, djobs, P.j_file, 1, true, a->tm[T_LOC], FN, S, true, s, a->d_partial);  // function.filename
     a->tm[T_LOC].launches += 2;
   }
   CK(cudaEventRecord(a->tm[T_LOC].b, s));
+  return PA_OK;
+}
 
-  // ---- run-end encoding of label + constant columns (dictionary first positions recorded on the fly)
+// run-end encoding of label + constant columns, three steps so that a merged batch can exchange in between:
+// count (+ partial scan), dictionary ranks, emit. `s` may be a second stream (the chain only depends on k_header).
+static int pass_labels_count(pa_agg* a, cudaStream_t s) {
+  Pass& P = a->P;
   if (getenv("PA_DEBUG_SYNC")) CK(cudaStreamSynchronize(s));
   CK(cudaEventRecord(a->tm[T_LABELS].a, s));
-  ra.n_rows = (uint32_t)N; ra.ncols = ncols; ra.n_ls = a->n_lscols; ra.c_kind = nlab; ra.cols = a->d_cols.as<ReeCol>();
-  ra.ls = a->d_ls.as<uint32_t>(); ra.cpu = a->d_cpu.as<uint32_t>(); ra.tid = a->d_tid.as<uint32_t>(); ra.comm = a->d_comm.as<uint32_t>(); ra.kind = a->d_kind.as<uint8_t>();
-  ra.lsmat = a->d_lsmat.as<uint32_t>(); ra.n_lscols = std::max<uint32_t>(1, a->n_lscols); ra.kindtab = a->d_kindtab.as<uint32_t>();
-  ra.partial = a->d_ree_partial.as<uint32_t>(); ra.ctr = ctr;
-  const int Gr = a->sms * 8;  // latency-bound passes: fill every warp slot
   if (a->n_lscols) {  // first rows of the labelset-derived values, from the per-labelset memo of k_header
     LsFirstArgs lf{};
-    lf.first_ls = first_ls; lf.n_labelsets = (uint32_t)a->ls.sets.size(); lf.lsmat = a->d_lsmat.as<uint32_t>();
+    lf.first_ls = P.first_ls; lf.n_labelsets = P.n_labelsets; lf.lsmat = a->d_lsmat.as<uint32_t>();
     lf.n_lscols = std::max<uint32_t>(1, a->n_lscols); lf.n_ls = a->n_lscols;
-    for (uint32_t c = 0; c < a->n_lscols; c++) lf.col_first[c] = col_first[c];
+    for (uint32_t c = 0; c < a->n_lscols; c++) lf.col_first[c] = P.col_first[c];
     k_ls_first<<<small_grid(a, (uint64_t)lf.n_labelsets * lf.n_ls), kThreads, 0, s>>>(lf);
     a->tm[T_LABELS].launches++;
   }
-  if (v1) { k_kind_ranks<<<1, 32, 0, s>>>(a->v1_first_kind, a->d_kindtab.as<uint32_t>(), a->v1_kindrank, a->v1_kind_order, a->v1_n_kind_dict); a->tm[T_LABELS].launches++; }
-  ReeGroups rg{};  // one launch row per column (the 8 kind-derived columns form one group)
-  for (uint32_t c = 0; c < ncols; c++) {
-    const ColPlan& cp = a->cols[c];
-    if (cp.type == COL_KIND && cp.param != 0) continue;
-    rg.g[rg.n++] = ReeGroup{cp.type, c, cp.param};
-  }
-  const dim3 ree_grid(Gr, rg.n);
-  k_ree_col<false><<<ree_grid, kThreads, 0, s>>>(ra, rg);  // run counts
-  k_ree_scan_partials<<<ncols, kThreads, 0, s>>>(ra, Gr * kWarps);
+  if (P.v1) { k_kind_ranks<<<1, 32, 0, s>>>(a->v1_first_kind, a->d_kindtab.as<uint32_t>(), a->v1_kindrank, a->v1_kind_order, a->v1_n_kind_dict); a->tm[T_LABELS].launches++; }
+  const int Gr = a->sms * 8;  // latency-bound passes: fill every warp slot
+  const dim3 ree_grid(Gr, P.rg.n);
+  if (P.merged) k_ree_col<false, true><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);  // run counts (+ this shard's border keys)
+  else k_ree_col<false, false><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);
+  k_ree_scan_partials<<<P.ncols, kThreads, 0, s>>>(P.ra, Gr * kWarps);
   a->tm[T_LABELS].launches += 2;
+  return PA_OK;
+}
+static int pass_label_dicts(pa_agg* a, cudaStream_t s, DBuf& partial) {
+  Pass& P = a->P;
   CK(cudaEventRecord(a->tm[T_DICTS].a, s));
-  if (nlab) run_jobs(j_lab0, (int)nlab, false, a->tm[T_DICTS], N, std::max<uint64_t>(std::max<uint64_t>(S, 65536), tcap), false);  // label dictionary ranks
+  if (P.nlab) run_fo_jobs(a, a->d_jobs.as<FoJob>(), P.j_lab0, (int)P.nlab, false, a->tm[T_DICTS], P.NT, std::max<uint64_t>(std::max<uint64_t>(P.S, 65536), P.tcap), false, s, partial);  // label dictionary ranks
   CK(cudaEventRecord(a->tm[T_DICTS].b, s));
-  k_ree_col<true><<<ree_grid, kThreads, 0, s>>>(ra, rg);   // run ends + final dictionary indices + validity bits
+  return PA_OK;
+}
+static int pass_labels_emit(pa_agg* a, cudaStream_t s) {
+  Pass& P = a->P;
+  const dim3 ree_grid(a->sms * 8, P.rg.n);
+  if (P.merged) k_ree_col<true, true><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);   // run ends + final dictionary indices + validity bits
+  else k_ree_col<true, false><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);
   a->tm[T_LABELS].launches += 1;
   CK(cudaEventRecord(a->tm[T_LABELS].b, s));
+  return PA_OK;
+}
 
+// counters to the host, synchronise, collect the group timings
+static int pass_finish(pa_agg* a) {
+  cudaStream_t s = a->s_comp;
+  Counters* ctr = a->d_ctr.as<Counters>();
   CK(cudaMemcpyAsync(a->h_ctr_pinned, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(a->tm[T_TOTAL].b, s));
   CK(cudaStreamSynchronize(s));
@@ -875,9 +1028,52 @@ static int process_once(pa_agg* a) {
   return PA_OK;
 }
 
+static int process_once(pa_agg* a) {
+  int rc = pass_plan(a, nullptr);
+  if (rc) return rc;
+  if ((rc = pass_front(a))) return rc;
+  // The label chain depends only on k_header's outputs; the stack-rank / location chain only on the table. Both are
+  // chains of small latency-bound launches, so they run side by side on two streams (PA_SERIAL=1: one stream, so
+  // that the per-group event timings do not overlap).
+  // (v1: the run-end encoded stacktrace_id column reads the stack ordinals the rank chain produces, so the chains stay in order)
+  const bool fork = !a->serial && !a->P.v1;
+  cudaStream_t s = a->s_comp, s2 = fork ? a->s_aux : a->s_comp;
+  if (fork) { CK(cudaEventRecord(a->ev_fork, s)); CK(cudaStreamWaitEvent(s2, a->ev_fork, 0)); }
+  if ((rc = pass_rank_single(a))) return rc;
+  if ((rc = pass_locations(a))) return rc;
+  if ((rc = pass_labels_count(a, s2))) return rc;
+  if ((rc = pass_label_dicts(a, s2, fork ? a->d_partial2 : a->d_partial))) return rc;
+  if ((rc = pass_labels_emit(a, s2))) return rc;
+  if (fork) { CK(cudaEventRecord(a->ev_join, s2)); CK(cudaStreamWaitEvent(s, a->ev_join, 0)); }
+  return pass_finish(a);
+}
+
+static int check_batch_errors(pa_agg* a, uint32_t e) {
+  if (e & ERR_TABLE_FULL) return a->fail(PA_ENOMEM, "stack table overflow");
+  if (e & ERR_INDEX_OVERFLOW) return a->fail(PA_ERANGE, "location-index stream exceeds int32 (reporter/arrow_v2.go:233)");
+  if (e & ERR_BAD_FRAME_ID) return a->fail(PA_EINVAL, "sample refers to an unregistered frame id");
+  if (e & ERR_BAD_STRING_ID) return a->fail(PA_EINVAL, "sample refers to an unregistered string id");
+  if (e & ERR_BAD_LABELSET) return a->fail(PA_EINVAL, "sample refers to an unregistered labelset id");
+  if (e & ERR_BAD_KIND) return a->fail(PA_EINVAL, "sample kind out of range");
+  if (e & ERR_BAD_CPU) return a->fail(PA_EINVAL, "cpu id >= 65536");
+  if (e & ERR_BAD_FRAME_RANGE) return a->fail(PA_EINVAL, "sample frame range outside the staged frames (frame_off must ascend with the rows)");
+  if (e & ERR_SLICE_CAP) return a->fail(PA_ENOSPC, "merged batch: this shard's part of the location-index stream exceeds max_frames");
+  if (e & ERR_MERGE_LOOKUP) return a->fail(PA_EIO, "merged batch: a local stack is missing from the merged dictionary");
+  return PA_OK;
+}
+
+static void remember_sizes(pa_agg* a) {  // adaptive table sizing for the next interval
+  a->prev_unique = a->h_ctr.n_unique;
+  a->prev_tids = 0;
+  for (uint32_t c = 0; c < a->n_label_cols; c++) if (a->cols[c].type == COL_TID) a->prev_tids = a->h_ctr.n_dict[c];
+  a->retry_cap = 0;
+  a->retry_tcap = 0;
+}
+
 static int process(pa_agg* a) {
   if (a->staged < 0) return a->fail(PA_EINVAL, "nothing staged");
   CK(cudaSetDevice(a->device));
+  a->merged_part = false;
   if (a->N == 0) { a->processed = true; a->last_unique = 0; memset(&a->h_ctr, 0, sizeof a->h_ctr); return PA_OK; }
   int rc = upload_tables(a);
   if (rc) return rc;
@@ -888,15 +1084,7 @@ static int process(pa_agg* a) {
     a->retry_cap = a->table_cap * 4;  // unique-stack / thread-id estimate was too small: grow and redo the batch
     a->retry_tcap = a->tid_cap * 4;
   }
-  uint32_t e = a->h_ctr.err;
-  if (e & ERR_TABLE_FULL) return a->fail(PA_ENOMEM, "stack table overflow");
-  if (e & ERR_INDEX_OVERFLOW) return a->fail(PA_ERANGE, "location-index stream exceeds int32 (reporter/arrow_v2.go:233)");
-  if (e & ERR_BAD_FRAME_ID) return a->fail(PA_EINVAL, "sample refers to an unregistered frame id");
-  if (e & ERR_BAD_STRING_ID) return a->fail(PA_EINVAL, "sample refers to an unregistered string id");
-  if (e & ERR_BAD_LABELSET) return a->fail(PA_EINVAL, "sample refers to an unregistered labelset id");
-  if (e & ERR_BAD_KIND) return a->fail(PA_EINVAL, "sample kind out of range");
-  if (e & ERR_BAD_CPU) return a->fail(PA_EINVAL, "cpu id >= 65536");
-  if (e & ERR_BAD_FRAME_RANGE) return a->fail(PA_EINVAL, "sample frame range outside the staged frames (frame_off must ascend with the rows)");
+  if ((rc = check_batch_errors(a, a->h_ctr.err))) return rc;
   if (a->cfg.schema == PA_SCHEMA_V1) {
     if (a->h_ctr.store_overflow) {
       // the store is full: start a new generation (every older stack becomes "missing", as after an LRU eviction)
@@ -909,11 +1097,7 @@ static int process(pa_agg* a) {
     }
     a->last_unique = a->h_ctr.n_unique;
   }
-  a->prev_unique = a->h_ctr.n_unique;
-  a->prev_tids = 0;
-  for (uint32_t c = 0; c < a->n_label_cols; c++) if (a->cols[c].type == COL_TID) a->prev_tids = a->h_ctr.n_dict[c];
-  a->retry_cap = 0;
-  a->retry_tcap = 0;
+  remember_sizes(a);
   a->processed = true;
   return PA_OK;
 }
@@ -983,15 +1167,23 @@ static int d2h_vec(pa_agg* a, std::vector<uint32_t>& dst, const uint32_t* src, s
   return PA_OK;
 }
 
-static int collect(pa_agg* a, pa_agg_result* res) {
-  memset(res, 0, sizeof *res);
-  if (!a->processed) return a->fail(PA_EINVAL, "collect before process");
-  CK(cudaSetDevice(a->device));
-  const uint64_t N = a->N;
-  a->hostbufs.clear();
-  if (N == 0) { a->staged = -1; return PA_OK; }  // reference skips empty batches (:1775-1778)
-  double t0 = now_ms();
+// Buffers of a merged batch (mode B) that are spread over the shards: every shard holds the part that belongs to its rows /
+// its runs / its range of the location-index stream. The plan only needs their total length; merge_impl.hpp copies each
+// shard's part to (placement + part offset).
+enum SliceKind : uint32_t { SL_TS = 1, SL_VALUE, SL_UUID, SL_STOFF, SL_STSIZE, SL_STREAM, SL_RUN_ENDS, SL_RUN_KEYS, SL_VALID };
+static BufRef sliced(uint32_t kind, uint32_t col, uint64_t len) { return BufRef{BufRef::SLICED, (const void*)(uintptr_t)(((uint64_t)kind << 16) | col), len}; }
+struct MergeView {
+  uint64_t NT;                                            // rows of the merged batch
+  const std::vector<std::vector<uint32_t>>* kind_keys;    // run keys of the 8 kind-derived columns, all shards concatenated
+};
+
+// the record's columns as Nodes (device buffers are referenced, host-built ones are kept in a->hostbufs)
+static int collect_nodes(pa_agg* a, const MergeView* mv, std::vector<Node>& cols) {
+  const uint64_t N = mv ? mv->NT : a->N;
   const Counters& c = a->h_ctr;
+  auto rowbuf = [&](uint32_t kind, const void* p, uint64_t elem) { return mv ? sliced(kind, 0, N * elem) : BufRef::dev(p, N * elem); };
+  auto runbuf = [&](uint32_t kind, uint32_t col, const void* p, uint64_t n, uint64_t elem) { return mv ? sliced(kind, col, n * elem) : BufRef::dev(p, n * elem); };
+  auto validbuf = [&](uint32_t col, const void* p, uint64_t nr) { return mv ? sliced(SL_VALID, col, (nr + 7) / 8) : BufRef::dev(p, (nr + 7) / 8); };
   const uint32_t nlab = a->n_label_cols;
   const bool v1 = a->cfg.schema == PA_SCHEMA_V1;
   const Ty lab_ty = v1 ? Ty::Binary : Ty::Utf8;                 // v1 label dictionaries hold binary values (arrow.go:465-471)
@@ -1008,8 +1200,11 @@ static int collect(pa_agg* a, pa_agg_result* res) {
     return rc;
   for (uint32_t i = 0; i < nlab; i++)
     if (c.last_nonnull_plus1[i] && (rc = d2h_vec(a, ord_lab[i], a->cols[i].order, c.n_dict[i]))) return rc;
-  for (uint32_t t = v1 ? 6 : 0; t < 8; t++)  // v1: the six string columns stay on the device as dictionary indices
+  if (mv && v1) return a->fail(PA_EINVAL, "a merged batch needs PA_SCHEMA_V2 shards");
+  for (uint32_t t = v1 ? 6 : 0; t < 8; t++) {  // v1: the six string columns stay on the device as dictionary indices
+    if (mv) { kind_keys[t] = (*mv->kind_keys)[t]; continue; }
     if ((rc = d2h_vec(a, kind_keys[t], a->cols[nlab + t].run_keys, c.n_runs[nlab + t]))) return rc;
+  }
   std::vector<uint32_t> kind_order, n_kind_dict;
   if (v1 && ((rc = d2h_vec(a, kind_order, a->v1_kind_order, 64)) || (rc = d2h_vec(a, n_kind_dict, a->v1_n_kind_dict, 8)))) return rc;
   CK(cudaStreamSynchronize(a->s_comp));
@@ -1057,6 +1252,7 @@ static int collect(pa_agg* a, pa_agg_result* res) {
     for (auto& e : ext) is_ext |= e.first == cp.name;
     std::vector<std::string> decimals;
     auto strs = label_dict_strings(i, decimals);
+    if (is_ext && mv) return a->fail(PA_EINVAL, "merged batch: an external label may not share its name with a sample label");
     if (is_ext) {  // bring the column to the host; LabelAll is applied below
       HostCol hc;
       uint32_t nr = c.n_runs[i];
@@ -1080,8 +1276,8 @@ static int collect(pa_agg* a, pa_agg_result* res) {
     }
     Node dictv = utf8_node(a, "values", true, strs, nullptr, lab_ty);
     uint32_t nr = c.n_runs[i];
-    Node values = dict_node("values", true, nr, c.n_null[i], BufRef::dev(cp.validity, (nr + 7) / 8), BufRef::dev(cp.run_keys, (uint64_t)nr * 4), std::move(dictv));
-    labels.push_back(LabelOut{cp.name, ree_node(lab_prefix + cp.name, true, (int64_t)N, nr, BufRef::dev(cp.run_ends, (uint64_t)nr * 4), std::move(values))});
+    Node values = dict_node("values", true, nr, c.n_null[i], validbuf(i, cp.validity, nr), runbuf(SL_RUN_KEYS, i, cp.run_keys, nr, 4), std::move(dictv));
+    labels.push_back(LabelOut{cp.name, ree_node(lab_prefix + cp.name, true, (int64_t)N, nr, runbuf(SL_RUN_ENDS, i, cp.run_ends, nr, 4), std::move(values))});
   }
   for (auto& e : ext) {  // LabelAll (arrow_v2.go:555-564), in flag order
     HostCol& hc = touched[e.first];
@@ -1109,7 +1305,6 @@ static int collect(pa_agg* a, pa_agg_result* res) {
   }
   std::sort(labels.begin(), labels.end(), [](const LabelOut& x, const LabelOut& y) { return x.name < y.name; });
 
-  std::vector<Node> cols;
   auto ree_run_ends_of = [&](uint32_t col) { return BufRef::dev(a->cols[col].run_ends, (uint64_t)c.n_runs[col] * 4); };
   if (v1) {
     // ---- v1 sample record (reporter/arrow.go:274-316, ArrowSamplesField :484-503): label columns first, then the 11 fixed columns
@@ -1122,7 +1317,7 @@ static int collect(pa_agg* a, pa_agg_result* res) {
       cols.push_back(ree_node("stacktrace_id", false, (int64_t)N, nr, ree_run_ends_of(c_ord),
                               dict_node("values", true, nr, 0, BufRef::none(), BufRef::dev(a->cols[c_ord].run_keys, (uint64_t)nr * 4), std::move(ids))));
     }
-    cols.push_back(int_node("value", 64, true, false, (int64_t)N, BufRef::dev(a->d_value.p, N * 8)));
+    cols.push_back(int_node("value", 64, true, false, (int64_t)N, rowbuf(SL_VALUE, a->d_value.p, 8)));
     static const char* names[6] = {"producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality"};
     for (uint32_t t = 0; t < 6; t++) {
       std::vector<std::pair<const uint8_t*, uint32_t>> strs;
@@ -1214,21 +1409,21 @@ static int collect(pa_agg* a, pa_agg_result* res) {
     loc.kids.push_back(dict_node("mapping_build_id", true, n_loc, c.null_bid, BufRef::dev(a->sd_valid[2], (n_loc + 7) / 8), BufRef::dev(a->sd_keys[2], (uint64_t)n_loc * 4),
                                  utf8_node(a, "mapping_build_id", true, strs_of(ord_bid))));
     loc.kids.push_back(std::move(lines));
-    Node locd = dict_node("item", true, n_idx, 0, BufRef::none(), BufRef::dev(a->d_ustream.p, (uint64_t)n_idx * 4), std::move(loc));
+    Node locd = dict_node("item", true, n_idx, 0, BufRef::none(), mv ? sliced(SL_STREAM, 0, (uint64_t)n_idx * 4) : BufRef::dev(a->d_ustream.p, (uint64_t)n_idx * 4), std::move(loc));
     Node st; st.ty = Ty::ListView; st.name = "stacktrace"; st.nullable = true; st.length = (int64_t)N;
-    st.bufs = {BufRef::dev(a->d_stoff.p, N * 4), BufRef::dev(a->d_stsize.p, N * 4)};
+    st.bufs = {rowbuf(SL_STOFF, a->d_stoff.p, 4), rowbuf(SL_STSIZE, a->d_stsize.p, 4)};
     st.kids.push_back(std::move(locd));
     cols.push_back(std::move(st));
   }
   {
-    Node id; id.ty = Ty::FixedBinary; id.name = "stacktrace_id"; id.byte_width = 16; id.length = (int64_t)N; id.bufs = {BufRef::dev(a->d_uuid.p, N * 16)};
+    Node id; id.ty = Ty::FixedBinary; id.name = "stacktrace_id"; id.byte_width = 16; id.length = (int64_t)N; id.bufs = {rowbuf(SL_UUID, a->d_uuid.p, 16)};
     id.metadata = {{"ARROW:extension:name", "arrow.uuid"}, {"ARROW:extension:metadata", ""}};
     cols.push_back(std::move(id));
   }
-  cols.push_back(int_node("value", 64, true, false, (int64_t)N, BufRef::dev(a->d_value.p, N * 8)));
+  cols.push_back(int_node("value", 64, true, false, (int64_t)N, rowbuf(SL_VALUE, a->d_value.p, 8)));
   // constant-ish columns: values per run built from the class of each run
   static const char* fixed_names[6] = {"producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality"};
-  auto ree_run_ends = [&](uint32_t t) { return BufRef::dev(a->cols[nlab + t].run_ends, (uint64_t)c.n_runs[nlab + t] * 4); };
+  auto ree_run_ends = [&](uint32_t t) { return runbuf(SL_RUN_ENDS, nlab + t, a->cols[nlab + t].run_ends, c.n_runs[nlab + t], 4); };
   auto string_col = [&](uint32_t t) {
     const auto& keys = kind_keys[t];
     std::vector<std::pair<const uint8_t*, uint32_t>> strs;
@@ -1248,11 +1443,32 @@ static int collect(pa_agg* a, pa_agg_result* res) {
     cols.push_back(ree_node("duration", false, (int64_t)N, (int64_t)dv.size(), ree_run_ends(7), int_node("values", 64, false, true, (int64_t)dv.size(), host_ref(a, dv))));
   }
   {
-    Node ts; ts.ty = Ty::TimestampNsUtc; ts.name = "timestamp"; ts.length = (int64_t)N; ts.bufs = {BufRef::dev(a->d_ts.p, N * 8)};
+    Node ts; ts.ty = Ty::TimestampNsUtc; ts.name = "timestamp"; ts.length = (int64_t)N; ts.bufs = {rowbuf(SL_TS, a->d_ts.p, 8)};
     cols.push_back(std::move(ts));
   }
 
   }
+
+  return PA_OK;
+}
+
+static int collect(pa_agg* a, pa_agg_result* res) {
+  memset(res, 0, sizeof *res);
+  if (!a->processed) return a->fail(PA_EINVAL, "collect before process");
+  if (a->merged_part) return a->fail(PA_EINVAL, "this batch is one shard of a merged record: collect it through pa_merge_collect (or pa_agg_discard it)");
+  CK(cudaSetDevice(a->device));
+  const uint64_t N = a->N;
+  a->hostbufs.clear();
+  if (N == 0) { a->staged = -1; return PA_OK; }  // reference skips empty batches (:1775-1778)
+  double t0 = now_ms();
+  const Counters& c = a->h_ctr;
+  const bool v1 = a->cfg.schema == PA_SCHEMA_V1;
+  std::vector<Node> cols;
+  {
+    int rcn = collect_nodes(a, nullptr, cols);
+    if (rcn) return rcn;
+  }
+  const uint32_t n_loc = c.n_locations, n_fn = c.n_functions, n_idx = (uint32_t)c.n_indices64;
 
   // ---- plan the stream and fill it
   StreamPlan plan;
@@ -1337,7 +1553,7 @@ static int stacktraces(pa_agg* a, const uint8_t* ids, uint64_t n, pa_agg_result*
   const StoreSlot* st = a->d_store.as<StoreSlot>();
   const uint32_t smask = (uint32_t)(a->store_slots - 1);
   k_st_lookup<<<small_grid(a, n), kThreads, 0, s>>>(d_ids, n32, st, smask, q_slot, q_nloc);
-  launch_scan(a, StLocF{q_nloc, n32, loc_off, ctr}, 1, tm, small_grid(a, n));
+  launch_scan(a, StLocF{q_nloc, n32, loc_off, ctr}, 1, tm, small_grid(a, n), s, a->d_partial);
   tm.launches += 1;
   CK(cudaMemcpyAsync(a->h_ctr_pinned, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -1398,7 +1614,7 @@ static int stacktraces(pa_agg* a, const uint8_t* ids, uint64_t n, pa_agg_result*
                                                                                     complete_b, listv_b, ctr);
   k_pack_bits<<<small_grid(a, n), kThreads, 0, s>>>(complete_b, nullptr, n32, complete_w);
   k_pack_bits<<<small_grid(a, n), kThreads, 0, s>>>(listv_b, nullptr, n32, listv_w);
-  launch_scan(a, StLinesF{ctr, ctr, loc_fid, ft1, o, unknown_cid, missing_cid}, 1, tm, small_grid(a, L));
+  launch_scan(a, StLinesF{ctr, ctr, loc_fid, ft1, o, unknown_cid, missing_cid}, 1, tm, small_grid(a, L), s, a->d_partial);
   k_pack_bits<<<small_grid(a, L), kThreads, 0, s>>>(o.has_line, &ctr->n_locations, 0, hasline_w);
   StRunF rf{};
   rf.c[0] = StRunCol{o.type_key, &ctr->n_locations, run_key[0], run_end[0]};
@@ -1406,8 +1622,8 @@ static int stacktraces(pa_agg* a, const uint8_t* ids, uint64_t n, pa_agg_result*
   rf.c[2] = StRunCol{o.bid_key, &ctr->n_locations, run_key[2], run_end[2]};
   rf.c[3] = StRunCol{o.file_key, &ctr->n_lines, run_key[3], run_end[3]};
   rf.ctr_w = ctr;
-  launch_scan(a, rf, 4, tm, small_grid(a, L));
-  run_fo_jobs(a, a->d_jobs.as<FoJob>(), 0, 5, true, tm, Ln, S2);
+  launch_scan(a, rf, 4, tm, small_grid(a, L), s, a->d_partial);
+  run_fo_jobs(a, a->d_jobs.as<FoJob>(), 0, 5, true, tm, Ln, S2, true, s, a->d_partial);
   tm.launches += 4;
   CK(cudaMemcpyAsync(a->h_ctr_pinned, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(a->tm[T_TOTAL].b, s));
@@ -1628,6 +1844,7 @@ int pa_agg_discard(pa_agg* a) {
   CK(cudaStreamSynchronize(a->s_copy));
   CK(cudaStreamSynchronize(a->s_comp));
   a->staged = -1;
+  a->merged_part = false;
   return PA_OK;
 }
 int pa_agg_stage_device(pa_agg* a, const pa_sample_hdr* hdr, uint64_t n_rows, const uint64_t* frames, uint64_t n_frames) {
@@ -1743,7 +1960,7 @@ int pa_agg_debug_pair_counts(pa_agg* a, uint32_t* labelset_ids, uint32_t* stack_
     k_pair_count<<<a->G, kThreads, 0, s>>>((uint32_t)N, a->d_ls.as<uint32_t>(), a->d_slot.as<uint32_t>(), a->d_table.as<StackSlot>(), pt, (uint32_t)(slots - 1), flags);
     k_pair_bits<<<small_grid(a, slots), kThreads, 0, s>>>(pt, (uint32_t)slots, bits);
     Timer t{};
-    launch_scan(a, WordsF{bits, wp, (uint32_t)((N + 31) / 32), flags + 1}, 1, t, small_grid(a, N / 32 + 1));
+    launch_scan(a, WordsF{bits, wp, (uint32_t)((N + 31) / 32), flags + 1}, 1, t, small_grid(a, N / 32 + 1), s, a->d_partial);
     k_pair_emit<<<small_grid(a, slots), kThreads, 0, s>>>(pt, (uint32_t)slots, bits, wp, (uint32_t)ocap, o_ls, o_st, o_ct);
     uint32_t h[2] = {0, 0};
     CK(cudaMemcpyAsync(h, flags, 8, cudaMemcpyDeviceToHost, s));
@@ -1835,3 +2052,5 @@ uint64_t pa_xxh64(const void* data, uint64_t len, uint64_t seed) {
 }
 
 }  // extern "C"
+
+#include "merge_impl.hpp"

@@ -24,7 +24,7 @@
 namespace pa {
 
 struct BufRef {
-  enum Kind : uint8_t { NONE, HOST, DEVICE, ZEROS } kind = NONE;
+  enum Kind : uint8_t { NONE, HOST, DEVICE, ZEROS, SLICED /* spread over the shards of a merged batch; ptr is a tag */ } kind = NONE;
   const void* ptr = nullptr;
   uint64_t len = 0;
   static BufRef none() { return BufRef{}; }

@@ -15,11 +15,14 @@ namespace pa {
 constexpr uint32_t kNull = 0xFFFFFFFFu;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxCols = 48;  // label columns + 8 constant-ish REE columns
+constexpr int kMaxCols = 256;  // label columns + 8 constant-ish REE columns (+2 in v1); kernel-parameter tables are sized by it
+constexpr int kMaxWorld = 64;   // shards of one merged batch (mode B)
 
 enum : uint32_t {
   ERR_TABLE_FULL = 1u, ERR_BAD_FRAME_ID = 2u, ERR_BAD_STRING_ID = 4u, ERR_BAD_LABELSET = 8u,
   ERR_BAD_KIND = 16u, ERR_INDEX_OVERFLOW = 32u, ERR_BAD_CPU = 64u, ERR_BAD_FRAME_RANGE = 128u,
+  ERR_SLICE_CAP = 256u,   // mode B: this shard's slice of the location-index stream exceeds its buffer
+  ERR_MERGE_LOOKUP = 512u,  // mode B: a local stack is missing from the merged dictionary (internal error)
 };
 
 struct __align__(16) Key128 { unsigned long long hi, lo; };
@@ -104,9 +107,13 @@ __device__ __forceinline__ void block_range(uint32_t n, uint32_t* begin, uint32_
 // stack table: find-or-claim on the 128-bit stack id (StacktraceDictBuilderV2.index, arrow_v2.go:230)
 // Every slot is appended to `claimed` by the one thread whose CAS claimed it, so the ranking passes walk the
 // unique stacks (U entries) instead of scanning the whole table.
-__device__ __forceinline__ uint32_t stack_find_or_insert(StackSlot* tab, uint32_t mask, Key128 k, Counters* ctr, uint32_t* claimed) {
+// control words of one open-address stack table (the per-batch table lives in Counters; the mode-B owner / merged
+// tables carry their own)
+struct TabCtl { uint32_t* n_claimed; uint32_t* zero_claimed; uint32_t* err; };
+__device__ __forceinline__ TabCtl ctl_of(Counters* c) { return TabCtl{&c->n_claimed, &c->zero_claimed, &c->err}; }
+__device__ __forceinline__ uint32_t stack_find_or_insert(StackSlot* tab, uint32_t mask, Key128 k, TabCtl ctr, uint32_t* claimed) {
   if (key_zero(k)) {  // the all-zero id lives in a dedicated slot past the table
-    if (*(volatile uint32_t*)&ctr->zero_claimed == 0u && atomicExch(&ctr->zero_claimed, 1u) == 0u) claimed[atomicAdd(&ctr->n_claimed, 1u)] = mask + 1;
+    if (*(volatile uint32_t*)ctr.zero_claimed == 0u && atomicExch(ctr.zero_claimed, 1u) == 0u) claimed[atomicAdd(ctr.n_claimed, 1u)] = mask + 1;
     return mask + 1;
   }
   uint32_t idx = mix_slot(k) & mask;
@@ -114,11 +121,23 @@ __device__ __forceinline__ uint32_t stack_find_or_insert(StackSlot* tab, uint32_
   for (uint32_t probe = 0; probe <= mask; probe++) {
     Key128 cur = ld_key(&tab[idx].key);
     if (cur.hi == 0 || cur.lo == 0) cur = cas128(&tab[idx].key, zero, k);  // empty / possibly torn: CAS is authoritative
-    if (key_zero(cur)) { claimed[atomicAdd(&ctr->n_claimed, 1u)] = idx; return idx; }
+    if (key_zero(cur)) { claimed[atomicAdd(ctr.n_claimed, 1u)] = idx; return idx; }
     if (key_eq(cur, k)) return idx;
     idx = (idx + 1) & mask;
   }
-  atomicOr(&ctr->err, ERR_TABLE_FULL);
+  atomicOr(ctr.err, ERR_TABLE_FULL);
+  return kNull;
+}
+// read-only probe (the table is complete): slot of k, or kNull
+__device__ __forceinline__ uint32_t stack_find(const StackSlot* tab, uint32_t mask, Key128 k, uint32_t zero_present) {
+  if (key_zero(k)) return zero_present ? mask + 1 : kNull;
+  uint32_t idx = mix_slot(k) & mask;
+  for (uint32_t probe = 0; probe <= mask; probe++) {
+    Key128 cur = tab[idx].key;
+    if (key_eq(cur, k)) return idx;
+    if (key_zero(cur)) return kNull;
+    idx = (idx + 1) & mask;
+  }
   return kNull;
 }
 
@@ -139,7 +158,7 @@ __device__ __forceinline__ uint32_t warp_insert(StackSlot* tab, uint32_t mask, K
   bool own = valid && (lane == leader || !agree);  // tag collisions between different ids fall back to a private insert
   uint32_t idx = kNull;
   if (own) {
-    idx = stack_find_or_insert(tab, mask, k, ctr, claimed);
+    idx = stack_find_or_insert(tab, mask, k, ctl_of(ctr), claimed);
     if (idx != kNull) {
       uint32_t inv = 0xFFFFFFFFu - row;
       if (*(volatile uint32_t*)&tab[idx].first_inv < inv) atomicMax(&tab[idx].first_inv, inv);
@@ -182,6 +201,7 @@ __device__ __forceinline__ uint32_t hashed_min_insert(unsigned long long* hslots
 struct HeaderArgs {
   const uint4* hdr;            // 4 x uint4 per row
   uint32_t row0, row1;         // this chunk
+  uint32_t row_base;           // mode B: global row of local row 0 (dictionary memos record GLOBAL rows); 0 otherwise
   long long* timestamp;        // Arrow column
   long long* value;            // Arrow column
   uint8_t* uuid;               // Arrow column (16 B/row), written here in provided-hash mode
@@ -248,11 +268,12 @@ __global__ void __launch_bounds__(kThreads) k_header(HeaderArgs a) {
       a.tid[r] = tid;
       const uint32_t comm_cid = a.sid2cid[comm_sid];
       a.comm[r] = comm_cid;
-      if (a.first_ls && a.first_ls[ls] > r) atomicMin(&a.first_ls[ls], r);
-      if (a.first_cpu && a.first_cpu[cpu] > r) atomicMin(&a.first_cpu[cpu], r);
-      if (a.tid_slots && hashed_min_insert(a.tid_slots, a.tid_mask, tid, r) == kNull) atomicOr(&a.ctr->err, ERR_TABLE_FULL);
-      if (a.first_comm && comm_cid != 0 && a.first_comm[comm_cid] > r) atomicMin(&a.first_comm[comm_cid], r);
-      if (a.first_kind && a.first_kind[knd] > r) atomicMin(&a.first_kind[knd], r);
+      const uint32_t gr = a.row_base + r;
+      if (a.first_ls && a.first_ls[ls] > gr) atomicMin(&a.first_ls[ls], gr);
+      if (a.first_cpu && a.first_cpu[cpu] > gr) atomicMin(&a.first_cpu[cpu], gr);
+      if (a.tid_slots && hashed_min_insert(a.tid_slots, a.tid_mask, tid, gr) == kNull) atomicOr(&a.ctr->err, ERR_TABLE_FULL);
+      if (a.first_comm && comm_cid != 0 && a.first_comm[comm_cid] > gr) atomicMin(&a.first_comm[comm_cid], gr);
+      if (a.first_kind && a.first_kind[knd] > gr) atomicMin(&a.first_kind[knd], gr);
       if (a.provided) {  // trace.Hash.Bytes(): big-endian hi||lo
         ulonglong2 id = make_ulonglong2(bswap64(k.hi), bswap64(k.lo));
         *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = id;
@@ -428,17 +449,11 @@ __device__ __forceinline__ void wide_stripes(const unsigned long long* q, uint32
     for (int u = 0; u < 3; u++) if (s + u < ns) rounds(w[u]);
   }
 }
-__global__ void __launch_bounds__(kThreads, 4) k_hash_insert_wide(HashArgs a) {
+// one warp-tile of 32 consecutive rows (lane = row r); every lane of the warp must call it
+__device__ __forceinline__ void wide_tile(const HashArgs& a, uint32_t r, bool valid, uint32_t n_me, unsigned long long off_me) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, h = lane & 1, g = lane >> 1;  // h: which half of the stripe, g: sample within the sub-step
-  const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
-  const uint32_t span = a.row1 - a.row0;
-  const uint32_t iters = (span + nwarps * 32 - 1) / (nwarps * 32);
-  for (uint32_t it = 0; it < iters; it++) {
-    const uint32_t r = a.row0 + (it * nwarps + warp) * 32 + lane;
-    const bool valid = r < a.row1;
-    const uint32_t n_me = valid ? a.nframes[r] : 0u;
-    const unsigned long long off_me = valid ? a.frame_off[r] : 0ull;
+  {
     unsigned long long v0[4], v1[4];
 #pragma unroll
     for (int sub = 0; sub < 2; sub++) {
@@ -475,6 +490,143 @@ __global__ void __launch_bounds__(kThreads, 4) k_hash_insert_wide(HashArgs a) {
     if (valid) a.slot_of_row[r] = slot;
   }
 }
+__global__ void __launch_bounds__(kThreads, 4) k_hash_insert_wide(HashArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+  const uint32_t span = a.row1 - a.row0;
+  const uint32_t iters = (span + nwarps * 32 - 1) / (nwarps * 32);
+  for (uint32_t it = 0; it < iters; it++) {
+    const uint32_t r = a.row0 + (it * nwarps + warp) * 32 + lane;
+    const bool valid = r < a.row1;
+    const uint32_t n_me = valid ? a.nframes[r] : 0u;
+    const unsigned long long off_me = valid ? a.frame_off[r] : 0ull;
+    wide_tile(a, r, valid, n_me, off_me);
+  }
+}
+
+// Variant D ("bulk"): the north-star mechanism. Every lane issues ONE cp.async.bulk (TMA 1-D bulk copy, SASS UBLKCP) that
+// brings its own sample's frame ids — one contiguous run of <= 64 ids — into a padded shared-memory slot; the copies of a
+// warp's 32 samples complete on one mbarrier (32 arrivals + their byte counts). STAGES tiles per warp are in flight, so
+// global loads are outstanding ALL the time without holding a single register, and no per-stripe address arithmetic is
+// left in the instruction stream. Hashing is thread-per-sample straight out of shared memory: eight independent multiply
+// chains per thread (4 XXH64 accumulators x 2 seeds), no shuffles, no transpose; slots are 528 B apart, so the 32 lanes'
+// 8-byte reads fall into banks 4*lane + c (4 wavefronts per LDS.64, bank-conflict bound but far from the issue limit).
+// A tile with a stack deeper than one slot falls back to the direct-load tile code above.
+__device__ __forceinline__ unsigned long long lds64(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+constexpr int kBulkSlotBytes = 64 * 8 + 16;              // 64 ids + 8 B alignment skew + 8 B round-up to a 16-byte multiple
+constexpr int kBulkStageBytes = 32 * kBulkSlotBytes;     // one warp-tile
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+template <int WARPS, int STAGES>
+struct BulkSmem {
+  alignas(128) uint8_t data[WARPS][STAGES][kBulkStageBytes];
+  alignas(8) unsigned long long bar[WARPS][STAGES];
+  uint32_t meta[WARPS][STAGES][32];  // per sample: nframes | skew << 16 | in-slot flag << 31
+};
+template <int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_hash_insert_bulk(HashArgs a) {
+  extern __shared__ __align__(128) uint8_t bulk_smem_raw[];
+  BulkSmem<WARPS, STAGES>& sm = *reinterpret_cast<BulkSmem<WARPS, STAGES>*>(bulk_smem_raw);
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * WARPS + wib, nwarps = gridDim.x * WARPS;
+  const uint32_t span = a.row1 - a.row0;
+  const uint32_t tiles = (span + 31) / 32;
+  if (lane == 0)
+    for (int st = 0; st < STAGES; st++) mbar_init(smem_u32(&sm.bar[wib][st]), 32);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  // issue the copies of tile `t` (if any) into stage `st`
+  auto issue = [&](uint32_t t, int st) {
+    if (t >= tiles) return;  // warp-uniform
+    const uint32_t r = a.row0 + t * 32 + lane;
+    const bool valid = r < a.row1;
+    const uint32_t n = valid ? a.nframes[r] : 0u;
+    const unsigned long long off = valid ? a.frame_off[r] : 0ull;
+    const bool fits = __all_sync(full, n <= 64u);
+    const uint32_t bar = smem_u32(&sm.bar[wib][st]);
+    const uint32_t skew = (uint32_t)(off & 1ull);
+    sm.meta[wib][st][lane] = n | (skew << 16) | (fits ? 0x80000000u : 0u);
+    if (fits && n) {
+      const uint32_t bytes = ((skew + n + 1u) & ~1u) * 8u;  // [off - skew, off + n) rounded up to a multiple of 16 bytes
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_g2s(smem_u32(&sm.data[wib][st][lane * kBulkSlotBytes]), a.frames + (off - skew), bytes, bar);
+    } else {
+      mbar_arrive(bar);
+    }
+  };
+  uint32_t my_tiles = tiles > warp ? (tiles - warp + nwarps - 1) / nwarps : 0u;
+#pragma unroll
+  for (int st = 0; st < STAGES - 1; st++) issue(warp + (uint32_t)st * nwarps, st);
+  uint32_t phase_bits = 0;  // parity of each stage's barrier
+  for (uint32_t k = 0; k < my_tiles; k++) {
+    const int st = (int)(k % STAGES);
+    // keep STAGES-1 tiles in flight: refill the stage consumed in the previous iteration
+    issue(warp + (k + STAGES - 1) * nwarps, (int)((k + STAGES - 1) % STAGES));
+    const uint32_t t = warp + k * nwarps;
+    const uint32_t r = a.row0 + t * 32 + lane;
+    const bool valid = r < a.row1;
+    mbar_wait(smem_u32(&sm.bar[wib][st]), (phase_bits >> st) & 1u);
+    phase_bits ^= 1u << st;
+    const uint32_t m = sm.meta[wib][st][lane];
+    const uint32_t n_me = m & 0xFFFFu;
+    if (!(m & 0x80000000u)) {  // warp-uniform: a stack deeper than one slot somewhere in the tile
+      wide_tile(a, r, valid, n_me, valid ? a.frame_off[r] : 0ull);
+      __syncwarp(full);
+      continue;
+    }
+    const uint32_t base = smem_u32(&sm.data[wib][st][lane * kBulkSlotBytes]) + ((m >> 16) & 1u) * 8u;
+    unsigned long long v0[4], v1[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { v0[j] = xxh_lane_init(0ull, j); v1[j] = xxh_lane_init(kSeedLo, j); }
+    const uint32_t ns = n_me >> 2;
+    uint32_t sx = 0;
+    for (; sx + 2 <= ns; sx += 2) {  // two stripes per step: 8 loads issued before their 24 multiplies
+      unsigned long long w[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) w[u] = lds64(base + 32u * sx + 8u * u);
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const unsigned long long mm = w[u] * XP2;
+        v0[u & 3] = xxh_round_pre(v0[u & 3], mm);
+        v1[u & 3] = xxh_round_pre(v1[u & 3], mm);
+      }
+    }
+    if (sx < ns) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const unsigned long long mm = lds64(base + 32u * sx + 8u * u) * XP2;
+        v0[u] = xxh_round_pre(v0[u], mm);
+        v1[u] = xxh_round_pre(v1[u], mm);
+      }
+    }
+    const uint32_t nt = n_me & 3u, tb = base + 8u * (n_me & ~3u);
+    const unsigned long long t0 = nt > 0 ? lds64(tb) : 0ull, t1 = nt > 1 ? lds64(tb + 8) : 0ull, t2 = nt > 2 ? lds64(tb + 16) : 0ull;
+    __syncwarp(full);  // every lane is done with this stage before the next iteration's refill
+    Key128 key;
+    key.hi = xxh_finish_own(v0, 0ull, n_me, t0, t1, t2);
+    key.lo = xxh_finish_own(v1, kSeedLo, n_me, t0, t1, t2);
+    if (valid) *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = make_ulonglong2(bswap64(key.hi), bswap64(key.lo));
+    const uint32_t slot = warp_insert(a.tab, a.mask, key, r, valid, a.ctr, a.claimed);
+    if (valid) a.slot_of_row[r] = slot;
+  }
+}
 
 // Variant C: same arithmetic and epilogue as k_hash_insert, but the frame ids reach the XXH64 lanes
 // through shared memory: every warp owns a two-stage ring (8 samples x 544 B per stage) that it fills
@@ -495,11 +647,6 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ unsigned long long lds64(uint32_t addr) {
-  unsigned long long v;
-  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
-  return v;
-}
 // stage the 8 samples owned by lanes sub*8 .. sub*8+7 (n <= 64 frames each) into `stage`
 __device__ __forceinline__ void stage_samples(const unsigned long long* frames, uint32_t n_me, unsigned long long off_me, int sub, uint32_t stage,
                                               int lane) {
@@ -691,8 +838,8 @@ __global__ void __launch_bounds__(kThreads) k_scan_emit(F f, const typename F::T
 // (1) unique stacks in first-occurrence order. The table holds each stack's first row; ordinals
 // come from a bitmap over rows (one bit per first occurrence) + a popcount prefix over its words,
 // so only table-sized and N/32-sized passes are needed (no scan over all rows).
-__global__ void __launch_bounds__(kThreads) k_stack_bits(const StackSlot* tab, const uint32_t* claimed, const Counters* ctr, uint32_t* rowbits) {
-  const uint32_t n = ctr->n_claimed;
+__global__ void __launch_bounds__(kThreads) k_stack_bits(const StackSlot* tab, const uint32_t* claimed, const uint32_t* n_claimed, uint32_t* rowbits) {
+  const uint32_t n = *n_claimed;
   for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     uint32_t f = 0xFFFFFFFFu - tab[claimed[i]].first_inv;
     atomicOr(&rowbits[f >> 5], 1u << (f & 31));
@@ -709,10 +856,11 @@ struct WordsF {  // exclusive popcount prefix over bitmap words
   __device__ void emit(uint32_t i, uint32_t ex, uint32_t) const { wprefix[i] = ex; }
   __device__ void total(int, uint32_t t) const { *total_out = t; }
 };
-__global__ void __launch_bounds__(kThreads) k_stack_assign(StackSlot* tab, const uint32_t* claimed, const Counters* ctr, const uint32_t* rowbits,
+// nframes == nullptr (mode B, merged table): the slot already carries the size of the stack's first occurrence
+__global__ void __launch_bounds__(kThreads) k_stack_assign(StackSlot* tab, const uint32_t* claimed, const uint32_t* n_claimed, const uint32_t* rowbits,
                                                            const uint32_t* wprefix, const uint16_t* nframes, uint32_t* uniq_row, uint32_t* uniq_slot,
                                                            uint32_t* uniq_size) {
-  const uint32_t n = ctr->n_claimed;
+  const uint32_t n = *n_claimed;
   for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     uint32_t sidx = claimed[i];
     uint32_t f = 0xFFFFFFFFu - tab[sidx].first_inv;
@@ -720,7 +868,7 @@ __global__ void __launch_bounds__(kThreads) k_stack_assign(StackSlot* tab, const
     uniq_row[ord] = f;
     tab[sidx].ordinal = ord;
     uniq_slot[ord] = sidx;
-    uniq_size[ord] = nframes[f];
+    uniq_size[ord] = nframes ? (uint32_t)nframes[f] : tab[sidx].size;
   }
 }
 struct UniqOffsetF {  // startOffset := indices.Len() at each first occurrence (arrow_v2.go:302)
@@ -853,6 +1001,7 @@ __global__ void __launch_bounds__(kThreads) k_gather_unique(const Counters* ctr,
 struct FoJob {
   const uint32_t* keys;
   const uint32_t* n_ptr;   // element count lives on the device (nullptr: use n_imm)
+  const uint32_t* n_map_ptr;  // mode B: elements THIS shard maps (its slice of the stream); nullptr = the same count
   uint32_t n_imm;
   uint32_t* first;         // direct: [universe] first position (memset 0xFF)
   unsigned long long* hslots;  // hashed: (key<<32 | first position), memset 0xFF
@@ -921,7 +1070,7 @@ __device__ __forceinline__ void fo_assign_dev(const FoJob& j) {
 // keep enough loads in flight.
 __device__ __forceinline__ void fo_map_dev(const FoJob& j) {
   if (!j.out) return;
-  uint32_t n = j.n_ptr ? *j.n_ptr : j.n_imm, begin, end;
+  uint32_t n = j.n_map_ptr ? *j.n_map_ptr : (j.n_ptr ? *j.n_ptr : j.n_imm), begin, end;
   block_range(n, &begin, &end);
   uint32_t nulls = 0;
   for (uint32_t tile = begin; tile < end; tile += 4 * kThreads) {
@@ -1069,6 +1218,20 @@ struct ReeArgs {
   int c_ord, c_ts;
   const uint32_t* kindrank;  // [6][8] class -> dictionary index of the kind-derived string columns
   uint32_t kind_dict_mask;   // bit t: kind column t is dictionary encoded
+  // mode B (one merged batch over several shards): this shard's rows are the global rows row_base .. row_base+n_rows-1
+  uint32_t row_base;         // added to every run end
+  uint32_t* edge_keys;       // [ncols][4] = first key, first null, last key, last null of this shard (count pass); nullptr = off
+  const struct MergeCol* mc; // per column: how many local runs stay in this shard's part + validity bit shift (emit pass); nullptr = off
+};
+struct EdgeCol {   // what one shard contributes to the cross-shard run merge of one REE column
+  uint32_t n_runs, n_null, lastnn, n_rows;
+  uint32_t first_key, first_null, last_key, last_null;
+};
+struct MergeCol {
+  uint32_t keep;       // local runs that stay in this shard's part: n_runs, or n_runs-1 when its last run continues in the next shard
+  uint32_t vshift;     // (global index of this shard's first run) mod 32: validity bits are written at their global bit position
+  uint32_t runbase;    // global index of this shard's first run
+  uint32_t pad;
 };
 __device__ __forceinline__ void warp_range(uint32_t n, uint32_t* begin, uint32_t* end, uint32_t* wg) {
   uint32_t nw = gridDim.x * kWarps;
@@ -1091,7 +1254,7 @@ struct ReeGroups { uint32_t n; ReeGroup g[kMaxCols]; };
 
 constexpr int kReeUnroll = 4;  // 32-row sub-steps per iteration: their key loads / rank lookups are in flight together
 
-template <bool EMIT, class KeyT, class K>
+template <bool EMIT, bool MERGED, class KeyT, class K>
 __device__ __forceinline__ void ree_single(const ReeArgs& a, uint32_t c, bool has_dict, K kf) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
@@ -1100,6 +1263,7 @@ __device__ __forceinline__ void ree_single(const ReeArgs& a, uint32_t c, bool ha
   const uint32_t nwarps = gridDim.x * kWarps;
   const ReeCol col = a.cols[c];
   uint32_t acc = EMIT ? a.partial[c * nwarps + wg] : 0u, last = 0, nulls = 0;
+  const uint32_t keep = (EMIT && MERGED) ? a.mc[c].keep : 0xFFFFFFFFu, vshift = (EMIT && MERGED) ? a.mc[c].vshift : 0u;  // single aggregator: folded away
   KeyT ckey = 0; bool cnull = true;                 // previous row of lane 0
   if (begin < end && begin > 0) kf.get(begin - 1, ckey, cnull);
   const unsigned lt = (1u << lane) - 1u;
@@ -1111,6 +1275,10 @@ __device__ __forceinline__ void ree_single(const ReeArgs& a, uint32_t c, bool ha
       const uint32_t r = base + u * 32 + lane;
       in[u] = r < end; key[u] = 0; null[u] = true;
       if (in[u]) kf.get(r, key[u], null[u]);
+      if (!EMIT && MERGED && in[u]) {
+        if (r == 0) { a.edge_keys[c * 4 + 0] = (uint32_t)key[u]; a.edge_keys[c * 4 + 1] = null[u] ? 1u : 0u; }
+        if (r + 1 == a.n_rows) { a.edge_keys[c * 4 + 2] = (uint32_t)key[u]; a.edge_keys[c * 4 + 3] = null[u] ? 1u : 0u; }
+      }
     }
 #pragma unroll
     for (int u = 0; u < kReeUnroll; u++) {
@@ -1142,19 +1310,19 @@ __device__ __forceinline__ void ree_single(const ReeArgs& a, uint32_t c, bool ha
 #pragma unroll
       for (int u = 0; u < kReeUnroll; u++) {
         if (bnd[u]) {
-          if (k[u] > 0) col.run_ends[k[u] - 1] = (int)(base + u * 32 + lane);  // run k starts here => run k-1 ends here
-          if (sizeof(KeyT) == 8) a.ts_vals[k[u]] = (long long)key[u]; else col.run_keys[k[u]] = stored[u];
+          if (k[u] > 0) col.run_ends[k[u] - 1] = (int)((MERGED ? a.row_base : 0u) + base + u * 32 + lane);  // run k starts here => run k-1 ends here
+          if (!MERGED || k[u] < keep) { if (sizeof(KeyT) == 8) a.ts_vals[k[u]] = (long long)key[u]; else col.run_keys[k[u]] = stored[u]; }
         }
       }
       if (col.validity && col.nullable) {  // validity bits of the runs emitted by one sub-step span at most two words
-        uint32_t pos = acc;
+        uint32_t pos = acc + vshift;
 #pragma unroll
         for (int u = 0; u < kReeUnroll; u++) {
           if (m[u]) {
-            const uint32_t w0 = pos >> 5;
-            const bool v = bnd[u] && !null[u];
-            unsigned m0 = __reduce_or_sync(full, (v && (k[u] >> 5) == w0) ? (1u << (k[u] & 31)) : 0u);
-            unsigned m1 = __reduce_or_sync(full, (v && (k[u] >> 5) != w0) ? (1u << (k[u] & 31)) : 0u);
+            const uint32_t w0 = pos >> 5, kb = k[u] + vshift;
+            const bool v = bnd[u] && !null[u] && (!MERGED || k[u] < keep);
+            unsigned m0 = __reduce_or_sync(full, (v && (kb >> 5) == w0) ? (1u << (kb & 31)) : 0u);
+            unsigned m1 = __reduce_or_sync(full, (v && (kb >> 5) != w0) ? (1u << (kb & 31)) : 0u);
             if (lane == 0) { if (m0) atomicOr(&col.validity[w0], m0); if (m1) atomicOr(&col.validity[w0 + 1], m1); }
           }
           pos += (uint32_t)__popc(m[u]);
@@ -1179,7 +1347,7 @@ struct KeyTs { const long long* v;
   __device__ __forceinline__ void get(uint32_t r, long long& k, bool& n) const { k = v[r]; n = false; } };
 
 // the 8 kind-derived columns: one warp, eight running positions in registers, one skip test per step
-template <bool EMIT>
+template <bool EMIT, bool MERGED>
 __device__ __forceinline__ void ree_kinds(const ReeArgs& a, const uint32_t* s_kind, const uint32_t* s_krank) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
@@ -1201,6 +1369,14 @@ __device__ __forceinline__ void ree_kinds(const ReeArgs& a, const uint32_t* s_ki
     uint32_t pkind = __shfl_up_sync(full, kind, 1);
     if (lane == 0) pkind = ckind;
     const bool first_row = r == 0;
+    if (!EMIT && MERGED && in && (first_row || r + 1 == a.n_rows)) {
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        const uint32_t v = s_kind[t * 8 + kind];
+        if (first_row) { a.edge_keys[(a.c_kind + t) * 4 + 0] = v; a.edge_keys[(a.c_kind + t) * 4 + 1] = v == kNull ? 1u : 0u; }
+        if (r + 1 == a.n_rows) { a.edge_keys[(a.c_kind + t) * 4 + 2] = v; a.edge_keys[(a.c_kind + t) * 4 + 3] = v == kNull ? 1u : 0u; }
+      }
+    }
     const bool kchange = in && (first_row || kind != pkind || kind >= 3u);  // kinds >= 3 carry a null temporality
     if (__ballot_sync(full, kchange)) {
 #pragma unroll
@@ -1215,16 +1391,17 @@ __device__ __forceinline__ void ree_kinds(const ReeArgs& a, const uint32_t* s_ki
         } else if (m) {
           const ReeCol& col = a.cols[a.c_kind + t];
           const uint32_t k = acc[t] + (uint32_t)__popc(m & lt);
+          const uint32_t keep = MERGED ? a.mc[a.c_kind + t].keep : 0xFFFFFFFFu, vshift = MERGED ? a.mc[a.c_kind + t].vshift : 0u;
           if ((a.kind_dict_mask >> t) & 1u) v = null ? 0u : s_krank[t * 8 + v];  // v1: dictionary index of the class
           if (boundary) {
-            if (k > 0) col.run_ends[k - 1] = (int)r;
-            col.run_keys[k] = v;
+            if (k > 0) col.run_ends[k - 1] = (int)((MERGED ? a.row_base : 0u) + r);
+            if (!MERGED || k < keep) col.run_keys[k] = v;
           }
           if (col.validity && col.nullable) {
-            const uint32_t w0 = acc[t] >> 5;
-            const bool ok = boundary && !null;
-            unsigned m0 = __reduce_or_sync(full, (ok && (k >> 5) == w0) ? (1u << (k & 31)) : 0u);
-            unsigned m1 = __reduce_or_sync(full, (ok && (k >> 5) != w0) ? (1u << (k & 31)) : 0u);
+            const uint32_t w0 = (acc[t] + vshift) >> 5, kb = k + vshift;
+            const bool ok = boundary && !null && (!MERGED || k < keep);
+            unsigned m0 = __reduce_or_sync(full, (ok && (kb >> 5) == w0) ? (1u << (kb & 31)) : 0u);
+            unsigned m1 = __reduce_or_sync(full, (ok && (kb >> 5) != w0) ? (1u << (kb & 31)) : 0u);
             if (lane == 0) { if (m0) atomicOr(&col.validity[w0], m0); if (m1) atomicOr(&col.validity[w0 + 1], m1); }
           }
           acc[t] += (uint32_t)__popc(m);
@@ -1242,23 +1419,23 @@ __device__ __forceinline__ void ree_kinds(const ReeArgs& a, const uint32_t* s_ki
   }
 }
 
-template <bool EMIT>
+template <bool EMIT, bool MERGED>
 __global__ void __launch_bounds__(kThreads) k_ree_col(ReeArgs a, ReeGroups groups) {
   __shared__ uint32_t s_kind[64], s_krank[64];
   const ReeGroup g = groups.g[blockIdx.y];
   if (g.type == COL_KIND) {
     if (threadIdx.x < 64) { s_kind[threadIdx.x] = a.kindtab[threadIdx.x]; s_krank[threadIdx.x] = (EMIT && a.kindrank && threadIdx.x < 48) ? a.kindrank[threadIdx.x] : 0u; }
     __syncthreads();
-    ree_kinds<EMIT>(a, s_kind, s_krank);
+    ree_kinds<EMIT, MERGED>(a, s_kind, s_krank);
     return;
   }
   switch (g.type) {
-    case COL_LS: ree_single<EMIT, uint32_t>(a, g.col, true, KeyLs{a.ls, a.lsmat, a.n_lscols, g.param}); break;
-    case COL_CPU: ree_single<EMIT, uint32_t>(a, g.col, true, KeyU32{a.cpu}); break;
-    case COL_TID: ree_single<EMIT, uint32_t>(a, g.col, true, KeyU32{a.tid}); break;
-    case COL_COMM: ree_single<EMIT, uint32_t>(a, g.col, true, KeyComm{a.comm}); break;
-    case COL_ORD: ree_single<EMIT, uint32_t>(a, g.col, false, KeyU32{a.ord}); break;  // bytes.Equal on the 16-byte id
-    default: ree_single<EMIT, long long>(a, g.col, false, KeyTs{a.ts}); break;           // COL_TS: Int64RunEndBuilder.Append
+    case COL_LS: ree_single<EMIT, MERGED, uint32_t>(a, g.col, true, KeyLs{a.ls, a.lsmat, a.n_lscols, g.param}); break;
+    case COL_CPU: ree_single<EMIT, MERGED, uint32_t>(a, g.col, true, KeyU32{a.cpu}); break;
+    case COL_TID: ree_single<EMIT, MERGED, uint32_t>(a, g.col, true, KeyU32{a.tid}); break;
+    case COL_COMM: ree_single<EMIT, MERGED, uint32_t>(a, g.col, true, KeyComm{a.comm}); break;
+    case COL_ORD: ree_single<EMIT, MERGED, uint32_t>(a, g.col, false, KeyU32{a.ord}); break;  // bytes.Equal on the 16-byte id
+    default: ree_single<EMIT, MERGED, long long>(a, g.col, false, KeyTs{a.ts}); break;           // COL_TS: Int64RunEndBuilder.Append
   }
 }
 __global__ void __launch_bounds__(kThreads) k_ree_scan_partials(ReeArgs a, int g) {  // grid = ncols, kThreads threads
@@ -1273,7 +1450,7 @@ __global__ void __launch_bounds__(kThreads) k_ree_scan_partials(ReeArgs a, int g
   }
   if (threadIdx.x == 0) {
     a.ctr->n_runs[blockIdx.x] = run;
-    if (run) a.cols[blockIdx.x].run_ends[run - 1] = (int)a.n_rows;  // the last run ends at the row count
+    if (run) a.cols[blockIdx.x].run_ends[run - 1] = (int)(a.row_base + a.n_rows);  // the last run ends at the (shard's last global) row count
   }
 }
 
@@ -1622,6 +1799,180 @@ __global__ void __launch_bounds__(kThreads) k_scatter_rows(const uint4* src, con
     unsigned long long g = global_row[t >> 2];
     if (g >= n_total) { *bad = 1u; continue; }
     dst[g * 4ull + (t & 3ull)] = __ldg(src + t);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU mode B, dictionary merge (the "slices" form): the merged batch is the reference's record for
+// the stream [shard 0's rows, shard 1's rows, ...], i.e. shard m's local row r is global row row_base_m + r. Rows never
+// leave their shard. What is exchanged is O(unique keys):
+//   stacks    : every shard sends (id, global first row, depth) of its unique stacks to the id's owner shard
+//               (hash of the id mod G: one all-to-all), owners keep the minimum row, the owners' lists are all-gathered
+//               and every shard ranks the merged list the usual way (first-row bitmap -> popcount prefix);
+//   locations : first positions in the merged unique-stack frame stream, one all-reduce(min) over the frame-indexed table;
+//   labels    : all-reduce(min) over the direct first-row tables, all-gather of the thread-id lists;
+//   run ends  : per column (run count, first/last key) of every shard, all-gathered; neighbouring runs merge at shard edges.
+// Because global rows ascend with the shard index, the stacks whose first occurrence is in shard m occupy one contiguous
+// range of ordinals, hence one contiguous range of the location-index stream: shard m gathers exactly that range.
+struct __align__(8) StackEntry { unsigned long long hi, lo; uint32_t row, size; };  // 24 B on the wire
+
+__device__ __forceinline__ uint32_t owner_of(Key128 k, uint32_t world) {
+  unsigned long long x = k.hi ^ rotl64(k.lo, 23);
+  x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+  return (uint32_t)(x % world);
+}
+struct OwnerOffsets { uint32_t off[kMaxWorld + 1]; };
+// pass 1: entries per owner
+__global__ void __launch_bounds__(kThreads) k_owner_count(const StackSlot* tab, const uint32_t* claimed, const uint32_t* n_claimed, uint32_t world, uint32_t* cnt) {
+  __shared__ uint32_t s_cnt[kMaxWorld];
+  if (threadIdx.x < kMaxWorld) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t n = *n_claimed;
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) atomicAdd(&s_cnt[owner_of(tab[claimed[i]].key, world)], 1u);
+  __syncthreads();
+  if (threadIdx.x < world && s_cnt[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], s_cnt[threadIdx.x]);
+}
+// pass 2: (id, global first row, depth of that first occurrence), bucketed by owner (order inside a bucket is irrelevant)
+__global__ void __launch_bounds__(kThreads) k_owner_pack(const StackSlot* tab, const uint32_t* claimed, const uint32_t* n_claimed, uint32_t world,
+                                                         OwnerOffsets offs, uint32_t* cursor, uint32_t row_base, const uint16_t* nframes, StackEntry* out) {
+  const uint32_t n = *n_claimed;
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const StackSlot e = tab[claimed[i]];
+    const uint32_t f = 0xFFFFFFFFu - e.first_inv, o = owner_of(e.key, world);
+    out[offs.off[o] + atomicAdd(&cursor[o], 1u)] = StackEntry{e.key.hi, e.key.lo, row_base + f, (uint32_t)nframes[f]};
+  }
+}
+// owner / merged table insert: keeps, per id, the entry with the smallest global row (its depth rides along: both live in
+// one 64-bit word, inverted row in the high half, so a single atomicMax decides)
+__device__ __forceinline__ unsigned long long* slot_minpack(StackSlot* e) { return reinterpret_cast<unsigned long long*>(&e->first_inv); }
+__global__ void __launch_bounds__(kThreads) k_entries_insert(const StackEntry* in, uint32_t n, StackSlot* tab, uint32_t mask, uint32_t* ctl /*n_claimed, zero_claimed, err*/,
+                                                             uint32_t* claimed) {
+  const TabCtl tc{ctl, ctl + 1, ctl + 2};
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const StackEntry en = in[i];
+    const uint32_t idx = stack_find_or_insert(tab, mask, Key128{en.hi, en.lo}, tc, claimed);
+    if (idx == kNull) continue;
+    const unsigned long long pack = ((unsigned long long)(0xFFFFFFFFu - en.row) << 32) | en.size;
+    unsigned long long* mp = slot_minpack(&tab[idx]);
+    if (*(volatile unsigned long long*)mp < pack) atomicMax(mp, pack);
+  }
+}
+// owner table -> list of its (deduplicated) entries
+__global__ void __launch_bounds__(kThreads) k_entries_compact(const StackSlot* tab, const uint32_t* claimed, const uint32_t* n_claimed, StackEntry* out) {
+  const uint32_t n = *n_claimed;
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    StackSlot e = tab[claimed[i]];
+    const unsigned long long pack = *slot_minpack(&e);
+    out[i] = StackEntry{e.key.hi, e.key.lo, 0xFFFFFFFFu - (uint32_t)(pack >> 32), (uint32_t)pack};
+  }
+}
+// merged table: minpack -> the regular slot fields (first_inv = inverted global first row, size) so that the ranking kernels
+// (k_stack_bits / k_stack_assign / UniqOffsetF) run on it unchanged
+__global__ void __launch_bounds__(kThreads) k_merged_unpack(StackSlot* tab, const uint32_t* claimed, const uint32_t* n_claimed) {
+  const uint32_t n = *n_claimed;
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    StackSlot* e = &tab[claimed[i]];
+    const unsigned long long pack = *slot_minpack(e);
+    e->first_inv = (uint32_t)(pack >> 32);
+    e->ordinal = 0;
+    e->size = (uint32_t)pack;
+  }
+}
+// every local unique stack takes (ordinal, offset, size) of the merged dictionary
+__global__ void __launch_bounds__(kThreads) k_local_adopt(StackSlot* ltab, const uint32_t* lclaimed, const uint32_t* n_lclaimed, const StackSlot* gtab, uint32_t gmask,
+                                                          const uint32_t* gctl, uint32_t* err) {
+  const uint32_t n = *n_lclaimed, zero_present = gctl[1];
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    StackSlot* e = &ltab[lclaimed[i]];
+    const uint32_t g = stack_find(gtab, gmask, e->key, zero_present);
+    if (g == kNull) { atomicOr(err, ERR_MERGE_LOOKUP); continue; }
+    e->ordinal = gtab[g].ordinal; e->offset = gtab[g].offset; e->size = gtab[g].size;
+  }
+}
+// which ordinals (a contiguous range, see above) have their first occurrence in this shard, and the stream range they cover
+struct MergeCtl { uint32_t ord0, ord1, off0, slice_len; uint32_t n_tids, pad[3]; };
+__global__ void k_won_range(const uint32_t* uniq_row, const uint32_t* uniq_slot, const StackSlot* gtab, const Counters* ctr, uint32_t row_base, uint32_t n_rows,
+                            uint32_t ustream_cap, MergeCtl* mc, Counters* ctr_w) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const uint32_t nu = ctr->n_unique;
+  auto lower = [&](unsigned long long row) { uint32_t lo = 0, hi = nu; while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (uniq_row[mid] < row) lo = mid + 1; else hi = mid; } return lo; };
+  const uint32_t o0 = lower(row_base), o1 = lower((unsigned long long)row_base + n_rows);
+  const unsigned long long total = ctr->n_indices64;
+  const unsigned long long f0 = o0 < nu ? gtab[uniq_slot[o0]].offset : total, f1 = o1 < nu ? gtab[uniq_slot[o1]].offset : total;
+  mc->ord0 = o0; mc->ord1 = o1; mc->off0 = (uint32_t)f0; mc->slice_len = (uint32_t)(f1 - f0);
+  if (f1 - f0 > ustream_cap) { atomicOr(&ctr_w->err, ERR_SLICE_CAP); mc->slice_len = 0; mc->ord1 = o0; }
+}
+// this shard's range of the merged unique-stack frame stream (frame ids; mapped to location indices in place later) and the
+// first GLOBAL position of every frame it contains
+__global__ void __launch_bounds__(kThreads) k_gather_won(const MergeCtl* mc, const uint32_t* uniq_row, const uint32_t* uniq_slot, const StackSlot* gtab, uint32_t row_base,
+                                                         const unsigned long long* frames, const unsigned long long* frame_off, uint32_t n_frames_registered,
+                                                         uint32_t* ustream, uint32_t* loc_first, Counters* ctr_w) {
+  const uint32_t o0 = mc->ord0, o1 = mc->ord1, off0 = mc->off0;
+  int lane = threadIdx.x & 31;
+  uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+  for (uint32_t u = o0 + warp; u < o1; u += nwarps) {
+    const uint32_t r = uniq_row[u] - row_base;
+    const StackSlot e = gtab[uniq_slot[u]];
+    const unsigned long long* src = frames + frame_off[r];
+    for (uint32_t jx = lane; jx < e.size; jx += 32) {
+      unsigned long long fid = src[jx];
+      const uint32_t pos = e.offset + jx;
+      if (fid >= n_frames_registered) { atomicOr(&ctr_w->err, ERR_BAD_FRAME_ID); fid = 0; }
+      ustream[pos - off0] = (uint32_t)fid;
+      if (loc_first[(uint32_t)fid] > pos) atomicMin(&loc_first[(uint32_t)fid], pos);
+    }
+  }
+}
+// thread-id dictionary: list of this shard's (tid, global first row) pairs, and the insert of the other shards' lists
+__global__ void __launch_bounds__(kThreads) k_tid_pack(const unsigned long long* hslots, uint32_t hmask, uint32_t* n_out, unsigned long long* out) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i <= hmask; i += gridDim.x * kThreads) {
+    const unsigned long long sl = hslots[i];
+    if (sl != ~0ull) out[atomicAdd(n_out, 1u)] = sl;
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_tid_insert(const unsigned long long* in, uint32_t n, unsigned long long* hslots, uint32_t hmask, Counters* ctr_w) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const unsigned long long sl = in[i];
+    if (hashed_min_insert(hslots, hmask, (uint32_t)(sl >> 32), (uint32_t)sl) == kNull) atomicOr(&ctr_w->err, ERR_TABLE_FULL);
+  }
+}
+// element-wise minimum (the in-process stand-in for ncclAllReduce(min) when every shard of the group lives on one device)
+__global__ void __launch_bounds__(kThreads) k_min_u32(uint32_t* dst, const uint32_t* src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) { uint32_t v = src[i]; if (v < dst[i]) dst[i] = v; }
+}
+// run-end columns across shards. edges[m][c] come from every shard (all-gather); a shard's last run continues in the next
+// non-empty shard when both border rows are non-null and carry the same key (BinaryDictionaryRunEndBuilder.Append,
+// reporter/arrow.go:97-131: a row extends the current run iff the previous value is non-null and byte-equal). The
+// continued run is written by the shard where it ENDS; the shard where it starts drops its last run.
+__global__ void __launch_bounds__(kThreads) k_edges_pack(const Counters* ctr, const uint32_t* edge_keys, uint32_t ncols, uint32_t row_base, uint32_t n_rows, EdgeCol* out) {
+  for (uint32_t c = threadIdx.x; c < ncols; c += blockDim.x) {
+    const uint32_t lnn = ctr->last_nonnull_plus1[c];
+    out[c] = EdgeCol{ctr->n_runs[c], ctr->n_null[c], lnn ? row_base + lnn : 0u, n_rows, edge_keys[c * 4 + 0], edge_keys[c * 4 + 1], edge_keys[c * 4 + 2], edge_keys[c * 4 + 3]};
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_merge_cols(const EdgeCol* edges /*[world][ncols]*/, uint32_t world, uint32_t me, uint32_t ncols,
+                                                         MergeCol* mine /*[ncols]*/, MergeCol* all /*[world][ncols]*/, Counters* ctr_w) {
+  for (uint32_t c = threadIdx.x; c < ncols; c += blockDim.x) {
+    uint32_t base = 0, nulls = 0, lastnn = 0;
+    for (uint32_t m = 0; m < world; m++) {
+      const EdgeCol e = edges[(size_t)m * ncols + c];
+      uint32_t keep = e.n_runs;
+      if (e.n_rows) {
+        uint32_t nx = m + 1;
+        while (nx < world && edges[(size_t)nx * ncols + c].n_rows == 0) nx++;
+        if (nx < world) {
+          const EdgeCol f = edges[(size_t)nx * ncols + c];
+          if (!e.last_null && !f.first_null && e.last_key == f.first_key) keep = e.n_runs - 1;
+        }
+      }
+      const MergeCol mcv{keep, base & 31u, base, 0u};
+      all[(size_t)m * ncols + c] = mcv;
+      if (m == me) mine[c] = mcv;
+      base += keep; nulls += e.n_null; lastnn = max(lastnn, e.lastnn);
+    }
+    // the counters now describe the MERGED column (identical on every shard)
+    ctr_w->n_runs[c] = base; ctr_w->n_null[c] = nulls; ctr_w->last_nonnull_plus1[c] = lastnn;
   }
 }
 

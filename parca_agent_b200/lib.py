@@ -19,6 +19,8 @@ EXPORTS = [
     "pa_agg_register_frames", "pa_agg_register_labelsets", "pa_agg_acquire", "pa_agg_commit", "pa_agg_submit",
     "pa_agg_flush", "pa_agg_release", "pa_agg_stage", "pa_agg_process", "pa_agg_collect", "pa_agg_last_kernel_ms",
     "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_agg_debug_pair_counts", "pa_agg_stacktraces", "pa_agg_last_stack_ids", "pa_agg_shard_sizes", "pa_agg_shard_export", "pa_agg_stage_device", "pa_agg_stage_device_parts", "pa_agg_discard", "pa_ipc_compress_lz4", "pa_ipc_free", "pa_fix_truncation", "pa_xxh64",
+    "pa_merge_create_local", "pa_merge_nccl_unique_id", "pa_merge_create_nccl", "pa_merge_destroy", "pa_merge_last_error", "pa_merge_process",
+    "pa_merge_plan", "pa_merge_collect", "pa_merge_flush", "pa_merge_last_stats",
 ]
 
 
@@ -72,6 +74,18 @@ def lib():
         L.pa_fix_truncation.restype = C.c_int64
         L.pa_xxh64.argtypes = [vp, C.c_uint64, C.c_uint64]
         L.pa_xxh64.restype = C.c_uint64
+        L.pa_merge_create_local.argtypes = [C.POINTER(vp), C.c_uint32, C.POINTER(vp)]
+        L.pa_merge_nccl_unique_id.argtypes = [C.c_char_p]
+        L.pa_merge_create_nccl.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+        L.pa_merge_destroy.argtypes = [vp]
+        L.pa_merge_destroy.restype = None
+        L.pa_merge_last_error.argtypes = [vp]
+        L.pa_merge_last_error.restype = C.c_char_p
+        L.pa_merge_process.argtypes = [vp]
+        L.pa_merge_plan.argtypes = [vp, u64p]
+        L.pa_merge_collect.argtypes = [vp, vp, C.c_uint64, C.POINTER(abi.PaAggResult)]
+        L.pa_merge_flush.argtypes = [vp, C.POINTER(abi.PaAggResult)]
+        L.pa_merge_last_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), u64p, u64p]
         _LIB = L
     return _LIB
 
@@ -244,6 +258,89 @@ class Aggregator:
         out = np.zeros(n, dtype=np.uint32)
         self._ck(lib().pa_agg_debug_stack_counts(self.h, out.ctypes.data, n))
         return out
+
+
+class MergeGroup:
+    """Shard aggregators that build ONE merged record batch (mode B, include/parcaagg.h pa_merge_*). The merged batch is the
+    record of the stream [member 0's rows, member 1's rows, ...]; only dictionary keys are exchanged between the GPUs."""
+
+    def __init__(self, handle, members):
+        self.h, self.members = handle, list(members)
+
+    @classmethod
+    def local(cls, members):
+        """All members in this process, on one device (device copies instead of NCCL)."""
+        arr = (C.c_void_p * len(members))(*[m.h for m in members])
+        h = C.c_void_p()
+        rc = lib().pa_merge_create_local(arr, len(members), C.byref(h))
+        if rc != 0:
+            raise PaError(rc, "pa_merge_create_local failed")
+        return cls(h, members)
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = C.create_string_buffer(128)
+        rc = lib().pa_merge_nccl_unique_id(buf)
+        if rc != 0:
+            raise PaError(rc, "pa_merge_nccl_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    @classmethod
+    def nccl(cls, member, unique_id, rank, world):
+        """One member per process / per GPU; `unique_id` comes from rank 0's nccl_unique_id()."""
+        h = C.c_void_p()
+        rc = lib().pa_merge_create_nccl(member.h, bytes(unique_id), rank, world, C.byref(h))
+        if rc != 0:
+            raise PaError(rc, "pa_merge_create_nccl failed")
+        return cls(h, [member])
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PaError(rc, (lib().pa_merge_last_error(self.h) or b"").decode(errors="replace"))
+
+    def process(self):
+        self._ck(lib().pa_merge_process(self.h))
+
+    def plan(self):
+        n = C.c_uint64()
+        self._ck(lib().pa_merge_plan(self.h, C.byref(n)))
+        return int(n.value)
+
+    def collect(self, base_ptr=None, cap=0):
+        raw = abi.PaAggResult()
+        self._ck(lib().pa_merge_collect(self.h, base_ptr, cap, C.byref(raw)))
+        return Result(raw) if raw.ipc else _HeadlessResult(raw)
+
+    def flush(self):
+        raw = abi.PaAggResult()
+        self._ck(lib().pa_merge_flush(self.h, C.byref(raw)))
+        return Result(raw)
+
+    def stats(self):
+        wall, wait, nb, nr = C.c_double(), C.c_double(), C.c_uint64(), C.c_uint64()
+        self._ck(lib().pa_merge_last_stats(self.h, C.byref(wall), C.byref(wait), C.byref(nb), C.byref(nr)))
+        return {"wall_ms": wall.value, "exchange_wait_ms": wait.value, "nvlink_bytes": int(nb.value), "rows": int(nr.value)}
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pa_merge_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _HeadlessResult(Result):
+    """Result on a rank that does not hold the stream (every rank but 0 of a multi-process merge)."""
+
+    def __init__(self, raw):
+        n = int(raw.ipc_len)
+        raw.ipc_len = 0
+        super().__init__(raw)
+        self.ipc_len = n
 
 
 def from_workload(w, device=0, max_samples=None, max_frames=None, chunk_samples=0, **kw):

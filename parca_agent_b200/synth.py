@@ -266,6 +266,72 @@ def config4_shard(rank, world, n_total=100_000_000, hash_mode=abi.PA_HASH_XXH64X
     return _pid_shard("cfg4", 0x5EED0004, rank, world, n_total // world, 1_000_000 // world * 2, 1_048_576, 65_536 // world, hash_mode)
 
 
+def config4_part(rank, world, rows_per_gpu=12_500_000, stacks_per_gpu=125_000, frames_per_gpu=131_072, pids_per_gpu=8_192,
+                 hash_mode=abi.PA_HASH_XXH64X2, seed=0x5EED0004):
+    """One rank's ring of a MERGED batch (mode B): BASELINE config 4 at world == 8 (100M samples x 64 frames, 1M unique stacks,
+    1,048,576 distinct frames, 65,536 pids sharded by xxh64(pid) mod world), proportionally smaller at other world sizes.
+    Strings, frames, labelsets and the stack table are common to every rank (the merge needs identical registrations: ids
+    are global); the rows are this rank's pids only. Every rank draws its stacks from the WHOLE stack table, so nearly every
+    stack occurs on every GPU — the hardest case for the dictionary merge."""
+    U, P, npids, F = stacks_per_gpu * world, frames_per_gpu * world, pids_per_gpu * world, 64
+    rng = np.random.Generator(np.random.PCG64(seed))
+    st = StringTable()
+    frames = _frame_table(rng, st, P, 0.8, 0.1, "python")
+    stack_table = rng.integers(0, P, (U, F), dtype=np.uint64)
+    n_comm, n_node, v_node = st.sid("comm"), st.sid("node"), st.sid("node-0")
+    labelsets = [[(n_comm, st.sid("proc-%05d" % q)), (n_node, v_node)] for q in range(npids)]
+    threads = 16
+    thread_comm = np.array([st.sid("worker-%02d" % t) for t in range(threads)], dtype=np.uint32)
+    owner = np.array([xxh64_u32(1000 + q) % world for q in range(npids)], dtype=np.int64)
+    mine = np.nonzero(owner == rank)[0]
+    rr = np.random.Generator(np.random.PCG64(seed + 1 + rank))
+    N = rows_per_gpu
+    choice = rr.integers(0, U, N)
+    pid_idx = mine[rr.integers(0, len(mine), N)]
+    thr_idx = rr.integers(0, threads, N)
+    hd = np.zeros(N, dtype=abi.HDR_DTYPE)
+    hd["pid"] = 1000 + pid_idx
+    hd["tid"] = 100000 + pid_idx * threads + thr_idx
+    hd["comm_sid"] = thread_comm[thr_idx]
+    hd["labelset_id"] = pid_idx
+    hd["cpu"] = rr.integers(0, 192, N)
+    hd["timestamp_ns"] = 1_700_000_000_000_000_000 + (np.arange(N, dtype=np.int64) * world + rank) * 52631
+    hd["kind"] = abi.PA_KIND_CPU
+    hd["nframes"] = F
+    hd["frame_off"] = np.arange(N, dtype=np.uint64) * np.uint64(F)
+    hd["hash_hi"] = splitmix64(choice.astype(np.uint64))
+    hd["hash_lo"] = splitmix64(choice.astype(np.uint64) ^ np.uint64(0xD1B54A32D192ED03))
+    return Workload("cfg4_part%d_of_%d" % (rank, world), st.strings, frames, labelsets, hd, stack_table=stack_table, stack_choice=choice,
+                    hash_mode=hash_mode, meta={"N": N, "F": F, "U": U, "P": P, "seed": seed, "rank": rank, "world": world, "N_total": N * world})
+
+
+def config5_part(rank, world, rows_per_gpu=47_500_000, hash_mode=abi.PA_HASH_XXH64X2):
+    """One rank's share of a BASELINE config-5 window: 19 Hz x 1M threads x 5 s = 95M samples per window over `world` GPUs
+    (47.5M rows per GPU at world == 2), 64-frame stacks, 500k unique stacks, 62,500 pids x 16 threads = 1M threads."""
+    total_pids = 62_500
+    return config4_part(rank, world, rows_per_gpu=rows_per_gpu, stacks_per_gpu=500_000 // world, frames_per_gpu=524_288 // world,
+                        pids_per_gpu=total_pids // world, hash_mode=hash_mode, seed=0x5EED0005)
+
+
+def concat(parts):
+    """The stream [part 0's rows, part 1's rows, ...] as one workload (what a merged batch must reproduce). Parts must share
+    their tables (config4_part / Workload.rows of one workload)."""
+    w0 = parts[0]
+    hd = np.concatenate([p.hdrs for p in parts])
+    nf = hd["nframes"].astype(np.int64)
+    off = np.zeros(len(hd), dtype=np.uint64)
+    if len(hd):
+        off[1:] = np.cumsum(nf)[:-1]
+    hd["frame_off"] = off
+    w = Workload("concat", w0.strings, w0.frames, w0.labelsets, hd, hash_mode=w0.hash_mode, label_flags=w0.label_flags,
+                 samples_per_second=w0.samples_per_second, external_labels=list(w0.external_labels), meta=dict(w0.meta), schema=w0.schema)
+    if all(p._frame_ids is None for p in parts):
+        w.stack_table, w.stack_choice = w0.stack_table, np.concatenate([p.stack_choice for p in parts])
+    else:
+        w._frame_ids = np.concatenate([p.frame_ids for p in parts])
+    return w
+
+
 def ragged(n=2_000_000, u=50_000, p=65_536, max_depth=127, seed=0x5EED00AA, hash_mode=abi.PA_HASH_XXH64X2):
     """Real-world-like stack depths: every unique stack has its own depth in 1..max_depth (not a BASELINE config; used
     to check that the ragged code paths of the hash kernel stay fast and exact)."""

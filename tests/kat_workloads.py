@@ -83,3 +83,43 @@ def labels_cpu_sequence(flags=0):
     cpus = [0, 1, 0, 3, 2, 1, 3, 0]
     samples = [dict(hash=(1, 1), frames=[0], tid=4243, pid=4140, cpu=c, comm="myprocess") for c in cpus]
     return build(samples, [native(0x1000)], labelsets=[{"node": "test-node"}], label_flags=flags), cpus
+
+
+# ---- inputs of the Go-side golden recipe (tools/golden/golden_parity_test.go feeds the SAME samples through the reference's
+# ReportTraceEvent -> buildSampleRecordV2 -> ipc.Writer). Only mapping-less frames are used, so the Go side needs nothing from
+# the un-vendored profiler module beyond libpf.Frame literals.
+GO_PIN_TYPE_NAMES = {"native": "native", "kernel": "kernel", "python": "python"}  # libpf.FrameType.String(); overridden by tests/golden/go/frame_types.json
+
+
+def interp(type_name, lineno, fn, file, line):
+    return dict(kind=abi.PA_FRAME_INTERP, flags=0, type_name_sid=type_name, address_or_lineno=lineno, function_name_sid=fn, source_file_sid=file, source_line=line)
+
+
+def go_pin_cases(type_names=None):
+    """name -> workload; keep in lock-step with the cases in tools/golden/golden_parity_test.go"""
+    tn = dict(GO_PIN_TYPE_NAMES, **(type_names or {}))
+    nat = lambda addr: dict(kind=abi.PA_FRAME_NATIVE, flags=0, type_name_sid=tn["native"], address_or_lineno=addr)  # noqa: E731  (no mapping: "UNKNOWN", null build id)
+    ker = lambda addr, fn, line: dict(kind=abi.PA_FRAME_KERNEL, flags=0, type_name_sid=tn["kernel"], address_or_lineno=addr, function_name_sid=fn, source_line=line)  # noqa: E731
+    cases = {}
+    # 1. one CPU sample, cached labels {pod, service}, per-sample labels disabled
+    cases["basic"] = build([dict(hash=(1, 2), frames=[0], ts=1234567890, pid=100, tid=100)], [nat(0x1000)],
+                           labelsets=[{"service": "my-service", "pod": "pod-1"}], label_flags=7)
+    # 2. mixed frame kinds and origins, per-sample cpu / thread_id / thread_name labels, two pids with different label names
+    #    (null back-fill), repeated stacks (ListView reuse), a function name longer than 12 bytes (StringView data block)
+    frames = [nat(0x1000), nat(0x2000), ker(0xffffffff81000010, "do_syscall_64", 100), ker(0xffffffff81000020, "", 0),
+              interp(tn["python"], 10, "handler", "/srv/app/main.py", 42), interp(tn["python"], 11, "a_function_name_longer_than_twelve_bytes", "", 7),
+              interp(tn["python"], 12, "", "ignored.py", 9)]
+    ls = [{"node": "test-node"}, {"node": "test-node", "job": "batch"}]
+    S, O, C = abi.PA_KIND_CPU, abi.PA_KIND_OFFCPU, abi.PA_KIND_CUDA
+    rows = [
+        dict(hash=(1, 1), frames=[0, 2], kind=S, ts=1000, pid=10, tid=11, cpu=0, comm="alpha", labelset=0),
+        dict(hash=(1, 1), frames=[0, 2], kind=S, ts=1001, pid=10, tid=11, cpu=0, comm="alpha", labelset=0),
+        dict(hash=(2, 2), frames=[4, 5, 1], kind=S, ts=1002, pid=20, tid=21, cpu=3, comm="beta", labelset=1),
+        dict(hash=(3, 3), frames=[3, 6], kind=O, ts=1003, value=5000, pid=20, tid=22, cpu=3, comm="", labelset=1),
+        dict(hash=(1, 1), frames=[0, 2], kind=C, ts=1004, value=777, pid=10, tid=11, cpu=1, comm="alpha", labelset=0),
+        dict(hash=(4, 4), frames=[], kind=S, ts=1005, pid=10, tid=12, cpu=1, comm="alpha", labelset=0),
+    ]
+    cases["mixed"] = build(rows, frames, labelsets=ls, label_flags=0)
+    # 3. the same rows with external labels: a new name and one that collides with a sample label
+    cases["mixed_external"] = build(rows, frames, labelsets=ls, label_flags=0, external=[("cluster", "prod"), ("job", "ext-job")])
+    return cases

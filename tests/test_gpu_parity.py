@@ -199,7 +199,7 @@ def test_bad_ids_are_reported(gpu):
     a.close()
 
 
-@pytest.mark.parametrize("variant", ["direct", "staged", "wide"])
+@pytest.mark.parametrize("variant", ["direct", "staged", "wide", "bulk", "bulk6x2"])
 def test_hash_kernel_variants(oracle, gpu, variant, monkeypatch):
     """Both hash kernels (direct global loads / cp.async-staged) must produce identical bytes, including
     ragged stacks, odd frame offsets (8-byte staging path) and stacks deeper than one staging slot."""
