@@ -130,6 +130,8 @@ struct pa_agg {
   int device = 0, sms = 148, G = 592;
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool fork_early = false;   // PA_FORK_EARLY=1: the label chain starts right after the header pass and runs beside the hash kernel
+  bool forked_early = false;
   bool serial = false;       // PA_SERIAL=1: the label chain stays on the compute stream (per-group timings do not overlap)
   Pass P;
   bool merged_part = false;  // the processed batch is one shard of a merged record (collected through pa_merge_collect)
@@ -365,6 +367,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   cudaEventCreateWithFlags(&a->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&a->ev_join, cudaEventDisableTiming);
   if (const char* sv = getenv("PA_SERIAL")) a->serial = sv[0] == '1';
+  if (const char* sv = getenv("PA_FORK_EARLY")) a->fork_early = sv[0] == '1';
   cudaEventCreate(&a->ev_h2d0);
   cudaEventCreate(&a->ev_h2d1);
   cudaEventCreate(&a->ev_d2h0);
@@ -654,8 +657,12 @@ static void launch_store_insert(pa_agg* a) {
 // ---------------------------------------------------------------------------------------------
 // The per-interval pass, in stages. A single aggregator runs them back to back (process_once); a group of shard
 // aggregators that builds ONE merged record (mode B, merge_impl.hpp) runs the same stages with its exchanges in between.
+// Upper bound on distinct keys used to size an open-address table: small batches take their row count; large ones take
+// 4x what the previous interval saw, and a cold start assumes one distinct key per 16 rows (a 10M-row batch then starts
+// with a 64 MB table instead of 1 GB). A wrong guess costs a redo of the pass with a 4x larger table (ERR_TABLE_FULL).
 static uint64_t table_bound(uint64_t n, uint64_t prev, uint64_t big, uint64_t floor_) {
-  return (prev && n > big) ? std::min<uint64_t>(n, std::max<uint64_t>(prev * 4, floor_)) : n;
+  if (n <= big) return n;
+  return std::min<uint64_t>(n, std::max<uint64_t>(prev ? prev * 4 : n / 16, floor_));
 }
 
 // sizes, arena layout, job / column descriptor tables for the staged batch. md != nullptr: this aggregator is shard
@@ -897,6 +904,7 @@ static int pass_front(pa_agg* a) {
   if (resident) {
     if (N) launch_header(0, N, a->NF);  // whole resident batch: one launch per pass
     CK(cudaEventRecord(a->tm[T_HEADER].b, s));
+    if (a->fork_early && !a->serial && !P.v1 && !P.merged) { CK(cudaEventRecord(a->ev_fork, s)); a->forked_early = true; }
     CK(cudaEventRecord(a->tm[T_HASH].a, s));
     if (!provided && N) launch_hash(0, N);
     CK(cudaEventRecord(a->tm[T_HASH].b, s));
@@ -1031,6 +1039,7 @@ static int pass_finish(pa_agg* a) {
 static int process_once(pa_agg* a) {
   int rc = pass_plan(a, nullptr);
   if (rc) return rc;
+  a->forked_early = false;
   if ((rc = pass_front(a))) return rc;
   // The label chain depends only on k_header's outputs; the stack-rank / location chain only on the table. Both are
   // chains of small latency-bound launches, so they run side by side on two streams (PA_SERIAL=1: one stream, so
@@ -1038,7 +1047,7 @@ static int process_once(pa_agg* a) {
   // (v1: the run-end encoded stacktrace_id column reads the stack ordinals the rank chain produces, so the chains stay in order)
   const bool fork = !a->serial && !a->P.v1;
   cudaStream_t s = a->s_comp, s2 = fork ? a->s_aux : a->s_comp;
-  if (fork) { CK(cudaEventRecord(a->ev_fork, s)); CK(cudaStreamWaitEvent(s2, a->ev_fork, 0)); }
+  if (fork) { if (!a->forked_early) CK(cudaEventRecord(a->ev_fork, s)); CK(cudaStreamWaitEvent(s2, a->ev_fork, 0)); }
   if ((rc = pass_rank_single(a))) return rc;
   if ((rc = pass_locations(a))) return rc;
   if ((rc = pass_labels_count(a, s2))) return rc;

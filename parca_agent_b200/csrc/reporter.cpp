@@ -28,7 +28,24 @@ struct AggSink final : Sink {
     if (pa_agg_register_labelsets(a, pairs.data(), off, 1, &id) != PA_OK) return PA_NO_STRING;
     return id;
   }
-  int Submit(const pa_sample_hdr& hdr, const uint64_t* frame_ids) override { return pa_agg_submit(a, &hdr, frame_ids, 1); }
+  // rows are handed to the ring kBatch at a time: one lock round-trip and one call across the ABI per batch instead of
+  // per sample (what a cgo shim must do too: a cgo call costs ~100 ns). Callers are serialised by the reporter's mutex.
+  static constexpr size_t kBatch = 256;
+  std::vector<pa_sample_hdr> pend_h;
+  std::vector<uint64_t> pend_f;
+  int push() {
+    if (pend_h.empty()) return PA_OK;
+    int rc = pa_agg_submit(a, pend_h.data(), pend_f.data(), pend_h.size());
+    pend_h.clear();
+    pend_f.clear();
+    return rc;
+  }
+  int Submit(const pa_sample_hdr& hdr, const uint64_t* frame_ids) override {
+    pend_h.push_back(hdr);
+    pend_f.insert(pend_f.end(), frame_ids, frame_ids + hdr.nframes);
+    return pend_h.size() >= kBatch ? push() : PA_OK;
+  }
+  int Publish() override { return push(); }
   int Flush(pa_agg_result* out) override { return pa_agg_flush(a, out); }
   void Release(pa_agg_result* res) override { pa_agg_release(a, res); }
   int LastStackIds(uint8_t* out, uint64_t n) override { return pa_agg_last_stack_ids(a, out, n); }
@@ -69,7 +86,7 @@ uint32_t ParcaReporter::sid(const std::string& s) {
   auto it = strings_.find(s);
   if (it != strings_.end()) return it->second;
   uint32_t id = sink_->RegisterString(s);
-  strings_.emplace(s, id);
+  if (id != PA_NO_STRING) strings_.emplace(s, id);  // a failed registration is retried next time
   return id;
 }
 
@@ -89,11 +106,17 @@ void ParcaReporter::ReportExecutable(const ExecutableMetadata& md) {
   if (it != unknown_by_file_.end()) {
     for (auto& key : it->second) frames_.erase(key);
     unknown_by_file_.erase(it);
+    trace_cache_.clear();  // cached id lists may contain the forgotten ids
+    trace_ids_.clear();
   }
 }
 
 // Frame value -> dense frame id. The key is the whole Frame (as libpf.Frame is the map key at :421).
 uint64_t ParcaReporter::frameId(const Frame& f) {
+  if (f.Handle) {  // interned handle: value identity is pointer identity
+    auto h = frames_by_handle_.find(f.Handle);
+    if (h != frames_by_handle_.end()) return h->second;
+  }
   std::string key;
   key.reserve(64 + f.FunctionName.size() + f.SourceFile.size());
   auto put = [&key](const void* p, size_t n) { key.append((const char*)p, n); };
@@ -104,7 +127,7 @@ uint64_t ParcaReporter::frameId(const Frame& f) {
   uint8_t mv = (uint8_t)((f.MappingValid ? 1 : 0) | (f.MappingHasFile ? 2 : 0));
   put(&mv, 1); put(&f.MappingFileID, sizeof(FileID));
   auto it = frames_.find(key);
-  if (it != frames_.end()) return it->second;
+  if (it != frames_.end()) { if (f.Handle) frames_by_handle_.emplace(f.Handle, it->second); return it->second; }
 
   pa_frame_desc d;
   memset(&d, 0, sizeof d);
@@ -135,6 +158,7 @@ uint64_t ParcaReporter::frameId(const Frame& f) {
   }
   uint64_t id = sink_->RegisterFrame(d);
   frames_.emplace(std::move(key), id);
+  if (f.Handle && !(has_file && !(d.flags & PA_FRAME_F_EXEC_KNOWN))) frames_by_handle_.emplace(f.Handle, id);  // frames of a still-unknown executable keep going through the value path (they are re-resolved once it is reported)
   return id;
 }
 
@@ -176,7 +200,7 @@ bool ParcaReporter::labelsForPID(uint32_t pid, PidLabels** out) {
 }
 
 int ParcaReporter::writeSampleV2(const Trace* trace, const TraceEventMeta* meta, uint32_t labelset, uint8_t kind, int64_t value,
-                                 const std::vector<uint64_t>& ids) {
+                                 const uint64_t* ids, size_t nids) {
   pa_sample_hdr h;
   memset(&h, 0, sizeof h);
   h.hash_hi = trace->Hash.hi;
@@ -188,9 +212,9 @@ int ParcaReporter::writeSampleV2(const Trace* trace, const TraceEventMeta* meta,
   h.comm_sid = sid(meta->Comm);
   h.labelset_id = labelset;
   h.cpu = (uint32_t)meta->CPU;
-  h.nframes = (uint16_t)ids.size();
+  h.nframes = (uint16_t)nids;
   h.kind = kind;
-  return sink_->Submit(h, ids.data());
+  return sink_->Submit(h, ids);
 }
 
 int ParcaReporter::ReportTraceEvent(const Trace* trace, const TraceEventMeta* meta) {
@@ -213,23 +237,41 @@ int ParcaReporter::ReportTraceEvent(const Trace* trace, const TraceEventMeta* me
     }
     labelset = labelsetId(Labels(lb.begin(), lb.end()));
   }
-  std::vector<uint64_t> ids;
-  ids.reserve(trace->Frames.size());
-  for (auto& f : trace->Frames) ids.push_back(frameId(f));
+  // frame ids of this trace: from the per-hash cache when the stack was seen before (one lookup), else per frame
+  const uint64_t* idp = nullptr;
+  const size_t nfr = trace->Frames.size();
+  const bool cacheable = (trace->Hash.hi | trace->Hash.lo) != 0;  // oomprof traces share the zero hash with different frames
+  if (cacheable) {
+    auto tc = trace_cache_.find(trace->Hash);
+    if (tc != trace_cache_.end() && tc->second.second == nfr) idp = trace_ids_.data() + tc->second.first;
+  }
+  if (!idp) {
+    scratch_ids_.clear();
+    scratch_ids_.reserve(nfr);
+    for (auto& f : trace->Frames) scratch_ids_.push_back(frameId(f));
+    if (cacheable) {
+      if (trace_cache_.size() >= kTraceCacheEntries) { trace_cache_.clear(); trace_ids_.clear(); }
+      trace_cache_[trace->Hash] = std::make_pair((uint64_t)trace_ids_.size(), (uint32_t)nfr);
+      trace_ids_.insert(trace_ids_.end(), scratch_ids_.begin(), scratch_ids_.end());
+    }
+    idp = scratch_ids_.data();
+  }
+  if (nfr > 65535) { droppedBatches++; return 0; }  // the row format carries a 16-bit depth; such a trace cannot come out of the unwinder
+  const uint64_t* ids = idp;
 
   int rc = 0;
   switch (meta->Origin) {  // reportTraceEventV2 :338-363
-    case TraceOriginSampling: rc = writeSampleV2(trace, meta, labelset, PA_KIND_CPU, 1, ids); cpuSamples++; break;
-    case TraceOriginOffCPU: rc = writeSampleV2(trace, meta, labelset, PA_KIND_OFFCPU, meta->OffTime, ids); offcpuSamples++; break;
-    case TraceOriginCuda: rc = writeSampleV2(trace, meta, labelset, PA_KIND_CUDA, meta->OffTime, ids); gpuSamples++; break;
+    case TraceOriginSampling: rc = writeSampleV2(trace, meta, labelset, PA_KIND_CPU, 1, ids, nfr); cpuSamples++; break;
+    case TraceOriginOffCPU: rc = writeSampleV2(trace, meta, labelset, PA_KIND_OFFCPU, meta->OffTime, ids, nfr); offcpuSamples++; break;
+    case TraceOriginCuda: rc = writeSampleV2(trace, meta, labelset, PA_KIND_CUDA, meta->OffTime, ids, nfr); gpuSamples++; break;
     case TraceOriginMemory: {
       const MemorySample* m = meta->OriginData;
       if (!m) break;  // "memory trace event missing OriginData" :345-348
-      if (m->Allocs != m->Frees) rc |= writeSampleV2(trace, meta, labelset, PA_KIND_MEM_INUSE_OBJECTS, (int64_t)(m->Allocs - m->Frees), ids);
-      if (m->AllocBytes != m->FreeBytes) rc |= writeSampleV2(trace, meta, labelset, PA_KIND_MEM_INUSE_SPACE, (int64_t)(m->AllocBytes - m->FreeBytes), ids);
+      if (m->Allocs != m->Frees) rc |= writeSampleV2(trace, meta, labelset, PA_KIND_MEM_INUSE_OBJECTS, (int64_t)(m->Allocs - m->Frees), ids, nfr);
+      if (m->AllocBytes != m->FreeBytes) rc |= writeSampleV2(trace, meta, labelset, PA_KIND_MEM_INUSE_SPACE, (int64_t)(m->AllocBytes - m->FreeBytes), ids, nfr);
       if (cfg_.reportAllocs) {
-        rc |= writeSampleV2(trace, meta, labelset, PA_KIND_MEM_ALLOC_OBJECTS, (int64_t)m->Allocs, ids);
-        rc |= writeSampleV2(trace, meta, labelset, PA_KIND_MEM_ALLOC_SPACE, (int64_t)m->AllocBytes, ids);
+        rc |= writeSampleV2(trace, meta, labelset, PA_KIND_MEM_ALLOC_OBJECTS, (int64_t)m->Allocs, ids, nfr);
+        rc |= writeSampleV2(trace, meta, labelset, PA_KIND_MEM_ALLOC_SPACE, (int64_t)m->AllocBytes, ids, nfr);
       }
       memorySamples++;
       break;
@@ -266,7 +308,15 @@ int ParcaReporter::SampleEvents(const std::vector<MemorySample>& samples, const 
 
 int64_t ParcaReporter::FlushOnce() {
   pa_agg_result res;
-  int rc = sink_->Flush(&res);
+  int rc;
+  {
+    // rows still buffered on the host side join this interval under the ingest lock; the ring swap itself is the
+    // aggregator's (buildSampleRecordV2 holds sampleWriterV2Mu only for its writer swap, :1745-1748)
+    std::lock_guard<std::mutex> g(mu_);
+    rc = sink_->Publish();
+  }
+  if (rc == PA_ENOSPC) droppedBatches++;  // ring full: those rows are lost, the interval still goes out
+  rc = sink_->Flush(&res);
   if (rc != PA_OK) { droppedBatches++; return rc; }  // flush error: logged, interval dropped (:1218-1220)
   int64_t rows = (int64_t)res.n_rows;
   if (res.n_rows) {  // empty intervals are skipped (:1842-1845)
@@ -281,12 +331,15 @@ int64_t ParcaReporter::FlushOnce() {
     // seen, and write their stacktrace record right behind the sample record (even when there are none)
     std::vector<uint8_t> ids(n_unique * 16), fresh;
     if ((rc = sink_->LastStackIds(ids.data(), n_unique)) != PA_OK) { droppedBatches++; return rc; }
-    for (uint64_t i = 0; i < n_unique; i++) {
-      std::string key((const char*)ids.data() + 16 * i, 16);
-      bool& seen = logged_stacks_[key];
-      if (seen) continue;
-      seen = true;
-      fresh.insert(fresh.end(), key.begin(), key.end());
+    {
+      std::lock_guard<std::mutex> g(mu_);  // ResetLoggedStacks (log rotation) may run on another thread
+      for (uint64_t i = 0; i < n_unique; i++) {
+        std::string key((const char*)ids.data() + 16 * i, 16);
+        bool& seen = logged_stacks_[key];
+        if (seen) continue;
+        seen = true;
+        fresh.insert(fresh.end(), key.begin(), key.end());
+      }
     }
     pa_agg_result st;
     if ((rc = sink_->Stacktraces(fresh.data(), fresh.size() / 16, &st)) != PA_OK) { droppedBatches++; return rc; }

@@ -47,6 +47,9 @@ struct Frame {  // libpf.Frame — the dedup key of appendLocationV2 (parca_repo
   bool MappingHasFile = false;   // m.File != (libpf.FrameMappingFile{})
   FileID MappingFileID;          // mf.FileID
   std::string MappingFileName, MappingGnuBuildID;  // mf.FileName / mf.GnuBuildID (v1 stacktrace record, :1716-1719)
+  // unique.Handle[libpf.Frame] (what libpf.Frames iterates, arrow_v2.go:305-306): handle equality == Frame value equality,
+  // so a non-zero Handle is the whole interning key (one 8-byte hash lookup per frame instead of serialising the value).
+  uint64_t Handle = 0;
 };
 struct Trace {  // libpf.Trace
   TraceHash Hash;
@@ -83,7 +86,8 @@ struct Sink {
   virtual uint32_t RegisterString(const std::string& s) = 0;
   virtual uint64_t RegisterFrame(const pa_frame_desc& d) = 0;
   virtual uint32_t RegisterLabelset(const std::vector<pa_label_pair>& pairs) = 0;
-  virtual int Submit(const pa_sample_hdr& hdr, const uint64_t* frame_ids) = 0;
+  virtual int Submit(const pa_sample_hdr& hdr, const uint64_t* frame_ids) = 0;  // may buffer rows until Publish
+  virtual int Publish() { return 0; }  // hand buffered rows to the aggregator; called under the reporter's ingest lock
   virtual int Flush(pa_agg_result* out) = 0;
   virtual void Release(pa_agg_result* res) = 0;
   // v1 schema only: the ids of the last flushed batch's unique stacks, and the stacktrace record for a set of ids
@@ -142,6 +146,16 @@ class ParcaReporter {
   std::mutex mu_;  // sampleWriterV2Mu (:335): row order == lock acquisition order
   std::unordered_map<std::string, uint32_t> strings_;
   std::unordered_map<std::string, uint64_t> frames_;          // serialised Frame value (+exec state) -> frame id
+  std::unordered_map<uint64_t, uint64_t> frames_by_handle_;   // Frame::Handle -> frame id (the fast path)
+  // trace.Hash -> the frame ids of that trace (the role of the reference's `stacks` LRU, :224-227, turned into an interning
+  // cache): a stack seen before costs ONE 16-byte lookup and a copy of its ids instead of one lookup per frame. Bounded;
+  // cleared when full and whenever an executable becomes known (frames resolved as UNKNOWN must be looked at again).
+  struct TraceHashHasher { size_t operator()(const TraceHash& h) const { return (size_t)(h.hi * 0x9E3779B97F4A7C15ull ^ h.lo); } };
+  struct TraceHashEq { bool operator()(const TraceHash& a, const TraceHash& b) const { return a.hi == b.hi && a.lo == b.lo; } };
+  std::unordered_map<TraceHash, std::pair<uint64_t, uint32_t>, TraceHashHasher, TraceHashEq> trace_cache_;  // -> (offset, count) in trace_ids_
+  std::vector<uint64_t> trace_ids_;
+  std::vector<uint64_t> scratch_ids_;
+  static constexpr size_t kTraceCacheEntries = 1u << 20;
   std::map<FileID, ExecutableMetadata> executables_;          // r.executables (:650-693)
   std::map<FileID, std::vector<std::string>> unknown_by_file_;  // frames interned while their executable was unknown
   std::unordered_map<uint32_t, PidLabels> labels_;            // r.labels LRU content (:569)
@@ -156,7 +170,7 @@ class ParcaReporter {
   uint64_t frameId(const Frame& f);
   uint32_t labelsetId(const Labels& l);
   bool labelsForPID(uint32_t pid, PidLabels** out);
-  int writeSampleV2(const Trace* trace, const TraceEventMeta* meta, uint32_t labelset, uint8_t kind, int64_t value, const std::vector<uint64_t>& ids);
+  int writeSampleV2(const Trace* trace, const TraceEventMeta* meta, uint32_t labelset, uint8_t kind, int64_t value, const uint64_t* ids, size_t nids);
 };
 
 // maybeFixTruncation (parca_reporter.go:190-216)

@@ -50,6 +50,7 @@ def merged_vs_oracle(oracle, gpu, w, idx_lists, staged=False, repeat=1, chunk_sa
         else:
             res = g.flush()
         got = res.ipc_bytes()
+        res.ipc = np.frombuffer(got, dtype=np.uint8)  # the library buffer goes away with the group: keep a copy
         if got != want:
             d = None
             if want and got:
