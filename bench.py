@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-merge", action="store_true", help="N>1: skip mode B (ONE merged record over all GPUs with an O(unique keys) NCCL dictionary "
                     "exchange, BASELINE config 4 at N=8); by default it is timed after the headline (mode A) and reported under \"mode_b\"")
     ap.add_argument("--merge-rows", type=int, default=12_500_000, help="mode B rows per GPU (config 4 = 100M / 8)")
+    ap.add_argument("--mode-b-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--merge-timeout", type=int, default=600, help="seconds after which a stalled mode B leg is abandoned (the headline line is printed without it)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="BASELINE.json config: 2 = headline (default), 3 = Zipf/CUDA-origin/50k labelsets")
     return ap.parse_args()
@@ -372,6 +373,19 @@ def main():
     torch.cuda.set_device(local)
     if args.stream:
         return run_stream(args, rank, world, local)
+    if args.mode_b_child:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+        def child_barrier():
+            dist.barrier()
+            torch.cuda.synchronize()
+        res = run_mode_b(args, rank, world, local, child_barrier)
+        if rank == 0:
+            with open(os.environ["PA_MODE_B_RESULT"] + ".tmp", "w") as f:
+                json.dump(res, f)
+            os.replace(os.environ["PA_MODE_B_RESULT"] + ".tmp", os.environ["PA_MODE_B_RESULT"])
+        dist.destroy_process_group()
+        return
     numa = pin_to_gpu_numa(local)  # the rings are first-touched by this rank: keep them next to its GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -535,23 +549,31 @@ def main():
             out["v1_stacktrace_record"] = v1_st
     a.close()
     if world > 1 and not args.no_merge and args.config == 2 and args.schema == "v2":
-        # the extra leg must never cost the headline line: a watchdog prints what is there and ends the process if the merged
-        # run stalls (a rank that died inside a collective leaves the others waiting)
-        def bail():
-            if rank == 0:
-                out["mode_b"] = {"error": "mode B did not finish within %d s" % args.merge_timeout}
-                print(json.dumps(out), flush=True)
-            os._exit(0)
-        dog = threading.Timer(args.merge_timeout, bail)
-        dog.daemon = True
-        dog.start()
+        # The merged-batch leg runs in CHILD processes (one per rank, own rendezvous port, own CUDA context): whatever happens
+        # in there — an exception, a crash inside a collective, a stall — the headline line above survives. Rank 0's child
+        # leaves its result in a file; every parent waits for its own child (bounded) and goes on.
+        port = int(os.environ.get("MASTER_PORT", "29500")) + 17
+        res_file = "/tmp/pa_mode_b_%d_%d.json" % (os.getppid(), port)
+        env = dict(os.environ, MASTER_PORT=str(port), PA_MODE_B_RESULT=res_file)
+        cmd = [sys.executable, os.path.abspath(__file__), "--mode-b-child", "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
+               "--merge-rows", str(args.merge_rows), "--hash-mode", args.hash_mode, "--e2e-steps", str(args.e2e_steps)]
+        if rank == 0 and os.path.exists(res_file):
+            os.remove(res_file)
+        barrier()
+        child = subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
         try:
-            mode_b = run_mode_b(args, rank, world, local, barrier)
-        except Exception as e:  # noqa: BLE001
-            mode_b = {"error": repr(e)[:500]}
-        dog.cancel()
+            _, cerr = child.communicate(timeout=args.merge_timeout)
+            status = "rc %d" % child.returncode
+        except subprocess.TimeoutExpired:
+            child.kill()
+            _, cerr = child.communicate()
+            status = "killed after %d s" % args.merge_timeout
         if rank == 0:
-            out["mode_b"] = mode_b
+            try:
+                out["mode_b"] = json.load(open(res_file))
+                os.remove(res_file)
+            except Exception:  # noqa: BLE001
+                out["mode_b"] = {"error": "mode B child %s" % status, "stderr_tail": (cerr or "")[-600:]}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

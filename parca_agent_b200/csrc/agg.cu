@@ -121,7 +121,10 @@ struct Pass {
   std::vector<FoJob> jobs;
   std::vector<ReeCol> rc;
   ReeArgs ra{};
-  ReeGroups rg{};
+  ReeGroups rg{};        // every column group
+  ReeGroups rg_single{}; // the groups the one-sweep kernel encodes (everything but the kind-derived columns)
+  ReeGroups rg_kind{};   // the kind-derived group alone
+  ReeTiles tiles{};
 };
 
 struct pa_agg {
@@ -130,6 +133,8 @@ struct pa_agg {
   int device = 0, sms = 148, G = 592;
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool use_onepass = true;   // PA_REE_ONEPASS=0: label columns run-end encoded in two sweeps (count, emit) instead of one
+  bool use_chain = true;     // PA_CHAIN=0: the stack-rank / dictionary chains as ~30 separate launches instead of two persistent kernels
   bool fork_early = false;   // PA_FORK_EARLY=1: the label chain starts right after the header pass and runs beside the hash kernel
   bool forked_early = false;
   bool serial = false;       // PA_SERIAL=1: the label chain stays on the compute stream (per-group timings do not overlap)
@@ -230,6 +235,10 @@ static void fatal_backtrace(int sig) {
   signal(sig, SIG_DFL);
   raise(sig);
 }
+// The one-sweep run-end kernel is persistent (tiles by ticket) and would fill the register file with 4 blocks per SM; asking
+// for 72 KB of (unused) dynamic shared memory holds it at 3, which leaves room for the two blocks per SM of the rank /
+// dictionary chain kernels that run beside it on the high-priority stream.
+static constexpr int kOnepassPadSmem = 72 * 1024;
 static uint64_t pow2_at_least(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
 
 #define CK(expr)                                                        \
@@ -355,6 +364,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   if (const char* hv = getenv("PA_HASH_VARIANT"))
     a->hash_variant = strcmp(hv, "staged") == 0 ? 1 : (strcmp(hv, "direct") == 0 ? 0 : (strcmp(hv, "bulk") == 0 ? 3 : (strcmp(hv, "bulk6x2") == 0 ? 4 : 2)));
   if (cudaFuncSetAttribute(k_hash_insert_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashStagedSmem) != cudaSuccess) return bail(PA_EIO);
+  if (cudaFuncSetAttribute(k_ree_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, kOnepassPadSmem) != cudaSuccess) return bail(PA_EIO);
   if (cudaFuncSetAttribute(k_hash_insert_bulk<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BulkSmem<4, 3>)) != cudaSuccess) return bail(PA_EIO);
   if (cudaFuncSetAttribute(k_hash_insert_bulk<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BulkSmem<6, 2>)) != cudaSuccess) return bail(PA_EIO);
   if (cudaStreamCreateWithFlags(&a->s_copy, cudaStreamNonBlocking) != cudaSuccess) return bail(PA_EIO);
@@ -368,6 +378,8 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   cudaEventCreateWithFlags(&a->ev_join, cudaEventDisableTiming);
   if (const char* sv = getenv("PA_SERIAL")) a->serial = sv[0] == '1';
   if (const char* sv = getenv("PA_FORK_EARLY")) a->fork_early = sv[0] == '1';
+  if (const char* sv = getenv("PA_CHAIN")) a->use_chain = sv[0] != '0';
+  if (const char* sv = getenv("PA_REE_ONEPASS")) a->use_onepass = sv[0] != '0';
   cudaEventCreate(&a->ev_h2d0);
   cudaEventCreate(&a->ev_h2d1);
   cudaEventCreate(&a->ev_d2h0);
@@ -740,6 +752,9 @@ static int pass_plan(pa_agg* a, const MergeDims* md) {
   want(&a->lo.address, Pn * 8); want(&a->lo.line_off, Pn * 4); want(&a->lo.line_size, Pn * 4); want(&a->lo.line_valid, (Pn / 32 + 2) * 4);
   want(&a->lo.line_no, Pn * 8);
   if (md) want(&P.edge_keys, (size_t)ncols * 16, 1);
+  P.tiles = ReeTiles{};
+  P.tiles.n_tiles = (uint32_t)((N + kTileRows - 1) / kTileRows);
+  if (!md) { want(&P.tiles.desc, (size_t)ncols * std::max<uint32_t>(P.tiles.n_tiles, 1) * 8, 1); want(&P.tiles.next, (size_t)ncols * 4, 1); }
   P.col_first.assign(ncols, nullptr); P.col_rank.assign(ncols, nullptr); P.col_bits.assign(ncols, nullptr); P.col_wp.assign(ncols, nullptr);
   a->tid_slots = nullptr; a->tid_rank = nullptr;
   for (uint32_t c = 0; c < ncols; c++) {
@@ -841,6 +856,12 @@ static int pass_plan(pa_agg* a, const MergeDims* md) {
     if (cp.type == COL_KIND && cp.param != 0) continue;
     rg.g[rg.n++] = ReeGroup{cp.type, c, cp.param};
   }
+  P.rg_single = ReeGroups{};
+  P.rg_kind = ReeGroups{};
+  for (uint32_t i = 0; i < rg.n; i++) {
+    if (rg.g[i].type == COL_KIND) P.rg_kind.g[P.rg_kind.n++] = rg.g[i];
+    else P.rg_single.g[P.rg_single.n++] = rg.g[i];
+  }
   int rcu = upload_descriptors(a, jobs.data(), jobs.size() * sizeof(FoJob), rc.data(), rc.size() * sizeof(ReeCol));
   if (rcu) return rcu;
   ra.cols = a->d_cols.as<ReeCol>();
@@ -929,6 +950,19 @@ static int pass_rank_single(pa_agg* a) {
   StackSlot* tab = a->d_table.as<StackSlot>();
   const int G = a->G;
   CK(cudaEventRecord(a->tm[T_RANK].a, s));
+  if (a->use_chain && !P.v1) {  // one persistent kernel: 5 grid barriers instead of 7 dependent launches
+    RankChainArgs ra{};
+    ra.tab = tab; ra.claimed = P.claimed; ra.ctr = ctr; ra.rowbits = P.rowbits; ra.row_wprefix = P.row_wprefix; ra.n_words = (uint32_t)((N + 31) / 32);
+    ra.nframes = a->d_nfr.as<uint16_t>(); ra.uniq_row = a->d_uniq_row.as<uint32_t>(); ra.uniq_slot = P.uniq_slot; ra.uniq_size = P.uniq_size;
+    ra.partial32 = a->d_partial.as<uint32_t>(); ra.partial64 = (unsigned long long*)(a->d_partial.as<uint8_t>() + 65536);
+    ra.n_rows = (uint32_t)N; ra.slot_of_row = a->d_slot.as<uint32_t>(); ra.st_offsets = a->d_stoff.as<int>(); ra.st_sizes = a->d_stsize.as<int>();
+    ra.frames = a->src_frames; ra.frame_off = a->d_foff.as<unsigned long long>(); ra.n_frames_registered = P.n_frames;
+    ra.ustream = a->d_ustream.as<uint32_t>(); ra.loc_first = a->loc_first;
+    k_rank_chain<<<a->sms * 2, kThreads, 0, s>>>(ra);
+    a->tm[T_RANK].launches += 1;
+    CK(cudaEventRecord(a->tm[T_RANK].b, s));
+    return PA_OK;
+  }
   const int Gw = small_grid(a, N / 32 + 1), Gu = small_grid(a, std::min<uint64_t>(N, P.cap / 2));
   k_stack_bits<<<Gu, kThreads, 0, s>>>(tab, P.claimed, &ctr->n_claimed, P.rowbits);
   launch_scan(a, WordsF{P.rowbits, P.row_wprefix, (uint32_t)((N + 31) / 32), &ctr->n_unique}, 1, a->tm[T_RANK], Gw, s, a->d_partial);
@@ -959,7 +993,15 @@ static int pass_locations(pa_agg* a) {
   const size_t Pn = P.Pn, S = P.S, FN = P.FN;
   CK(cudaEventRecord(a->tm[T_LOC].a, s));
   FrameTable ftd{(const unsigned long long*)a->m_addr.ptr(), a->m_type.ptr(), a->m_map.ptr(), a->m_bid.ptr(), (const unsigned long long*)a->m_line.ptr(), a->m_func.ptr()};
-  if (!P.v1) {  // v1 carries no locations in the sample record
+  if (!P.v1 && a->use_chain && !P.merged) {  // one persistent kernel: 21 grid barriers instead of 24 dependent launches
+    LocChainArgs la{};
+    la.jobs = djobs; la.j_loc = P.j_loc; la.j_type = P.j_type; la.j_file = P.j_file; la.ctr = ctr;
+    la.loc_order = a->loc_order; la.ft = ftd; la.lo = a->lo;
+    la.fn_order = a->fn_order; la.fn_file_cid = a->m_fnfile.ptr(); la.file_key = a->sd_keys[3];
+    la.partial = a->d_partial.as<uint32_t>();
+    k_loc_chain<<<a->sms * 2, kThreads, 0, s>>>(la);
+    a->tm[T_LOC].launches += 1;
+  } else if (!P.v1) {  // v1 carries no locations in the sample record
     run_fo_jobs(a, djobs, P.j_loc, 1, false, a->tm[T_LOC], std::min<uint64_t>(P.NI, P.merged ? P.NI : P.cap * 32), Pn, true, s, a->d_partial);  // location index per unique-stack frame (in place over the gathered stream)
     launch_scan(a, LocLinesF{ctr, ctr, a->loc_order, ftd, a->lo}, 1, a->tm[T_LOC], small_grid(a, Pn), s, a->d_partial);
     k_line_validity<<<std::max(1, std::min(G, (int)(Pn / 256 + 1))), kThreads, 0, s>>>(ctr, a->lo.line_size, a->lo.line_valid);
@@ -987,12 +1029,30 @@ static int pass_labels_count(pa_agg* a, cudaStream_t s) {
     a->tm[T_LABELS].launches++;
   }
   if (P.v1) { k_kind_ranks<<<1, 32, 0, s>>>(a->v1_first_kind, a->d_kindtab.as<uint32_t>(), a->v1_kindrank, a->v1_kind_order, a->v1_n_kind_dict); a->tm[T_LABELS].launches++; }
+  if (a->use_onepass && !P.merged) return PA_OK;  // single aggregator: dictionary ranks next, then one sweep (pass_labels_onepass)
   const int Gr = a->sms * 8;  // latency-bound passes: fill every warp slot
   const dim3 ree_grid(Gr, P.rg.n);
   if (P.merged) k_ree_col<false, true><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);  // run counts (+ this shard's border keys)
   else k_ree_col<false, false><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);
-  k_ree_scan_partials<<<P.ncols, kThreads, 0, s>>>(P.ra, Gr * kWarps);
+  k_ree_scan_partials<<<P.ncols, kThreads, 0, s>>>(P.ra, Gr * kWarps, 0u);
   a->tm[T_LABELS].launches += 2;
+  return PA_OK;
+}
+// single aggregator: every label column (and the v1 stacktrace_id / timestamp columns) in ONE sweep with decoupled look-back;
+// the kind-derived group (one shared key, almost always a single run) keeps its count / scan / emit form
+static int pass_labels_onepass(pa_agg* a, cudaStream_t s) {
+  Pass& P = a->P;
+  const int Gr = a->sms * 8;
+  // tiles are handed out by ticket, so the grid only has to fill the machine once (56 registers: 4 blocks per SM)
+  if (P.rg_single.n) { k_ree_onepass<<<dim3((unsigned)std::max(1, std::min(Gr / 2, (int)(P.tiles.n_tiles / kWarps + 1))), P.rg_single.n), kThreads, a->serial ? 0 : kOnepassPadSmem, s>>>(P.ra, P.rg_single, P.tiles); a->tm[T_LABELS].launches++; }
+  if (P.rg_kind.n) {
+    const dim3 kg(a->sms * 4, 1);
+    k_ree_col<false, false><<<kg, kThreads, 0, s>>>(P.ra, P.rg_kind);
+    k_ree_scan_partials<<<8, kThreads, 0, s>>>(P.ra, (int)kg.x * kWarps, P.nlab);
+    k_ree_col<true, false><<<kg, kThreads, 0, s>>>(P.ra, P.rg_kind);
+    a->tm[T_LABELS].launches += 3;
+  }
+  CK(cudaEventRecord(a->tm[T_LABELS].b, s));
   return PA_OK;
 }
 static int pass_label_dicts(pa_agg* a, cudaStream_t s, DBuf& partial) {
@@ -1052,7 +1112,7 @@ static int process_once(pa_agg* a) {
   if ((rc = pass_locations(a))) return rc;
   if ((rc = pass_labels_count(a, s2))) return rc;
   if ((rc = pass_label_dicts(a, s2, fork ? a->d_partial2 : a->d_partial))) return rc;
-  if ((rc = pass_labels_emit(a, s2))) return rc;
+  if ((rc = a->use_onepass ? pass_labels_onepass(a, s2) : pass_labels_emit(a, s2))) return rc;
   if (fork) { CK(cudaEventRecord(a->ev_join, s2)); CK(cudaStreamWaitEvent(s, a->ev_join, 0)); }
   return pass_finish(a);
 }
