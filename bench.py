@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="rows of the batch timed on the CPU port for cpu_baseline (0 = the whole batch, the default)")
     ap.add_argument("--ref-sample", type=int, default=0, help="rows per step of the --impl reference arm (0 = the whole batch, the default)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-u32", action="store_true", help="skip the narrow-ring (uint32 frame ids) leg")
     ap.add_argument("--no-host-shim", action="store_true", help="skip the producer-side measurements (pa_agg_submit from pageable memory, C++ ReportTraceEvent mirror)")
     ap.add_argument("--stream", type=int, default=0, metavar="WINDOWS",
                     help="streaming mode (BASELINE config 5): WINDOWS back-to-back windows per GPU through two alternating aggregators, "
@@ -211,10 +212,10 @@ def run_stream(args, rank, world, local):
     w = synth.config5_part(rank, world, rows_per_gpu=args.stream_rows, hash_mode=mode)
     aggs = []
     for _ in range(2):
-        a = lib.from_workload(w, device=local, max_samples=w.n, max_frames=w.n_frame_ids, chunk_samples=1 << 20)
-        for _ in range(2):  # fill both ring buffers of this instance once
-            lib.load(a, w)
-            a.flush()
+        # one ring buffer per instance (the replay never ingests while a flush is in flight): 2 x 27 GB pinned per GPU at config 5
+        a = lib.from_workload(w, device=local, max_samples=w.n, max_frames=w.n_frame_ids, chunk_samples=1 << 20, flags=abi.PA_CFG_SINGLE_RING)
+        lib.load(a, w)
+        a.flush()
         aggs.append(a)
     results = [[], []]
 
@@ -462,6 +463,45 @@ def main():
         sr = a.stacktraces(ids)
         v1_st = {"ids": sr.n_rows, "locations": sr.n_locations, "gpu_ms": sr.gpu_ms, "d2h_ms": sr.d2h_ms, "host_ms": sr.host_ms,
                  "wall_ms": 1e3 * (time.perf_counter() - t1), "ipc_bytes": sr.ipc_len, "gpu_launches": sr.gpu_launches}
+    # ---- the same batch through a NARROW ring (pa_agg_config.frame_id_bytes = 4: frame ids are dense registration indices, so
+    # uint32 carries them; stack ids and every output byte are unchanged). Reported beside the headline, which keeps the
+    # uint64 ring: half the PCIe bytes end to end, half the HBM bytes for the hash kernel.
+    u32 = None
+    if rank == 0 and not provided and not args.no_u32 and args.schema == "v2":
+        try:
+            from parca_agent_b200 import abi as _abi
+            a32 = lib.from_workload(w, device=local, max_samples=w.n, max_frames=w.n_frame_ids, chunk_samples=1 << 20, frame_id_bytes=4,
+                                    flags=_abi.PA_CFG_SINGLE_RING)
+            lib.load(a32, w)
+            a32.stage()
+            for _ in range(args.warmup):
+                a32.process()
+            ms32, hash32 = [], []
+            for _ in range(args.steps):
+                a32.process()
+                ms32.append(a32.kernel_ms("total")[0])
+                hash32.append(a32.kernel_ms("hash")[0])
+            a32.collect()
+            t32 = []
+            for i in range(3):
+                lib.load(a32, w)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                r32 = a32.flush()
+                torch.cuda.synchronize()
+                if i:
+                    t32.append(time.perf_counter() - t1)
+            peak32, _ = measured_peak()
+            hb32 = w.n * F * 4 + w.n * 16
+            u32 = {"value": w.n * len(ms32) / (float(np.sum(ms32)) / 1e3), "unit": "samples/s", "ms_per_step": float(np.mean(ms32)),
+                   "hash_kernel": {"kernel": "k_hash_insert_wide32", "ms": float(np.mean(hash32)), "algorithmic_bytes": hb32,
+                                   "achieved_gbs": hb32 / (float(np.mean(hash32)) * 1e-3) / 1e9, "frac_of_hbm_peak": hb32 / (float(np.mean(hash32)) * 1e-3) / 1e9 / peak32},
+                   "e2e": {"value": w.n * len(t32) / float(np.sum(t32)), "unit": "samples/s", "h2d_bytes_per_step": int(w.n * 64 + w.n_frame_ids * 4),
+                           "d2h_bytes_per_step": int(r32.ipc_len), "stages_ms_last_step": {"h2d_ms": r32.h2d_ms, "gpu_ms": r32.gpu_ms, "d2h_ms": r32.d2h_ms, "host_ms": r32.host_ms}},
+                   "ipc_sha256_equals_u64_ring": hashlib.sha256(r32.ipc).hexdigest() == gpu_digest}
+            a32.close()
+        except Exception as e:  # noqa: BLE001
+            u32 = {"error": repr(e)[:300]}
     # ---- the producer side (judge's question: what does the host shim cost?). (1) pa_agg_submit from ordinary (unpinned)
     # memory in 64k-row batches + flush, everything timed: the copy into the pinned ring is now inside the region.
     # (2) the C++ mirror of ReportTraceEvent (per-PID labels, comm interning, per-trace frame-id cache, batched submit)
@@ -539,6 +579,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
                     "steps": len(e2e_times), "stages_ms_last_step": stage_ms},
             "cpu_baseline": cpu,
+            "u32_ring": u32,
             "host_shim": host_shim,
             "clocks": clk,
             "result": {"rows": res.n_rows, "unique_stacks": res.n_unique_stacks, "locations": res.n_locations, "functions": res.n_functions,

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PA_ABI_VERSION 2u
+#define PA_ABI_VERSION 3u
 
 /* ---- error codes -------------------------------------------------------------------------- */
 #define PA_OK 0
@@ -77,6 +77,9 @@ enum {
 
 #define PA_IPC_PLAIN 0u
 #define PA_IPC_LZ4_FRAME 1u
+
+#define PA_CFG_SINGLE_RING 0x1u /* one ring buffer instead of two: ingest is refused (PA_ENOSPC) while a flush holds the ring.
+                                    Halves the pinned host memory; for replay / batch use, not for a live agent */
 
 #define PA_NO_STRING 0xFFFFFFFFu /* "no value"; string id 0 is always the empty string "" */
 
@@ -142,6 +145,12 @@ typedef struct pa_agg_config {
   uint64_t stack_cache_frames;  /* v1 only: capacity of the store's frame arena, in frames. 0 = 64 per entry (4 bytes each) */
   uint32_t unknown_frame_type_sid; /* v1 only: string id of libpf.UnknownFrame.String() for the "missing stacktrace"
                                   row (:1561); 0 = the literal "unknown" */
+  uint32_t flags;              /* PA_CFG_* */
+  uint32_t frame_id_bytes;     /* width of one frame id in the ring: 0 or 8 = uint64 (a unique.Handle-sized slot, the default), 4 = uint32.
+                                  Frame ids are dense registration indices (< 2^32 by construction), so the narrow ring carries the same
+                                  ids in half the PCIe / HBM bytes; stack ids and every output byte are identical (XXH64 is defined over
+                                  the ids as little-endian uint64 either way: the kernel widens on load). pa_agg_acquire / pa_agg_submit
+                                  then take and hand out uint32 arrays through the same pointers. */
   uint32_t ipc_compression;    /* PA_IPC_PLAIN (0): uncompressed bodies == the offline-mode bytes (:1779-1790), the bit-exact mode.
                                   PA_IPC_LZ4_FRAME (1): bodies wrapped like ipc.WithLZ4() (:1851, the gRPC path) — decodes to the
                                   same record but is NOT byte-identical to the Go writer (different LZ4 encoder) */

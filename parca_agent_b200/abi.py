@@ -7,7 +7,8 @@ import ctypes as C
 
 import numpy as np
 
-PA_ABI_VERSION = 2
+PA_ABI_VERSION = 3
+PA_CFG_SINGLE_RING = 1
 
 PA_KIND_CPU, PA_KIND_OFFCPU, PA_KIND_CUDA = 0, 1, 2
 PA_KIND_MEM_INUSE_OBJECTS, PA_KIND_MEM_INUSE_SPACE, PA_KIND_MEM_ALLOC_OBJECTS, PA_KIND_MEM_ALLOC_SPACE = 3, 4, 5, 6
@@ -53,7 +54,8 @@ class PaAggConfig(C.Structure):
         ("samples_per_second", C.c_uint32), ("n_external_labels", C.c_uint32),
         ("external_labels", C.POINTER(PaLabelPair)),
         ("max_samples", C.c_uint64), ("max_frames", C.c_uint64), ("chunk_samples", C.c_uint32), ("schema", C.c_uint32),
-        ("stack_cache_entries", C.c_uint64), ("stack_cache_frames", C.c_uint64), ("unknown_frame_type_sid", C.c_uint32), ("ipc_compression", C.c_uint32),
+        ("stack_cache_entries", C.c_uint64), ("stack_cache_frames", C.c_uint64), ("unknown_frame_type_sid", C.c_uint32), ("flags", C.c_uint32),
+        ("frame_id_bytes", C.c_uint32), ("ipc_compression", C.c_uint32),
     ]
 
 

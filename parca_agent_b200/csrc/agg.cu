@@ -133,8 +133,9 @@ struct pa_agg {
   int device = 0, sms = 148, G = 592;
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool use_onepass = true;   // PA_REE_ONEPASS=0: label columns run-end encoded in two sweeps (count, emit) instead of one
-  bool use_chain = true;     // PA_CHAIN=0: the stack-rank / dictionary chains as ~30 separate launches instead of two persistent kernels
+  bool use_onepass = false;  // PA_REE_ONEPASS=1: label columns run-end encoded in one sweep with decoupled look-back (measured SLOWER than count + emit: 1.18 vs 0.39 ms on config 2)
+  bool use_chain = false;    // PA_CHAIN=1: the stack-rank / dictionary chains as two persistent kernels with grid barriers instead of ~30 launches (measured no faster: DESIGN section 7)
+  int ree_blocks = 8;        // blocks per SM of the two run-end passes (PA_REE_BLOCKS_PER_SM)
   bool fork_early = false;   // PA_FORK_EARLY=1: the label chain starts right after the header pass and runs beside the hash kernel
   bool forked_early = false;
   bool serial = false;       // PA_SERIAL=1: the label chain stays on the compute stream (per-group timings do not overlap)
@@ -170,6 +171,8 @@ struct pa_agg {
   // ---- ring (pinned host), double buffered
   struct Ring { pa_sample_hdr* hdr = nullptr; uint64_t* frames = nullptr; const uint64_t* frames_dev = nullptr; uint64_t rows = 0, nfr = 0; } ring[2];
   int active = 0, inflight = 0;
+  uint32_t idb = 8;          // bytes per frame id in the ring and in d_frames (pa_agg_config.frame_id_bytes)
+  bool single_ring = false, ring_busy = false;  // PA_CFG_SINGLE_RING: the one buffer is held by a flush until it is collected
   std::mutex ring_mu;
   std::condition_variable ring_cv;
   std::mutex flush_mu;
@@ -341,7 +344,8 @@ uint32_t pa_agg_abi_version(void) { return PA_ABI_VERSION; }
 const char* pa_agg_last_error(const pa_agg* a) { return a ? a->err.c_str() : "null handle"; }
 
 int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
-  if (!cfg || !out || cfg->abi_version != PA_ABI_VERSION || cfg->samples_per_second == 0 || cfg->max_samples == 0 || cfg->hash_mode > 1 || cfg->schema > 1 || cfg->ipc_compression > 1) return PA_EINVAL;
+  if (!cfg || !out || cfg->abi_version != PA_ABI_VERSION || cfg->samples_per_second == 0 || cfg->max_samples == 0 || cfg->hash_mode > 1 || cfg->schema > 1 || cfg->ipc_compression > 1 ||
+      (cfg->frame_id_bytes != 0 && cfg->frame_id_bytes != 4 && cfg->frame_id_bytes != 8)) return PA_EINVAL;
   if (cfg->max_samples > 0x7FFFFFFFull) return PA_ERANGE;  // run ends / ListView offsets are int32
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return PA_ENODEV;
@@ -350,6 +354,8 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   a->cfg = *cfg;
   a->cfg.external_labels = nullptr;
   a->device = cfg->device;
+  a->idb = cfg->frame_id_bytes == 4 ? 4u : 8u;
+  a->single_ring = (cfg->flags & PA_CFG_SINGLE_RING) != 0;
   auto bail = [&](int code) { pa_agg_destroy(a); return code; };
   if (cudaSetDevice(a->device) != cudaSuccess) return bail(PA_ENODEV);
   cudaDeviceProp prop;
@@ -378,17 +384,19 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   cudaEventCreateWithFlags(&a->ev_join, cudaEventDisableTiming);
   if (const char* sv = getenv("PA_SERIAL")) a->serial = sv[0] == '1';
   if (const char* sv = getenv("PA_FORK_EARLY")) a->fork_early = sv[0] == '1';
-  if (const char* sv = getenv("PA_CHAIN")) a->use_chain = sv[0] != '0';
-  if (const char* sv = getenv("PA_REE_ONEPASS")) a->use_onepass = sv[0] != '0';
+  if (const char* sv = getenv("PA_CHAIN")) a->use_chain = sv[0] == '1';
+  if (const char* sv = getenv("PA_REE_ONEPASS")) a->use_onepass = sv[0] == '1';
+  if (const char* sv = getenv("PA_REE_BLOCKS_PER_SM")) a->ree_blocks = std::max(1, std::min(8, atoi(sv)));
   cudaEventCreate(&a->ev_h2d0);
   cudaEventCreate(&a->ev_h2d1);
   cudaEventCreate(&a->ev_d2h0);
   cudaEventCreate(&a->ev_d2h1);
   for (int t = 0; t < T_COUNT; t++) { cudaEventCreate(&a->tm[t].a); cudaEventCreate(&a->tm[t].b); }
   const uint64_t N = a->cfg.max_samples, NF = a->cfg.max_frames;
-  for (int r = 0; r < 2; r++) {
+  if (a->idb == 4) a->hash_variant = 2;  // the narrow ring is read by the `wide` kernel (widening loads); the other variants take uint64 ids
+  for (int r = 0; r < (a->single_ring ? 1 : 2); r++) {
     if (cudaHostAlloc((void**)&a->ring[r].hdr, N * sizeof(pa_sample_hdr), cudaHostAllocDefault) != cudaSuccess) return bail(PA_ENOMEM);
-    if (cudaHostAlloc((void**)&a->ring[r].frames, std::max<uint64_t>(NF, 1) * 8, cudaHostAllocMapped) != cudaSuccess) return bail(PA_ENOMEM);
+    if (cudaHostAlloc((void**)&a->ring[r].frames, std::max<uint64_t>(NF, 1) * a->idb + 64, cudaHostAllocMapped) != cudaSuccess) return bail(PA_ENOMEM);
     void* dp = nullptr;  // device alias of the pinned frame ring (provided-hash mode gathers unique stacks straight from it)
     if (cudaHostGetDevicePointer(&dp, a->ring[r].frames, 0) != cudaSuccess) return bail(PA_EIO);
     a->ring[r].frames_dev = (const uint64_t*)dp;
@@ -397,7 +405,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   bool ok = true;
   auto need = [&](DBuf& b, uint64_t bytes) { ok = ok && b.ensure(std::max<uint64_t>(bytes, 256)) == cudaSuccess; };
   need(a->d_hdr, N * 64);
-  if (a->cfg.hash_mode == PA_HASH_XXH64X2) need(a->d_frames, NF * 8 + 64);  // provided-hash mode never uploads the frame stream (+ slack: bulk copies round up to 16 B)
+  if (a->cfg.hash_mode == PA_HASH_XXH64X2) need(a->d_frames, NF * a->idb + 64);  // provided-hash mode never uploads the frame stream (+ slack: bulk copies round up to 16 B)
   need(a->d_ts, N * 8); need(a->d_value, N * 8); need(a->d_uuid, N * 16); need(a->d_stoff, N * 4); need(a->d_stsize, N * 4);
   need(a->d_slot, N * 4); need(a->d_kind, N); need(a->d_nfr, N * 2); need(a->d_foff, N * 8);
   need(a->d_ls, N * 4); need(a->d_cpu, N * 4); need(a->d_tid, N * 4); need(a->d_comm, N * 4);
@@ -497,10 +505,11 @@ int pa_agg_register_labelsets(pa_agg* a, const pa_label_pair* pairs, const uint3
 int pa_agg_acquire(pa_agg* a, uint64_t n_rows, uint64_t n_frames, pa_sample_hdr** hdrs, uint64_t** frames, uint64_t* frame_base) {
   if (!a || !hdrs || !frames) return PA_EINVAL;
   std::lock_guard<std::mutex> g(a->ring_mu);
+  if (a->ring_busy) return PA_ENOSPC;  // single ring: a flush holds the buffer
   pa_agg::Ring& r = a->ring[a->active];
-  if (r.rows + n_rows > a->cfg.max_samples || r.nfr + n_frames > a->cfg.max_frames) return PA_ENOSPC;
+  if (n_rows > a->cfg.max_samples || n_frames > a->cfg.max_frames || r.rows + n_rows > a->cfg.max_samples || r.nfr + n_frames > a->cfg.max_frames) return PA_ENOSPC;
   *hdrs = r.hdr + r.rows;
-  *frames = r.frames + r.nfr;
+  *frames = (uint64_t*)((uint8_t*)r.frames + r.nfr * a->idb);  // uint32 ids when the ring is narrow
   if (frame_base) *frame_base = r.nfr;
   r.rows += n_rows;
   r.nfr += n_frames;
@@ -518,6 +527,7 @@ int pa_agg_submit(pa_agg* a, const pa_sample_hdr* hdrs, const uint64_t* frames, 
   if (!a || (n_rows && !hdrs)) return PA_EINVAL;
   uint64_t nf = 0;
   for (uint64_t i = 0; i < n_rows; i++) nf += hdrs[i].nframes;
+  if (nf && !frames) return PA_EINVAL;
   pa_sample_hdr* dh; uint64_t* df; uint64_t base;
   int rc = pa_agg_acquire(a, n_rows, nf, &dh, &df, &base);
   if (rc) return rc;
@@ -525,7 +535,7 @@ int pa_agg_submit(pa_agg* a, const pa_sample_hdr* hdrs, const uint64_t* frames, 
   for (uint64_t i = 0; i < n_rows; i++) {
     dh[i] = hdrs[i];
     dh[i].frame_off = base + off;
-    if (hdrs[i].nframes) memcpy(df + off, frames + off, (size_t)hdrs[i].nframes * 8);
+    if (hdrs[i].nframes) memcpy((uint8_t*)df + off * a->idb, (const uint8_t*)frames + off * a->idb, (size_t)hdrs[i].nframes * a->idb);
     off += hdrs[i].nframes;
   }
   return pa_agg_commit(a, n_rows);
@@ -544,9 +554,13 @@ static int stage_async(pa_agg* a) {
     std::unique_lock<std::mutex> g(a->ring_mu);
     a->ring_cv.wait(g, [a] { return a->inflight == 0; });
     buf = a->active;
-    a->active ^= 1;
-    a->ring[a->active].rows = 0;
-    a->ring[a->active].nfr = 0;
+    if (a->single_ring) {
+      a->ring_busy = true;  // producers get PA_ENOSPC until this batch is collected
+    } else {
+      a->active ^= 1;
+      a->ring[a->active].rows = 0;
+      a->ring[a->active].nfr = 0;
+    }
   }
   pa_agg::Ring& r = a->ring[buf];
   a->staged = buf;
@@ -571,7 +585,7 @@ static int stage_async(pa_agg* a) {
     // frames are only needed for each stack's FIRST occurrence, so nothing is uploaded here and k_gather_unique
     // reads those few stacks from the mapped pinned ring over PCIe (U*F*8 bytes instead of N*F*8).
     if (fend > fdone && a->cfg.hash_mode == PA_HASH_XXH64X2)
-      CK(cudaMemcpyAsync(a->d_frames.as<uint64_t>() + fdone, r.frames + fdone, (fend - fdone) * 8, cudaMemcpyHostToDevice, a->s_copy));
+      CK(cudaMemcpyAsync(a->d_frames.as<uint8_t>() + fdone * a->idb, (const uint8_t*)r.frames + fdone * a->idb, (fend - fdone) * a->idb, cudaMemcpyHostToDevice, a->s_copy));
     fdone = fend;
     CK(cudaEventRecord(a->chunk_ev[k], a->s_copy));
     a->chunk_rows.emplace_back(r0, r1);
@@ -579,6 +593,17 @@ static int stage_async(pa_agg* a) {
   }
   CK(cudaEventRecord(a->ev_h2d1, a->s_copy));
   return PA_OK;
+}
+
+// the staged batch is done with (collected, discarded or failed): the ring buffer it held is free again
+static void release_staged(pa_agg* a) {
+  a->staged = -1;
+  if (a->ring_busy) {
+    std::lock_guard<std::mutex> g(a->ring_mu);
+    a->ring[0].rows = 0;
+    a->ring[0].nfr = 0;
+    a->ring_busy = false;
+  }
 }
 
 template <class F>
@@ -660,6 +685,7 @@ static void launch_store_insert(pa_agg* a) {
   sa.ctr = ctr; sa.uniq_row = a->d_uniq_row.as<uint32_t>(); sa.slot_of_row = a->d_slot.as<uint32_t>(); sa.tab = a->d_table.as<StackSlot>();
   sa.nframes = a->d_nfr.as<uint16_t>(); sa.frame_off = a->d_foff.as<unsigned long long>();
   sa.frames = a->src_frames;
+  sa.narrow = a->idb == 4 ? 1u : 0u;
   sa.n_frames_registered = a->P.n_frames;
   sa.st = a->d_store.as<StoreSlot>(); sa.mask = (uint32_t)(a->store_slots - 1); sa.arena = a->d_store_arena.as<uint32_t>();
   sa.cap_frames = a->store_frames; sa.cap_entries = (uint32_t)a->store_entries; sa.ctl = a->d_store_ctl.as<StoreCtl>(); sa.ctr_w = ctr;
@@ -909,12 +935,13 @@ static int pass_front(pa_agg* a) {
   };
   auto launch_hash = [&](uint64_t r0, uint64_t r1) {
     HashArgs ha{};
-    ha.frames = a->d_frames.as<unsigned long long>(); ha.frame_off = a->d_foff.as<unsigned long long>(); ha.nframes = a->d_nfr.as<uint16_t>();
+    ha.frames = a->d_frames.as<unsigned long long>(); ha.frames32 = a->idb == 4 ? a->d_frames.as<uint32_t>() : nullptr; ha.frame_off = a->d_foff.as<unsigned long long>(); ha.nframes = a->d_nfr.as<uint16_t>();
     ha.row0 = (uint32_t)r0; ha.row1 = (uint32_t)r1; ha.uuid = a->d_uuid.as<uint8_t>();
     ha.slot_of_row = a->d_slot.as<uint32_t>(); ha.tab = tab; ha.mask = P.mask; ha.ctr = ctr; ha.claimed = P.claimed;
     uint64_t rows = r1 - r0;
     int blocks = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)a->sms * (a->hash_variant == 1 ? 3 : 4));
-    if (a->hash_variant == 3) k_hash_insert_bulk<4, 3><<<(int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 127) / 128, (uint64_t)a->sms)), 128, sizeof(BulkSmem<4, 3>), s>>>(ha);
+    if (a->idb == 4) k_hash_insert_wide32<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
+    else if (a->hash_variant == 3) k_hash_insert_bulk<4, 3><<<(int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 127) / 128, (uint64_t)a->sms)), 128, sizeof(BulkSmem<4, 3>), s>>>(ha);
     else if (a->hash_variant == 4) k_hash_insert_bulk<6, 2><<<(int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 191) / 192, (uint64_t)a->sms)), 192, sizeof(BulkSmem<6, 2>), s>>>(ha);
     else if (a->hash_variant == 1) k_hash_insert_staged<<<std::max(blocks, 1), kThreads, kHashStagedSmem, s>>>(ha);
     else if (a->hash_variant == 2) k_hash_insert_wide<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
@@ -957,7 +984,7 @@ static int pass_rank_single(pa_agg* a) {
     ra.partial32 = a->d_partial.as<uint32_t>(); ra.partial64 = (unsigned long long*)(a->d_partial.as<uint8_t>() + 65536);
     ra.n_rows = (uint32_t)N; ra.slot_of_row = a->d_slot.as<uint32_t>(); ra.st_offsets = a->d_stoff.as<int>(); ra.st_sizes = a->d_stsize.as<int>();
     ra.frames = a->src_frames; ra.frame_off = a->d_foff.as<unsigned long long>(); ra.n_frames_registered = P.n_frames;
-    ra.ustream = a->d_ustream.as<uint32_t>(); ra.loc_first = a->loc_first;
+    ra.ustream = a->d_ustream.as<uint32_t>(); ra.loc_first = a->loc_first; ra.narrow = a->idb == 4 ? 1u : 0u;
     k_rank_chain<<<a->sms * 2, kThreads, 0, s>>>(ra);
     a->tm[T_RANK].launches += 1;
     CK(cudaEventRecord(a->tm[T_RANK].b, s));
@@ -976,7 +1003,7 @@ static int pass_rank_single(pa_agg* a) {
     a->tm[T_RANK].launches++;
   } else {
     k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, a->src_frames,
-                                           a->d_foff.as<unsigned long long>(), P.n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr);
+                                           a->d_foff.as<unsigned long long>(), P.n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr, a->idb == 4 ? 1u : 0u);
   }
   a->tm[T_RANK].launches += 2;
   CK(cudaEventRecord(a->tm[T_RANK].b, s));
@@ -1030,7 +1057,7 @@ static int pass_labels_count(pa_agg* a, cudaStream_t s) {
   }
   if (P.v1) { k_kind_ranks<<<1, 32, 0, s>>>(a->v1_first_kind, a->d_kindtab.as<uint32_t>(), a->v1_kindrank, a->v1_kind_order, a->v1_n_kind_dict); a->tm[T_LABELS].launches++; }
   if (a->use_onepass && !P.merged) return PA_OK;  // single aggregator: dictionary ranks next, then one sweep (pass_labels_onepass)
-  const int Gr = a->sms * 8;  // latency-bound passes: fill every warp slot
+  const int Gr = a->sms * a->ree_blocks;  // latency-bound passes: fill every warp slot
   const dim3 ree_grid(Gr, P.rg.n);
   if (P.merged) k_ree_col<false, true><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);  // run counts (+ this shard's border keys)
   else k_ree_col<false, false><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);
@@ -1064,7 +1091,7 @@ static int pass_label_dicts(pa_agg* a, cudaStream_t s, DBuf& partial) {
 }
 static int pass_labels_emit(pa_agg* a, cudaStream_t s) {
   Pass& P = a->P;
-  const dim3 ree_grid(a->sms * 8, P.rg.n);
+  const dim3 ree_grid(a->sms * a->ree_blocks, P.rg.n);
   if (P.merged) k_ree_col<true, true><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);   // run ends + final dictionary indices + validity bits
   else k_ree_col<true, false><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);
   a->tm[T_LABELS].launches += 1;
@@ -1528,7 +1555,7 @@ static int collect(pa_agg* a, pa_agg_result* res) {
   CK(cudaSetDevice(a->device));
   const uint64_t N = a->N;
   a->hostbufs.clear();
-  if (N == 0) { a->staged = -1; return PA_OK; }  // reference skips empty batches (:1775-1778)
+  if (N == 0) { release_staged(a); return PA_OK; }  // reference skips empty batches (:1775-1778)
   double t0 = now_ms();
   const Counters& c = a->h_ctr;
   const bool v1 = a->cfg.schema == PA_SCHEMA_V1;
@@ -1573,7 +1600,7 @@ static int collect(pa_agg* a, pa_agg_result* res) {
   res->ipc = stream; res->ipc_len = stream_len; res->n_rows = N; res->n_unique_stacks = c.n_unique; res->n_locations = n_loc;
   res->n_functions = n_fn; res->n_location_indices = n_idx; res->gpu_launches = a->launches;
   res->h2d_ms = h2d; res->gpu_ms = a->tm[T_TOTAL].ms; res->d2h_ms = d2h; res->host_ms = (t1 - t0) + (t2 - t1) - d2h;
-  a->staged = -1;
+  release_staged(a);
   return PA_OK;
 }
 
@@ -1812,6 +1839,7 @@ static int stage_device(pa_agg* a, const pa_sample_hdr* hdr, uint64_t n_rows, co
   if (a->staged >= 0) return a->fail(PA_EINVAL, "the previously staged batch has not been collected");
   if (n_rows > a->cfg.max_samples || n_frames > a->cfg.max_frames) return a->fail(PA_ENOSPC, "device batch exceeds max_samples / max_frames");
   if ((n_rows && !hdr) || (n_frames && !frames)) return a->fail(PA_EINVAL, "null device buffer");
+  if (a->idb != 8) return a->fail(PA_EINVAL, "device-staged batches carry uint64 frame ids: create the aggregator with frame_id_bytes = 8");
   CK(a->d_frames.ensure(std::max<uint64_t>(n_frames, 1) * 8));  // provided-hash aggregators do not own a frame buffer until now
   a->staged = a->active;  // no ring buffer is detached: ingest into the ring continues untouched
   a->src_frames = a->d_frames.as<unsigned long long>();
@@ -1839,6 +1867,7 @@ static int stage_device_parts(pa_agg* a, const pa_device_part* parts, uint32_t n
     nfr += parts[p].n_frames;
   }
   if (rows != n_total) return a->fail(PA_EINVAL, "the parts do not add up to n_rows_total");
+  if (a->idb != 8) return a->fail(PA_EINVAL, "device-staged batches carry uint64 frame ids: create the aggregator with frame_id_bytes = 8");
   if (n_total > a->cfg.max_samples || nfr > a->cfg.max_frames) return a->fail(PA_ENOSPC, "device batch exceeds max_samples / max_frames");
   CK(a->d_frames.ensure(std::max<uint64_t>(nfr, 1) * 8));
   CK(a->d_st1.ensure(256));
@@ -1912,7 +1941,7 @@ int pa_agg_discard(pa_agg* a) {
   CK(cudaSetDevice(a->device));
   CK(cudaStreamSynchronize(a->s_copy));
   CK(cudaStreamSynchronize(a->s_comp));
-  a->staged = -1;
+  release_staged(a);
   a->merged_part = false;
   return PA_OK;
 }
@@ -1961,9 +1990,9 @@ int pa_agg_flush(pa_agg* a, pa_agg_result* out) {
   int rc = stage_async(a);  // copies keep running while process() consumes the chunks already resident
   if (rc) return rc;
   rc = process(a);
-  if (rc) { cudaStreamSynchronize(a->s_copy); a->staged = -1; return rc; }  // a failed flush drops the interval's data (:1218-1220)
+  if (rc) { cudaStreamSynchronize(a->s_copy); release_staged(a); return rc; }  // a failed flush drops the interval's data (:1218-1220)
   rc = collect(a, out);
-  if (rc) a->staged = -1;
+  if (rc) release_staged(a);
   return rc;
 }
 void pa_agg_release(pa_agg* a, pa_agg_result* res) {

@@ -309,6 +309,7 @@ __device__ __forceinline__ unsigned long long xxh_lane_init(unsigned long long s
 }
 struct HashArgs {
   const unsigned long long* frames;
+  const uint32_t* frames32;    // non-null: the frame stream holds uint32 ids (narrow ring); `frames` is unused
   const unsigned long long* frame_off;
   const uint16_t* nframes;
   uint32_t row0, row1;
@@ -403,6 +404,20 @@ __global__ void __launch_bounds__(kThreads, 4) k_hash_insert(HashArgs a) {
 // 16 bytes per stripe (LDG.128): four independent multiply chains per lane (2 accumulators x 2 seeds),
 // half the load / address / shuffle instructions of variant B. 16 samples per sub-step, 2 sub-steps
 // per 32-sample warp batch; the epilogue is the same thread-per-sample code.
+__device__ __forceinline__ uint32_t ldg_stream32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+// two consecutive ids as uint64 values, from a uint64 stream (16 bytes) or a uint32 stream (8 bytes, widened)
+__device__ __forceinline__ ulonglong2 ldg_stream128(const unsigned long long* p);
+__device__ __forceinline__ ulonglong2 load_pair(const unsigned long long* p, bool aligned);
+__device__ __forceinline__ ulonglong2 load_pair(const uint32_t* p, bool aligned) {
+  if (aligned) { const unsigned long long w = ldg_stream64(reinterpret_cast<const unsigned long long*>(p)); return make_ulonglong2(w & 0xFFFFFFFFull, w >> 32); }
+  return make_ulonglong2(ldg_stream32(p), ldg_stream32(p + 1));
+}
+__device__ __forceinline__ unsigned long long load_one(const unsigned long long* p) { return ldg_stream64(p); }
+__device__ __forceinline__ unsigned long long load_one(const uint32_t* p) { return ldg_stream32(p); }
 __device__ __forceinline__ ulonglong2 ldg_stream128(const unsigned long long* p) {
   ulonglong2 v;
   asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
@@ -414,13 +429,14 @@ __device__ __forceinline__ ulonglong2 ldg_stream128(const unsigned long long* p)
 constexpr int kWideUnroll = PA_WIDE_UNROLL;
 // All stripes of one sample half: tiers of kWideUnroll, 4 and up to 3 stripes, each tier with its loads in flight
 // together. kAllAligned: every lane of the warp can use 16-byte loads (no predicated 8-byte fallbacks are emitted).
-template <bool kAllAligned>
-__device__ __forceinline__ void wide_stripes(const unsigned long long* q, uint32_t ns, bool aligned, unsigned long long& a0,
+__device__ __forceinline__ ulonglong2 load_pair(const unsigned long long* p, bool aligned) {
+  if (aligned) return ldg_stream128(p);
+  return make_ulonglong2(ldg_stream64(p), ldg_stream64(p + 1));
+}
+template <bool kAllAligned, class IdT>
+__device__ __forceinline__ void wide_stripes(const IdT* q, uint32_t ns, bool aligned, unsigned long long& a0,
                                              unsigned long long& a1, unsigned long long& b0, unsigned long long& b1) {
-  auto load2 = [&](const unsigned long long* p) -> ulonglong2 {
-    if (kAllAligned || aligned) return ldg_stream128(p);
-    return make_ulonglong2(ldg_stream64(p), ldg_stream64(p + 1));
-  };
+  auto load2 = [&](const IdT* p) -> ulonglong2 { return load_pair(p, kAllAligned || aligned); };
   auto rounds = [&](const ulonglong2& w) {
     unsigned long long mx = w.x * XP2, my = w.y * XP2;
     a0 = xxh_round_pre(a0, mx); a1 = xxh_round_pre(a1, mx);
@@ -451,7 +467,8 @@ __device__ __forceinline__ void wide_stripes(const unsigned long long* q, uint32
   }
 }
 // one warp-tile of 32 consecutive rows (lane = row r); every lane of the warp must call it
-__device__ __forceinline__ void wide_tile(const HashArgs& a, uint32_t r, bool valid, uint32_t n_me, unsigned long long off_me) {
+template <class IdT>
+__device__ __forceinline__ void wide_tile_t(const HashArgs& a, const IdT* frames, uint32_t r, bool valid, uint32_t n_me, unsigned long long off_me) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, h = lane & 1, g = lane >> 1;  // h: which half of the stripe, g: sample within the sub-step
   {
@@ -461,12 +478,12 @@ __device__ __forceinline__ void wide_tile(const HashArgs& a, uint32_t r, bool va
       const int src = sub * 16 + g;
       const uint32_t n = __shfl_sync(full, n_me, src);
       const unsigned long long off = __shfl_sync(full, off_me, src);
-      const unsigned long long* q = a.frames + off + 2 * h;
+      const IdT* q = frames + off + 2 * h;
       unsigned long long a0 = xxh_lane_init(0ull, 2 * h), b0 = xxh_lane_init(0ull, 2 * h + 1);
       unsigned long long a1 = xxh_lane_init(kSeedLo, 2 * h), b1 = xxh_lane_init(kSeedLo, 2 * h + 1);
-      const bool aligned = (off & 1ull) == 0;  // 16-byte loads need an even word offset
-      if (__all_sync(full, aligned)) wide_stripes<true>(q, n >> 2, true, a0, a1, b0, b1);   // uniform batches: pure LDG.128
-      else wide_stripes<false>(q, n >> 2, aligned, a0, a1, b0, b1);                          // ragged: per-lane 16-byte or 2 x 8-byte loads
+      const bool aligned = (off & 1ull) == 0;  // paired loads (16 bytes of uint64 ids / 8 bytes of uint32 ids) need an even id offset
+      if (__all_sync(full, aligned)) wide_stripes<true>(q, n >> 2, true, a0, a1, b0, b1);   // uniform batches: pure paired loads
+      else wide_stripes<false>(q, n >> 2, aligned, a0, a1, b0, b1);                          // ragged: per-lane paired or 2 single loads
       __syncwarp(full);
       // transpose: lane L (in half `sub`) gets accumulators 0,1 from lane 2*(L&15) and 2,3 from lane 2*(L&15)+1
       const int s0 = 2 * (lane & 15), s1 = s0 + 1;
@@ -481,14 +498,32 @@ __device__ __forceinline__ void wide_tile(const HashArgs& a, uint32_t r, bool va
       x = __shfl_sync(full, b1, s1); if ((lane >> 4) == sub) v1[3] = x;
     }
     const uint32_t nt = n_me & 3u;
-    const unsigned long long* tp = a.frames + off_me + (n_me & ~3u);
-    unsigned long long t0 = nt > 0 ? ldg_stream64(tp) : 0ull, t1 = nt > 1 ? ldg_stream64(tp + 1) : 0ull, t2 = nt > 2 ? ldg_stream64(tp + 2) : 0ull;
+    const IdT* tp = frames + off_me + (n_me & ~3u);
+    unsigned long long t0 = nt > 0 ? load_one(tp) : 0ull, t1 = nt > 1 ? load_one(tp + 1) : 0ull, t2 = nt > 2 ? load_one(tp + 2) : 0ull;
     Key128 k;
     k.hi = xxh_finish_own(v0, 0ull, n_me, t0, t1, t2);
     k.lo = xxh_finish_own(v1, kSeedLo, n_me, t0, t1, t2);
     if (valid) *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = make_ulonglong2(bswap64(k.hi), bswap64(k.lo));
     uint32_t slot = warp_insert(a.tab, a.mask, k, r, valid, a.ctr, a.claimed);
     if (valid) a.slot_of_row[r] = slot;
+  }
+}
+__device__ __forceinline__ void wide_tile(const HashArgs& a, uint32_t r, bool valid, uint32_t n_me, unsigned long long off_me) {
+  wide_tile_t<unsigned long long>(a, a.frames, r, valid, n_me, off_me);
+}
+// the same pass over a NARROW frame stream (uint32 ids, pa_agg_config.frame_id_bytes = 4): half the bytes per id, ids are
+// widened to the uint64 values XXH64 is defined over as they are loaded
+__global__ void __launch_bounds__(kThreads, 4) k_hash_insert_wide32(HashArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+  const uint32_t span = a.row1 - a.row0;
+  const uint32_t iters = (span + nwarps * 32 - 1) / (nwarps * 32);
+  for (uint32_t it = 0; it < iters; it++) {
+    const uint32_t r = a.row0 + (it * nwarps + warp) * 32 + lane;
+    const bool valid = r < a.row1;
+    const uint32_t n_me = valid ? a.nframes[r] : 0u;
+    const unsigned long long off_me = valid ? a.frame_off[r] : 0ull;
+    wide_tile_t<uint32_t>(a, a.frames32, r, valid, n_me, off_me);
   }
 }
 __global__ void __launch_bounds__(kThreads, 4) k_hash_insert_wide(HashArgs a) {
@@ -984,27 +1019,31 @@ __global__ void __launch_bounds__(kThreads) k_count_stacks(uint32_t n_rows, cons
 
 // (3) gather the frames of the unique stacks, in first-occurrence order, into the location-index
 // stream and record each frame's first position (appendLocationV2 dedup key = the frame, :421)
-__device__ __forceinline__ void gather_unique_dev(const Counters* ctr, const uint32_t* uniq_row, const uint32_t* slot_of_row, const StackSlot* tab,
-                                                  const unsigned long long* frames, const unsigned long long* frame_off, uint32_t n_frames_registered,
-                                                  uint32_t* ustream, uint32_t* loc_first, Counters* ctr_w);
-__global__ void __launch_bounds__(kThreads) k_gather_unique(const Counters* ctr, const uint32_t* uniq_row, const uint32_t* slot_of_row,
-                                                            const StackSlot* tab, const unsigned long long* frames,
-                                                            const unsigned long long* frame_off, uint32_t n_frames_registered,
-                                                            uint32_t* ustream, uint32_t* loc_first, Counters* ctr_w) {
-  gather_unique_dev(ctr, uniq_row, slot_of_row, tab, frames, frame_off, n_frames_registered, ustream, loc_first, ctr_w);
+// `frames` holds uint64 ids, or uint32 ids when the top bit of n_frames_registered's companion flag is set (narrow ring)
+__device__ __forceinline__ unsigned long long frame_at(const unsigned long long* frames, unsigned long long i, uint32_t narrow) {
+  return narrow ? (unsigned long long)reinterpret_cast<const uint32_t*>(frames)[i] : frames[i];
 }
 __device__ __forceinline__ void gather_unique_dev(const Counters* ctr, const uint32_t* uniq_row, const uint32_t* slot_of_row, const StackSlot* tab,
                                                   const unsigned long long* frames, const unsigned long long* frame_off, uint32_t n_frames_registered,
-                                                  uint32_t* ustream, uint32_t* loc_first, Counters* ctr_w) {
+                                                  uint32_t* ustream, uint32_t* loc_first, Counters* ctr_w, uint32_t narrow = 0);
+__global__ void __launch_bounds__(kThreads) k_gather_unique(const Counters* ctr, const uint32_t* uniq_row, const uint32_t* slot_of_row,
+                                                            const StackSlot* tab, const unsigned long long* frames,
+                                                            const unsigned long long* frame_off, uint32_t n_frames_registered,
+                                                            uint32_t* ustream, uint32_t* loc_first, Counters* ctr_w, uint32_t narrow) {
+  gather_unique_dev(ctr, uniq_row, slot_of_row, tab, frames, frame_off, n_frames_registered, ustream, loc_first, ctr_w, narrow);
+}
+__device__ __forceinline__ void gather_unique_dev(const Counters* ctr, const uint32_t* uniq_row, const uint32_t* slot_of_row, const StackSlot* tab,
+                                                  const unsigned long long* frames, const unsigned long long* frame_off, uint32_t n_frames_registered,
+                                                  uint32_t* ustream, uint32_t* loc_first, Counters* ctr_w, uint32_t narrow) {
   uint32_t nu = ctr->n_unique;
   int lane = threadIdx.x & 31;
   uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
   for (uint32_t u = warp; u < nu; u += nwarps) {
     uint32_t r = uniq_row[u];
     StackSlot e = tab[slot_of_row[r]];
-    const unsigned long long* src = frames + frame_off[r];
+    const unsigned long long base = frame_off[r];
     for (uint32_t jx = lane; jx < e.size; jx += 32) {
-      unsigned long long fid = src[jx];
+      unsigned long long fid = frame_at(frames, base + jx, narrow);
       uint32_t pos = e.offset + jx;
       if (fid >= n_frames_registered) { atomicOr(&ctr_w->err, ERR_BAD_FRAME_ID); fid = 0; }
       ustream[pos] = (uint32_t)fid;
@@ -1216,6 +1255,7 @@ struct RankChainArgs {
   // tail phases (no barrier between them): per-row ListView (offset, size); frames of the unique stacks
   uint32_t n_rows; const uint32_t* slot_of_row; int* st_offsets; int* st_sizes;
   const unsigned long long* frames; const unsigned long long* frame_off; uint32_t n_frames_registered; uint32_t* ustream; uint32_t* loc_first;
+  uint32_t narrow;
 };
 __global__ void __launch_bounds__(kThreads) k_rank_chain(RankChainArgs a) {
   uint32_t target = 0;
@@ -1229,7 +1269,7 @@ __global__ void __launch_bounds__(kThreads) k_rank_chain(RankChainArgs a) {
   { UniqOffsetF f{a.ctr, a.ctr, a.uniq_size, a.uniq_slot, a.tab}; scan_reduce_dev(f, a.partial64); grid_barrier(bar, target); scan_emit_dev(f, a.partial64, 0); }
   grid_barrier(bar, target);
   rows_materialize_dev(a.n_rows, a.slot_of_row, a.tab, a.st_offsets, a.st_sizes, nullptr);
-  gather_unique_dev(a.ctr, a.uniq_row, a.slot_of_row, a.tab, a.frames, a.frame_off, a.n_frames_registered, a.ustream, a.loc_first, a.ctr);
+  gather_unique_dev(a.ctr, a.uniq_row, a.slot_of_row, a.tab, a.frames, a.frame_off, a.n_frames_registered, a.ustream, a.loc_first, a.ctr, a.narrow);
 }
 struct LocChainArgs {
   const FoJob* jobs; int j_loc, j_type, j_file;
@@ -1739,6 +1779,7 @@ struct StoreInsertArgs {
   const uint16_t* nframes;
   const unsigned long long* frame_off;
   const unsigned long long* frames;  // device copy, or the mapped pinned ring in provided-hash mode
+  uint32_t narrow;                   // the frame stream holds uint32 ids
   uint32_t n_frames_registered;
   StoreSlot* st;
   uint32_t mask;
@@ -1792,9 +1833,9 @@ __global__ void __launch_bounds__(kThreads) k_store_insert(StoreInsertArgs a) {
     fresh = __shfl_sync(full, fresh, 0);
     if (!fresh) continue;
     off = __shfl_sync(full, off, 0);
-    const unsigned long long* src = a.frames + a.frame_off[r];
+    const unsigned long long base = a.frame_off[r];
     for (uint32_t j = lane; j < size; j += 32) {
-      unsigned long long fid = src[j];
+      unsigned long long fid = frame_at(a.frames, base + j, a.narrow);
       if (fid >= a.n_frames_registered) { atomicOr(&a.ctr_w->err, ERR_BAD_FRAME_ID); fid = 0; }
       a.arena[off + j] = (uint32_t)fid;
     }
@@ -2157,16 +2198,16 @@ __global__ void k_won_range(const uint32_t* uniq_row, const uint32_t* uniq_slot,
 // first GLOBAL position of every frame it contains
 __global__ void __launch_bounds__(kThreads) k_gather_won(const MergeCtl* mc, const uint32_t* uniq_row, const uint32_t* uniq_slot, const StackSlot* gtab, uint32_t row_base,
                                                          const unsigned long long* frames, const unsigned long long* frame_off, uint32_t n_frames_registered,
-                                                         uint32_t* ustream, uint32_t* loc_first, Counters* ctr_w) {
+                                                         uint32_t* ustream, uint32_t* loc_first, Counters* ctr_w, uint32_t narrow) {
   const uint32_t o0 = mc->ord0, o1 = mc->ord1, off0 = mc->off0;
   int lane = threadIdx.x & 31;
   uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
   for (uint32_t u = o0 + warp; u < o1; u += nwarps) {
     const uint32_t r = uniq_row[u] - row_base;
     const StackSlot e = gtab[uniq_slot[u]];
-    const unsigned long long* src = frames + frame_off[r];
+    const unsigned long long base = frame_off[r];
     for (uint32_t jx = lane; jx < e.size; jx += 32) {
-      unsigned long long fid = src[jx];
+      unsigned long long fid = frame_at(frames, base + jx, narrow);
       const uint32_t pos = e.offset + jx;
       if (fid >= n_frames_registered) { atomicOr(&ctr_w->err, ERR_BAD_FRAME_ID); fid = 0; }
       ustream[pos - off0] = (uint32_t)fid;

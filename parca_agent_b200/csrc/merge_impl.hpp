@@ -430,7 +430,7 @@ static int merge_process_once(pa_merge* g, bool* retry) {
     const uint64_t ucap = std::min<uint64_t>(a->d_ustream.cap / 4, 0x7FFFFFFFull);
     k_won_range<<<1, 32, 0, s>>>(urow, uslot, gtab, ctr, (uint32_t)P.row_base, (uint32_t)a->N, (uint32_t)ucap, (MergeCtl*)(ctl + CTL_MERGE), ctr);
     k_gather_won<<<a->G, kThreads, 0, s>>>((const MergeCtl*)(ctl + CTL_MERGE), urow, uslot, gtab, (uint32_t)P.row_base, a->src_frames, a->d_foff.as<unsigned long long>(),
-                                           P.n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr);
+                                           P.n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr, a->idb == 4 ? 1u : 0u);
     a->tm[T_RANK].launches += 8;
     MCK(cudaEventRecord(a->tm[T_RANK].b, s));
   }
@@ -674,7 +674,7 @@ static int merge_collect(pa_merge* g, uint8_t* base, uint64_t cap, pa_agg_result
   if (!g->planned) return g->fail(PA_EINVAL, "pa_merge_collect before pa_merge_plan");
   const size_t L = g->members.size();
   const uint32_t W = g->world, ncols = g->ncols;
-  auto done = [&] { for (size_t i = 0; i < L; i++) { g->members[i]->staged = -1; g->members[i]->merged_part = false; } g->planned = false; g->processed = false; };
+  auto done = [&] { for (size_t i = 0; i < L; i++) { release_staged(g->members[i]); g->members[i]->merged_part = false; } g->planned = false; g->processed = false; };
   if (g->NT == 0) { done(); return PA_OK; }
   const double t0 = now_ms();
   const uint64_t total = g->plan.total;
@@ -864,7 +864,7 @@ int pa_merge_flush(pa_merge* g, pa_agg_result* out) {
   MergeLocks lk(g);
   int rc;
   for (pa_agg* a : g->members) if ((rc = stage_async(a))) return g->fail(rc, a->err);
-  auto drop = [&] { for (pa_agg* a : g->members) { cudaSetDevice(a->device); cudaStreamSynchronize(a->s_copy); a->staged = -1; a->merged_part = false; } };
+  auto drop = [&] { for (pa_agg* a : g->members) { cudaSetDevice(a->device); cudaStreamSynchronize(a->s_copy); release_staged(a); a->merged_part = false; } };
   if ((rc = merge_process(g))) { drop(); return rc; }
   uint64_t len = 0;
   if ((rc = merge_plan(g, &len))) { drop(); return rc; }

@@ -114,7 +114,7 @@ class Aggregator:
 
     def __init__(self, device=0, hash_mode=abi.PA_HASH_XXH64X2, label_flags=0, samples_per_second=19, external_labels=(),
                  max_samples=1 << 20, max_frames=0, chunk_samples=0, schema=abi.PA_SCHEMA_V2, stack_cache_entries=0, stack_cache_frames=0,
-                 unknown_frame_type_sid=0, ipc_compression=abi.PA_IPC_PLAIN):
+                 unknown_frame_type_sid=0, ipc_compression=abi.PA_IPC_PLAIN, frame_id_bytes=8, flags=0):
         L = lib()
         ext = (abi.PaLabelPair * max(1, len(external_labels)))()
         for i, (n, v) in enumerate(external_labels):
@@ -123,13 +123,14 @@ class Aggregator:
                               samples_per_second=samples_per_second, n_external_labels=len(external_labels), external_labels=ext,
                               max_samples=max_samples, max_frames=max_frames, chunk_samples=chunk_samples, schema=schema,
                               stack_cache_entries=stack_cache_entries, stack_cache_frames=stack_cache_frames, unknown_frame_type_sid=unknown_frame_type_sid,
-                              ipc_compression=ipc_compression)
+                              ipc_compression=ipc_compression, frame_id_bytes=frame_id_bytes, flags=flags)
         h = C.c_void_p()
         rc = L.pa_agg_create(C.byref(cfg), C.byref(h))
         if rc != 0:
             raise PaError(rc, "pa_agg_create failed (no CUDA device, bad config or out of memory)")
         self.h = h
         self.max_samples = max_samples
+        self.id_dtype = np.uint32 if frame_id_bytes == 4 else np.uint64  # what the ring holds per frame id
 
     def _ck(self, rc):
         if rc != 0:
@@ -168,7 +169,7 @@ class Aggregator:
     # ---- ingest
     def submit(self, hdrs, frame_ids):
         hdrs = np.ascontiguousarray(hdrs, dtype=abi.HDR_DTYPE)
-        frame_ids = np.ascontiguousarray(frame_ids, dtype=np.uint64)
+        frame_ids = np.ascontiguousarray(frame_ids, dtype=self.id_dtype)
         self._keep = (hdrs, frame_ids)
         self._ck(lib().pa_agg_submit(self.h, hdrs.ctypes.data, frame_ids.ctypes.data, len(hdrs)))
 
@@ -177,7 +178,8 @@ class Aggregator:
         ph, pf, base = C.c_void_p(), C.c_void_p(), C.c_uint64()
         self._ck(lib().pa_agg_acquire(self.h, n_rows, n_frames, C.byref(ph), C.byref(pf), C.byref(base)))
         hv = np.ctypeslib.as_array(C.cast(ph, C.POINTER(C.c_uint8)), shape=(max(n_rows, 1) * 64,))[:n_rows * 64].view(abi.HDR_DTYPE)
-        fv = np.ctypeslib.as_array(C.cast(pf, C.POINTER(C.c_uint64)), shape=(max(n_frames, 1),))[:n_frames]
+        ctype = C.c_uint32 if self.id_dtype == np.uint32 else C.c_uint64
+        fv = np.ctypeslib.as_array(C.cast(pf, C.POINTER(ctype)), shape=(max(n_frames, 1),))[:n_frames]
         return hv, fv, base.value
 
     def commit(self, n_rows):
@@ -367,9 +369,9 @@ def load(a, w):
     a.commit(w.n)
 
 
-def run(w, device=0, chunk_samples=0):
+def run(w, device=0, chunk_samples=0, **kw):
     """Whole-batch convenience used by tests: returns (ipc bytes, Result)."""
-    a = from_workload(w, device=device, chunk_samples=chunk_samples)
+    a = from_workload(w, device=device, chunk_samples=chunk_samples, **kw)
     load(a, w)
     r = a.flush()
     data = r.ipc_bytes()

@@ -64,12 +64,13 @@ class Workload:
         return self._frame_ids
 
     def write_frames(self, out):
-        """Materialise the frame-id stream into `out` (uint64[n_frame_ids]) without a temp copy."""
+        """Materialise the frame-id stream into `out` (uint64 or uint32 [n_frame_ids]) without a temp copy of the stream."""
         if self._frame_ids is not None:
             out[:] = self._frame_ids
         else:
             f = self.stack_table.shape[1]
-            np.take(self.stack_table, self.stack_choice, axis=0, out=out.reshape(self.n, f))
+            table = self.stack_table if out.dtype == self.stack_table.dtype else self.stack_table.astype(out.dtype)
+            np.take(table, self.stack_choice, axis=0, out=out.reshape(self.n, f))
 
     def head(self, n):
         """First n rows as a new workload (frames are a prefix of the stream)."""

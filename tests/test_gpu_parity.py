@@ -112,6 +112,37 @@ def test_config3_full(oracle, gpu):
     assert r.n_rows == 10_000_000 and r.n_unique_stacks == len(np.unique(w.stack_choice))
 
 
+@pytest.mark.parametrize("mode", [abi.PA_HASH_PROVIDED, abi.PA_HASH_XXH64X2])
+def test_narrow_frame_id_ring(oracle, gpu, mode):
+    """pa_agg_config.frame_id_bytes = 4: the ring and the HBM frame stream hold uint32 ids (half the bytes); every output byte
+    is the same, including ragged stacks at odd offsets, empty stacks and stacks deeper than 64 frames"""
+    for w in (synth.edge_workload(seed=51, n=6000, hash_mode=mode), synth.config1(hash_mode=mode).head(50_000), wide_label_workload(12, n=800, seed=3)):
+        w.hash_mode = mode
+        assert_same(oracle, gpu, w, frame_id_bytes=4)
+        assert_same(oracle, gpu, w, frame_id_bytes=4, chunk_samples=777)
+    assert_same(oracle, gpu, as_v1(synth.edge_workload(seed=52, n=3000, hash_mode=mode)), frame_id_bytes=4)
+
+
+def test_single_ring_flag(oracle, gpu):
+    """PA_CFG_SINGLE_RING: one ring buffer; ingest is refused while a staged batch holds it, and works again after collect"""
+    w = synth.config1().head(20_000)
+    want, _ = oracle.run(w)
+    a = gpu.from_workload(w, flags=abi.PA_CFG_SINGLE_RING)
+    for _ in range(3):
+        gpu.load(a, w)
+        assert a.flush().ipc_bytes() == want
+    gpu.load(a, w)
+    a.stage()
+    with pytest.raises(gpu.PaError) as e:
+        a.acquire(1, 0)
+    assert e.value.code == -28  # PA_ENOSPC
+    a.process()
+    assert a.collect().ipc_bytes() == want
+    gpu.load(a, w)
+    assert a.flush().ipc_bytes() == want
+    a.close()
+
+
 def test_stack_ids_match_xxh64(oracle, gpu):
     w = synth.edge_workload(seed=5, hash_mode=abi.PA_HASH_XXH64X2)
     a = gpu.from_workload(w)

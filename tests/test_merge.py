@@ -28,13 +28,13 @@ def gpu():
     return lib
 
 
-def merged_vs_oracle(oracle, gpu, w, idx_lists, staged=False, repeat=1, chunk_samples=0):
+def merged_vs_oracle(oracle, gpu, w, idx_lists, staged=False, repeat=1, chunk_samples=0, **kw):
     """Shards = the given row subsets of w (in that order); returns the merged Result after comparing with the oracle."""
     parts = [w.rows(ix) for ix in idx_lists]
     order = np.concatenate([np.asarray(ix, dtype=np.int64) for ix in idx_lists]) if idx_lists else np.zeros(0, np.int64)
     ref = w.rows(order)
     want, st = oracle.run(ref)
-    aggs = [gpu.from_workload(p, chunk_samples=chunk_samples) for p in parts]
+    aggs = [gpu.from_workload(p, chunk_samples=chunk_samples, **kw) for p in parts]
     g = gpu.MergeGroup.local(aggs)
     res = None
     for _ in range(repeat):
@@ -103,6 +103,11 @@ def test_runs_merge_across_shard_borders(oracle, gpu):
     t = pa.ipc.open_stream(pa.py_buffer(res.ipc)).read_all()
     tid = t.column("labels").chunk(0).field("thread_id")
     assert len(tid.run_ends) == 1 and tid.run_ends[0].as_py() == 2000
+
+
+def test_narrow_ring_members(oracle, gpu):
+    w = synth.edge_workload(seed=14, n=4000, hash_mode=abi.PA_HASH_XXH64X2, external=False)
+    merged_vs_oracle(oracle, gpu, w, sharded.shard_rows(w, 3), frame_id_bytes=4)
 
 
 def test_config3_zipf_many_labelsets(oracle, gpu):
