@@ -277,8 +277,24 @@ int pa_agg_stage_device_parts(pa_agg* a, const pa_device_part* parts, uint32_t n
  * All three are collective. pa_merge_collect writes this process's members' parts of the stream into `base`, a buffer of at
  * least *ipc_len bytes that ALL processes of the group share (e.g. a POSIX shared-memory mapping; it is page-locked on first
  * use); rank 0 adds the dictionaries and the metadata, and gets out->ipc == base. base == NULL: groups whose members all live
- * in this process use a library-owned pinned buffer. */
+ * in this process use a library-owned pinned buffer.
+ *   pa_merge_create_host  : one member per call; the caller supplies the four collectives on HOST buffers (MPI, gloo, sockets ...):
+ *                           the library stages device buffers through pinned memory around them. For hosts without NCCL, and for
+ *                           exercising the multi-process path on one GPU (two processes may share a device). */
 typedef struct pa_merge pa_merge;
+/* Collectives over the `world` ranks of the group, on host memory; every callback returns 0 on success. Byte counts.
+ *   allgather         recv[r*bytes .. ) = rank r's send
+ *   allgatherv        recv[displs[r] .. +counts[r]) = rank r's send (counts[my rank] bytes)
+ *   alltoallv         send[sdispls[r] .. +scounts[r]) goes to rank r; recv[rdispls[r] .. +rcounts[r]) comes from rank r
+ *   allreduce_min_u32 element-wise minimum over all ranks, in place */
+typedef struct pa_merge_host_transport {
+  void* user;
+  int (*allgather)(void* user, const void* send, void* recv, uint64_t bytes);
+  int (*allgatherv)(void* user, const void* send, void* recv, const uint64_t* counts, const uint64_t* displs);
+  int (*alltoallv)(void* user, const void* send, const uint64_t* scounts, const uint64_t* sdispls, void* recv, const uint64_t* rcounts, const uint64_t* rdispls);
+  int (*allreduce_min_u32)(void* user, uint32_t* buf, uint64_t count);
+} pa_merge_host_transport;
+int pa_merge_create_host(pa_agg* member, const pa_merge_host_transport* t, uint32_t rank, uint32_t world, pa_merge** out);
 int pa_merge_create_local(pa_agg* const* members, uint32_t n, pa_merge** out);
 int pa_merge_nccl_unique_id(uint8_t* id128);
 int pa_merge_create_nccl(pa_agg* member, const uint8_t* id128, uint32_t rank, uint32_t world, pa_merge** out);

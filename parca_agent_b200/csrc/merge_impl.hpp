@@ -85,8 +85,12 @@ struct pa_merge {
   std::vector<pa_agg*> members;   // the shards this process drives
   std::vector<uint32_t> ranks;    // their ranks in the group
   uint32_t world = 0;
-  bool use_nccl = false;
+  bool use_nccl = false;        // one stream per member, collectives order them (NCCL, or the caller's host transport)
   std::vector<ncclComm_t> comms;
+  const pa_merge_host_transport* host = nullptr;  // non-null: collectives go through the caller's callbacks on host buffers
+  pa_merge_host_transport host_copy{};
+  uint8_t *h_xs = nullptr, *h_xr = nullptr;       // pinned staging of the host transport
+  size_t h_xs_cap = 0, h_xr_cap = 0;
   std::vector<MergeBufs> mb;
   std::vector<cudaStream_t> saved_streams;
   std::string err;
@@ -157,11 +161,39 @@ static int pin_room(pa_merge* g, size_t bytes) {
   return PA_OK;
 }
 
+// host transport: device buffers are staged through pinned memory around the caller's collective (one member per process)
+static int xroom(pa_merge* g, size_t send_bytes, size_t recv_bytes) {
+  auto grow = [&](uint8_t*& p, size_t& cap, size_t need) -> int {
+    if (need <= cap) return PA_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    MCK(cudaHostAlloc((void**)&p, need * 2 + 256, cudaHostAllocDefault));
+    cap = need * 2 + 256;
+    return PA_OK;
+  };
+  int rc = grow(g->h_xs, g->h_xs_cap, send_bytes);
+  return rc ? rc : grow(g->h_xr, g->h_xr_cap, recv_bytes);
+}
+#define HCK(expr)                                                                            \
+  do {                                                                                       \
+    if ((expr) != 0) return g->fail(PA_EIO, std::string("host transport callback failed: ") + #expr); \
+  } while (0)
+
 // ---- collectives over the members of the group (every call is made for all local members at once) -------------------
 // all-gather `bytes` from every rank's device buffer into every member's `dst` (world x bytes)
 static int t_allgather(pa_merge* g, const std::vector<const void*>& src, const std::vector<void*>& dst, size_t bytes) {
   const size_t L = g->members.size();
-  if (g->use_nccl) {
+  if (g->host) {
+    int rc = xroom(g, bytes, (size_t)g->world * bytes);
+    if (rc) return rc;
+    cudaStream_t s = mstream(g, 0);
+    MCK(cudaMemcpyAsync(g->h_xs, src[0], bytes, cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    HCK(g->host->allgather(g->host->user, g->h_xs, g->h_xr, bytes));
+    MCK(cudaMemcpyAsync(dst[0], g->h_xr, (size_t)g->world * bytes, cudaMemcpyHostToDevice, s));
+    MCK(cudaStreamSynchronize(s));
+    g->nvlink_bytes += bytes * (g->world - 1);
+  } else if (g->use_nccl) {
     NcclApi* n = nccl_api();
     NCK(n->GroupStart());
     for (size_t i = 0; i < L; i++) NCK(n->AllGather(src[i], dst[i], bytes, ncclChar, g->comms[i], mstream(g, i)));
@@ -196,7 +228,20 @@ static int t_allgather_host(pa_merge* g, const std::vector<const void*>& src, si
 // all-gather with per-rank byte counts; dst holds rank r's block at displ[r]
 static int t_allgatherv(pa_merge* g, const std::vector<const void*>& src, const std::vector<void*>& dst, const std::vector<uint64_t>& count, const std::vector<uint64_t>& displ) {
   const size_t L = g->members.size();
-  if (g->use_nccl) {
+  if (g->host) {
+    uint64_t total = 0;
+    for (uint32_t r = 0; r < g->world; r++) total = std::max<uint64_t>(total, displ[r] + count[r]);
+    const uint64_t mine = count[g->ranks[0]];
+    int rc = xroom(g, std::max<uint64_t>(mine, 1), std::max<uint64_t>(total, 1));
+    if (rc) return rc;
+    cudaStream_t s = mstream(g, 0);
+    if (mine) MCK(cudaMemcpyAsync(g->h_xs, src[0], mine, cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    HCK(g->host->allgatherv(g->host->user, g->h_xs, g->h_xr, count.data(), displ.data()));
+    if (total) MCK(cudaMemcpyAsync(dst[0], g->h_xr, total, cudaMemcpyHostToDevice, s));
+    MCK(cudaStreamSynchronize(s));
+    g->nvlink_bytes += mine * (g->world - 1);
+  } else if (g->use_nccl) {
     NcclApi* n = nccl_api();
     NCK(n->GroupStart());
     for (size_t i = 0; i < L; i++)
@@ -218,7 +263,19 @@ static int t_allgatherv(pa_merge* g, const std::vector<const void*>& src, const 
 static int t_alltoallv(pa_merge* g, const std::vector<const void*>& send, const std::vector<std::vector<uint64_t>>& scount, const std::vector<std::vector<uint64_t>>& sdispl,
                        const std::vector<void*>& recv, const std::vector<std::vector<uint64_t>>& rcount, const std::vector<std::vector<uint64_t>>& rdispl) {
   const size_t L = g->members.size();
-  if (g->use_nccl) {
+  if (g->host) {
+    uint64_t stot = 0, rtot = 0;
+    for (uint32_t r = 0; r < g->world; r++) { stot = std::max<uint64_t>(stot, sdispl[0][r] + scount[0][r]); rtot = std::max<uint64_t>(rtot, rdispl[0][r] + rcount[0][r]); }
+    int rc = xroom(g, std::max<uint64_t>(stot, 1), std::max<uint64_t>(rtot, 1));
+    if (rc) return rc;
+    cudaStream_t s = mstream(g, 0);
+    if (stot) MCK(cudaMemcpyAsync(g->h_xs, send[0], stot, cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    HCK(g->host->alltoallv(g->host->user, g->h_xs, scount[0].data(), sdispl[0].data(), g->h_xr, rcount[0].data(), rdispl[0].data()));
+    if (rtot) MCK(cudaMemcpyAsync(recv[0], g->h_xr, rtot, cudaMemcpyHostToDevice, s));
+    MCK(cudaStreamSynchronize(s));
+    for (uint32_t r = 0; r < g->world; r++) if (r != g->ranks[0]) g->nvlink_bytes += scount[0][r];
+  } else if (g->use_nccl) {
     NcclApi* n = nccl_api();
     for (size_t i = 0; i < L; i++) {  // the part that stays on the shard
       const uint32_t me = g->ranks[i];
@@ -244,7 +301,17 @@ static int t_alltoallv(pa_merge* g, const std::vector<const void*>& send, const 
 static int t_allreduce_min(pa_merge* g, const std::vector<uint32_t*>& buf, size_t count) {
   const size_t L = g->members.size();
   if (!count) return PA_OK;
-  if (g->use_nccl) {
+  if (g->host) {
+    int rc = xroom(g, count * 4, 1);
+    if (rc) return rc;
+    cudaStream_t s = mstream(g, 0);
+    MCK(cudaMemcpyAsync(g->h_xs, buf[0], count * 4, cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    HCK(g->host->allreduce_min_u32(g->host->user, (uint32_t*)g->h_xs, (uint64_t)count));
+    MCK(cudaMemcpyAsync(buf[0], g->h_xs, count * 4, cudaMemcpyHostToDevice, s));
+    MCK(cudaStreamSynchronize(s));
+    g->nvlink_bytes += (uint64_t)count * 4 * 2 * (g->world - 1) / g->world;
+  } else if (g->use_nccl) {
     NcclApi* n = nccl_api();
     NCK(n->GroupStart());
     for (size_t i = 0; i < L; i++) NCK(n->AllReduce(buf[i], buf[i], count, ncclUint32, ncclMin, g->comms[i], mstream(g, i)));
@@ -820,6 +887,20 @@ int pa_merge_create_nccl(pa_agg* member, const uint8_t* id128, uint32_t rank, ui
   *out = g;
   return PA_OK;
 }
+int pa_merge_create_host(pa_agg* member, const pa_merge_host_transport* t, uint32_t rank, uint32_t world, pa_merge** out) {
+  if (!member || !t || !out || world == 0 || world > (uint32_t)kMaxWorld || rank >= world || !t->allgather || !t->allgatherv || !t->alltoallv || !t->allreduce_min_u32)
+    return PA_EINVAL;
+  pa_merge* g = new pa_merge();
+  g->world = world;
+  g->use_nccl = true;  // one stream per member; ordering comes from the (synchronous) collectives
+  g->host_copy = *t;
+  g->host = &g->host_copy;
+  g->members.push_back(member);
+  g->ranks.push_back(rank);
+  g->mb.resize(1);
+  *out = g;
+  return PA_OK;
+}
 void pa_merge_destroy(pa_merge* g) {
   if (!g) return;
   for (size_t i = 0; i < g->members.size(); i++) {
@@ -827,7 +908,9 @@ void pa_merge_destroy(pa_merge* g) {
     cudaStreamSynchronize(g->members[i]->s_comp);
     g->mb[i].release();
   }
-  if (g->use_nccl) for (auto c : g->comms) nccl_api()->CommDestroy(c);
+  if (g->use_nccl && !g->host) for (auto c : g->comms) nccl_api()->CommDestroy(c);
+  if (g->h_xs) cudaFreeHost(g->h_xs);
+  if (g->h_xr) cudaFreeHost(g->h_xr);
   if (g->registered) cudaHostUnregister(g->registered);
   if (g->out) cudaFreeHost(g->out);
   if (g->h_pin) cudaFreeHost(g->h_pin);

@@ -20,7 +20,7 @@ EXPORTS = [
     "pa_agg_flush", "pa_agg_release", "pa_agg_stage", "pa_agg_process", "pa_agg_collect", "pa_agg_last_kernel_ms",
     "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_agg_debug_pair_counts", "pa_agg_stacktraces", "pa_agg_last_stack_ids", "pa_agg_shard_sizes", "pa_agg_shard_export", "pa_agg_stage_device", "pa_agg_stage_device_parts", "pa_agg_discard", "pa_ipc_compress_lz4", "pa_ipc_free", "pa_fix_truncation", "pa_xxh64",
     "pa_merge_create_local", "pa_merge_nccl_unique_id", "pa_merge_create_nccl", "pa_merge_destroy", "pa_merge_last_error", "pa_merge_process",
-    "pa_merge_plan", "pa_merge_collect", "pa_merge_flush", "pa_merge_last_stats",
+    "pa_merge_plan", "pa_merge_collect", "pa_merge_flush", "pa_merge_last_stats", "pa_merge_create_host",
 ]
 
 
@@ -77,6 +77,7 @@ def lib():
         L.pa_merge_create_local.argtypes = [C.POINTER(vp), C.c_uint32, C.POINTER(vp)]
         L.pa_merge_nccl_unique_id.argtypes = [C.c_char_p]
         L.pa_merge_create_nccl.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+        L.pa_merge_create_host.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]
         L.pa_merge_destroy.argtypes = [vp]
         L.pa_merge_destroy.restype = None
         L.pa_merge_last_error.argtypes = [vp]
@@ -296,9 +297,21 @@ class MergeGroup:
             raise PaError(rc, "pa_merge_create_nccl failed")
         return cls(h, [member])
 
+    @classmethod
+    def host(cls, member, transport, rank, world):
+        """One member per process; `transport` provides the collectives on host buffers (host_transport.GlooTransport)."""
+        h = C.c_void_p()
+        rc = lib().pa_merge_create_host(member.h, C.byref(transport.struct), rank, world, C.byref(h))
+        if rc != 0:
+            raise PaError(rc, "pa_merge_create_host failed")
+        g = cls(h, [member])
+        g._transport = transport  # the callbacks must outlive the group
+        return g
+
     def _ck(self, rc):
         if rc != 0:
-            raise PaError(rc, (lib().pa_merge_last_error(self.h) or b"").decode(errors="replace"))
+            extra = "; ".join(getattr(getattr(self, "_transport", None), "errors", []) or [])
+            raise PaError(rc, (lib().pa_merge_last_error(self.h) or b"").decode(errors="replace") + (" | " + extra if extra else ""))
 
     def process(self):
         self._ck(lib().pa_merge_process(self.h))

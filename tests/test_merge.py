@@ -166,6 +166,16 @@ def test_single_aggregator_still_works_after_merge(oracle, gpu):
         a.close()
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_process_group_over_host_transport(world):
+    """one shard per PROCESS (gloo collectives on host buffers, stream in shared memory), all processes on this one GPU"""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", PA_ONE_GPU="1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", str(29533 + world), os.path.join(ROOT, "tests", "dist_merge_hostcb_check.py")], capture_output=True, text=True, env=env, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "merge-hostcb ok world=%d" % world in p.stdout
+
+
 def test_nccl_group_on_two_gpus():
     import torch
     if torch.cuda.device_count() < 2:

@@ -34,6 +34,15 @@ def test_world_size_2_gloo():
     assert "shard-check ok world=2" in p.stdout
 
 
+def test_host_transport_collectives_world_3_gloo():
+    """the host collectives a multi-process merge group calls back into (pa_merge_create_host), against their definitions"""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "3", "--master-addr", "127.0.0.1",
+                        "--master-port", "29519", os.path.join(ROOT, "tests", "dist_hostcb_transport_check.py")], capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "hostcb-transport ok world=3" in p.stdout
+
+
 @pytest.mark.gpu
 def test_each_shard_matches_oracle_on_gpu(oracle):
     from parca_agent_b200 import lib
