@@ -50,7 +50,10 @@ def parse():
                     "exchange, BASELINE config 4 at N=8); by default it is timed after the headline (mode A) and reported under \"mode_b\"")
     ap.add_argument("--merge-rows", type=int, default=12_500_000, help="mode B rows per GPU (config 4 = 100M / 8)")
     ap.add_argument("--mode-b-child", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--merge-timeout", type=int, default=600, help="seconds after which a stalled mode B leg is abandoned (the headline line is printed without it)")
+    ap.add_argument("--merge-transport", default="host", choices=["host", "nccl"],
+                    help="how the merged-batch leg exchanges its dictionary keys: host = the library's host-callback transport over gloo (default: "
+                         "the only multi-process transport the builder could validate on hardware this round); nccl = NCCL over NVLink from inside the library")
+    ap.add_argument("--merge-timeout", type=int, default=360, help="seconds after which a stalled mode B leg is abandoned (the headline line is printed without it)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="BASELINE.json config: 2 = headline (default), 3 = Zipf/CUDA-origin/50k labelsets")
     return ap.parse_args()
 
@@ -283,7 +286,7 @@ def run_mode_b(args, rank, world, local, barrier):
     exchanges, max over ranks); `e2e` = ring -> HBM -> merged pass -> stream in host shared memory, every GPU over its own
     PCIe link, wall clock between barriers."""
     import ctypes
-    from multiprocessing import shared_memory
+    from multiprocessing import resource_tracker, shared_memory
 
     import torch
     import torch.distributed as dist
@@ -291,9 +294,14 @@ def run_mode_b(args, rank, world, local, barrier):
     mode = abi.PA_HASH_PROVIDED if args.hash_mode == "provided" else abi.PA_HASH_XXH64X2
     w = synth.config4_part(rank, world, rows_per_gpu=args.merge_rows, hash_mode=mode)
     a = lib.from_workload(w, device=local, max_samples=w.n, max_frames=w.n_frame_ids, chunk_samples=1 << 20)
-    ids = [lib.MergeGroup.nccl_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
-    g = lib.MergeGroup.nccl(a, ids[0], rank, world)
+    tdev = "cuda" if args.merge_transport == "nccl" else "cpu"  # where the few bench-level reductions live (the default process group's backend)
+    if args.merge_transport == "nccl":
+        ids = [lib.MergeGroup.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        g = lib.MergeGroup.nccl(a, ids[0], rank, world)
+    else:
+        from parca_agent_b200.host_transport import GlooTransport
+        g = lib.MergeGroup.host(a, GlooTransport(), rank, world)
     lib.load(a, w)
     a.stage()
     for _ in range(args.warmup):
@@ -317,6 +325,7 @@ def run_mode_b(args, rank, world, local, barrier):
     dist.broadcast_object_list(names, src=0)
     if rank != 0:
         shm = shared_memory.SharedMemory(name=names[0])
+        resource_tracker.unregister(shm._name, "shared_memory")  # attached, not owned: Python < 3.13 would unlink it when this process exits
     view = ctypes.c_char.from_buffer(shm.buf)
     base = ctypes.addressof(view)
     res = g.collect(base, n)  # first collect page-locks the shared buffer
@@ -332,7 +341,7 @@ def run_mode_b(args, rank, world, local, barrier):
         barrier()
         e2e_times.append(time.perf_counter() - t1)
         stage_ms = {"h2d_ms": res.h2d_ms, "gpu_ms": res.gpu_ms, "d2h_ms": res.d2h_ms, "host_ms": res.host_ms}
-    t = torch.tensor([float(np.sum(dev_ms)) / 1e3, wall, float(np.sum(e2e_times)), float(stats["nvlink_bytes"])], dtype=torch.float64, device="cuda")
+    t = torch.tensor([float(np.sum(dev_ms)) / 1e3, wall, float(np.sum(e2e_times)), float(stats["nvlink_bytes"]), stats["exchange_wait_ms"]], dtype=torch.float64, device=tdev)
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -346,8 +355,12 @@ def run_mode_b(args, rank, world, local, barrier):
                "wall_ms_per_step": 1e3 * float(tmax[1]) / len(dev_ms),
                "e2e": {"value": total * len(e2e_times) / float(tmax[2]), "unit": "samples/s", "h2d_bytes_per_step": int((w.n * 64 + w.n_frame_ids * 8) * world),
                        "d2h_bytes_per_step": int(n), "steps": len(e2e_times), "stages_ms_last_step_rank0": stage_ms},
-               "nvlink_payload_bytes_per_step_all_ranks": int(float(t[3])), "nvlink_payload_bytes_per_row": float(t[3]) / total,
-               "exchange_wait_ms_rank0": stats["exchange_wait_ms"], "kernel_groups_ms_rank0": {k: float(np.mean(v)) for k, v in groups.items()},
+               "transport": ("NCCL over NVLink, called from the library" if args.merge_transport == "nccl" else
+                             "host callbacks over gloo (pa_merge_create_host): every exchange is staged device -> pinned host -> TCP loopback -> device; "
+                             "the exchanged BYTES are the same as over NCCL, the exchange TIME is not representative of NVLink"),
+               "exchange_payload_bytes_per_step_all_ranks": int(float(t[3])), "exchange_payload_bytes_per_row": float(t[3]) / total,
+               "exchange_wait_ms_per_step_max_rank": float(tmax[4]), "ms_per_step_minus_exchange_wait": max(0.0, 1e3 * float(tmax[0]) / len(dev_ms) - float(tmax[4])),
+               "kernel_groups_ms_rank0": {k: float(np.mean(v)) for k, v in groups.items()},
                "rows": res.n_rows, "unique_stacks": res.n_unique_stacks, "locations": res.n_locations, "ipc_bytes": int(n),
                "ipc_sha256": hashlib.sha256(shm.buf[:n]).hexdigest(),
                "note": "one record for the stream [GPU0 rows, GPU1 rows, ...]; bit-exactness vs the oracle is held by tests/test_merge.py and tests/dist_merge_slices_check.py"}
@@ -356,7 +369,10 @@ def run_mode_b(args, rank, world, local, barrier):
     a.close()
     shm.close()
     if rank == 0:
-        shm.unlink()
+        try:
+            shm.unlink()
+        except FileNotFoundError:
+            pass
     return out
 
 
@@ -371,11 +387,17 @@ def main():
     import torch
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    one_gpu = os.environ.get("PA_ONE_GPU") == "1"  # dry run of the N>1 flow with every rank on cuda:0 (gloo instead of NCCL between the ranks)
+    if one_gpu:
+        local = 0
     torch.cuda.set_device(local)
     if args.stream:
         return run_stream(args, rank, world, local)
     if args.mode_b_child:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if args.merge_transport == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
 
         def child_barrier():
             dist.barrier()
@@ -388,8 +410,12 @@ def main():
         dist.destroy_process_group()
         return
     numa = pin_to_gpu_numa(local)  # the rings are first-touched by this rank: keep them next to its GPU
+    rdev = "cpu" if one_gpu else "cuda"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if one_gpu:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
         if world > 1:
@@ -426,7 +452,7 @@ def main():
     wall = time.perf_counter() - t0
     res = a.collect()
     dev_s = float(np.sum(step_ms)) / 1e3
-    tmax = torch.tensor([dev_s, wall], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([dev_s, wall], dtype=torch.float64, device=rdev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dev_s_max, wall_max = float(tmax[0]), float(tmax[1])
@@ -449,7 +475,7 @@ def main():
             e2e_times.append(dt)
     import hashlib
     gpu_digest = hashlib.sha256(r.ipc).hexdigest() if rank == 0 else None  # the stream the LAST TIMED end-to-end flush produced
-    e2e_t = torch.tensor([float(np.sum(e2e_times))], dtype=torch.float64, device="cuda")
+    e2e_t = torch.tensor([float(np.sum(e2e_times))], dtype=torch.float64, device=rdev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = total_rows * len(e2e_times) / float(e2e_t[0])
@@ -459,10 +485,14 @@ def main():
         # first time it sees them. Reported beside the headline, not part of it (it is not a per-interval cost in steady state).
         ids = a.last_stack_ids(r.n_unique_stacks).tobytes()
         a.stacktraces(ids[:16 * 1024])  # warm the output buffer
-        t1 = time.perf_counter()
-        sr = a.stacktraces(ids)
+        walls = []
+        for _ in range(4):  # the first full-size call grows the device scratch (cudaFree + cudaMalloc of ~0.6 GB): round 1's "7 vs 37 ms"
+            t1 = time.perf_counter()
+            sr = a.stacktraces(ids)
+            walls.append(1e3 * (time.perf_counter() - t1))
         v1_st = {"ids": sr.n_rows, "locations": sr.n_locations, "gpu_ms": sr.gpu_ms, "d2h_ms": sr.d2h_ms, "host_ms": sr.host_ms,
-                 "wall_ms": 1e3 * (time.perf_counter() - t1), "ipc_bytes": sr.ipc_len, "gpu_launches": sr.gpu_launches}
+                 "wall_ms": float(np.min(walls[1:])), "wall_ms_first_full_size_call": walls[0], "wall_ms_all": walls,
+                 "ipc_bytes": sr.ipc_len, "gpu_launches": sr.gpu_launches}
     # ---- the same batch through a NARROW ring (pa_agg_config.frame_id_bytes = 4: frame ids are dense registration indices, so
     # uint32 carries them; stack ids and every output byte are unchanged). Reported beside the headline, which keeps the
     # uint64 ring: half the PCIe bytes end to end, half the HBM bytes for the hash kernel.
@@ -595,8 +625,9 @@ def main():
         # leaves its result in a file; every parent waits for its own child (bounded) and goes on.
         port = int(os.environ.get("MASTER_PORT", "29500")) + 17
         res_file = "/tmp/pa_mode_b_%d_%d.json" % (os.getppid(), port)
-        env = dict(os.environ, MASTER_PORT=str(port), PA_MODE_B_RESULT=res_file)
-        cmd = [sys.executable, os.path.abspath(__file__), "--mode-b-child", "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
+        # the children rendezvous among themselves on their own port: they must not look for torchrun's agent store there
+        env = dict(os.environ, MASTER_PORT=str(port), PA_MODE_B_RESULT=res_file, TORCHELASTIC_USE_AGENT_STORE="False")
+        cmd = [sys.executable, os.path.abspath(__file__), "--mode-b-child", "--merge-transport", args.merge_transport, "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
                "--merge-rows", str(args.merge_rows), "--hash-mode", args.hash_mode, "--e2e-steps", str(args.e2e_steps)]
         if rank == 0 and os.path.exists(res_file):
             os.remove(res_file)

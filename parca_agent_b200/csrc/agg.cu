@@ -466,7 +466,7 @@ void pa_agg_destroy(pa_agg* a) {
 
 // ---- registration ---------------------------------------------------------------------------
 int pa_agg_register_strings(pa_agg* a, const uint8_t* bytes, const uint32_t* offsets, uint32_t n, uint32_t* first_id) {
-  if (!a || (n && (!bytes && offsets[n] != 0)) || (n && !offsets)) return PA_EINVAL;
+  if (!a || (n && !offsets) || (n && !bytes && offsets[n] != 0)) return PA_EINVAL;
   std::lock_guard<std::mutex> g(a->reg_mu);
   if (first_id) *first_id = (uint32_t)a->sp.sid2cid.size();
   for (uint32_t i = 0; i < n; i++) {

@@ -184,6 +184,7 @@ static int xroom(pa_merge* g, size_t send_bytes, size_t recv_bytes) {
 static int t_allgather(pa_merge* g, const std::vector<const void*>& src, const std::vector<void*>& dst, size_t bytes) {
   const size_t L = g->members.size();
   if (g->host) {
+    const double th0 = now_ms();
     int rc = xroom(g, bytes, (size_t)g->world * bytes);
     if (rc) return rc;
     cudaStream_t s = mstream(g, 0);
@@ -193,6 +194,7 @@ static int t_allgather(pa_merge* g, const std::vector<const void*>& src, const s
     MCK(cudaMemcpyAsync(dst[0], g->h_xr, (size_t)g->world * bytes, cudaMemcpyHostToDevice, s));
     MCK(cudaStreamSynchronize(s));
     g->nvlink_bytes += bytes * (g->world - 1);
+    g->ms_exchange_wait += now_ms() - th0;  // host transport: the stream idles while the caller's collective runs
   } else if (g->use_nccl) {
     NcclApi* n = nccl_api();
     NCK(n->GroupStart());
@@ -229,6 +231,7 @@ static int t_allgather_host(pa_merge* g, const std::vector<const void*>& src, si
 static int t_allgatherv(pa_merge* g, const std::vector<const void*>& src, const std::vector<void*>& dst, const std::vector<uint64_t>& count, const std::vector<uint64_t>& displ) {
   const size_t L = g->members.size();
   if (g->host) {
+    const double th0 = now_ms();
     uint64_t total = 0;
     for (uint32_t r = 0; r < g->world; r++) total = std::max<uint64_t>(total, displ[r] + count[r]);
     const uint64_t mine = count[g->ranks[0]];
@@ -241,6 +244,7 @@ static int t_allgatherv(pa_merge* g, const std::vector<const void*>& src, const 
     if (total) MCK(cudaMemcpyAsync(dst[0], g->h_xr, total, cudaMemcpyHostToDevice, s));
     MCK(cudaStreamSynchronize(s));
     g->nvlink_bytes += mine * (g->world - 1);
+    g->ms_exchange_wait += now_ms() - th0;  // host transport: the stream idles while the caller's collective runs
   } else if (g->use_nccl) {
     NcclApi* n = nccl_api();
     NCK(n->GroupStart());
@@ -264,6 +268,7 @@ static int t_alltoallv(pa_merge* g, const std::vector<const void*>& send, const 
                        const std::vector<void*>& recv, const std::vector<std::vector<uint64_t>>& rcount, const std::vector<std::vector<uint64_t>>& rdispl) {
   const size_t L = g->members.size();
   if (g->host) {
+    const double th0 = now_ms();
     uint64_t stot = 0, rtot = 0;
     for (uint32_t r = 0; r < g->world; r++) { stot = std::max<uint64_t>(stot, sdispl[0][r] + scount[0][r]); rtot = std::max<uint64_t>(rtot, rdispl[0][r] + rcount[0][r]); }
     int rc = xroom(g, std::max<uint64_t>(stot, 1), std::max<uint64_t>(rtot, 1));
@@ -275,6 +280,7 @@ static int t_alltoallv(pa_merge* g, const std::vector<const void*>& send, const 
     if (rtot) MCK(cudaMemcpyAsync(recv[0], g->h_xr, rtot, cudaMemcpyHostToDevice, s));
     MCK(cudaStreamSynchronize(s));
     for (uint32_t r = 0; r < g->world; r++) if (r != g->ranks[0]) g->nvlink_bytes += scount[0][r];
+    g->ms_exchange_wait += now_ms() - th0;  // host transport: the stream idles while the caller's collective runs
   } else if (g->use_nccl) {
     NcclApi* n = nccl_api();
     for (size_t i = 0; i < L; i++) {  // the part that stays on the shard
@@ -302,6 +308,7 @@ static int t_allreduce_min(pa_merge* g, const std::vector<uint32_t*>& buf, size_
   const size_t L = g->members.size();
   if (!count) return PA_OK;
   if (g->host) {
+    const double th0 = now_ms();
     int rc = xroom(g, count * 4, 1);
     if (rc) return rc;
     cudaStream_t s = mstream(g, 0);
@@ -311,6 +318,7 @@ static int t_allreduce_min(pa_merge* g, const std::vector<uint32_t*>& buf, size_
     MCK(cudaMemcpyAsync(buf[0], g->h_xs, count * 4, cudaMemcpyHostToDevice, s));
     MCK(cudaStreamSynchronize(s));
     g->nvlink_bytes += (uint64_t)count * 4 * 2 * (g->world - 1) / g->world;
+    g->ms_exchange_wait += now_ms() - th0;  // host transport: the stream idles while the caller's collective runs
   } else if (g->use_nccl) {
     NcclApi* n = nccl_api();
     NCK(n->GroupStart());

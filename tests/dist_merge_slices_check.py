@@ -8,7 +8,7 @@ compares the bytes with the CPU oracle on the stream [shard 0 rows, shard 1 rows
 import ctypes
 import os
 import sys
-from multiprocessing import shared_memory
+from multiprocessing import resource_tracker, shared_memory
 
 import numpy as np
 import torch
@@ -51,6 +51,7 @@ def main():
                 dist.broadcast_object_list(names, src=0)
                 if rank != 0:
                     shm = shared_memory.SharedMemory(name=names[0])
+                    resource_tracker.unregister(shm._name, "shared_memory")  # attached, not owned: Python < 3.13 would unlink it when this process exits
             view = ctypes.c_char.from_buffer(shm.buf)
             res = group.collect(ctypes.addressof(view), n)
             del view
@@ -65,7 +66,10 @@ def main():
         a.close()
         shm.close()
         if rank == 0:
-            shm.unlink()
+            try:
+                shm.unlink()
+            except FileNotFoundError:
+                pass
     if rank == 0:
         print("merge-slices ok world=%d" % world)
     dist.destroy_process_group()

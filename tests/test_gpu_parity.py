@@ -341,6 +341,48 @@ def test_randomized_sweep(oracle, gpu):
         assert_same(oracle, gpu, w, chunk_samples=int(rng.choice([0, 97, 512])))
 
 
+def test_registration_concurrent_with_flush(oracle, gpu):
+    """ParcaReporter registers strings / frames / labelsets from producer threads while the report ticker flushes
+    (reporter.cpp: FlushOnce runs without the ingest lock). The pass must only ever use the registration state it snapshotted
+    under the lock: no out-of-range table reads, every flushed batch still byte-exact."""
+    import threading
+    w = synth.edge_workload(seed=61, n=4000, hash_mode=abi.PA_HASH_XXH64X2, external=False)
+    want, _ = oracle.run(w)
+    a = gpu.from_workload(w)
+    stop, errors = threading.Event(), []
+
+    names = a.register_strings([b"late_label_a", b"late_label_b"])  # a fixed set of label NAMES (columns), ever new values
+
+    def registrar():
+        i = 0
+        try:
+            while not stop.is_set():
+                first = a.register_strings([("late-%d-%d" % (i, k)).encode() for k in range(8)])
+                fr = np.zeros(4, dtype=abi.FRAME_DTYPE)
+                fr["kind"] = abi.PA_FRAME_INTERP
+                fr["type_name_sid"] = first
+                fr["function_name_sid"] = first + 1
+                fr["source_file_sid"] = first + 2
+                fr["address_or_lineno"] = np.arange(4) + i
+                a.register_frames(fr)
+                a.register_labelsets([[(names, first + 4)], [(names, first + 5), (names + 1, first + 7)]])
+                i += 1
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    t = threading.Thread(target=registrar)
+    t.start()
+    try:
+        for _ in range(40):
+            gpu.load(a, w)
+            assert a.flush().ipc_bytes() == want  # the late registrations are not referenced by any row: the record is unchanged
+    finally:
+        stop.set()
+        t.join()
+    a.close()
+    assert not errors, errors
+
+
 def test_two_aggregators_concurrently(oracle, gpu):
     """Two instances on one GPU, flushed from two host threads at once (the streaming bench mode)."""
     import threading
