@@ -50,9 +50,10 @@ def parse():
                     "exchange, BASELINE config 4 at N=8); by default it is timed after the headline (mode A) and reported under \"mode_b\"")
     ap.add_argument("--merge-rows", type=int, default=12_500_000, help="mode B rows per GPU (config 4 = 100M / 8)")
     ap.add_argument("--mode-b-child", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--merge-transport", default="host", choices=["host", "nccl"],
-                    help="how the merged-batch leg exchanges its dictionary keys: host = the library's host-callback transport over gloo (default: "
-                         "the only multi-process transport the builder could validate on hardware this round); nccl = NCCL over NVLink from inside the library")
+    ap.add_argument("--merge-transport", default="shm", choices=["shm", "host", "nccl"],
+                    help="how the merged-batch leg exchanges its dictionary keys: shm = page-locked shared-memory mailboxes, every GPU over its own PCIe "
+                         "link (default: validated on hardware with several processes); host = host callbacks over gloo; nccl = NCCL over NVLink from "
+                         "inside the library (not validated on hardware this round)")
     ap.add_argument("--merge-timeout", type=int, default=360, help="seconds after which a stalled mode B leg is abandoned (the headline line is printed without it)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="BASELINE.json config: 2 = headline (default), 3 = Zipf/CUDA-origin/50k labelsets")
     return ap.parse_args()
@@ -299,6 +300,10 @@ def run_mode_b(args, rank, world, local, barrier):
         ids = [lib.MergeGroup.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         g = lib.MergeGroup.nccl(a, ids[0], rank, world)
+    elif args.merge_transport == "shm":
+        seg = ["/pa_merge_bench_%d" % os.getpid()]
+        dist.broadcast_object_list(seg, src=0)
+        g = lib.MergeGroup.shm(a, seg[0], rank, world)
     else:
         from parca_agent_b200.host_transport import GlooTransport
         g = lib.MergeGroup.host(a, GlooTransport(), rank, world)
@@ -356,6 +361,9 @@ def run_mode_b(args, rank, world, local, barrier):
                "e2e": {"value": total * len(e2e_times) / float(tmax[2]), "unit": "samples/s", "h2d_bytes_per_step": int((w.n * 64 + w.n_frame_ids * 8) * world),
                        "d2h_bytes_per_step": int(n), "steps": len(e2e_times), "stages_ms_last_step_rank0": stage_ms},
                "transport": ("NCCL over NVLink, called from the library" if args.merge_transport == "nccl" else
+                             "page-locked shared-memory mailboxes (pa_merge_create_shm): every exchange is GPU -> own mailbox -> peer GPUs by DMA over "
+                             "each GPU's own PCIe link, process-shared barriers in between; the exchanged BYTES are the same as over NCCL"
+                             if args.merge_transport == "shm" else
                              "host callbacks over gloo (pa_merge_create_host): every exchange is staged device -> pinned host -> TCP loopback -> device; "
                              "the exchanged BYTES are the same as over NCCL, the exchange TIME is not representative of NVLink"),
                "exchange_payload_bytes_per_step_all_ranks": int(float(t[3])), "exchange_payload_bytes_per_row": float(t[3]) / total,

@@ -295,6 +295,10 @@ typedef struct pa_merge_host_transport {
   int (*allreduce_min_u32)(void* user, uint32_t* buf, uint64_t count);
 } pa_merge_host_transport;
 int pa_merge_create_host(pa_agg* member, const pa_merge_host_transport* t, uint32_t rank, uint32_t world, pa_merge** out);
+/* one member per call; the exchange runs through ONE POSIX shared-memory segment `name` ("/...", created by rank 0, mapped and page-locked by
+ * every rank): each GPU copies its keys into its own mailbox and the blocks it needs out of the others' over its own PCIe link, with
+ * process-shared barriers in between. Needs nothing but CUDA and /dev/shm. mailbox_bytes: 0 = 64 MiB per rank (larger payloads go in rounds). */
+int pa_merge_create_shm(pa_agg* member, const char* name, uint32_t rank, uint32_t world, uint64_t mailbox_bytes, pa_merge** out);
 int pa_merge_create_local(pa_agg* const* members, uint32_t n, pa_merge** out);
 int pa_merge_nccl_unique_id(uint8_t* id128);
 int pa_merge_create_nccl(pa_agg* member, const uint8_t* id128, uint32_t rank, uint32_t world, pa_merge** out);

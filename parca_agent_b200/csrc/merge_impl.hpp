@@ -18,7 +18,13 @@
 // several rings), plain device copies on a shared stream.
 #pragma once
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <nccl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+
+#include <atomic>
 
 namespace pa {
 
@@ -81,6 +87,22 @@ enum { CTL_MERGE = 0 /* MergeCtl: 8 words */, CTL_OWNER = 8 /* n_claimed, zero_c
 
 }  // namespace pa
 
+namespace pa {
+// Shared-memory transport (pa_merge_create_shm): ONE POSIX shm segment that every process of the group maps and page-locks.
+// A collective is: every rank DMAs its block from its GPU into its own mailbox (over its own PCIe link), a process-shared
+// barrier, every rank DMAs the blocks it needs out of the others' mailboxes into its GPU, another barrier. No NCCL, no
+// sockets; payloads larger than a mailbox go in rounds. Header first, then `world` mailboxes of mailbox_bytes each.
+struct ShmHeader {
+  std::atomic<uint32_t> ready;     // rank 0 has initialised the segment
+  uint32_t world;
+  uint64_t mailbox_bytes;
+  std::atomic<uint32_t> arrive, gen;  // barrier: arrival counter + generation
+  std::atomic<uint32_t> failed;    // a rank gave up (timeout / error): everybody leaves the barrier with an error
+  uint64_t desc[kMaxWorld][2 * kMaxWorld + 2];  // per rank: scounts | sdispls | total of the all-to-all in flight
+};
+constexpr size_t kShmHeaderBytes = (sizeof(ShmHeader) + 4095) & ~(size_t)4095;
+}  // namespace pa
+
 struct pa_merge {
   std::vector<pa_agg*> members;   // the shards this process drives
   std::vector<uint32_t> ranks;    // their ranks in the group
@@ -91,6 +113,12 @@ struct pa_merge {
   pa_merge_host_transport host_copy{};
   uint8_t *h_xs = nullptr, *h_xr = nullptr;       // pinned staging of the host transport
   size_t h_xs_cap = 0, h_xr_cap = 0;
+  // shared-memory transport
+  uint8_t* shm = nullptr;
+  size_t shm_len = 0;
+  std::string shm_name;
+  bool shm_owner = false, shm_registered = false;
+  DBuf shm_scratch;                               // device scratch of the all-reduce
   std::vector<MergeBufs> mb;
   std::vector<cudaStream_t> saved_streams;
   std::string err;
@@ -161,6 +189,102 @@ static int pin_room(pa_merge* g, size_t bytes) {
   return PA_OK;
 }
 
+// ---- shared-memory transport ---------------------------------------------------------------------------------------------
+static ShmHeader* shm_hdr(pa_merge* g) { return reinterpret_cast<ShmHeader*>(g->shm); }
+static uint8_t* shm_box(pa_merge* g, uint32_t r) { return g->shm + kShmHeaderBytes + (size_t)r * shm_hdr(g)->mailbox_bytes; }
+static int shm_barrier(pa_merge* g) {
+  ShmHeader* h = shm_hdr(g);
+  const uint32_t gen = h->gen.load(std::memory_order_acquire);
+  if (h->arrive.fetch_add(1, std::memory_order_acq_rel) + 1 == h->world) {
+    h->arrive.store(0, std::memory_order_relaxed);
+    h->gen.fetch_add(1, std::memory_order_release);
+    return PA_OK;
+  }
+  const double t0 = now_ms();
+  uint32_t spins = 0;
+  while (h->gen.load(std::memory_order_acquire) == gen) {
+    if (h->failed.load(std::memory_order_relaxed)) return g->fail(PA_EIO, "shared-memory transport: another rank failed");
+    if ((++spins & 0x3FF) == 0) {
+      sched_yield();
+      if (now_ms() - t0 > 120000.0) { h->failed.store(1); return g->fail(PA_EIO, "shared-memory transport: barrier timed out (a rank of the group is gone)"); }
+    }
+  }
+  return PA_OK;
+}
+#define SBAR() do { int rcb_ = shm_barrier(g); if (rcb_) return rcb_; } while (0)
+// rank r's block `src` (bytes[r] bytes) lands at dst + displ[r] on every rank
+static int shm_allgatherv(pa_merge* g, const void* src, void* dst, const std::vector<uint64_t>& count, const std::vector<uint64_t>& displ) {
+  const uint32_t W = g->world, me = g->ranks[0];
+  const uint64_t M = shm_hdr(g)->mailbox_bytes;
+  cudaStream_t s = mstream(g, 0);
+  uint64_t maxc = 0;
+  for (uint32_t r = 0; r < W; r++) maxc = std::max(maxc, count[r]);
+  for (uint64_t off = 0; off < maxc; off += M) {
+    const uint64_t mine = count[me] > off ? std::min<uint64_t>(M, count[me] - off) : 0;
+    if (mine) MCK(cudaMemcpyAsync(shm_box(g, me), (const uint8_t*)src + off, mine, cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    SBAR();
+    for (uint32_t r = 0; r < W; r++) {
+      const uint64_t n = count[r] > off ? std::min<uint64_t>(M, count[r] - off) : 0;
+      if (n) MCK(cudaMemcpyAsync((uint8_t*)dst + displ[r] + off, shm_box(g, r), n, cudaMemcpyHostToDevice, s));
+    }
+    MCK(cudaStreamSynchronize(s));
+    SBAR();  // nobody overwrites its mailbox before everybody has read it
+  }
+  g->nvlink_bytes += count[me] * (W - 1);
+  return PA_OK;
+}
+static int shm_alltoallv(pa_merge* g, const void* send, const std::vector<uint64_t>& sc, const std::vector<uint64_t>& sd, void* recv, const std::vector<uint64_t>& rd) {
+  const uint32_t W = g->world, me = g->ranks[0];
+  ShmHeader* h = shm_hdr(g);
+  const uint64_t M = h->mailbox_bytes;
+  cudaStream_t s = mstream(g, 0);
+  uint64_t tot = 0;
+  for (uint32_t r = 0; r < W; r++) { h->desc[me][r] = sc[r]; h->desc[me][W + r] = sd[r]; tot = std::max(tot, sd[r] + sc[r]); }
+  h->desc[me][2 * W] = tot;
+  SBAR();
+  uint64_t maxtot = 0;
+  for (uint32_t r = 0; r < W; r++) maxtot = std::max<uint64_t>(maxtot, h->desc[r][2 * W]);
+  for (uint64_t off = 0; off < maxtot; off += M) {  // round: bytes [off, off + M) of every rank's flat send buffer
+    const uint64_t mine = tot > off ? std::min<uint64_t>(M, tot - off) : 0;
+    if (mine) MCK(cudaMemcpyAsync(shm_box(g, me), (const uint8_t*)send + off, mine, cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    SBAR();
+    for (uint32_t j = 0; j < W; j++) {  // what rank j has for me in this round
+      const uint64_t b0 = h->desc[j][W + me], b1 = b0 + h->desc[j][me];
+      const uint64_t lo = std::max<uint64_t>(b0, off), hi = std::min<uint64_t>(b1, off + M);
+      if (hi > lo) MCK(cudaMemcpyAsync((uint8_t*)recv + rd[j] + (lo - b0), shm_box(g, j) + (lo - off), hi - lo, cudaMemcpyHostToDevice, s));
+    }
+    MCK(cudaStreamSynchronize(s));
+    SBAR();
+  }
+  for (uint32_t r = 0; r < W; r++) if (r != me) g->nvlink_bytes += sc[r];
+  return PA_OK;
+}
+static int shm_allreduce_min(pa_merge* g, uint32_t* buf, size_t count) {
+  const uint32_t W = g->world, me = g->ranks[0];
+  const uint64_t M = shm_hdr(g)->mailbox_bytes & ~(uint64_t)3;
+  cudaStream_t s = mstream(g, 0);
+  const uint64_t bytes = (uint64_t)count * 4;
+  MCK(g->shm_scratch.ensure(std::min<uint64_t>(M, bytes)));
+  for (uint64_t off = 0; off < bytes; off += M) {
+    const uint64_t n = std::min<uint64_t>(M, bytes - off);
+    MCK(cudaMemcpyAsync(shm_box(g, me), (const uint8_t*)buf + off, n, cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    SBAR();
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g->members[0]->G, (n / 4 + 2047) / 2048));
+    for (uint32_t r = 0; r < W; r++) {
+      if (r == me) continue;
+      MCK(cudaMemcpyAsync(g->shm_scratch.p, shm_box(g, r), n, cudaMemcpyHostToDevice, s));
+      k_min_u32<<<grid, kThreads, 0, s>>>((uint32_t*)((uint8_t*)buf + off), g->shm_scratch.as<uint32_t>(), n / 4);
+    }
+    MCK(cudaStreamSynchronize(s));
+    SBAR();
+  }
+  g->nvlink_bytes += bytes * 2 * (W - 1) / W;
+  return PA_OK;
+}
+
 // host transport: device buffers are staged through pinned memory around the caller's collective (one member per process)
 static int xroom(pa_merge* g, size_t send_bytes, size_t recv_bytes) {
   auto grow = [&](uint8_t*& p, size_t& cap, size_t need) -> int {
@@ -183,6 +307,14 @@ static int xroom(pa_merge* g, size_t send_bytes, size_t recv_bytes) {
 // all-gather `bytes` from every rank's device buffer into every member's `dst` (world x bytes)
 static int t_allgather(pa_merge* g, const std::vector<const void*>& src, const std::vector<void*>& dst, size_t bytes) {
   const size_t L = g->members.size();
+  if (g->shm) {
+    const double th0 = now_ms();
+    std::vector<uint64_t> cnt(g->world, bytes), dsp(g->world);
+    for (uint32_t r = 0; r < g->world; r++) dsp[r] = (uint64_t)r * bytes;
+    int rc = shm_allgatherv(g, src[0], dst[0], cnt, dsp);
+    g->ms_exchange_wait += now_ms() - th0;
+    return rc;
+  }
   if (g->host) {
     const double th0 = now_ms();
     int rc = xroom(g, bytes, (size_t)g->world * bytes);
@@ -210,6 +342,18 @@ static int t_allgather(pa_merge* g, const std::vector<const void*>& src, const s
 // the same, landing in host memory (out: world x bytes); synchronises
 static int t_allgather_host(pa_merge* g, const std::vector<const void*>& src, size_t bytes, std::vector<uint8_t>& out) {
   const size_t L = g->members.size();
+  if (g->shm && bytes <= shm_hdr(g)->mailbox_bytes) {  // small control blocks: straight out of the mailboxes, no trip back through the device
+    const double th0 = now_ms();
+    cudaStream_t s = mstream(g, 0);
+    if (bytes) MCK(cudaMemcpyAsync(shm_box(g, g->ranks[0]), src[0], bytes, cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    SBAR();
+    out.resize((size_t)g->world * bytes);
+    for (uint32_t r = 0; r < g->world; r++) memcpy(out.data() + (size_t)r * bytes, shm_box(g, r), bytes);
+    SBAR();
+    g->ms_exchange_wait += now_ms() - th0;
+    return PA_OK;
+  }
   std::vector<void*> dst(L);
   for (size_t i = 0; i < L; i++) {
     MCK(cudaSetDevice(g->members[i]->device));
@@ -230,6 +374,12 @@ static int t_allgather_host(pa_merge* g, const std::vector<const void*>& src, si
 // all-gather with per-rank byte counts; dst holds rank r's block at displ[r]
 static int t_allgatherv(pa_merge* g, const std::vector<const void*>& src, const std::vector<void*>& dst, const std::vector<uint64_t>& count, const std::vector<uint64_t>& displ) {
   const size_t L = g->members.size();
+  if (g->shm) {
+    const double th0 = now_ms();
+    int rc = shm_allgatherv(g, src[0], dst[0], count, displ);
+    g->ms_exchange_wait += now_ms() - th0;
+    return rc;
+  }
   if (g->host) {
     const double th0 = now_ms();
     uint64_t total = 0;
@@ -267,6 +417,12 @@ static int t_allgatherv(pa_merge* g, const std::vector<const void*>& src, const 
 static int t_alltoallv(pa_merge* g, const std::vector<const void*>& send, const std::vector<std::vector<uint64_t>>& scount, const std::vector<std::vector<uint64_t>>& sdispl,
                        const std::vector<void*>& recv, const std::vector<std::vector<uint64_t>>& rcount, const std::vector<std::vector<uint64_t>>& rdispl) {
   const size_t L = g->members.size();
+  if (g->shm) {
+    const double th0 = now_ms();
+    int rc = shm_alltoallv(g, send[0], scount[0], sdispl[0], recv[0], rdispl[0]);
+    g->ms_exchange_wait += now_ms() - th0;
+    return rc;
+  }
   if (g->host) {
     const double th0 = now_ms();
     uint64_t stot = 0, rtot = 0;
@@ -307,6 +463,12 @@ static int t_alltoallv(pa_merge* g, const std::vector<const void*>& send, const 
 static int t_allreduce_min(pa_merge* g, const std::vector<uint32_t*>& buf, size_t count) {
   const size_t L = g->members.size();
   if (!count) return PA_OK;
+  if (g->shm) {
+    const double th0 = now_ms();
+    int rc = shm_allreduce_min(g, buf[0], count);
+    g->ms_exchange_wait += now_ms() - th0;
+    return rc;
+  }
   if (g->host) {
     const double th0 = now_ms();
     int rc = xroom(g, count * 4, 1);
@@ -909,6 +1071,57 @@ int pa_merge_create_host(pa_agg* member, const pa_merge_host_transport* t, uint3
   *out = g;
   return PA_OK;
 }
+int pa_merge_create_shm(pa_agg* member, const char* name, uint32_t rank, uint32_t world, uint64_t mailbox_bytes, pa_merge** out) {
+  if (!member || !name || name[0] != '/' || !out || world == 0 || world > (uint32_t)kMaxWorld || rank >= world) return PA_EINVAL;
+  if (mailbox_bytes == 0) mailbox_bytes = 64ull << 20;
+  mailbox_bytes = (mailbox_bytes + 4095) & ~4095ull;
+  const size_t len = kShmHeaderBytes + (size_t)world * mailbox_bytes;
+  int fd = -1;
+  if (rank == 0) {
+    shm_unlink(name);  // a stale segment of a previous run
+    fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)len) != 0) { if (fd >= 0) close(fd); return PA_EIO; }
+  } else {
+    const double t0 = now_ms();
+    for (;;) {  // wait for rank 0 to create and size it
+      fd = shm_open(name, O_RDWR, 0600);
+      struct stat st;
+      if (fd >= 0 && fstat(fd, &st) == 0 && (size_t)st.st_size >= len) break;
+      if (fd >= 0) { close(fd); fd = -1; }
+      if (now_ms() - t0 > 120000.0) return PA_EIO;
+      sched_yield();
+    }
+  }
+  void* base = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (base == MAP_FAILED) return PA_ENOMEM;
+  ShmHeader* h = reinterpret_cast<ShmHeader*>(base);
+  if (rank == 0) {
+    memset(base, 0, kShmHeaderBytes);
+    h->world = world;
+    h->mailbox_bytes = mailbox_bytes;
+    h->ready.store(1, std::memory_order_release);
+  } else {
+    const double t0 = now_ms();
+    while (h->ready.load(std::memory_order_acquire) != 1) { if (now_ms() - t0 > 120000.0) { munmap(base, len); return PA_EIO; } sched_yield(); }
+    if (h->world != world || h->mailbox_bytes != mailbox_bytes) { munmap(base, len); return PA_EINVAL; }
+  }
+  pa_merge* g = new pa_merge();
+  g->world = world;
+  g->use_nccl = true;  // one stream per member; the (synchronous) collectives order the ranks
+  g->shm = (uint8_t*)base;
+  g->shm_len = len;
+  g->shm_name = name;
+  g->shm_owner = rank == 0;
+  cudaSetDevice(member->device);
+  if (cudaHostRegister(base, len, cudaHostRegisterPortable) == cudaSuccess) g->shm_registered = true;  // DMA straight into / out of the mailboxes
+  else cudaGetLastError();
+  g->members.push_back(member);
+  g->ranks.push_back(rank);
+  g->mb.resize(1);
+  *out = g;
+  return PA_OK;
+}
 void pa_merge_destroy(pa_merge* g) {
   if (!g) return;
   for (size_t i = 0; i < g->members.size(); i++) {
@@ -916,7 +1129,13 @@ void pa_merge_destroy(pa_merge* g) {
     cudaStreamSynchronize(g->members[i]->s_comp);
     g->mb[i].release();
   }
-  if (g->use_nccl && !g->host) for (auto c : g->comms) nccl_api()->CommDestroy(c);
+  if (g->use_nccl && !g->host && !g->shm) for (auto c : g->comms) nccl_api()->CommDestroy(c);
+  if (g->shm) {
+    if (g->shm_registered) cudaHostUnregister(g->shm);
+    g->shm_scratch.release();
+    munmap(g->shm, g->shm_len);
+    if (g->shm_owner) shm_unlink(g->shm_name.c_str());
+  }
   if (g->h_xs) cudaFreeHost(g->h_xs);
   if (g->h_xr) cudaFreeHost(g->h_xr);
   if (g->registered) cudaHostUnregister(g->registered);

@@ -20,7 +20,7 @@ EXPORTS = [
     "pa_agg_flush", "pa_agg_release", "pa_agg_stage", "pa_agg_process", "pa_agg_collect", "pa_agg_last_kernel_ms",
     "pa_agg_debug_stack_ids", "pa_agg_debug_stack_counts", "pa_agg_debug_pair_counts", "pa_agg_stacktraces", "pa_agg_last_stack_ids", "pa_agg_shard_sizes", "pa_agg_shard_export", "pa_agg_stage_device", "pa_agg_stage_device_parts", "pa_agg_discard", "pa_ipc_compress_lz4", "pa_ipc_free", "pa_fix_truncation", "pa_xxh64",
     "pa_merge_create_local", "pa_merge_nccl_unique_id", "pa_merge_create_nccl", "pa_merge_destroy", "pa_merge_last_error", "pa_merge_process",
-    "pa_merge_plan", "pa_merge_collect", "pa_merge_flush", "pa_merge_last_stats", "pa_merge_create_host",
+    "pa_merge_plan", "pa_merge_collect", "pa_merge_flush", "pa_merge_last_stats", "pa_merge_create_host", "pa_merge_create_shm",
 ]
 
 
@@ -78,6 +78,7 @@ def lib():
         L.pa_merge_nccl_unique_id.argtypes = [C.c_char_p]
         L.pa_merge_create_nccl.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(vp)]
         L.pa_merge_create_host.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+        L.pa_merge_create_shm.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(vp)]
         L.pa_merge_destroy.argtypes = [vp]
         L.pa_merge_destroy.restype = None
         L.pa_merge_last_error.argtypes = [vp]
@@ -307,6 +308,16 @@ class MergeGroup:
         g = cls(h, [member])
         g._transport = transport  # the callbacks must outlive the group
         return g
+
+    @classmethod
+    def shm(cls, member, name, rank, world, mailbox_bytes=0):
+        """One member per process; the exchange goes through the POSIX shared-memory segment `name` ("/..."), which rank 0 creates
+        and every rank page-locks: GPU -> own mailbox -> the other GPUs, each over its own PCIe link. No NCCL, no sockets."""
+        h = C.c_void_p()
+        rc = lib().pa_merge_create_shm(member.h, name.encode(), rank, world, mailbox_bytes, C.byref(h))
+        if rc != 0:
+            raise PaError(rc, "pa_merge_create_shm failed")
+        return cls(h, [member])
 
     def _ck(self, rc):
         if rc != 0:

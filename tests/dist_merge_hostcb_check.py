@@ -1,5 +1,7 @@
-"""Run under torch.distributed.run with the gloo backend: mode B through pa_merge_create_host — one shard aggregator per
-PROCESS, collectives on host buffers over gloo, the merged stream in POSIX shared memory that every rank maps. All ranks may
+"""Run under torch.distributed.run with the gloo backend: mode B through pa_merge_create_host (collectives on host buffers
+over gloo) or, with PA_MERGE_TRANSPORT=shm, pa_merge_create_shm (mailboxes in one page-locked shared-memory segment;
+PA_SHM_MAILBOX bytes per rank, small values force multi-round collectives) — one shard aggregator per
+PROCESS, the merged stream in POSIX shared memory that every rank maps. All ranks may
 share ONE GPU (PA_ONE_GPU=1, the driver's 1-GPU test tier): everything but the NCCL calls themselves is the code the NCCL
 group runs (per-process size exchanges, per-process parts of the sliced buffers, validity words completed across processes,
 rank 0 adding dictionaries and metadata). Rank 0 compares the bytes with the CPU oracle on [shard 0 rows, shard 1 rows, ...]."""
@@ -24,7 +26,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
+    kind = os.environ.get("PA_MERGE_TRANSPORT", "gloo")
     transport = GlooTransport()
+    seg = ["/pa_merge_test_%d" % os.getpid()]
+    dist.broadcast_object_list(seg, src=0)
     cases = [synth.edge_workload(seed=33, n=5000, hash_mode=abi.PA_HASH_PROVIDED, external=False),
              synth.edge_workload(seed=34, n=4000, hash_mode=abi.PA_HASH_XXH64X2, external=False),
              synth.config3(n=120_000, u=9_000, p=4_096, npids=96, lsets=6),
@@ -35,7 +40,10 @@ def main():
             idx = [idx[0]] + [np.zeros(0, np.int64)] * (world - 2) + [np.concatenate(idx[1:])] if world > 2 else idx
         part = w.rows(idx[rank])
         a = lib.from_workload(part, device=local, frame_id_bytes=4 if ci == 2 else 8)
-        group = lib.MergeGroup.host(a, transport, rank, world)
+        if kind == "shm":
+            group = lib.MergeGroup.shm(a, "%s_%d" % (seg[0], ci), rank, world, int(os.environ.get("PA_SHM_MAILBOX", "0")))
+        else:
+            group = lib.MergeGroup.host(a, transport, rank, world)
         want, st = oracle_py.run(w.rows(np.concatenate(idx))) if rank == 0 else (None, None)
         shm = None
         for rep in range(2):
@@ -72,7 +80,7 @@ def main():
                 pass
     assert not transport.errors, transport.errors
     if rank == 0:
-        print("merge-hostcb ok world=%d" % world)
+        print("merge-hostcb ok world=%d transport=%s" % (world, kind))
     dist.destroy_process_group()
 
 

@@ -166,14 +166,16 @@ def test_single_aggregator_still_works_after_merge(oracle, gpu):
         a.close()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_multi_process_group_over_host_transport(world):
-    """one shard per PROCESS (gloo collectives on host buffers, stream in shared memory), all processes on this one GPU"""
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", PA_ONE_GPU="1")
+@pytest.mark.parametrize("world,transport,mailbox", [(2, "gloo", 0), (3, "gloo", 0), (2, "shm", 0), (3, "shm", 0), (3, "shm", 8192)])
+def test_multi_process_group_over_host_transport(world, transport, mailbox):
+    """one shard per PROCESS, all processes on this one GPU, the stream in shared memory: the exchange over gloo callbacks on host
+    buffers (pa_merge_create_host) or through page-locked shared-memory mailboxes (pa_merge_create_shm; an 8 KiB mailbox makes
+    every collective take many rounds)"""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", PA_ONE_GPU="1", PA_MERGE_TRANSPORT=transport, PA_SHM_MAILBOX=str(mailbox))
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-                        "--master-port", str(29533 + world), os.path.join(ROOT, "tests", "dist_merge_hostcb_check.py")], capture_output=True, text=True, env=env, timeout=900)
+                        "--master-port", str(29533 + world + (10 if transport == "shm" else 0) + (5 if mailbox else 0)), os.path.join(ROOT, "tests", "dist_merge_hostcb_check.py")], capture_output=True, text=True, env=env, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert "merge-hostcb ok world=%d" % world in p.stdout
+    assert "merge-hostcb ok world=%d transport=%s" % (world, transport) in p.stdout
 
 
 def test_nccl_group_on_two_gpus():
