@@ -50,6 +50,10 @@ def parse():
                     "exchange, BASELINE config 4 at N=8); by default it is timed after the headline (mode A) and reported under \"mode_b\"")
     ap.add_argument("--merge-rows", type=int, default=12_500_000, help="mode B rows per GPU (config 4 = 100M / 8)")
     ap.add_argument("--mode-b-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--config4-local", type=int, default=0, metavar="S", help="BASELINE config 4 at FULL size on ONE GPU: S shard aggregators (S x --merge-rows rows) in "
+                    "one in-process merge group on cuda:0 (the same kernels and host code as the multi-GPU group, device copies as the transport); prints its own JSON line")
+    ap.add_argument("--config4-single", type=int, default=0, metavar="S", help="the SAME S x --merge-rows row stream through ONE aggregator (no merge): its stream digest must "
+                    "equal --config4-local's")
     ap.add_argument("--merge-transport", default="shm", choices=["shm", "host", "nccl"],
                     help="how the merged-batch leg exchanges its dictionary keys: shm = page-locked shared-memory mailboxes, every GPU over its own PCIe "
                          "link (default: validated on hardware with several processes); host = host callbacks over gloo; nccl = NCCL over NVLink from "
@@ -384,8 +388,99 @@ def run_mode_b(args, rank, world, local, barrier):
     return out
 
 
+def run_config4_one_gpu(args):
+    """BASELINE config 4 (100M samples x 64 frames, 1M unique stacks, 1M distinct frames, 65 536 pids) at full size on ONE
+    B200: either S shard aggregators in an in-process merge group (mode B with device copies as the transport), or the
+    concatenated stream through one aggregator. Both print sha256 of the IPC stream: equal digests tie the merged record
+    at full size to the single-aggregator path (which is byte-compared with the CPU port at 10M rows)."""
+    import hashlib
+
+    from parca_agent_b200 import abi, lib, synth
+    merged = args.config4_local > 0
+    S = args.config4_local or args.config4_single
+    mode = abi.PA_HASH_PROVIDED if args.hash_mode == "provided" else abi.PA_HASH_XXH64X2
+    t_gen = time.perf_counter()
+    parts = [synth.config4_part(r, S, rows_per_gpu=args.merge_rows, hash_mode=mode) for r in range(S)]
+    for p in parts[1:]:  # the tables are equal by construction: keep one copy
+        p.strings, p.frames, p.labelsets, p.stack_table = parts[0].strings, parts[0].frames, parts[0].labelsets, parts[0].stack_table
+    if merged:
+        aggs = []
+        for p in parts:
+            a = lib.from_workload(p, device=0, max_samples=p.n, max_frames=p.n_frame_ids, chunk_samples=1 << 20, flags=abi.PA_CFG_SINGLE_RING)
+            lib.load(a, p)
+            aggs.append(a)
+        g = lib.MergeGroup.local(aggs)
+        run_once = g.process
+        flush = g.flush
+
+        def stage():
+            for a in aggs:
+                a.stage()
+
+        def reload():
+            for a, p in zip(aggs, parts):
+                lib.load(a, p)
+    else:
+        w = synth.concat(parts)
+        parts = None
+        a = lib.from_workload(w, device=0, max_samples=w.n, max_frames=w.n_frame_ids, chunk_samples=1 << 20, flags=abi.PA_CFG_SINGLE_RING)
+        lib.load(a, w)
+        aggs, g = [a], None
+        run_once, flush, stage = a.process, a.flush, a.stage
+
+        def reload():
+            lib.load(a, w)
+    t_gen = time.perf_counter() - t_gen
+    total = args.merge_rows * S
+    stage()
+    for _ in range(max(1, args.warmup)):
+        run_once()
+    wall = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        run_once()
+        wall.append(time.perf_counter() - t0)
+    groups = {name: float(np.sum([x.kernel_ms(name)[0] for x in aggs])) for name in ("header", "hash", "rank", "locations", "labels", "dicts", "total")}
+    stats = g.stats() if g else None
+    if g:
+        g.plan()
+        res = g.collect()
+    else:
+        res = a.collect()
+    digest = hashlib.sha256(res.ipc).hexdigest()
+    out = {"metric": "config4_one_gpu_%s" % ("merged_%d_shards" % S if merged else "single_aggregator"),
+           "workload": "config 4: %d samples x 64 frames, %d unique stacks, %d distinct frames, %d pids, %s" % (
+               total, 125_000 * S, 131_072 * S, 8_192 * S, ("%d shard aggregators of %d rows in one in-process merge group" % (S, args.merge_rows)) if merged
+               else "one aggregator over the concatenated stream"),
+           "value": total / float(np.mean(wall)), "unit": "samples/s", "ms_per_step": 1e3 * float(np.mean(wall)), "steps": args.steps, "n_gpus": 1,
+           "kernel_groups_ms_sum_over_members": groups, "rows": res.n_rows, "unique_stacks": res.n_unique_stacks, "locations": res.n_locations,
+           "functions": res.n_functions, "location_indices": res.n_location_indices, "ipc_bytes": res.ipc_len, "ipc_sha256": digest,
+           "workload_generation_and_ring_fill_s": t_gen}
+    if stats:
+        out["exchange_payload_bytes_per_step"] = stats["nvlink_bytes"]
+        out["exchange_payload_bytes_per_row"] = stats["nvlink_bytes"] / total
+    e2e = []
+    for _ in range(max(0, args.e2e_steps - 1)):
+        reload()
+        t0 = time.perf_counter()
+        res = flush()
+        e2e.append(time.perf_counter() - t0)
+    if e2e:
+        out["e2e"] = {"value": total / float(np.mean(e2e)), "unit": "samples/s", "ms": 1e3 * float(np.mean(e2e)), "h2d_bytes_per_step": int(total * (64 + 64 * 8)),
+                      "d2h_bytes_per_step": int(res.ipc_len), "note": "all shards' rings go through this ONE GPU's PCIe link",
+                      "stages_ms": {"h2d_ms": res.h2d_ms, "gpu_ms": res.gpu_ms, "d2h_ms": res.d2h_ms, "host_ms": res.host_ms}}
+        out["e2e_ipc_sha256_equal"] = hashlib.sha256(res.ipc).hexdigest() == digest
+    print(json.dumps(out))
+    if g:
+        g.close()
+    for x in aggs:
+        x.close()
+
+
 def main():
     args = parse()
+    if args.config4_local or args.config4_single:
+        return run_config4_one_gpu(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -70,7 +70,7 @@ class Workload:
         else:
             f = self.stack_table.shape[1]
             table = self.stack_table if out.dtype == self.stack_table.dtype else self.stack_table.astype(out.dtype)
-            np.take(table, self.stack_choice, axis=0, out=out.reshape(self.n, f))
+            np.take(table, self.stack_choice, axis=0, out=out.reshape(self.n, f), mode="clip")  # indices are valid by construction; the default mode buffers `out` (45x slower)
 
     def head(self, n):
         """First n rows as a new workload (frames are a prefix of the stream)."""
@@ -267,6 +267,26 @@ def config4_shard(rank, world, n_total=100_000_000, hash_mode=abi.PA_HASH_XXH64X
     return _pid_shard("cfg4", 0x5EED0004, rank, world, n_total // world, 1_000_000 // world * 2, 1_048_576, 65_536 // world, hash_mode)
 
 
+_CONFIG4_TABLES = {}
+
+
+def _config4_tables(U, P, npids, F, threads, world, seed):
+    """The tables every rank of a merged batch shares (strings, frames, stack table, labelsets): built once per process."""
+    key = (U, P, npids, F, threads, world, seed)
+    if key not in _CONFIG4_TABLES:
+        _CONFIG4_TABLES.clear()
+        rng = np.random.Generator(np.random.PCG64(seed))
+        st = StringTable()
+        frames = _frame_table(rng, st, P, 0.8, 0.1, "python")
+        stack_table = rng.integers(0, P, (U, F), dtype=np.uint64)
+        n_comm, n_node, v_node = st.sid("comm"), st.sid("node"), st.sid("node-0")
+        labelsets = [[(n_comm, st.sid("proc-%05d" % q)), (n_node, v_node)] for q in range(npids)]
+        thread_comm = np.array([st.sid("worker-%02d" % t) for t in range(threads)], dtype=np.uint32)
+        owner = np.array([xxh64_u32(1000 + q) % world for q in range(npids)], dtype=np.int64)
+        _CONFIG4_TABLES[key] = (st, frames, stack_table, labelsets, thread_comm, owner)
+    return _CONFIG4_TABLES[key]
+
+
 def config4_part(rank, world, rows_per_gpu=12_500_000, stacks_per_gpu=125_000, frames_per_gpu=131_072, pids_per_gpu=8_192,
                  hash_mode=abi.PA_HASH_XXH64X2, seed=0x5EED0004):
     """One rank's ring of a MERGED batch (mode B): BASELINE config 4 at world == 8 (100M samples x 64 frames, 1M unique stacks,
@@ -275,15 +295,8 @@ def config4_part(rank, world, rows_per_gpu=12_500_000, stacks_per_gpu=125_000, f
     are global); the rows are this rank's pids only. Every rank draws its stacks from the WHOLE stack table, so nearly every
     stack occurs on every GPU — the hardest case for the dictionary merge."""
     U, P, npids, F = stacks_per_gpu * world, frames_per_gpu * world, pids_per_gpu * world, 64
-    rng = np.random.Generator(np.random.PCG64(seed))
-    st = StringTable()
-    frames = _frame_table(rng, st, P, 0.8, 0.1, "python")
-    stack_table = rng.integers(0, P, (U, F), dtype=np.uint64)
-    n_comm, n_node, v_node = st.sid("comm"), st.sid("node"), st.sid("node-0")
-    labelsets = [[(n_comm, st.sid("proc-%05d" % q)), (n_node, v_node)] for q in range(npids)]
     threads = 16
-    thread_comm = np.array([st.sid("worker-%02d" % t) for t in range(threads)], dtype=np.uint32)
-    owner = np.array([xxh64_u32(1000 + q) % world for q in range(npids)], dtype=np.int64)
+    st, frames, stack_table, labelsets, thread_comm, owner = _config4_tables(U, P, npids, F, threads, world, seed)
     mine = np.nonzero(owner == rank)[0]
     rr = np.random.Generator(np.random.PCG64(seed + 1 + rank))
     N = rows_per_gpu
