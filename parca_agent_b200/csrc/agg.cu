@@ -368,7 +368,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
     a->external.emplace_back(cfg->external_labels[i].name_sid, cfg->external_labels[i].value_sid);
   }
   if (const char* hv = getenv("PA_HASH_VARIANT"))
-    a->hash_variant = strcmp(hv, "staged") == 0 ? 1 : (strcmp(hv, "direct") == 0 ? 0 : (strcmp(hv, "bulk") == 0 ? 3 : (strcmp(hv, "bulk6x2") == 0 ? 4 : 2)));
+    a->hash_variant = strcmp(hv, "staged") == 0 ? 1 : (strcmp(hv, "direct") == 0 ? 0 : (strcmp(hv, "bulk") == 0 ? 3 : (strcmp(hv, "bulk6x2") == 0 ? 4 : (strcmp(hv, "widepf") == 0 ? 5 : 2))));
   if (cudaFuncSetAttribute(k_hash_insert_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashStagedSmem) != cudaSuccess) return bail(PA_EIO);
   if (cudaFuncSetAttribute(k_ree_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, kOnepassPadSmem) != cudaSuccess) return bail(PA_EIO);
   if (cudaFuncSetAttribute(k_hash_insert_bulk<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BulkSmem<4, 3>)) != cudaSuccess) return bail(PA_EIO);
@@ -393,7 +393,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   cudaEventCreate(&a->ev_d2h1);
   for (int t = 0; t < T_COUNT; t++) { cudaEventCreate(&a->tm[t].a); cudaEventCreate(&a->tm[t].b); }
   const uint64_t N = a->cfg.max_samples, NF = a->cfg.max_frames;
-  if (a->idb == 4) a->hash_variant = 2;  // the narrow ring is read by the `wide` kernel (widening loads); the other variants take uint64 ids
+  if (a->idb == 4 && a->hash_variant != 5) a->hash_variant = 2;  // the narrow ring is read by the `wide` kernel (widening loads); the other variants take uint64 ids
   for (int r = 0; r < (a->single_ring ? 1 : 2); r++) {
     if (cudaHostAlloc((void**)&a->ring[r].hdr, N * sizeof(pa_sample_hdr), cudaHostAllocDefault) != cudaSuccess) return bail(PA_ENOMEM);
     if (cudaHostAlloc((void**)&a->ring[r].frames, std::max<uint64_t>(NF, 1) * a->idb + 64, cudaHostAllocMapped) != cudaSuccess) return bail(PA_ENOMEM);
@@ -940,7 +940,9 @@ static int pass_front(pa_agg* a) {
     ha.slot_of_row = a->d_slot.as<uint32_t>(); ha.tab = tab; ha.mask = P.mask; ha.ctr = ctr; ha.claimed = P.claimed;
     uint64_t rows = r1 - r0;
     int blocks = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)a->sms * (a->hash_variant == 1 ? 3 : 4));
-    if (a->idb == 4) k_hash_insert_wide32<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
+    if (a->hash_variant == 5 && a->idb == 4) k_hash_insert_widepf32<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
+    else if (a->hash_variant == 5) k_hash_insert_widepf<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
+    else if (a->idb == 4) k_hash_insert_wide32<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     else if (a->hash_variant == 3) k_hash_insert_bulk<4, 3><<<(int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 127) / 128, (uint64_t)a->sms)), 128, sizeof(BulkSmem<4, 3>), s>>>(ha);
     else if (a->hash_variant == 4) k_hash_insert_bulk<6, 2><<<(int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 191) / 192, (uint64_t)a->sms)), 192, sizeof(BulkSmem<6, 2>), s>>>(ha);
     else if (a->hash_variant == 1) k_hash_insert_staged<<<std::max(blocks, 1), kThreads, kHashStagedSmem, s>>>(ha);

@@ -57,7 +57,14 @@ struct Counters {
 
 // ---------------------------------------------------------------------------------------------
 // small helpers
-__device__ __forceinline__ unsigned long long rotl64(unsigned long long x, int r) { return (x << r) | (x >> (64 - r)); }
+// two funnel shifts (SHF) for any constant rotation; the generic (x << r) | (x >> (64 - r)) form compiled to four
+// instructions for r = 31 (shift, shift-as-IMAD, shift, LOP3), which is the rotation of every XXH64 round
+__device__ __forceinline__ unsigned long long rotl64(unsigned long long x, int r) {
+  uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+  if (r & 32) { const uint32_t t = lo; lo = hi; hi = t; }
+  const uint32_t nhi = __funnelshift_l(lo, hi, r & 31), nlo = __funnelshift_l(hi, lo, r & 31);
+  return ((unsigned long long)nhi << 32) | nlo;
+}
 __device__ __forceinline__ unsigned long long bswap64(unsigned long long x) {
   uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
   return ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
@@ -539,6 +546,140 @@ __global__ void __launch_bounds__(kThreads, 4) k_hash_insert_wide(HashArgs a) {
     wide_tile(a, r, valid, n_me, off_me);
   }
 }
+
+// Variant B3 ("widepf"): the lane layout of `wide` (two lanes per sample, 16-byte loads, thread-per-sample epilogue) with the
+// loads software-pipelined: batches of kPfU stripes ping-pong between two register buffers, the loads of batch i+1 are
+// issued before the rounds of batch i, across the two sub-steps of a tile and across tiles (the next tile's depths and
+// offsets are fetched one tile ahead). A warp therefore has kPfU..2*kPfU 16-byte loads in flight ALL the time instead of
+// 8 during a load phase and none during the ~340 instructions of arithmetic that follow. Ragged depths are handled by
+// predication (a warp iterates to its deepest sample), so there is no separate tail code.
+constexpr int kPfU = 4;
+template <bool kAllAligned, class IdT>
+__device__ __forceinline__ void pf_load(ulonglong2 (&w)[kPfU], const IdT* q, uint32_t ns, bool aligned, uint32_t s, bool whole) {
+  if (whole) {  // warp-uniform: every lane has all kPfU stripes
+#pragma unroll
+    for (int u = 0; u < kPfU; u++) w[u] = load_pair(q + 4 * (s + u), kAllAligned || aligned);
+  } else {
+#pragma unroll
+    for (int u = 0; u < kPfU; u++) w[u] = (s + u < ns) ? load_pair(q + 4 * (s + u), kAllAligned || aligned) : make_ulonglong2(0ull, 0ull);
+  }
+}
+__device__ __forceinline__ void pf_rounds(const ulonglong2 (&w)[kPfU], uint32_t ns, uint32_t s, bool whole, unsigned long long& a0, unsigned long long& a1,
+                                          unsigned long long& b0, unsigned long long& b1) {
+#pragma unroll
+  for (int u = 0; u < kPfU; u++) {
+    if (whole || s + u < ns) {
+      const unsigned long long mx = w[u].x * XP2, my = w[u].y * XP2;
+      a0 = xxh_round_pre(a0, mx); a1 = xxh_round_pre(a1, mx);
+      b0 = xxh_round_pre(b0, my); b1 = xxh_round_pre(b1, my);
+    }
+  }
+}
+struct PfSub {  // one sub-step (16 samples x 2 lanes) as this lane sees it
+  unsigned long long off;  // first id of the lane's sample
+  uint32_t ns;             // whole stripes of the lane's sample
+  uint32_t nsmax, nsmin;   // over the warp
+  bool aligned;
+};
+__device__ __forceinline__ PfSub pf_sub(uint32_t n_me, unsigned long long off_me, int src) {
+  const unsigned full = 0xFFFFFFFFu;
+  PfSub p;
+  p.off = __shfl_sync(full, off_me, src);
+  p.ns = __shfl_sync(full, n_me, src) >> 2;
+  p.nsmax = __reduce_max_sync(full, p.ns);
+  p.nsmin = __reduce_min_sync(full, p.ns);
+  p.aligned = (p.off & 1ull) == 0;
+  return p;
+}
+// All batches of one sub-step. On entry A holds the sub-step's first batch; on exit A holds the first batch of `nx` (if has_next).
+template <bool kAllAligned, class IdT>
+__device__ __forceinline__ void pf_run_sub(const IdT* frames, int h, const PfSub& cu, const PfSub& nx, bool has_next, ulonglong2 (&A)[kPfU], ulonglong2 (&B)[kPfU],
+                                           unsigned long long& a0, unsigned long long& a1, unsigned long long& b0, unsigned long long& b1) {
+  const IdT* q = frames + cu.off + 2 * h;
+  const IdT* qn = frames + nx.off + 2 * h;
+  uint32_t s = 0;
+  for (;;) {
+    bool more = s + kPfU < cu.nsmax;
+    if (more) pf_load<kAllAligned>(B, q, cu.ns, cu.aligned, s + kPfU, s + 2 * kPfU <= cu.nsmin);
+    else if (has_next) pf_load<kAllAligned>(B, qn, nx.ns, nx.aligned, 0, kPfU <= nx.nsmin);
+    pf_rounds(A, cu.ns, s, s + kPfU <= cu.nsmin, a0, a1, b0, b1);
+    s += kPfU;
+    if (!more) {
+#pragma unroll
+      for (int u = 0; u < kPfU; u++) A[u] = B[u];
+      break;
+    }
+    more = s + kPfU < cu.nsmax;
+    if (more) pf_load<kAllAligned>(A, q, cu.ns, cu.aligned, s + kPfU, s + 2 * kPfU <= cu.nsmin);
+    else if (has_next) pf_load<kAllAligned>(A, qn, nx.ns, nx.aligned, 0, kPfU <= nx.nsmin);
+    pf_rounds(B, cu.ns, s, s + kPfU <= cu.nsmin, a0, a1, b0, b1);
+    s += kPfU;
+    if (!more) break;
+  }
+}
+template <class IdT>
+__device__ __forceinline__ void hash_insert_widepf(const HashArgs& a, const IdT* frames) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, h = lane & 1, g = lane >> 1;
+  const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+  const uint32_t span = a.row1 - a.row0;
+  const uint32_t iters = (span + nwarps * 32 - 1) / (nwarps * 32);
+  if (iters == 0) return;
+  auto meta = [&](uint32_t it, uint32_t& r, bool& valid, uint32_t& n_me, unsigned long long& off_me) {
+    r = a.row0 + (it * nwarps + warp) * 32 + lane;
+    valid = r < a.row1;
+    n_me = valid ? a.nframes[r] : 0u;
+    off_me = valid ? a.frame_off[r] : 0ull;
+  };
+  uint32_t r, n_me; bool valid; unsigned long long off_me;
+  meta(0, r, valid, n_me, off_me);
+  ulonglong2 A[kPfU], B[kPfU];
+  PfSub s0 = pf_sub(n_me, off_me, g);
+  bool all_al = __all_sync(full, (off_me & 1ull) == 0);
+  if (all_al) pf_load<true>(A, frames + s0.off + 2 * h, s0.ns, true, 0, kPfU <= s0.nsmin);
+  else pf_load<false>(A, frames + s0.off + 2 * h, s0.ns, s0.aligned, 0, kPfU <= s0.nsmin);
+  for (uint32_t it = 0; it < iters; it++) {
+    const bool has_next = it + 1 < iters;
+    uint32_t r_nx = 0, n_nx = 0; bool valid_nx = false; unsigned long long off_nx = 0;
+    if (has_next) meta(it + 1, r_nx, valid_nx, n_nx, off_nx);
+    const PfSub s1 = pf_sub(n_me, off_me, 16 + g);
+    const PfSub t0 = pf_sub(n_nx, off_nx, g);
+    const bool nx_al = __all_sync(full, (off_nx & 1ull) == 0);
+    unsigned long long a0 = xxh_lane_init(0ull, 2 * h), b0 = xxh_lane_init(0ull, 2 * h + 1);
+    unsigned long long a1 = xxh_lane_init(kSeedLo, 2 * h), b1 = xxh_lane_init(kSeedLo, 2 * h + 1);
+    if (all_al) pf_run_sub<true>(frames, h, s0, s1, true, A, B, a0, a1, b0, b1);
+    else pf_run_sub<false>(frames, h, s0, s1, true, A, B, a0, a1, b0, b1);
+    unsigned long long c0 = xxh_lane_init(0ull, 2 * h), d0 = xxh_lane_init(0ull, 2 * h + 1);
+    unsigned long long c1 = xxh_lane_init(kSeedLo, 2 * h), d1 = xxh_lane_init(kSeedLo, 2 * h + 1);
+    // the next tile's first batch is loaded with ITS alignment class: a mixed pair of tiles takes the per-lane path for that batch
+    if (all_al && (nx_al || !has_next)) pf_run_sub<true>(frames, h, s1, t0, has_next, A, B, c0, c1, d0, d1);
+    else pf_run_sub<false>(frames, h, s1, t0, has_next, A, B, c0, c1, d0, d1);
+    // transpose: lane L gets accumulators 0,1 from lane 2*(L&15) and 2,3 from lane 2*(L&15)+1 of ITS half's sub-step
+    const int l0 = 2 * (lane & 15), l1 = l0 + 1;
+    const bool up = lane >= 16;
+    unsigned long long v0[4], v1[4], x, y;
+    x = __shfl_sync(full, a0, l0); y = __shfl_sync(full, c0, l0); v0[0] = up ? y : x;
+    x = __shfl_sync(full, b0, l0); y = __shfl_sync(full, d0, l0); v0[1] = up ? y : x;
+    x = __shfl_sync(full, a0, l1); y = __shfl_sync(full, c0, l1); v0[2] = up ? y : x;
+    x = __shfl_sync(full, b0, l1); y = __shfl_sync(full, d0, l1); v0[3] = up ? y : x;
+    x = __shfl_sync(full, a1, l0); y = __shfl_sync(full, c1, l0); v1[0] = up ? y : x;
+    x = __shfl_sync(full, b1, l0); y = __shfl_sync(full, d1, l0); v1[1] = up ? y : x;
+    x = __shfl_sync(full, a1, l1); y = __shfl_sync(full, c1, l1); v1[2] = up ? y : x;
+    x = __shfl_sync(full, b1, l1); y = __shfl_sync(full, d1, l1); v1[3] = up ? y : x;
+    const uint32_t nt = n_me & 3u;
+    const IdT* tp = frames + off_me + (n_me & ~3u);
+    unsigned long long t0w = nt > 0 ? load_one(tp) : 0ull, t1w = nt > 1 ? load_one(tp + 1) : 0ull, t2w = nt > 2 ? load_one(tp + 2) : 0ull;
+    Key128 k;
+    k.hi = xxh_finish_own(v0, 0ull, n_me, t0w, t1w, t2w);
+    k.lo = xxh_finish_own(v1, kSeedLo, n_me, t0w, t1w, t2w);
+    if (valid) *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = make_ulonglong2(bswap64(k.hi), bswap64(k.lo));
+    uint32_t slot = warp_insert(a.tab, a.mask, k, r, valid, a.ctr, a.claimed);
+    if (valid) a.slot_of_row[r] = slot;
+    r = r_nx; valid = valid_nx; n_me = n_nx; off_me = off_nx; s0 = t0; all_al = nx_al;
+  }
+}
+__global__ void __launch_bounds__(kThreads, 4) k_hash_insert_widepf(HashArgs a) { hash_insert_widepf<unsigned long long>(a, a.frames); }
+__global__ void __launch_bounds__(kThreads, 4) k_hash_insert_widepf32(HashArgs a) { hash_insert_widepf<uint32_t>(a, a.frames32); }
 
 // Variant D ("bulk"): the north-star mechanism. Every lane issues ONE cp.async.bulk (TMA 1-D bulk copy, SASS UBLKCP) that
 // brings its own sample's frame ids — one contiguous run of <= 64 ids — into a padded shared-memory slot; the copies of a
