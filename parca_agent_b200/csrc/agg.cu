@@ -131,8 +131,23 @@ struct pa_agg {
   pa_agg_config cfg{};
   std::string err;
   int device = 0, sms = 148, G = 592;
-  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // Early copy-out during a flush (XXH64 mode, v2, more than one chunk): all headers are uploaded first, k_header and the label
+  // chain run while the frame ids are still uploading, and stacktrace_id / value / timestamp leave for the host on s_d2h as soon
+  // as they are final, at positions counted from the END of the output buffer (see append_tail_v2). collect() anchors the stream
+  // so that it ends there and skips what is already in place; anything that does not match is copied the ordinary way.
+  struct Early {
+    bool hdr_first = false;   // this batch was staged headers-first
+    bool issued = false;      // early copies are in flight / done
+    uint8_t* out_end = nullptr;
+    uint64_t dist_ts = 0, dist_value = 0, dist_uuid = 0;
+  } early;
+  bool early_enabled = true;
+  cudaEvent_t ev_hdr_all = nullptr, ev_hdr_done = nullptr, ev_early = nullptr, ev_early_done = nullptr;
+  std::vector<cudaEvent_t> hash_ev;
+  uint8_t* h_early = nullptr;  // pinned: Counters, then the run keys of the eight kind-derived columns
+  static constexpr uint32_t kEarlyMaxRuns = 512;
   bool use_onepass = false;  // PA_REE_ONEPASS=1: label columns run-end encoded in one sweep with decoupled look-back (measured SLOWER than count + emit: 1.18 vs 0.39 ms on config 2)
   bool use_chain = false;    // PA_CHAIN=1: the stack-rank / dictionary chains as two persistent kernels with grid barriers instead of ~30 launches (measured no faster: DESIGN section 7)
   int ree_blocks = 8;        // blocks per SM of the two run-end passes (PA_REE_BLOCKS_PER_SM)
@@ -367,11 +382,24 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   for (uint32_t i = 0; i < cfg->n_external_labels; i++) {  // resolved to canonical ids lazily at flush (strings may come later)
     a->external.emplace_back(cfg->external_labels[i].name_sid, cfg->external_labels[i].value_sid);
   }
-  if (const char* hv = getenv("PA_HASH_VARIANT"))
-    a->hash_variant = strcmp(hv, "staged") == 0 ? 1 : (strcmp(hv, "direct") == 0 ? 0 : (strcmp(hv, "bulk") == 0 ? 3 : (strcmp(hv, "bulk6x2") == 0 ? 4 : (strcmp(hv, "widepf") == 0 ? 5 : 2))));
+  if (const char* hv = getenv("PA_HASH_VARIANT")) {
+    static const struct { const char* name; int id; } kVariants[] = {{"direct", 0}, {"staged", 1}, {"wide", 2}, {"bulk", 3}, {"bulk6x2", 4}, {"widepf", 5},
+                                                                   {"tma", 6}, {"tma12x4", 7}, {"tma24x2", 8}, {"tma12x2r", 9}, {"tma13x2r", 10}, {"tma8x3r", 11}, {"tmag13x2", 12}, {"tmag9x3", 13}, {"tmag6x4", 14}};
+    a->hash_variant = 2;
+    for (auto& v : kVariants) if (strcmp(hv, v.name) == 0) a->hash_variant = v.id;
+  }
   if (cudaFuncSetAttribute(k_hash_insert_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashStagedSmem) != cudaSuccess) return bail(PA_EIO);
   if (cudaFuncSetAttribute(k_ree_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, kOnepassPadSmem) != cudaSuccess) return bail(PA_EIO);
   if (cudaFuncSetAttribute(k_hash_insert_bulk<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BulkSmem<4, 3>)) != cudaSuccess) return bail(PA_EIO);
+  if (cudaFuncSetAttribute(k_hash_insert_tma<16, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem<16, 3, 8>)) != cudaSuccess) return bail(PA_EIO);
+  if (cudaFuncSetAttribute(k_hash_insert_tma<12, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem<12, 4, 8>)) != cudaSuccess) return bail(PA_EIO);
+  if (cudaFuncSetAttribute(k_hash_insert_tma<24, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem<24, 2, 8>)) != cudaSuccess) return bail(PA_EIO);
+  if (cudaFuncSetAttribute(k_hash_insert_tma<12, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem<12, 2, 16>)) != cudaSuccess) return bail(PA_EIO);
+  if (cudaFuncSetAttribute(k_hash_insert_tma<13, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem<13, 2, 16>)) != cudaSuccess) return bail(PA_EIO);
+  if (cudaFuncSetAttribute(k_hash_insert_tma<8, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem<8, 3, 16>)) != cudaSuccess) return bail(PA_EIO);
+  if (cudaFuncSetAttribute(k_hash_insert_tmag<13, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmagSmem<13, 2>)) != cudaSuccess) return bail(PA_EIO);
+  if (cudaFuncSetAttribute(k_hash_insert_tmag<9, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmagSmem<9, 3>)) != cudaSuccess) return bail(PA_EIO);
+  if (cudaFuncSetAttribute(k_hash_insert_tmag<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmagSmem<6, 4>)) != cudaSuccess) return bail(PA_EIO);
   if (cudaFuncSetAttribute(k_hash_insert_bulk<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BulkSmem<6, 2>)) != cudaSuccess) return bail(PA_EIO);
   if (cudaStreamCreateWithFlags(&a->s_copy, cudaStreamNonBlocking) != cudaSuccess) return bail(PA_EIO);
   int prio_lo = 0, prio_hi = 0;
@@ -380,6 +408,13 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   // ahead of the label chain's large run-end grids, which fill whatever is left
   if (cudaStreamCreateWithPriority(&a->s_comp, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(PA_EIO);
   if (cudaStreamCreateWithPriority(&a->s_aux, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return bail(PA_EIO);
+  if (cudaStreamCreateWithFlags(&a->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return bail(PA_EIO);
+  cudaEventCreateWithFlags(&a->ev_hdr_all, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&a->ev_hdr_done, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&a->ev_early, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&a->ev_early_done, cudaEventDisableTiming);
+  if (cudaHostAlloc((void**)&a->h_early, sizeof(Counters) + 8 * pa_agg::kEarlyMaxRuns * 4, cudaHostAllocDefault) != cudaSuccess) return bail(PA_ENOMEM);
+  if (getenv("PA_NO_EARLY_D2H")) a->early_enabled = false;
   cudaEventCreateWithFlags(&a->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&a->ev_join, cudaEventDisableTiming);
   if (const char* sv = getenv("PA_SERIAL")) a->serial = sv[0] == '1';
@@ -393,7 +428,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   cudaEventCreate(&a->ev_d2h1);
   for (int t = 0; t < T_COUNT; t++) { cudaEventCreate(&a->tm[t].a); cudaEventCreate(&a->tm[t].b); }
   const uint64_t N = a->cfg.max_samples, NF = a->cfg.max_frames;
-  if (a->idb == 4 && a->hash_variant != 5) a->hash_variant = 2;  // the narrow ring is read by the `wide` kernel (widening loads); the other variants take uint64 ids
+  if (a->idb == 4 && a->hash_variant != 5) a->hash_variant = 2;  // (the tma variants fall through to wide32 in launch_hash)  // the narrow ring is read by the `wide` kernel (widening loads); the other variants take uint64 ids
   for (int r = 0; r < (a->single_ring ? 1 : 2); r++) {
     if (cudaHostAlloc((void**)&a->ring[r].hdr, N * sizeof(pa_sample_hdr), cudaHostAllocDefault) != cudaSuccess) return bail(PA_ENOMEM);
     if (cudaHostAlloc((void**)&a->ring[r].frames, std::max<uint64_t>(NF, 1) * a->idb + 64, cudaHostAllocMapped) != cudaSuccess) return bail(PA_ENOMEM);
@@ -439,6 +474,11 @@ void pa_agg_destroy(pa_agg* a) {
   if (a->s_comp) cudaStreamSynchronize(a->s_comp);
   if (a->s_aux) cudaStreamSynchronize(a->s_aux);
   if (a->s_copy) cudaStreamSynchronize(a->s_copy);
+  if (a->s_d2h) cudaStreamSynchronize(a->s_d2h);
+  if (a->h_early) cudaFreeHost(a->h_early);
+  for (auto e : a->hash_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : {a->ev_hdr_all, a->ev_hdr_done, a->ev_early, a->ev_early_done}) if (e) cudaEventDestroy(e);
+  if (a->s_d2h) cudaStreamDestroy(a->s_d2h);
   for (int r = 0; r < 2; r++) { if (a->ring[r].hdr) cudaFreeHost(a->ring[r].hdr); if (a->ring[r].frames) cudaFreeHost(a->ring[r].frames); }
   if (a->h_ctr_pinned) cudaFreeHost(a->h_ctr_pinned);
   if (a->out) cudaFreeHost(a->out);
@@ -574,13 +614,22 @@ static int stage_async(pa_agg* a) {
   uint64_t nchunks = (a->N + C - 1) / C;
   while (a->chunk_ev.size() < nchunks) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); a->chunk_ev.push_back(e); }
   CK(cudaEventRecord(a->ev_h2d0, a->s_copy));
+  a->early = pa_agg::Early{};
+  // headers first when the frame ids take several chunks: everything that depends only on the headers (k_header, the label chain,
+  // the early copy-out) then overlaps the upload of the ids
+  a->early.hdr_first = a->early_enabled && nchunks > 1 && a->cfg.hash_mode == PA_HASH_XXH64X2 && a->cfg.schema != PA_SCHEMA_V1 && !a->serial;
+  if (a->early.hdr_first) {
+    CK(cudaMemcpyAsync(a->d_hdr.p, r.hdr, a->N * 64, cudaMemcpyHostToDevice, a->s_copy));
+    CK(cudaEventRecord(a->ev_hdr_all, a->s_copy));
+    while (a->hash_ev.size() < nchunks) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); a->hash_ev.push_back(e); }
+  }
   uint64_t fdone = 0;
   for (uint64_t k = 0; k < nchunks; k++) {
     uint64_t r0 = k * C, r1 = std::min(a->N, r0 + C);
     // frames are laid out in row order (acquire hands out ascending frame_base): a chunk's frames end where the next chunk's begin
     uint64_t fend = (r1 < a->N) ? std::min<uint64_t>(r.hdr[r1].frame_off, a->NF) : a->NF;
     if (fend < fdone) fend = fdone;
-    CK(cudaMemcpyAsync(a->d_hdr.as<uint8_t>() + r0 * 64, r.hdr + r0, (r1 - r0) * 64, cudaMemcpyHostToDevice, a->s_copy));
+    if (!a->early.hdr_first) CK(cudaMemcpyAsync(a->d_hdr.as<uint8_t>() + r0 * 64, r.hdr + r0, (r1 - r0) * 64, cudaMemcpyHostToDevice, a->s_copy));
     // The stack id arrives with the sample in PA_HASH_PROVIDED mode (the reference's dataflow, parca_reporter.go:224):
     // frames are only needed for each stack's FIRST occurrence, so nothing is uploaded here and k_gather_unique
     // reads those few stacks from the mapped pinned ring over PCIe (U*F*8 bytes instead of N*F*8).
@@ -940,7 +989,17 @@ static int pass_front(pa_agg* a) {
     ha.slot_of_row = a->d_slot.as<uint32_t>(); ha.tab = tab; ha.mask = P.mask; ha.ctr = ctr; ha.claimed = P.claimed;
     uint64_t rows = r1 - r0;
     int blocks = (int)std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)a->sms * (a->hash_variant == 1 ? 3 : 4));
-    if (a->hash_variant == 5 && a->idb == 4) k_hash_insert_widepf32<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
+    auto tma_grid = [&](int warps) { return (int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 32ull * warps - 1) / (32ull * warps), (uint64_t)a->sms)); };
+    if (a->hash_variant == 6 && a->idb == 8) k_hash_insert_tma<16, 3, 8><<<tma_grid(16), 16 * 32, sizeof(TmaSmem<16, 3, 8>), s>>>(ha);
+    else if (a->hash_variant == 7 && a->idb == 8) k_hash_insert_tma<12, 4, 8><<<tma_grid(12), 12 * 32, sizeof(TmaSmem<12, 4, 8>), s>>>(ha);
+    else if (a->hash_variant == 8 && a->idb == 8) k_hash_insert_tma<24, 2, 8><<<tma_grid(24), 24 * 32, sizeof(TmaSmem<24, 2, 8>), s>>>(ha);
+    else if (a->hash_variant == 9 && a->idb == 8) k_hash_insert_tma<12, 2, 16><<<tma_grid(12), 12 * 32, sizeof(TmaSmem<12, 2, 16>), s>>>(ha);
+    else if (a->hash_variant == 10 && a->idb == 8) k_hash_insert_tma<13, 2, 16><<<tma_grid(13), 13 * 32, sizeof(TmaSmem<13, 2, 16>), s>>>(ha);
+    else if (a->hash_variant == 11 && a->idb == 8) k_hash_insert_tma<8, 3, 16><<<tma_grid(8), 8 * 32, sizeof(TmaSmem<8, 3, 16>), s>>>(ha);
+    else if (a->hash_variant == 12 && a->idb == 8) k_hash_insert_tmag<13, 2><<<tma_grid(13), 13 * 32, sizeof(TmagSmem<13, 2>), s>>>(ha);
+    else if (a->hash_variant == 13 && a->idb == 8) k_hash_insert_tmag<9, 3><<<tma_grid(9), 9 * 32, sizeof(TmagSmem<9, 3>), s>>>(ha);
+    else if (a->hash_variant == 14 && a->idb == 8) k_hash_insert_tmag<6, 4><<<tma_grid(6), 6 * 32, sizeof(TmagSmem<6, 4>), s>>>(ha);
+    else if (a->hash_variant == 5 && a->idb == 4) k_hash_insert_widepf32<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     else if (a->hash_variant == 5) k_hash_insert_widepf<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     else if (a->idb == 4) k_hash_insert_wide32<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     else if (a->hash_variant == 3) k_hash_insert_bulk<4, 3><<<(int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 127) / 128, (uint64_t)a->sms)), 128, sizeof(BulkSmem<4, 3>), s>>>(ha);
@@ -958,6 +1017,17 @@ static int pass_front(pa_agg* a) {
     CK(cudaEventRecord(a->tm[T_HASH].a, s));
     if (!provided && N) launch_hash(0, N);
     CK(cudaEventRecord(a->tm[T_HASH].b, s));
+  } else if (a->early.hdr_first && !provided) {
+    CK(cudaStreamWaitEvent(s, a->ev_hdr_all, 0));
+    if (N) launch_header(0, N, a->NF);
+    CK(cudaEventRecord(a->tm[T_HEADER].b, s));
+    CK(cudaEventRecord(a->ev_hdr_done, s));
+    if (!a->serial && !P.v1 && !P.merged) { CK(cudaEventRecord(a->ev_fork, s)); a->forked_early = true; }  // the label chain starts here, under the upload of the ids
+    for (size_t k = 0; k < a->chunk_rows.size(); k++) {
+      CK(cudaStreamWaitEvent(s, a->chunk_ev[k], 0));
+      launch_hash(a->chunk_rows[k].first, a->chunk_rows[k].second);
+      CK(cudaEventRecord(a->hash_ev[k], s));
+    }
   } else {
     for (size_t k = 0; k < a->chunk_rows.size(); k++) {
       CK(cudaStreamWaitEvent(s, a->chunk_ev[k], 0));
@@ -1125,6 +1195,8 @@ static int pass_finish(pa_agg* a) {
   return PA_OK;
 }
 
+static int early_copy_issue(pa_agg* a);
+
 static int process_once(pa_agg* a) {
   int rc = pass_plan(a, nullptr);
   if (rc) return rc;
@@ -1142,7 +1214,15 @@ static int process_once(pa_agg* a) {
   if ((rc = pass_labels_count(a, s2))) return rc;
   if ((rc = pass_label_dicts(a, s2, fork ? a->d_partial2 : a->d_partial))) return rc;
   if ((rc = a->use_onepass ? pass_labels_onepass(a, s2) : pass_labels_emit(a, s2))) return rc;
+  // (the early copy-out is not worth starting when the upload has already finished: nothing left to hide behind)
+  const bool early = fork && a->forked_early && a->early.hdr_first && !a->early.issued && !a->P.merged && a->out && !a->chunk_rows.empty() &&
+                     cudaEventQuery(a->chunk_ev[a->chunk_rows.size() - 1]) != cudaSuccess;
+  if (early) {
+    CK(cudaMemcpyAsync(a->h_early, a->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, s2));
+    CK(cudaEventRecord(a->ev_early, s2));
+  }
   if (fork) { CK(cudaEventRecord(a->ev_join, s2)); CK(cudaStreamWaitEvent(s, a->ev_join, 0)); }
+  if (early && (rc = early_copy_issue(a))) return rc;
   return pass_finish(a);
 }
 
@@ -1179,6 +1259,7 @@ static int process(pa_agg* a) {
     rc = process_once(a);
     if (rc) return rc;
     if (!(a->h_ctr.err & ERR_TABLE_FULL)) break;
+    if (a->early.issued) CK(cudaStreamSynchronize(a->s_d2h));  // (k_header runs again and rewrites, with the same values, what is being copied out)
     a->retry_cap = a->table_cap * 4;  // unique-stack / thread-id estimate was too small: grow and redo the batch
     a->retry_tcap = a->tid_cap * 4;
   }
@@ -1274,6 +1355,47 @@ struct MergeView {
   uint64_t NT;                                            // rows of the merged batch
   const std::vector<std::vector<uint32_t>>* kind_keys;    // run keys of the 8 kind-derived columns, all shards concatenated
 };
+
+// The v2 record's trailing columns — stacktrace_id, value, the eight kind-derived run-end columns, timestamp (arrow_v2.go:612-663
+// order). Their sizes depend only on N and on the kind runs, which are known as soon as the label chain has run: a flush copies
+// stacktrace_id / value / timestamp to the host while the frame ids are still uploading (early_copy_issue), at positions counted
+// from the END of the stream, which is where these buffers sit.
+static void append_tail_v2(pa_agg* a, const MergeView* mv, uint64_t N, const std::vector<std::vector<uint32_t>>& kind_keys, std::vector<Node>& cols) {
+  auto rowbuf = [&](uint32_t kind, const void* p, uint64_t elem) { return mv ? sliced(kind, 0, N * elem) : BufRef::dev(p, N * elem); };
+  auto runbuf = [&](uint32_t kind, uint32_t col, const void* p, uint64_t n, uint64_t elem) { return mv ? sliced(kind, col, n * elem) : BufRef::dev(p, n * elem); };
+  const uint32_t nlab = a->n_label_cols;
+  {
+    Node id; id.ty = Ty::FixedBinary; id.name = "stacktrace_id"; id.byte_width = 16; id.length = (int64_t)N; id.bufs = {rowbuf(SL_UUID, a->d_uuid.p, 16)};
+    id.metadata = {{"ARROW:extension:name", "arrow.uuid"}, {"ARROW:extension:metadata", ""}};
+    cols.push_back(std::move(id));
+  }
+  cols.push_back(int_node("value", 64, true, false, (int64_t)N, rowbuf(SL_VALUE, a->d_value.p, 8)));
+  // constant-ish columns: values per run built from the class of each run
+  static const char* fixed_names[6] = {"producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality"};
+  auto ree_run_ends = [&](uint32_t t) { return runbuf(SL_RUN_ENDS, nlab + t, a->cols[nlab + t].run_ends, mv ? (uint64_t)a->h_ctr.n_runs[nlab + t] : (uint64_t)kind_keys[t].size(), 4); };
+  auto string_col = [&](uint32_t t) {
+    const auto& keys = kind_keys[t];
+    std::vector<std::pair<const uint8_t*, uint32_t>> strs;
+    std::vector<uint8_t> valid(keys.size(), 1);
+    for (size_t i = 0; i < keys.size(); i++) {
+      if (keys[i] == kNull) { valid[i] = 0; strs.emplace_back(nullptr, 0); continue; }
+      const std::string& s = a->kind_strings[t][keys[i]];
+      strs.emplace_back((const uint8_t*)s.data(), (uint32_t)s.size());
+    }
+    return ree_node(fixed_names[t], t == 5, (int64_t)N, (int64_t)keys.size(), ree_run_ends(t), utf8_node(a, "values", true, strs, &valid));
+  };
+  for (uint32_t t = 0; t < 6; t++) cols.push_back(string_col(t));
+  {
+    std::vector<int64_t> pv; for (uint32_t k : kind_keys[6]) pv.push_back(a->period_vals[k]);
+    std::vector<uint64_t> dv; for (uint32_t k : kind_keys[7]) dv.push_back(a->duration_vals[k]);
+    cols.push_back(ree_node("period", false, (int64_t)N, (int64_t)pv.size(), ree_run_ends(6), int_node("values", 64, true, true, (int64_t)pv.size(), host_ref(a, pv))));
+    cols.push_back(ree_node("duration", false, (int64_t)N, (int64_t)dv.size(), ree_run_ends(7), int_node("values", 64, false, true, (int64_t)dv.size(), host_ref(a, dv))));
+  }
+  {
+    Node ts; ts.ty = Ty::TimestampNsUtc; ts.name = "timestamp"; ts.length = (int64_t)N; ts.bufs = {rowbuf(SL_TS, a->d_ts.p, 8)};
+    cols.push_back(std::move(ts));
+  }
+}
 
 // the record's columns as Nodes (device buffers are referenced, host-built ones are kept in a->hostbufs)
 static int collect_nodes(pa_agg* a, const MergeView* mv, std::vector<Node>& cols) {
@@ -1513,40 +1635,55 @@ static int collect_nodes(pa_agg* a, const MergeView* mv, std::vector<Node>& cols
     st.kids.push_back(std::move(locd));
     cols.push_back(std::move(st));
   }
-  {
-    Node id; id.ty = Ty::FixedBinary; id.name = "stacktrace_id"; id.byte_width = 16; id.length = (int64_t)N; id.bufs = {rowbuf(SL_UUID, a->d_uuid.p, 16)};
-    id.metadata = {{"ARROW:extension:name", "arrow.uuid"}, {"ARROW:extension:metadata", ""}};
-    cols.push_back(std::move(id));
-  }
-  cols.push_back(int_node("value", 64, true, false, (int64_t)N, rowbuf(SL_VALUE, a->d_value.p, 8)));
-  // constant-ish columns: values per run built from the class of each run
-  static const char* fixed_names[6] = {"producer", "sample_type", "sample_unit", "period_type", "period_unit", "temporality"};
-  auto ree_run_ends = [&](uint32_t t) { return runbuf(SL_RUN_ENDS, nlab + t, a->cols[nlab + t].run_ends, c.n_runs[nlab + t], 4); };
-  auto string_col = [&](uint32_t t) {
-    const auto& keys = kind_keys[t];
-    std::vector<std::pair<const uint8_t*, uint32_t>> strs;
-    std::vector<uint8_t> valid(keys.size(), 1);
-    for (size_t i = 0; i < keys.size(); i++) {
-      if (keys[i] == kNull) { valid[i] = 0; strs.emplace_back(nullptr, 0); continue; }
-      const std::string& s = a->kind_strings[t][keys[i]];
-      strs.emplace_back((const uint8_t*)s.data(), (uint32_t)s.size());
-    }
-    return ree_node(fixed_names[t], t == 5, (int64_t)N, (int64_t)keys.size(), ree_run_ends(t), utf8_node(a, "values", true, strs, &valid));
-  };
-  for (uint32_t t = 0; t < 6; t++) cols.push_back(string_col(t));
-  {
-    std::vector<int64_t> pv; for (uint32_t k : kind_keys[6]) pv.push_back(a->period_vals[k]);
-    std::vector<uint64_t> dv; for (uint32_t k : kind_keys[7]) dv.push_back(a->duration_vals[k]);
-    cols.push_back(ree_node("period", false, (int64_t)N, (int64_t)pv.size(), ree_run_ends(6), int_node("values", 64, true, true, (int64_t)pv.size(), host_ref(a, pv))));
-    cols.push_back(ree_node("duration", false, (int64_t)N, (int64_t)dv.size(), ree_run_ends(7), int_node("values", 64, false, true, (int64_t)dv.size(), host_ref(a, dv))));
-  }
-  {
-    Node ts; ts.ty = Ty::TimestampNsUtc; ts.name = "timestamp"; ts.length = (int64_t)N; ts.bufs = {rowbuf(SL_TS, a->d_ts.p, 8)};
-    cols.push_back(std::move(ts));
-  }
+  append_tail_v2(a, mv, N, kind_keys, cols);
 
   }
 
+  return PA_OK;
+}
+
+// Called with the whole pass enqueued: wait for the label chain (it only needs the headers, so it finishes long before the ids are
+// in), size the record's trailing columns, and start copying stacktrace_id / value / timestamp into their final places counted
+// from the end of the output buffer: value and timestamp at once, stacktrace_id chunk by chunk as the hash kernel produces it.
+static int early_copy_issue(pa_agg* a) {
+  const uint32_t nlab = a->n_label_cols;
+  CK(cudaEventSynchronize(a->ev_early));
+  const Counters* ec = reinterpret_cast<const Counters*>(a->h_early);
+  uint32_t* keys = reinterpret_cast<uint32_t*>(a->h_early + sizeof(Counters));
+  uint32_t nr[8];
+  for (uint32_t t = 0; t < 8; t++) {
+    nr[t] = ec->n_runs[nlab + t];
+    if (nr[t] > pa_agg::kEarlyMaxRuns) return PA_OK;  // a batch that alternates sample kinds: the ordinary copy-out handles it
+    if (nr[t]) CK(cudaMemcpyAsync(keys + t * pa_agg::kEarlyMaxRuns, a->cols[nlab + t].run_keys, nr[t] * 4, cudaMemcpyDeviceToHost, a->s_aux));
+  }
+  CK(cudaStreamSynchronize(a->s_aux));
+  std::vector<std::vector<uint32_t>> kind_keys(8);
+  for (uint32_t t = 0; t < 8; t++) kind_keys[t].assign(keys + t * pa_agg::kEarlyMaxRuns, keys + t * pa_agg::kEarlyMaxRuns + nr[t]);
+  std::vector<Node> tail;
+  {
+    std::lock_guard<std::mutex> g(a->reg_mu);
+    append_tail_v2(a, nullptr, a->N, kind_keys, tail);
+  }
+  pa_agg::Early& e = a->early;
+  for (auto& bd : StreamPlan::tail_distances(tail)) {
+    if (bd.first.kind != BufRef::DEVICE) continue;
+    if (bd.first.ptr == a->d_uuid.p) e.dist_uuid = bd.second;
+    if (bd.first.ptr == a->d_value.p) e.dist_value = bd.second;
+    if (bd.first.ptr == a->d_ts.p) e.dist_ts = bd.second;
+  }
+  e.out_end = a->out + (a->out_cap & ~63ull);
+  if (!e.dist_uuid || !e.dist_value || !e.dist_ts || e.dist_uuid > (a->out_cap & ~63ull)) return PA_OK;
+  const uint64_t N = a->N;
+  CK(cudaStreamWaitEvent(a->s_d2h, a->ev_hdr_done, 0));
+  CK(cudaMemcpyAsync(e.out_end - e.dist_ts, a->d_ts.p, N * 8, cudaMemcpyDeviceToHost, a->s_d2h));
+  CK(cudaMemcpyAsync(e.out_end - e.dist_value, a->d_value.p, N * 8, cudaMemcpyDeviceToHost, a->s_d2h));
+  for (size_t k = 0; k < a->chunk_rows.size(); k++) {
+    const uint64_t r0 = a->chunk_rows[k].first, r1 = a->chunk_rows[k].second;
+    CK(cudaStreamWaitEvent(a->s_d2h, a->hash_ev[k], 0));
+    CK(cudaMemcpyAsync(e.out_end - e.dist_uuid + r0 * 16, a->d_uuid.as<uint8_t>() + r0 * 16, (r1 - r0) * 16, cudaMemcpyDeviceToHost, a->s_d2h));
+  }
+  CK(cudaEventRecord(a->ev_early_done, a->s_d2h));
+  e.issued = true;
   return PA_OK;
 }
 
@@ -1572,6 +1709,7 @@ static int collect(pa_agg* a, pa_agg_result* res) {
   StreamPlan plan;
   plan.build(cols, {{"parca_write_schema_version", v1 ? "v1" : "v2"}}, (int64_t)N);
   if (plan.total > a->out_cap) {
+    if (a->early.issued) { CK(cudaStreamSynchronize(a->s_d2h)); a->early.issued = false; }  // the early copies went into the buffer that is too small
     if (a->out) cudaFreeHost(a->out);
     a->out = nullptr;
     a->out_cap = 0;
@@ -1580,18 +1718,28 @@ static int collect(pa_agg* a, pa_agg_result* res) {
     a->out_cap = want;
   }
   double t1 = now_ms();
+  // a stream whose tail was copied out early ends where those copies assumed it would
+  const pa_agg::Early& e = a->early;
+  const bool anchored = e.issued && e.out_end == a->out + (a->out_cap & ~63ull) && plan.total <= (a->out_cap & ~63ull);
+  uint8_t* const base = anchored ? e.out_end - plan.total : a->out;
   cudaEvent_t d0 = a->ev_d2h0, d1 = a->ev_d2h1;
   CK(cudaEventRecord(d0, a->s_comp));
-  for (auto& p : plan.placements)
-    if (p.src.kind == BufRef::DEVICE && p.src.len) CK(cudaMemcpyAsync(a->out + p.at, p.src.ptr, p.src.len, cudaMemcpyDeviceToHost, a->s_comp));
+  for (auto& p : plan.placements) {
+    if (p.src.kind != BufRef::DEVICE || !p.src.len) continue;
+    const uint64_t dist = plan.total - p.at;
+    if (anchored && ((p.src.ptr == a->d_ts.p && dist == e.dist_ts) || (p.src.ptr == a->d_value.p && dist == e.dist_value) || (p.src.ptr == a->d_uuid.p && dist == e.dist_uuid)))
+      continue;  // already there
+    CK(cudaMemcpyAsync(base + p.at, p.src.ptr, p.src.len, cudaMemcpyDeviceToHost, a->s_comp));
+  }
   CK(cudaEventRecord(d1, a->s_comp));
-  plan.write_host_parts(a->out);  // metadata, host-built buffers, zero fills and padding overlap the D2H
+  if (e.issued) CK(cudaStreamWaitEvent(a->s_comp, a->ev_early_done, 0));
+  plan.write_host_parts(base);  // metadata, host-built buffers, zero fills and padding overlap the D2H
   CK(cudaStreamSynchronize(a->s_comp));
-  const uint8_t* stream = a->out;
+  const uint8_t* stream = base;
   uint64_t stream_len = plan.total;
   if (a->cfg.ipc_compression == PA_IPC_LZ4_FRAME) {  // network-path framing (ipc.WithLZ4(), :1851); host work, counted in host_ms
     std::string why;
-    if (!ipc_compress_lz4(a->out, plan.total, a->comp_out, &why)) return a->fail(PA_EIO, why.c_str());
+    if (!ipc_compress_lz4(base, plan.total, a->comp_out, &why)) return a->fail(PA_EIO, why.c_str());
     stream = a->comp_out.data();
     stream_len = a->comp_out.size();
   }
@@ -1801,6 +1949,7 @@ static int stacktraces(pa_agg* a, const uint8_t* ids, uint64_t n, pa_agg_result*
   StreamPlan plan;
   plan.build(cols, {{"parca_write_schema_version", "v1"}}, (int64_t)n);
   if (plan.total > a->out_cap) {
+    CK(cudaStreamSynchronize(a->s_d2h));
     if (a->out) cudaFreeHost(a->out);
     a->out = nullptr;
     a->out_cap = 0;

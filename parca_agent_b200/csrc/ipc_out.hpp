@@ -184,6 +184,15 @@ class StreamPlan {
     meta_.push_back({total, std::vector<uint8_t>((const uint8_t*)eos, (const uint8_t*)eos + 8)});
     total += 8;
   }
+  // `tail` = the LAST columns of a record. Returns, per buffer of those columns in IPC order, its source and the distance from
+  // its first byte to the END of the stream (nothing but the 8-byte end-of-stream marker follows the record batch body).
+  static std::vector<std::pair<BufRef, uint64_t>> tail_distances(const std::vector<Node>& tail) {
+    Body body;
+    for (auto& c : tail) walk(c, body);
+    std::vector<std::pair<BufRef, uint64_t>> out;
+    for (size_t i = 0; i < body.srcs.size(); i++) out.emplace_back(body.srcs[i], body.size - (uint64_t)body.buffers[2 * i] + 8);
+    return out;
+  }
   // pass 2 (host part): write metadata blobs and every padding gap's zeros; HOST/ZEROS buffers too.
   void write_host_parts(uint8_t* out) const {
     for (auto& m : meta_) memcpy(out + m.first, m.second.data(), m.second.size());

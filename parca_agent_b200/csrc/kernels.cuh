@@ -805,6 +805,311 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_hash_insert_bulk(HashArgs a) 
   }
 }
 
+// Variant E ("tma"): the lane layout and arithmetic of `wide` (two lanes per sample, four multiply chains per lane,
+// thread-per-sample epilogue), but the ids reach the lanes through shared memory, brought there by cp.async.bulk (SASS UBLKCP)
+// in SMALL stages: one stage = one batch of 8 stripes (256 B) of the 16 samples of a sub-step = 16 bulk copies of <= 272 B
+// into 288-B slots (4.5 KB), STAGES of them per warp, WARPS warps per SM (16 x 3: 216 KB). Why this shape: `wide`'s 16-byte
+// loads touch one 32-byte sector of 16 different lines per instruction — 16 L1 wavefronts and 16 L2 tag look-ups per 512 B
+// (ncu: LSU data pipe 66 %, L2 tags 62 %, DRAM 65 %: everything moderately busy, nothing saturated). A bulk copy fetches whole
+// lines without passing the LSU pipe, and the LDS.128 reads of the staged batch are conflict free (slot stride 288 B: four
+// consecutive samples fall into four different 32-byte bank groups), 4 wavefronts per 512 B. The first bulk kernel (variant D)
+// had whole-stack slots and thread-per-sample hashing and could keep only 6 warps per SM resident; this one keeps 16.
+// Odd id offsets are copied from one id earlier (16-byte alignment) and read back with 8-byte loads; any depth works (a
+// sub-step simply takes more batches); the < 4 trailing ids of a stack are read directly.
+__device__ __forceinline__ ulonglong2 lds128(uint32_t addr) {
+  ulonglong2 v;
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(addr));
+  return v;
+}
+// BATCH = stripes per sample per stage (8 or 16): the copy engine handles one bulk copy per ~16-19 cycles per SM whatever its size,
+// so 256-byte copies (BATCH 8) cap the kernel near 4 TB/s; 512-byte copies (BATCH 16 = whole 64-frame stacks) do not.
+template <int BATCH> constexpr int kTmaSlotBytes = BATCH * 32 + 32;   // BATCH stripes + 8 B alignment skew + 8 B round-up, padded (stride = 32 mod 128)
+template <int WARPS, int STAGES, int BATCH>
+struct TmaSmem {
+  alignas(128) uint8_t data[WARPS][STAGES][16 * kTmaSlotBytes<BATCH>];  // one stage = one batch of the 16 samples of a sub-step
+  alignas(8) unsigned long long bar[WARPS][STAGES];
+};
+template <int WARPS, int STAGES, int BATCH>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_hash_insert_tma(HashArgs a) {
+  extern __shared__ __align__(128) uint8_t tma_smem_raw[];
+  TmaSmem<WARPS, STAGES, BATCH>& sm = *reinterpret_cast<TmaSmem<WARPS, STAGES, BATCH>*>(tma_smem_raw);
+  constexpr uint32_t kSlot = kTmaSlotBytes<BATCH>, kStage = 16u * kSlot;
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, h = lane & 1, g = lane >> 1;
+  const uint32_t warp = blockIdx.x * WARPS + wib, nwarps = gridDim.x * WARPS;
+  const uint32_t span = a.row1 - a.row0;
+  const uint32_t tiles = (span + 31) / 32;
+  if (lane == 0)
+    for (int st = 0; st < STAGES; st++) mbar_init(smem_u32(&sm.bar[wib][st]), 32);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const uint32_t my_tiles = tiles > warp ? (tiles - warp + nwarps - 1) / nwarps : 0u;
+  if (my_tiles == 0) return;
+  // rows of this warp's k-th tile, as every lane sees its own row; nb = batches per sub-step (warp-uniform)
+  auto load_meta = [&](uint32_t k, uint32_t& r, bool& valid, uint32_t& n, unsigned long long& off, uint32_t& nb) {
+    r = a.row0 + (warp + k * nwarps) * 32 + lane;
+    valid = r < a.row1;
+    n = valid ? a.nframes[r] : 0u;
+    off = valid ? a.frame_off[r] : 0ull;
+    nb = (__reduce_max_sync(full, n >> 2) + (uint32_t)BATCH - 1u) / (uint32_t)BATCH;
+  };
+  const uint32_t data0 = smem_u32(&sm.data[wib][0][0]), bar0 = smem_u32(&sm.bar[wib][0]);
+  // ---- producer: items are (tile, sub-step, batch) in consumption order
+  uint32_t pk = 0, p_sub = 0, p_b = 0, p_stage = 0, p_r, p_n, p_nb; bool p_valid; unsigned long long p_off;
+  load_meta(0, p_r, p_valid, p_n, p_off, p_nb);
+  auto produce = [&]() {
+    while (pk < my_tiles && p_nb == 0) {  // tiles without a whole stripe have no items
+      if (++pk < my_tiles) load_meta(pk, p_r, p_valid, p_n, p_off, p_nb);
+    }
+    if (pk >= my_tiles) return;  // warp-uniform
+    const int src_lane = (int)p_sub * 16 + (lane & 15);
+    const uint32_t n_s = __shfl_sync(full, p_n, src_lane);
+    const unsigned long long off_s = __shfl_sync(full, p_off, src_lane);
+    const uint32_t bar = bar0 + 8u * p_stage;
+    const uint32_t ns = n_s >> 2, first = (uint32_t)BATCH * p_b;
+    const uint32_t cnt = ns > first ? min((uint32_t)BATCH, ns - first) : 0u;
+    if (lane < 16 && cnt) {
+      const uint32_t skew = (uint32_t)(off_s & 1ull);
+      const uint32_t bytes = ((skew + 4u * cnt + 1u) & ~1u) * 8u;  // [first id - skew, last id] rounded up to a multiple of 16 bytes
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_g2s(data0 + p_stage * kStage + (uint32_t)lane * kSlot, a.frames + (off_s + 4ull * first - skew), bytes, bar);
+    } else {
+      mbar_arrive(bar);
+    }
+    p_stage = p_stage + 1 == STAGES ? 0 : p_stage + 1;
+    if (++p_b == p_nb) {
+      p_b = 0;
+      if (++p_sub == 2) {
+        p_sub = 0;
+        p_nb = 0;
+        if (++pk < my_tiles) load_meta(pk, p_r, p_valid, p_n, p_off, p_nb);
+      }
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < STAGES - 1; i++) produce();
+  // ---- consumer
+  uint32_t c_stage = 0, phase_bits = 0;
+  for (uint32_t k = 0; k < my_tiles; k++) {
+    uint32_t r, n_me, nb; bool valid; unsigned long long off_me;
+    load_meta(k, r, valid, n_me, off_me, nb);
+    unsigned long long acc[2][4];  // [sub][a0, a1, b0, b1]
+#pragma unroll
+    for (int sub = 0; sub < 2; sub++) {
+      const uint32_t ns_s = __shfl_sync(full, n_me, sub * 16 + g) >> 2;
+      const uint32_t skew_s = (uint32_t)(__shfl_sync(full, off_me, sub * 16 + g) & 1ull);
+      const bool any_skew = __any_sync(full, skew_s != 0);
+      unsigned long long a0 = xxh_lane_init(0ull, 2 * h), b0 = xxh_lane_init(0ull, 2 * h + 1);
+      unsigned long long a1 = xxh_lane_init(kSeedLo, 2 * h), b1 = xxh_lane_init(kSeedLo, 2 * h + 1);
+      for (uint32_t b = 0; b < nb; b++) {
+        produce();  // refills the stage consumed in the previous iteration
+        mbar_wait(bar0 + 8u * c_stage, (phase_bits >> c_stage) & 1u);
+        phase_bits ^= 1u << c_stage;
+        const uint32_t first = (uint32_t)BATCH * b;
+        const uint32_t cnt = ns_s > first ? min((uint32_t)BATCH, ns_s - first) : 0u;
+        const uint32_t base = data0 + c_stage * kStage + (uint32_t)g * kSlot + skew_s * 8u + (uint32_t)h * 16u;
+        if (!any_skew && __all_sync(full, cnt == (uint32_t)BATCH)) {
+#pragma unroll
+          for (int blk = 0; blk < BATCH / 8; blk++) {
+            ulonglong2 w[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) w[u] = lds128(base + 32u * (8 * blk + u));
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const unsigned long long mx = w[u].x * XP2, my = w[u].y * XP2;
+              a0 = xxh_round_pre(a0, mx); a1 = xxh_round_pre(a1, mx);
+              b0 = xxh_round_pre(b0, my); b1 = xxh_round_pre(b1, my);
+            }
+          }
+        } else {
+          for (uint32_t u = 0; u < cnt; u++) {
+            const unsigned long long mx = lds64(base + 32u * u) * XP2, my = lds64(base + 32u * u + 8u) * XP2;
+            a0 = xxh_round_pre(a0, mx); a1 = xxh_round_pre(a1, mx);
+            b0 = xxh_round_pre(b0, my); b1 = xxh_round_pre(b1, my);
+          }
+        }
+        __syncwarp(full);  // every lane has read this stage before the next produce() refills it
+        c_stage = c_stage + 1 == STAGES ? 0 : c_stage + 1;
+      }
+      acc[sub][0] = a0; acc[sub][1] = a1; acc[sub][2] = b0; acc[sub][3] = b1;
+    }
+    // transpose: lane L gets accumulators 0,1 from lane 2*(L&15) and 2,3 from lane 2*(L&15)+1 of ITS half's sub-step
+    const int l0 = 2 * (lane & 15), l1 = l0 + 1;
+    const bool up = lane >= 16;
+    unsigned long long v0[4], v1[4], x, y;
+    x = __shfl_sync(full, acc[0][0], l0); y = __shfl_sync(full, acc[1][0], l0); v0[0] = up ? y : x;
+    x = __shfl_sync(full, acc[0][2], l0); y = __shfl_sync(full, acc[1][2], l0); v0[1] = up ? y : x;
+    x = __shfl_sync(full, acc[0][0], l1); y = __shfl_sync(full, acc[1][0], l1); v0[2] = up ? y : x;
+    x = __shfl_sync(full, acc[0][2], l1); y = __shfl_sync(full, acc[1][2], l1); v0[3] = up ? y : x;
+    x = __shfl_sync(full, acc[0][1], l0); y = __shfl_sync(full, acc[1][1], l0); v1[0] = up ? y : x;
+    x = __shfl_sync(full, acc[0][3], l0); y = __shfl_sync(full, acc[1][3], l0); v1[1] = up ? y : x;
+    x = __shfl_sync(full, acc[0][1], l1); y = __shfl_sync(full, acc[1][1], l1); v1[2] = up ? y : x;
+    x = __shfl_sync(full, acc[0][3], l1); y = __shfl_sync(full, acc[1][3], l1); v1[3] = up ? y : x;
+    const uint32_t nt = n_me & 3u;
+    const unsigned long long* tp = a.frames + off_me + (n_me & ~3u);
+    const unsigned long long t0w = nt > 0 ? load_one(tp) : 0ull, t1w = nt > 1 ? load_one(tp + 1) : 0ull, t2w = nt > 2 ? load_one(tp + 2) : 0ull;
+    Key128 key;
+    key.hi = xxh_finish_own(v0, 0ull, n_me, t0w, t1w, t2w);
+    key.lo = xxh_finish_own(v1, kSeedLo, n_me, t0w, t1w, t2w);
+    if (valid) *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * r) = make_ulonglong2(bswap64(key.hi), bswap64(key.lo));
+    const uint32_t slot = warp_insert(a.tab, a.mask, key, r, valid, a.ctr, a.claimed);
+    if (valid) a.slot_of_row[r] = slot;
+  }
+}
+
+// Variant F ("tmag"): variant E with FOUR bulk copies per stage instead of sixteen. ptxas turns a per-lane cp.async.bulk into a
+// loop over the active lanes (ELECT / R2UR x5 / UBLKCP / BRA.U.ANY: its operands live in uniform registers), so sixteen copies
+// cost ~160 issue slots and ~600 cycles of one warp per stage. Rows are contiguous in the ring, so one copy can bring the whole
+// stacks of four consecutive samples (<= 2 KiB); the four groups of a sub-step sit 2080 B apart (= 32 mod 128) and lane pair g
+// hashes sample (g & 3) * 4 + (g >> 2), so the four pairs of every 128-bit shared-memory phase read from four different groups:
+// conflict free for uniform depths. One stage = one sub-step (16 whole stacks, 8.3 KB). A tile whose groups are not contiguous
+// or exceed 256 ids goes through the direct-load tile code.
+constexpr int kTmagGroupBytes = 2048 + 32;
+constexpr int kTmagStageBytes = 4 * kTmagGroupBytes;
+template <int WARPS, int STAGES>
+struct TmagSmem {
+  alignas(128) uint8_t data[WARPS][STAGES][kTmagStageBytes];
+  alignas(8) unsigned long long bar[WARPS][STAGES];
+};
+template <int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_hash_insert_tmag(HashArgs a) {
+  extern __shared__ __align__(128) uint8_t tmag_smem_raw[];
+  TmagSmem<WARPS, STAGES>& sm = *reinterpret_cast<TmagSmem<WARPS, STAGES>*>(tmag_smem_raw);
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, h = lane & 1, g = lane >> 1;
+  const uint32_t warp = blockIdx.x * WARPS + wib, nwarps = gridDim.x * WARPS;
+  const uint32_t span = a.row1 - a.row0;
+  const uint32_t tiles = (span + 31) / 32;
+  if (lane == 0)
+    for (int st = 0; st < STAGES; st++) mbar_init(smem_u32(&sm.bar[wib][st]), 32);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const uint32_t my_tiles = tiles > warp ? (tiles - warp + nwarps - 1) / nwarps : 0u;
+  if (my_tiles == 0) return;
+  // Per tile, as lane L sees its own row: depth, offset, ids of the earlier rows of its group of four (pre), ids of the whole
+  // group (tot), and whether the whole tile can be staged (every group contiguous and <= 256 ids).
+  struct Meta { uint32_t r, n, pre, tot; unsigned long long off; bool valid, staged; };
+  auto load_meta = [&](uint32_t k) {
+    Meta m;
+    m.r = a.row0 + (warp + k * nwarps) * 32 + lane;
+    m.valid = m.r < a.row1;
+    m.n = m.valid ? a.nframes[m.r] : 0u;
+    m.off = m.valid ? a.frame_off[m.r] : 0ull;
+    const uint32_t up1 = __shfl_up_sync(full, m.n, 1), up2 = __shfl_up_sync(full, m.n, 2), up3 = __shfl_up_sync(full, m.n, 3);
+    const int q = lane & 3;
+    m.pre = (q > 0 ? up1 : 0u) + (q > 1 ? up2 : 0u) + (q > 2 ? up3 : 0u);
+    m.tot = __shfl_sync(full, m.pre + m.n, lane | 3);
+    const unsigned long long off0 = __shfl_sync(full, m.off, lane & ~3);
+    m.staged = __all_sync(full, (m.n == 0 || m.off == off0 + m.pre) && m.tot <= 256u);
+    return m;
+  };
+  const uint32_t data0 = smem_u32(&sm.data[wib][0][0]), bar0 = smem_u32(&sm.bar[wib][0]);
+  // ---- producer: two items per tile (its two sub-steps), in consumption order
+  uint32_t pk = 0, p_sub = 0, p_stage = 0;
+  Meta pm = load_meta(0);
+  auto produce = [&]() {
+    if (pk >= my_tiles) return;  // warp-uniform
+    const uint32_t bar = bar0 + 8u * p_stage;
+    const int src_lane = (int)p_sub * 16 + (lane & 15);
+    const uint32_t tot_s = __shfl_sync(full, pm.tot, src_lane);
+    const unsigned long long off_s = __shfl_sync(full, pm.off, src_lane);
+    if (pm.staged && lane < 16 && (lane & 3) == 0 && tot_s) {
+      const uint32_t skew = (uint32_t)(off_s & 1ull);
+      const uint32_t bytes = ((skew + tot_s + 1u) & ~1u) * 8u;
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_g2s(data0 + p_stage * kTmagStageBytes + (uint32_t)(lane >> 2) * kTmagGroupBytes, a.frames + (off_s - skew), bytes, bar);
+    } else {
+      mbar_arrive(bar);
+    }
+    p_stage = p_stage + 1 == STAGES ? 0 : p_stage + 1;
+    if (++p_sub == 2) {
+      p_sub = 0;
+      if (++pk < my_tiles) pm = load_meta(pk);
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < STAGES - 1; i++) produce();
+  // ---- consumer
+  uint32_t c_stage = 0, phase_bits = 0;
+  const int sg = (g & 3) * 4 + (g >> 2);  // the sample (within a sub-step) this lane pair hashes
+  for (uint32_t k = 0; k < my_tiles; k++) {
+    const Meta cm = load_meta(k);
+    if (!cm.staged) {  // warp-uniform: both (empty) items of the tile are consumed, the tile goes through the direct-load code
+      for (int sub = 0; sub < 2; sub++) {
+        produce();
+        mbar_wait(bar0 + 8u * c_stage, (phase_bits >> c_stage) & 1u);
+        phase_bits ^= 1u << c_stage;
+        c_stage = c_stage + 1 == STAGES ? 0 : c_stage + 1;
+      }
+      wide_tile(a, cm.r, cm.valid, cm.n, cm.off);
+      __syncwarp(full);
+      continue;
+    }
+    unsigned long long acc[2][4];  // [sub][a0, a1, b0, b1]
+#pragma unroll
+    for (int sub = 0; sub < 2; sub++) {
+      const int ml = sub * 16 + sg;  // the lane that holds this pair's sample
+      const uint32_t ns = __shfl_sync(full, cm.n, ml) >> 2;
+      const uint32_t pre = __shfl_sync(full, cm.pre, ml);
+      const uint32_t skew = (uint32_t)(__shfl_sync(full, cm.off, ml & ~3) & 1ull);  // of the group's first id
+      unsigned long long a0 = xxh_lane_init(0ull, 2 * h), b0 = xxh_lane_init(0ull, 2 * h + 1);
+      unsigned long long a1 = xxh_lane_init(kSeedLo, 2 * h), b1 = xxh_lane_init(kSeedLo, 2 * h + 1);
+      produce();  // refills the stage consumed before this one
+      mbar_wait(bar0 + 8u * c_stage, (phase_bits >> c_stage) & 1u);
+      phase_bits ^= 1u << c_stage;
+      const uint32_t base = data0 + c_stage * kTmagStageBytes + (uint32_t)(g & 3) * kTmagGroupBytes + (skew + pre) * 8u + (uint32_t)h * 16u;
+      const bool al16 = ((skew + pre) & 1u) == 0;
+      const uint32_t nsmin = __reduce_min_sync(full, ns), nsmax = __reduce_max_sync(full, ns);
+      uint32_t s = 0;
+      if (__all_sync(full, al16)) {
+        for (; s + 8 <= nsmin; s += 8) {  // warp-uniform: every pair has 8 more stripes
+          ulonglong2 w[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) w[u] = lds128(base + 32u * (s + u));
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const unsigned long long mx = w[u].x * XP2, my = w[u].y * XP2;
+            a0 = xxh_round_pre(a0, mx); a1 = xxh_round_pre(a1, mx);
+            b0 = xxh_round_pre(b0, my); b1 = xxh_round_pre(b1, my);
+          }
+        }
+      }
+      for (; s < nsmax; s++) {  // ragged rest (and everything, when an odd id offset forces 8-byte reads)
+        if (s < ns) {
+          const unsigned long long mx = lds64(base + 32u * s) * XP2, my = lds64(base + 32u * s + 8u) * XP2;
+          a0 = xxh_round_pre(a0, mx); a1 = xxh_round_pre(a1, mx);
+          b0 = xxh_round_pre(b0, my); b1 = xxh_round_pre(b1, my);
+        }
+      }
+      __syncwarp(full);  // every lane has read this stage before the next produce() refills it
+      c_stage = c_stage + 1 == STAGES ? 0 : c_stage + 1;
+      acc[sub][0] = a0; acc[sub][1] = a1; acc[sub][2] = b0; acc[sub][3] = b1;
+    }
+    // transpose: lane L (sample s = L & 15 of its half's sub-step) takes accumulators 0,1 / 2,3 from the two lanes of the pair that hashed s
+    const int sp = ((lane & 3) * 4 + ((lane & 15) >> 2));
+    const int l0 = 2 * sp, l1 = l0 + 1;
+    const bool up = lane >= 16;
+    unsigned long long v0[4], v1[4], x, y;
+    x = __shfl_sync(full, acc[0][0], l0); y = __shfl_sync(full, acc[1][0], l0); v0[0] = up ? y : x;
+    x = __shfl_sync(full, acc[0][2], l0); y = __shfl_sync(full, acc[1][2], l0); v0[1] = up ? y : x;
+    x = __shfl_sync(full, acc[0][0], l1); y = __shfl_sync(full, acc[1][0], l1); v0[2] = up ? y : x;
+    x = __shfl_sync(full, acc[0][2], l1); y = __shfl_sync(full, acc[1][2], l1); v0[3] = up ? y : x;
+    x = __shfl_sync(full, acc[0][1], l0); y = __shfl_sync(full, acc[1][1], l0); v1[0] = up ? y : x;
+    x = __shfl_sync(full, acc[0][3], l0); y = __shfl_sync(full, acc[1][3], l0); v1[1] = up ? y : x;
+    x = __shfl_sync(full, acc[0][1], l1); y = __shfl_sync(full, acc[1][1], l1); v1[2] = up ? y : x;
+    x = __shfl_sync(full, acc[0][3], l1); y = __shfl_sync(full, acc[1][3], l1); v1[3] = up ? y : x;
+    const uint32_t nt = cm.n & 3u;
+    const unsigned long long* tp = a.frames + cm.off + (cm.n & ~3u);
+    const unsigned long long t0w = nt > 0 ? load_one(tp) : 0ull, t1w = nt > 1 ? load_one(tp + 1) : 0ull, t2w = nt > 2 ? load_one(tp + 2) : 0ull;
+    Key128 key;
+    key.hi = xxh_finish_own(v0, 0ull, cm.n, t0w, t1w, t2w);
+    key.lo = xxh_finish_own(v1, kSeedLo, cm.n, t0w, t1w, t2w);
+    if (cm.valid) *reinterpret_cast<ulonglong2*>(a.uuid + 16ull * cm.r) = make_ulonglong2(bswap64(key.hi), bswap64(key.lo));
+    const uint32_t slot = warp_insert(a.tab, a.mask, key, cm.r, cm.valid, a.ctr, a.claimed);
+    if (cm.valid) a.slot_of_row[cm.r] = slot;
+  }
+}
+
 // Variant C: same arithmetic and epilogue as k_hash_insert, but the frame ids reach the XXH64 lanes
 // through shared memory: every warp owns a two-stage ring (8 samples x 544 B per stage) that it fills
 // with cp.async (LDGSTS, 16 B per lane = one coalesced 512-B sample per instruction, no registers

@@ -230,7 +230,7 @@ def test_bad_ids_are_reported(gpu):
     a.close()
 
 
-@pytest.mark.parametrize("variant", ["direct", "staged", "wide", "widepf", "bulk", "bulk6x2"])
+@pytest.mark.parametrize("variant", ["direct", "staged", "wide", "widepf", "bulk", "bulk6x2", "tma", "tma12x4", "tma24x2", "tma12x2r", "tma13x2r", "tma8x3r", "tmag13x2", "tmag9x3", "tmag6x4"])
 def test_hash_kernel_variants(oracle, gpu, variant, monkeypatch):
     """Both hash kernels (direct global loads / cp.async-staged) must produce identical bytes, including
     ragged stacks, odd frame offsets (8-byte staging path) and stacks deeper than one staging slot."""
@@ -248,7 +248,7 @@ def test_hash_kernel_variants(oracle, gpu, variant, monkeypatch):
     w.hdrs["nframes"][::7] = 63  # mixed depths inside one warp batch (frames stay where they are)
     assert_same(oracle, gpu, w)
     assert_same(oracle, gpu, w, chunk_samples=333)  # tiles that end in the middle of a warp, several launches
-    if variant in ("wide", "widepf"):  # the two kernels that also read a narrow (uint32) frame stream
+    if variant in ("wide", "widepf", "tma", "tmag13x2"):  # wide / widepf also read a narrow (uint32) frame stream (tma hands those to wide)
         assert_same(oracle, gpu, w, frame_id_bytes=4)
         assert_same(oracle, gpu, synth.edge_workload(seed=43, n=5000, hash_mode=abi.PA_HASH_XXH64X2), frame_id_bytes=4, chunk_samples=1000)
         assert_same(oracle, gpu, synth.ragged(n=60_000, u=3_000, p=4_096))
