@@ -143,7 +143,8 @@ struct pa_agg {
     uint8_t* out_end = nullptr;
     uint64_t dist_ts = 0, dist_value = 0, dist_uuid = 0;
   } early;
-  bool early_enabled = true;
+  bool early_enabled = true, early_force = false;
+  bool use_pdl = false;  // PA_PDL=1: the small dependent kernels of the rank / location / label chains are launched with programmatic stream serialization
   cudaEvent_t ev_hdr_all = nullptr, ev_hdr_done = nullptr, ev_early = nullptr, ev_early_done = nullptr;
   std::vector<cudaEvent_t> hash_ev;
   uint8_t* h_early = nullptr;  // pinned: Counters, then the run keys of the eight kind-derived columns
@@ -414,7 +415,9 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   cudaEventCreateWithFlags(&a->ev_early, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&a->ev_early_done, cudaEventDisableTiming);
   if (cudaHostAlloc((void**)&a->h_early, sizeof(Counters) + 8 * pa_agg::kEarlyMaxRuns * 4, cudaHostAllocDefault) != cudaSuccess) return bail(PA_ENOMEM);
+  if (const char* e = getenv("PA_PDL")) a->use_pdl = atoi(e) != 0;
   if (getenv("PA_NO_EARLY_D2H")) a->early_enabled = false;
+  if (getenv("PA_EARLY_D2H_ALWAYS")) a->early_force = true;  // tests: take the early path even when the (tiny) upload is already over
   cudaEventCreateWithFlags(&a->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&a->ev_join, cudaEventDisableTiming);
   if (const char* sv = getenv("PA_SERIAL")) a->serial = sv[0] == '1';
@@ -655,13 +658,25 @@ static void release_staged(pa_agg* a) {
   }
 }
 
+// launch of a chain kernel (every one of them starts with pdl_enter())
+template <class... KArgs, class... Args>
+static void launch_chain(const pa_agg* a, void (*k)(KArgs...), dim3 grid, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = a->use_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
+}
+
 template <class F>
 static void launch_scan(pa_agg* a, F f, int njobs, Timer& t, int gx, cudaStream_t s, DBuf& scratch) {
   if (gx <= 0) gx = a->G;
   dim3 grid(gx, njobs);
   typename F::T* partial = scratch.as<typename F::T>();  // per-block totals: two concurrent scans need two scratch buffers
-  k_scan_reduce<F><<<grid, kThreads, 0, s>>>(f, partial);
-  k_scan_emit<F><<<grid, kThreads, 0, s>>>(f, partial);
+  launch_chain(a, k_scan_reduce<F>, grid, s, f, partial);
+  launch_chain(a, k_scan_emit<F>, grid, s, f, partial);
   t.launches += 2;
 }
 // grid for a pass over at most `bound` elements: >= 2048 elements per CTA, never more than the full grid
@@ -699,12 +714,12 @@ static int upload_tables(pa_agg* a) {
 static void run_fo_jobs(pa_agg* a, const FoJob* djobs, int first, int count, bool need_min, Timer& t, uint64_t elem_bound, uint64_t table_bound,
                         bool do_map, cudaStream_t s, DBuf& scratch) {
   const int ge = small_grid(a, elem_bound), gt = small_grid(a, table_bound), gw = small_grid(a, elem_bound / 32 + 1);
-  k_fo_zero<<<dim3(gw, count), kThreads, 0, s>>>(djobs + first);
-  if (need_min) { k_fo_min<<<dim3(ge, count), kThreads, 0, s>>>(djobs + first); t.launches++; }
-  k_fo_bits<<<dim3(gt, count), kThreads, 0, s>>>(djobs + first);
+  launch_chain(a, k_fo_zero, dim3(gw, count), s, djobs + first);
+  if (need_min) { launch_chain(a, k_fo_min, dim3(ge, count), s, djobs + first); t.launches++; }
+  launch_chain(a, k_fo_bits, dim3(gt, count), s, djobs + first);
   launch_scan(a, FoWordsF{djobs + first, -1}, count, t, gw, s, scratch);
-  k_fo_assign<<<dim3(gt, count), kThreads, 0, s>>>(djobs + first);
-  if (do_map) { k_fo_map<<<dim3(ge, count), kThreads, 0, s>>>(djobs + first); t.launches++; }
+  launch_chain(a, k_fo_assign, dim3(gt, count), s, djobs + first);
+  if (do_map) { launch_chain(a, k_fo_map, dim3(ge, count), s, djobs + first); t.launches++; }
   t.launches += 3;
 }
 
@@ -1063,18 +1078,18 @@ static int pass_rank_single(pa_agg* a) {
     return PA_OK;
   }
   const int Gw = small_grid(a, N / 32 + 1), Gu = small_grid(a, std::min<uint64_t>(N, P.cap / 2));
-  k_stack_bits<<<Gu, kThreads, 0, s>>>(tab, P.claimed, &ctr->n_claimed, P.rowbits);
+  launch_chain(a, k_stack_bits, dim3((unsigned)(Gu)), s, tab, P.claimed, &ctr->n_claimed, P.rowbits);
   launch_scan(a, WordsF{P.rowbits, P.row_wprefix, (uint32_t)((N + 31) / 32), &ctr->n_unique}, 1, a->tm[T_RANK], Gw, s, a->d_partial);
-  k_stack_assign<<<Gu, kThreads, 0, s>>>(tab, P.claimed, &ctr->n_claimed, P.rowbits, P.row_wprefix, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(), P.uniq_slot, P.uniq_size);
+  launch_chain(a, k_stack_assign, dim3((unsigned)(Gu)), s, tab, P.claimed, &ctr->n_claimed, P.rowbits, P.row_wprefix, a->d_nfr.as<uint16_t>(), a->d_uniq_row.as<uint32_t>(), P.uniq_slot, P.uniq_size);
   launch_scan(a, UniqOffsetF{ctr, ctr, P.uniq_size, P.uniq_slot, tab}, 1, a->tm[T_RANK], Gu, s, a->d_partial);
   a->tm[T_RANK].launches += 2;
-  k_rows_materialize<<<G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>(), P.v1 ? a->v1_ord : nullptr);
+  launch_chain(a, k_rows_materialize, dim3((unsigned)(G)), s, (uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>(), P.v1 ? a->v1_ord : nullptr);
   if (P.v1) {  // v1 has no inline stacktraces: only the dictionary of unique stack ids
     k_gather_ids<<<small_grid(a, std::min<uint64_t>(N, P.cap / 2) + 1), kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_uuid.as<uint8_t>(), a->v1_ids, a->v1_id_off);
     launch_store_insert(a);
     a->tm[T_RANK].launches++;
   } else {
-    k_gather_unique<<<G, kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, a->src_frames,
+    launch_chain(a, k_gather_unique, dim3((unsigned)(G)), s, ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, a->src_frames,
                                            a->d_foff.as<unsigned long long>(), P.n_frames, a->d_ustream.as<uint32_t>(), a->loc_first, ctr, a->idb == 4 ? 1u : 0u);
   }
   a->tm[T_RANK].launches += 2;
@@ -1103,9 +1118,9 @@ static int pass_locations(pa_agg* a) {
   } else if (!P.v1) {  // v1 carries no locations in the sample record
     run_fo_jobs(a, djobs, P.j_loc, 1, false, a->tm[T_LOC], std::min<uint64_t>(P.NI, P.merged ? P.NI : P.cap * 32), Pn, true, s, a->d_partial);  // location index per unique-stack frame (in place over the gathered stream)
     launch_scan(a, LocLinesF{ctr, ctr, a->loc_order, ftd, a->lo}, 1, a->tm[T_LOC], small_grid(a, Pn), s, a->d_partial);
-    k_line_validity<<<std::max(1, std::min(G, (int)(Pn / 256 + 1))), kThreads, 0, s>>>(ctr, a->lo.line_size, a->lo.line_valid);
+    launch_chain(a, k_line_validity, dim3((unsigned)(std::max(1, std::min(G, (int)(Pn / 256 + 1))))), s, ctr, a->lo.line_size, a->lo.line_valid);
     run_fo_jobs(a, djobs, P.j_type, 4, true, a->tm[T_LOC], Pn, std::max(S, FN), true, s, a->d_partial);  // frame_type, mapping_file, mapping_build_id, function
-    k_func_keys<<<std::max(1, std::min(G, (int)(FN / 256 + 1))), kThreads, 0, s>>>(ctr, a->fn_order, a->m_fnfile.ptr(), a->sd_keys[3]);
+    launch_chain(a, k_func_keys, dim3((unsigned)(std::max(1, std::min(G, (int)(FN / 256 + 1))))), s, ctr, a->fn_order, a->m_fnfile.ptr(), a->sd_keys[3]);
     run_fo_jobs(a, djobs, P.j_file, 1, true, a->tm[T_LOC], FN, S, true, s, a->d_partial);  // function.filename
     a->tm[T_LOC].launches += 2;
   }
@@ -1124,16 +1139,16 @@ static int pass_labels_count(pa_agg* a, cudaStream_t s) {
     lf.first_ls = P.first_ls; lf.n_labelsets = P.n_labelsets; lf.lsmat = a->d_lsmat.as<uint32_t>();
     lf.n_lscols = std::max<uint32_t>(1, a->n_lscols); lf.n_ls = a->n_lscols;
     for (uint32_t c = 0; c < a->n_lscols; c++) lf.col_first[c] = P.col_first[c];
-    k_ls_first<<<small_grid(a, (uint64_t)lf.n_labelsets * lf.n_ls), kThreads, 0, s>>>(lf);
+    launch_chain(a, k_ls_first, dim3((unsigned)(small_grid(a, (uint64_t)lf.n_labelsets * lf.n_ls))), s, lf);
     a->tm[T_LABELS].launches++;
   }
   if (P.v1) { k_kind_ranks<<<1, 32, 0, s>>>(a->v1_first_kind, a->d_kindtab.as<uint32_t>(), a->v1_kindrank, a->v1_kind_order, a->v1_n_kind_dict); a->tm[T_LABELS].launches++; }
   if (a->use_onepass && !P.merged) return PA_OK;  // single aggregator: dictionary ranks next, then one sweep (pass_labels_onepass)
   const int Gr = a->sms * a->ree_blocks;  // latency-bound passes: fill every warp slot
   const dim3 ree_grid(Gr, P.rg.n);
-  if (P.merged) k_ree_col<false, true><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);  // run counts (+ this shard's border keys)
-  else k_ree_col<false, false><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);
-  k_ree_scan_partials<<<P.ncols, kThreads, 0, s>>>(P.ra, Gr * kWarps, 0u);
+  if (P.merged) launch_chain(a, k_ree_col<false, true>, ree_grid, s, P.ra, P.rg);  // run counts (+ this shard's border keys)
+  else launch_chain(a, k_ree_col<false, false>, ree_grid, s, P.ra, P.rg);
+  launch_chain(a, k_ree_scan_partials, dim3((unsigned)(P.ncols)), s, P.ra, Gr * kWarps, 0u);
   a->tm[T_LABELS].launches += 2;
   return PA_OK;
 }
@@ -1146,9 +1161,9 @@ static int pass_labels_onepass(pa_agg* a, cudaStream_t s) {
   if (P.rg_single.n) { k_ree_onepass<<<dim3((unsigned)std::max(1, std::min(Gr / 2, (int)(P.tiles.n_tiles / kWarps + 1))), P.rg_single.n), kThreads, a->serial ? 0 : kOnepassPadSmem, s>>>(P.ra, P.rg_single, P.tiles); a->tm[T_LABELS].launches++; }
   if (P.rg_kind.n) {
     const dim3 kg(a->sms * 4, 1);
-    k_ree_col<false, false><<<kg, kThreads, 0, s>>>(P.ra, P.rg_kind);
-    k_ree_scan_partials<<<8, kThreads, 0, s>>>(P.ra, (int)kg.x * kWarps, P.nlab);
-    k_ree_col<true, false><<<kg, kThreads, 0, s>>>(P.ra, P.rg_kind);
+    launch_chain(a, k_ree_col<false, false>, kg, s, P.ra, P.rg_kind);
+    launch_chain(a, k_ree_scan_partials, dim3((unsigned)(8)), s, P.ra, (int)kg.x * kWarps, P.nlab);
+    launch_chain(a, k_ree_col<true, false>, kg, s, P.ra, P.rg_kind);
     a->tm[T_LABELS].launches += 3;
   }
   CK(cudaEventRecord(a->tm[T_LABELS].b, s));
@@ -1164,8 +1179,8 @@ static int pass_label_dicts(pa_agg* a, cudaStream_t s, DBuf& partial) {
 static int pass_labels_emit(pa_agg* a, cudaStream_t s) {
   Pass& P = a->P;
   const dim3 ree_grid(a->sms * a->ree_blocks, P.rg.n);
-  if (P.merged) k_ree_col<true, true><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);   // run ends + final dictionary indices + validity bits
-  else k_ree_col<true, false><<<ree_grid, kThreads, 0, s>>>(P.ra, P.rg);
+  if (P.merged) launch_chain(a, k_ree_col<true, true>, ree_grid, s, P.ra, P.rg);   // run ends + final dictionary indices + validity bits
+  else launch_chain(a, k_ree_col<true, false>, ree_grid, s, P.ra, P.rg);
   a->tm[T_LABELS].launches += 1;
   CK(cudaEventRecord(a->tm[T_LABELS].b, s));
   return PA_OK;
@@ -1216,7 +1231,7 @@ static int process_once(pa_agg* a) {
   if ((rc = a->use_onepass ? pass_labels_onepass(a, s2) : pass_labels_emit(a, s2))) return rc;
   // (the early copy-out is not worth starting when the upload has already finished: nothing left to hide behind)
   const bool early = fork && a->forked_early && a->early.hdr_first && !a->early.issued && !a->P.merged && a->out && !a->chunk_rows.empty() &&
-                     cudaEventQuery(a->chunk_ev[a->chunk_rows.size() - 1]) != cudaSuccess;
+                     (a->early_force || cudaEventQuery(a->chunk_ev[a->chunk_rows.size() - 1]) != cudaSuccess);
   if (early) {
     CK(cudaMemcpyAsync(a->h_early, a->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, s2));
     CK(cudaEventRecord(a->ev_early, s2));
@@ -1410,6 +1425,9 @@ static int collect_nodes(pa_agg* a, const MergeView* mv, std::vector<Node>& cols
   const std::string lab_prefix = v1 ? "labels." : "";           // v1: top-level columns "labels.<name>" (ColumnLabelsPrefix)
   const uint32_t n_loc = c.n_locations, n_lines = c.n_lines, n_fn = c.n_functions, n_idx = (uint32_t)c.n_indices64;
 
+  const bool prof = getenv("PA_COLLECT_PROFILE") != nullptr;
+  const double tp0 = now_ms();
+  double tp1 = 0, tp2 = 0, tp3 = 0;
   // ---- small D2H: dictionary orders, constant-column run keys, function order
   std::vector<uint32_t> ord_type, ord_map, ord_bid, ord_file, ord_fn;
   std::vector<std::vector<uint32_t>> ord_lab(nlab), kind_keys(8);
@@ -1428,6 +1446,7 @@ static int collect_nodes(pa_agg* a, const MergeView* mv, std::vector<Node>& cols
   std::vector<uint32_t> kind_order, n_kind_dict;
   if (v1 && ((rc = d2h_vec(a, kind_order, a->v1_kind_order, 64)) || (rc = d2h_vec(a, n_kind_dict, a->v1_n_kind_dict, 8)))) return rc;
   CK(cudaStreamSynchronize(a->s_comp));
+  tp1 = now_ms();
 
   std::lock_guard<std::mutex> g(a->reg_mu);
   const StringPool& sp = a->sp;
@@ -1450,14 +1469,23 @@ static int collect_nodes(pa_agg* a, const MergeView* mv, std::vector<Node>& cols
     uint32_t n = sp.sid2cid[e.first], v = sp.sid2cid[e.second];
     ext.emplace_back(std::string((const char*)sp.ptr(n), sp.len(n)), std::string((const char*)sp.ptr(v), sp.len(v)));
   }
-  auto label_dict_strings = [&](uint32_t i, std::vector<std::string>& decimals) {
+  auto label_dict_strings = [&](uint32_t i, std::vector<char>& decimals) {
     const ColPlan& cp = a->cols[i];
     std::vector<std::pair<const uint8_t*, uint32_t>> v;
     const auto& ord = ord_lab[i];
-    if (cp.type == COL_CPU || cp.type == COL_TID) {
-      decimals.resize(ord.size());
-      for (size_t k = 0; k < ord.size(); k++) decimals[k] = std::to_string(ord[k]);  // fmt.Sprint(cpu|tid) (:618,:621)
-      for (auto& s : decimals) v.emplace_back((const uint8_t*)s.data(), (uint32_t)s.size());
+    v.reserve(ord.size());
+    if (cp.type == COL_CPU || cp.type == COL_TID) {  // fmt.Sprint(cpu|tid) (:618,:621): decimal digits, formatted into one arena
+      decimals.resize(ord.size() * 10);
+      char* out = decimals.data();
+      for (size_t k = 0; k < ord.size(); k++) {
+        char tmp[10];
+        int n = 0;
+        uint32_t x = ord[k];
+        do { tmp[n++] = (char)('0' + x % 10u); x /= 10u; } while (x);
+        for (int d = 0; d < n; d++) out[d] = tmp[n - 1 - d];
+        v.emplace_back((const uint8_t*)out, (uint32_t)n);
+        out += n;
+      }
     } else if (cp.type == COL_LS) {
       for (uint32_t local : ord) v.push_back(cstr(cp.vals[local]));
     } else {
@@ -1470,7 +1498,7 @@ static int collect_nodes(pa_agg* a, const MergeView* mv, std::vector<Node>& cols
     if (!c.last_nonnull_plus1[i]) continue;  // no sample carried this label: the reference never created the builder
     bool is_ext = false;
     for (auto& e : ext) is_ext |= e.first == cp.name;
-    std::vector<std::string> decimals;
+    std::vector<char> decimals;
     auto strs = label_dict_strings(i, decimals);
     if (is_ext && mv) return a->fail(PA_EINVAL, "merged batch: an external label may not share its name with a sample label");
     if (is_ext) {  // bring the column to the host; LabelAll is applied below
@@ -1524,6 +1552,7 @@ static int collect_nodes(pa_agg* a, const MergeView* mv, std::vector<Node>& cols
     labels.push_back(LabelOut{kv.first, ree_node(lab_prefix + kv.first, true, (int64_t)N, (int64_t)hc.run_ends.size(), host_ref(a, hc.run_ends), std::move(values))});
   }
   std::sort(labels.begin(), labels.end(), [](const LabelOut& x, const LabelOut& y) { return x.name < y.name; });
+  tp2 = now_ms();
 
   auto ree_run_ends_of = [&](uint32_t col) { return BufRef::dev(a->cols[col].run_ends, (uint64_t)c.n_runs[col] * 4); };
   if (v1) {
@@ -1635,7 +1664,9 @@ static int collect_nodes(pa_agg* a, const MergeView* mv, std::vector<Node>& cols
     st.kids.push_back(std::move(locd));
     cols.push_back(std::move(st));
   }
+  tp3 = now_ms();
   append_tail_v2(a, mv, N, kind_keys, cols);
+  if (prof) fprintf(stderr, "collect_nodes: small copies %.3f ms, labels %.3f, stacktrace dictionaries %.3f, tail %.3f\n", tp1 - tp0, tp2 - tp1, tp3 - tp2, now_ms() - tp3);
 
   }
 
@@ -1703,11 +1734,13 @@ static int collect(pa_agg* a, pa_agg_result* res) {
     int rcn = collect_nodes(a, nullptr, cols);
     if (rcn) return rcn;
   }
+  const double t_nodes = now_ms();
   const uint32_t n_loc = c.n_locations, n_fn = c.n_functions, n_idx = (uint32_t)c.n_indices64;
 
   // ---- plan the stream and fill it
   StreamPlan plan;
   plan.build(cols, {{"parca_write_schema_version", v1 ? "v1" : "v2"}}, (int64_t)N);
+  const double t_plan = now_ms();
   if (plan.total > a->out_cap) {
     if (a->early.issued) { CK(cudaStreamSynchronize(a->s_d2h)); a->early.issued = false; }  // the early copies went into the buffer that is too small
     if (a->out) cudaFreeHost(a->out);
@@ -1733,8 +1766,13 @@ static int collect(pa_agg* a, pa_agg_result* res) {
   }
   CK(cudaEventRecord(d1, a->s_comp));
   if (e.issued) CK(cudaStreamWaitEvent(a->s_comp, a->ev_early_done, 0));
+  const double t_enq = now_ms();
   plan.write_host_parts(base);  // metadata, host-built buffers, zero fills and padding overlap the D2H
+  const double t_hostparts = now_ms();
   CK(cudaStreamSynchronize(a->s_comp));
+  if (getenv("PA_COLLECT_PROFILE"))
+    fprintf(stderr, "collect: nodes %.3f ms, plan %.3f, alloc+enqueue %.3f, host parts %.3f, wait for copies %.3f (anchored %d)\n", t_nodes - t0, t_plan - t_nodes,
+            t_enq - t_plan, t_hostparts - t_enq, now_ms() - t_hostparts, (int)anchored);
   const uint8_t* stream = base;
   uint64_t stream_len = plan.total;
   if (a->cfg.ipc_compression == PA_IPC_LZ4_FRAME) {  // network-path framing (ipc.WithLZ4(), :1851); host work, counted in host_ms

@@ -57,6 +57,13 @@ struct Counters {
 
 // ---------------------------------------------------------------------------------------------
 // small helpers
+// Programmatic dependent launch (PA_PDL=1): a chain kernel lets its successor in the stream be scheduled at once and then waits
+// until its own predecessor has completed and flushed — the launch latency of kernel i+1 overlaps the execution of kernel i.
+// Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 // two funnel shifts (SHF) for any constant rotation; the generic (x << r) | (x >> (64 - r)) form compiled to four
 // instructions for r = 31 (shift, shift-as-IMAD, shift, LOP3), which is the rotation of every XXH64 round
 __device__ __forceinline__ unsigned long long rotl64(unsigned long long x, int r) {
@@ -1308,11 +1315,11 @@ __device__ __forceinline__ void scan_emit_dev(const F& f, const typename F::T* p
   }
 }
 template <class F>
-__global__ void __launch_bounds__(kThreads) k_scan_reduce(F f, typename F::T* partial) {
+__global__ void __launch_bounds__(kThreads) k_scan_reduce(F f, typename F::T* partial) { pdl_enter();
   scan_reduce_dev(f, partial + (size_t)blockIdx.y * gridDim.x);
 }
 template <class F>
-__global__ void __launch_bounds__(kThreads) k_scan_emit(F f, const typename F::T* partial) {
+__global__ void __launch_bounds__(kThreads) k_scan_emit(F f, const typename F::T* partial) { pdl_enter();
   scan_emit_dev(f, partial + (size_t)blockIdx.y * gridDim.x, (int)blockIdx.y);
 }
 
@@ -1327,7 +1334,7 @@ __device__ __forceinline__ void stack_bits_dev(const StackSlot* tab, const uint3
     atomicOr(&rowbits[f >> 5], 1u << (f & 31));
   }
 }
-__global__ void __launch_bounds__(kThreads) k_stack_bits(const StackSlot* tab, const uint32_t* claimed, const uint32_t* n_claimed, uint32_t* rowbits) {
+__global__ void __launch_bounds__(kThreads) k_stack_bits(const StackSlot* tab, const uint32_t* claimed, const uint32_t* n_claimed, uint32_t* rowbits) { pdl_enter();
   stack_bits_dev(tab, claimed, n_claimed, rowbits);
 }
 struct WordsF {  // exclusive popcount prefix over bitmap words
@@ -1346,7 +1353,7 @@ __device__ __forceinline__ void stack_assign_dev(StackSlot* tab, const uint32_t*
                                                  const uint32_t* wprefix, const uint16_t* nframes, uint32_t* uniq_row, uint32_t* uniq_slot, uint32_t* uniq_size);
 __global__ void __launch_bounds__(kThreads) k_stack_assign(StackSlot* tab, const uint32_t* claimed, const uint32_t* n_claimed, const uint32_t* rowbits,
                                                            const uint32_t* wprefix, const uint16_t* nframes, uint32_t* uniq_row, uint32_t* uniq_slot,
-                                                           uint32_t* uniq_size) {
+                                                           uint32_t* uniq_size) { pdl_enter();
   stack_assign_dev(tab, claimed, n_claimed, rowbits, wprefix, nframes, uniq_row, uniq_slot, uniq_size);
 }
 __device__ __forceinline__ void stack_assign_dev(StackSlot* tab, const uint32_t* claimed, const uint32_t* n_claimed, const uint32_t* rowbits,
@@ -1387,7 +1394,7 @@ struct UniqOffsetF {  // startOffset := indices.Len() at each first occurrence (
 // both the run key and the dictionary index of the stacktrace_id column.
 __device__ __forceinline__ void rows_materialize_dev(uint32_t n_rows, const uint32_t* slot_of_row, const StackSlot* tab, int* st_offsets, int* st_sizes, uint32_t* ord_out);
 __global__ void __launch_bounds__(kThreads) k_rows_materialize(uint32_t n_rows, const uint32_t* slot_of_row, const StackSlot* tab,
-                                                               int* st_offsets, int* st_sizes, uint32_t* ord_out) {
+                                                               int* st_offsets, int* st_sizes, uint32_t* ord_out) { pdl_enter();
   rows_materialize_dev(n_rows, slot_of_row, tab, st_offsets, st_sizes, ord_out);
 }
 __device__ __forceinline__ void rows_materialize_dev(uint32_t n_rows, const uint32_t* slot_of_row, const StackSlot* tab, int* st_offsets, int* st_sizes, uint32_t* ord_out) {
@@ -1475,7 +1482,7 @@ __device__ __forceinline__ void gather_unique_dev(const Counters* ctr, const uin
 __global__ void __launch_bounds__(kThreads) k_gather_unique(const Counters* ctr, const uint32_t* uniq_row, const uint32_t* slot_of_row,
                                                             const StackSlot* tab, const unsigned long long* frames,
                                                             const unsigned long long* frame_off, uint32_t n_frames_registered,
-                                                            uint32_t* ustream, uint32_t* loc_first, Counters* ctr_w, uint32_t narrow) {
+                                                            uint32_t* ustream, uint32_t* loc_first, Counters* ctr_w, uint32_t narrow) { pdl_enter();
   gather_unique_dev(ctr, uniq_row, slot_of_row, tab, frames, frame_off, n_frames_registered, ustream, loc_first, ctr_w, narrow);
 }
 __device__ __forceinline__ void gather_unique_dev(const Counters* ctr, const uint32_t* uniq_row, const uint32_t* slot_of_row, const StackSlot* tab,
@@ -1604,11 +1611,11 @@ __device__ __forceinline__ void fo_map_dev(const FoJob& j) {
     if ((threadIdx.x & 31) == 0 && nulls) atomicAdd(j.n_null, nulls);
   }
 }
-__global__ void __launch_bounds__(kThreads) k_fo_min(const FoJob* jobs) { fo_min_dev(jobs[blockIdx.y]); }
-__global__ void __launch_bounds__(kThreads) k_fo_zero(const FoJob* jobs) { fo_zero_dev(jobs[blockIdx.y]); }
-__global__ void __launch_bounds__(kThreads) k_fo_bits(const FoJob* jobs) { fo_bits_dev(jobs[blockIdx.y]); }
-__global__ void __launch_bounds__(kThreads) k_fo_assign(const FoJob* jobs) { fo_assign_dev(jobs[blockIdx.y]); }
-__global__ void __launch_bounds__(kThreads) k_fo_map(const FoJob* jobs) { fo_map_dev(jobs[blockIdx.y]); }
+__global__ void __launch_bounds__(kThreads) k_fo_min(const FoJob* jobs) { pdl_enter(); fo_min_dev(jobs[blockIdx.y]); }
+__global__ void __launch_bounds__(kThreads) k_fo_zero(const FoJob* jobs) { pdl_enter(); fo_zero_dev(jobs[blockIdx.y]); }
+__global__ void __launch_bounds__(kThreads) k_fo_bits(const FoJob* jobs) { pdl_enter(); fo_bits_dev(jobs[blockIdx.y]); }
+__global__ void __launch_bounds__(kThreads) k_fo_assign(const FoJob* jobs) { pdl_enter(); fo_assign_dev(jobs[blockIdx.y]); }
+__global__ void __launch_bounds__(kThreads) k_fo_map(const FoJob* jobs) { pdl_enter(); fo_map_dev(jobs[blockIdx.y]); }
 
 // ---------------------------------------------------------------------------------------------
 // location dictionary: resolved per-frame attributes gathered in location order
@@ -1654,7 +1661,7 @@ struct LocLinesF {  // scan of has_line over locations (lineListOffsets, parca_r
 };
 // validity words of the lines ListView (null where the location has no line, arrow_v2.go:403-418)
 __device__ __forceinline__ void line_validity_dev(const Counters* ctr, const int* line_size, uint32_t* words);
-__global__ void __launch_bounds__(kThreads) k_line_validity(const Counters* ctr, const int* line_size, uint32_t* words) { line_validity_dev(ctr, line_size, words); }
+__global__ void __launch_bounds__(kThreads) k_line_validity(const Counters* ctr, const int* line_size, uint32_t* words) { pdl_enter(); line_validity_dev(ctr, line_size, words); }
 __device__ __forceinline__ void line_validity_dev(const Counters* ctr, const int* line_size, uint32_t* words) {
   uint32_t n = ctr->n_locations;
   uint32_t nw = (n + 31) / 32;
@@ -1672,7 +1679,7 @@ __device__ __forceinline__ void func_keys_dev(const Counters* ctr, const uint32_
   for (uint32_t k = blockIdx.x * kThreads + threadIdx.x; k < n; k += gridDim.x * kThreads) file_key[k] = fn_file_cid[func_order[k]];
 }
 __global__ void __launch_bounds__(kThreads) k_func_keys(const Counters* ctr, const uint32_t* func_order, const uint32_t* fn_file_cid,
-                                                        uint32_t* file_key) {
+                                                        uint32_t* file_key) { pdl_enter();
   func_keys_dev(ctr, func_order, fn_file_cid, file_key);
 }
 
@@ -1772,7 +1779,7 @@ struct LsFirstArgs {
   const uint32_t* lsmat; uint32_t n_lscols, n_ls;
   uint32_t* col_first[kMaxCols];
 };
-__global__ void __launch_bounds__(kThreads) k_ls_first(LsFirstArgs a) {
+__global__ void __launch_bounds__(kThreads) k_ls_first(LsFirstArgs a) { pdl_enter();
   uint32_t cells = a.n_labelsets * a.n_ls;
   for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < cells; i += gridDim.x * kThreads) {
     uint32_t ls = i / a.n_ls, c = i % a.n_ls;
@@ -2021,7 +2028,7 @@ __device__ __forceinline__ void ree_kinds(const ReeArgs& a, const uint32_t* s_ki
 }
 
 template <bool EMIT, bool MERGED>
-__global__ void __launch_bounds__(kThreads) k_ree_col(ReeArgs a, ReeGroups groups) {
+__global__ void __launch_bounds__(kThreads) k_ree_col(ReeArgs a, ReeGroups groups) { pdl_enter();
   __shared__ uint32_t s_kind[64], s_krank[64];
   const ReeGroup g = groups.g[blockIdx.y];
   if (g.type == COL_KIND) {
@@ -2039,7 +2046,7 @@ __global__ void __launch_bounds__(kThreads) k_ree_col(ReeArgs a, ReeGroups group
     default: ree_single<EMIT, MERGED, long long>(a, g.col, false, KeyTs{a.ts}); break;           // COL_TS: Int64RunEndBuilder.Append
   }
 }
-__global__ void __launch_bounds__(kThreads) k_ree_scan_partials(ReeArgs a, int g, uint32_t col0) {  // grid = columns col0 .., kThreads threads
+__global__ void __launch_bounds__(kThreads) k_ree_scan_partials(ReeArgs a, int g, uint32_t col0) { pdl_enter();  // grid = columns col0 .., kThreads threads
   const uint32_t c = col0 + blockIdx.x;
   uint32_t* p = a.partial + (size_t)c * g;
   uint32_t run = 0;

@@ -123,6 +123,44 @@ def test_narrow_frame_id_ring(oracle, gpu, mode):
     assert_same(oracle, gpu, as_v1(synth.edge_workload(seed=52, n=3000, hash_mode=mode)), frame_id_bytes=4)
 
 
+def test_early_copy_out_of_trailing_columns(oracle, gpu, monkeypatch):
+    """A multi-chunk flush copies stacktrace_id / value / timestamp to the host while the ids are still uploading, at positions
+    counted from the END of the output buffer of the previous flush. Intervals of different sizes and shapes through ONE
+    aggregator: bigger than the buffer (re-allocation drops the early copies), smaller (the stream starts in the middle of the
+    buffer), mixed sample kinds (many kind runs: too many -> ordinary path), LZ4 bodies, a narrow ring."""
+    monkeypatch.setenv("PA_EARLY_D2H_ALWAYS", "1")
+    base = synth.config1()
+    edge = synth.edge_workload(seed=61, n=9000, hash_mode=abi.PA_HASH_XXH64X2, external=False)
+    for kw in ({}, {"frame_id_bytes": 4}, {"ipc_compression": abi.PA_IPC_LZ4_FRAME}):
+        a = gpu.from_workload(base, chunk_samples=4096, **kw)
+        for n in (20_000, 20_000, 60_000, 5_000, 33_333, 1):
+            w = base.head(n)
+            want, st = oracle.run(w)
+            gpu.load(a, w)
+            res = a.flush()
+            got = res.ipc_bytes()
+            if kw.get("ipc_compression"):
+                assert pa.ipc.open_stream(got).read_all().equals(pa.ipc.open_stream(want).read_all())
+            else:
+                assert got == want, "interval of %d rows differs" % n
+            assert res.n_rows == st["rows"]
+        a.close()
+    a = gpu.from_workload(edge, chunk_samples=1000)   # every sample kind, alternating: hundreds of kind runs
+    want, _ = oracle.run(edge)
+    for _ in range(3):
+        gpu.load(a, edge)
+        assert a.flush().ipc_bytes() == want
+    a.close()
+    w = synth.config1().head(30_000)
+    w.hdrs["kind"][:] = np.arange(w.n) % 2 * abi.PA_KIND_OFFCPU  # 30k kind runs: far beyond what the early path sizes
+    a = gpu.from_workload(w, chunk_samples=5000)
+    want, _ = oracle.run(w)
+    for _ in range(2):
+        gpu.load(a, w)
+        assert a.flush().ipc_bytes() == want
+    a.close()
+
+
 def test_single_ring_flag(oracle, gpu):
     """PA_CFG_SINGLE_RING: one ring buffer; ingest is refused while a staged batch holds it, and works again after collect"""
     w = synth.config1().head(20_000)
