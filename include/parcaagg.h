@@ -141,8 +141,10 @@ typedef struct pa_agg_config {
   uint32_t schema;             /* PA_SCHEMA_V2 (0, default here) or PA_SCHEMA_V1 (--remote-store-use-v2-schema=false,
                                   flags/flags.go:349): which sample record pa_agg_flush builds */
   uint64_t stack_cache_entries; /* v1 only: capacity of the known-stacks store (the `stacks` LRU, cacheSize at
-                                  parca_reporter.go:876; main.go:630 keeps it >= 65536). 0 = max(65536, max_samples) */
-  uint64_t stack_cache_frames;  /* v1 only: capacity of the store's frame arena, in frames. 0 = 64 per entry (4 bytes each) */
+                                  parca_reporter.go:876; main.go:630 keeps it >= 65536). 0 = max(65536, max_samples). Exact LRU:
+                                  after every batch and every pa_agg_stacktraces call the store holds the stacks accessed last */
+  uint64_t stack_cache_frames;  /* v1 only: capacity of the store's frame arena, in frames. 0 = 128 per entry (4 bytes each: content + one batch of 64-frame stacks). Not a
+                                  reference limit: when the live stacks alone exceed it the store starts over from the current batch */
   uint32_t unknown_frame_type_sid; /* v1 only: string id of libpf.UnknownFrame.String() for the "missing stacktrace"
                                   row (:1561); 0 = the literal "unknown" */
   uint32_t flags;              /* PA_CFG_* */

@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <map>
 #include <string>
+#include <list>
 #include <unordered_map>
 #include <vector>
 
@@ -346,9 +347,26 @@ struct Reporter {
   std::vector<pa_frame_desc> frames;
   std::vector<std::vector<std::pair<std::string, std::string>>> labelsets;  // the labels LRU content (:569)
   std::unordered_map<TraceHash, std::pair<const uint64_t*, int>, TraceHashHasher> stacks;  // r.stacks LRU (:224-227), v2: never read
-  // v1: the same LRU, persistent across intervals and read by buildStacktraceRecord. Eviction is not modelled
-  // (an evicted stack and a never-seen one produce the same "missing stacktrace" row).
-  std::unordered_map<TraceHash, std::vector<uint64_t>, TraceHashHasher> known;
+  // v1: the same LRU, persistent across intervals and read by buildStacktraceRecord: lru.SyncedLRU[libpf.TraceHash, libpf.Frames]
+  // (parca_reporter.go:106, :876; github.com/elastic/go-freelru is not vendored: this is the textbook LRU its README describes —
+  // Get moves the entry to the front, Add inserts at the front and evicts the entry at the back once `cap` entries are held).
+  // cap = pa_agg_config.stack_cache_entries (cacheSize, main.go:630-645); 0 = unbounded.
+  struct StackLru {
+    uint64_t cap = 0;
+    std::list<std::pair<TraceHash, std::vector<uint64_t>>> order;  // front = most recently used
+    std::unordered_map<TraceHash, std::list<std::pair<TraceHash, std::vector<uint64_t>>>::iterator, TraceHashHasher> map;
+    const std::vector<uint64_t>* Get(const TraceHash& h) {
+      auto it = map.find(h);
+      if (it == map.end()) return nullptr;
+      order.splice(order.begin(), order, it->second);
+      return &it->second->second;
+    }
+    void Add(const TraceHash& h, std::vector<uint64_t> fr) {
+      if (cap && map.size() >= cap) { map.erase(order.back().first); order.pop_back(); }
+      order.emplace_front(h, std::move(fr));
+      map[h] = order.begin();
+    }
+  } known;
   SampleWriterV2* w = new SampleWriterV2();
   SampleWriter* w1 = new SampleWriter();  // v1 schema writer (r.sampleWriter)
   uint64_t emptySamples = 0;
@@ -481,7 +499,7 @@ struct Reporter {
       hash.lo = orc_xxh64_impl(fr, (uint64_t)h.nframes * 8, PA_XXH_SEED_LO);
     }
     if (cfg.schema == PA_SCHEMA_V1) {
-      if (known.find(hash) == known.end()) known.emplace(hash, std::vector<uint64_t>(fr, fr + h.nframes));        // :224-227
+      if (!known.Get(hash)) known.Add(hash, std::vector<uint64_t>(fr, fr + h.nframes));                           // :224-227
     } else if (stacks.find(hash) == stacks.end()) stacks.emplace(hash, std::make_pair(fr, (int)h.nframes));
     auto labels = labelsForTID(h.tid, h.labelset_id, S(h.comm_sid), h.cpu);                            // :229
     if (h.nframes == 0) emptySamples++;                                                                 // :237-239
@@ -563,8 +581,8 @@ struct Reporter {
       bool isComplete = true;
       TraceHash th{0, 0};  // libpf.TraceHashFromBytes
       for (int k = 0; k < 8; k++) { th.hi = (th.hi << 8) | ids[16 * i + k]; th.lo = (th.lo << 8) | ids[16 * i + 8 + k]; }
-      auto it = known.find(th);
-      if (it == known.end()) {  // :1556-1573
+      const std::vector<uint64_t>* hit = known.Get(th);  // :1555
+      if (!hit) {  // :1556-1573
         w.LocationsList.Append(true, w.Locations);
         w.Locations++;
         w.Address.Append(0);
@@ -582,7 +600,7 @@ struct Reporter {
         w.IsComplete.Append(false);
         continue;
       }
-      const std::vector<uint64_t>& traceInfo = it->second;
+      const std::vector<uint64_t>& traceInfo = *hit;
       w.LocationsList.Append(!traceInfo.empty(), w.Locations);  // :1576-1580
       for (uint64_t frame_id : traceInfo) {
         const pa_frame_desc& f = frames[frame_id];
@@ -833,6 +851,7 @@ void* orc_create(const pa_agg_config* cfg) {
   if (!cfg || cfg->samples_per_second == 0) return nullptr;
   Reporter* r = new Reporter();
   r->cfg = *cfg;
+  r->known.cap = cfg->stack_cache_entries;
   return r;
 }
 void orc_destroy(void* p) { if (!p) return; Reporter* r = (Reporter*)p; delete r->w; delete r->w1; delete r; }

@@ -57,11 +57,11 @@ STAT_NAMES = ("rows", "unique_stacks", "locations", "functions", "location_indic
 class Oracle:
     """One reporter instance: register the workload's tables once, then ingest/flush batches."""
 
-    def __init__(self, w):
+    def __init__(self, w, stack_cache_entries=0):
         L = lib()
         cfg = abi.PaAggConfig(abi_version=abi.PA_ABI_VERSION, device=0, hash_mode=w.hash_mode, label_flags=w.label_flags,
                               samples_per_second=w.samples_per_second, schema=getattr(w, "schema", 0),
-                              unknown_frame_type_sid=getattr(w, "unknown_frame_type_sid", 0))
+                              unknown_frame_type_sid=getattr(w, "unknown_frame_type_sid", 0), stack_cache_entries=stack_cache_entries)
         self.h = L.orc_create(C.byref(cfg))
         assert self.h
         blob, offs = abi.pack_strings(w.strings[1:])  # id 0 == "" is implicit

@@ -181,7 +181,11 @@ struct pa_agg {
   Mirror<uint64_t> m1_line, m1_col;
   Mirror<uint8_t> m1_complete;
   DBuf d_store, d_store_arena, d_store_ctl, d_v1_ids, d_st1;
+  DBuf d_store_stamp, d_v1_last, d_select;  // last access per store slot; last row per stack of the batch; radix-select scratch
   uint64_t store_entries = 0, store_slots = 0, store_frames = 0, last_unique = 0;
+  uint64_t store_epoch = 0;                  // LRU clock: one tick per ingested batch and per stacktrace request
+  uint32_t* h_select = nullptr;              // pinned: 256-bin histogram of a select pass, then a StoreCtl read-back
+  uint64_t store_compactions = 0, store_evictions = 0;
   uint32_t cid_unknown = 0, cid_missing = 0;  // "unknown" (libpf.UnknownFrame.String()) and "missing stacktrace" (:1561, :1568)
 
   // ---- ring (pinned host), double buffered
@@ -457,14 +461,20 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
     a->cid_unknown = a->sp.intern("unknown");
     a->cid_missing = a->sp.intern("missing stacktrace");
     a->store_entries = cfg->stack_cache_entries ? cfg->stack_cache_entries : std::min<uint64_t>(std::max<uint64_t>(65536, N), 1ull << 24);
-    if (a->store_entries > (1ull << 30)) return bail(PA_ERANGE);
-    a->store_slots = pow2_at_least(2 * a->store_entries);
-    a->store_frames = cfg->stack_cache_frames ? cfg->stack_cache_frames : a->store_entries * 64;
+    if (a->store_entries > (1ull << 28)) return bail(PA_ERANGE);
+    // room for the cache's content PLUS one batch's new stacks (fewer than the capacity, or the batch replaces the content): the
+    // batch is inserted first and the least recently used entries are evicted afterwards
+    a->store_slots = pow2_at_least(4 * a->store_entries);
+    a->store_frames = cfg->stack_cache_frames ? cfg->stack_cache_frames : a->store_entries * 128;
     need(a->d_store, (a->store_slots + 2) * sizeof(StoreSlot));
     need(a->d_store_arena, a->store_frames * 4);
     need(a->d_store_ctl, sizeof(StoreCtl));
+    need(a->d_store_stamp, (a->store_slots + 2) * 8);
+    need(a->d_select, 256 * 4);
     need(a->d_v1_ids, N * 16);
-    if (ok) ok = cudaMemset(a->d_store.p, 0, (a->store_slots + 2) * sizeof(StoreSlot)) == cudaSuccess && cudaMemset(a->d_store_ctl.p, 0, sizeof(StoreCtl)) == cudaSuccess;
+    if (ok) ok = cudaMemset(a->d_store.p, 0, (a->store_slots + 2) * sizeof(StoreSlot)) == cudaSuccess && cudaMemset(a->d_store_ctl.p, 0, sizeof(StoreCtl)) == cudaSuccess &&
+                 cudaMemset(a->d_store_stamp.p, 0, (a->store_slots + 2) * 8) == cudaSuccess &&
+                 cudaHostAlloc((void**)&a->h_select, 256 * 4 + sizeof(StoreCtl), cudaHostAllocDefault) == cudaSuccess;
   }
   if (!ok) return bail(PA_ENOMEM);
   *out = a;
@@ -479,6 +489,7 @@ void pa_agg_destroy(pa_agg* a) {
   if (a->s_copy) cudaStreamSynchronize(a->s_copy);
   if (a->s_d2h) cudaStreamSynchronize(a->s_d2h);
   if (a->h_early) cudaFreeHost(a->h_early);
+  if (a->h_select) cudaFreeHost(a->h_select);
   for (auto e : a->hash_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : {a->ev_hdr_all, a->ev_hdr_done, a->ev_early, a->ev_early_done}) if (e) cudaEventDestroy(e);
   if (a->s_d2h) cudaStreamDestroy(a->s_d2h);
@@ -491,7 +502,7 @@ void pa_agg_destroy(pa_agg* a) {
                  &a->d_arena, &a->d_partial, &a->d_partial2, &a->d_ree_partial, &a->d_lsmat, &a->d_kindtab, &a->d_cols, &a->d_jobs,
                  &a->m_addr.buf, &a->m_line.buf, &a->m_type.buf, &a->m_map.buf, &a->m_bid.buf, &a->m_func.buf, &a->m_fnfile.buf, &a->m_sid2cid.buf,
                  &a->m1_map.buf, &a->m1_bid.buf, &a->m1_fn.buf, &a->m1_file.buf, &a->m1_line.buf, &a->m1_col.buf, &a->m1_complete.buf,
-                 &a->d_store, &a->d_store_arena, &a->d_store_ctl, &a->d_v1_ids, &a->d_st1};
+                 &a->d_store, &a->d_store_arena, &a->d_store_ctl, &a->d_v1_ids, &a->d_st1, &a->d_store_stamp, &a->d_v1_last, &a->d_select};
   for (DBuf* b : all) b->release();
   for (auto e : a->chunk_ev) cudaEventDestroy(e);
   if (a->ev_h2d0) cudaEventDestroy(a->ev_h2d0);
@@ -742,8 +753,9 @@ static int upload_descriptors(pa_agg* a, const void* jobs, size_t jb, const void
   return PA_OK;
 }
 
-// v1: add this batch's new unique stacks to the known-stacks store (parca_reporter.go:224-227)
-static void launch_store_insert(pa_agg* a) {
+// v1: the batch's accesses to the `stacks` LRU (parca_reporter.go:224-227): every unique stack of the batch is looked up and, if
+// unknown, added; known ones (evicted ones included) get the batch's access time
+static void launch_store_insert(pa_agg* a, uint32_t min_last_p1) {
   StoreInsertArgs sa{};
   Counters* ctr = a->d_ctr.as<Counters>();
   sa.ctr = ctr; sa.uniq_row = a->d_uniq_row.as<uint32_t>(); sa.slot_of_row = a->d_slot.as<uint32_t>(); sa.tab = a->d_table.as<StackSlot>();
@@ -752,8 +764,121 @@ static void launch_store_insert(pa_agg* a) {
   sa.narrow = a->idb == 4 ? 1u : 0u;
   sa.n_frames_registered = a->P.n_frames;
   sa.st = a->d_store.as<StoreSlot>(); sa.mask = (uint32_t)(a->store_slots - 1); sa.arena = a->d_store_arena.as<uint32_t>();
-  sa.cap_frames = a->store_frames; sa.cap_entries = (uint32_t)a->store_entries; sa.ctl = a->d_store_ctl.as<StoreCtl>(); sa.ctr_w = ctr;
+  sa.cap_frames = a->store_frames; sa.cap_entries = (uint32_t)(a->store_slots - a->store_slots / 4); sa.ctl = a->d_store_ctl.as<StoreCtl>(); sa.ctr_w = ctr;
+  sa.stamp = a->d_store_stamp.as<unsigned long long>(); sa.last_row = a->d_v1_last.as<uint32_t>();
+  sa.epoch_hi = a->store_epoch << 32; sa.min_last_p1 = min_last_p1;
   k_store_insert<<<a->G, kThreads, 0, a->s_comp>>>(sa);
+}
+// the k-th largest of the non-zero keys (k >= 1, at least k of them exist): eight histogram passes from the top byte down
+static int select_kth_largest(pa_agg* a, const unsigned long long* keys, uint64_t n, uint64_t k, unsigned long long* out) {
+  cudaStream_t s = a->s_comp;
+  unsigned long long prefix = 0;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    CK(cudaMemsetAsync(a->d_select.p, 0, 256 * 4, s));
+    k_select_hist<<<small_grid(a, n), kThreads, 0, s>>>(keys, n, prefix, shift, a->d_select.as<uint32_t>());
+    CK(cudaMemcpyAsync(a->h_select, a->d_select.p, 256 * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int b = 255;
+    for (; b > 0; b--) {
+      if (a->h_select[b] >= k) break;
+      k -= a->h_select[b];
+    }
+    prefix |= (unsigned long long)b << shift;
+  }
+  *out = prefix;
+  return PA_OK;
+}
+static int store_ctl_read(pa_agg* a, StoreCtl* out) {
+  CK(cudaMemcpyAsync(a->h_select + 256, a->d_store_ctl.p, sizeof(StoreCtl), cudaMemcpyDeviceToHost, a->s_comp));
+  CK(cudaStreamSynchronize(a->s_comp));
+  memcpy(out, a->h_select + 256, sizeof(StoreCtl));
+  return PA_OK;
+}
+static int store_clear(pa_agg* a) {
+  CK(cudaMemsetAsync(a->d_store.p, 0, (a->store_slots + 2) * sizeof(StoreSlot), a->s_comp));
+  CK(cudaMemsetAsync(a->d_store_stamp.p, 0, (a->store_slots + 2) * 8, a->s_comp));
+  CK(cudaMemsetAsync(a->d_store_ctl.p, 0, sizeof(StoreCtl), a->s_comp));
+  return PA_OK;
+}
+// compaction: evicted entries give their slots and frames back (the live ones move to a fresh table and arena)
+static int store_compact(pa_agg* a) {
+  cudaStream_t s = a->s_comp;
+  DBuf st2, stamp2, arena2;
+  CK(st2.ensure((a->store_slots + 2) * sizeof(StoreSlot)));
+  CK(stamp2.ensure((a->store_slots + 2) * 8));
+  CK(arena2.ensure(a->store_frames * 4));
+  CK(cudaMemsetAsync(st2.p, 0, (a->store_slots + 2) * sizeof(StoreSlot), s));
+  CK(cudaMemsetAsync(stamp2.p, 0, (a->store_slots + 2) * 8, s));
+  CK(cudaMemsetAsync(a->d_store_ctl.p, 0, sizeof(StoreCtl), s));
+  StoreRebuildArgs ra{};
+  ra.old_st = a->d_store.as<StoreSlot>(); ra.old_stamp = a->d_store_stamp.as<unsigned long long>(); ra.old_arena = a->d_store_arena.as<uint32_t>();
+  ra.old_mask = (uint32_t)(a->store_slots - 1);
+  ra.st = st2.as<StoreSlot>(); ra.stamp = stamp2.as<unsigned long long>(); ra.arena = arena2.as<uint32_t>(); ra.mask = ra.old_mask; ra.ctl = a->d_store_ctl.as<StoreCtl>();
+  k_store_rebuild<<<small_grid(a, a->store_slots * 32), kThreads, 0, s>>>(ra);
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  std::swap(a->d_store, st2); std::swap(a->d_store_stamp, stamp2); std::swap(a->d_store_arena, arena2);
+  st2.release(); stamp2.release(); arena2.release();
+  a->store_compactions++;
+  return PA_OK;
+}
+// One batch's worth of LRU traffic, after the pass has ranked the batch's unique stacks (a->h_ctr is current).
+static int v1_store_update(pa_agg* a) {
+  cudaStream_t s = a->s_comp;
+  const uint64_t U = a->h_ctr.n_unique, C = a->store_entries, N = a->N;
+  Counters* ctr = a->d_ctr.as<Counters>();
+  a->store_epoch++;
+  if (a->store_epoch >= (1ull << 32)) return a->fail(PA_ERANGE, "stack store: access clock overflow");
+  CK(a->d_v1_last.ensure((a->table_cap + 2) * 4));
+  CK(cudaMemsetAsync(a->d_v1_last.p, 0, (a->table_cap + 2) * 4, s));
+  k_last_rows<<<a->G, kThreads, 0, s>>>((uint32_t)N, a->d_slot.as<uint32_t>(), a->d_v1_last.as<uint32_t>());
+  uint32_t min_last_p1 = 0;
+  StoreCtl ctl{};
+  int rc;
+  if (U >= C) {
+    // the batch alone touches at least as many stacks as the cache holds: afterwards it holds exactly the C of them seen last
+    DBuf tmp;
+    CK(tmp.ensure(U * 8));
+    k_batch_stamps<<<small_grid(a, U), kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), a->d_v1_last.as<uint32_t>(), tmp.as<unsigned long long>());
+    unsigned long long t = 0;
+    if ((rc = select_kth_largest(a, tmp.as<unsigned long long>(), U, C, &t))) return rc;
+    tmp.release();
+    min_last_p1 = (uint32_t)t;
+    if ((rc = store_clear(a))) return rc;
+    a->store_evictions++;
+  } else {
+    if ((rc = store_ctl_read(a, &ctl))) return rc;
+    const uint64_t phys = a->store_slots - a->store_slots / 4;
+    if (ctl.entries > ctl.live && (ctl.entries + U > phys || ctl.used_frames + a->h_ctr.n_indices64 > a->store_frames) && (rc = store_compact(a))) return rc;
+  }
+  bool cleared = U >= C;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    CK(cudaMemsetAsync(&ctr->store_overflow, 0, 4, s));
+    launch_store_insert(a, min_last_p1);
+    CK(cudaMemcpyAsync(a->h_ctr_pinned, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    if ((rc = store_ctl_read(a, &ctl))) return rc;
+    CK(cudaGetLastError());
+    a->h_ctr.err |= a->h_ctr_pinned->err;
+    if (!a->h_ctr_pinned->store_overflow || attempt == 2) break;  // (third time: whatever still does not fit stays marked as dropped)
+    // out of slots or of frame space: first give back what evicted entries hold; if that is not enough, start over with this
+    // batch only (the frame arena is this library's limit, not the reference's: DESIGN section 5a)
+    if (ctl.entries > ctl.live && !cleared && attempt == 0) {
+      if ((rc = store_compact(a))) return rc;
+    } else {
+      if ((rc = store_clear(a))) return rc;
+      cleared = true;
+      a->store_evictions++;
+    }
+  }
+  if (ctl.live > C) {  // evict everything but the C entries accessed last
+    unsigned long long t = 0;
+    if ((rc = select_kth_largest(a, a->d_store_stamp.as<unsigned long long>(), a->store_slots + 2, C, &t))) return rc;
+    k_store_kill<<<small_grid(a, a->store_slots + 2), kThreads, 0, s>>>(a->d_store_stamp.as<unsigned long long>(), a->store_slots + 2, t, a->d_store_ctl.as<StoreCtl>());
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    a->store_evictions++;
+  }
+  return PA_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1086,7 +1211,6 @@ static int pass_rank_single(pa_agg* a) {
   launch_chain(a, k_rows_materialize, dim3((unsigned)(G)), s, (uint32_t)N, a->d_slot.as<uint32_t>(), tab, a->d_stoff.as<int>(), a->d_stsize.as<int>(), P.v1 ? a->v1_ord : nullptr);
   if (P.v1) {  // v1 has no inline stacktraces: only the dictionary of unique stack ids
     k_gather_ids<<<small_grid(a, std::min<uint64_t>(N, P.cap / 2) + 1), kThreads, 0, s>>>(ctr, a->d_uniq_row.as<uint32_t>(), a->d_uuid.as<uint8_t>(), a->v1_ids, a->v1_id_off);
-    launch_store_insert(a);
     a->tm[T_RANK].launches++;
   } else {
     launch_chain(a, k_gather_unique, dim3((unsigned)(G)), s, ctr, a->d_uniq_row.as<uint32_t>(), a->d_slot.as<uint32_t>(), tab, a->src_frames,
@@ -1280,15 +1404,8 @@ static int process(pa_agg* a) {
   }
   if ((rc = check_batch_errors(a, a->h_ctr.err))) return rc;
   if (a->cfg.schema == PA_SCHEMA_V1) {
-    if (a->h_ctr.store_overflow) {
-      // the store is full: start a new generation (every older stack becomes "missing", as after an LRU eviction)
-      // and add this batch's stacks again; whatever still does not fit stays marked as dropped
-      CK(cudaMemsetAsync(a->d_store.p, 0, (a->store_slots + 2) * sizeof(StoreSlot), a->s_comp));
-      CK(cudaMemsetAsync(a->d_store_ctl.p, 0, sizeof(StoreCtl), a->s_comp));
-      launch_store_insert(a);
-      CK(cudaStreamSynchronize(a->s_comp));
-      CK(cudaGetLastError());
-    }
+    if ((rc = v1_store_update(a))) return rc;
+    if ((rc = check_batch_errors(a, a->h_ctr.err))) return rc;
     a->last_unique = a->h_ctr.n_unique;
   }
   remember_sizes(a);
@@ -1836,7 +1953,9 @@ static int stacktraces(pa_agg* a, const uint8_t* ids, uint64_t n, pa_agg_result*
   if (n) CK(cudaMemcpyAsync(d_ids, ids_host, n * 16, cudaMemcpyHostToDevice, s));
   const StoreSlot* st = a->d_store.as<StoreSlot>();
   const uint32_t smask = (uint32_t)(a->store_slots - 1);
-  k_st_lookup<<<small_grid(a, n), kThreads, 0, s>>>(d_ids, n32, st, smask, q_slot, q_nloc);
+  a->store_epoch++;  // one tick of the LRU clock per request: its Gets are more recent than every access before it
+  if (a->store_epoch >= (1ull << 32)) return a->fail(PA_ERANGE, "stack store: access clock overflow");
+  k_st_lookup<<<small_grid(a, n), kThreads, 0, s>>>(d_ids, n32, st, smask, q_slot, q_nloc, a->d_store_stamp.as<unsigned long long>(), a->store_epoch << 32);
   launch_scan(a, StLocF{q_nloc, n32, loc_off, ctr}, 1, tm, small_grid(a, n), s, a->d_partial);
   tm.launches += 1;
   CK(cudaMemcpyAsync(a->h_ctr_pinned, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));

@@ -2200,17 +2200,22 @@ __global__ void __launch_bounds__(kThreads) k_ree_onepass(ReeArgs a, ReeGroups g
 
 // ---------------------------------------------------------------------------------------------
 // v1 schema: device-resident store of known stacks — the `stacks` LRU of the reference
-// (reporter/parca_reporter.go:105, filled at :224-227, read by buildStacktraceRecord :1555). Every v1
-// flush adds the batch's NEW unique stacks (first occurrence wins, exactly like "if !exists { Add }");
-// the store is append-only and is cleared as a whole when it runs out of room (an evicted stack and a
-// never-seen one both produce the reference's "missing stacktrace" row).
+// (reporter/parca_reporter.go:105; `Get` then `Add` per sample at :224-227, `Get` per requested id in buildStacktraceRecord :1555).
+// An LRU's content after any access sequence is the `capacity` distinct keys accessed most recently, so the store keeps, per
+// entry, the time of its last access —
+//     stamp = epoch << 32 | position      epoch: one per ingested batch and per stacktrace request
+//                                         position: LAST row of the stack in the batch / index of the id in the request
+// — and after every batch drops all but the `capacity` largest stamps (radix select + k_store_kill). stamp 0 = evicted: the slot
+// and its frames stay until the next compaction (k_store_rebuild) or until the stack is seen again (it is then revived in place).
+// What is NOT reference behaviour: the frame arena is finite (pa_agg_config.stack_cache_frames); running out of it clears the
+// store as a whole (an evicted stack and a never-seen one both produce the reference's "missing stacktrace" row).
 struct __align__(32) StoreSlot {
   Key128 key;              // (0,0) = empty; claimed by a 128-bit CAS
   unsigned long long off;  // first frame in the store's frame arena
   uint32_t size;           // frames; kNull = claimed but dropped (no room)
   uint32_t claimed;        // only used by the dedicated all-zero-id slot (index mask+1)
 };
-struct StoreCtl { unsigned long long used_frames; uint32_t entries; uint32_t pad; };
+struct StoreCtl { unsigned long long used_frames; uint32_t entries; uint32_t live; };  // entries: claimed slots (live + evicted)
 
 __device__ __forceinline__ uint32_t store_find(const StoreSlot* st, uint32_t mask, Key128 k) {
   if (key_zero(k)) return st[mask + 1].claimed ? mask + 1 : kNull;
@@ -2238,10 +2243,50 @@ struct StoreInsertArgs {
   uint32_t mask;
   uint32_t* arena;
   unsigned long long cap_frames;
-  uint32_t cap_entries;
+  uint32_t cap_entries;              // physical: claimed slots the table may hold
   StoreCtl* ctl;
   Counters* ctr_w;
+  unsigned long long* stamp;         // [mask + 2] last access per slot, 0 = evicted
+  const uint32_t* last_row;          // [batch table slots] last row of every stack of the batch
+  unsigned long long epoch_hi;       // epoch << 32
+  uint32_t min_last_p1;              // only stacks with last_row + 1 >= this are stored (a batch with more unique stacks than the cache holds)
 };
+// last occurrence of every stack of the batch (the LRU's access time of its entry)
+__global__ void __launch_bounds__(kThreads) k_last_rows(uint32_t n_rows, const uint32_t* slot_of_row, uint32_t* last_row) {
+  for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < n_rows; r += gridDim.x * kThreads) {
+    const uint32_t s = slot_of_row[r];
+    if (s != kNull && last_row[s] < r) atomicMax(&last_row[s], r);
+  }
+}
+// stamps of the batch's unique stacks as select keys (last row + 1, so that 0 stays "nothing")
+__global__ void __launch_bounds__(kThreads) k_batch_stamps(const Counters* ctr, const uint32_t* uniq_row, const uint32_t* slot_of_row, const uint32_t* last_row,
+                                                           unsigned long long* out) {
+  const uint32_t nu = ctr->n_unique;
+  for (uint32_t u = blockIdx.x * kThreads + threadIdx.x; u < nu; u += gridDim.x * kThreads) out[u] = (unsigned long long)last_row[slot_of_row[uniq_row[u]]] + 1ull;
+}
+// one radix-select pass: histogram of byte `shift / 8` over the non-zero keys whose higher bytes equal `prefix`
+__global__ void __launch_bounds__(kThreads) k_select_hist(const unsigned long long* keys, uint64_t n, unsigned long long prefix, int shift, uint32_t* hist) {
+  __shared__ uint32_t h[256];
+  if (threadIdx.x < 256) h[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned long long hi_mask = shift >= 56 ? 0ull : (~0ull << (shift + 8));
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kThreads) {
+    const unsigned long long k = keys[i];
+    if (k != 0 && (k & hi_mask) == prefix) atomicAdd(&h[(k >> shift) & 0xFFu], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 256 && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+// evict: every entry accessed before `threshold`
+__global__ void __launch_bounds__(kThreads) k_store_kill(unsigned long long* stamp, uint64_t n, unsigned long long threshold, StoreCtl* ctl) {
+  uint32_t killed = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kThreads) {
+    const unsigned long long k = stamp[i];
+    if (k != 0 && k < threshold) { stamp[i] = 0; killed++; }
+  }
+  for (int o = 16; o > 0; o >>= 1) killed += __shfl_xor_sync(0xFFFFFFFFu, killed, o);
+  if ((threadIdx.x & 31) == 0 && killed) atomicSub(&ctl->live, killed);
+}
 // one warp per unique stack of the batch (unique within the launch, so a key is claimed by at most one warp)
 __global__ void __launch_bounds__(kThreads) k_store_insert(StoreInsertArgs a) {
   const unsigned full = 0xFFFFFFFFu;
@@ -2254,6 +2299,8 @@ __global__ void __launch_bounds__(kThreads) k_store_insert(StoreInsertArgs a) {
     uint32_t size = a.nframes[r];
     unsigned long long off = 0;
     int fresh = 0;
+    const uint32_t lr = a.last_row[a.slot_of_row[r]];
+    if (lr + 1u < a.min_last_p1) continue;  // warp-uniform: older than everything the cache will hold after this batch
     if (lane == 0) {
       Key128 k = a.tab[a.slot_of_row[r]].key;
       uint32_t idx = kNull;
@@ -2270,8 +2317,11 @@ __global__ void __launch_bounds__(kThreads) k_store_insert(StoreInsertArgs a) {
           p = (p + 1) & a.mask;
         }
       }
-      if (fresh) {
-        uint32_t e = atomicAdd(&a.ctl->entries, 1u);
+      if (idx == kNull) {  // the table itself is full
+        atomicOr(&a.ctr_w->store_overflow, 1u);
+      } else if (fresh || a.st[idx].size == kNull) {  // new key, or one that was claimed when there was no room for its frames
+        const bool was_claimed = !fresh;
+        uint32_t e = was_claimed ? 0u : atomicAdd(&a.ctl->entries, 1u);
         off = atomicAdd(&a.ctl->used_frames, (unsigned long long)size);
         if (e >= a.cap_entries || off + size > a.cap_frames) {
           a.st[idx].size = kNull;
@@ -2280,7 +2330,13 @@ __global__ void __launch_bounds__(kThreads) k_store_insert(StoreInsertArgs a) {
         } else {
           a.st[idx].off = off;
           a.st[idx].size = size;
+          a.stamp[idx] = a.epoch_hi | lr;
+          atomicAdd(&a.ctl->live, 1u);
+          fresh = 1;
         }
+      } else {  // known: refresh the access time; an evicted entry comes back with the frames it already has
+        if (a.stamp[idx] == 0) atomicAdd(&a.ctl->live, 1u);
+        a.stamp[idx] = a.epoch_hi | lr;
       }
     }
     fresh = __shfl_sync(full, fresh, 0);
@@ -2298,13 +2354,55 @@ __global__ void __launch_bounds__(kThreads) k_store_insert(StoreInsertArgs a) {
 // ---------------------------------------------------------------------------------------------
 // v1 stacktrace record (buildStacktraceRecord, parca_reporter.go:1545-1739): requested ids -> flattened
 // locations -> lines, every column of LocationsWriter (arrow.go:209-254) built by scans and gathers.
+// compaction: the live entries of one store into an empty one (one warp per old slot)
+struct StoreRebuildArgs {
+  const StoreSlot* old_st; const unsigned long long* old_stamp; const uint32_t* old_arena; uint32_t old_mask;
+  StoreSlot* st; unsigned long long* stamp; uint32_t* arena; uint32_t mask; StoreCtl* ctl;
+};
+__global__ void __launch_bounds__(kThreads) k_store_rebuild(StoreRebuildArgs a) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kThreads) >> 5;
+  const Key128 zero{0ull, 0ull};
+  for (uint32_t i = warp; i <= a.old_mask + 1; i += nwarps) {
+    const unsigned long long stp = a.old_stamp[i];
+    const uint32_t size = a.old_st[i].size;
+    if (stp == 0 || size == kNull) continue;  // warp-uniform
+    if (i <= a.old_mask && key_zero(a.old_st[i].key)) continue;
+    unsigned long long off = 0;
+    if (lane == 0) {
+      uint32_t idx;
+      if (i == a.old_mask + 1) { idx = a.mask + 1; a.st[idx].claimed = 1u; }
+      else {
+        const Key128 k = a.old_st[i].key;
+        uint32_t p = mix_slot(k) & a.mask;
+        for (;;) {  // the new table has room for every live entry
+          Key128 cur = cas128(&a.st[p].key, zero, k);
+          if (key_zero(cur)) break;
+          p = (p + 1) & a.mask;
+        }
+        idx = p;
+      }
+      atomicAdd(&a.ctl->entries, 1u);
+      atomicAdd(&a.ctl->live, 1u);
+      off = atomicAdd(&a.ctl->used_frames, (unsigned long long)size);
+      a.st[idx].off = off;
+      a.st[idx].size = size;
+      a.stamp[idx] = stp;
+    }
+    off = __shfl_sync(full, off, 0);
+    const unsigned long long src = a.old_st[i].off;
+    for (uint32_t j = lane; j < size; j += 32) a.arena[off + j] = a.old_arena[src + j];
+  }
+}
 __global__ void __launch_bounds__(kThreads) k_st_lookup(const uint8_t* ids, uint32_t n, const StoreSlot* st, uint32_t mask, uint32_t* q_slot,
-                                                        uint32_t* q_nloc) {
+                                                        uint32_t* q_nloc, unsigned long long* stamp, unsigned long long epoch_hi) {
   for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     ulonglong2 raw = *reinterpret_cast<const ulonglong2*>(ids + 16ull * i);  // libpf.TraceHashFromBytes: big-endian hi||lo
     Key128 k{bswap64(raw.x), bswap64(raw.y)};
     uint32_t sl = store_find(st, mask, k);
-    if (sl != kNull && st[sl].size == kNull) sl = kNull;
+    if (sl != kNull && (st[sl].size == kNull || stamp[sl] == 0)) sl = kNull;  // dropped for lack of room / evicted
+    if (sl != kNull) atomicMax(&stamp[sl], epoch_hi | i);                     // r.stacks.Get moves the entry to the front (:1555)
     q_slot[i] = sl;
     q_nloc[i] = sl == kNull ? 1u : st[sl].size;  // a missing stack still yields one placeholder location (:1556-1573)
   }

@@ -602,7 +602,7 @@ def assert_same_stacktraces(o, a, ids):
 def feed_both(oracle, gpu, w, o=None, a=None, **kw_agg):
     """One v1 interval through both sides; returns (o, a, this interval's unique ids in first-occurrence order)."""
     as_v1(w)
-    o = o or oracle.Oracle(w)
+    o = o or oracle.Oracle(w, stack_cache_entries=kw_agg.get("stack_cache_entries", 0))
     a = a or gpu.from_workload(w, **kw_agg)
     o.ingest(w.hdrs, w.frame_ids)
     want, st = o.flush()
@@ -665,23 +665,58 @@ def test_stacktrace_store_persists_across_intervals(oracle, gpu):
     a.close(); o.close()
 
 
-def test_stacktrace_store_overflow_starts_a_new_generation(oracle, gpu):
-    """Out of entries (or frame space): the store is cleared and refilled from the current batch, so it then behaves
-    like a reporter that has only seen that batch — older stacks come back as "missing stacktrace" rows, exactly what
-    the reference answers for an evicted LRU entry (:1556-1573)."""
+def test_stacktrace_store_is_an_lru(oracle, gpu):
+    """`stacks` is lru.SyncedLRU (parca_reporter.go:106): `Get` per sample and per requested id moves an entry to the front, `Add`
+    evicts the entry at the back. The store must answer every request like the oracle's LRU of the same capacity: evicted
+    stacks come back as "missing stacktrace" rows (:1556-1573), stacks refreshed by a later sample or by a request survive,
+    an evicted stack that is sampled again is known again, a batch with more distinct stacks than the cache keeps its last C."""
     big = synth.config2(n=12_000, u=10_000, p=8_192)                      # 64-frame stacks, ~3.6k distinct per 4.5k rows
     w1, w2 = big.head(4500), big.rows(np.arange(6000, 10_500))
-    for kw_agg in (dict(stack_cache_entries=4096), dict(stack_cache_entries=1 << 16, stack_cache_frames=4096 * 64)):
-        o, a, ids1 = feed_both(oracle, gpu, w1, max_samples=8000, max_frames=8000 * 64, **kw_agg)
-        assert 2048 < len(ids1) <= 4096
-        assert_same_stacktraces(o, a, ids1)
-        _, _, ids2 = feed_both(oracle, gpu, w2, o=o, a=a)
-        assert len(set(ids1) | set(ids2)) > 4096
-        o2 = oracle.Oracle(as_v1(w2))                                     # a reporter that only ever saw the second batch
-        o2.ingest(w2.hdrs, w2.frame_ids)
-        o2.flush()
-        assert_same_stacktraces(o2, a, ids2 + ids1[:50] + missing_ids(1))
-        a.close(); o.close(); o2.close()
+    o, a, ids1 = feed_both(oracle, gpu, w1, max_samples=8000, max_frames=8000 * 64, stack_cache_entries=4096)
+    assert 2048 < len(ids1) <= 4096
+    assert_same_stacktraces(o, a, ids1[:300])                             # these 300 are now the most recently used
+    _, _, ids2 = feed_both(oracle, gpu, w2, o=o, a=a)
+    assert len(set(ids1) | set(ids2)) > 4096                              # something had to go
+    assert_same_stacktraces(o, a, ids1 + ids2 + missing_ids(1))
+    a.close(); o.close()
+    # many small intervals against a tiny cache: evictions every interval, revivals, compactions of the slot table and the arena
+    w = synth.config2(n=9000, u=2500, p=4096)
+    o = a = None
+    seen = []
+    rng = np.random.Generator(np.random.PCG64(9))
+    for k in range(18):  # 2500 distinct stacks against 1536 usable slots: the table is compacted along the way
+        part = w.rows(np.sort(rng.choice(w.n, 900 if k == 7 else 220, replace=False)))  # interval 7 alone holds more stacks than the cache
+        o, a, ids = feed_both(oracle, gpu, part, o=o, a=a, max_samples=4000, max_frames=400_000, stack_cache_entries=300)
+        seen += [i for i in ids if i not in set(seen)]
+        probe = [seen[int(j)] for j in rng.choice(len(seen), min(len(seen), 120), replace=False)]
+        assert_same_stacktraces(o, a, probe + missing_ids(1) + probe[:5])  # the request itself refreshes what it finds
+    assert_same_stacktraces(o, a, seen)
+    a.close(); o.close()
+    # one interval with more distinct stacks than the cache holds: the last C by last occurrence stay
+    o, a, ids = feed_both(oracle, gpu, w1, max_samples=8000, max_frames=8000 * 64, stack_cache_entries=1000)
+    assert len(ids) > 1000
+    assert_same_stacktraces(o, a, ids)
+    _, _, ids_b = feed_both(oracle, gpu, w2.head(300), o=o, a=a)
+    assert_same_stacktraces(o, a, ids + ids_b)
+    a.close(); o.close()
+
+
+def test_stacktrace_store_out_of_frame_space_starts_over(oracle, gpu):
+    """The frame arena (pa_agg_config.stack_cache_frames) is this library's own limit. Out of it: evicted entries are compacted
+    away first; if the live ones alone do not fit, the store is cleared and refilled from the current batch, so it then
+    behaves like a reporter that has only seen that batch — older stacks come back as "missing stacktrace" rows."""
+    big = synth.config2(n=12_000, u=10_000, p=8_192)
+    w1, w2 = big.head(4500), big.rows(np.arange(6000, 10_500))
+    o, a, ids1 = feed_both(oracle, gpu, w1, max_samples=8000, max_frames=8000 * 64, stack_cache_entries=1 << 16, stack_cache_frames=4096 * 64)
+    assert 2048 < len(ids1) <= 4096
+    assert_same_stacktraces(o, a, ids1)
+    _, _, ids2 = feed_both(oracle, gpu, w2, o=o, a=a)
+    assert len(set(ids1) | set(ids2)) > 4096
+    o2 = oracle.Oracle(as_v1(w2))                                         # a reporter that only ever saw the second batch
+    o2.ingest(w2.hdrs, w2.frame_ids)
+    o2.flush()
+    assert_same_stacktraces(o2, a, ids2 + ids1[:50] + missing_ids(1))
+    a.close(); o.close(); o2.close()
 
 
 def test_stacktrace_custom_unknown_type_and_errors(oracle, gpu):
