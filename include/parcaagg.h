@@ -220,7 +220,8 @@ int pa_agg_stage(pa_agg* a);
 int pa_agg_process(pa_agg* a);
 int pa_agg_collect(pa_agg* a, pa_agg_result* out);
 /* device time (ms, CUDA events on the compute stream) of named kernel groups during the last
- * process(): names are "hash", "header", "rank", "locations", "labels", "columns", "total". */
+ * process(): names are "hash", "header", "rank", "locations", "labels", "dicts", "total". Two more names report counters of the
+ * v1 stack store since creation in *launches (ms = 0): "store_compactions", "store_evictions". */
 int pa_agg_last_kernel_ms(const pa_agg* a, const char* name, double* ms, uint32_t* launches);
 /* copies the per-row 128-bit stack ids (big-endian hi‖lo, 16 B per row) of the staged batch. */
 int pa_agg_debug_stack_ids(pa_agg* a, uint8_t* out, uint64_t n_rows);

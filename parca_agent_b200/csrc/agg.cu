@@ -1406,6 +1406,15 @@ static int process(pa_agg* a) {
   if (a->cfg.schema == PA_SCHEMA_V1) {
     if ((rc = v1_store_update(a))) return rc;
     if ((rc = check_batch_errors(a, a->h_ctr.err))) return rc;
+    {  // the store's share belongs to the pass: "total" runs to the end of it
+      CK(cudaEventRecord(a->tm[T_TOTAL].b, a->s_comp));
+      CK(cudaEventSynchronize(a->tm[T_TOTAL].b));
+      float tot = 0;
+      cudaEventElapsedTime(&tot, a->tm[T_TOTAL].a, a->tm[T_TOTAL].b);
+      a->tm[T_TOTAL].ms = tot;
+      a->launches += 2;  // k_last_rows, k_store_insert (select / kill / rebuild launches come on top when they run)
+      a->tm[T_TOTAL].launches = a->launches;
+    }
     a->last_unique = a->h_ctr.n_unique;
   }
   remember_sizes(a);
@@ -2317,6 +2326,12 @@ int pa_agg_last_kernel_ms(const pa_agg* a, const char* name, double* ms, uint32_
       if (launches) *launches = a->tm[t].launches;
       return PA_OK;
     }
+  // counters of the v1 stack store since creation (ms is 0): table compactions / eviction rounds
+  if (!strcmp(name, "store_compactions") || !strcmp(name, "store_evictions")) {
+    if (ms) *ms = 0;
+    if (launches) *launches = (uint32_t)(name[6] == 'c' ? a->store_compactions : a->store_evictions);
+    return PA_OK;
+  }
   return PA_EINVAL;
 }
 int pa_agg_debug_stack_ids(pa_agg* a, uint8_t* out, uint64_t n_rows) {

@@ -2253,7 +2253,10 @@ struct StoreInsertArgs {
 };
 // last occurrence of every stack of the batch (the LRU's access time of its entry)
 __global__ void __launch_bounds__(kThreads) k_last_rows(uint32_t n_rows, const uint32_t* slot_of_row, uint32_t* last_row) {
-  for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < n_rows; r += gridDim.x * kThreads) {
+  // from the last row down: the first visit of a stack is (nearly always) its last row, every earlier row then fails the plain
+  // comparison and issues no atomic
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_rows; i += gridDim.x * kThreads) {
+    const uint32_t r = n_rows - 1u - i;
     const uint32_t s = slot_of_row[r];
     if (s != kNull && last_row[s] < r) atomicMax(&last_row[s], r);
   }

@@ -691,6 +691,7 @@ def test_stacktrace_store_is_an_lru(oracle, gpu):
         probe = [seen[int(j)] for j in rng.choice(len(seen), min(len(seen), 120), replace=False)]
         assert_same_stacktraces(o, a, probe + missing_ids(1) + probe[:5])  # the request itself refreshes what it finds
     assert_same_stacktraces(o, a, seen)
+    assert a.kernel_ms("store_compactions")[1] >= 1 and a.kernel_ms("store_evictions")[1] >= 10
     a.close(); o.close()
     # one interval with more distinct stacks than the cache holds: the last C by last occurrence stay
     o, a, ids = feed_both(oracle, gpu, w1, max_samples=8000, max_frames=8000 * 64, stack_cache_entries=1000)
