@@ -1,5 +1,6 @@
 """One-off differential stress run on a GPU box (not collected by pytest): many random small batches through every mode —
-v2 and v1 sample records, the v1 stacktrace record with shuffled / unknown / repeated ids, multi-interval stores, random chunking.
+v2 and v1 sample records, the v1 stacktrace record with shuffled / unknown / repeated ids, multi-interval stores with tiny LRU
+capacities, random chunking (PA_EARLY_D2H_ALWAYS=1 sends every multi-chunk flush after the first through the early copy-out).
 
 usage: python tests/stress_gpu.py [--cases 300] [--seed 1]   (prints a one-line summary; exits non-zero on the first mismatch)
 """
@@ -25,8 +26,9 @@ def one_case(rng, i):
     w.schema = abi.PA_SCHEMA_V1 if v1 else abi.PA_SCHEMA_V2
     chunk = int(rng.choice([0, 61, 97, 512, 4096]))
     cuts = sorted(set([0, n] + [int(x) for x in rng.integers(0, n + 1, int(rng.integers(0, 3)))]))
-    o = oracle_py.Oracle(w)
-    a = lib.from_workload(w, chunk_samples=chunk)
+    cap = int(rng.choice([0, 0, 5, 12, 25, 40])) if v1 else 0  # small `stacks` LRU capacities: evictions, revivals, over-full intervals
+    o = oracle_py.Oracle(w, stack_cache_entries=cap)
+    a = lib.from_workload(w, chunk_samples=chunk, stack_cache_entries=cap)
     seen = []
     for lo, hi in zip(cuts[:-1], cuts[1:]):
         part = w.rows(np.arange(lo, hi))
@@ -51,7 +53,7 @@ def one_case(rng, i):
             ws, nloc = o.stacktraces(blob)
             rs = a.stacktraces(blob)
             if rs.ipc_bytes() != ws or rs.n_locations != nloc:
-                return "stacktrace record differs (case %d, %d ids)" % (i, len(req))
+                return "stacktrace record differs (case %d, %d ids, cache capacity %d)" % (i, len(req), cap)
     a.close()
     o.close()
     return None
