@@ -2322,7 +2322,10 @@ __global__ void __launch_bounds__(kThreads) k_store_insert(StoreInsertArgs a) {
       }
       if (idx == kNull) {  // the table itself is full
         atomicOr(&a.ctr_w->store_overflow, 1u);
-      } else if (fresh || a.st[idx].size == kNull) {  // new key, or one that was claimed when there was no room for its frames
+      } else if (fresh || a.st[idx].size == kNull || a.stamp[idx] == 0) {
+        // new key; or one that was claimed when there was no room for its frames; or an evicted one, which the reference would Add
+        // again with the frames of THIS interval's first sample carrying the id (they differ from the old ones only when two
+        // stacks share a provided id) — its old frames are garbage until the next compaction
         const bool was_claimed = !fresh;
         uint32_t e = was_claimed ? 0u : atomicAdd(&a.ctl->entries, 1u);
         off = atomicAdd(&a.ctl->used_frames, (unsigned long long)size);
@@ -2337,8 +2340,7 @@ __global__ void __launch_bounds__(kThreads) k_store_insert(StoreInsertArgs a) {
           atomicAdd(&a.ctl->live, 1u);
           fresh = 1;
         }
-      } else {  // known: refresh the access time; an evicted entry comes back with the frames it already has
-        if (a.stamp[idx] == 0) atomicAdd(&a.ctl->live, 1u);
+      } else {  // known and alive: refresh the access time
         a.stamp[idx] = a.epoch_hi | lr;
       }
     }

@@ -26,7 +26,10 @@ def one_case(rng, i):
     w.schema = abi.PA_SCHEMA_V1 if v1 else abi.PA_SCHEMA_V2
     chunk = int(rng.choice([0, 61, 97, 512, 4096]))
     cuts = sorted(set([0, n] + [int(x) for x in rng.integers(0, n + 1, int(rng.integers(0, 3)))]))
-    cap = int(rng.choice([0, 0, 5, 12, 25, 40])) if v1 else 0  # small `stacks` LRU capacities: evictions, revivals, over-full intervals
+    # small `stacks` LRU capacities: evictions, revivals, over-full intervals. Not with provided ids: edge workloads make different
+    # stacks share an id on purpose, and which of them an entry holds after an eviction inside an interval is the one documented
+    # deviation of the store
+    cap = int(rng.choice([0, 0, 5, 12, 25, 40])) if v1 and mode == abi.PA_HASH_XXH64X2 else 0
     o = oracle_py.Oracle(w, stack_cache_entries=cap)
     a = lib.from_workload(w, chunk_samples=chunk, stack_cache_entries=cap)
     seen = []
@@ -53,7 +56,7 @@ def one_case(rng, i):
             ws, nloc = o.stacktraces(blob)
             rs = a.stacktraces(blob)
             if rs.ipc_bytes() != ws or rs.n_locations != nloc:
-                return "stacktrace record differs (case %d, %d ids, cache capacity %d)" % (i, len(req), cap)
+                return "stacktrace record differs (case %d, %d ids, cache capacity %d, hash mode %d, rows %d..%d of %d, chunk %d)" % (i, len(req), cap, mode, lo, hi, n, chunk)
     a.close()
     o.close()
     return None
