@@ -628,6 +628,7 @@ static int stage_async(pa_agg* a) {
   uint64_t nchunks = (a->N + C - 1) / C;
   while (a->chunk_ev.size() < nchunks) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); a->chunk_ev.push_back(e); }
   CK(cudaEventRecord(a->ev_h2d0, a->s_copy));
+  if (a->early.issued) CK(cudaStreamSynchronize(a->s_d2h));  // a batch that was discarded or failed after its early copies were started
   a->early = pa_agg::Early{};
   // headers first when the frame ids take several chunks: everything that depends only on the headers (k_header, the label chain,
   // the early copy-out) then overlaps the upload of the ids

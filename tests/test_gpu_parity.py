@@ -145,6 +145,15 @@ def test_early_copy_out_of_trailing_columns(oracle, gpu, monkeypatch):
                 assert got == want, "interval of %d rows differs" % n
             assert res.n_rows == st["rows"]
         a.close()
+    a = gpu.from_workload(base, chunk_samples=4096)   # a batch dropped after its early copies were started must not leak into the next one
+    w = base.head(30_000)
+    gpu.load(a, w)
+    a.flush()
+    gpu.load(a, base.head(25_000))
+    a.stage(); a.process(); a.discard()
+    gpu.load(a, w)
+    assert a.flush().ipc_bytes() == oracle.run(w)[0]
+    a.close()
     a = gpu.from_workload(edge, chunk_samples=1000)   # every sample kind, alternating: hundreds of kind runs
     want, _ = oracle.run(edge)
     for _ in range(3):
