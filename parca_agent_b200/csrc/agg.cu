@@ -389,7 +389,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   }
   if (const char* hv = getenv("PA_HASH_VARIANT")) {
     static const struct { const char* name; int id; } kVariants[] = {{"direct", 0}, {"staged", 1}, {"wide", 2}, {"bulk", 3}, {"bulk6x2", 4}, {"widepf", 5},
-                                                                   {"tma", 6}, {"tma12x4", 7}, {"tma24x2", 8}, {"tma12x2r", 9}, {"tma13x2r", 10}, {"tma8x3r", 11}, {"tmag13x2", 12}, {"tmag9x3", 13}, {"tmag6x4", 14}};
+                                                                   {"tma", 6}, {"tma12x4", 7}, {"tma24x2", 8}, {"tma12x2r", 9}, {"tma13x2r", 10}, {"tma8x3r", 11}, {"tmag13x2", 12}, {"tmag9x3", 13}, {"tmag6x4", 14}, {"widepf3", 15}};
     a->hash_variant = 2;
     for (auto& v : kVariants) if (strcmp(hv, v.name) == 0) a->hash_variant = v.id;
   }
@@ -1140,6 +1140,7 @@ static int pass_front(pa_agg* a) {
     else if (a->hash_variant == 12 && a->idb == 8) k_hash_insert_tmag<13, 2><<<tma_grid(13), 13 * 32, sizeof(TmagSmem<13, 2>), s>>>(ha);
     else if (a->hash_variant == 13 && a->idb == 8) k_hash_insert_tmag<9, 3><<<tma_grid(9), 9 * 32, sizeof(TmagSmem<9, 3>), s>>>(ha);
     else if (a->hash_variant == 14 && a->idb == 8) k_hash_insert_tmag<6, 4><<<tma_grid(6), 6 * 32, sizeof(TmagSmem<6, 4>), s>>>(ha);
+    else if (a->hash_variant == 15 && a->idb == 8) k_hash_insert_widepf3<<<(int)std::max<uint64_t>(1, std::min<uint64_t>((rows + kThreads - 1) / kThreads, (uint64_t)a->sms * 3)), kThreads, 0, s>>>(ha);
     else if (a->hash_variant == 5 && a->idb == 4) k_hash_insert_widepf32<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     else if (a->hash_variant == 5) k_hash_insert_widepf<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     else if (a->idb == 4) k_hash_insert_wide32<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);

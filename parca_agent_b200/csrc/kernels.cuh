@@ -686,6 +686,7 @@ __device__ __forceinline__ void hash_insert_widepf(const HashArgs& a, const IdT*
   }
 }
 __global__ void __launch_bounds__(kThreads, 4) k_hash_insert_widepf(HashArgs a) { hash_insert_widepf<unsigned long long>(a, a.frames); }
+__global__ void __launch_bounds__(kThreads, 3) k_hash_insert_widepf3(HashArgs a) { hash_insert_widepf<unsigned long long>(a, a.frames); }  // 85 registers: no spills, 24 warps per SM
 __global__ void __launch_bounds__(kThreads, 4) k_hash_insert_widepf32(HashArgs a) { hash_insert_widepf<uint32_t>(a, a.frames32); }
 
 // Variant D ("bulk"): the north-star mechanism. Every lane issues ONE cp.async.bulk (TMA 1-D bulk copy, SASS UBLKCP) that
