@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <functional>
 #include <chrono>
 #include <cstdlib>
 #include <condition_variable>
@@ -142,6 +143,7 @@ struct pa_agg {
     bool issued = false;      // early copies are in flight / done
     uint8_t* out_end = nullptr;
     uint64_t dist_ts = 0, dist_value = 0, dist_uuid = 0;
+    uint64_t dist_stoff = 0, dist_stsize = 0, dist_stream = 0;  // second wave (collect): list offsets / sizes and the location-index stream sit right before stacktrace_id
   } early;
   bool early_enabled = true, early_force = false;
   bool use_pdl = false;  // PA_PDL=1: the small dependent kernels of the rank / location / label chains are launched with programmatic stream serialization
@@ -1541,7 +1543,7 @@ static void append_tail_v2(pa_agg* a, const MergeView* mv, uint64_t N, const std
 }
 
 // the record's columns as Nodes (device buffers are referenced, host-built ones are kept in a->hostbufs)
-static int collect_nodes(pa_agg* a, const MergeView* mv, std::vector<Node>& cols) {
+static int collect_nodes(pa_agg* a, const MergeView* mv, std::vector<Node>& cols, const std::function<int()>& after_small_copies = nullptr) {
   const uint64_t N = mv ? mv->NT : a->N;
   const Counters& c = a->h_ctr;
   auto rowbuf = [&](uint32_t kind, const void* p, uint64_t elem) { return mv ? sliced(kind, 0, N * elem) : BufRef::dev(p, N * elem); };
@@ -1575,6 +1577,7 @@ static int collect_nodes(pa_agg* a, const MergeView* mv, std::vector<Node>& cols
   if (v1 && ((rc = d2h_vec(a, kind_order, a->v1_kind_order, 64)) || (rc = d2h_vec(a, n_kind_dict, a->v1_n_kind_dict, 8)))) return rc;
   CK(cudaStreamSynchronize(a->s_comp));
   tp1 = now_ms();
+  if (after_small_copies && (rc = after_small_copies())) return rc;  // (large copies that may run under the host work below)
 
   std::lock_guard<std::mutex> g(a->reg_mu);
   const StringPool& sp = a->sp;
@@ -1857,9 +1860,30 @@ static int collect(pa_agg* a, pa_agg_result* res) {
   double t0 = now_ms();
   const Counters& c = a->h_ctr;
   const bool v1 = a->cfg.schema == PA_SCHEMA_V1;
+  auto second_wave = [&]() -> int {
+    if (a->early.issued && a->early.out_end == a->out + (a->out_cap & ~63ull)) {
+      // second wave of the early copy-out: with the pass finished the length of the location-index stream is known, and with it the
+      // positions (from the end) of the three buffers in front of stacktrace_id. They leave on the copy-out stream while the host
+      // assembles the dictionaries (collect_nodes); the plan below confirms the positions like those of the first wave.
+      pa_agg::Early& e = a->early;
+      const uint64_t nidx = c.n_indices64, pad = 7;
+      e.dist_stream = e.dist_uuid + ((nidx * 4 + pad) & ~pad);
+      e.dist_stsize = e.dist_stream + ((N * 4 + pad) & ~pad);
+      e.dist_stoff = e.dist_stsize + ((N * 4 + pad) & ~pad);
+      if (e.dist_stoff <= (a->out_cap & ~63ull)) {
+        CK(cudaMemcpyAsync(e.out_end - e.dist_stoff, a->d_stoff.p, N * 4, cudaMemcpyDeviceToHost, a->s_d2h));
+        CK(cudaMemcpyAsync(e.out_end - e.dist_stsize, a->d_stsize.p, N * 4, cudaMemcpyDeviceToHost, a->s_d2h));
+        if (nidx) CK(cudaMemcpyAsync(e.out_end - e.dist_stream, a->d_ustream.p, nidx * 4, cudaMemcpyDeviceToHost, a->s_d2h));
+        CK(cudaEventRecord(a->ev_early_done, a->s_d2h));
+      } else {
+        e.dist_stream = e.dist_stsize = e.dist_stoff = 0;
+      }
+    }
+    return PA_OK;
+  };
   std::vector<Node> cols;
   {
-    int rcn = collect_nodes(a, nullptr, cols);
+    int rcn = collect_nodes(a, nullptr, cols, second_wave);
     if (rcn) return rcn;
   }
   const double t_nodes = now_ms();
@@ -1885,11 +1909,22 @@ static int collect(pa_agg* a, pa_agg_result* res) {
   uint8_t* const base = anchored ? e.out_end - plan.total : a->out;
   cudaEvent_t d0 = a->ev_d2h0, d1 = a->ev_d2h1;
   CK(cudaEventRecord(d0, a->s_comp));
-  for (auto& p : plan.placements) {
-    if (p.src.kind != BufRef::DEVICE || !p.src.len) continue;
+  auto placed_early = [&](const Placement& p) {
     const uint64_t dist = plan.total - p.at;
-    if (anchored && ((p.src.ptr == a->d_ts.p && dist == e.dist_ts) || (p.src.ptr == a->d_value.p && dist == e.dist_value) || (p.src.ptr == a->d_uuid.p && dist == e.dist_uuid)))
-      continue;  // already there
+    return anchored && ((p.src.ptr == a->d_ts.p && dist == e.dist_ts) || (p.src.ptr == a->d_value.p && dist == e.dist_value) || (p.src.ptr == a->d_uuid.p && dist == e.dist_uuid) ||
+                        (p.src.ptr == a->d_stoff.p && dist == e.dist_stoff) || (p.src.ptr == a->d_stsize.p && dist == e.dist_stsize) ||
+                        (p.src.ptr == a->d_ustream.p && dist == e.dist_stream));
+  };
+  if (e.issued) {
+    // an early copy that is NOT where the plan puts its buffer may still be landing somewhere in the output: let it finish before
+    // anything else is written there (the ordinary copies below then overwrite whatever it hit)
+    int hits = 0;
+    for (auto& p : plan.placements) if (p.src.kind == BufRef::DEVICE && p.src.len && placed_early(p)) hits++;
+    const int expected = 3 + (e.dist_stoff ? 2 : 0) + (e.dist_stream && c.n_indices64 ? 1 : 0);
+    if (hits != expected) CK(cudaStreamSynchronize(a->s_d2h));
+  }
+  for (auto& p : plan.placements) {
+    if (p.src.kind != BufRef::DEVICE || !p.src.len || placed_early(p)) continue;
     CK(cudaMemcpyAsync(base + p.at, p.src.ptr, p.src.len, cudaMemcpyDeviceToHost, a->s_comp));
   }
   CK(cudaEventRecord(d1, a->s_comp));
