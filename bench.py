@@ -163,7 +163,7 @@ def run_reference(args, rank, world):
     for _ in range(args.warmup):
         time_cpu_port(w, min(w.n, 100_000))
     times, st, digest = [], None, None
-    budget_s = float(os.environ.get("PA_REF_BUDGET_S", "170"))  # a step is ~15 s of CPU: K of them must still end "within a few minutes"
+    budget_s = float(os.environ.get("PA_REF_BUDGET_S", "600"))  # a step is ~15 s of CPU (the driver asks for 20: ~5 min); a much slower host stops early and says so
     for i in range(args.steps):
         if times and float(np.sum(times)) + float(np.mean(times)) > budget_s:
             break
