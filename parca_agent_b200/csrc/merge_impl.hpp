@@ -261,22 +261,46 @@ static int shm_alltoallv(pa_merge* g, const void* send, const std::vector<uint64
   for (uint32_t r = 0; r < W; r++) if (r != me) g->nvlink_bytes += sc[r];
   return PA_OK;
 }
+// all-reduce(min) as reduce-scatter + all-gather through the mailboxes: every rank reduces ITS slice of the round (1/W of the
+// elements, pulled from the W-1 other mailboxes), publishes the reduced slice, and pulls the other reduced slices — 2(W-1)/W of the
+// buffer per rank over PCIe instead of (W-1) times the buffer
 static int shm_allreduce_min(pa_merge* g, uint32_t* buf, size_t count) {
   const uint32_t W = g->world, me = g->ranks[0];
   const uint64_t M = shm_hdr(g)->mailbox_bytes & ~(uint64_t)3;
   cudaStream_t s = mstream(g, 0);
   const uint64_t bytes = (uint64_t)count * 4;
-  MCK(g->shm_scratch.ensure(std::min<uint64_t>(M, bytes)));
+  if (W == 1) return PA_OK;
   for (uint64_t off = 0; off < bytes; off += M) {
-    const uint64_t n = std::min<uint64_t>(M, bytes - off);
-    MCK(cudaMemcpyAsync(shm_box(g, me), (const uint8_t*)buf + off, n, cudaMemcpyDeviceToHost, s));
+    const uint64_t n = std::min<uint64_t>(M, bytes - off), ne = n / 4;
+    const uint64_t per = (ne + W - 1) / W;
+    auto slice = [&](uint32_t r, uint64_t* e0, uint64_t* e1) { *e0 = std::min<uint64_t>((uint64_t)r * per, ne); *e1 = std::min<uint64_t>(*e0 + per, ne); };
+    uint32_t* round = (uint32_t*)((uint8_t*)buf + off);
+    uint64_t m0, m1;
+    slice(me, &m0, &m1);
+    MCK(g->shm_scratch.ensure(std::max<uint64_t>((m1 - m0) * 4, 256)));
+    // phase 1: everybody's round into its own mailbox; each rank reduces its slice
+    MCK(cudaMemcpyAsync(shm_box(g, me), round, n, cudaMemcpyDeviceToHost, s));
     MCK(cudaStreamSynchronize(s));
     SBAR();
-    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g->members[0]->G, (n / 4 + 2047) / 2048));
+    if (m1 > m0) {
+      const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g->members[0]->G, (m1 - m0 + 2047) / 2048));
+      for (uint32_t r = 0; r < W; r++) {
+        if (r == me) continue;
+        MCK(cudaMemcpyAsync(g->shm_scratch.p, shm_box(g, r) + m0 * 4, (m1 - m0) * 4, cudaMemcpyHostToDevice, s));
+        k_min_u32<<<grid, kThreads, 0, s>>>(round + m0, g->shm_scratch.as<uint32_t>(), m1 - m0);
+      }
+    }
+    MCK(cudaStreamSynchronize(s));
+    SBAR();  // every mailbox has been read: it may be overwritten
+    // phase 2: publish the reduced slice, fetch the others
+    if (m1 > m0) MCK(cudaMemcpyAsync(shm_box(g, me) + m0 * 4, round + m0, (m1 - m0) * 4, cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    SBAR();
     for (uint32_t r = 0; r < W; r++) {
       if (r == me) continue;
-      MCK(cudaMemcpyAsync(g->shm_scratch.p, shm_box(g, r), n, cudaMemcpyHostToDevice, s));
-      k_min_u32<<<grid, kThreads, 0, s>>>((uint32_t*)((uint8_t*)buf + off), g->shm_scratch.as<uint32_t>(), n / 4);
+      uint64_t r0, r1;
+      slice(r, &r0, &r1);
+      if (r1 > r0) MCK(cudaMemcpyAsync(round + r0, shm_box(g, r) + r0 * 4, (r1 - r0) * 4, cudaMemcpyHostToDevice, s));
     }
     MCK(cudaStreamSynchronize(s));
     SBAR();
