@@ -209,7 +209,12 @@ int ParcaReporter::writeSampleV2(const Trace* trace, const TraceEventMeta* meta,
   h.value = value;
   h.pid = meta->PID;
   h.tid = meta->TID;
-  h.comm_sid = sid(meta->Comm);
+  if (!last_comm_valid_ || meta->Comm != last_comm_) {
+    last_comm_sid_ = sid(meta->Comm);
+    last_comm_ = meta->Comm;
+    last_comm_valid_ = last_comm_sid_ != PA_NO_STRING;
+  }
+  h.comm_sid = last_comm_sid_;
   h.labelset_id = labelset;
   h.cpu = (uint32_t)meta->CPU;
   h.nframes = (uint16_t)nids;
@@ -242,8 +247,8 @@ int ParcaReporter::ReportTraceEvent(const Trace* trace, const TraceEventMeta* me
   const size_t nfr = trace->Frames.size();
   const bool cacheable = (trace->Hash.hi | trace->Hash.lo) != 0;  // oomprof traces share the zero hash with different frames
   if (cacheable) {
-    auto tc = trace_cache_.find(trace->Hash);
-    if (tc != trace_cache_.end() && tc->second.second == nfr) idp = trace_ids_.data() + tc->second.first;
+    const TraceSlot* tc = trace_cache_.find(trace->Hash);
+    if (tc && tc->n == nfr) idp = trace_ids_.data() + tc->off;
   }
   if (!idp) {
     scratch_ids_.clear();
@@ -251,7 +256,7 @@ int ParcaReporter::ReportTraceEvent(const Trace* trace, const TraceEventMeta* me
     for (auto& f : trace->Frames) scratch_ids_.push_back(frameId(f));
     if (cacheable) {
       if (trace_cache_.size() >= kTraceCacheEntries) { trace_cache_.clear(); trace_ids_.clear(); }
-      trace_cache_[trace->Hash] = std::make_pair((uint64_t)trace_ids_.size(), (uint32_t)nfr);
+      trace_cache_.put(trace->Hash, (uint64_t)trace_ids_.size(), (uint32_t)nfr);
       trace_ids_.insert(trace_ids_.end(), scratch_ids_.begin(), scratch_ids_.end());
     }
     idp = scratch_ids_.data();

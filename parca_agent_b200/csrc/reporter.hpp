@@ -145,6 +145,9 @@ class ParcaReporter {
   Config cfg_;
   std::mutex mu_;  // sampleWriterV2Mu (:335): row order == lock acquisition order
   std::unordered_map<std::string, uint32_t> strings_;
+  std::string last_comm_;            // consecutive samples mostly come from the same few threads: skip the string hash on a repeat
+  uint32_t last_comm_sid_ = 0;
+  bool last_comm_valid_ = false;
   std::unordered_map<std::string, uint64_t> frames_;          // serialised Frame value (+exec state) -> frame id
   std::unordered_map<uint64_t, uint64_t> frames_by_handle_;   // Frame::Handle -> frame id (the fast path)
   // trace.Hash -> the frame ids of that trace (the role of the reference's `stacks` LRU, :224-227, turned into an interning
@@ -152,7 +155,40 @@ class ParcaReporter {
   // cleared when full and whenever an executable becomes known (frames resolved as UNKNOWN must be looked at again).
   struct TraceHashHasher { size_t operator()(const TraceHash& h) const { return (size_t)(h.hi * 0x9E3779B97F4A7C15ull ^ h.lo); } };
   struct TraceHashEq { bool operator()(const TraceHash& a, const TraceHash& b) const { return a.hi == b.hi && a.lo == b.lo; } };
-  std::unordered_map<TraceHash, std::pair<uint64_t, uint32_t>, TraceHashHasher, TraceHashEq> trace_cache_;  // -> (offset, count) in trace_ids_
+  // trace.Hash -> (offset, count) in trace_ids_: open addressing in one flat array (a hit is one cache line, where a node-based map
+  // takes a bucket and a node), cleared as a whole when it is three quarters full
+  struct TraceSlot { TraceHash key; uint64_t off; uint32_t n; uint32_t used; };
+  struct TraceCache {
+    std::vector<TraceSlot> slots;
+    size_t count = 0;
+    const TraceSlot* find(const TraceHash& h) const {
+      if (slots.empty()) return nullptr;
+      const size_t mask = slots.size() - 1;
+      for (size_t i = (size_t)(h.hi * 0x9E3779B97F4A7C15ull ^ h.lo) & mask;; i = (i + 1) & mask) {
+        const TraceSlot& s = slots[i];
+        if (!s.used) return nullptr;
+        if (s.key.hi == h.hi && s.key.lo == h.lo) return &s;
+      }
+    }
+    void put(const TraceHash& h, uint64_t off, uint32_t n) {
+      if (slots.empty()) slots.resize(1u << 16);
+      if ((count + 1) * 4 > slots.size() * 3) {  // grow (rehash) up to kTraceCacheEntries slots; beyond that the caller clears
+        std::vector<TraceSlot> old;
+        old.swap(slots);
+        slots.resize(old.size() * 2);
+        count = 0;
+        for (auto& s : old) if (s.used) put(s.key, s.off, s.n);
+      }
+      const size_t mask = slots.size() - 1;
+      for (size_t i = (size_t)(h.hi * 0x9E3779B97F4A7C15ull ^ h.lo) & mask;; i = (i + 1) & mask) {
+        TraceSlot& s = slots[i];
+        if (!s.used) { s = TraceSlot{h, off, n, 1u}; count++; return; }
+        if (s.key.hi == h.hi && s.key.lo == h.lo) { s.off = off; s.n = n; return; }
+      }
+    }
+    void clear() { slots.clear(); count = 0; }
+    size_t size() const { return count; }
+  } trace_cache_;
   std::vector<uint64_t> trace_ids_;
   std::vector<uint64_t> scratch_ids_;
   static constexpr size_t kTraceCacheEntries = 1u << 20;
