@@ -665,6 +665,30 @@ def main():
             host_shim["e2e_submit"] = {"rows": nsub, "value": nsub / (t3 - t1), "unit": "samples/s", "submit_s": t2 - t1, "flush_s": t3 - t2,
                                        "note": "pa_agg_submit from pageable memory (64k-row batches, one thread: memcpy into the pinned ring) + pa_agg_flush"}
             assert rr.n_rows == nsub
+            # several producers: the reference serialises them on one mutex (parca_reporter.go:335); here a producer holds the ring lock
+            # only to reserve its rows and copies outside it
+            T = 4
+            per = nsub // T
+
+            def producer(t):
+                lo, hi = t * per, (t + 1) * per
+                for i in range(lo, hi, B):
+                    j = min(hi, i + B)
+                    a.submit(sub.hdrs[i:j], fr[i * F:j * F])
+
+            ths = [threading.Thread(target=producer, args=(t,)) for t in range(T)]
+            t4 = time.perf_counter()
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+            t5 = time.perf_counter()
+            rr = a.flush()
+            torch.cuda.synchronize()
+            t6 = time.perf_counter()
+            assert rr.n_rows == per * T
+            host_shim["e2e_submit_4_threads"] = {"rows": per * T, "value": per * T / (t6 - t4), "unit": "samples/s", "submit_s": t5 - t4, "flush_s": t6 - t5,
+                                                 "submit_samples_per_s": per * T / (t5 - t4), "note": "4 producer threads, 64k-row pa_agg_submit calls each"}
             exe = os.path.join(ROOT, "tests", "cpp", "_build", "bench_reporter")
             if os.path.exists(exe) and local == 0:
                 for key in ("handle", "value"):

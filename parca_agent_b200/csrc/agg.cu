@@ -587,11 +587,11 @@ int pa_agg_submit(pa_agg* a, const pa_sample_hdr* hdrs, const uint64_t* frames, 
   pa_sample_hdr* dh; uint64_t* df; uint64_t base;
   int rc = pa_agg_acquire(a, n_rows, nf, &dh, &df, &base);
   if (rc) return rc;
+  if (n_rows) memcpy(dh, hdrs, n_rows * sizeof(pa_sample_hdr));
+  if (nf) memcpy(df, frames, (size_t)nf * a->idb);  // the caller's ids are concatenated in row order, exactly as the ring holds them
   uint64_t off = 0;
   for (uint64_t i = 0; i < n_rows; i++) {
-    dh[i] = hdrs[i];
     dh[i].frame_off = base + off;
-    if (hdrs[i].nframes) memcpy((uint8_t*)df + off * a->idb, (const uint8_t*)frames + off * a->idb, (size_t)hdrs[i].nframes * a->idb);
     off += hdrs[i].nframes;
   }
   return pa_agg_commit(a, n_rows);
