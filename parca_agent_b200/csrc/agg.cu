@@ -133,6 +133,8 @@ struct pa_agg {
   std::string err;
   int device = 0, sms = 148, G = 592;
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr, s_d2h = nullptr;
+  cudaStream_t s_copy2 = nullptr;  // PA_COPY_STREAMS=2 (experiment): odd chunks of the id upload go through a second copy stream
+  cudaEvent_t ev_copy2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // Early copy-out during a flush (XXH64 mode, v2, more than one chunk): all headers are uploaded first, k_header and the label
   // chain run while the frame ids are still uploading, and stacktrace_id / value / timestamp leave for the host on s_d2h as soon
@@ -409,6 +411,9 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   if (cudaFuncSetAttribute(k_hash_insert_tmag<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmagSmem<6, 4>)) != cudaSuccess) return bail(PA_EIO);
   if (cudaFuncSetAttribute(k_hash_insert_bulk<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BulkSmem<6, 2>)) != cudaSuccess) return bail(PA_EIO);
   if (cudaStreamCreateWithFlags(&a->s_copy, cudaStreamNonBlocking) != cudaSuccess) return bail(PA_EIO);
+  if (const char* cs = getenv("PA_COPY_STREAMS")) {
+    if (atoi(cs) >= 2 && (cudaStreamCreateWithFlags(&a->s_copy2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&a->ev_copy2, cudaEventDisableTiming) != cudaSuccess)) return bail(PA_EIO);
+  }
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
   // the compute stream carries the chain of short dependent launches (stack rank, dictionaries): its blocks are scheduled
@@ -514,6 +519,8 @@ void pa_agg_destroy(pa_agg* a) {
   for (int t = 0; t < T_COUNT; t++) { if (a->tm[t].a) cudaEventDestroy(a->tm[t].a); if (a->tm[t].b) cudaEventDestroy(a->tm[t].b); }
   if (a->ev_fork) cudaEventDestroy(a->ev_fork);
   if (a->ev_join) cudaEventDestroy(a->ev_join);
+  if (a->s_copy2) { cudaStreamSynchronize(a->s_copy2); cudaStreamDestroy(a->s_copy2); }
+  if (a->ev_copy2) cudaEventDestroy(a->ev_copy2);
   if (a->s_copy) cudaStreamDestroy(a->s_copy);
   if (a->s_comp) cudaStreamDestroy(a->s_comp);
   if (a->s_aux) cudaStreamDestroy(a->s_aux);
@@ -651,12 +658,14 @@ static int stage_async(pa_agg* a) {
     // frames are only needed for each stack's FIRST occurrence, so nothing is uploaded here and k_gather_unique
     // reads those few stacks from the mapped pinned ring over PCIe (U*F*8 bytes instead of N*F*8).
     if (fend > fdone && a->cfg.hash_mode == PA_HASH_XXH64X2)
-      CK(cudaMemcpyAsync(a->d_frames.as<uint8_t>() + fdone * a->idb, (const uint8_t*)r.frames + fdone * a->idb, (fend - fdone) * a->idb, cudaMemcpyHostToDevice, a->s_copy));
+      CK(cudaMemcpyAsync(a->d_frames.as<uint8_t>() + fdone * a->idb, (const uint8_t*)r.frames + fdone * a->idb, (fend - fdone) * a->idb, cudaMemcpyHostToDevice,
+                         (a->s_copy2 && a->early.hdr_first && (k & 1)) ? a->s_copy2 : a->s_copy));
     fdone = fend;
-    CK(cudaEventRecord(a->chunk_ev[k], a->s_copy));
+    CK(cudaEventRecord(a->chunk_ev[k], (a->s_copy2 && a->early.hdr_first && (k & 1)) ? a->s_copy2 : a->s_copy));
     a->chunk_rows.emplace_back(r0, r1);
     a->chunk_frames_end.push_back(fend);
   }
+  if (a->s_copy2) { CK(cudaEventRecord(a->ev_copy2, a->s_copy2)); CK(cudaStreamWaitEvent(a->s_copy, a->ev_copy2, 0)); }  // s_copy stands for both from here on
   CK(cudaEventRecord(a->ev_h2d1, a->s_copy));
   return PA_OK;
 }
