@@ -393,7 +393,7 @@ int pa_agg_create(const pa_agg_config* cfg, pa_agg** out) {
   }
   if (const char* hv = getenv("PA_HASH_VARIANT")) {
     static const struct { const char* name; int id; } kVariants[] = {{"direct", 0}, {"staged", 1}, {"wide", 2}, {"bulk", 3}, {"bulk6x2", 4}, {"widepf", 5},
-                                                                   {"tma", 6}, {"tma12x4", 7}, {"tma24x2", 8}, {"tma12x2r", 9}, {"tma13x2r", 10}, {"tma8x3r", 11}, {"tmag13x2", 12}, {"tmag9x3", 13}, {"tmag6x4", 14}, {"widepf3", 15}};
+                                                                   {"tma", 6}, {"tma12x4", 7}, {"tma24x2", 8}, {"tma12x2r", 9}, {"tma13x2r", 10}, {"tma8x3r", 11}, {"tmag13x2", 12}, {"tmag9x3", 13}, {"tmag6x4", 14}, {"widepf3", 15}, {"widenp", 16}};
     a->hash_variant = 2;
     for (auto& v : kVariants) if (strcmp(hv, v.name) == 0) a->hash_variant = v.id;
   }
@@ -1158,7 +1158,8 @@ static int pass_front(pa_agg* a) {
     else if (a->hash_variant == 3) k_hash_insert_bulk<4, 3><<<(int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 127) / 128, (uint64_t)a->sms)), 128, sizeof(BulkSmem<4, 3>), s>>>(ha);
     else if (a->hash_variant == 4) k_hash_insert_bulk<6, 2><<<(int)std::max<uint64_t>(1, std::min<uint64_t>((rows + 191) / 192, (uint64_t)a->sms)), 192, sizeof(BulkSmem<6, 2>), s>>>(ha);
     else if (a->hash_variant == 1) k_hash_insert_staged<<<std::max(blocks, 1), kThreads, kHashStagedSmem, s>>>(ha);
-    else if (a->hash_variant == 2) k_hash_insert_wide<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
+    else if (a->hash_variant == 16 && a->idb == 8) k_hash_insert_wide_np<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
+    else if (a->hash_variant == 2 || a->hash_variant == 16) k_hash_insert_wide<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     else k_hash_insert<<<std::max(blocks, 1), kThreads, 0, s>>>(ha);
     a->tm[T_HASH].launches++;
   };

@@ -277,7 +277,7 @@ def test_bad_ids_are_reported(gpu):
     a.close()
 
 
-@pytest.mark.parametrize("variant", ["direct", "staged", "wide", "widepf", "widepf3", "bulk", "bulk6x2", "tma", "tma12x4", "tma24x2", "tma12x2r", "tma13x2r", "tma8x3r", "tmag13x2", "tmag9x3", "tmag6x4"])
+@pytest.mark.parametrize("variant", ["direct", "staged", "wide", "widenp", "widepf", "widepf3", "bulk", "bulk6x2", "tma", "tma12x4", "tma24x2", "tma12x2r", "tma13x2r", "tma8x3r", "tmag13x2", "tmag9x3", "tmag6x4"])
 def test_hash_kernel_variants(oracle, gpu, variant, monkeypatch):
     """Both hash kernels (direct global loads / cp.async-staged) must produce identical bytes, including
     ragged stacks, odd frame offsets (8-byte staging path) and stacks deeper than one staging slot."""
