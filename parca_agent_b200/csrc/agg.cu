@@ -1837,7 +1837,7 @@ static int early_copy_issue(pa_agg* a) {
     append_tail_v2(a, nullptr, a->N, kind_keys, tail);
   }
   pa_agg::Early& e = a->early;
-  for (auto& bd : StreamPlan::tail_distances(tail)) {
+  for (auto& bd : StreamPlan::tail_distances(tail.data(), tail.size())) {
     if (bd.first.kind != BufRef::DEVICE) continue;
     if (bd.first.ptr == a->d_uuid.p) e.dist_uuid = bd.second;
     if (bd.first.ptr == a->d_value.p) e.dist_value = bd.second;

@@ -186,9 +186,9 @@ class StreamPlan {
   }
   // `tail` = the LAST columns of a record. Returns, per buffer of those columns in IPC order, its source and the distance from
   // its first byte to the END of the stream (nothing but the 8-byte end-of-stream marker follows the record batch body).
-  static std::vector<std::pair<BufRef, uint64_t>> tail_distances(const std::vector<Node>& tail) {
+  static std::vector<std::pair<BufRef, uint64_t>> tail_distances(const Node* tail, size_t n) {
     Body body;
-    for (auto& c : tail) walk(c, body);
+    for (size_t c = 0; c < n; c++) walk(tail[c], body);
     std::vector<std::pair<BufRef, uint64_t>> out;
     for (size_t i = 0; i < body.srcs.size(); i++) out.emplace_back(body.srcs[i], body.size - (uint64_t)body.buffers[2 * i] + 8);
     return out;

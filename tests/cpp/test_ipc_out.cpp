@@ -85,6 +85,19 @@ int main(int argc, char** argv) {
   std::vector<uint8_t> got(plan.total, 0xCD);  // poison: every byte must be written (padding included)
   for (auto& p : plan.placements) if (p.src.kind == BufRef::DEVICE) { fprintf(stderr, "unexpected device buffer\n"); return 2; }
   plan.write_host_parts(got.data());
+  // StreamPlan::tail_distances (what the early copy-out of a flush relies on): for every suffix of the column list, the
+  // end-relative position it predicts for each buffer must be where the full plan put that buffer
+  size_t checked = 0;
+  for (size_t first = 0; first < cols.size(); first++) {
+    for (auto& bd : pa::StreamPlan::tail_distances(&cols[first], cols.size() - first)) {
+      if (!bd.first.len) continue;
+      bool found = false;
+      for (auto& p : plan.placements) if (p.src.ptr == bd.first.ptr && p.src.len == bd.first.len && plan.total - p.at == bd.second) found = true;
+      if (!found) { fprintf(stderr, "tail_distances: a buffer of the columns from %zu on is not where the plan has it\n", first); return 3; }
+      checked++;
+    }
+  }
+  if (checked < cols.size()) { fprintf(stderr, "tail_distances: nothing was checked\n"); return 3; }
 
   // ---- oracle: the same record with the checker's model --------------------------------------------------------------
   using namespace orc;
